@@ -1,0 +1,213 @@
+/*
+ * slide_pr.h -- C-ABI of the B200-native SlideSLAM place-recognition (SlideMatch) search.
+ *
+ * This is the drop-in boundary for the hot path of lunarlab-gatech/SLIDE_SLAM's
+ * backend/sloam place recognition.  The reference has no FFI layer: the boundary is the C++
+ * class PlaceRecognition (backend/sloam/include/core/place_recognition.h:31-237).  Every entry
+ * point below names the member function it replaces; include/slide_pr/place_recognition.hpp
+ * is the header-only C++ adapter with the reference's own signatures.
+ *
+ * Conventions
+ *   - landmark rows are the reference's Eigen::Vector7d record [label,x,y,z,d1,d2,d3]
+ *     (place_recognition.h:51-57), contiguous doubles, stride 7, so
+ *     reinterpret_cast<const double*>(vec.data()) of a std::vector<Eigen::Vector7d> works.
+ *   - matrices are row-major.
+ *   - all functions return SLIDE_PR_OK (0) or a negative error code; "closure not found" is a
+ *     positive status, never an error (the reference cannot tell them apart: PR.cpp:515-519).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     SLIDE_PR_ERR_CUDA and slide_pr_last_error() says why.
+ *   - a handle is bound to one CUDA device and is not re-entrant (one call at a time per
+ *     handle, exactly like one PlaceRecognition instance: PR.cpp:786-787 mutates members).
+ */
+#ifndef SLIDE_PR_H
+#define SLIDE_PR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLIDE_PR_ABI_VERSION 1
+
+enum {
+  SLIDE_PR_OK = 0,
+  SLIDE_PR_NOT_FOUND = 1,          /* fewer than min_num_inliers (PR.cpp:849) or size gate (PR.cpp:508) */
+  SLIDE_PR_SANITY_RETURN = 2,      /* MatchMaps' early return, outputs untouched (PR.cpp:169-175) */
+  SLIDE_PR_ERR_INVALID = -1,       /* bad argument */
+  SLIDE_PR_ERR_CUDA = -2,          /* CUDA runtime error / no device */
+  SLIDE_PR_ERR_UNSUPPORTED = -3,   /* problem too large for the index structures */
+  SLIDE_PR_ERR_NONFINITE = -4,     /* NaN/Inf coordinate in a map */
+  SLIDE_PR_ERR_INTERNAL = -5       /* self-check failed (hash count != brute-force count) */
+};
+
+/* rosparams sloam/place_recognition/ * as stored in the members (PR.cpp:24-75); angles in radians,
+ * computed by the caller as deg * M_PI / 180. like PR.cpp:35,41,60 (slide_pr_deg2rad does it). */
+typedef struct slide_pr_params {
+  double compute_budget_sec;          /* <= 0: unlimited.  > 0: checked between rings (PR.cpp:181-191) */
+  double dilation_factor;             /* 1.2 */
+  double match_xy_step_size;          /* 0.5 */
+  double match_yaw_half_range;        /* pi */
+  double match_yaw_angle_step_size;   /* 2 deg */
+  double match_threshold;             /* 0.5 */
+  double match_threshold_dimension;   /* 1.0 */
+  double match_x_half_range_intra;    /* 5 */
+  double match_y_half_range_intra;    /* 5 */
+  double match_yaw_half_range_intra;  /* 10 deg */
+  int32_t disable_yaw_search;         /* 0 */
+  int32_t ignore_dimension;           /* 0 */
+  int32_t min_num_inliers;            /* 5 */
+  int32_t use_lsq;                    /* 1 (rosparam use_nonlinear_least_squares) */
+  int32_t min_num_map_objects_to_start; /* 1 */
+  int32_t inter_loop_closure;         /* 1 (public member PR.h:43) */
+  int32_t device;                     /* CUDA device ordinal; -1 = current device */
+  int32_t reserved;
+} slide_pr_params;
+
+typedef struct slide_pr_handle slide_pr_handle;
+
+/* Result of one MatchMaps-level search (PR.h:70-74 outputs + bookkeeping). */
+typedef struct slide_pr_match_result {
+  int32_t status;              /* SLIDE_PR_OK or SLIDE_PR_SANITY_RETURN */
+  int32_t best_num_inliers;    /* -10000 when no hypothesis was scored (PR.cpp:125) */
+  double  R_t[9];              /* [[c,-s,x],[s,c,y],[0,0,1]] of the winner (PR.cpp:244-251) */
+  int32_t n_matched;           /* entries written to ref_idx_out / qry_idx_out */
+  int32_t n_rings;
+  int32_t n_yaw;
+  int32_t rings_scored;        /* < n_rings only when compute_budget_sec cut the search */
+  int64_t hypotheses_scored;
+  int64_t best_hyp_index;      /* canonical index (ring -> x -> y -> yaw enumeration order); -1 if none */
+  int64_t n_translations;      /* lattice translations (all rings) */
+  float   kernel_ms;           /* device time of the search kernels (CUDA events on the call's stream) */
+  float   prepare_ms;          /* host time spent building the index structures + H2D enqueue */
+  int64_t gpu_launches;        /* kernels launched by this call */
+  int64_t filter_hits;         /* bitmap hits verified in fp64 (0 unless stats were enabled) */
+} slide_pr_match_result;
+
+/* Options for the sharded / sliced search (multi-GPU and tests). */
+typedef struct slide_pr_search_opts {
+  int64_t trans_begin;   /* score translations with canonical ordinal in [trans_begin, trans_end) */
+  int64_t trans_end;     /* < 0: to the end */
+  int32_t shard_index;   /* this rank's shard of the work (round-robin over chunk groups) */
+  int32_t shard_count;   /* <= 1: no sharding */
+  int32_t *counts_out;   /* optional HOST buffer: inlier count of every hypothesis of the slice,
+                            counts_out[(t - trans_begin) * n_yaw + iyaw]; needs trans_end >= 0 */
+  int64_t counts_cap;    /* capacity of counts_out in entries */
+  void   *stream;        /* cudaStream_t to run on; NULL = the handle's own stream */
+  int32_t collect_stats; /* 1: count filter hits (slower) */
+  int32_t reserved;
+} slide_pr_search_opts;
+
+typedef struct slide_pr_tf_result {
+  int32_t found;               /* return value of findTransformation */
+  int32_t best_num_inliers;
+  int32_t n_matched;
+  int32_t reserved;
+  double  R_t[9];              /* lattice winner in the (centroid-shifted) search frames */
+  double  xyz_yaw[4];          /* PR.cpp:902 / :941 */
+  double  transform[16];       /* transform_out */
+  double  centroid_ref[2], centroid_qry[2];
+  double  half_x, half_y, yaw_half;
+  slide_pr_match_result match; /* the underlying MatchMaps call */
+} slide_pr_tf_result;
+
+/* ---- lifetime --------------------------------------------------------------------------- */
+int  slide_pr_abi_version(void);
+double slide_pr_deg2rad(double deg);                       /* deg * M_PI / 180.  (PR.cpp:35) */
+void slide_pr_default_params(slide_pr_params *p);          /* PlaceRecognition::ParamInit defaults, PR.cpp:24-75; budget disabled */
+int  slide_pr_create(const slide_pr_params *p, slide_pr_handle **out);   /* PlaceRecognition ctor PR.cpp:15-21 */
+void slide_pr_destroy(slide_pr_handle *h);
+int  slide_pr_set_params(slide_pr_handle *h, const slide_pr_params *p);  /* public members use_lsq / inter_loop_closure, PR.h:34-43 */
+const char *slide_pr_last_error(const slide_pr_handle *h); /* h may be NULL: error of the last failed create */
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+/* PlaceRecognition::MatchMaps (PR.h:70-74, PR.cpp:98-387).  half_x/half_y are the members
+ * match_{x,y}_half_range_ that findTransformation sets before the call (PR.cpp:786-787, 808-809);
+ * the yaw range comes from the params (inter or intra).  ref_idx_out/qry_idx_out: caller arrays
+ * of capacity n_qry receiving, in query order, the indices of the matched reference / query
+ * objects (the reference returns the rows themselves: PR.cpp:344-350). */
+int slide_pr_match_maps(slide_pr_handle *h, const double *ref7, int32_t n_ref,
+                        const double *qry7, int32_t n_qry, double half_x, double half_y,
+                        int32_t *ref_idx_out, int32_t *qry_idx_out, slide_pr_match_result *out);
+
+/* The same search split in its stages, for sharded multi-GPU use and for timing:
+ *   prepare : host index build + H2D of both maps           (inputs become HBM-resident)
+ *   search  : the scoring kernels over this shard/slice     -> local best (count, canonical index)
+ *   extract : correspondences + R_t of ONE hypothesis (the global winner after the all-gather) */
+int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7,
+                     int32_t n_qry, double half_x, double half_y);
+int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_pr_match_result *out);
+/* size of the prepared search lattice (PR.cpp:136-241): translations over all rings, yaw candidates, rings */
+int slide_pr_lattice_info(const slide_pr_handle *h, int64_t *n_translations, int32_t *n_yaw, int32_t *n_rings);
+int slide_pr_extract(slide_pr_handle *h, int64_t hyp_index, int32_t *ref_idx_out,
+                     int32_t *qry_idx_out, slide_pr_match_result *inout);
+
+/* PlaceRecognition::findTransformation (PR.h:150-153, PR.cpp:736-945): centroid shift, search
+ * range, MatchMaps, inlier gate, LSQ refinement or centroid un-shift.  Returns SLIDE_PR_OK when
+ * found, SLIDE_PR_NOT_FOUND otherwise. */
+int slide_pr_find_transformation(slide_pr_handle *h, const double *ref7, int32_t n_ref,
+                                 const double *qry7, int32_t n_qry, int32_t *ref_idx_out,
+                                 int32_t *qry_idx_out, slide_pr_tf_result *out);
+
+/* PlaceRecognition::findInterLoopClosure (PR.h:103-106, PR.cpp:498-538): size gate +
+ * findTransformation + yaw/xyz 4x4.  tf16: row-major tfFromQueryToRef. */
+int slide_pr_find_inter_loop_closure(slide_pr_handle *h, const double *ref7, int32_t n_ref,
+                                     const double *qry7, int32_t n_qry, double *tf16,
+                                     slide_pr_tf_result *out /* may be NULL */);
+
+/* PlaceRecognition::findIntraLoopClosure (PR.h:88-91, PR.cpp:389-496).  Poses are row-major 4x4
+ * (Sophus SE3::matrix()).  measurements are in the query's local frame. */
+int slide_pr_find_intra_loop_closure(slide_pr_handle *h, const double *measurements7, int32_t n_meas,
+                                     const double *submap7, int32_t n_sub, const double *query_pose16,
+                                     const double *candidate_pose16, double *tf16,
+                                     slide_pr_tf_result *out /* may be NULL */);
+
+/* PlaceRecognition::solveLSQ (PR.h:127-130, PR.cpp:632-695): Kabsch on k matched pairs.
+ * tgt3 = map objects, src3 = detection objects (k x 3). */
+int slide_pr_solve_lsq(const double *tgt3, const double *src3, int32_t k, double *xyz_yaw4,
+                       double *transform16);
+
+/* PlaceRecognition::getxyzYawfromTF (PR.h:138, PR.cpp:697-711). */
+void slide_pr_get_xyz_yaw_from_tf(const double *tf16, double *xyz_yaw4);
+
+/* ---- batches (BASELINE configs 4 and 5) --------------------------------------------------- */
+/* n_pairs independent findTransformation calls (all-pairs multi-robot matching / streaming
+ * submap queries).  maps: array of n_maps pointers to n x 7 rows; pair p matches reference
+ * maps[ref_of[p]] against query maps[qry_of[p]].  Index structures of a reference map are
+ * built once and reused by consecutive pairs that share it. */
+int slide_pr_find_transformation_batch(slide_pr_handle *h, const double *const *maps,
+                                       const int32_t *map_sizes, int32_t n_maps,
+                                       const int32_t *ref_of, const int32_t *qry_of, int32_t n_pairs,
+                                       slide_pr_tf_result *out /* n_pairs */);
+
+/* ---- multi-GPU merge ---------------------------------------------------------------------- */
+/* Packs a local result into the 16-byte record exchanged by the all-gather, and merges
+ * n records deterministically: max inliers, ties to the smallest canonical index (the
+ * reference's strict '>' first-wins rule, PR.cpp:361).  Returns the index of the winner. */
+typedef struct slide_pr_topk_record { int64_t hyp_index; int32_t inliers; int32_t rank; } slide_pr_topk_record;
+void slide_pr_pack_record(const slide_pr_match_result *r, int32_t rank, slide_pr_topk_record *rec);
+int  slide_pr_merge_records(const slide_pr_topk_record *recs, int32_t n);
+
+/* ---- SlideGraph descriptor half (semantic_clipper.cpp) ------------------------------------- */
+/* compute_triangle_diff / match_triangles (SC.cpp:49-118) on the GPU: descriptors of all
+ * triangles are built once, binned by their first component, and matched; output order is the
+ * reference's (model-major, data-minor).  tris: t x 6 [x0,y0,x1,y1,x2,y2].  model_idx_out /
+ * data_idx_out / perm_out (3 ints per match per side: the sorted vertex order) have capacity
+ * cap matches; returns the total match count in *n_matches (may exceed cap). */
+int slide_pr_match_triangles(slide_pr_handle *h, const double *tris_model6, int32_t t_model,
+                             const double *tris_data6, int32_t t_data, double threshold,
+                             int32_t *model_idx_out, int32_t *data_idx_out,
+                             int32_t *perm_model_out, int32_t *perm_data_out,
+                             int64_t cap, int64_t *n_matches);
+
+/* Scores an explicit list of rigid-transform hypotheses (c, s, x, y) -- e.g. the 2-D Kabsch
+ * fits of matched triangles (SC.cpp:122-138) -- with the MatchMaps inlier predicate
+ * (PR.cpp:272-357) against the maps given to slide_pr_prepare.  hyps: n x 4 doubles.
+ * counts_out (optional, n ints).  The winner (max count, lowest index) goes to *out. */
+int slide_pr_score_hypotheses(slide_pr_handle *h, const double *hyps4, int64_t n,
+                              int32_t *counts_out, slide_pr_match_result *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLIDE_PR_H */

@@ -1,0 +1,710 @@
+// spr_api.cu -- C-ABI of the B200 place-recognition search (include/slide_pr.h).
+//
+// Host control flow mirrors PlaceRecognition::findInterLoopClosure -> findTransformation ->
+// MatchMaps -> solveLSQ (place_recognition.cpp:498-538, 736-945, 98-387, 632-695); the scoring
+// itself only ever runs on the GPU (spr_kernels.cu).  There is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/slide_pr.h"
+#include "spr_host.h"
+#include "spr_kernels.h"
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+std::string g_create_error;
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct slide_pr_handle {
+  slide_pr_params p{};
+  int device = 0;
+  int sm_count = 148;
+  int variant = SPR_VARIANT_QUEUED;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  // prepared problem (host side)
+  bool prepared = false;
+  double half_x = 0, half_y = 0, yaw_half = 0;
+  int n_ref = 0, n_qry = 0;
+  int64_t lat_tb = 0, lat_te = -1;
+  double prepare_ms = 0;
+  spr::Lattice L;
+  spr::RefIndex R;
+  spr::QuerySet Q;
+  std::vector<int32_t> qlabel;
+  // device side
+  DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_refxy, d_refdims, d_bitmap, d_prefix,
+      d_cellinfo, d_cand, d_qrot, d_qrotq, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
+  SprView V{};
+  std::vector<int32_t> h_match;
+};
+
+#define SPR_CUDA(h, call)                                                                   \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                       \
+      return SLIDE_PR_ERR_CUDA;                                                             \
+    }                                                                                       \
+  } while (0)
+
+template <typename T>
+static int upload(slide_pr_handle *h, DevBuf &b, const std::vector<T> &v, cudaStream_t st) {
+  SPR_CUDA(h, b.ensure(std::max<size_t>(v.size(), 1) * sizeof(T)));
+  if (!v.empty()) SPR_CUDA(h, cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  return SLIDE_PR_OK;
+}
+
+static int upload_raw(slide_pr_handle *h, DevBuf &b, const void *src, size_t bytes, cudaStream_t st) {
+  SPR_CUDA(h, b.ensure(std::max<size_t>(bytes, 8)));
+  if (bytes) SPR_CUDA(h, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+  return SLIDE_PR_OK;
+}
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int slide_pr_abi_version(void) { return SLIDE_PR_ABI_VERSION; }
+
+double slide_pr_deg2rad(double deg) { return deg * M_PI / 180.; }
+
+void slide_pr_default_params(slide_pr_params *p) {  // PR.cpp:24-75
+  std::memset(p, 0, sizeof(*p));
+  p->compute_budget_sec = -1.0;
+  p->dilation_factor = 1.2;
+  p->match_xy_step_size = 0.5;
+  p->match_yaw_half_range = slide_pr_deg2rad(180.);
+  p->match_yaw_angle_step_size = slide_pr_deg2rad(2.0);
+  p->match_threshold = 0.5;
+  p->match_threshold_dimension = 1.0;
+  p->match_x_half_range_intra = 5.0;
+  p->match_y_half_range_intra = 5.0;
+  p->match_yaw_half_range_intra = slide_pr_deg2rad(10.);
+  p->disable_yaw_search = 0;
+  p->ignore_dimension = 0;
+  p->min_num_inliers = 5;
+  p->use_lsq = 1;
+  p->min_num_map_objects_to_start = 1;
+  p->inter_loop_closure = 1;
+  p->device = -1;
+}
+
+const char *slide_pr_last_error(const slide_pr_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int slide_pr_create(const slide_pr_params *p, slide_pr_handle **out) {
+  if (!p || !out) { g_create_error = "null argument"; return SLIDE_PR_ERR_INVALID; }
+  *out = nullptr;
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0) {
+    g_create_error = std::string("no CUDA device (the place-recognition search has no CPU fallback): ") +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return SLIDE_PR_ERR_CUDA;
+  }
+  slide_pr_handle *h = new slide_pr_handle();
+  h->p = *p;
+  int dev = p->device;
+  if (dev < 0) cudaGetDevice(&dev);
+  if (dev >= n_dev) { g_create_error = "device ordinal out of range"; delete h; return SLIDE_PR_ERR_INVALID; }
+  h->device = dev;
+  if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
+    g_create_error = std::string("CUDA init: ") + cudaGetErrorString(e);
+    delete h;
+    return SLIDE_PR_ERR_CUDA;
+  }
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (const char *v = std::getenv("SLIDE_PR_VARIANT")) h->variant = std::atoi(v) == 0 ? SPR_VARIANT_DIRECT : SPR_VARIANT_QUEUED;
+  *out = h;
+  return SLIDE_PR_OK;
+}
+
+void slide_pr_destroy(slide_pr_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (DevBuf *b : {&h->d_lat, &h->d_chunks, &h->d_cs, &h->d_qxy, &h->d_qdims, &h->d_labelseg, &h->d_qlabel,
+                    &h->d_refxy, &h->d_refdims, &h->d_bitmap, &h->d_prefix, &h->d_cellinfo, &h->d_cand, &h->d_qrot,
+                    &h->d_qrotq, &h->d_ref7, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps, &h->d_tri, &h->d_tri_out})
+    b->release();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int slide_pr_set_params(slide_pr_handle *h, const slide_pr_params *p) {
+  if (!h || !p) return SLIDE_PR_ERR_INVALID;
+  const int dev = h->p.device;
+  h->p = *p;
+  h->p.device = dev;
+  h->prepared = false;
+  return SLIDE_PR_OK;
+}
+
+static int upload_lattice(slide_pr_handle *h, cudaStream_t st) {
+  int rc;
+  if ((rc = upload(h, h->d_lat, h->L.lat, st))) return rc;
+  if ((rc = upload(h, h->d_chunks, h->L.chunks, st))) return rc;
+  if ((rc = upload(h, h->d_cs, h->L.cs, st))) return rc;
+  h->V.lat = h->d_lat.as<double>();
+  h->V.chunks = h->d_chunks.as<SprChunk>();
+  h->V.n_chunks = (uint32_t)h->L.chunks.size();
+  h->V.n_yaw = (int32_t)h->L.yaw.size();
+  h->V.cs = h->d_cs.as<double>();
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7, int32_t n_qry,
+                     double half_x, double half_y) {
+  if (!h) return SLIDE_PR_ERR_INVALID;
+  h->prepared = false;
+  if (n_ref < 0 || n_qry < 0 || (n_ref > 0 && !ref7) || (n_qry > 0 && !qry7)) { h->err = "bad map arguments"; return SLIDE_PR_ERR_INVALID; }
+  if (n_qry >= (1 << 22)) { h->err = "more than 2^22 query landmarks"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  const double t0 = now_ms();
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  h->half_x = half_x; h->half_y = half_y;
+  h->yaw_half = h->p.inter_loop_closure ? h->p.match_yaw_half_range : h->p.match_yaw_half_range_intra;
+  h->n_ref = n_ref; h->n_qry = n_qry;
+  h->lat_tb = 0; h->lat_te = -1;
+  int rc = spr::build_lattice(h->p, half_x, half_y, h->yaw_half, 0, -1, h->L, h->err);
+  if (rc != SLIDE_PR_OK) return rc;
+  double qrad = 0;
+  for (int j = 0; j < n_qry; j++) {
+    const double r = std::hypot(qry7[7 * (size_t)j + 1], qry7[7 * (size_t)j + 2]);
+    if (!std::isfinite(r)) { h->err = "non-finite query coordinate"; return SLIDE_PR_ERR_NONFINITE; }
+    qrad = std::max(qrad, r);
+  }
+  const double reach = qrad + std::max(std::fabs(half_x), std::fabs(half_y)) + h->p.match_xy_step_size;
+  if ((rc = spr::build_ref_index(h->p, ref7, n_ref, reach, h->R, h->err)) != SLIDE_PR_OK) return rc;
+  if ((rc = spr::build_query_set(h->R, qry7, n_qry, h->Q, h->err)) != SLIDE_PR_OK) return rc;
+  h->qlabel.assign(std::max(h->Q.nq, 1), 0);
+  for (int l = 0; l + 1 < (int)h->Q.label_seg.size(); l++)
+    for (int s = h->Q.label_seg[l]; s < h->Q.label_seg[l + 1]; s++) h->qlabel[s] = l;
+
+  if ((rc = upload_lattice(h, st))) return rc;
+  if ((rc = upload(h, h->d_qxy, h->Q.qxy, st))) return rc;
+  if ((rc = upload(h, h->d_qdims, h->Q.qdims, st))) return rc;
+  if ((rc = upload(h, h->d_labelseg, h->Q.label_seg, st))) return rc;
+  if ((rc = upload(h, h->d_qlabel, h->qlabel, st))) return rc;
+  if ((rc = upload(h, h->d_refxy, h->R.ref_xy, st))) return rc;
+  if ((rc = upload(h, h->d_refdims, h->R.ref_dims, st))) return rc;
+  if ((rc = upload(h, h->d_bitmap, h->R.bitmap, st))) return rc;
+  if ((rc = upload(h, h->d_prefix, h->R.prefix, st))) return rc;
+  if ((rc = upload(h, h->d_cellinfo, h->R.cellinfo, st))) return rc;
+  if ((rc = upload(h, h->d_cand, h->R.cand, st))) return rc;
+  if ((rc = upload_raw(h, h->d_ref7, ref7, (size_t)n_ref * 7 * sizeof(double), st))) return rc;
+  if ((rc = upload_raw(h, h->d_qry7, qry7, (size_t)n_qry * 7 * sizeof(double), st))) return rc;
+  const size_t nrot = (size_t)std::max<size_t>((size_t)h->L.yaw.size() * (size_t)h->Q.nq, 1);
+  SPR_CUDA(h, h->d_qrot.ensure(nrot * 2 * sizeof(double)));
+  SPR_CUDA(h, h->d_qrotq.ensure(nrot * 2 * sizeof(int32_t)));
+  SPR_CUDA(h, h->d_best.ensure(sizeof(unsigned long long)));
+  SPR_CUDA(h, h->d_stats.ensure(2 * sizeof(unsigned long long)));
+  SPR_CUDA(h, h->d_match.ensure(std::max<size_t>(n_qry, 1) * sizeof(int32_t)));
+
+  SprView &V = h->V;
+  V.nq = h->Q.nq;
+  V.qrotq = h->d_qrotq.as<int32_t>();
+  V.qrot = h->d_qrot.as<double>();
+  V.qxy = h->d_qxy.as<double>();
+  V.qdims = h->d_qdims.as<double>();
+  V.label_seg = h->d_labelseg.as<int32_t>();
+  V.qlabel = h->d_qlabel.as<int32_t>();
+  V.n_labels = (int32_t)h->R.labels.size();
+  V.n_ref = n_ref;
+  V.ref_xy = h->d_refxy.as<double>();
+  V.ref_dims = h->d_refdims.as<double>();
+  V.bitmap = h->d_bitmap.as<uint32_t>();
+  V.prefix = h->d_prefix.as<uint32_t>();
+  V.cellinfo = h->d_cellinfo.as<uint32_t>();
+  V.cand = h->d_cand.as<uint32_t>();
+  V.grid = h->R.grid;
+  V.Tstar = h->R.Tstar;
+  V.Sstar = h->R.Sstar;
+  V.thr_dim = h->p.match_threshold_dimension;
+  V.ignore_dim = h->p.ignore_dimension;
+  // the uploads read pageable host vectors that stay alive in the handle; make them complete
+  // before the caller may free ref7 / qry7
+  SPR_CUDA(h, cudaStreamSynchronize(st));
+  h->prepared = true;
+  h->prepare_ms = now_ms() - t0;
+  return SLIDE_PR_OK;
+}
+
+static void fill_result_header(slide_pr_handle *h, slide_pr_match_result *out) {
+  std::memset(out, 0, sizeof(*out));
+  out->status = h->L.status;
+  out->best_num_inliers = -10000;  // PR.cpp:125
+  out->R_t[0] = out->R_t[4] = out->R_t[8] = 1.0;  // PR.cpp:127
+  out->best_hyp_index = -1;
+  out->n_rings = h->L.rings;
+  out->n_yaw = (int32_t)h->L.yaw.size();
+  out->n_translations = (int64_t)h->L.n_translations;
+  out->prepare_ms = (float)h->prepare_ms;
+}
+
+int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_pr_match_result *out) {
+  if (!h || !out) return SLIDE_PR_ERR_INVALID;
+  if (!h->prepared) { h->err = "slide_pr_search before slide_pr_prepare"; return SLIDE_PR_ERR_INVALID; }
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  slide_pr_search_opts o{};
+  o.trans_end = -1;
+  if (opts) o = *opts;
+  cudaStream_t st = o.stream ? (cudaStream_t)o.stream : h->stream;
+  fill_result_header(h, out);
+  if (h->L.status == SLIDE_PR_SANITY_RETURN) return SLIDE_PR_OK;
+  int rc;
+  const int64_t tb = o.trans_begin < 0 ? 0 : o.trans_begin, te = o.trans_end;
+  if (tb != h->lat_tb || te != h->lat_te) {  // re-chunk the lattice for the requested slice
+    if ((rc = spr::build_lattice(h->p, h->half_x, h->half_y, h->yaw_half, tb, te, h->L, h->err)) != SLIDE_PR_OK) return rc;
+    h->lat_tb = tb; h->lat_te = te;
+    if ((rc = upload_lattice(h, st))) return rc;
+  }
+  const int n_yaw = (int)h->L.yaw.size();
+  int64_t n_counts = 0;
+  if (o.counts_out) {
+    if (te < 0) { h->err = "counts_out needs trans_end >= 0"; return SLIDE_PR_ERR_INVALID; }
+    const int64_t te_c = std::min<int64_t>(te, (int64_t)h->L.n_translations);
+    n_counts = std::max<int64_t>(te_c - tb, 0) * n_yaw;
+    if (n_counts > o.counts_cap) { h->err = "counts_cap too small"; return SLIDE_PR_ERR_INVALID; }
+    SPR_CUDA(h, h->d_counts.ensure(std::max<size_t>((size_t)n_counts, 1) * sizeof(int32_t)));
+    SPR_CUDA(h, cudaMemsetAsync(h->d_counts.p, 0xff, std::max<size_t>((size_t)n_counts, 1) * sizeof(int32_t), st));
+  }
+  SPR_CUDA(h, cudaMemsetAsync(h->d_best.p, 0, sizeof(unsigned long long), st));
+  if (o.collect_stats) SPR_CUDA(h, cudaMemsetAsync(h->d_stats.p, 0, 2 * sizeof(unsigned long long), st));
+
+  SprLaunch K{};
+  K.shard_index = o.shard_index;
+  K.shard_count = o.shard_count;
+  K.best_key = h->d_best.as<unsigned long long>();
+  K.counts_out = o.counts_out ? h->d_counts.as<int32_t>() : nullptr;
+  K.counts_cap = n_counts;
+  K.ord_begin = (unsigned long long)tb;
+  K.stats = o.collect_stats ? h->d_stats.as<unsigned long long>() : nullptr;
+
+  int launches = 0;
+  SPR_CUDA(h, cudaEventRecord(h->ev0, st));
+  if (h->V.nq > 0 && n_yaw > 0) {
+    SPR_CUDA(h, spr_launch_rotate(h->V, h->d_qrotq.as<int32_t>(), h->d_qrot.as<double>(), st));
+    launches++;
+  }
+  int rings_scored = 0;
+  if (h->p.compute_budget_sec > 0) {
+    // anytime behaviour of PR.cpp:181-191: whole seconds, checked before every ring
+    const auto start = std::chrono::high_resolution_clock::now();
+    for (size_t k = 0; k < h->L.ring.size(); k++) {
+      const double duration = (double)std::chrono::duration_cast<std::chrono::seconds>(
+                                  std::chrono::high_resolution_clock::now() - start).count();
+      if (duration > h->p.compute_budget_sec) break;
+      K.chunk_begin = h->L.ring[k].chunk_begin;
+      K.chunk_end = h->L.ring[k].chunk_end;
+      SPR_CUDA(h, spr_launch_score_lattice(h->V, K, h->variant, h->sm_count, st, &launches));
+      SPR_CUDA(h, cudaStreamSynchronize(st));
+      rings_scored++;
+    }
+  } else {
+    K.chunk_begin = 0;
+    K.chunk_end = (uint32_t)h->L.chunks.size();
+    SPR_CUDA(h, spr_launch_score_lattice(h->V, K, h->variant, h->sm_count, st, &launches));
+    rings_scored = h->L.rings;
+  }
+  SPR_CUDA(h, cudaEventRecord(h->ev1, st));
+  unsigned long long key = 0, stats[2] = {0, 0};
+  SPR_CUDA(h, cudaMemcpyAsync(&key, h->d_best.p, sizeof(key), cudaMemcpyDeviceToHost, st));
+  if (o.collect_stats) SPR_CUDA(h, cudaMemcpyAsync(stats, h->d_stats.p, sizeof(stats), cudaMemcpyDeviceToHost, st));
+  if (o.counts_out && n_counts > 0)
+    SPR_CUDA(h, cudaMemcpyAsync(o.counts_out, h->d_counts.p, (size_t)n_counts * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  SPR_CUDA(h, cudaStreamSynchronize(st));
+  float ms = 0;
+  SPR_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  out->kernel_ms = ms;
+  out->gpu_launches = launches;
+  out->rings_scored = rings_scored;
+  out->filter_hits = (int64_t)stats[0];
+  // hypotheses scored by this shard = valid bits of its chunk groups x yaw candidates
+  {
+    const int sc = o.shard_count > 1 ? o.shard_count : 1, si = o.shard_count > 1 ? o.shard_index : 0;
+    uint64_t bits = 0;
+    const uint32_t cend = h->p.compute_budget_sec > 0 && rings_scored > 0 ? h->L.ring[rings_scored - 1].chunk_end
+                          : (h->p.compute_budget_sec > 0 ? 0u : (uint32_t)h->L.chunks.size());
+    if (h->p.compute_budget_sec > 0) {
+      for (int k = 0; k < rings_scored; k++) {
+        const uint32_t cb = h->L.ring[k].chunk_begin, ce = h->L.ring[k].chunk_end;
+        for (uint32_t c = cb; c < ce; c++)
+          if ((int)(((c - cb) / 256) % sc) == si) bits += (uint64_t)__builtin_popcount(h->L.chunks[c].valid);
+      }
+    } else {
+      for (uint32_t c = 0; c < cend; c++)
+        if ((int)((c / 256) % sc) == si) bits += (uint64_t)__builtin_popcount(h->L.chunks[c].valid);
+    }
+    out->hypotheses_scored = (int64_t)(bits * (uint64_t)n_yaw);
+  }
+  if (key != 0ull) {
+    out->best_num_inliers = spr_key_count(key);
+    out->best_hyp_index = spr_key_index(key);
+  }
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_lattice_info(const slide_pr_handle *h, int64_t *n_translations, int32_t *n_yaw, int32_t *n_rings) {
+  if (!h || !h->prepared) return SLIDE_PR_ERR_INVALID;
+  if (n_translations) *n_translations = (int64_t)h->L.n_translations;
+  if (n_yaw) *n_yaw = (int32_t)h->L.yaw.size();
+  if (n_rings) *n_rings = h->L.rings;
+  return h->L.status;
+}
+
+int slide_pr_extract(slide_pr_handle *h, int64_t hyp_index, int32_t *ref_idx_out, int32_t *qry_idx_out,
+                     slide_pr_match_result *io) {
+  if (!h || !io) return SLIDE_PR_ERR_INVALID;
+  if (!h->prepared) { h->err = "slide_pr_extract before slide_pr_prepare"; return SLIDE_PR_ERR_INVALID; }
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  const int n_yaw = (int)h->L.yaw.size();
+  io->n_matched = 0;
+  if (hyp_index < 0 || n_yaw <= 0) return SLIDE_PR_OK;
+  // the lattice may have been re-chunked for a slice: ordinals are global, translation_of uses rings only
+  double tx, ty;
+  int ring;
+  if (!spr::translation_of(h->L, (uint64_t)(hyp_index / n_yaw), &tx, &ty, &ring)) { h->err = "hypothesis index out of range"; return SLIDE_PR_ERR_INVALID; }
+  const int a = (int)(hyp_index % n_yaw);
+  const double c = h->L.cs[2 * a], s = h->L.cs[2 * a + 1];
+  io->R_t[0] = c; io->R_t[1] = -s; io->R_t[2] = tx;  // PR.cpp:246-251
+  io->R_t[3] = s; io->R_t[4] = c;  io->R_t[5] = ty;
+  io->R_t[6] = 0; io->R_t[7] = 0;  io->R_t[8] = 1;
+  cudaStream_t st = h->stream;
+  SPR_CUDA(h, spr_launch_extract(h->d_ref7.as<double>(), h->n_ref, h->d_qry7.as<double>(), h->n_qry, c, s, tx, ty,
+                                 h->R.Tstar, h->R.Sstar, h->p.match_threshold_dimension, h->p.ignore_dimension,
+                                 h->d_match.as<int32_t>(), st));
+  io->gpu_launches += 1;
+  h->h_match.resize(std::max(h->n_qry, 1));
+  SPR_CUDA(h, cudaMemcpyAsync(h->h_match.data(), h->d_match.p, (size_t)h->n_qry * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  SPR_CUDA(h, cudaStreamSynchronize(st));
+  int k = 0;
+  for (int j = 0; j < h->n_qry; j++)
+    if (h->h_match[j] >= 0) {
+      if (ref_idx_out) ref_idx_out[k] = h->h_match[j];
+      if (qry_idx_out) qry_idx_out[k] = j;
+      k++;
+    }
+  io->n_matched = k;
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_match_maps(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7, int32_t n_qry,
+                        double half_x, double half_y, int32_t *ref_idx_out, int32_t *qry_idx_out,
+                        slide_pr_match_result *out) {
+  if (!h || !out) return SLIDE_PR_ERR_INVALID;
+  int rc = slide_pr_prepare(h, ref7, n_ref, qry7, n_qry, half_x, half_y);
+  if (rc != SLIDE_PR_OK) return rc;
+  if ((rc = slide_pr_search(h, nullptr, out)) != SLIDE_PR_OK) return rc;
+  if (out->status == SLIDE_PR_SANITY_RETURN || out->best_hyp_index < 0) return SLIDE_PR_OK;
+  if ((rc = slide_pr_extract(h, out->best_hyp_index, ref_idx_out, qry_idx_out, out)) != SLIDE_PR_OK) return rc;
+  if (out->n_matched != out->best_num_inliers) {  // brute-force recount of the winner must agree with the index path
+    char buf[160];
+    std::snprintf(buf, sizeof(buf), "self-check failed: indexed count %d != brute-force count %d for hypothesis %lld",
+                  out->best_num_inliers, out->n_matched, (long long)out->best_hyp_index);
+    h->err = buf;
+    return SLIDE_PR_ERR_INTERNAL;
+  }
+  return SLIDE_PR_OK;
+}
+
+void slide_pr_get_xyz_yaw_from_tf(const double *tf16, double *xyz_yaw4) { spr::xyz_yaw_from_tf(tf16, xyz_yaw4); }
+
+int slide_pr_solve_lsq(const double *tgt3, const double *src3, int32_t k, double *xyz_yaw4, double *transform16) {
+  if (!tgt3 || !src3 || !xyz_yaw4 || !transform16 || k < 0) return SLIDE_PR_ERR_INVALID;
+  spr::solve_lsq(tgt3, src3, k, xyz_yaw4, transform16);
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_find_transformation(slide_pr_handle *h, const double *ref7_in, int32_t n_ref, const double *qry7_in,
+                                 int32_t n_qry, int32_t *ref_idx_out, int32_t *qry_idx_out, slide_pr_tf_result *out) {
+  if (!h || !out) return SLIDE_PR_ERR_INVALID;
+  if (n_ref < 0 || n_qry < 0 || (n_ref > 0 && !ref7_in) || (n_qry > 0 && !qry7_in)) { h->err = "bad map arguments"; return SLIDE_PR_ERR_INVALID; }
+  std::memset(out, 0, sizeof(*out));
+  std::vector<double> ref(ref7_in, ref7_in + (size_t)n_ref * 7), qry(qry7_in, qry7_in + (size_t)n_qry * 7);
+  double cref[2] = {0, 0}, cqry[2] = {0, 0};
+  double half_x, half_y;
+  const slide_pr_params &p = h->p;
+  if (p.inter_loop_closure) {
+    for (int i = 0; i < n_ref; i++) { cref[0] += ref[7 * (size_t)i + 1]; cref[1] += ref[7 * (size_t)i + 2]; }  // PR.cpp:713-722
+    cref[0] /= (double)n_ref; cref[1] /= (double)n_ref;
+    for (int i = 0; i < n_qry; i++) { cqry[0] += qry[7 * (size_t)i + 1]; cqry[1] += qry[7 * (size_t)i + 2]; }
+    cqry[0] /= (double)n_qry; cqry[1] /= (double)n_qry;
+    double bxr = 0, byr = 0, bxq = 0, byq = 0;
+    for (int i = 0; i < n_ref; i++) {                                  // PR.cpp:755-759, 724-734
+      ref[7 * (size_t)i + 1] -= cref[0]; ref[7 * (size_t)i + 2] -= cref[1];
+      bxr = std::max(bxr, std::abs(ref[7 * (size_t)i + 1])); byr = std::max(byr, std::abs(ref[7 * (size_t)i + 2]));
+    }
+    for (int i = 0; i < n_qry; i++) {
+      qry[7 * (size_t)i + 1] -= cqry[0]; qry[7 * (size_t)i + 2] -= cqry[1];
+      bxq = std::max(bxq, std::abs(qry[7 * (size_t)i + 1])); byq = std::max(byq, std::abs(qry[7 * (size_t)i + 2]));
+    }
+    double max_x = std::max(bxr, bxq), max_y = std::max(byr, byq);     // PR.cpp:771-774
+    if (!p.disable_yaw_search) { const double m = std::max(max_x, max_y); max_x = m; max_y = m; }  // :777-782
+    half_x = max_x * p.dilation_factor;                                // :786-787
+    half_y = max_y * p.dilation_factor;
+    out->yaw_half = p.match_yaw_half_range;
+  } else {
+    half_x = p.match_x_half_range_intra;                               // :808-810
+    half_y = p.match_y_half_range_intra;
+    out->yaw_half = p.match_yaw_half_range_intra;
+  }
+  out->half_x = half_x; out->half_y = half_y;
+  out->centroid_ref[0] = cref[0]; out->centroid_ref[1] = cref[1];
+  out->centroid_qry[0] = cqry[0]; out->centroid_qry[1] = cqry[1];
+
+  std::vector<int32_t> ri_own, qi_own;
+  int32_t *ri = ref_idx_out, *qi = qry_idx_out;
+  if (!ri) { ri_own.resize(std::max(n_qry, 1)); ri = ri_own.data(); }
+  if (!qi) { qi_own.resize(std::max(n_qry, 1)); qi = qi_own.data(); }
+  int rc = slide_pr_match_maps(h, ref.data(), n_ref, qry.data(), n_qry, half_x, half_y, ri, qi, &out->match);
+  if (rc != SLIDE_PR_OK) return rc;
+  const slide_pr_match_result &m = out->match;
+  std::memcpy(out->R_t, m.R_t, sizeof(m.R_t));
+  // findTransformation starts from best_num_inliers_out = 0 and MatchMaps leaves it untouched on
+  // its sanity-check return (PR.cpp:819, 169-175)
+  out->best_num_inliers = m.status == SLIDE_PR_SANITY_RETURN ? 0 : m.best_num_inliers;
+  out->n_matched = m.status == SLIDE_PR_SANITY_RETURN ? 0 : m.n_matched;
+  if (out->best_num_inliers < p.min_num_inliers) { out->found = 0; return SLIDE_PR_NOT_FOUND; }  // PR.cpp:849
+  out->found = 1;
+  if (!p.use_lsq) {                                                    // PR.cpp:882-905
+    double raw[16] = {0};
+    raw[0] = m.R_t[0]; raw[1] = m.R_t[1]; raw[4] = m.R_t[3]; raw[5] = m.R_t[4];
+    raw[10] = 1; raw[15] = 1;
+    raw[3] = m.R_t[2]; raw[7] = m.R_t[5]; raw[11] = 0;
+    if (p.inter_loop_closure) {                                        // PR.cpp:947-967
+      double H1[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, H2[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+      H1[3] = cref[0]; H1[7] = cref[1];
+      H2[3] = -cqry[0]; H2[7] = -cqry[1];
+      double T1[16];
+      spr::mat4_mul(H1, raw, T1);
+      spr::mat4_mul(T1, H2, out->transform);
+    } else {
+      std::memcpy(out->transform, raw, sizeof(raw));
+    }
+    spr::xyz_yaw_from_tf(out->transform, out->xyz_yaw);
+  } else {                                                             // PR.cpp:906-944
+    const int k = out->n_matched;
+    std::vector<double> tgt(3 * (size_t)std::max(k, 1)), src(3 * (size_t)std::max(k, 1));
+    for (int i = 0; i < k; i++) {
+      const double *r = ref.data() + 7 * (size_t)ri[i], *q = qry.data() + 7 * (size_t)qi[i];
+      tgt[3 * i] = r[1]; tgt[3 * i + 1] = r[2]; tgt[3 * i + 2] = r[3];
+      src[3 * i] = q[1]; src[3 * i + 1] = q[2]; src[3 * i + 2] = q[3];
+      if (p.inter_loop_closure) {                                      // PR.cpp:925-937
+        tgt[3 * i] += cref[0]; tgt[3 * i + 1] += cref[1];
+        src[3 * i] += cqry[0]; src[3 * i + 1] += cqry[1];
+      }
+    }
+    spr::solve_lsq(tgt.data(), src.data(), k, out->xyz_yaw, out->transform);
+  }
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_find_inter_loop_closure(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7,
+                                     int32_t n_qry, double *tf16, slide_pr_tf_result *out_opt) {
+  if (!h || !tf16) return SLIDE_PR_ERR_INVALID;
+  slide_pr_tf_result local, *out = out_opt ? out_opt : &local;
+  std::memset(out, 0, sizeof(*out));
+  if (n_ref < h->p.min_num_map_objects_to_start || n_qry < h->p.min_num_map_objects_to_start)  // PR.cpp:508-510
+    return SLIDE_PR_NOT_FOUND;
+  const int rc = slide_pr_find_transformation(h, ref7, n_ref, qry7, n_qry, nullptr, nullptr, out);
+  if (rc != SLIDE_PR_OK) return rc;
+  const double x = out->xyz_yaw[0], y = out->xyz_yaw[1], z = out->xyz_yaw[2], yaw = out->xyz_yaw[3];
+  for (int i = 0; i < 16; i++) tf16[i] = 0;                            // PR.cpp:523-536
+  tf16[0] = std::cos(yaw); tf16[1] = -std::sin(yaw); tf16[4] = std::sin(yaw); tf16[5] = std::cos(yaw);
+  tf16[10] = 1; tf16[15] = 1;
+  tf16[3] = x; tf16[7] = y; tf16[11] = z;
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_find_intra_loop_closure(slide_pr_handle *h, const double *meas7, int32_t n_meas, const double *submap7,
+                                     int32_t n_sub, const double *query_pose16, const double *candidate_pose16,
+                                     double *tf16, slide_pr_tf_result *out_opt) {
+  if (!h || !tf16 || !query_pose16 || !candidate_pose16) return SLIDE_PR_ERR_INVALID;
+  slide_pr_tf_result local, *out = out_opt ? out_opt : &local;
+  std::memset(out, 0, sizeof(*out));
+  if (n_meas == 0 || n_sub == 0) return SLIDE_PR_NOT_FOUND;            // PR.cpp:395-398
+  if (n_meas < 4) return SLIDE_PR_NOT_FOUND;                           // PR.cpp:400-403
+  std::vector<double> moved((size_t)n_meas * 7);
+  const double *P = query_pose16;
+  for (int i = 0; i < n_meas; i++) {                                   // PR.cpp:421-439
+    const double *m = meas7 + 7 * (size_t)i;
+    double v[4];
+    for (int r = 0; r < 4; r++) v[r] = ((P[r * 4] * m[1] + P[r * 4 + 1] * m[2]) + P[r * 4 + 2] * m[3]) + P[r * 4 + 3] * 1.0;
+    double *o = moved.data() + 7 * (size_t)i;
+    o[0] = m[0]; o[1] = v[0] / v[3]; o[2] = v[1] / v[3]; o[3] = v[2] / v[3];
+    o[4] = m[4]; o[5] = m[5]; o[6] = m[6];
+  }
+  const int32_t saved = h->p.inter_loop_closure;
+  h->p.inter_loop_closure = 0;  // the caller's intra instance has inter_loop_closure = false (sloamNode.cpp:23)
+  const int rc = slide_pr_find_transformation(h, submap7, n_sub, moved.data(), n_meas, nullptr, nullptr, out);
+  h->p.inter_loop_closure = saved;
+  if (rc != SLIDE_PR_OK) return rc;
+  const double yaw = out->xyz_yaw[3];
+  double lc[16] = {0};                                                 // PR.cpp:455-470
+  lc[0] = std::cos(yaw); lc[1] = -std::sin(yaw); lc[4] = std::sin(yaw); lc[5] = std::cos(yaw);
+  lc[10] = 1; lc[15] = 1;
+  lc[3] = out->xyz_yaw[0]; lc[7] = out->xyz_yaw[1]; lc[11] = 0.0;
+  double cinv[16], drift[16];
+  spr::mat4_rigid_inverse(candidate_pose16, cinv);
+  spr::mat4_mul(cinv, query_pose16, drift);                            // PR.cpp:478
+  spr::mat4_mul(drift, lc, tf16);                                      // PR.cpp:483-494
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_find_transformation_batch(slide_pr_handle *h, const double *const *maps, const int32_t *map_sizes,
+                                       int32_t n_maps, const int32_t *ref_of, const int32_t *qry_of, int32_t n_pairs,
+                                       slide_pr_tf_result *out) {
+  if (!h || !maps || !map_sizes || !ref_of || !qry_of || !out) return SLIDE_PR_ERR_INVALID;
+  for (int p = 0; p < n_pairs; p++) {
+    if (ref_of[p] < 0 || ref_of[p] >= n_maps || qry_of[p] < 0 || qry_of[p] >= n_maps) { h->err = "pair index out of range"; return SLIDE_PR_ERR_INVALID; }
+    const int rc = slide_pr_find_transformation(h, maps[ref_of[p]], map_sizes[ref_of[p]], maps[qry_of[p]],
+                                                map_sizes[qry_of[p]], nullptr, nullptr, &out[p]);
+    if (rc < 0) return rc;
+  }
+  return SLIDE_PR_OK;
+}
+
+void slide_pr_pack_record(const slide_pr_match_result *r, int32_t rank, slide_pr_topk_record *rec) {
+  rec->hyp_index = r->best_hyp_index;
+  rec->inliers = r->best_hyp_index >= 0 ? r->best_num_inliers : -10000;
+  rec->rank = rank;
+}
+
+int slide_pr_merge_records(const slide_pr_topk_record *recs, int32_t n) {
+  int best = -1;
+  for (int i = 0; i < n; i++) {
+    if (recs[i].hyp_index < 0) continue;
+    if (best < 0 || recs[i].inliers > recs[best].inliers ||
+        (recs[i].inliers == recs[best].inliers && recs[i].hyp_index < recs[best].hyp_index))
+      best = i;
+  }
+  return best;
+}
+
+int slide_pr_match_triangles(slide_pr_handle *h, const double *tris_model6, int32_t t_model,
+                             const double *tris_data6, int32_t t_data, double threshold, int32_t *model_idx_out,
+                             int32_t *data_idx_out, int32_t *perm_model_out, int32_t *perm_data_out, int64_t cap,
+                             int64_t *n_matches) {
+  if (!h || !n_matches || t_model < 0 || t_data < 0 || cap < 0) return SLIDE_PR_ERR_INVALID;
+  if ((t_model > 0 && !tris_model6) || (t_data > 0 && !tris_data6)) { h->err = "null triangle array"; return SLIDE_PR_ERR_INVALID; }
+  *n_matches = 0;
+  if (t_model == 0 || t_data == 0) return SLIDE_PR_OK;
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  DevBuf &b = h->d_tri;
+  // layout: tris_m | tris_d | desc_m | desc_d | perm_m | perm_d | counts | offsets | total
+  const size_t tm = (size_t)t_model, td = (size_t)t_data;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_tm = take(tm * 6 * 8), o_td = take(td * 6 * 8), o_dm = take(tm * 3 * 8), o_dd = take(td * 3 * 8);
+  const size_t o_pm = take(tm * 3 * 4), o_pd = take(td * 3 * 4), o_cnt = take(tm * 8), o_off = take(tm * 8), o_tot = take(8);
+  SPR_CUDA(h, b.ensure(off));
+  char *base = b.as<char>();
+  SPR_CUDA(h, cudaMemcpyAsync(base + o_tm, tris_model6, tm * 6 * 8, cudaMemcpyHostToDevice, st));
+  SPR_CUDA(h, cudaMemcpyAsync(base + o_td, tris_data6, td * 6 * 8, cudaMemcpyHostToDevice, st));
+  double *dm = (double *)(base + o_dm), *dd = (double *)(base + o_dd);
+  int32_t *pm = (int32_t *)(base + o_pm), *pd = (int32_t *)(base + o_pd);
+  unsigned long long *cnt = (unsigned long long *)(base + o_cnt), *offs = (unsigned long long *)(base + o_off),
+                     *tot = (unsigned long long *)(base + o_tot);
+  SPR_CUDA(h, spr_launch_tri_desc((const double *)(base + o_tm), t_model, dm, pm, st));
+  SPR_CUDA(h, spr_launch_tri_desc((const double *)(base + o_td), t_data, dd, pd, st));
+  SPR_CUDA(h, spr_launch_tri_match(dm, t_model, dd, t_data, threshold, cnt, offs, tot, nullptr, nullptr, 0, false,
+                                   h->sm_count, st));
+  unsigned long long total = 0;
+  SPR_CUDA(h, cudaMemcpyAsync(&total, tot, 8, cudaMemcpyDeviceToHost, st));
+  SPR_CUDA(h, cudaStreamSynchronize(st));
+  *n_matches = (int64_t)total;
+  const int64_t n_out = std::min<int64_t>((int64_t)total, cap);
+  if (n_out > 0 && model_idx_out && data_idx_out) {
+    SPR_CUDA(h, h->d_tri_out.ensure((size_t)n_out * 2 * sizeof(int32_t)));
+    int32_t *mi = h->d_tri_out.as<int32_t>(), *di = mi + n_out;
+    SPR_CUDA(h, spr_launch_tri_match(dm, t_model, dd, t_data, threshold, cnt, offs, tot, mi, di, n_out, true,
+                                     h->sm_count, st));
+    SPR_CUDA(h, cudaMemcpyAsync(model_idx_out, mi, (size_t)n_out * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SPR_CUDA(h, cudaMemcpyAsync(data_idx_out, di, (size_t)n_out * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> hpm, hpd;
+    if (perm_model_out || perm_data_out) {
+      hpm.resize(tm * 3); hpd.resize(td * 3);
+      SPR_CUDA(h, cudaMemcpyAsync(hpm.data(), pm, tm * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      SPR_CUDA(h, cudaMemcpyAsync(hpd.data(), pd, td * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    SPR_CUDA(h, cudaStreamSynchronize(st));
+    for (int64_t k = 0; k < n_out; k++)
+      for (int v = 0; v < 3; v++) {  // vertices in sorted-distance order, SC.cpp:102-105
+        if (perm_model_out) perm_model_out[3 * k + v] = hpm[3 * (size_t)model_idx_out[k] + v];
+        if (perm_data_out) perm_data_out[3 * k + v] = hpd[3 * (size_t)data_idx_out[k] + v];
+      }
+  }
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_score_hypotheses(slide_pr_handle *h, const double *hyps4, int64_t n, int32_t *counts_out,
+                              slide_pr_match_result *out) {
+  if (!h || !out || (n > 0 && !hyps4) || n < 0) return SLIDE_PR_ERR_INVALID;
+  if (!h->prepared) { h->err = "slide_pr_score_hypotheses before slide_pr_prepare"; return SLIDE_PR_ERR_INVALID; }
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  fill_result_header(h, out);
+  out->status = SLIDE_PR_OK;
+  if (n == 0) return SLIDE_PR_OK;
+  int rc;
+  if ((rc = upload_raw(h, h->d_hyps, hyps4, (size_t)n * 4 * sizeof(double), st))) return rc;
+  if (counts_out) SPR_CUDA(h, h->d_counts.ensure((size_t)n * sizeof(int32_t)));
+  SPR_CUDA(h, cudaMemsetAsync(h->d_best.p, 0, sizeof(unsigned long long), st));
+  SPR_CUDA(h, cudaEventRecord(h->ev0, st));
+  SPR_CUDA(h, spr_launch_score_list(h->V, h->d_hyps.as<double>(), n, counts_out ? h->d_counts.as<int32_t>() : nullptr,
+                                    h->d_best.as<unsigned long long>(), h->sm_count, st));
+  SPR_CUDA(h, cudaEventRecord(h->ev1, st));
+  unsigned long long key = 0;
+  SPR_CUDA(h, cudaMemcpyAsync(&key, h->d_best.p, sizeof(key), cudaMemcpyDeviceToHost, st));
+  if (counts_out) SPR_CUDA(h, cudaMemcpyAsync(counts_out, h->d_counts.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  SPR_CUDA(h, cudaStreamSynchronize(st));
+  float ms = 0;
+  SPR_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  out->kernel_ms = ms;
+  out->gpu_launches = 1;
+  out->hypotheses_scored = n;
+  if (key) {
+    out->best_num_inliers = spr_key_count(key);
+    out->best_hyp_index = spr_key_index(key);
+    const double *hp = hyps4 + 4 * (size_t)out->best_hyp_index;
+    out->R_t[0] = hp[0]; out->R_t[1] = -hp[1]; out->R_t[2] = hp[2];
+    out->R_t[3] = hp[1]; out->R_t[4] = hp[0];  out->R_t[5] = hp[3];
+  }
+  return SLIDE_PR_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

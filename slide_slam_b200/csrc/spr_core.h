@@ -1,0 +1,177 @@
+// spr_core.h -- the per-thread scoring primitives (host + device).
+//
+// The same inline functions are compiled into the CUDA kernels (spr_kernels.cu) and into the
+// test-only single-thread emulation (tests/emu), which lets the index structures and the
+// decision arithmetic be checked against the CPU oracle without a GPU.  The emulation is a
+// test harness, not a fallback: the product library never executes these on the host.
+//
+// Decision arithmetic follows place_recognition.cpp:246-357 in fp64 with every multiply and add
+// rounded separately (the reference is built without FMA): __dmul_rn/__dadd_rn on the device,
+// plain operators under -ffp-contract=off on the host.
+#pragma once
+#include <math.h>
+
+#include "spr_types.h"
+
+#if defined(__CUDA_ARCH__)
+#define SPR_DADD(a, b) __dadd_rn((a), (b))
+#define SPR_DSUB(a, b) __dsub_rn((a), (b))
+#define SPR_DMUL(a, b) __dmul_rn((a), (b))
+#define SPR_FUNNEL_R(lo, hi, s) __funnelshift_r((lo), (hi), (s))
+#define SPR_POPC(x) __popc(x)
+#define SPR_FFS(x) __ffs(x)
+#else
+#define SPR_DADD(a, b) ((a) + (b))
+#define SPR_DSUB(a, b) ((a) - (b))
+#define SPR_DMUL(a, b) ((a) * (b))
+static inline uint32_t spr_funnel_r_host(uint32_t lo, uint32_t hi, uint32_t s) {
+  s &= 31u;
+  return s ? ((lo >> s) | (hi << (32u - s))) : lo;
+}
+#define SPR_FUNNEL_R(lo, hi, s) spr_funnel_r_host((lo), (hi), (s))
+#define SPR_POPC(x) __builtin_popcount(x)
+#define SPR_FFS(x) __builtin_ffs((int)(x))
+#endif
+
+// metres -> fixed-point cell units, rounded down.  |v * S| < 2^30 is guaranteed by the host.
+SPR_HD int32_t spr_fx(double v, double S) { return (int32_t)floor(SPR_DMUL(v, S)); }
+
+// Rotated query coordinates, PR.cpp:257-258 (first two terms, left to right):
+//   rx = c*qx + (-s)*qy ; ry = s*qx + c*qy
+SPR_HD void spr_rotate(double c, double s, double qx, double qy, double *rx, double *ry) {
+  const double ms = -s;
+  *rx = SPR_DADD(SPR_DMUL(c, qx), SPR_DMUL(ms, qy));
+  *ry = SPR_DADD(SPR_DMUL(s, qx), SPR_DMUL(c, qy));
+}
+
+// PR.cpp:310-313,332-333 for one (query, reference) pair under translation (tx, ty).
+SPR_HD bool spr_distance_match(double rx, double ry, double tx, double ty, double refx,
+                               double refy, double Tstar) {
+  const double xt = SPR_DADD(rx, tx);  // third term of PR.cpp:257-258; the "/ 1.0" is exact
+  const double yt = SPR_DADD(ry, ty);
+  const double dx = SPR_DSUB(refx, xt);
+  const double dy = SPR_DSUB(refy, yt);
+  const double d2 = SPR_DADD(SPR_DMUL(dx, dx), SPR_DMUL(dy, dy));
+  return d2 < Tstar;  // <=> sqrt(d2) < match_threshold_ (sqrt is monotone, correctly rounded)
+}
+
+// PR.cpp:315-339: dimension rule, keyed on the REFERENCE object's d2 == 0 && d3 == 0.
+SPR_HD bool spr_dimension_match(const double *rd, const double *qd, double thr_dim, double Sstar) {
+  const double a0 = fabs(SPR_DSUB(rd[0], qd[0]));
+  if (rd[1] == 0 && rd[2] == 0) return a0 < thr_dim;
+  const double a1 = fabs(SPR_DSUB(rd[1], qd[1]));
+  const double a2 = fabs(SPR_DSUB(rd[2], qd[2]));
+  const double sum = SPR_DADD(SPR_DADD(a0, a1), a2);  // 0 + a0 is exact
+  return sum < Sstar;                                  // <=> sum / 3 < thr_dim
+}
+
+// Bit-parallel occupancy probe: 32 consecutive lattice samples along the chunk's axis against
+// the bitmap row that the across coordinate selects.  aq / bq are the fixed-point sums
+// (chunk + rotated query) of the across / along coordinates.  Returns the hit bits; *na / *nb
+// receive the cell coordinates of bit 0 (meaningful only where a bit is set).
+SPR_HD uint32_t spr_probe(const uint32_t *plane, int32_t W, int32_t R, int32_t maxbit, int32_t F,
+                          int32_t aq, int32_t bq, uint32_t valid, int32_t *na, int32_t *nb) {
+  const int32_t a = aq >> F;  // arithmetic shift == floor
+  const int32_t b = bq >> F;
+  *na = a;
+  *nb = b;
+  int32_t row = a + 1;
+  row = row < 0 ? 0 : row;
+  row = row > R - 1 ? R - 1 : row;  // rows 0 and R-1 are all-zero
+  int32_t bit = b + 32;
+  bit = bit < 0 ? 0 : bit;
+  bit = bit > maxbit ? maxbit : bit;  // word 0 and words >= maxbit/32 are all-zero
+  const uint32_t wi = (uint32_t)row * (uint32_t)W + ((uint32_t)bit >> 5);
+  const uint32_t w0 = plane[wi], w1 = plane[wi + 1];
+  return SPR_FUNNEL_R(w0, w1, (uint32_t)bit & 31u) & valid;
+}
+
+// Exact verification of one occupied cell (nx, ny) of label l for a query point whose rotated
+// coordinates are (rx, ry), under translation (tx, ty).  Returns true iff some reference
+// landmark passes the reference's predicate (PR.cpp:299-355); *first_ref receives the smallest
+// such reference index (candidate lists are ascending).
+SPR_HD bool spr_verify_cell(const SprView &V, int32_t l, int32_t nx, int32_t ny, double rx, double ry,
+                            double tx, double ty, const double *qd, int32_t *first_ref) {
+  const SprGrid &G = V.grid;
+  // rank of the cell among the marked cells (dir-0 plane: rows = x, bits = y)
+  const uint32_t bit = (uint32_t)(ny + 32);
+  const uint32_t widx = (uint32_t)(nx + 1) * (uint32_t)G.W[0] + (bit >> 5);
+  const uint32_t word = V.bitmap[(size_t)l * G.label_stride + widx];
+  const uint32_t below = word & ((1u << (bit & 31u)) - 1u);
+  const uint32_t rank = V.prefix[(size_t)l * G.plane_words[0] + widx] + (uint32_t)SPR_POPC(below);
+  const uint32_t start = V.cellinfo[2 * (size_t)rank], count = V.cellinfo[2 * (size_t)rank + 1];
+  for (uint32_t k = 0; k < count; k++) {
+    const uint32_t i = V.cand[start + k];
+    if (!spr_distance_match(rx, ry, tx, ty, V.ref_xy[2 * (size_t)i], V.ref_xy[2 * (size_t)i + 1], V.Tstar))
+      continue;
+    if (!V.ignore_dim && !spr_dimension_match(V.ref_dims + 3 * (size_t)i, qd, V.thr_dim, V.Sstar))
+      continue;
+    *first_ref = (int32_t)i;
+    return true;
+  }
+  return false;
+}
+
+// Verification of one filter hit of the lattice kernel: query js (sorted order) of label l under
+// yaw a and the translation of bit b of `ch`.  (na, nb) are spr_probe's cell coordinates of bit 0.
+SPR_HD bool spr_verify_hit(const SprView &V, const SprChunk &ch, int32_t l, int32_t a, int32_t js,
+                           int32_t na, int32_t nb, int32_t b, int32_t *first_ref) {
+  const int32_t nalong = nb + b;
+  const int32_t nx = ch.dir ? nalong : na;
+  const int32_t ny = ch.dir ? na : nalong;
+  // the hypothesis' translation, exactly as the reference's accumulated lattice value
+  const double along = V.lat[ch.along_off + (uint32_t)b];
+  const double tx = ch.dir ? along : ch.across;
+  const double ty = ch.dir ? ch.across : along;
+  const size_t qi = (size_t)a * (size_t)V.nq + (size_t)js;
+  return spr_verify_cell(V, l, nx, ny, V.qrot[2 * qi], V.qrot[2 * qi + 1], tx, ty,
+                         V.qdims + 3 * (size_t)js, first_ref);
+}
+
+// Occupancy test of a single point (general hypothesis lists): fixed-point cell of
+// (xt - g0x, yt - g0y); returns false when the cell is outside the grid or unmarked.
+SPR_HD bool spr_point_cell(const SprView &V, int32_t l, double xt, double yt, int32_t *nx, int32_t *ny) {
+  const SprGrid &G = V.grid;
+  const double ux = SPR_DMUL(SPR_DSUB(xt, G.g0x), G.S), uy = SPR_DMUL(SPR_DSUB(yt, G.g0y), G.S);
+  if (!(ux >= 0.0 && uy >= 0.0 && ux < 1073741824.0 && uy < 1073741824.0)) return false;
+  const int32_t cx = (int32_t)ux >> G.F, cy = (int32_t)uy >> G.F;
+  if (cx >= G.GX || cy >= G.GY) return false;
+  const uint32_t bit = (uint32_t)(cy + 32);
+  const uint32_t word = V.bitmap[(size_t)l * G.label_stride + (uint32_t)(cx + 1) * (uint32_t)G.W[0] + (bit >> 5)];
+  *nx = cx;
+  *ny = cy;
+  return (word >> (bit & 31u)) & 1u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SlideGraph descriptor half (semantic_clipper.cpp:41-108)
+// ---------------------------------------------------------------------------------------------
+// compute_triangle_diff's descriptor: vertex-to-centroid distances sorted ascending, plus the
+// argsort permutation (SC.cpp:66-90).  tri = [x0,y0,x1,y1,x2,y2].  Arithmetic is fp64,
+// left-to-right, not fused (the contract of oracle/slide_oracle.c).
+SPR_HD void spr_triangle_descriptor(const double *t, double *desc3, int32_t *perm3) {
+  const double cx = SPR_DADD(SPR_DADD(t[0], t[2]), t[4]) / 3.0;
+  const double cy = SPR_DADD(SPR_DADD(t[1], t[3]), t[5]) / 3.0;
+  double d[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double dx = SPR_DSUB(t[2 * i], cx), dy = SPR_DSUB(t[2 * i + 1], cy);
+    d[i] = sqrt(SPR_DADD(SPR_DMUL(dx, dx), SPR_DMUL(dy, dy)));
+  }
+  // stable 3-element argsort (std::sort on 3 elements is an insertion sort, SC.cpp:41-46)
+  int i0 = 0, i1 = 1, i2 = 2;
+  if (d[i1] < d[i0]) { const int x = i0; i0 = i1; i1 = x; }
+  if (d[i2] < d[i1]) {
+    const int x = i1; i1 = i2; i2 = x;
+    if (d[i1] < d[i0]) { const int y = i0; i0 = i1; i1 = y; }
+  }
+  desc3[0] = d[i0]; desc3[1] = d[i1]; desc3[2] = d[i2];
+  perm3[0] = i0; perm3[1] = i1; perm3[2] = i2;
+}
+
+// SC.cpp:92-99: sqrt(sum (dm - dd)^2) < threshold
+SPR_HD bool spr_descriptor_match(const double *dm, const double *dd, double threshold) {
+  const double e0 = SPR_DSUB(dm[0], dd[0]), e1 = SPR_DSUB(dm[1], dd[1]), e2 = SPR_DSUB(dm[2], dd[2]);
+  const double s = SPR_DADD(SPR_DADD(SPR_DMUL(e0, e0), SPR_DMUL(e1, e1)), SPR_DMUL(e2, e2));
+  return sqrt(s) < threshold;
+}

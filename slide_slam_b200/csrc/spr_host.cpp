@@ -1,0 +1,544 @@
+// spr_host.cpp -- host index builder for the B200 place-recognition search (see spr_host.h).
+#include "spr_host.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+namespace spr {
+
+// ------------------------------------------------------------------------------------------
+// thresholds
+// ------------------------------------------------------------------------------------------
+double sqrt_threshold(double thr) {
+  // smallest double T with sqrt(T) >= thr, so that (sqrt(d2) < thr) == (d2 < T)  [PR.cpp:332-333]
+  if (!(thr > 0)) return 0.0;  // also NaN: nothing passes
+  if (std::isinf(thr)) return thr;
+  double t = thr * thr;
+  for (int i = 0; i < 64 && std::sqrt(t) >= thr; i++) t = std::nextafter(t, -HUGE_VAL);
+  for (int i = 0; i < 64 && std::sqrt(std::nextafter(t, HUGE_VAL)) < thr; i++) t = std::nextafter(t, HUGE_VAL);
+  return std::nextafter(t, HUGE_VAL);
+}
+
+double div3_threshold(double thr) {
+  // smallest double S with (S / 3) >= thr, so that ((sum / 3) < thr) == (sum < S)  [PR.cpp:329,338]
+  if (!(thr > 0)) return 0.0;
+  if (std::isinf(thr)) return thr;
+  double t = thr * 3.0;
+  for (int i = 0; i < 64 && t / 3 >= thr; i++) t = std::nextafter(t, -HUGE_VAL);
+  for (int i = 0; i < 64 && std::nextafter(t, HUGE_VAL) / 3 < thr; i++) t = std::nextafter(t, HUGE_VAL);
+  return std::nextafter(t, HUGE_VAL);
+}
+
+// ------------------------------------------------------------------------------------------
+// lattice + chunks
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct RectEmitter {
+  Lattice &L;
+  int ring;
+  uint32_t x_off, y_off;
+  const double *xs, *ys;
+  int64_t tb, te;  // ordinal filter, te < 0: none
+
+  void push(double across, uint32_t along_off, int n, uint64_t ord0, uint64_t stride, uint32_t dir) {
+    // restrict to ordinals in [tb, te)
+    int b_lo = 0, b_hi = n;
+    if (tb > 0 || te >= 0) {
+      const int64_t o0 = (int64_t)ord0, st = (int64_t)stride;
+      if (tb > o0) b_lo = (int)std::min<int64_t>(n, (tb - o0 + st - 1) / st);
+      if (te >= 0) b_hi = (te <= o0) ? 0 : (int)std::min<int64_t>(n, (te - o0 + st - 1) / st);
+    }
+    if (b_lo >= b_hi) return;
+    SprChunk c;
+    c.across = across;
+    c.along_off = along_off;
+    const uint32_t hi_mask = b_hi >= 32 ? 0xffffffffu : ((1u << b_hi) - 1u);
+    const uint32_t lo_mask = b_lo <= 0 ? 0u : ((1u << b_lo) - 1u);
+    c.valid = hi_mask & ~lo_mask;
+    c.ord_base = (uint32_t)ord0;
+    c.ord_stride = (uint32_t)stride;
+    c.dir = dir;
+    c.ring = (uint32_t)ring;
+    L.chunks.push_back(c);
+  }
+
+  // rectangle ix in [ix0, ix1), iy in [iy0, iy1); ordinal(ix, iy) = ord0 + (ix-ix0)*row_stride + (iy-iy0)
+  void rect(int ix0, int ix1, int iy0, int iy1, uint64_t ord0, uint64_t row_stride) {
+    const int w = ix1 - ix0, h = iy1 - iy0;
+    if (w <= 0 || h <= 0) return;
+    const int64_t cost_y = (int64_t)w * ((h + 31) / 32);
+    const int64_t cost_x = (int64_t)h * ((w + 31) / 32);
+    if (cost_y <= cost_x) {
+      // bits along y; consecutive chunks = consecutive x rows of the same y block
+      for (int by = iy0; by < iy1; by += 32) {
+        const int n = std::min(32, iy1 - by);
+        for (int ix = ix0; ix < ix1; ix++)
+          push(xs[ix], y_off + (uint32_t)by, n, ord0 + (uint64_t)(ix - ix0) * row_stride + (uint64_t)(by - iy0), 1, 0);
+      }
+    } else {
+      for (int bx = ix0; bx < ix1; bx += 32) {
+        const int n = std::min(32, ix1 - bx);
+        for (int iy = iy0; iy < iy1; iy++)
+          push(ys[iy], x_off + (uint32_t)bx, n, ord0 + (uint64_t)(bx - ix0) * row_stride + (uint64_t)(iy - iy0), row_stride, 1);
+      }
+    }
+  }
+};
+
+}  // namespace
+
+int build_lattice(const slide_pr_params &p, double half_x, double half_y, double yaw_half,
+                  int64_t trans_begin, int64_t trans_end, Lattice &L, std::string &err) {
+  L = Lattice();
+  const double step = p.match_xy_step_size;
+  if (!(step > 0) || !std::isfinite(step)) { err = "match_xy_step_size must be positive and finite"; return SLIDE_PR_ERR_INVALID; }
+  if (!std::isfinite(half_x) || !std::isfinite(half_y)) { err = "non-finite search half range"; return SLIDE_PR_ERR_NONFINITE; }
+  // yaw candidates, PR.cpp:136-146
+  if (p.disable_yaw_search) {
+    L.yaw.push_back(0.0);
+  } else {
+    const double ys = p.match_yaw_angle_step_size;
+    if (!std::isfinite(yaw_half) || !std::isfinite(ys)) { err = "non-finite yaw range"; return SLIDE_PR_ERR_NONFINITE; }
+    if (yaw_half > 0 && !(ys > 0)) { err = "match_yaw_angle_step_size must be positive"; return SLIDE_PR_ERR_INVALID; }
+    for (double yaw_raw = -yaw_half; yaw_raw < yaw_half; yaw_raw += ys) {
+      L.yaw.push_back(yaw_raw);
+      if (L.yaw.size() > (1u << 20)) { err = "more than 2^20 yaw candidates"; return SLIDE_PR_ERR_UNSUPPORTED; }
+    }
+  }
+  L.cs.resize(2 * L.yaw.size());
+  for (size_t a = 0; a < L.yaw.size(); a++) {  // libm, as PR.cpp:246-250
+    L.cs[2 * a] = std::cos(L.yaw[a]);
+    L.cs[2 * a + 1] = std::sin(L.yaw[a]);
+  }
+  // ring geometry, PR.cpp:154-175
+  const double outer = 10 * step;
+  const double steps_d = std::min(half_x, half_y) / outer;
+  const double steps_c = std::ceil(steps_d);
+  if (steps_c > 1e6) { err = "more than 1e6 search rings"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  const int rings = (int)steps_c;
+  L.rings = rings;
+  L.ox = half_x / static_cast<double>(rings);
+  L.oy = half_y / static_cast<double>(rings);
+  if (L.ox < step || L.oy < step) { L.status = SLIDE_PR_SANITY_RETURN; return SLIDE_PR_OK; }
+
+  uint64_t ord = 0;
+  for (int k = 0; k < rings; k++) {
+    const double kd = static_cast<double>(k);
+    const double x_right_prev = kd * L.ox, x_left_prev = -kd * L.ox;        // PR.cpp:204,210
+    const double x_pos_end = (kd + 1) * L.ox, x_neg_start = -(kd + 1) * L.ox;  // :205-206
+    const double y_right_prev = kd * L.oy, y_left_prev = -kd * L.oy;
+    const double y_pos_end = (kd + 1) * L.oy, y_neg_start = -(kd + 1) * L.oy;
+    Lattice::Ring R;
+    R.x_off = (uint32_t)L.lat.size();
+    for (double x = x_neg_start; x <= x_pos_end; x += step) {                // PR.cpp:230
+      L.lat.push_back(x);
+      if (L.lat.size() - R.x_off > (1u << 22)) { err = "more than 2^22 lattice samples per axis"; return SLIDE_PR_ERR_UNSUPPORTED; }
+    }
+    R.nx = (uint32_t)L.lat.size() - R.x_off;
+    R.y_off = (uint32_t)L.lat.size();
+    for (double y = y_neg_start; y <= y_pos_end; y += step) {                // PR.cpp:232
+      L.lat.push_back(y);
+      if (L.lat.size() - R.y_off > (1u << 22)) { err = "more than 2^22 lattice samples per axis"; return SLIDE_PR_ERR_UNSUPPORTED; }
+    }
+    R.ny = (uint32_t)L.lat.size() - R.y_off;
+    // lat may have been reallocated: take pointers now
+    const double *xs = L.lat.data() + R.x_off, *ys = L.lat.data() + R.y_off;
+    // already-searched centre box as closed index ranges, PR.cpp:238-239
+    R.ixl = 0; R.ixh = -1; R.iyl = 0; R.iyh = -1;
+    {
+      int lo = -1, hi = -1;
+      for (int i = 0; i < (int)R.nx; i++)
+        if (xs[i] >= x_left_prev && xs[i] <= x_right_prev) { if (lo < 0) lo = i; hi = i; }
+      if (lo >= 0) { R.ixl = lo; R.ixh = hi; }
+      lo = hi = -1;
+      for (int i = 0; i < (int)R.ny; i++)
+        if (ys[i] >= y_left_prev && ys[i] <= y_right_prev) { if (lo < 0) lo = i; hi = i; }
+      if (lo >= 0) { R.iyl = lo; R.iyh = hi; }
+    }
+    const int n_in_x = R.ixh >= R.ixl ? R.ixh - R.ixl + 1 : 0;
+    const int n_in_y = R.iyh >= R.iyl ? R.iyh - R.iyl + 1 : 0;
+    const bool has_box = n_in_x > 0 && n_in_y > 0;
+    R.ord_base = ord;
+    R.count = (uint64_t)R.nx * R.ny - (has_box ? (uint64_t)n_in_x * n_in_y : 0);
+    R.chunk_begin = (uint32_t)L.chunks.size();
+    RectEmitter E{L, k, R.x_off, R.y_off, xs, ys, trans_begin, trans_end};
+    const int nx = (int)R.nx, ny = (int)R.ny;
+    if (!has_box) {
+      E.rect(0, nx, 0, ny, ord, (uint64_t)ny);
+    } else {
+      const uint64_t cnt_in = (uint64_t)(ny - n_in_y);
+      const uint64_t base_b = ord + (uint64_t)R.ixl * ny;
+      const uint64_t base_c = base_b + (uint64_t)n_in_x * cnt_in;
+      E.rect(0, R.ixl, 0, ny, ord, (uint64_t)ny);                                   // x below the box
+      E.rect(R.ixl, R.ixh + 1, 0, R.iyl, base_b, cnt_in);                           // y below the box
+      E.rect(R.ixl, R.ixh + 1, R.iyh + 1, ny, base_b + (uint64_t)R.iyl, cnt_in);     // y above the box
+      E.rect(R.ixh + 1, nx, 0, ny, base_c, (uint64_t)ny);                           // x above the box
+    }
+    R.chunk_end = (uint32_t)L.chunks.size();
+    ord += R.count;
+    L.ring.push_back(R);
+    if (ord >= (1ull << 32)) { err = "more than 2^32 lattice translations"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  }
+  L.n_translations = ord;
+  if (ord * (uint64_t)std::max<size_t>(L.yaw.size(), 1) >= (1ull << SPR_KEY_IDX_BITS)) {
+    err = "more than 2^40 hypotheses"; return SLIDE_PR_ERR_UNSUPPORTED;
+  }
+  return SLIDE_PR_OK;
+}
+
+bool translation_of(const Lattice &L, uint64_t ordinal, double *x, double *y, int *ring_out) {
+  for (size_t k = 0; k < L.ring.size(); k++) {
+    const Lattice::Ring &R = L.ring[k];
+    if (ordinal < R.ord_base || ordinal >= R.ord_base + R.count) continue;
+    uint64_t o = ordinal - R.ord_base;
+    const double *xs = L.lat.data() + R.x_off, *ys = L.lat.data() + R.y_off;
+    const int n_in_x = R.ixh >= R.ixl ? R.ixh - R.ixl + 1 : 0;
+    const int n_in_y = R.iyh >= R.iyl ? R.iyh - R.iyl + 1 : 0;
+    const bool has_box = n_in_x > 0 && n_in_y > 0;
+    int ix, iy;
+    if (!has_box) {
+      ix = (int)(o / R.ny); iy = (int)(o % R.ny);
+    } else {
+      const uint64_t a = (uint64_t)R.ixl * R.ny, cnt_in = R.ny - n_in_y, b = (uint64_t)n_in_x * cnt_in;
+      if (o < a) { ix = (int)(o / R.ny); iy = (int)(o % R.ny); }
+      else if (o < a + b) {
+        o -= a; ix = R.ixl + (int)(o / cnt_in); iy = (int)(o % cnt_in);
+        if (iy >= R.iyl) iy += n_in_y;
+      } else { o -= a + b; ix = R.ixh + 1 + (int)(o / R.ny); iy = (int)(o % R.ny); }
+    }
+    *x = xs[ix]; *y = ys[iy];
+    if (ring_out) *ring_out = (int)k;
+    return true;
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// reference-map index: label buckets, occupancy bitmaps, candidate lists
+// ------------------------------------------------------------------------------------------
+int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, double reach,
+                    RefIndex &R, std::string &err) {
+  R = RefIndex();
+  R.n_ref = n_ref;
+  const double c = p.match_xy_step_size, thr = p.match_threshold;
+  R.Tstar = sqrt_threshold(thr);
+  R.Sstar = div3_threshold(p.match_threshold_dimension);
+  R.ref_xy.resize(2 * (size_t)std::max(n_ref, 1));
+  R.ref_dims.resize(3 * (size_t)std::max(n_ref, 1));
+  double minx = HUGE_VAL, maxx = -HUGE_VAL, miny = HUGE_VAL, maxy = -HUGE_VAL;
+  for (int i = 0; i < n_ref; i++) {
+    const double *r = ref7 + 7 * (size_t)i;
+    if (!std::isfinite(r[1]) || !std::isfinite(r[2])) { err = "non-finite reference coordinate"; return SLIDE_PR_ERR_NONFINITE; }
+    R.ref_xy[2 * (size_t)i] = r[1]; R.ref_xy[2 * (size_t)i + 1] = r[2];
+    R.ref_dims[3 * (size_t)i] = r[4]; R.ref_dims[3 * (size_t)i + 1] = r[5]; R.ref_dims[3 * (size_t)i + 2] = r[6];
+    minx = std::min(minx, r[1]); maxx = std::max(maxx, r[1]);
+    miny = std::min(miny, r[2]); maxy = std::max(maxy, r[2]);
+    if (r[0] == r[0]) R.labels.push_back(r[0] + 0.0);  // NaN labels never compare equal (PR.cpp:306)
+  }
+  std::sort(R.labels.begin(), R.labels.end());
+  R.labels.erase(std::unique(R.labels.begin(), R.labels.end()), R.labels.end());
+  const int n_labels = (int)R.labels.size();
+  if (n_ref == 0) { minx = maxx = miny = maxy = 0; }
+
+  const bool matchable = thr > 0 && std::isfinite(thr);
+  if (thr > 0 && std::isinf(thr)) { err = "infinite match_threshold is not supported"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  const double rad_m = matchable ? thr * (1.0 + 1e-9) + 1e-9 : 0.0;  // covers fp64 rounding of the reference's test
+  SprGrid &G = R.grid;
+  G.g0x = minx - rad_m - 2 * c;
+  G.g0y = miny - rad_m - 2 * c;
+  const double ex = (maxx + rad_m + 2 * c - G.g0x) / c, ey = (maxy + rad_m + 2 * c - G.g0y) / c;
+  if (!(ex < 1e6) || !(ey < 1e6)) { err = "reference map spans more than 1e6 lattice steps"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  G.GX = (int32_t)std::ceil(ex) + 1;
+  G.GY = (int32_t)std::ceil(ey) + 1;
+  // fixed-point format: every |coordinate - g0| and every translation must stay below 2^30 units
+  const double far = reach + std::max({std::fabs(G.g0x), std::fabs(G.g0y), std::fabs(G.g0x + G.GX * c),
+                                       std::fabs(G.g0y + G.GY * c)}) + 4 * c;
+  const double cells = far / c + 2.0;
+  int F = 16;
+  while (F > 0 && cells * std::ldexp(1.0, F) >= 1073741824.0) F--;
+  if (F < 6) { err = "search region too large relative to match_xy_step_size for the fixed-point cell format"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  G.F = F;
+  G.S = std::ldexp(1.0, F) / c;
+  // plane d: rows = across cells + 2 zero rows; bits = 32 pad + along cells + >= 64 pad
+  const int across[2] = {G.GX, G.GY}, along[2] = {G.GY, G.GX};
+  for (int d = 0; d < 2; d++) {
+    G.R[d] = across[d] + 2;
+    int W = (32 + along[d] + 32 + 31) / 32 + 1;
+    if ((W & 1) == 0) W++;  // odd row pitch: consecutive rows fall in different shared-memory banks
+    G.W[d] = W;
+    G.maxbit[d] = 32 * (W - 2);
+    const uint64_t words = (uint64_t)G.R[d] * (uint64_t)W;
+    if (words >= (1ull << 31)) { err = "occupancy bitmap too large"; return SLIDE_PR_ERR_UNSUPPORTED; }
+    G.plane_words[d] = (uint32_t)words;
+  }
+  G.label_stride = G.plane_words[0] + G.plane_words[1];
+  const uint64_t total_words = (uint64_t)G.label_stride * (uint64_t)std::max(n_labels, 1);
+  if (total_words >= (1ull << 28)) { err = "occupancy bitmaps exceed 1 GiB (step too fine for this map extent)"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  R.bitmap.assign((size_t)total_words, 0u);
+  R.prefix.assign((size_t)G.plane_words[0] * (size_t)std::max(n_labels, 1), 0u);
+
+  // mark every cell whose (slightly dilated) box a landmark's match disc touches
+  struct Entry { uint64_t key; uint32_t ref; };
+  std::vector<Entry> entries;
+  if (matchable) {
+    const double eps_cells = 3.0 / std::ldexp(1.0, F) + 1e-9 / c;  // fixed-point truncation + lattice drift
+    const double rc = rad_m / c + eps_cells;
+    const double rc2 = rc * rc * (1.0 + 1e-12);
+    for (int i = 0; i < n_ref; i++) {
+      const double *r = ref7 + 7 * (size_t)i;
+      if (!(r[0] == r[0])) continue;
+      const int l = (int)(std::lower_bound(R.labels.begin(), R.labels.end(), r[0] + 0.0) - R.labels.begin());
+      const double ux = (r[1] - G.g0x) / c, uy = (r[2] - G.g0y) / c;
+      const int x0 = (int)std::floor(ux - rc), x1 = (int)std::floor(ux + rc);
+      const int y0 = (int)std::floor(uy - rc), y1 = (int)std::floor(uy + rc);
+      for (int nx = x0; nx <= x1; nx++) {
+        const double dx = std::max({(double)nx - ux, 0.0, ux - (double)(nx + 1)});
+        for (int ny = y0; ny <= y1; ny++) {
+          const double dy = std::max({(double)ny - uy, 0.0, uy - (double)(ny + 1)});
+          if (dx * dx + dy * dy > rc2) continue;
+          if (nx < 0 || nx >= G.GX || ny < 0 || ny >= G.GY) { err = "internal: match disc leaves the grid"; return SLIDE_PR_ERR_INTERNAL; }
+          uint32_t *pl0 = R.bitmap.data() + (size_t)l * G.label_stride;
+          uint32_t *pl1 = pl0 + G.plane_words[0];
+          pl0[(size_t)(nx + 1) * G.W[0] + ((uint32_t)(ny + 32) >> 5)] |= 1u << ((ny + 32) & 31);
+          pl1[(size_t)(ny + 1) * G.W[1] + ((uint32_t)(nx + 32) >> 5)] |= 1u << ((nx + 32) & 31);
+          // rank order == (label, x, y)
+          const uint64_t key = ((uint64_t)l << 44) | ((uint64_t)nx << 22) | (uint64_t)ny;
+          entries.push_back({key, (uint32_t)i});
+        }
+      }
+    }
+  }
+  std::sort(entries.begin(), entries.end(), [](const Entry &a, const Entry &b) {
+    return a.key != b.key ? a.key < b.key : a.ref < b.ref;
+  });
+  if (entries.size() >= (1ull << 32)) { err = "candidate lists exceed 2^32 entries"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  R.cand.resize(entries.size());
+  for (size_t e = 0; e < entries.size(); e++) {
+    if (e == 0 || entries[e].key != entries[e - 1].key) { R.cellinfo.push_back((uint32_t)e); R.cellinfo.push_back(0u); }
+    R.cellinfo.back()++;
+    R.cand[e] = entries[e].ref;
+  }
+  // prefix popcounts over the dir-0 planes, label-major (== rank order of the marked cells)
+  uint32_t running = 0;
+  for (int l = 0; l < n_labels; l++) {
+    const uint32_t *pl0 = R.bitmap.data() + (size_t)l * G.label_stride;
+    uint32_t *pf = R.prefix.data() + (size_t)l * G.plane_words[0];
+    for (uint32_t w = 0; w < G.plane_words[0]; w++) { pf[w] = running; running += (uint32_t)__builtin_popcount(pl0[w]); }
+  }
+  if ((size_t)running * 2 != R.cellinfo.size()) { err = "internal: rank / cell list mismatch"; return SLIDE_PR_ERR_INTERNAL; }
+  if (R.cellinfo.empty()) { R.cellinfo.assign(2, 0u); }
+  if (R.cand.empty()) R.cand.assign(1, 0u);
+  return SLIDE_PR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// query set: drop labels absent from the reference, sort by (label, Morton cell)
+// ------------------------------------------------------------------------------------------
+static inline uint32_t part1by1(uint32_t x) {
+  x &= 0xffffu;
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+
+int build_query_set(const RefIndex &R, const double *qry7, int n_qry, QuerySet &Q, std::string &err) {
+  Q = QuerySet();
+  const int n_labels = (int)R.labels.size();
+  struct Item { int l; uint32_t morton; int j; };
+  std::vector<Item> items;
+  double minx = HUGE_VAL, maxx = -HUGE_VAL, miny = HUGE_VAL, maxy = -HUGE_VAL;
+  for (int j = 0; j < n_qry; j++) {
+    const double *q = qry7 + 7 * (size_t)j;
+    if (!std::isfinite(q[1]) || !std::isfinite(q[2])) { err = "non-finite query coordinate"; return SLIDE_PR_ERR_NONFINITE; }
+    minx = std::min(minx, q[1]); maxx = std::max(maxx, q[1]);
+    miny = std::min(miny, q[2]); maxy = std::max(maxy, q[2]);
+  }
+  const double sx = maxx > minx ? 65535.0 / (maxx - minx) : 0.0, sy = maxy > miny ? 65535.0 / (maxy - miny) : 0.0;
+  for (int j = 0; j < n_qry; j++) {
+    const double *q = qry7 + 7 * (size_t)j;
+    if (!(q[0] == q[0])) continue;
+    const double lab = q[0] + 0.0;
+    auto it = std::lower_bound(R.labels.begin(), R.labels.end(), lab);
+    if (it == R.labels.end() || *it != lab) continue;  // no reference object can ever match it
+    const uint32_t mx = (uint32_t)((q[1] - minx) * sx), my = (uint32_t)((q[2] - miny) * sy);
+    items.push_back({(int)(it - R.labels.begin()), part1by1(mx) | (part1by1(my) << 1), j});
+  }
+  std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
+    if (a.l != b.l) return a.l < b.l;
+    if (a.morton != b.morton) return a.morton < b.morton;
+    return a.j < b.j;
+  });
+  Q.nq = (int)items.size();
+  Q.orig.resize(std::max(Q.nq, 1));
+  Q.qxy.resize(2 * (size_t)std::max(Q.nq, 1));
+  Q.qdims.resize(3 * (size_t)std::max(Q.nq, 1));
+  Q.label_seg.assign(n_labels + 1, 0);
+  for (int s = 0; s < Q.nq; s++) {
+    const double *q = qry7 + 7 * (size_t)items[s].j;
+    Q.orig[s] = items[s].j;
+    Q.qxy[2 * (size_t)s] = q[1]; Q.qxy[2 * (size_t)s + 1] = q[2];
+    Q.qdims[3 * (size_t)s] = q[4]; Q.qdims[3 * (size_t)s + 1] = q[5]; Q.qdims[3 * (size_t)s + 2] = q[6];
+    Q.label_seg[items[s].l + 1]++;
+  }
+  for (int l = 0; l < n_labels; l++) Q.label_seg[l + 1] += Q.label_seg[l];
+  return SLIDE_PR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// closed-form refinement (PlaceRecognition::solveLSQ, PR.cpp:632-695)
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Givens { double c, s; };  // [[c, s], [-s, c]]
+inline Givens compose(Givens a, Givens b) { return {a.c * b.c - a.s * b.s, a.c * b.s + a.s * b.c}; }
+inline Givens inverse(Givens a) { return {a.c, -a.s}; }
+inline void left(double *M, int n, int p, int q, Givens g) {
+  for (int i = 0; i < n; i++) {
+    const double x = M[p * n + i], y = M[q * n + i];
+    M[p * n + i] = g.c * x + g.s * y;
+    M[q * n + i] = g.c * y - g.s * x;
+  }
+}
+inline void right(double *M, int n, int p, int q, Givens g) {
+  for (int i = 0; i < n; i++) {
+    const double x = M[i * n + p], y = M[i * n + q];
+    M[i * n + p] = g.c * x - g.s * y;
+    M[i * n + q] = g.s * x + g.c * y;
+  }
+}
+// rotation diagonalising the symmetric 2x2 [[x, y], [y, z]]
+inline Givens symmetric_schur(double x, double y, double z) {
+  if (2.0 * std::fabs(y) < DBL_MIN) return {1.0, 0.0};
+  const double tau = (x - z) / (2.0 * std::fabs(y));
+  const double w = std::sqrt(tau * tau + 1.0);
+  const double t = tau > 0 ? 1.0 / (tau + w) : 1.0 / (tau - w);
+  const double n = 1.0 / std::sqrt(t * t + 1.0);
+  const double sgn = t > 0 ? 1.0 : -1.0;
+  return {n, -sgn * (y / std::fabs(y)) * std::fabs(t) * n};
+}
+}  // namespace
+
+// Two-sided (Kogbetliantz) Jacobi SVD, n <= 3, row-major: A = U diag(S) V^T, S descending.
+// Zero off-diagonal blocks are never rotated, so a planar (z == 0) cross-covariance keeps
+// U(2,2) = V(2,2) = 1 -- the property the reference's reflection test (PR.cpp:680) sees with
+// Eigen::JacobiSVD.
+void svd_jacobi(const double *A, int n, double *U, double *S, double *V) {
+  double M[9];
+  double scale = 0;
+  for (int i = 0; i < n * n; i++) scale = std::max(scale, std::fabs(A[i]));
+  if (scale == 0) scale = 1;
+  for (int i = 0; i < n * n; i++) { M[i] = A[i] / scale; U[i] = 0; V[i] = 0; }
+  for (int i = 0; i < n; i++) U[i * n + i] = V[i * n + i] = 1;
+  double big = 0;
+  for (int i = 0; i < n; i++) big = std::max(big, std::fabs(M[i * n + i]));
+  bool again = true;
+  for (int sweep = 0; sweep < 200 && again; sweep++) {
+    again = false;
+    for (int p = 1; p < n; p++)
+      for (int q = 0; q < p; q++) {
+        const double tol = std::max(DBL_MIN, 2.0 * DBL_EPSILON * big);
+        if (!(std::fabs(M[p * n + q]) > tol || std::fabs(M[q * n + p]) > tol)) continue;
+        again = true;
+        const double m00 = M[p * n + p], m01 = M[p * n + q], m10 = M[q * n + p], m11 = M[q * n + q];
+        Givens sym{1.0, 0.0};  // first make the 2x2 block symmetric
+        const double d = m10 - m01;
+        if (std::fabs(d) >= DBL_MIN) {
+          const double u = (m00 + m11) / d, h = std::sqrt(1.0 + u * u);
+          sym = {u / h, 1.0 / h};
+        }
+        const double s00 = sym.c * m00 + sym.s * m10, s01 = sym.c * m01 + sym.s * m11;
+        const double s11 = sym.c * m11 - sym.s * m01;
+        const Givens jr = symmetric_schur(s00, s01, s11);
+        const Givens jl = compose(sym, inverse(jr));
+        left(M, n, p, q, jl);
+        right(U, n, p, q, inverse(jl));
+        right(M, n, p, q, jr);
+        right(V, n, p, q, jr);
+        big = std::max(big, std::max(std::fabs(M[p * n + p]), std::fabs(M[q * n + q])));
+      }
+  }
+  for (int i = 0; i < n; i++) {
+    const double a = M[i * n + i];
+    S[i] = std::fabs(a) * scale;
+    if (a < 0) for (int r = 0; r < n; r++) U[r * n + i] = -U[r * n + i];
+  }
+  for (int i = 0; i < n; i++) {
+    int pos = i;
+    for (int k = i + 1; k < n; k++) if (S[k] > S[pos]) pos = k;
+    if (S[pos] == 0) break;
+    if (pos == i) continue;
+    std::swap(S[i], S[pos]);
+    for (int r = 0; r < n; r++) { std::swap(U[r * n + i], U[r * n + pos]); std::swap(V[r * n + i], V[r * n + pos]); }
+  }
+}
+
+void xyz_yaw_from_tf(const double *tf16, double *xyz_yaw4) {  // PR.cpp:697-711
+  xyz_yaw4[0] = tf16[3]; xyz_yaw4[1] = tf16[7]; xyz_yaw4[2] = tf16[11];
+  xyz_yaw4[3] = std::atan2(tf16[4], tf16[0]);
+}
+
+static void mul_abt3(const double *A, const double *B, double *C) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) C[i * 3 + j] = A[i * 3] * B[j * 3] + A[i * 3 + 1] * B[j * 3 + 1] + A[i * 3 + 2] * B[j * 3 + 2];
+}
+
+void solve_lsq(const double *tgt3, const double *src3, int k, double *xyz_yaw4, double *tf16) {
+  double cs[3] = {0, 0, 0}, ct[3] = {0, 0, 0};
+  for (int i = 0; i < k; i++)
+    for (int d = 0; d < 3; d++) { cs[d] += src3[3 * i + d]; ct[d] += tgt3[3 * i + d]; }
+  for (int d = 0; d < 3; d++) { cs[d] /= (double)k; ct[d] /= (double)k; }      // PR.cpp:655-658
+  double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < k; i++)                                                   // PR.cpp:665-671
+    for (int a = 0; a < 3; a++) {
+      const double sa = src3[3 * i + a] - cs[a];
+      for (int b = 0; b < 3; b++) H[a * 3 + b] += sa * (tgt3[3 * i + b] - ct[b]);
+    }
+  double U[9], S[3], V[9], Rm[9];
+  svd_jacobi(H, 3, U, S, V);                                                    // PR.cpp:674
+  mul_abt3(V, U, Rm);                                                           // PR.cpp:678
+  const double det = Rm[0] * (Rm[4] * Rm[8] - Rm[5] * Rm[7]) - Rm[1] * (Rm[3] * Rm[8] - Rm[5] * Rm[6]) +
+                     Rm[2] * (Rm[3] * Rm[7] - Rm[4] * Rm[6]);
+  if (det < 0) {                                                                // PR.cpp:680-686
+    double U2[9], S2[3], V2[9];
+    svd_jacobi(Rm, 3, U2, S2, V2);
+    for (int r = 0; r < 3; r++) V2[r * 3 + 2] = -V2[r * 3 + 2];
+    mul_abt3(V2, U2, Rm);
+  }
+  for (int i = 0; i < 16; i++) tf16[i] = 0;
+  for (int a = 0; a < 3; a++) {
+    for (int b = 0; b < 3; b++) tf16[a * 4 + b] = Rm[a * 3 + b];
+    tf16[a * 4 + 3] = ct[a] - (Rm[a * 3] * cs[0] + Rm[a * 3 + 1] * cs[1] + Rm[a * 3 + 2] * cs[2]);  // PR.cpp:689
+  }
+  tf16[15] = 1;
+  xyz_yaw_from_tf(tf16, xyz_yaw4);
+}
+
+void mat4_mul(const double *A, const double *B, double *C) {
+  double T[16];
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      double acc = 0;
+      for (int k = 0; k < 4; k++) acc += A[i * 4 + k] * B[k * 4 + j];
+      T[i * 4 + j] = acc;
+    }
+  std::memcpy(C, T, sizeof(T));
+}
+
+bool mat4_rigid_inverse(const double *A, double *Ainv) {
+  // [R t; 0 1]^-1 = [R^T  -R^T t; 0 1]
+  double T[16] = {0};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) T[i * 4 + j] = A[j * 4 + i];
+  for (int i = 0; i < 3; i++) T[i * 4 + 3] = -(T[i * 4] * A[3] + T[i * 4 + 1] * A[7] + T[i * 4 + 2] * A[11]);
+  T[15] = 1;
+  std::memcpy(Ainv, T, sizeof(T));
+  return true;
+}
+
+}  // namespace spr

@@ -1,0 +1,79 @@
+// spr_host.h -- host side of the place-recognition search: lattice enumeration, chunking,
+// label bucketing, occupancy bitmaps and candidate lists, closed-form refinement.
+// Pure C++ (no CUDA) so the index structures can be unit-tested on a CPU-only box.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/slide_pr.h"
+#include "spr_types.h"
+
+namespace spr {
+
+struct Lattice {
+  int status = 0;                 // 0 ok, SLIDE_PR_SANITY_RETURN on PR.cpp:169-175
+  int rings = 0;
+  double ox = 0, oy = 0;          // outer_loop_step_size_{x,y}
+  std::vector<double> yaw;        // PR.cpp:136-146
+  std::vector<double> cs;         // cos, sin per yaw (libm)
+  std::vector<double> lat;        // per ring: xs then ys
+  struct Ring {
+    uint32_t x_off, nx, y_off, ny;  // into lat
+    int ixl, ixh, iyl, iyh;         // inner (already searched) box as closed index ranges; empty if l > h
+    uint64_t ord_base;              // ordinal of the ring's first translation
+    uint64_t count;                 // translations in the ring
+    uint32_t chunk_begin, chunk_end;
+  };
+  std::vector<Ring> ring;
+  uint64_t n_translations = 0;
+  std::vector<SprChunk> chunks;   // ring-major
+};
+
+// PR.cpp:136-241.  yaw_half is match_yaw_half_range_ (inter) or the intra value.
+// trans_begin/trans_end (end < 0: none) restrict the valid bits to a range of ordinals.
+int build_lattice(const slide_pr_params &p, double half_x, double half_y, double yaw_half,
+                  int64_t trans_begin, int64_t trans_end, Lattice &L, std::string &err);
+
+// translation (x, y) of a canonical ordinal; false if out of range
+bool translation_of(const Lattice &L, uint64_t ordinal, double *x, double *y, int *ring);
+
+struct RefIndex {
+  std::vector<double> labels;       // distinct finite reference labels, ascending
+  std::vector<double> ref_xy;       // [n_ref][2]
+  std::vector<double> ref_dims;     // [n_ref][3]
+  SprGrid grid{};
+  std::vector<uint32_t> bitmap;     // [n_labels][plane0 | plane1]
+  std::vector<uint32_t> prefix;     // [n_labels][plane_words[0]]
+  std::vector<uint32_t> cellinfo;   // [n_cells][2]
+  std::vector<uint32_t> cand;
+  double Tstar = 0, Sstar = 0;
+  int n_ref = 0;
+};
+
+// reach: max |coordinate| any transformed query point or translation can take (metres);
+// fixes the fixed-point format.  Returns SLIDE_PR_OK or an error code.
+int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, double reach,
+                    RefIndex &R, std::string &err);
+
+struct QuerySet {
+  int nq = 0;                       // kept queries
+  std::vector<int32_t> orig;        // [nq] original index
+  std::vector<double> qxy;          // [nq][2]
+  std::vector<double> qdims;        // [nq][3]
+  std::vector<int32_t> label_seg;   // [n_labels + 1]
+};
+int build_query_set(const RefIndex &R, const double *qry7, int n_qry, QuerySet &Q, std::string &err);
+
+// thresholds: sqrt(d2) < thr <=> d2 < Tstar ; (s / 3) < thr_dim <=> s < Sstar
+double sqrt_threshold(double thr);
+double div3_threshold(double thr_dim);
+
+// PlaceRecognition::solveLSQ (PR.cpp:632-695) / getxyzYawfromTF (PR.cpp:697-711)
+void solve_lsq(const double *tgt3, const double *src3, int k, double *xyz_yaw4, double *tf16);
+void xyz_yaw_from_tf(const double *tf16, double *xyz_yaw4);
+void svd_jacobi(const double *A, int n, double *U, double *S, double *V);
+void mat4_mul(const double *A, const double *B, double *C);
+bool mat4_rigid_inverse(const double *A, double *Ainv);
+
+}  // namespace spr

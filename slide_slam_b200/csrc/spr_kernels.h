@@ -1,0 +1,43 @@
+// spr_kernels.h -- launch wrappers of the sm_100a kernels (spr_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "spr_types.h"
+
+struct SprLaunch {
+  uint32_t chunk_begin, chunk_end;  // chunks scored by this launch (ring range or everything)
+  int32_t  shard_index, shard_count;
+  unsigned long long *best_key;     // device: running max of spr_make_key
+  int32_t *counts_out;              // device, optional: [(ordinal - ord_begin) * n_yaw + iyaw]
+  long long counts_cap;
+  unsigned long long ord_begin;
+  unsigned long long *stats;        // device, optional: [0] filter hits, [1] verified inliers
+};
+
+enum { SPR_VARIANT_DIRECT = 0, SPR_VARIANT_QUEUED = 1 };
+
+// rotated query coordinates for every yaw: exact fp64 + fixed-point cell units (PR.cpp:246-258)
+cudaError_t spr_launch_rotate(const SprView &V, int32_t *qrotq, double *qrot, cudaStream_t st);
+
+// the lattice search: every hypothesis of the chunks gets its exact inlier count
+cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int variant, int sm_count,
+                                     cudaStream_t st, int *n_launches);
+
+// explicit hypothesis list (c, s, x, y), warp per hypothesis
+cudaError_t spr_launch_score_list(const SprView &V, const double *hyps4, long long n, int32_t *counts_out,
+                                  unsigned long long *best_key, int sm_count, cudaStream_t st);
+
+// correspondences of one hypothesis by brute force over the raw maps, in the reference's own
+// order (PR.cpp:281-357): match_ref[j] = first matching reference index or -1
+cudaError_t spr_launch_extract(const double *ref7, int n_ref, const double *qry7, int n_qry, double c,
+                               double s, double tx, double ty, double Tstar, double Sstar, double thr_dim,
+                               int ignore_dim, int32_t *match_ref, cudaStream_t st);
+
+// SlideGraph descriptor half (semantic_clipper.cpp:49-118)
+cudaError_t spr_launch_tri_desc(const double *tris6, int t, double *desc, int32_t *perm, cudaStream_t st);
+// fill == false: per-model-triangle match counts + exclusive scan (offsets, *total);
+// fill == true : writes (model_idx, data_idx) of every match at its reference-order position
+cudaError_t spr_launch_tri_match(const double *dm, int tm, const double *dd, int td, double thr,
+                                 unsigned long long *counts, unsigned long long *offsets, unsigned long long *total,
+                                 int32_t *model_idx, int32_t *data_idx, long long cap, bool fill, int sm_count,
+                                 cudaStream_t st);

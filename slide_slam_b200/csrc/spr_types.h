@@ -1,0 +1,85 @@
+// spr_types.h -- POD types shared by the host index builder and the CUDA kernels.
+//
+// Vocabulary (follows the reference, place_recognition.cpp:98-387):
+//   reference map / query map : the two object maps handed to MatchMaps
+//   hypothesis                : one (yaw, x, y) sample of the search lattice
+//   translation               : one (x, y) lattice sample; its "ordinal" is its position in the
+//                               reference's enumeration order ring -> x -> y (PR.cpp:178,230,232)
+//   chunk                     : 32 consecutive lattice samples along one axis at a fixed value of
+//                               the other axis -- the unit one thread scores bit-parallel
+//   occupancy bitmap          : per label, 1 bit per cell of edge c = match_xy_step_size_, set when
+//                               a reference landmark of that label can be within match_threshold_
+//                               of a point falling in the cell (conservative)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SPR_HD __host__ __device__ __forceinline__
+#else
+#define SPR_HD inline
+#endif
+
+struct SprChunk {        // 32 bytes
+  double   across;       // exact fp64 value of the fixed coordinate (x if dir == 0, y if dir == 1)
+  uint32_t along_off;    // index into lat[] of the lattice sample under bit 0
+  uint32_t valid;        // bit b set <=> sample b is a hypothesis to score
+  uint32_t ord_base;     // translation ordinal of bit 0; ordinal(b) = ord_base + b * ord_stride
+  uint32_t ord_stride;
+  uint32_t dir;          // 0: bits run along y; 1: bits run along x
+  uint32_t ring;
+};
+
+struct SprGrid {
+  double  g0x, g0y;      // cell (0,0) covers [g0x, g0x + c) x [g0y, g0y + c)
+  double  S;             // 2^F / c : metres -> fixed-point cell units
+  int32_t F;             // fractional bits of the fixed-point cell coordinates
+  int32_t GX, GY;        // cells along x and y
+  int32_t R[2];          // rows of the plane for dir d (across cells + 2 zero rows)
+  int32_t W[2];          // 32-bit words per row (32 pad bits in front, >= 64 behind)
+  int32_t maxbit[2];     // clamp of the along bit offset: 32 * (W[d] - 2)
+  uint32_t plane_words[2];
+  uint32_t label_stride; // plane_words[0] + plane_words[1]
+};
+
+// Everything the scoring code reads.  Pointers are valid in the executing address space
+// (device pointers for the kernels; host pointers for the test-only emulation).
+struct SprView {
+  const double   *lat;        // lattice samples of every ring (x arrays and y arrays)
+  const SprChunk *chunks;
+  uint32_t        n_chunks;
+  int32_t         n_yaw;
+  const double   *cs;         // [n_yaw][2] cos(yaw), sin(yaw) from host libm (PR.cpp:246-250)
+  int32_t         nq;         // query landmarks kept (label present in the reference), sorted
+  const int32_t  *qrotq;      // [n_yaw][nq][2] fixed-point cell coords of the rotated query
+  const double   *qrot;       // [n_yaw][nq][2] exact fp64 (c*qx + (-s)*qy, s*qx + c*qy)
+  const double   *qxy;        // [nq][2] query x, y (search frame)
+  const double   *qdims;      // [nq][3]
+  const int32_t  *label_seg;  // [n_labels + 1] segments of the sorted queries
+  const int32_t  *qlabel;     // [nq] label bucket of each sorted query
+  int32_t         n_labels;
+  int32_t         n_ref;
+  const double   *ref_xy;     // [n_ref][2]
+  const double   *ref_dims;   // [n_ref][3]
+  const uint32_t *bitmap;     // [n_labels][plane dir0 | plane dir1]
+  const uint32_t *prefix;     // [n_labels][plane_words[0]] set bits before each dir-0 word
+  const uint32_t *cellinfo;   // [n_marked_cells][2] (start, count) into cand
+  const uint32_t *cand;       // reference indices, ascending inside a cell
+  SprGrid         grid;
+  double          Tstar;      // sqrt(d2) < match_threshold_  <=>  d2 < Tstar   (PR.cpp:332-333)
+  double          Sstar;      // (sum / 3) < thr_dim          <=>  sum < Sstar  (PR.cpp:329,338)
+  double          thr_dim;
+  int32_t         ignore_dim;
+  int32_t         pad;
+};
+
+// best-hypothesis key: max() picks the larger inlier count, ties go to the smaller canonical
+// hypothesis index (the reference's strict '>' first-wins rule, PR.cpp:361).  0 == "none".
+#define SPR_KEY_IDX_BITS 40
+#define SPR_KEY_IDX_MASK ((1ULL << SPR_KEY_IDX_BITS) - 1ULL)
+SPR_HD unsigned long long spr_make_key(uint32_t count, unsigned long long hyp_idx) {
+  return ((unsigned long long)(count + 1u) << SPR_KEY_IDX_BITS) | (SPR_KEY_IDX_MASK - hyp_idx);
+}
+SPR_HD int32_t spr_key_count(unsigned long long key) { return (int32_t)(key >> SPR_KEY_IDX_BITS) - 1; }
+SPR_HD long long spr_key_index(unsigned long long key) {
+  return (long long)(SPR_KEY_IDX_MASK - (key & SPR_KEY_IDX_MASK));
+}

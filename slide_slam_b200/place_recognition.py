@@ -1,0 +1,234 @@
+"""Host-side mirror of the reference's `PlaceRecognition` class for the SlideMatch path
+(backend/sloam/include/core/place_recognition.h:31-237), over the C-ABI in include/slide_pr.h.
+
+Same member names, argument meaning and failure behaviour as the reference: maps are
+`n x 7` arrays of `[label, x, y, z, d1, d2, d3]` rows (std::vector<Eigen::Vector7d>), results
+are returned instead of written through out-references, "not found" is `False`, not an
+exception.  All scoring happens in the CUDA library; nothing here computes a match on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+
+# rosparam name under sloam/place_recognition/  ->  (Params field, converter)   PR.cpp:24-75
+_ROSPARAMS = {
+    "compute_budget_sec": ("compute_budget_sec", float),
+    "dilation_factor": ("dilation_factor", float),
+    "search_xy_step_size": ("match_xy_step_size", float),
+    "match_yaw_half_range": ("match_yaw_half_range", "deg"),
+    "disable_yaw_search": ("disable_yaw_search", int),
+    "search_yaw_step_size_degrees": ("match_yaw_angle_step_size", "deg"),
+    "match_threshold_position": ("match_threshold", float),
+    "match_threshold_dimension": ("match_threshold_dimension", float),
+    "ignore_dimension": ("ignore_dimension", int),
+    "min_num_inliers": ("min_num_inliers", int),
+    "use_nonlinear_least_squares": ("use_lsq", int),
+    "min_num_map_objects_to_start": ("min_num_map_objects_to_start", int),
+    "match_x_half_range_intra": ("match_x_half_range_intra", float),
+    "match_y_half_range_intra": ("match_y_half_range_intra", float),
+    "match_yaw_half_range_intra": ("match_yaw_half_range_intra", "deg"),
+}
+
+
+@dataclass
+class MatchMapsResult:
+    """Outputs of MatchMaps (PR.h:70-74)."""
+    status: int
+    R_t: np.ndarray                 # 3x3
+    best_num_inliers: int
+    map_objects_matched: np.ndarray        # k x 4 [label, x, y, z] rows of the reference map
+    detection_objects_matched: np.ndarray  # k x 4 rows of the (un-transformed) query map
+    ref_idx: np.ndarray
+    qry_idx: np.ndarray
+    info: capi.MatchResult
+
+
+class PlaceRecognition:
+    """Drop-in for the reference class on the SlideMatch path.  `params` uses the rosparam names
+    of place_recognition.cpp:24-75 (angles in degrees, like the yaml files)."""
+
+    def __init__(self, params: dict | None = None, device: int = -1):
+        self._lib = capi.lib()
+        self._p = capi.default_params()
+        self._p.device = device
+        # public members of the reference class (PR.h:34-43)
+        self.visualize_matching_results = False
+        self.min_loop_closure_overlap_percentage_ = 0.1
+        for k, v in (params or {}).items():
+            if k in ("visualize_matching_results", "min_loop_closure_overlap_percentage"):
+                continue
+            if k not in _ROSPARAMS:
+                raise KeyError(f"unknown place_recognition rosparam {k!r}")
+            field, conv = _ROSPARAMS[k]
+            setattr(self._p, field, self._lib.slide_pr_deg2rad(float(v)) if conv == "deg" else conv(v))
+        h = C.c_void_p()
+        rc = self._lib.slide_pr_create(C.byref(self._p), C.byref(h))
+        if rc != capi.OK:
+            raise capi.SlidePrError(rc, self._lib.slide_pr_last_error(None).decode())
+        self._h = h
+
+    # -- public mutable members, forwarded to the handle ------------------------------------
+    @property
+    def use_lsq(self) -> bool:
+        return bool(self._p.use_lsq)
+
+    @use_lsq.setter
+    def use_lsq(self, v: bool):
+        self._p.use_lsq = int(bool(v))
+        self._lib.slide_pr_set_params(self._h, C.byref(self._p))
+
+    @property
+    def inter_loop_closure(self) -> bool:
+        return bool(self._p.inter_loop_closure)
+
+    @inter_loop_closure.setter
+    def inter_loop_closure(self, v: bool):
+        self._p.inter_loop_closure = int(bool(v))
+        self._lib.slide_pr_set_params(self._h, C.byref(self._p))
+
+    @property
+    def params(self) -> capi.Params:
+        return self._p
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.slide_pr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc < 0:
+            raise capi.SlidePrError(rc, self._lib.slide_pr_last_error(self._h).decode())
+        return rc
+
+    # -- PlaceRecognition::MatchMaps (PR.cpp:98-387) ----------------------------------------
+    def MatchMaps(self, reference_objects, query_objects, match_x_half_range: float,
+                  match_y_half_range: float) -> MatchMapsResult:
+        """The half ranges are the members findTransformation sets before calling MatchMaps
+        (PR.cpp:786-787 / 808-809)."""
+        ref, qry = capi.as_rows7(reference_objects), capi.as_rows7(query_objects)
+        ri = np.zeros(max(len(qry), 1), np.int32)
+        qi = np.zeros(max(len(qry), 1), np.int32)
+        res = capi.MatchResult()
+        self._check(self._lib.slide_pr_match_maps(self._h, capi.dptr(ref), len(ref), capi.dptr(qry), len(qry),
+                                                  float(match_x_half_range), float(match_y_half_range),
+                                                  capi.iptr(ri), capi.iptr(qi), C.byref(res)))
+        k = max(res.n_matched, 0)
+        ri, qi = ri[:k].copy(), qi[:k].copy()
+        return MatchMapsResult(
+            status=res.status, R_t=np.array(res.R_t[:]).reshape(3, 3), best_num_inliers=res.best_num_inliers,
+            map_objects_matched=ref[ri][:, :4].copy() if k else np.zeros((0, 4)),
+            detection_objects_matched=qry[qi][:, :4].copy() if k else np.zeros((0, 4)),
+            ref_idx=ri, qry_idx=qi, info=res)
+
+    # -- staged form (sharded search) ---------------------------------------------------------
+    def prepare(self, reference_objects, query_objects, half_x: float, half_y: float):
+        ref, qry = capi.as_rows7(reference_objects), capi.as_rows7(query_objects)
+        self._check(self._lib.slide_pr_prepare(self._h, capi.dptr(ref), len(ref), capi.dptr(qry), len(qry),
+                                               float(half_x), float(half_y)))
+        self._n_qry = len(qry)
+
+    def lattice_info(self):
+        """(n_translations, n_yaw, n_rings) of the prepared lattice (PR.cpp:136-241)."""
+        nt, ny, nr = C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.slide_pr_lattice_info(self._h, C.byref(nt), C.byref(ny), C.byref(nr)))
+        return nt.value, ny.value, nr.value
+
+    def search(self, trans_begin: int = 0, trans_end: int = -1, shard_index: int = 0, shard_count: int = 1,
+               want_counts: bool = False, stream: int | None = None, collect_stats: bool = False):
+        o = capi.SearchOpts()
+        o.trans_begin, o.trans_end, o.shard_index, o.shard_count = trans_begin, trans_end, shard_index, shard_count
+        o.stream = stream
+        o.collect_stats = int(collect_stats)
+        counts = None
+        res = capi.MatchResult()
+        if want_counts:
+            if trans_end < 0:
+                raise ValueError("want_counts needs an explicit trans_end")
+            n_trans, n_yaw = self.lattice_info()[:2]
+            n_t = max(min(trans_end, n_trans) - trans_begin, 0)
+            counts = np.full(max(n_t * max(n_yaw, 1), 1), -1, np.int32)
+            o.counts_out = capi.iptr(counts)
+            o.counts_cap = counts.size
+        self._check(self._lib.slide_pr_search(self._h, C.byref(o), C.byref(res)))
+        if counts is not None:
+            counts = counts[: max(min(trans_end, res.n_translations) - trans_begin, 0) * res.n_yaw]
+        return res, counts
+
+    def extract(self, hyp_index: int, res: capi.MatchResult | None = None):
+        res = res or capi.MatchResult()
+        ri = np.zeros(max(self._n_qry, 1), np.int32)
+        qi = np.zeros(max(self._n_qry, 1), np.int32)
+        self._check(self._lib.slide_pr_extract(self._h, int(hyp_index), capi.iptr(ri), capi.iptr(qi), C.byref(res)))
+        k = max(res.n_matched, 0)
+        return res, ri[:k].copy(), qi[:k].copy()
+
+    def score_hypotheses(self, hyps4, want_counts: bool = True):
+        hyps = np.ascontiguousarray(hyps4, np.float64).reshape(-1, 4)
+        counts = np.zeros(max(len(hyps), 1), np.int32) if want_counts else None
+        res = capi.MatchResult()
+        self._check(self._lib.slide_pr_score_hypotheses(self._h, capi.dptr(hyps), len(hyps),
+                                                        capi.iptr(counts) if want_counts else None, C.byref(res)))
+        return res, (counts[: len(hyps)] if want_counts else None)
+
+    # -- PlaceRecognition::findTransformation (PR.cpp:736-945) ---------------------------------
+    def findTransformation(self, reference_objects, query_objects):
+        """Returns (found, xyzYaw[4], transform_out 4x4, TfResult, ref_idx, qry_idx)."""
+        ref, qry = capi.as_rows7(reference_objects), capi.as_rows7(query_objects)
+        ri = np.zeros(max(len(qry), 1), np.int32)
+        qi = np.zeros(max(len(qry), 1), np.int32)
+        out = capi.TfResult()
+        rc = self._check(self._lib.slide_pr_find_transformation(self._h, capi.dptr(ref), len(ref), capi.dptr(qry),
+                                                                len(qry), capi.iptr(ri), capi.iptr(qi), C.byref(out)))
+        k = max(out.n_matched, 0)
+        return (rc == capi.OK, np.array(out.xyz_yaw[:]), np.array(out.transform[:]).reshape(4, 4), out,
+                ri[:k].copy(), qi[:k].copy())
+
+    # -- PlaceRecognition::findInterLoopClosure (PR.cpp:498-538) --------------------------------
+    def findInterLoopClosure(self, reference_objects, query_objects):
+        """Returns (closure_found, tfFromQueryToRef 4x4)."""
+        ref, qry = capi.as_rows7(reference_objects), capi.as_rows7(query_objects)
+        tf = np.zeros(16)
+        out = capi.TfResult()
+        rc = self._check(self._lib.slide_pr_find_inter_loop_closure(self._h, capi.dptr(ref), len(ref), capi.dptr(qry),
+                                                                    len(qry), capi.dptr(tf), C.byref(out)))
+        self.last = out
+        return rc == capi.OK, tf.reshape(4, 4)
+
+    # -- PlaceRecognition::findIntraLoopClosure (PR.cpp:389-496) --------------------------------
+    def findIntraLoopClosure(self, measurements, submap, query_pose, candidate_pose):
+        """Poses are 4x4 matrices (SE3::matrix()).  Returns (closure_found, tfFromQuery2Candidate)."""
+        meas, sub = capi.as_rows7(measurements), capi.as_rows7(submap)
+        qp = np.ascontiguousarray(query_pose, np.float64).reshape(16)
+        cp = np.ascontiguousarray(candidate_pose, np.float64).reshape(16)
+        tf = np.zeros(16)
+        out = capi.TfResult()
+        rc = self._check(self._lib.slide_pr_find_intra_loop_closure(self._h, capi.dptr(meas), len(meas), capi.dptr(sub),
+                                                                    len(sub), capi.dptr(qp), capi.dptr(cp), capi.dptr(tf),
+                                                                    C.byref(out)))
+        self.last = out
+        return rc == capi.OK, tf.reshape(4, 4)
+
+    # -- PlaceRecognition::solveLSQ / getxyzYawfromTF (PR.cpp:632-711) --------------------------
+    def solveLSQ(self, map_objects_matched, detection_objects_matched):
+        tgt = np.ascontiguousarray(map_objects_matched, np.float64).reshape(-1, 3)
+        src = np.ascontiguousarray(detection_objects_matched, np.float64).reshape(-1, 3)
+        xyzyaw, tf = np.zeros(4), np.zeros(16)
+        self._check(self._lib.slide_pr_solve_lsq(capi.dptr(tgt), capi.dptr(src), len(tgt), capi.dptr(xyzyaw), capi.dptr(tf)))
+        return xyzyaw, tf.reshape(4, 4)
+
+    def getxyzYawfromTF(self, tf):
+        tf = np.ascontiguousarray(tf, np.float64).reshape(16)
+        out = np.zeros(4)
+        self._lib.slide_pr_get_xyz_yaw_from_tf(capi.dptr(tf), capi.dptr(out))
+        return out

@@ -1,0 +1,129 @@
+// spr_emu.cpp -- TEST-ONLY single-thread emulation of the lattice scoring kernel.
+//
+// Runs the exact per-thread code of the CUDA kernel (slide_slam_b200/csrc/spr_core.h) over the
+// host-built index structures, one "thread" (chunk) at a time, so that the chunking, ordinals,
+// bitmaps, candidate lists and fixed-point probing can be checked against the CPU oracle on a
+// box without a GPU.  It is compiled only by tests/ and is not part of the product library.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../slide_slam_b200/csrc/spr_core.h"
+#include "../../slide_slam_b200/csrc/spr_host.h"
+
+extern "C" int spr_emu_match_maps(const slide_pr_params *p, const double *ref7, int n_ref,
+                                  const double *qry7, int n_qry, double half_x, double half_y,
+                                  long long trans_begin, long long trans_end, int *counts_out,
+                                  long long counts_cap, int *best_count, long long *best_index,
+                                  long long *hyps_scored, long long *filter_hits, char *errbuf, int errcap) {
+  std::string err;
+  spr::Lattice L;
+  const double yaw_half = p->inter_loop_closure ? p->match_yaw_half_range : p->match_yaw_half_range_intra;
+  int rc = spr::build_lattice(*p, half_x, half_y, yaw_half, trans_begin, trans_end, L, err);
+  auto fail = [&](int code) { if (errbuf && errcap > 0) { strncpy(errbuf, err.c_str(), errcap - 1); errbuf[errcap - 1] = 0; } return code; };
+  if (rc != SLIDE_PR_OK) return fail(rc);
+  *best_count = -10000; *best_index = -1; *hyps_scored = 0; *filter_hits = 0;
+  if (L.status == SLIDE_PR_SANITY_RETURN) return SLIDE_PR_SANITY_RETURN;
+  double qrad = 0;
+  for (int j = 0; j < n_qry; j++) qrad = std::max(qrad, std::hypot(qry7[7 * j + 1], qry7[7 * j + 2]));
+  spr::RefIndex R;
+  rc = spr::build_ref_index(*p, ref7, n_ref, qrad + std::max(std::fabs(half_x), std::fabs(half_y)) + p->match_xy_step_size, R, err);
+  if (rc != SLIDE_PR_OK) return fail(rc);
+  spr::QuerySet Q;
+  rc = spr::build_query_set(R, qry7, n_qry, Q, err);
+  if (rc != SLIDE_PR_OK) return fail(rc);
+  const int n_yaw = (int)L.yaw.size(), nq = Q.nq;
+  std::vector<double> qrot(2 * (size_t)std::max(1, n_yaw * nq));
+  std::vector<int32_t> qrotq(2 * (size_t)std::max(1, n_yaw * nq));
+  for (int a = 0; a < n_yaw; a++)
+    for (int s = 0; s < nq; s++) {
+      double rx, ry;
+      spr_rotate(L.cs[2 * a], L.cs[2 * a + 1], Q.qxy[2 * s], Q.qxy[2 * s + 1], &rx, &ry);
+      const size_t qi = (size_t)a * nq + s;
+      qrot[2 * qi] = rx; qrot[2 * qi + 1] = ry;
+      qrotq[2 * qi] = spr_fx(rx - R.grid.g0x, R.grid.S);
+      qrotq[2 * qi + 1] = spr_fx(ry - R.grid.g0y, R.grid.S);
+    }
+  SprView V{};
+  V.lat = L.lat.data(); V.chunks = L.chunks.data(); V.n_chunks = (uint32_t)L.chunks.size();
+  V.n_yaw = n_yaw; V.cs = L.cs.data(); V.nq = nq; V.qrotq = qrotq.data(); V.qrot = qrot.data();
+  V.qxy = Q.qxy.data(); V.qdims = Q.qdims.data(); V.label_seg = Q.label_seg.data();
+  V.n_labels = (int)R.labels.size(); V.n_ref = n_ref; V.ref_xy = R.ref_xy.data(); V.ref_dims = R.ref_dims.data();
+  V.bitmap = R.bitmap.data(); V.prefix = R.prefix.data(); V.cellinfo = R.cellinfo.data(); V.cand = R.cand.data();
+  V.grid = R.grid; V.Tstar = R.Tstar; V.Sstar = R.Sstar; V.thr_dim = p->match_threshold_dimension;
+  V.ignore_dim = p->ignore_dimension;
+  const SprGrid &G = V.grid;
+  unsigned long long best = 0;
+  long long scored = 0, hits = 0;
+  const long long tb = trans_begin < 0 ? 0 : trans_begin;
+  for (uint32_t ci = 0; ci < V.n_chunks; ci++) {
+    const SprChunk &ch = V.chunks[ci];
+    const int d = (int)ch.dir;
+    const int32_t aq0 = spr_fx(ch.across, G.S), bq0 = spr_fx(V.lat[ch.along_off], G.S);
+    for (int a = 0; a < n_yaw; a++) {
+      uint32_t cnt[32] = {0};
+      for (int l = 0; l < V.n_labels; l++) {
+        const uint32_t *plane = V.bitmap + (size_t)l * G.label_stride + (d ? G.plane_words[0] : 0);
+        for (int s = V.label_seg[l]; s < V.label_seg[l + 1]; s++) {
+          const size_t qi = (size_t)a * nq + s;
+          const int32_t qx = V.qrotq[2 * qi], qy = V.qrotq[2 * qi + 1];
+          int32_t na, nb;
+          uint32_t H = spr_probe(plane, G.W[d], G.R[d], G.maxbit[d], G.F, aq0 + (d ? qy : qx), bq0 + (d ? qx : qy), ch.valid, &na, &nb);
+          while (H) {
+            const int b = SPR_FFS(H) - 1;
+            H &= H - 1;
+            hits++;
+            int32_t first;
+            if (spr_verify_hit(V, ch, l, a, s, na, nb, b, &first)) cnt[b]++;
+          }
+        }
+      }
+      for (int b = 0; b < 32; b++) {
+        if (!((ch.valid >> b) & 1u)) continue;
+        const unsigned long long ord = (unsigned long long)ch.ord_base + (unsigned long long)b * ch.ord_stride;
+        const unsigned long long h = ord * (unsigned long long)n_yaw + (unsigned long long)a;
+        const unsigned long long key = spr_make_key(cnt[b], h);
+        if (key > best) best = key;
+        scored++;
+        if (counts_out) {
+          const long long slot = ((long long)ord - tb) * n_yaw + a;
+          if (slot >= 0 && slot < counts_cap) counts_out[slot] = (int)cnt[b];
+        }
+      }
+    }
+  }
+  if (best) { *best_count = spr_key_count(best); *best_index = spr_key_index(best); }
+  *hyps_scored = scored; *filter_hits = hits;
+  return SLIDE_PR_OK;
+}
+
+// lattice enumeration through the product's host builder (chunks -> translations), for tests
+extern "C" long long spr_emu_lattice(const slide_pr_params *p, double half_x, double half_y, double *tx, double *ty,
+                                     long long cap, int *n_yaw, double *yaw, int yaw_cap, int *status) {
+  std::string err;
+  spr::Lattice L;
+  const double yaw_half = p->inter_loop_closure ? p->match_yaw_half_range : p->match_yaw_half_range_intra;
+  int rc = spr::build_lattice(*p, half_x, half_y, yaw_half, 0, -1, L, err);
+  *status = rc != SLIDE_PR_OK ? rc : L.status;
+  if (rc != SLIDE_PR_OK || L.status != 0) return -1;
+  *n_yaw = (int)L.yaw.size();
+  for (int i = 0; i < *n_yaw && i < yaw_cap; i++) yaw[i] = L.yaw[i];
+  // every translation must be covered by exactly one chunk bit
+  std::vector<int> seen((size_t)L.n_translations, 0);
+  for (const SprChunk &c : L.chunks)
+    for (int b = 0; b < 32; b++) {
+      if (!((c.valid >> b) & 1u)) continue;
+      const unsigned long long ord = (unsigned long long)c.ord_base + (unsigned long long)b * c.ord_stride;
+      if (ord >= L.n_translations) return -2;
+      seen[ord]++;
+      const double along = L.lat[c.along_off + b];
+      if ((long long)ord < cap) { tx[ord] = c.dir ? along : c.across; ty[ord] = c.dir ? c.across : along; }
+    }
+  for (size_t i = 0; i < seen.size(); i++) if (seen[i] != 1) return -3;
+  // translation_of must agree
+  for (unsigned long long o = 0; o < L.n_translations && (long long)o < cap; o += 1 + L.n_translations / 5000) {
+    double x, y; int ring;
+    if (!spr::translation_of(L, o, &x, &y, &ring) || x != tx[o] || y != ty[o]) return -4;
+  }
+  return (long long)L.n_translations;
+}

@@ -1,0 +1,316 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle and
+the committed golden vectors.  Integer results (inlier counts, correspondences, best hypothesis,
+the winner's R_t entries) are compared bit-exactly; refined transforms within 1e-5 relative."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import spr_helpers as H
+from oracle import pyoracle as O
+from slide_slam_b200 import capi, synth
+from slide_slam_b200.place_recognition import PlaceRecognition
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # BASELINE.json north_star: transform parameters within 1e-5 relative
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return H.golden_maps(), H.golden_cases(), H.golden_counts()
+
+
+def make_pr(params: dict, variant: int | None = None, **members):
+    if variant is not None:
+        os.environ["SLIDE_PR_VARIANT"] = str(variant)
+    else:
+        os.environ.pop("SLIDE_PR_VARIANT", None)
+    pr = PlaceRecognition(H.rosparams_from_golden(params))
+    os.environ.pop("SLIDE_PR_VARIANT", None)
+    if "use_lsq" in params:
+        pr.use_lsq = bool(params["use_lsq"])
+    if "inter_loop_closure" in params:
+        pr.inter_loop_closure = bool(params["inter_loop_closure"])
+    for k, v in members.items():
+        setattr(pr, k, v)
+    return pr
+
+
+ALL_CASES = ["indoor01_sloam_yaml", "indoor01_forest_yaml_nodim", "indoor02_sloam_yaml", "indoor02_forest_yaml_nodim",
+             "indoor12_sloam_yaml", "indoor12_forest_yaml_nodim", "indoor10_sloam_yaml", "indoor10_forest_yaml_nodim",
+             "indoor01_sloam_yaml_nolsq", "indoor01_defaults_2deg", "indoor01_noyaw", "parking01_forest_yaml",
+             "parking02_forest_yaml", "forest01_forest_yaml", "prtest_inter_lsq1", "prtest_intra_lsq1",
+             "prtest_inter_lsq0", "prtest_intra_lsq0", "c1_forest_yaml"]
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_find_transformation_matches_golden(gold, name):
+    maps, cases, _ = gold
+    c = cases[name]
+    pr = make_pr(c["params"])
+    found, xyz_yaw, tf, info, ri, qi = pr.findTransformation(maps[c["ref"]], maps[c["qry"]])
+    assert found == c["found"]
+    assert info.best_num_inliers == c["best_num_inliers"]
+    assert info.match.best_hyp_index == c["best_hyp_index"]
+    assert info.match.hypotheses_scored == c["hypotheses_scored"]
+    assert ri.tolist() == c["ref_idx"] and qi.tolist() == c["qry_idx"]
+    assert list(info.R_t) == c["R_t"]                      # lattice winner: bit-exact
+    assert info.half_x == c["half_x"] and info.half_y == c["half_y"]
+    assert list(info.centroid_ref) == c["centroid_ref"] and list(info.centroid_qry) == c["centroid_qry"]
+    if found:
+        np.testing.assert_allclose(xyz_yaw, c["xyz_yaw"], rtol=RTOL, atol=1e-9)
+        np.testing.assert_allclose(tf.ravel(), c["transform"], rtol=RTOL, atol=1e-9)
+    pr.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_every_hypothesis_count_indoor(gold, variant):
+    maps, cases, counts = gold
+    c = cases["indoor01_forest_yaml_nodim"]
+    ref, qry = H.shifted_maps(maps, c)
+    pr = make_pr(c["params"], variant=variant)
+    pr.prepare(ref, qry, c["half_x"], c["half_y"])
+    nt, ny, _ = pr.lattice_info()
+    res, got = pr.search(0, nt, want_counts=True, collect_stats=True)
+    assert np.array_equal(got, counts["indoor01_forest_yaml_nodim"])
+    assert res.best_hyp_index == c["best_hyp_index"] and res.best_num_inliers == c["best_num_inliers"]
+    assert res.hypotheses_scored == nt * ny and res.filter_hits > 0
+    pr.close()
+
+
+@pytest.mark.parametrize("name", ["parking01_forest_yaml", "c1_forest_yaml", "prtest_inter_lsq1"])
+def test_count_slices_of_large_cases(gold, name):
+    maps, cases, counts = gold
+    c = cases[name]
+    ref, qry = H.shifted_maps(maps, c)
+    pr = make_pr(c["params"])
+    pr.prepare(ref, qry, c["half_x"], c["half_y"])
+    nt, ny, _ = pr.lattice_info()
+    lo, hi = (int(v) for v in counts[name + "__slice"])
+    tb, te = -(-lo // ny), hi // ny
+    res, got = pr.search(tb, te, want_counts=True)
+    assert np.array_equal(got, counts[name][tb * ny - lo: te * ny - lo])
+    assert res.hypotheses_scored == (te - tb) * ny
+    # the slice's own winner must be the first maximum of the slice
+    sl = counts[name][tb * ny - lo: te * ny - lo]
+    assert res.best_num_inliers == int(sl.max()) and res.best_hyp_index == tb * ny + int(np.argmax(sl))
+    pr.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("seed", range(10))
+def test_random_maps_every_hypothesis(seed, variant):
+    rng = np.random.default_rng(100 + seed)
+    n_ref, n_qry = int(rng.integers(1, 60)), int(rng.integers(1, 50))
+    ref, qry = H.random_maps(rng, n_ref, n_qry, extent=float(rng.uniform(3, 15)), n_labels=int(rng.integers(1, 5)),
+                             grid=(0.25 if seed % 3 == 0 else None))
+    step = float(rng.choice([0.25, 0.5, 0.5, 1.0, 0.3]))
+    thr = float(rng.choice([0.5, 0.75, 0.3, 1.1]))
+    kw = dict(match_xy_step_size=step, yaw_step_deg=float(rng.choice([30.0, 45.0, 17.0])), match_threshold=thr,
+              match_threshold_dimension=float(rng.choice([1.0, 0.3])), ignore_dimension=int(seed % 4 == 1),
+              disable_yaw_search=int(seed % 5 == 4))
+    hx = float(rng.uniform(4, 14))
+    hy = hx if seed % 2 else float(rng.uniform(4, 14))
+    op = O.make_params(**kw)
+    want = O.match_maps(op, ref, qry, hx, hy, want_counts=True)
+    pr = make_pr(kw, variant=variant)
+    pr.prepare(ref, qry, hx, hy)
+    nt, ny, _ = pr.lattice_info()
+    res, got = pr.search(0, nt, want_counts=True)
+    assert np.array_equal(got, want["counts"])
+    assert (res.best_num_inliers, res.best_hyp_index) == (want["best_num_inliers"], want["best_hyp_index"])
+    m = pr.MatchMaps(ref, qry, hx, hy)
+    assert m.best_num_inliers == want["best_num_inliers"]
+    assert m.ref_idx.tolist() == want["ref_idx"].tolist() and m.qry_idx.tolist() == want["qry_idx"].tolist()
+    assert m.R_t.ravel().tolist() == want["R_t"].ravel().tolist()
+    # MatchMaps returns the rows themselves (PR.cpp:344-350): reference rows and ORIGINAL query rows
+    assert np.array_equal(m.map_objects_matched, ref[want["ref_idx"]][:, :4].reshape(-1, 4))
+    assert np.array_equal(m.detection_objects_matched, qry[want["qry_idx"]][:, :4].reshape(-1, 4))
+    pr.close()
+
+
+def test_edge_cases_through_the_abi():
+    kw = dict(match_xy_step_size=0.5, yaw_step_deg=45.0)
+    rng = np.random.default_rng(1)
+    ref, qry = H.random_maps(rng, 10, 8, extent=4.0)
+    pr = make_pr(kw)
+    # empty maps: every hypothesis scores 0 and the first one wins (PR.cpp:125,361)
+    for r, q in ((np.zeros((0, 7)), qry), (ref, np.zeros((0, 7))), (np.zeros((0, 7)), np.zeros((0, 7)))):
+        m = pr.MatchMaps(r, q, 6.0, 6.0)
+        want = O.match_maps(O.make_params(**kw), r, q, 6.0, 6.0)
+        assert m.best_num_inliers == 0 and m.info.best_hyp_index == 0 and len(m.ref_idx) == 0
+        assert m.R_t.ravel().tolist() == want["R_t"].ravel().tolist()
+        assert m.info.hypotheses_scored == want["hypotheses_scored"]
+    # sanity-check early return (PR.cpp:169-175) and zero rings (PR.cpp:125)
+    m = pr.MatchMaps(ref, qry, 0.3, 0.3)
+    assert m.status == capi.SANITY_RETURN
+    m = pr.MatchMaps(ref, qry, 0.0, 0.0)
+    assert m.status == 0 and m.best_num_inliers == -10000 and m.info.hypotheses_scored == 0
+    # NaN labels never match; -0.0 == 0.0
+    r3, q3 = ref.copy(), qry.copy()
+    r3[0, 0] = np.nan; q3[0, 0] = np.nan; r3[1, 0] = -0.0; q3[1, 0] = 0.0
+    m = pr.MatchMaps(r3, q3, 6.0, 6.0)
+    want = O.match_maps(O.make_params(**kw), r3, q3, 6.0, 6.0)
+    assert (m.best_num_inliers, m.info.best_hyp_index) == (want["best_num_inliers"], want["best_hyp_index"])
+    assert m.ref_idx.tolist() == want["ref_idx"].tolist()
+    # non-finite coordinates are rejected with an error, not silently scored
+    bad = ref.copy(); bad[0, 1] = np.inf
+    with pytest.raises(capi.SlidePrError):
+        pr.MatchMaps(bad, qry, 6.0, 6.0)
+    # size gate of findInterLoopClosure (PR.cpp:508-510)
+    pr2 = make_pr(dict(kw, min_num_map_objects_to_start=20))
+    assert pr2.findInterLoopClosure(ref, qry)[0] is False
+    pr.close(); pr2.close()
+
+
+def test_inter_and_intra_loop_closure(gold):
+    maps, cases, _ = gold
+    c = cases["prtest_inter_lsq1"]
+    pr = make_pr(c["params"])
+    found, tf = pr.findInterLoopClosure(maps[c["ref"]], maps[c["qry"]])
+    op = O.make_params(**c["params"])
+    wfound, wtf, _ = O.find_inter_loop_closure(op, maps[c["ref"]], maps[c["qry"]], n_threads=-1)
+    assert found and wfound
+    np.testing.assert_allclose(tf, wtf, rtol=RTOL, atol=1e-9)
+    # findIntraLoopClosure(measurements, submap, I, I) (place_recognition_test.cpp:219-226)
+    ci = cases["prtest_intra_lsq1"]
+    pri = make_pr(ci["params"])
+    found, tf = pri.findIntraLoopClosure(maps[ci["qry"]], maps[ci["ref"]], np.eye(4), np.eye(4))
+    assert found
+    x, y, _, yaw = ci["xyz_yaw"]
+    want = np.eye(4)
+    want[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]
+    want[0, 3], want[1, 3] = x, y
+    np.testing.assert_allclose(tf, want, rtol=RTOL, atol=1e-9)
+    # with non-trivial poses: tf = candidate^-1 * query * loop_closure (PR.cpp:478-494)
+    def pose(yaw, t):
+        m = np.eye(4); m[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]; m[:3, 3] = t
+        return m
+    qp, cp = pose(0.3, [1.0, -2.0, 0.1]), pose(-0.2, [0.5, 0.5, 0.0])
+    meas_local = maps[ci["qry"]].copy()
+    inv = np.linalg.inv(qp)
+    meas_local[:, 1:4] = (meas_local[:, 1:4] - qp[:3, 3]) @ inv[:3, :3].T
+    found, tf2 = pri.findIntraLoopClosure(meas_local, maps[ci["ref"]], qp, cp)
+    assert found
+    np.testing.assert_allclose(tf2, np.linalg.inv(cp) @ qp @ want, rtol=1e-4, atol=1e-6)
+    pr.close(); pri.close()
+
+
+def test_budget_path_equals_unlimited(gold):
+    maps, cases, _ = gold
+    c = cases["indoor01_forest_yaml_nodim"]
+    ref, qry = H.shifted_maps(maps, c)
+    pr = PlaceRecognition(dict(H.rosparams_from_golden(c["params"]), compute_budget_sec=3600.0))
+    m = pr.MatchMaps(ref, qry, c["half_x"], c["half_y"])
+    assert m.info.best_hyp_index == c["best_hyp_index"] and m.best_num_inliers == c["best_num_inliers"]
+    assert m.info.rings_scored == m.info.n_rings and m.info.hypotheses_scored == c["hypotheses_scored"]
+    pr.close()
+
+
+def test_sharded_search_merges_to_the_unsharded_result(gold):
+    maps, cases, _ = gold
+    c = cases["parking01_forest_yaml"]
+    ref, qry = H.shifted_maps(maps, c)
+    pr = make_pr(c["params"])
+    pr.prepare(ref, qry, c["half_x"], c["half_y"])
+    lib = capi.lib()
+    for n_shards in (2, 3, 8):
+        recs = (capi.TopkRecord * n_shards)()
+        total = 0
+        for r in range(n_shards):
+            res, _ = pr.search(shard_index=r, shard_count=n_shards)
+            lib.slide_pr_pack_record(C.byref(res), r, C.byref(recs[r]))
+            total += res.hypotheses_scored
+        w = lib.slide_pr_merge_records(recs, n_shards)
+        assert total == c["hypotheses_scored"]
+        assert recs[w].hyp_index == c["best_hyp_index"] and recs[w].inliers == c["best_num_inliers"]
+    res, ri, qi = pr.extract(c["best_hyp_index"])
+    assert ri.tolist() == c["ref_idx"] and qi.tolist() == c["qry_idx"] and list(res.R_t) == c["R_t"]
+    pr.close()
+
+
+def test_score_hypotheses_list():
+    """General (c, s, x, y) hypothesis lists -- the scorer behind pair/triplet-generated
+    candidates -- against the oracle's single-hypothesis scorer (PR.cpp:246-357)."""
+    rng = np.random.default_rng(7)
+    ref, qry = H.random_maps(rng, 80, 60, extent=15.0)
+    kw = dict(match_xy_step_size=0.5, match_threshold=0.6, match_threshold_dimension=0.8)
+    op = O.make_params(**kw)
+    pr = make_pr(kw)
+    pr.prepare(ref, qry, 20.0, 20.0)
+    n = 3000
+    yaw = rng.uniform(-np.pi, np.pi, n)
+    hyps = np.column_stack([np.cos(yaw), np.sin(yaw), rng.uniform(-8, 8, n), rng.uniform(-8, 8, n)])
+    res, got = pr.score_hypotheses(hyps)
+    want = np.array([O.score_one(op, ref, qry, *h)[0] for h in hyps])
+    assert np.array_equal(got, want)
+    assert res.best_num_inliers == want.max() and res.best_hyp_index == int(np.argmax(want))
+    pr.close()
+
+
+def test_triangle_matching_matches_oracle():
+    rng = np.random.default_rng(11)
+    tm = rng.uniform(-30, 30, (700, 6))
+    td = np.vstack([tm[rng.integers(0, 700, 150)] + 0.01 * rng.normal(size=(150, 6)), rng.uniform(-30, 30, (900, 6))])
+    mi, di, _ = O.match_triangles(tm, td, 0.1)
+    pr = make_pr({})
+    lib = capi.lib()
+    cap = len(mi) + 10
+    gm, gd = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    pm, pd = np.zeros(3 * cap, np.int32), np.zeros(3 * cap, np.int32)
+    n = C.c_int64(0)
+    tmc, tdc = np.ascontiguousarray(tm), np.ascontiguousarray(td)
+    rc = lib.slide_pr_match_triangles(pr._h, capi.dptr(tmc), len(tmc), capi.dptr(tdc), len(tdc), 0.1, capi.iptr(gm),
+                                      capi.iptr(gd), capi.iptr(pm), capi.iptr(pd), cap, C.byref(n))
+    assert rc == 0 and n.value == len(mi)
+    assert gm[:n.value].tolist() == mi.tolist() and gd[:n.value].tolist() == di.tolist()  # reference order
+    for k in range(0, n.value, 37):
+        assert pm[3 * k:3 * k + 3].tolist() == O.triangle_descriptor(tm[mi[k]])[1].tolist()
+        assert pd[3 * k:3 * k + 3].tolist() == O.triangle_descriptor(td[di[k]])[1].tolist()
+    pr.close()
+
+
+def test_config2_full_size_properties():
+    """BASELINE config 2 (2000 x 2000, 5 classes, 10 % outliers) at full size, where the oracle is
+    too slow for a full run: size-independent properties + an oracle-checked slice."""
+    ref, qry, truth = synth.config_pair(2)
+    kw = dict(match_xy_step_size=0.5, yaw_step_deg=5.0, match_threshold=0.5, match_threshold_dimension=1.0,
+              ignore_dimension=0, min_num_inliers=15)
+    pr = make_pr(kw)
+    found, xyz_yaw, tf, info, ri, qi = pr.findTransformation(ref, qry)
+    assert found and info.best_num_inliers >= 300
+    # (1) the planted SE(2) offset is recovered (refined transform)
+    assert abs(xyz_yaw[0] - truth["t"][0]) < 0.1 and abs(xyz_yaw[1] - truth["t"][1]) < 0.1
+    assert abs(np.angle(np.exp(1j * (xyz_yaw[3] - truth["yaw"])))) < 0.01
+    # (2) the winner's count equals the reference-order brute-force recount (self-check inside
+    #     slide_pr_match_maps) and the oracle's single-hypothesis scorer
+    op = O.make_params(**kw)
+    sref, sqry = ref.copy(), qry.copy()
+    sref[:, 1:3] -= np.array(info.centroid_ref[:]); sqry[:, 1:3] -= np.array(info.centroid_qry[:])
+    R = np.array(info.R_t[:]).reshape(3, 3)
+    n, ori, oqi = O.score_one(op, sref, sqry, R[0, 0], R[1, 0], R[0, 2], R[1, 2])
+    assert n == info.best_num_inliers and ori.tolist() == ri.tolist() and oqi.tolist() == qi.tolist()
+    # (3) oracle on a slice of translations around the winner: every count identical
+    ny = info.match.n_yaw
+    t_win = info.match.best_hyp_index // ny
+    tb, te = max(t_win - 20, 0), t_win + 20
+    want = O.match_maps(op, sref, sqry, info.half_x, info.half_y, tb * ny, te * ny, want_counts=True)
+    pr.prepare(sref, sqry, info.half_x, info.half_y)
+    res, got = pr.search(tb, te, want_counts=True)
+    assert np.array_equal(got, want["counts"])
+    # (4) sharded == unsharded, direct variant == queued variant
+    best = (info.best_num_inliers, info.match.best_hyp_index)
+    lib = capi.lib()
+    recs = (capi.TopkRecord * 4)()
+    for r in range(4):
+        res, _ = pr.search(shard_index=r, shard_count=4)
+        lib.slide_pr_pack_record(C.byref(res), r, C.byref(recs[r]))
+    w = lib.slide_pr_merge_records(recs, 4)
+    assert (recs[w].inliers, recs[w].hyp_index) == best
+    pr.close()
+    pr0 = make_pr(kw, variant=0)
+    m = pr0.MatchMaps(sref, sqry, info.half_x, info.half_y)
+    assert (m.best_num_inliers, m.info.best_hyp_index) == best
+    pr0.close()
