@@ -82,6 +82,8 @@ typedef struct slide_pr_match_result {
   float   prepare_ms;          /* host time spent building the index structures + H2D enqueue */
   int64_t gpu_launches;        /* kernels launched by this call */
   int64_t filter_hits;         /* bitmap hits verified in fp64 (0 unless stats were enabled) */
+  int64_t h2d_bytes;           /* bytes copied host->device by prepare (+ re-chunking in search) */
+  int64_t d2h_bytes;           /* bytes copied device->host by search/extract */
 } slide_pr_match_result;
 
 /* Options for the sharded / sliced search (multi-GPU and tests). */

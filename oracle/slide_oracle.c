@@ -263,8 +263,7 @@ int slide_oracle_match_maps_mt(const slide_oracle_params *p, const double *ref7,
   long long total = nt * (long long)n_yaw;
   long long hb = hyp_begin < 0 ? 0 : hyp_begin;
   long long he = (hyp_end < 0 || hyp_end > total) ? total : hyp_end;
-  long long t_begin = n_yaw ? hb / n_yaw : 0;
-  long long t_end = n_yaw ? (he + n_yaw - 1) / n_yaw : 0;
+  if (n_yaw <= 0) { hb = 0; he = 0; }
   int best = -10000;
   long long best_h = -1, scored = 0;
 #ifdef _OPENMP
@@ -276,16 +275,14 @@ int slide_oracle_match_maps_mt(const slide_oracle_params *p, const double *ref7,
   {
     int lbest = -10000;
     long long lbest_h = -1, lscored = 0;
-#pragma omp for schedule(dynamic, 64) nowait
-    for (long long t = t_begin; t < t_end; t++) {
-      for (int a = 0; a < n_yaw; a++) {
-        long long h = t * n_yaw + a;
-        if (h < hb || h >= he) continue;
-        int cur = slide_oracle_score_one(p, ref7, n_ref, qry7, n_qry, cs[2 * a], cs[2 * a + 1],
-                                         tx[t], ty[t], NULL, NULL);
-        lscored++;
-        if (cur > lbest || (cur == lbest && h < lbest_h)) { lbest = cur; lbest_h = h; }
-      }
+#pragma omp for schedule(dynamic, 8) nowait
+    for (long long h = hb; h < he; h++) {
+      const long long t = h / n_yaw;
+      const int a = (int)(h % n_yaw);
+      int cur = slide_oracle_score_one(p, ref7, n_ref, qry7, n_qry, cs[2 * a], cs[2 * a + 1],
+                                       tx[t], ty[t], NULL, NULL);
+      lscored++;
+      if (cur > lbest || (cur == lbest && h < lbest_h)) { lbest = cur; lbest_h = h; }
     }
 #pragma omp critical
     {

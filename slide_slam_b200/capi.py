@@ -70,6 +70,8 @@ class MatchResult(C.Structure):
         ("prepare_ms", C.c_float),
         ("gpu_launches", C.c_int64),
         ("filter_hits", C.c_int64),
+        ("h2d_bytes", C.c_int64),
+        ("d2h_bytes", C.c_int64),
     ]
 
 

@@ -58,6 +58,7 @@ struct slide_pr_handle {
   int n_ref = 0, n_qry = 0;
   int64_t lat_tb = 0, lat_te = -1;
   double prepare_ms = 0;
+  int64_t h2d_bytes = 0;
   spr::Lattice L;
   spr::RefIndex R;
   spr::QuerySet Q;
@@ -82,12 +83,14 @@ template <typename T>
 static int upload(slide_pr_handle *h, DevBuf &b, const std::vector<T> &v, cudaStream_t st) {
   SPR_CUDA(h, b.ensure(std::max<size_t>(v.size(), 1) * sizeof(T)));
   if (!v.empty()) SPR_CUDA(h, cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  h->h2d_bytes += (int64_t)(v.size() * sizeof(T));
   return SLIDE_PR_OK;
 }
 
 static int upload_raw(slide_pr_handle *h, DevBuf &b, const void *src, size_t bytes, cudaStream_t st) {
   SPR_CUDA(h, b.ensure(std::max<size_t>(bytes, 8)));
   if (bytes) SPR_CUDA(h, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+  h->h2d_bytes += (int64_t)bytes;
   return SLIDE_PR_OK;
 }
 
@@ -194,6 +197,7 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   SPR_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   h->half_x = half_x; h->half_y = half_y;
+  h->h2d_bytes = 0;
   h->yaw_half = h->p.inter_loop_closure ? h->p.match_yaw_half_range : h->p.match_yaw_half_range_intra;
   h->n_ref = n_ref; h->n_qry = n_qry;
   h->lat_tb = 0; h->lat_te = -1;
@@ -271,6 +275,7 @@ static void fill_result_header(slide_pr_handle *h, slide_pr_match_result *out) {
   out->n_yaw = (int32_t)h->L.yaw.size();
   out->n_translations = (int64_t)h->L.n_translations;
   out->prepare_ms = (float)h->prepare_ms;
+  out->h2d_bytes = h->h2d_bytes;
 }
 
 int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_pr_match_result *out) {
@@ -351,6 +356,8 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   out->gpu_launches = launches;
   out->rings_scored = rings_scored;
   out->filter_hits = (int64_t)stats[0];
+  out->h2d_bytes = h->h2d_bytes;
+  out->d2h_bytes = (int64_t)sizeof(key) + (o.collect_stats ? (int64_t)sizeof(stats) : 0) + n_counts * (int64_t)sizeof(int32_t);
   // hypotheses scored by this shard = valid bits of its chunk groups x yaw candidates
   {
     const int sc = o.shard_count > 1 ? o.shard_count : 1, si = o.shard_count > 1 ? o.shard_index : 0;
@@ -417,6 +424,7 @@ int slide_pr_extract(slide_pr_handle *h, int64_t hyp_index, int32_t *ref_idx_out
       k++;
     }
   io->n_matched = k;
+  io->d2h_bytes += (int64_t)h->n_qry * (int64_t)sizeof(int32_t);
   return SLIDE_PR_OK;
 }
 
