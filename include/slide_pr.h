@@ -84,6 +84,8 @@ typedef struct slide_pr_match_result {
   int64_t filter_hits;         /* bitmap hits verified in fp64 (0 unless stats were enabled) */
   int64_t h2d_bytes;           /* bytes copied host->device by prepare (+ re-chunking in search) */
   int64_t d2h_bytes;           /* bytes copied device->host by search/extract */
+  int64_t groups_probed;       /* (warp, query group) pairs probed / skipped by the bounding-box test */
+  int64_t groups_skipped;      /*   (0 unless stats were enabled) */
 } slide_pr_match_result;
 
 /* Options for the sharded / sliced search (multi-GPU and tests). */

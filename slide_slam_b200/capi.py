@@ -72,6 +72,8 @@ class MatchResult(C.Structure):
         ("filter_hits", C.c_int64),
         ("h2d_bytes", C.c_int64),
         ("d2h_bytes", C.c_int64),
+        ("groups_probed", C.c_int64),
+        ("groups_skipped", C.c_int64),
     ]
 
 

@@ -62,10 +62,9 @@ struct slide_pr_handle {
   spr::Lattice L;
   spr::RefIndex R;
   spr::QuerySet Q;
-  std::vector<int32_t> qlabel;
   // device side
-  DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_refxy, d_refdims, d_bitmap, d_prefix,
-      d_cellinfo, d_cand, d_qrot, d_qrotq, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
+  DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_cellword,
+      d_cellinfo, d_cand, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
   SprView V{};
   std::vector<int32_t> h_match;
 };
@@ -156,8 +155,8 @@ void slide_pr_destroy(slide_pr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (DevBuf *b : {&h->d_lat, &h->d_chunks, &h->d_cs, &h->d_qxy, &h->d_qdims, &h->d_labelseg, &h->d_qlabel,
-                    &h->d_refxy, &h->d_refdims, &h->d_bitmap, &h->d_prefix, &h->d_cellinfo, &h->d_cand, &h->d_qrot,
-                    &h->d_qrotq, &h->d_ref7, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps, &h->d_tri, &h->d_tri_out})
+                    &h->d_labelbox, &h->d_gbox, &h->d_bitmap, &h->d_cellword, &h->d_cellinfo, &h->d_cand, &h->d_qrot,
+                    &h->d_qrotq, &h->d_qrotq_yx, &h->d_work, &h->d_ref7, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps, &h->d_tri, &h->d_tri_out})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -212,46 +211,48 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   const double reach = qrad + std::max(std::fabs(half_x), std::fabs(half_y)) + h->p.match_xy_step_size;
   if ((rc = spr::build_ref_index(h->p, ref7, n_ref, reach, h->R, h->err)) != SLIDE_PR_OK) return rc;
   if ((rc = spr::build_query_set(h->R, qry7, n_qry, h->Q, h->err)) != SLIDE_PR_OK) return rc;
-  h->qlabel.assign(std::max(h->Q.nq, 1), 0);
-  for (int l = 0; l + 1 < (int)h->Q.label_seg.size(); l++)
-    for (int s = h->Q.label_seg[l]; s < h->Q.label_seg[l + 1]; s++) h->qlabel[s] = l;
 
   if ((rc = upload_lattice(h, st))) return rc;
   if ((rc = upload(h, h->d_qxy, h->Q.qxy, st))) return rc;
   if ((rc = upload(h, h->d_qdims, h->Q.qdims, st))) return rc;
-  if ((rc = upload(h, h->d_labelseg, h->Q.label_seg, st))) return rc;
-  if ((rc = upload(h, h->d_qlabel, h->qlabel, st))) return rc;
-  if ((rc = upload(h, h->d_refxy, h->R.ref_xy, st))) return rc;
-  if ((rc = upload(h, h->d_refdims, h->R.ref_dims, st))) return rc;
+  if ((rc = upload(h, h->d_labelseg, h->Q.label_gseg, st))) return rc;
+  if ((rc = upload(h, h->d_qlabel, h->Q.qlabel, st))) return rc;
+  if ((rc = upload(h, h->d_labelbox, h->R.labelbox, st))) return rc;
   if ((rc = upload(h, h->d_bitmap, h->R.bitmap, st))) return rc;
-  if ((rc = upload(h, h->d_prefix, h->R.prefix, st))) return rc;
+  if ((rc = upload(h, h->d_cellword, h->R.cellword, st))) return rc;
   if ((rc = upload(h, h->d_cellinfo, h->R.cellinfo, st))) return rc;
   if ((rc = upload(h, h->d_cand, h->R.cand, st))) return rc;
   if ((rc = upload_raw(h, h->d_ref7, ref7, (size_t)n_ref * 7 * sizeof(double), st))) return rc;
   if ((rc = upload_raw(h, h->d_qry7, qry7, (size_t)n_qry * 7 * sizeof(double), st))) return rc;
-  const size_t nrot = (size_t)std::max<size_t>((size_t)h->L.yaw.size() * (size_t)h->Q.nq, 1);
+  const size_t nrot = (size_t)std::max<size_t>((size_t)h->L.yaw.size() * (size_t)h->Q.nqp, 1);
+  const size_t ngb = (size_t)std::max<size_t>((size_t)h->L.yaw.size() * (size_t)(h->Q.nqp / SPR_QGROUP), 1);
   SPR_CUDA(h, h->d_qrot.ensure(nrot * 2 * sizeof(double)));
   SPR_CUDA(h, h->d_qrotq.ensure(nrot * 2 * sizeof(int32_t)));
+  SPR_CUDA(h, h->d_qrotq_yx.ensure(nrot * 2 * sizeof(int32_t)));
+  SPR_CUDA(h, h->d_gbox.ensure(ngb * sizeof(SprBox)));
+  SPR_CUDA(h, h->d_work.ensure(sizeof(unsigned long long)));
   SPR_CUDA(h, h->d_best.ensure(sizeof(unsigned long long)));
-  SPR_CUDA(h, h->d_stats.ensure(2 * sizeof(unsigned long long)));
+  SPR_CUDA(h, h->d_stats.ensure(4 * sizeof(unsigned long long)));
   SPR_CUDA(h, h->d_match.ensure(std::max<size_t>(n_qry, 1) * sizeof(int32_t)));
 
   SprView &V = h->V;
-  V.nq = h->Q.nq;
-  V.qrotq = h->d_qrotq.as<int32_t>();
+  V.nqp = h->Q.nqp;
+  V.n_groups = h->Q.nqp / SPR_QGROUP;
+  V.qrotq_xy = h->d_qrotq.as<int32_t>();
+  V.qrotq_yx = h->d_qrotq_yx.as<int32_t>();
+  V.gbox = h->d_gbox.as<SprBox>();
   V.qrot = h->d_qrot.as<double>();
   V.qxy = h->d_qxy.as<double>();
   V.qdims = h->d_qdims.as<double>();
-  V.label_seg = h->d_labelseg.as<int32_t>();
+  V.label_gseg = h->d_labelseg.as<int32_t>();
   V.qlabel = h->d_qlabel.as<int32_t>();
   V.n_labels = (int32_t)h->R.labels.size();
   V.n_ref = n_ref;
-  V.ref_xy = h->d_refxy.as<double>();
-  V.ref_dims = h->d_refdims.as<double>();
+  V.labelbox = h->d_labelbox.as<SprBox>();
   V.bitmap = h->d_bitmap.as<uint32_t>();
-  V.prefix = h->d_prefix.as<uint32_t>();
+  V.cellword = h->d_cellword.as<uint32_t>();
   V.cellinfo = h->d_cellinfo.as<uint32_t>();
-  V.cand = h->d_cand.as<uint32_t>();
+  V.cand = h->d_cand.as<SprCand>();
   V.grid = h->R.grid;
   V.Tstar = h->R.Tstar;
   V.Sstar = h->R.Sstar;
@@ -306,7 +307,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     SPR_CUDA(h, cudaMemsetAsync(h->d_counts.p, 0xff, std::max<size_t>((size_t)n_counts, 1) * sizeof(int32_t), st));
   }
   SPR_CUDA(h, cudaMemsetAsync(h->d_best.p, 0, sizeof(unsigned long long), st));
-  if (o.collect_stats) SPR_CUDA(h, cudaMemsetAsync(h->d_stats.p, 0, 2 * sizeof(unsigned long long), st));
+  if (o.collect_stats) SPR_CUDA(h, cudaMemsetAsync(h->d_stats.p, 0, 4 * sizeof(unsigned long long), st));
 
   SprLaunch K{};
   K.shard_index = o.shard_index;
@@ -316,11 +317,13 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   K.counts_cap = n_counts;
   K.ord_begin = (unsigned long long)tb;
   K.stats = o.collect_stats ? h->d_stats.as<unsigned long long>() : nullptr;
+  K.work_counter = h->d_work.as<unsigned long long>();
 
   int launches = 0;
   SPR_CUDA(h, cudaEventRecord(h->ev0, st));
-  if (h->V.nq > 0 && n_yaw > 0) {
-    SPR_CUDA(h, spr_launch_rotate(h->V, h->d_qrotq.as<int32_t>(), h->d_qrot.as<double>(), st));
+  if (h->V.nqp > 0 && n_yaw > 0) {
+    SPR_CUDA(h, spr_launch_rotate(h->V, h->d_qrotq.as<int32_t>(), h->d_qrotq_yx.as<int32_t>(), h->d_qrot.as<double>(),
+                                  h->d_gbox.as<SprBox>(), st));
     launches++;
   }
   int rings_scored = 0;
@@ -344,7 +347,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     rings_scored = h->L.rings;
   }
   SPR_CUDA(h, cudaEventRecord(h->ev1, st));
-  unsigned long long key = 0, stats[2] = {0, 0};
+  unsigned long long key = 0, stats[4] = {0, 0, 0, 0};
   SPR_CUDA(h, cudaMemcpyAsync(&key, h->d_best.p, sizeof(key), cudaMemcpyDeviceToHost, st));
   if (o.collect_stats) SPR_CUDA(h, cudaMemcpyAsync(stats, h->d_stats.p, sizeof(stats), cudaMemcpyDeviceToHost, st));
   if (o.counts_out && n_counts > 0)
@@ -356,6 +359,8 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   out->gpu_launches = launches;
   out->rings_scored = rings_scored;
   out->filter_hits = (int64_t)stats[0];
+  out->groups_probed = (int64_t)stats[2];
+  out->groups_skipped = (int64_t)stats[3];
   out->h2d_bytes = h->h2d_bytes;
   out->d2h_bytes = (int64_t)sizeof(key) + (o.collect_stats ? (int64_t)sizeof(stats) : 0) + n_counts * (int64_t)sizeof(int32_t);
   // hypotheses scored by this shard = valid bits of its chunk groups x yaw candidates
@@ -368,11 +373,11 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
       for (int k = 0; k < rings_scored; k++) {
         const uint32_t cb = h->L.ring[k].chunk_begin, ce = h->L.ring[k].chunk_end;
         for (uint32_t c = cb; c < ce; c++)
-          if ((int)(((c - cb) / 256) % sc) == si) bits += (uint64_t)__builtin_popcount(h->L.chunks[c].valid);
+          if ((int)(((c - cb) / SPR_WARP_CHUNKS) % sc) == si) bits += (uint64_t)__builtin_popcount(h->L.chunks[c].valid);
       }
     } else {
       for (uint32_t c = 0; c < cend; c++)
-        if ((int)((c / 256) % sc) == si) bits += (uint64_t)__builtin_popcount(h->L.chunks[c].valid);
+        if ((int)((c / SPR_WARP_CHUNKS) % sc) == si) bits += (uint64_t)__builtin_popcount(h->L.chunks[c].valid);
     }
     out->hypotheses_scored = (int64_t)(bits * (uint64_t)n_yaw);
   }

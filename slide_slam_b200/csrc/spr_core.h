@@ -20,6 +20,7 @@
 #define SPR_FUNNEL_R(lo, hi, s) __funnelshift_r((lo), (hi), (s))
 #define SPR_POPC(x) __popc(x)
 #define SPR_FFS(x) __ffs(x)
+#define SPR_UMIN(a, b) min((uint32_t)(a), (uint32_t)(b))
 #else
 #define SPR_DADD(a, b) ((a) + (b))
 #define SPR_DSUB(a, b) ((a) - (b))
@@ -31,9 +32,11 @@ static inline uint32_t spr_funnel_r_host(uint32_t lo, uint32_t hi, uint32_t s) {
 #define SPR_FUNNEL_R(lo, hi, s) spr_funnel_r_host((lo), (hi), (s))
 #define SPR_POPC(x) __builtin_popcount(x)
 #define SPR_FFS(x) __builtin_ffs((int)(x))
+#define SPR_UMIN(a, b) ((uint32_t)(a) < (uint32_t)(b) ? (uint32_t)(a) : (uint32_t)(b))
 #endif
 
-// metres -> fixed-point cell units, rounded down.  |v * S| < 2^30 is guaranteed by the host.
+// metres -> fixed-point cell units, rounded down.  The host guarantees that for every
+// translation t and rotated query q:  |fx(t)| + |fx(q - g0)| < 2^30.
 SPR_HD int32_t spr_fx(double v, double S) { return (int32_t)floor(SPR_DMUL(v, S)); }
 
 // Rotated query coordinates, PR.cpp:257-258 (first two terms, left to right):
@@ -42,6 +45,35 @@ SPR_HD void spr_rotate(double c, double s, double qx, double qy, double *rx, dou
   const double ms = -s;
   *rx = SPR_DADD(SPR_DMUL(c, qx), SPR_DMUL(ms, qy));
   *ry = SPR_DADD(SPR_DMUL(s, qx), SPR_DMUL(c, qy));
+}
+
+// One query group (SPR_QGROUP sorted queries) under yaw a: exact rotated coordinates, their
+// fixed-point cell coordinates in both layouts, and the group's fixed-point bounding box.
+// Padding queries (qlabel < 0) get the sentinel coordinate and do not widen the box.
+SPR_HD void spr_rotate_group(const double *cs, const double *qxy, const int32_t *qlabel, const SprGrid &G,
+                             int32_t nqp, int32_t n_groups, int32_t a, int32_t g, int32_t *qrotq_xy,
+                             int32_t *qrotq_yx, double *qrot, SprBox *gbox) {
+  const double c = cs[2 * a], s = cs[2 * a + 1];
+  SprBox box = {1 << 30, -(1 << 30), 1 << 30, -(1 << 30)};
+  for (int k = 0; k < SPR_QGROUP; k++) {
+    const int32_t js = g * SPR_QGROUP + k;
+    const size_t qi = (size_t)a * (size_t)nqp + (size_t)js;
+    int32_t fxq = SPR_Q_SENTINEL, fyq = SPR_Q_SENTINEL;
+    double rx = 0.0, ry = 0.0;
+    if (qlabel[js] >= 0) {
+      spr_rotate(c, s, qxy[2 * (size_t)js], qxy[2 * (size_t)js + 1], &rx, &ry);
+      fxq = spr_fx(SPR_DSUB(rx, G.g0x), G.S);
+      fyq = spr_fx(SPR_DSUB(ry, G.g0y), G.S);
+      box.x0 = fxq < box.x0 ? fxq : box.x0;
+      box.x1 = fxq + 1 > box.x1 ? fxq + 1 : box.x1;
+      box.y0 = fyq < box.y0 ? fyq : box.y0;
+      box.y1 = fyq + 1 > box.y1 ? fyq + 1 : box.y1;
+    }
+    qrot[2 * qi] = rx; qrot[2 * qi + 1] = ry;
+    qrotq_xy[2 * qi] = fxq; qrotq_xy[2 * qi + 1] = fyq;
+    qrotq_yx[2 * qi] = fyq; qrotq_yx[2 * qi + 1] = fxq;
+  }
+  gbox[(size_t)a * (size_t)n_groups + (size_t)g] = box;
 }
 
 // PR.cpp:310-313,332-333 for one (query, reference) pair under translation (tx, ty).
@@ -56,34 +88,39 @@ SPR_HD bool spr_distance_match(double rx, double ry, double tx, double ty, doubl
 }
 
 // PR.cpp:315-339: dimension rule, keyed on the REFERENCE object's d2 == 0 && d3 == 0.
-SPR_HD bool spr_dimension_match(const double *rd, const double *qd, double thr_dim, double Sstar) {
-  const double a0 = fabs(SPR_DSUB(rd[0], qd[0]));
-  if (rd[1] == 0 && rd[2] == 0) return a0 < thr_dim;
-  const double a1 = fabs(SPR_DSUB(rd[1], qd[1]));
-  const double a2 = fabs(SPR_DSUB(rd[2], qd[2]));
+SPR_HD bool spr_dimension_match(double r1, double r2, double r3, const double *qd, double thr_dim,
+                                double Sstar) {
+  const double a0 = fabs(SPR_DSUB(r1, qd[0]));
+  if (r2 == 0 && r3 == 0) return a0 < thr_dim;
+  const double a1 = fabs(SPR_DSUB(r2, qd[1]));
+  const double a2 = fabs(SPR_DSUB(r3, qd[2]));
   const double sum = SPR_DADD(SPR_DADD(a0, a1), a2);  // 0 + a0 is exact
   return sum < Sstar;                                  // <=> sum / 3 < thr_dim
 }
 
+// Biased fixed-point origin of a chunk: adding a query's fixed coordinates and shifting by F
+// gives directly the bitmap row (across + 1 zero row) and bit offset (along + 32 pad bits).
+SPR_HD int32_t spr_bias_across(int32_t aq0, int32_t F) { return aq0 + (1 << F); }
+SPR_HD int32_t spr_bias_along(int32_t bq0, int32_t F) { return bq0 + (32 << F); }
+
 // Bit-parallel occupancy probe: 32 consecutive lattice samples along the chunk's axis against
-// the bitmap row that the across coordinate selects.  aq / bq are the fixed-point sums
-// (chunk + rotated query) of the across / along coordinates.  Returns the hit bits; *na / *nb
-// receive the cell coordinates of bit 0 (meaningful only where a bit is set).
-SPR_HD uint32_t spr_probe(const uint32_t *plane, int32_t W, int32_t R, int32_t maxbit, int32_t F,
-                          int32_t aq, int32_t bq, uint32_t valid, int32_t *na, int32_t *nb) {
-  const int32_t a = aq >> F;  // arithmetic shift == floor
-  const int32_t b = bq >> F;
-  *na = a;
-  *nb = b;
-  int32_t row = a + 1;
-  row = row < 0 ? 0 : row;
-  row = row > R - 1 ? R - 1 : row;  // rows 0 and R-1 are all-zero
-  int32_t bit = b + 32;
-  bit = bit < 0 ? 0 : bit;
-  bit = bit > maxbit ? maxbit : bit;  // word 0 and words >= maxbit/32 are all-zero
-  const uint32_t wi = (uint32_t)row * (uint32_t)W + ((uint32_t)bit >> 5);
+// the bitmap row that the across coordinate selects.  a / b are the biased fixed-point sums
+// (chunk + rotated query).  Out-of-grid sums clamp onto all-zero rows / words (unsigned min:
+// negative values wrap to the upper clamp).
+SPR_HD uint32_t spr_probe(const uint32_t *plane, uint32_t W, uint32_t Rm1, uint32_t maxbit, int32_t F,
+                          int32_t a, int32_t b, uint32_t valid) {
+  const uint32_t row = SPR_UMIN((uint32_t)(a >> F), Rm1);    // rows 0 and R-1 are all-zero
+  const uint32_t bit = SPR_UMIN((uint32_t)(b >> F), maxbit);  // word 0 and words >= maxbit/32 are all-zero
+  const uint32_t wi = row * W + (bit >> 5);
   const uint32_t w0 = plane[wi], w1 = plane[wi + 1];
-  return SPR_FUNNEL_R(w0, w1, (uint32_t)bit & 31u) & valid;
+  return SPR_FUNNEL_R(w0, w1, bit & 31u) & valid;
+}
+
+// May query group `g` (box of its fixed coords) land on label box `lb` for any translation of a
+// patch whose unbiased fixed-point chunk origins span [X0, X1] x [Y0, Y1]?  (X1 / Y1 include the
+// 32-sample extent of the chunks.)
+SPR_HD bool spr_group_visible(const SprBox &g, const SprBox &lb, int32_t X0, int32_t X1, int32_t Y0, int32_t Y1) {
+  return (g.x1 > lb.x0 - X1) && (g.x0 < lb.x1 - X0) && (g.y1 > lb.y0 - Y1) && (g.y0 < lb.y1 - Y0);
 }
 
 // Exact verification of one occupied cell (nx, ny) of label l for a query point whose rotated
@@ -95,36 +132,34 @@ SPR_HD bool spr_verify_cell(const SprView &V, int32_t l, int32_t nx, int32_t ny,
   const SprGrid &G = V.grid;
   // rank of the cell among the marked cells (dir-0 plane: rows = x, bits = y)
   const uint32_t bit = (uint32_t)(ny + 32);
-  const uint32_t widx = (uint32_t)(nx + 1) * (uint32_t)G.W[0] + (bit >> 5);
-  const uint32_t word = V.bitmap[(size_t)l * G.label_stride + widx];
-  const uint32_t below = word & ((1u << (bit & 31u)) - 1u);
-  const uint32_t rank = V.prefix[(size_t)l * G.plane_words[0] + widx] + (uint32_t)SPR_POPC(below);
+  const size_t widx = (size_t)l * G.plane_words[0] + (uint32_t)(nx + 1) * (uint32_t)G.W[0] + (bit >> 5);
+  const uint32_t word = V.cellword[2 * widx], before = V.cellword[2 * widx + 1];
+  const uint32_t rank = before + (uint32_t)SPR_POPC(word & ((1u << (bit & 31u)) - 1u));
   const uint32_t start = V.cellinfo[2 * (size_t)rank], count = V.cellinfo[2 * (size_t)rank + 1];
   for (uint32_t k = 0; k < count; k++) {
-    const uint32_t i = V.cand[start + k];
-    if (!spr_distance_match(rx, ry, tx, ty, V.ref_xy[2 * (size_t)i], V.ref_xy[2 * (size_t)i + 1], V.Tstar))
-      continue;
-    if (!V.ignore_dim && !spr_dimension_match(V.ref_dims + 3 * (size_t)i, qd, V.thr_dim, V.Sstar))
-      continue;
-    *first_ref = (int32_t)i;
+    const SprCand &c = V.cand[start + k];
+    if (!spr_distance_match(rx, ry, tx, ty, c.x, c.y, V.Tstar)) continue;
+    if (!V.ignore_dim && !spr_dimension_match(c.d1, c.d2, c.d3, qd, V.thr_dim, V.Sstar)) continue;
+    *first_ref = (int32_t)c.ref;
     return true;
   }
   return false;
 }
 
-// Verification of one filter hit of the lattice kernel: query js (sorted order) of label l under
-// yaw a and the translation of bit b of `ch`.  (na, nb) are spr_probe's cell coordinates of bit 0.
-SPR_HD bool spr_verify_hit(const SprView &V, const SprChunk &ch, int32_t l, int32_t a, int32_t js,
-                           int32_t na, int32_t nb, int32_t b, int32_t *first_ref) {
-  const int32_t nalong = nb + b;
+// Verification of one filter hit of the lattice kernel: query js (sorted order) under yaw a and
+// the translation of bit b of `ch`.  a_sum / b_sum are the biased sums that produced the hit.
+SPR_HD bool spr_verify_hit(const SprView &V, const SprChunk &ch, int32_t a, int32_t js, int32_t a_sum,
+                           int32_t b_sum, int32_t b, int32_t *first_ref) {
+  const int32_t F = V.grid.F;
+  const int32_t na = (a_sum >> F) - 1, nalong = (b_sum >> F) - 32 + b;
   const int32_t nx = ch.dir ? nalong : na;
   const int32_t ny = ch.dir ? na : nalong;
   // the hypothesis' translation, exactly as the reference's accumulated lattice value
   const double along = V.lat[ch.along_off + (uint32_t)b];
   const double tx = ch.dir ? along : ch.across;
   const double ty = ch.dir ? ch.across : along;
-  const size_t qi = (size_t)a * (size_t)V.nq + (size_t)js;
-  return spr_verify_cell(V, l, nx, ny, V.qrot[2 * qi], V.qrot[2 * qi + 1], tx, ty,
+  const size_t qi = (size_t)a * (size_t)V.nqp + (size_t)js;
+  return spr_verify_cell(V, V.qlabel[js], nx, ny, V.qrot[2 * qi], V.qrot[2 * qi + 1], tx, ty,
                          V.qdims + 3 * (size_t)js, first_ref);
 }
 

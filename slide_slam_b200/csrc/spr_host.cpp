@@ -228,14 +228,10 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
   const double c = p.match_xy_step_size, thr = p.match_threshold;
   R.Tstar = sqrt_threshold(thr);
   R.Sstar = div3_threshold(p.match_threshold_dimension);
-  R.ref_xy.resize(2 * (size_t)std::max(n_ref, 1));
-  R.ref_dims.resize(3 * (size_t)std::max(n_ref, 1));
   double minx = HUGE_VAL, maxx = -HUGE_VAL, miny = HUGE_VAL, maxy = -HUGE_VAL;
   for (int i = 0; i < n_ref; i++) {
     const double *r = ref7 + 7 * (size_t)i;
     if (!std::isfinite(r[1]) || !std::isfinite(r[2])) { err = "non-finite reference coordinate"; return SLIDE_PR_ERR_NONFINITE; }
-    R.ref_xy[2 * (size_t)i] = r[1]; R.ref_xy[2 * (size_t)i + 1] = r[2];
-    R.ref_dims[3 * (size_t)i] = r[4]; R.ref_dims[3 * (size_t)i + 1] = r[5]; R.ref_dims[3 * (size_t)i + 2] = r[6];
     minx = std::min(minx, r[1]); maxx = std::max(maxx, r[1]);
     miny = std::min(miny, r[2]); maxy = std::max(maxy, r[2]);
     if (r[0] == r[0]) R.labels.push_back(r[0] + 0.0);  // NaN labels never compare equal (PR.cpp:306)
@@ -280,7 +276,10 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
   const uint64_t total_words = (uint64_t)G.label_stride * (uint64_t)std::max(n_labels, 1);
   if (total_words >= (1ull << 28)) { err = "occupancy bitmaps exceed 1 GiB (step too fine for this map extent)"; return SLIDE_PR_ERR_UNSUPPORTED; }
   R.bitmap.assign((size_t)total_words, 0u);
-  R.prefix.assign((size_t)G.plane_words[0] * (size_t)std::max(n_labels, 1), 0u);
+  R.cellword.assign(2 * (size_t)G.plane_words[0] * (size_t)std::max(n_labels, 1), 0u);
+  // per-label bounds of the marked cells (empty until a cell is marked)
+  struct CellBounds { int x0, x1, y0, y1; };
+  std::vector<CellBounds> cb((size_t)std::max(n_labels, 1), CellBounds{INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN});
 
   // mark every cell whose (slightly dilated) box a landmark's match disc touches
   struct Entry { uint64_t key; uint32_t ref; };
@@ -306,6 +305,8 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
           uint32_t *pl1 = pl0 + G.plane_words[0];
           pl0[(size_t)(nx + 1) * G.W[0] + ((uint32_t)(ny + 32) >> 5)] |= 1u << ((ny + 32) & 31);
           pl1[(size_t)(ny + 1) * G.W[1] + ((uint32_t)(nx + 32) >> 5)] |= 1u << ((nx + 32) & 31);
+          cb[l].x0 = std::min(cb[l].x0, nx); cb[l].x1 = std::max(cb[l].x1, nx);
+          cb[l].y0 = std::min(cb[l].y0, ny); cb[l].y1 = std::max(cb[l].y1, ny);
           // rank order == (label, x, y)
           const uint64_t key = ((uint64_t)l << 44) | ((uint64_t)nx << 22) | (uint64_t)ny;
           entries.push_back({key, (uint32_t)i});
@@ -321,18 +322,28 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
   for (size_t e = 0; e < entries.size(); e++) {
     if (e == 0 || entries[e].key != entries[e - 1].key) { R.cellinfo.push_back((uint32_t)e); R.cellinfo.push_back(0u); }
     R.cellinfo.back()++;
-    R.cand[e] = entries[e].ref;
+    const double *r = ref7 + 7 * (size_t)entries[e].ref;
+    R.cand[e] = SprCand{r[1], r[2], r[4], r[5], r[6], entries[e].ref, 0u};
   }
-  // prefix popcounts over the dir-0 planes, label-major (== rank order of the marked cells)
+  // (word, set bits before it) over the dir-0 planes, label-major == rank order of the marked cells
   uint32_t running = 0;
   for (int l = 0; l < n_labels; l++) {
     const uint32_t *pl0 = R.bitmap.data() + (size_t)l * G.label_stride;
-    uint32_t *pf = R.prefix.data() + (size_t)l * G.plane_words[0];
-    for (uint32_t w = 0; w < G.plane_words[0]; w++) { pf[w] = running; running += (uint32_t)__builtin_popcount(pl0[w]); }
+    uint32_t *cw = R.cellword.data() + 2 * (size_t)l * G.plane_words[0];
+    for (uint32_t w = 0; w < G.plane_words[0]; w++) {
+      cw[2 * (size_t)w] = pl0[w];
+      cw[2 * (size_t)w + 1] = running;
+      running += (uint32_t)__builtin_popcount(pl0[w]);
+    }
   }
   if ((size_t)running * 2 != R.cellinfo.size()) { err = "internal: rank / cell list mismatch"; return SLIDE_PR_ERR_INTERNAL; }
+  R.labelbox.resize((size_t)std::max(n_labels, 1));
+  for (int l = 0; l < std::max(n_labels, 1); l++) {
+    if (cb[l].x0 > cb[l].x1) { R.labelbox[l] = SprBox{0, -(1 << 30), 0, -(1 << 30)}; continue; }  // empty: never visible
+    R.labelbox[l] = SprBox{cb[l].x0 << F, (cb[l].x1 + 1) << F, cb[l].y0 << F, (cb[l].y1 + 1) << F};
+  }
   if (R.cellinfo.empty()) { R.cellinfo.assign(2, 0u); }
-  if (R.cand.empty()) R.cand.assign(1, 0u);
+  if (R.cand.empty()) R.cand.assign(1, SprCand{0, 0, 0, 0, 0, 0u, 0u});
   return SLIDE_PR_OK;
 }
 
@@ -376,18 +387,27 @@ int build_query_set(const RefIndex &R, const double *qry7, int n_qry, QuerySet &
     return a.j < b.j;
   });
   Q.nq = (int)items.size();
-  Q.orig.resize(std::max(Q.nq, 1));
-  Q.qxy.resize(2 * (size_t)std::max(Q.nq, 1));
-  Q.qdims.resize(3 * (size_t)std::max(Q.nq, 1));
-  Q.label_seg.assign(n_labels + 1, 0);
-  for (int s = 0; s < Q.nq; s++) {
-    const double *q = qry7 + 7 * (size_t)items[s].j;
-    Q.orig[s] = items[s].j;
-    Q.qxy[2 * (size_t)s] = q[1]; Q.qxy[2 * (size_t)s + 1] = q[2];
-    Q.qdims[3 * (size_t)s] = q[4]; Q.qdims[3 * (size_t)s + 1] = q[5]; Q.qdims[3 * (size_t)s + 2] = q[6];
-    Q.label_seg[items[s].l + 1]++;
+  // every label segment is padded to a whole number of query groups; padding entries carry
+  // qlabel = -1 and get the sentinel fixed-point coordinate (never inside the grid)
+  std::vector<int> per_label(n_labels, 0);
+  for (const Item &it : items) per_label[it.l]++;
+  Q.label_gseg.assign(n_labels + 1, 0);
+  for (int l = 0; l < n_labels; l++) Q.label_gseg[l + 1] = Q.label_gseg[l] + (per_label[l] + SPR_QGROUP - 1) / SPR_QGROUP;
+  Q.nqp = Q.label_gseg[n_labels] * SPR_QGROUP;
+  const size_t n = (size_t)std::max(Q.nqp, 1);
+  Q.orig.assign(n, -1);
+  Q.qlabel.assign(n, -1);
+  Q.qxy.assign(2 * n, 0.0);
+  Q.qdims.assign(3 * n, 0.0);
+  std::vector<int> fill(n_labels, 0);
+  for (const Item &it : items) {
+    const size_t s = (size_t)Q.label_gseg[it.l] * SPR_QGROUP + (size_t)fill[it.l]++;
+    const double *q = qry7 + 7 * (size_t)it.j;
+    Q.orig[s] = it.j;
+    Q.qlabel[s] = it.l;
+    Q.qxy[2 * s] = q[1]; Q.qxy[2 * s + 1] = q[2];
+    Q.qdims[3 * s] = q[4]; Q.qdims[3 * s + 1] = q[5]; Q.qdims[3 * s + 2] = q[6];
   }
-  for (int l = 0; l < n_labels; l++) Q.label_seg[l + 1] += Q.label_seg[l];
   return SLIDE_PR_OK;
 }
 

@@ -40,13 +40,12 @@ bool translation_of(const Lattice &L, uint64_t ordinal, double *x, double *y, in
 
 struct RefIndex {
   std::vector<double> labels;       // distinct finite reference labels, ascending
-  std::vector<double> ref_xy;       // [n_ref][2]
-  std::vector<double> ref_dims;     // [n_ref][3]
   SprGrid grid{};
   std::vector<uint32_t> bitmap;     // [n_labels][plane0 | plane1]
-  std::vector<uint32_t> prefix;     // [n_labels][plane_words[0]]
-  std::vector<uint32_t> cellinfo;   // [n_cells][2]
-  std::vector<uint32_t> cand;
+  std::vector<uint32_t> cellword;   // [n_labels][plane_words[0]][2] (bits, set bits before)
+  std::vector<uint32_t> cellinfo;   // [n_cells][2] (start, count)
+  std::vector<SprCand> cand;        // candidates of every marked cell, reference index ascending
+  std::vector<SprBox> labelbox;     // [n_labels] fixed-point bounds of the label's marked cells
   double Tstar = 0, Sstar = 0;
   int n_ref = 0;
 };
@@ -57,11 +56,13 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
                     RefIndex &R, std::string &err);
 
 struct QuerySet {
-  int nq = 0;                       // kept queries
-  std::vector<int32_t> orig;        // [nq] original index
-  std::vector<double> qxy;          // [nq][2]
-  std::vector<double> qdims;        // [nq][3]
-  std::vector<int32_t> label_seg;   // [n_labels + 1]
+  int nq = 0;                       // kept queries (label present in the reference)
+  int nqp = 0;                      // with every label segment padded to SPR_QGROUP
+  std::vector<int32_t> orig;        // [nqp] original index, -1 for padding
+  std::vector<double> qxy;          // [nqp][2]
+  std::vector<double> qdims;        // [nqp][3]
+  std::vector<int32_t> qlabel;      // [nqp] label bucket, -1 for padding
+  std::vector<int32_t> label_gseg;  // [n_labels + 1] group (SPR_QGROUP queries) boundaries
 };
 int build_query_set(const RefIndex &R, const double *qry7, int n_qry, QuerySet &Q, std::string &err);
 

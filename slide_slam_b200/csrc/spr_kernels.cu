@@ -3,15 +3,19 @@
 // Replaces the five nested loops of PlaceRecognition::MatchMaps (place_recognition.cpp:178-372).
 // Work decomposition:
 //   * one THREAD owns one chunk = 32 consecutive lattice translations along one axis, for one
-//     yaw candidate; a warp owns 32 chunks (1024 hypotheses), a CTA 8 warps;
-//   * for every query landmark the thread reads two words of the label's occupancy bitmap and
-//     obtains the 32 hypotheses' filter bits with one funnel shift (spr_probe);
-//   * set bits ("filter hits", a few % of the probes) are compacted through a per-warp
+//     yaw candidate; a WARP owns 32 chunks (1024 hypotheses) and is the unit of scheduling: warps
+//     pull (yaw, 32-chunk) work items from a global counter, there is no block-level barrier;
+//   * query landmarks come in groups of 8 (one label, Morton order) with a bounding box per yaw;
+//     a group that cannot reach the label's occupied cells from any of the warp's 1024
+//     translations is skipped with four integer compares;
+//   * for every remaining query landmark the thread reads two words of the label's occupancy
+//     bitmap and obtains the 32 hypotheses' filter bits with one funnel shift (spr_probe);
+//   * set bits ("filter hits", well under 1 % of the probes) are compacted through a per-warp
 //     shared-memory queue (warp prefix-sum over popcounts) and verified 32 at a time in exact,
 //     non-fused fp64 against the cell's candidate list (spr_verify_cell) -- the reference's own
 //     predicate, so every hypothesis gets its exact inlier count;
 //   * per-hypothesis counters live in shared memory; the best (count, canonical index) key is
-//     reduced with shuffles and one 64-bit atomicMax per warp and work item.
+//     reduced with shuffles and one 64-bit atomicMax per warp.
 // This is integer/bit and fp64 ALU work on L1/L2-resident data; there is no GEMM in it, so no
 // tensor-core path (BASELINE.json north_star).
 #include <cuda_runtime.h>
@@ -23,29 +27,26 @@
 #define SPR_BLOCK 256
 #define SPR_WARPS (SPR_BLOCK / 32)
 #define SPR_QCAP 512            // per-warp hit queue, records
-#define SPR_UNROLL 4
+#define SPR_FULL 0xffffffffu
 
 // ---------------------------------------------------------------------------------------------
-// rotate: qrot[a][s] = R(yaw_a) * q_s in the reference's operation order, plus fixed-point cells
+// rotate: one thread per (yaw, query group)
 // ---------------------------------------------------------------------------------------------
-__global__ void spr_rotate_kernel(SprView V, int32_t *__restrict__ qrotq, double *__restrict__ qrot) {
-  const long long n = (long long)V.n_yaw * V.nq;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int a = (int)(i / V.nq), s = (int)(i % V.nq);
-    double rx, ry;
-    spr_rotate(V.cs[2 * a], V.cs[2 * a + 1], V.qxy[2 * (size_t)s], V.qxy[2 * (size_t)s + 1], &rx, &ry);
-    reinterpret_cast<double2 *>(qrot)[i] = make_double2(rx, ry);
-    reinterpret_cast<int2 *>(qrotq)[i] =
-        make_int2(spr_fx(SPR_DSUB(rx, V.grid.g0x), V.grid.S), spr_fx(SPR_DSUB(ry, V.grid.g0y), V.grid.S));
-  }
+__global__ void spr_rotate_kernel(SprView V, int32_t *__restrict__ qrotq_xy, int32_t *__restrict__ qrotq_yx,
+                                  double *__restrict__ qrot, SprBox *__restrict__ gbox) {
+  const long long n = (long long)V.n_yaw * V.n_groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    spr_rotate_group(V.cs, V.qxy, V.qlabel, V.grid, V.nqp, V.n_groups, (int)(i / V.n_groups), (int)(i % V.n_groups),
+                     qrotq_xy, qrotq_yx, qrot, gbox);
 }
 
-cudaError_t spr_launch_rotate(const SprView &V, int32_t *qrotq, double *qrot, cudaStream_t st) {
-  const long long n = (long long)V.n_yaw * V.nq;
+cudaError_t spr_launch_rotate(const SprView &V, int32_t *qrotq_xy, int32_t *qrotq_yx, double *qrot, SprBox *gbox,
+                              cudaStream_t st) {
+  const long long n = (long long)V.n_yaw * V.n_groups;
   if (n <= 0) return cudaSuccess;
-  const int block = 256;
-  const int grid = (int)((n + block - 1) / block > 148 * 8 ? 148 * 8 : (n + block - 1) / block);
-  spr_rotate_kernel<<<grid, block, 0, st>>>(V, qrotq, qrot);
+  const int block = 128;
+  const long long want = (n + block - 1) / block;
+  spr_rotate_kernel<<<(int)(want > 148 * 16 ? 148 * 16 : want), block, 0, st>>>(V, qrotq_xy, qrotq_yx, qrot, gbox);
   return cudaGetLastError();
 }
 
@@ -58,43 +59,49 @@ struct WarpState {
   int qcount;       // warp-uniform
 };
 
+// exact verification of one hit given the owning chunk's parameters
+__device__ __forceinline__ bool spr_verify_owned(const SprView &V, int a, int js, int b, int32_t o_aqb, int32_t o_bqb,
+                                                 uint32_t o_dir, uint32_t o_off, double o_across) {
+  const SprGrid &G = V.grid;
+  const size_t qi = (size_t)a * (size_t)V.nqp + (size_t)js;
+  const int2 qq = __ldg(reinterpret_cast<const int2 *>(V.qrotq_xy) + qi);
+  const double2 r = __ldg(reinterpret_cast<const double2 *>(V.qrot) + qi);
+  const int l = __ldg(V.qlabel + js);
+  const double along = __ldg(V.lat + o_off + b);
+  const int32_t na = ((o_aqb + (o_dir ? qq.y : qq.x)) >> G.F) - 1;
+  const int32_t nb = ((o_bqb + (o_dir ? qq.x : qq.y)) >> G.F) - 32 + b;
+  const int32_t nx = o_dir ? nb : na, ny = o_dir ? na : nb;
+  const double tx = o_dir ? along : o_across, ty = o_dir ? o_across : along;
+  int32_t first;
+  return spr_verify_cell(V, l, nx, ny, r.x, r.y, tx, ty, V.qdims + 3 * (size_t)js, &first);
+}
+
 // Verify up to 32 queued hits, one per lane.  Chunk parameters of the owning lane come through
 // shuffles; every lane executes the shuffles.
-__device__ __forceinline__ void spr_drain32(const SprView &V, WarpState &ws, int a, int lane,
-                                            const SprChunk &ch, int32_t aq0, int32_t bq0,
+__device__ __forceinline__ void spr_drain32(const SprView &V, WarpState &ws, int a, int lane, int32_t aqb,
+                                            int32_t bqb, uint32_t dir, uint32_t along_off, double across,
                                             unsigned long long &n_inl) {
   const int n = ws.qcount < 32 ? ws.qcount : 32;
   const bool active = lane < n;
   const uint32_t rec = active ? ws.queue[ws.qcount - n + lane] : 0u;
   const int owner = (rec >> 5) & 31, b = rec & 31;
   const int js = (int)(rec >> 10);
-  const int32_t o_aq0 = __shfl_sync(0xffffffffu, aq0, owner);
-  const int32_t o_bq0 = __shfl_sync(0xffffffffu, bq0, owner);
-  const uint32_t o_dir = __shfl_sync(0xffffffffu, ch.dir, owner);
-  const uint32_t o_off = __shfl_sync(0xffffffffu, ch.along_off, owner);
-  const double o_across = __shfl_sync(0xffffffffu, ch.across, owner);
-  if (active) {
-    const SprGrid &G = V.grid;
-    const int2 qq = __ldg(reinterpret_cast<const int2 *>(V.qrotq) + (size_t)a * V.nq + js);
-    const int32_t na = (o_aq0 + (o_dir ? qq.y : qq.x)) >> G.F;
-    const int32_t nb = ((o_bq0 + (o_dir ? qq.x : qq.y)) >> G.F) + b;
-    const int32_t nx = o_dir ? nb : na, ny = o_dir ? na : nb;
-    const double along = __ldg(V.lat + o_off + b);
-    const double tx = o_dir ? along : o_across, ty = o_dir ? o_across : along;
-    const double2 r = __ldg(reinterpret_cast<const double2 *>(V.qrot) + (size_t)a * V.nq + js);
-    int32_t first;
-    if (spr_verify_cell(V, __ldg(V.qlabel + js), nx, ny, r.x, r.y, tx, ty, V.qdims + 3 * (size_t)js, &first)) {
-      atomicAdd(&ws.cnt[b * 32 + owner], 1u);
-      n_inl++;
-    }
+  const int32_t o_aqb = __shfl_sync(SPR_FULL, aqb, owner);
+  const int32_t o_bqb = __shfl_sync(SPR_FULL, bqb, owner);
+  const uint32_t o_dir = __shfl_sync(SPR_FULL, dir, owner);
+  const uint32_t o_off = __shfl_sync(SPR_FULL, along_off, owner);
+  const double o_across = __shfl_sync(SPR_FULL, across, owner);
+  if (active && spr_verify_owned(V, a, js, b, o_aqb, o_bqb, o_dir, o_off, o_across)) {
+    atomicAdd(&ws.cnt[b * 32 + owner], 1u);
+    n_inl++;
   }
   ws.qcount -= n;
   __syncwarp();
 }
 
 template <int VARIANT, bool WRITE_COUNTS, bool STATS>
-__global__ void __launch_bounds__(SPR_BLOCK)
-spr_score_lattice_kernel(SprView V, SprLaunch K, int n_groups_local, long long n_items) {
+__global__ void __launch_bounds__(SPR_BLOCK, 4)
+spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_local, const long long n_items) {
   extern __shared__ uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpState ws;
@@ -102,114 +109,127 @@ spr_score_lattice_kernel(SprView V, SprLaunch K, int n_groups_local, long long n
   ws.queue = smem + SPR_WARPS * 1024 + warp * SPR_QCAP;
   ws.qcount = 0;
   const SprGrid &G = V.grid;
-  unsigned long long best = 0ull, n_hits = 0ull, n_inl = 0ull;
+  const int32_t F = G.F;
+  unsigned long long best = 0ull, n_hits = 0ull, n_inl = 0ull, n_probed = 0ull, n_skipped = 0ull;
 
-  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-    // yaw-major order: neighbouring CTAs work on the same yaw and share qrotq[a][*] in L2/L1
-    const int a = (int)(item / n_groups_local);
-    const int g = K.shard_index + (int)(item % n_groups_local) * K.shard_count;
-    const uint32_t cidx = K.chunk_begin + (uint32_t)g * SPR_BLOCK + threadIdx.x;
-    SprChunk ch;
+  for (;;) {
+    // per-warp dynamic scheduling, yaw-major: warps running at the same time share qrotq[a][*]
+    long long item = 0;
+    if (lane == 0) item = (long long)atomicAdd(K.work_counter, 1ull);
+    item = __shfl_sync(SPR_FULL, item, 0);
+    if (item >= n_items) break;
+    const int a = (int)(item / n_wg_local);
+    const int wg = K.shard_index + (int)(item % n_wg_local) * K.shard_count;
+    const uint32_t cidx = K.chunk_begin + (uint32_t)wg * SPR_WARP_CHUNKS + (uint32_t)lane;
+    double across = 0.0;
+    uint32_t along_off = 0u, valid = 0u, ord_base = 0u, ord_stride = 0u, dir = 0u;
     if (cidx < K.chunk_end) {
-      ch = V.chunks[cidx];
-    } else {
-      ch.across = 0.0; ch.along_off = 0; ch.valid = 0; ch.ord_base = 0; ch.ord_stride = 0; ch.dir = 0; ch.ring = 0;
+      const SprChunk ch = V.chunks[cidx];
+      across = ch.across; along_off = ch.along_off; valid = ch.valid;
+      ord_base = ch.ord_base; ord_stride = ch.ord_stride; dir = ch.dir;
     }
 #pragma unroll
     for (int b = 0; b < 32; b++) ws.cnt[b * 32 + lane] = 0u;
+    const int32_t aq0 = spr_fx(across, G.S);
+    const int32_t bq0 = spr_fx(__ldg(V.lat + along_off), G.S);
+    const int32_t aqb = spr_bias_across(aq0, F), bqb = spr_bias_along(bq0, F);
+    // patch window of the warp's 1024 translations (unbiased fixed point)
+    const int32_t big = 1 << 30;
+    const bool live = valid != 0u;
+    const int32_t lx0 = dir ? bq0 : aq0, lx1 = dir ? bq0 + (32 << F) : aq0;
+    const int32_t ly0 = dir ? aq0 : bq0, ly1 = dir ? aq0 : bq0 + (32 << F);
+    const int32_t X0 = __reduce_min_sync(SPR_FULL, live ? lx0 : big), X1 = __reduce_max_sync(SPR_FULL, live ? lx1 : -big);
+    const int32_t Y0 = __reduce_min_sync(SPR_FULL, live ? ly0 : big), Y1 = __reduce_max_sync(SPR_FULL, live ? ly1 : -big);
     __syncwarp();
-    const int d = (int)ch.dir;
-    const int32_t aq0 = spr_fx(ch.across, G.S);
-    const int32_t bq0 = spr_fx(__ldg(V.lat + ch.along_off), G.S);
-    const int32_t W = G.W[d], R = G.R[d], maxbit = G.maxbit[d];
-    const int2 *__restrict__ qa = reinterpret_cast<const int2 *>(V.qrotq) + (size_t)a * V.nq;
-    // skip the whole item when the warp has nothing to score (tail of the chunk list)
-    if (__ballot_sync(0xffffffffu, ch.valid != 0u) != 0u) {
+    const uint32_t W = (uint32_t)G.W[dir], Rm1 = (uint32_t)G.R[dir] - 1u, maxbit = (uint32_t)G.maxbit[dir];
+    const uint32_t *__restrict__ plane0 = V.bitmap + (dir ? G.plane_words[0] : 0u);
+    const int4 *__restrict__ qa =
+        reinterpret_cast<const int4 *>((dir ? V.qrotq_yx : V.qrotq_xy) + 2 * (size_t)a * (size_t)V.nqp);
+    const int4 *__restrict__ gb = reinterpret_cast<const int4 *>(V.gbox) + (size_t)a * (size_t)V.n_groups;
+
+    if (X0 <= X1) {  // at least one live lane
       for (int l = 0; l < V.n_labels; l++) {
-        const uint32_t *__restrict__ plane = V.bitmap + (size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u);
-        const int s1 = V.label_seg[l + 1];
-        for (int s0 = V.label_seg[l]; s0 < s1; s0 += SPR_UNROLL) {
-          uint32_t H[SPR_UNROLL];
-          int32_t na[SPR_UNROLL], nb[SPR_UNROLL];
-#pragma unroll
-          for (int u = 0; u < SPR_UNROLL; u++) {
-            const int s = s0 + u < s1 ? s0 + u : s1 - 1;
-            const int2 qq = __ldg(qa + s);
-            H[u] = spr_probe(plane, W, R, maxbit, G.F, aq0 + (d ? qq.y : qq.x), bq0 + (d ? qq.x : qq.y),
-                             s0 + u < s1 ? ch.valid : 0u, &na[u], &nb[u]);
+        const uint32_t *__restrict__ plane = plane0 + (size_t)l * G.label_stride;
+        const SprBox lb = V.labelbox[l];
+        // a group is visible iff gx1 > tx_lo && gx0 < tx_hi && gy1 > ty_lo && gy0 < ty_hi
+        const int32_t tx_lo = lb.x0 - X1, tx_hi = lb.x1 - X0, ty_lo = lb.y0 - Y1, ty_hi = lb.y1 - Y0;
+        const int g1 = V.label_gseg[l + 1];
+        for (int g = V.label_gseg[l]; g < g1; g++) {
+          const int4 box = __ldg(gb + g);  // (x0, x1, y0, y1), same address for the whole warp
+          if (!(box.y > tx_lo && box.x < tx_hi && box.w > ty_lo && box.z < ty_hi)) {
+            if (STATS) n_skipped++;
+            continue;
           }
+          if (STATS) n_probed++;
+          uint32_t H[SPR_QGROUP];
+#pragma unroll
+          for (int u = 0; u < SPR_QGROUP / 2; u++) {
+            const int4 v = __ldg(qa + (size_t)g * (SPR_QGROUP / 2) + u);  // two queries: (across, along) x 2
+            H[2 * u] = spr_probe(plane, W, Rm1, maxbit, F, aqb + v.x, bqb + v.y, SPR_FULL);
+            H[2 * u + 1] = spr_probe(plane, W, Rm1, maxbit, F, aqb + v.z, bqb + v.w, SPR_FULL);
+          }
+          uint32_t any = 0u;
+#pragma unroll
+          for (int u = 0; u < SPR_QGROUP; u++) any |= H[u];
+          any &= valid;
+          if (__ballot_sync(SPR_FULL, any != 0u) == 0u) continue;
           int n = 0;
 #pragma unroll
-          for (int u = 0; u < SPR_UNROLL; u++) n += __popc(H[u]);
+          for (int u = 0; u < SPR_QGROUP; u++) { H[u] &= valid; n += __popc(H[u]); }
           if (STATS) n_hits += (unsigned long long)n;
-          if (__ballot_sync(0xffffffffu, n != 0) == 0u) continue;
-          if (VARIANT == SPR_VARIANT_DIRECT) {
+          const int js0 = g * SPR_QGROUP;
+          bool in_place = VARIANT == SPR_VARIANT_DIRECT;
+          int incl = n, total = 0;
+          if (!in_place) {
+            // warp inclusive prefix sum of the per-lane hit counts
 #pragma unroll
-            for (int u = 0; u < SPR_UNROLL; u++) {
+            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+              const int t = __shfl_up_sync(SPR_FULL, incl, dlt);
+              if (lane >= dlt) incl += t;
+            }
+            total = __shfl_sync(SPR_FULL, incl, 31);
+            in_place = total > SPR_QCAP;  // pathological density: verify in place
+          }
+          if (in_place) {
+#pragma unroll
+            for (int u = 0; u < SPR_QGROUP; u++) {
               uint32_t h = H[u];
               while (h) {
                 const int b = __ffs(h) - 1;
                 h &= h - 1;
-                int32_t first;
-                if (spr_verify_hit(V, ch, l, a, s0 + u, na[u], nb[u], b, &first)) {
-                  ws.cnt[b * 32 + lane]++;
+                if (spr_verify_owned(V, a, js0 + u, b, aqb, bqb, dir, along_off, across)) {
+                  atomicAdd(&ws.cnt[b * 32 + lane], 1u);  // atomics: queued hits may target our column
                   n_inl++;
                 }
               }
             }
-          } else {
-            // warp inclusive prefix sum of the per-lane hit counts
-            int incl = n;
-#pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-              const int t = __shfl_up_sync(0xffffffffu, incl, dlt);
-              if (lane >= dlt) incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total > SPR_QCAP) {
-              // pathological density: verify in place (atomics: queued hits may target our columns)
-#pragma unroll
-              for (int u = 0; u < SPR_UNROLL; u++) {
-                uint32_t h = H[u];
-                while (h) {
-                  const int b = __ffs(h) - 1;
-                  h &= h - 1;
-                  int32_t first;
-                  if (spr_verify_hit(V, ch, l, a, s0 + u, na[u], nb[u], b, &first)) {
-                    atomicAdd(&ws.cnt[b * 32 + lane], 1u);
-                    n_inl++;
-                  }
-                }
-              }
-              continue;
-            }
-            while (ws.qcount + total > SPR_QCAP) spr_drain32(V, ws, a, lane, ch, aq0, bq0, n_inl);
-            int pos = ws.qcount + incl - n;
-#pragma unroll
-            for (int u = 0; u < SPR_UNROLL; u++) {
-              uint32_t h = H[u];
-              while (h) {
-                const int b = __ffs(h) - 1;
-                h &= h - 1;
-                ws.queue[pos++] = ((uint32_t)(s0 + u) << 10) | ((uint32_t)lane << 5) | (uint32_t)b;
-              }
-            }
-            ws.qcount += total;
-            __syncwarp();
-            while (ws.qcount >= 32) spr_drain32(V, ws, a, lane, ch, aq0, bq0, n_inl);
+            continue;
           }
+          while (ws.qcount + total > SPR_QCAP) spr_drain32(V, ws, a, lane, aqb, bqb, dir, along_off, across, n_inl);
+          int pos = ws.qcount + incl - n;
+#pragma unroll
+          for (int u = 0; u < SPR_QGROUP; u++) {
+            uint32_t h = H[u];
+            while (h) {
+              const int b = __ffs(h) - 1;
+              h &= h - 1;
+              ws.queue[pos++] = ((uint32_t)(js0 + u) << 10) | ((uint32_t)lane << 5) | (uint32_t)b;
+            }
+          }
+          ws.qcount += total;
+          __syncwarp();
+          while (ws.qcount >= 32) spr_drain32(V, ws, a, lane, aqb, bqb, dir, along_off, across, n_inl);
         }
       }
-      if (VARIANT != SPR_VARIANT_DIRECT)
-        while (ws.qcount > 0) spr_drain32(V, ws, a, lane, ch, aq0, bq0, n_inl);
+      while (ws.qcount > 0) spr_drain32(V, ws, a, lane, aqb, bqb, dir, along_off, across, n_inl);
       __syncwarp();
       // each lane scans the 32 hypotheses of its chunk
-      uint32_t v = ch.valid;
+      uint32_t v = valid;
       while (v) {
         const int b = __ffs(v) - 1;
         v &= v - 1;
         const uint32_t c = ws.cnt[b * 32 + lane];
-        const unsigned long long ord = (unsigned long long)ch.ord_base + (unsigned long long)b * ch.ord_stride;
+        const unsigned long long ord = (unsigned long long)ord_base + (unsigned long long)b * ord_stride;
         const unsigned long long key = spr_make_key(c, ord * (unsigned long long)V.n_yaw + (unsigned long long)a);
         best = key > best ? key : best;
         if (WRITE_COUNTS) {
@@ -223,22 +243,25 @@ spr_score_lattice_kernel(SprView V, SprLaunch K, int n_groups_local, long long n
   // warp max of the 64-bit key, then one atomic per warp
 #pragma unroll
   for (int dlt = 16; dlt > 0; dlt >>= 1) {
-    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, dlt);
+    const unsigned long long o = __shfl_xor_sync(SPR_FULL, best, dlt);
     best = o > best ? o : best;
   }
   if (lane == 0 && best != 0ull) atomicMax(K.best_key, best);
   if (STATS) {
 #pragma unroll
     for (int dlt = 16; dlt > 0; dlt >>= 1) {
-      n_hits += __shfl_xor_sync(0xffffffffu, n_hits, dlt);
-      n_inl += __shfl_xor_sync(0xffffffffu, n_inl, dlt);
+      n_hits += __shfl_xor_sync(SPR_FULL, n_hits, dlt);
+      n_inl += __shfl_xor_sync(SPR_FULL, n_inl, dlt);
     }
-    if (lane == 0) { atomicAdd(K.stats, n_hits); atomicAdd(K.stats + 1, n_inl); }
+    if (lane == 0) {
+      atomicAdd(K.stats, n_hits); atomicAdd(K.stats + 1, n_inl);
+      atomicAdd(K.stats + 2, n_probed); atomicAdd(K.stats + 3, n_skipped);
+    }
   }
 }
 
 template <int VARIANT>
-static cudaError_t launch_variant(const SprView &V, const SprLaunch &K, int n_groups_local, long long n_items,
+static cudaError_t launch_variant(const SprView &V, const SprLaunch &K, int n_wg_local, long long n_items,
                                   int grid, size_t smem, cudaStream_t st) {
   const bool wc = K.counts_out != nullptr, stt = K.stats != nullptr;
 #define SPR_GO(WC, ST)                                                                                     \
@@ -246,7 +269,7 @@ static cudaError_t launch_variant(const SprView &V, const SprLaunch &K, int n_gr
     cudaError_t e = cudaFuncSetAttribute(spr_score_lattice_kernel<VARIANT, WC, ST>,                        \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
     if (e != cudaSuccess) return e;                                                                        \
-    spr_score_lattice_kernel<VARIANT, WC, ST><<<grid, SPR_BLOCK, smem, st>>>(V, K, n_groups_local, n_items); \
+    spr_score_lattice_kernel<VARIANT, WC, ST><<<grid, SPR_BLOCK, smem, st>>>(V, K, n_wg_local, n_items);    \
   } while (0)
   if (wc && stt) SPR_GO(true, true);
   else if (wc) SPR_GO(true, false);
@@ -260,21 +283,24 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int v
                                      cudaStream_t st, int *n_launches) {
   if (K.chunk_end <= K.chunk_begin || V.n_yaw <= 0) return cudaSuccess;
   const uint32_t n_chunks = K.chunk_end - K.chunk_begin;
-  const int n_groups = (int)((n_chunks + SPR_BLOCK - 1) / SPR_BLOCK);
+  const int n_wg = (int)((n_chunks + SPR_WARP_CHUNKS - 1) / SPR_WARP_CHUNKS);
   const int sc = K.shard_count > 1 ? K.shard_count : 1;
   const int si = K.shard_count > 1 ? K.shard_index : 0;
-  const int n_groups_local = n_groups > si ? (n_groups - si + sc - 1) / sc : 0;
-  if (n_groups_local <= 0) return cudaSuccess;
+  const int n_wg_local = n_wg > si ? (n_wg - si + sc - 1) / sc : 0;
+  if (n_wg_local <= 0) return cudaSuccess;
   SprLaunch K2 = K;
   K2.shard_index = si;
   K2.shard_count = sc;
-  const long long n_items = (long long)n_groups_local * V.n_yaw;
+  const long long n_items = (long long)n_wg_local * V.n_yaw;
   const size_t smem = (size_t)SPR_WARPS * (1024 + SPR_QCAP) * sizeof(uint32_t);
   const long long max_grid = (long long)sm_count * 4;
-  const int grid = (int)(n_items < max_grid ? n_items : max_grid);
+  const long long want = (n_items + SPR_WARPS - 1) / SPR_WARPS;
+  const int grid = (int)(want < max_grid ? want : max_grid);
+  cudaError_t e = cudaMemsetAsync(K.work_counter, 0, sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return e;
   if (n_launches) (*n_launches)++;
-  if (variant == SPR_VARIANT_DIRECT) return launch_variant<SPR_VARIANT_DIRECT>(V, K2, n_groups_local, n_items, grid, smem, st);
-  return launch_variant<SPR_VARIANT_QUEUED>(V, K2, n_groups_local, n_items, grid, smem, st);
+  if (variant == SPR_VARIANT_DIRECT) return launch_variant<SPR_VARIANT_DIRECT>(V, K2, n_wg_local, n_items, grid, smem, st);
+  return launch_variant<SPR_VARIANT_QUEUED>(V, K2, n_wg_local, n_items, grid, smem, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -290,18 +316,19 @@ spr_score_list_kernel(SprView V, const double *__restrict__ hyps4, long long n, 
   for (long long h = warp0; h < n; h += n_warps) {
     const double c = hyps4[4 * h], s = hyps4[4 * h + 1], tx = hyps4[4 * h + 2], ty = hyps4[4 * h + 3];
     int cnt = 0;
-    for (int js = lane; js < V.nq; js += 32) {
+    for (int js = lane; js < V.nqp; js += 32) {
+      const int l = V.qlabel[js];
+      if (l < 0) continue;  // padding
       double rx, ry;
       spr_rotate(c, s, V.qxy[2 * (size_t)js], V.qxy[2 * (size_t)js + 1], &rx, &ry);
       const double xt = SPR_DADD(rx, tx), yt = SPR_DADD(ry, ty);
-      const int l = V.qlabel[js];
       int32_t nx, ny, first;
       if (spr_point_cell(V, l, xt, yt, &nx, &ny) &&
           spr_verify_cell(V, l, nx, ny, rx, ry, tx, ty, V.qdims + 3 * (size_t)js, &first))
         cnt++;
     }
 #pragma unroll
-    for (int dlt = 16; dlt > 0; dlt >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, dlt);
+    for (int dlt = 16; dlt > 0; dlt >>= 1) cnt += __shfl_xor_sync(SPR_FULL, cnt, dlt);
     if (lane == 0) {
       if (counts_out) counts_out[h] = cnt;
       const unsigned long long key = spr_make_key((uint32_t)cnt, (unsigned long long)h);
@@ -339,10 +366,7 @@ __global__ void spr_extract_kernel(const double *__restrict__ ref7, int n_ref, c
     const double *r = ref7 + 7 * (size_t)i;
     if (r[0] != label) continue;                                         // PR.cpp:306
     if (!spr_distance_match(rx, ry, tx, ty, r[1], r[2], Tstar)) continue;  // PR.cpp:332
-    if (!ignore_dim) {
-      const double rd[3] = {r[4], r[5], r[6]};
-      if (!spr_dimension_match(rd, qd, thr_dim, Sstar)) continue;        // PR.cpp:334-339
-    }
+    if (!ignore_dim && !spr_dimension_match(r[4], r[5], r[6], qd, thr_dim, Sstar)) continue;  // PR.cpp:334-339
     found = i;
     break;                                                               // PR.cpp:353
   }
@@ -397,7 +421,7 @@ spr_tri_match_kernel(const double *__restrict__ dm, int tm, const double *__rest
         const double d[3] = {dd[3 * (size_t)j], dd[3 * (size_t)j + 1], dd[3 * (size_t)j + 2]};
         hit = spr_descriptor_match(m, d, thr);
       }
-      const unsigned mask = __ballot_sync(0xffffffffu, hit);
+      const unsigned mask = __ballot_sync(SPR_FULL, hit);
       if (FILL && hit) {
         const unsigned long long pos = base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
         if ((long long)pos < cap) { model_idx[pos] = i; data_idx[pos] = j; }

@@ -4,20 +4,26 @@
 
 #include "spr_types.h"
 
+#define SPR_WARP_CHUNKS 32  // chunks per work item (one warp); the sharding granule
+
 struct SprLaunch {
   uint32_t chunk_begin, chunk_end;  // chunks scored by this launch (ring range or everything)
   int32_t  shard_index, shard_count;
   unsigned long long *best_key;     // device: running max of spr_make_key
+  unsigned long long *work_counter; // device: next work item (zeroed by the launcher)
   int32_t *counts_out;              // device, optional: [(ordinal - ord_begin) * n_yaw + iyaw]
   long long counts_cap;
   unsigned long long ord_begin;
-  unsigned long long *stats;        // device, optional: [0] filter hits, [1] verified inliers
+  unsigned long long *stats;        // device, optional: [0] filter hits, [1] verified inliers,
+                                    //                   [2] query groups probed, [3] query groups skipped
 };
 
 enum { SPR_VARIANT_DIRECT = 0, SPR_VARIANT_QUEUED = 1 };
 
-// rotated query coordinates for every yaw: exact fp64 + fixed-point cell units (PR.cpp:246-258)
-cudaError_t spr_launch_rotate(const SprView &V, int32_t *qrotq, double *qrot, cudaStream_t st);
+// rotated query coordinates for every yaw: exact fp64 + fixed-point cell units in both layouts
+// + per-group bounding boxes (PR.cpp:246-258)
+cudaError_t spr_launch_rotate(const SprView &V, int32_t *qrotq_xy, int32_t *qrotq_yx, double *qrot, SprBox *gbox,
+                              cudaStream_t st);
 
 // the lattice search: every hypothesis of the chunks gets its exact inlier count
 cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int variant, int sm_count,

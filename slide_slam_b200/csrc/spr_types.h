@@ -10,6 +10,9 @@
 //   occupancy bitmap          : per label, 1 bit per cell of edge c = match_xy_step_size_, set when
 //                               a reference landmark of that label can be within match_threshold_
 //                               of a point falling in the cell (conservative)
+//   query group               : SPR_QGROUP consecutive query landmarks of one label in Morton
+//                               order; has a bounding box per yaw so that a warp can skip it when
+//                               none of its 1024 hypotheses can bring it over the label's cells
 #pragma once
 #include <stdint.h>
 
@@ -18,6 +21,9 @@
 #else
 #define SPR_HD inline
 #endif
+
+#define SPR_QGROUP 8
+#define SPR_Q_SENTINEL (-1073741824)  // -2^30: fixed-point coordinate of a padding query (never inside the grid)
 
 struct SprChunk {        // 32 bytes
   double   across;       // exact fp64 value of the fixed coordinate (x if dir == 0, y if dir == 1)
@@ -41,6 +47,11 @@ struct SprGrid {
   uint32_t label_stride; // plane_words[0] + plane_words[1]
 };
 
+struct SprBox { int32_t x0, x1, y0, y1; };  // fixed-point, [x0, x1) x [y0, y1); empty if x0 >= x1
+
+// one candidate of a marked cell: everything the exact test needs, in one 48-byte record
+struct SprCand { double x, y, d1, d2, d3; uint32_t ref; uint32_t pad; };
+
 // Everything the scoring code reads.  Pointers are valid in the executing address space
 // (device pointers for the kernels; host pointers for the test-only emulation).
 struct SprView {
@@ -49,21 +60,24 @@ struct SprView {
   uint32_t        n_chunks;
   int32_t         n_yaw;
   const double   *cs;         // [n_yaw][2] cos(yaw), sin(yaw) from host libm (PR.cpp:246-250)
-  int32_t         nq;         // query landmarks kept (label present in the reference), sorted
-  const int32_t  *qrotq;      // [n_yaw][nq][2] fixed-point cell coords of the rotated query
-  const double   *qrot;       // [n_yaw][nq][2] exact fp64 (c*qx + (-s)*qy, s*qx + c*qy)
-  const double   *qxy;        // [nq][2] query x, y (search frame)
-  const double   *qdims;      // [nq][3]
-  const int32_t  *label_seg;  // [n_labels + 1] segments of the sorted queries
-  const int32_t  *qlabel;     // [nq] label bucket of each sorted query
+  int32_t         nqp;        // query landmarks kept (label present in the reference), sorted by
+                              // (label, Morton), every label segment padded to SPR_QGROUP
+  int32_t         n_groups;   // nqp / SPR_QGROUP
+  const int32_t  *qrotq_xy;   // [n_yaw][nqp][2] fixed-point cell coords (x, y) of the rotated query
+  const int32_t  *qrotq_yx;   // [n_yaw][nqp][2] the same, swapped (y, x): layout read by dir-1 chunks
+  const SprBox   *gbox;       // [n_yaw][n_groups] bounding box of each query group's fixed coords
+  const double   *qrot;       // [n_yaw][nqp][2] exact fp64 (c*qx + (-s)*qy, s*qx + c*qy)
+  const double   *qxy;        // [nqp][2] query x, y (search frame)
+  const double   *qdims;      // [nqp][3]
+  const int32_t  *label_gseg; // [n_labels + 1] group index boundaries of the label segments
+  const int32_t  *qlabel;     // [nqp] label bucket of each sorted query; -1 for padding
   int32_t         n_labels;
   int32_t         n_ref;
-  const double   *ref_xy;     // [n_ref][2]
-  const double   *ref_dims;   // [n_ref][3]
+  const SprBox   *labelbox;   // [n_labels] fixed-point bounds of the label's marked cells
   const uint32_t *bitmap;     // [n_labels][plane dir0 | plane dir1]
-  const uint32_t *prefix;     // [n_labels][plane_words[0]] set bits before each dir-0 word
+  const uint32_t *cellword;   // [n_labels][plane_words[0]][2] (bits, set bits before this word)
   const uint32_t *cellinfo;   // [n_marked_cells][2] (start, count) into cand
-  const uint32_t *cand;       // reference indices, ascending inside a cell
+  const SprCand  *cand;       // candidates, reference index ascending inside a cell
   SprGrid         grid;
   double          Tstar;      // sqrt(d2) < match_threshold_  <=>  d2 < Tstar   (PR.cpp:332-333)
   double          Sstar;      // (sum / 3) < thr_dim          <=>  sum < Sstar  (PR.cpp:329,338)

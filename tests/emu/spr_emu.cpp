@@ -2,8 +2,11 @@
 //
 // Runs the exact per-thread code of the CUDA kernel (slide_slam_b200/csrc/spr_core.h) over the
 // host-built index structures, one "thread" (chunk) at a time, so that the chunking, ordinals,
-// bitmaps, candidate lists and fixed-point probing can be checked against the CPU oracle on a
-// box without a GPU.  It is compiled only by tests/ and is not part of the product library.
+// bitmaps, candidate lists, query groups and fixed-point probing can be checked against the CPU
+// oracle on a box without a GPU.  It is compiled only by tests/ and is not part of the product
+// library.
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -32,24 +35,22 @@ extern "C" int spr_emu_match_maps(const slide_pr_params *p, const double *ref7, 
   spr::QuerySet Q;
   rc = spr::build_query_set(R, qry7, n_qry, Q, err);
   if (rc != SLIDE_PR_OK) return fail(rc);
-  const int n_yaw = (int)L.yaw.size(), nq = Q.nq;
-  std::vector<double> qrot(2 * (size_t)std::max(1, n_yaw * nq));
-  std::vector<int32_t> qrotq(2 * (size_t)std::max(1, n_yaw * nq));
+  const int n_yaw = (int)L.yaw.size(), nqp = Q.nqp, n_groups = nqp / SPR_QGROUP;
+  const size_t nrot = (size_t)std::max(1, n_yaw * nqp);
+  std::vector<double> qrot(2 * nrot);
+  std::vector<int32_t> qxy_fx(2 * nrot), qyx_fx(2 * nrot);
+  std::vector<SprBox> gbox((size_t)std::max(1, n_yaw * n_groups));
   for (int a = 0; a < n_yaw; a++)
-    for (int s = 0; s < nq; s++) {
-      double rx, ry;
-      spr_rotate(L.cs[2 * a], L.cs[2 * a + 1], Q.qxy[2 * s], Q.qxy[2 * s + 1], &rx, &ry);
-      const size_t qi = (size_t)a * nq + s;
-      qrot[2 * qi] = rx; qrot[2 * qi + 1] = ry;
-      qrotq[2 * qi] = spr_fx(rx - R.grid.g0x, R.grid.S);
-      qrotq[2 * qi + 1] = spr_fx(ry - R.grid.g0y, R.grid.S);
-    }
+    for (int g = 0; g < n_groups; g++)
+      spr_rotate_group(L.cs.data(), Q.qxy.data(), Q.qlabel.data(), R.grid, nqp, n_groups, a, g, qxy_fx.data(),
+                       qyx_fx.data(), qrot.data(), gbox.data());
   SprView V{};
   V.lat = L.lat.data(); V.chunks = L.chunks.data(); V.n_chunks = (uint32_t)L.chunks.size();
-  V.n_yaw = n_yaw; V.cs = L.cs.data(); V.nq = nq; V.qrotq = qrotq.data(); V.qrot = qrot.data();
-  V.qxy = Q.qxy.data(); V.qdims = Q.qdims.data(); V.label_seg = Q.label_seg.data();
-  V.n_labels = (int)R.labels.size(); V.n_ref = n_ref; V.ref_xy = R.ref_xy.data(); V.ref_dims = R.ref_dims.data();
-  V.bitmap = R.bitmap.data(); V.prefix = R.prefix.data(); V.cellinfo = R.cellinfo.data(); V.cand = R.cand.data();
+  V.n_yaw = n_yaw; V.cs = L.cs.data(); V.nqp = nqp; V.n_groups = n_groups;
+  V.qrotq_xy = qxy_fx.data(); V.qrotq_yx = qyx_fx.data(); V.gbox = gbox.data(); V.qrot = qrot.data();
+  V.qxy = Q.qxy.data(); V.qdims = Q.qdims.data(); V.label_gseg = Q.label_gseg.data(); V.qlabel = Q.qlabel.data();
+  V.n_labels = (int)R.labels.size(); V.n_ref = n_ref; V.labelbox = R.labelbox.data();
+  V.bitmap = R.bitmap.data(); V.cellword = R.cellword.data(); V.cellinfo = R.cellinfo.data(); V.cand = R.cand.data();
   V.grid = R.grid; V.Tstar = R.Tstar; V.Sstar = R.Sstar; V.thr_dim = p->match_threshold_dimension;
   V.ignore_dim = p->ignore_dimension;
   const SprGrid &G = V.grid;
@@ -60,21 +61,29 @@ extern "C" int spr_emu_match_maps(const slide_pr_params *p, const double *ref7, 
     const SprChunk &ch = V.chunks[ci];
     const int d = (int)ch.dir;
     const int32_t aq0 = spr_fx(ch.across, G.S), bq0 = spr_fx(V.lat[ch.along_off], G.S);
+    const int32_t aqb = spr_bias_across(aq0, G.F), bqb = spr_bias_along(bq0, G.F);
+    // this chunk's own window (the kernel uses the union over the warp's 32 chunks: weaker skip)
+    const int32_t X0 = d ? bq0 : aq0, X1 = d ? bq0 + (32 << G.F) : aq0;
+    const int32_t Y0 = d ? aq0 : bq0, Y1 = d ? aq0 : bq0 + (32 << G.F);
+    const int32_t *qfx = d ? V.qrotq_yx : V.qrotq_xy;
     for (int a = 0; a < n_yaw; a++) {
       uint32_t cnt[32] = {0};
       for (int l = 0; l < V.n_labels; l++) {
         const uint32_t *plane = V.bitmap + (size_t)l * G.label_stride + (d ? G.plane_words[0] : 0);
-        for (int s = V.label_seg[l]; s < V.label_seg[l + 1]; s++) {
-          const size_t qi = (size_t)a * nq + s;
-          const int32_t qx = V.qrotq[2 * qi], qy = V.qrotq[2 * qi + 1];
-          int32_t na, nb;
-          uint32_t H = spr_probe(plane, G.W[d], G.R[d], G.maxbit[d], G.F, aq0 + (d ? qy : qx), bq0 + (d ? qx : qy), ch.valid, &na, &nb);
-          while (H) {
-            const int b = SPR_FFS(H) - 1;
-            H &= H - 1;
-            hits++;
-            int32_t first;
-            if (spr_verify_hit(V, ch, l, a, s, na, nb, b, &first)) cnt[b]++;
+        for (int g = V.label_gseg[l]; g < V.label_gseg[l + 1]; g++) {
+          if (!spr_group_visible(V.gbox[(size_t)a * n_groups + g], V.labelbox[l], X0, X1, Y0, Y1)) continue;
+          for (int k = 0; k < SPR_QGROUP; k++) {
+            const int s = g * SPR_QGROUP + k;
+            const size_t qi = (size_t)a * nqp + s;
+            const int32_t asum = aqb + qfx[2 * qi], bsum = bqb + qfx[2 * qi + 1];
+            uint32_t H = spr_probe(plane, (uint32_t)G.W[d], (uint32_t)G.R[d] - 1u, (uint32_t)G.maxbit[d], G.F, asum, bsum, ch.valid);
+            while (H) {
+              const int b = SPR_FFS(H) - 1;
+              H &= H - 1;
+              hits++;
+              int32_t first;
+              if (spr_verify_hit(V, ch, a, s, asum, bsum, b, &first)) cnt[b]++;
+            }
           }
         }
       }
