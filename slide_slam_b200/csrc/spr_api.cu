@@ -64,7 +64,7 @@ struct slide_pr_handle {
   spr::QuerySet Q;
   // device side
   DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_cellword,
-      d_cellinfo, d_cand, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
+      d_cand, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
   SprView V{};
   std::vector<int32_t> h_match;
 };
@@ -155,7 +155,7 @@ void slide_pr_destroy(slide_pr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (DevBuf *b : {&h->d_lat, &h->d_chunks, &h->d_cs, &h->d_qxy, &h->d_qdims, &h->d_labelseg, &h->d_qlabel,
-                    &h->d_labelbox, &h->d_gbox, &h->d_bitmap, &h->d_cellword, &h->d_cellinfo, &h->d_cand, &h->d_qrot,
+                    &h->d_labelbox, &h->d_gbox, &h->d_bitmap, &h->d_cellword, &h->d_cand, &h->d_qrot,
                     &h->d_qrotq, &h->d_qrotq_yx, &h->d_work, &h->d_ref7, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps, &h->d_tri, &h->d_tri_out})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -220,7 +220,6 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   if ((rc = upload(h, h->d_labelbox, h->R.labelbox, st))) return rc;
   if ((rc = upload(h, h->d_bitmap, h->R.bitmap, st))) return rc;
   if ((rc = upload(h, h->d_cellword, h->R.cellword, st))) return rc;
-  if ((rc = upload(h, h->d_cellinfo, h->R.cellinfo, st))) return rc;
   if ((rc = upload(h, h->d_cand, h->R.cand, st))) return rc;
   if ((rc = upload_raw(h, h->d_ref7, ref7, (size_t)n_ref * 7 * sizeof(double), st))) return rc;
   if ((rc = upload_raw(h, h->d_qry7, qry7, (size_t)n_qry * 7 * sizeof(double), st))) return rc;
@@ -251,7 +250,6 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   V.labelbox = h->d_labelbox.as<SprBox>();
   V.bitmap = h->d_bitmap.as<uint32_t>();
   V.cellword = h->d_cellword.as<uint32_t>();
-  V.cellinfo = h->d_cellinfo.as<uint32_t>();
   V.cand = h->d_cand.as<SprCand>();
   V.grid = h->R.grid;
   V.Tstar = h->R.Tstar;

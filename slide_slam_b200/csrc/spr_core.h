@@ -111,9 +111,18 @@ SPR_HD uint32_t spr_probe(const uint32_t *plane, uint32_t W, uint32_t Rm1, uint3
                           int32_t a, int32_t b, uint32_t valid) {
   const uint32_t row = SPR_UMIN((uint32_t)(a >> F), Rm1);    // rows 0 and R-1 are all-zero
   const uint32_t bit = SPR_UMIN((uint32_t)(b >> F), maxbit);  // word 0 and words >= maxbit/32 are all-zero
-  const uint32_t wi = row * W + (bit >> 5);
-  const uint32_t w0 = plane[wi], w1 = plane[wi + 1];
-  return SPR_FUNNEL_R(w0, w1, bit & 31u) & valid;
+  const uint32_t *p = plane + (row * W + (bit >> 5));
+  return SPR_FUNNEL_R(p[0], p[1], bit) & valid;  // the funnel shift uses the low 5 bits of `bit`
+}
+
+// Address of a hit's cell in the dir-0 ("canonical") plane, packed as (word index << 5) | bit:
+// what the verification needs to rank the cell.  a / b are the biased sums of the probe, bitno
+// the hit's bit inside the chunk.
+SPR_HD uint32_t spr_cell_code(const SprGrid &G, uint32_t dir, int32_t a, int32_t b, int32_t bitno) {
+  const uint32_t row = (uint32_t)(a >> G.F), bit = (uint32_t)(b >> G.F) + (uint32_t)bitno;
+  // dir 0: x + 1 = row, y + 32 = bit.   dir 1: y + 32 = row + 31, x + 1 = bit - 31.
+  const uint32_t xrow = dir ? bit - 31u : row, ybit = dir ? row + 31u : bit;
+  return ((xrow * (uint32_t)G.W[0] + (ybit >> 5)) << 5) | (ybit & 31u);
 }
 
 // May query group `g` (box of its fixed coords) land on label box `lb` for any translation of a
@@ -123,58 +132,53 @@ SPR_HD bool spr_group_visible(const SprBox &g, const SprBox &lb, int32_t X0, int
   return (g.x1 > lb.x0 - X1) && (g.x0 < lb.x1 - X0) && (g.y1 > lb.y0 - Y1) && (g.y0 < lb.y1 - Y0);
 }
 
-// Exact verification of one occupied cell (nx, ny) of label l for a query point whose rotated
-// coordinates are (rx, ry), under translation (tx, ty).  Returns true iff some reference
-// landmark passes the reference's predicate (PR.cpp:299-355); *first_ref receives the smallest
-// such reference index (candidate lists are ascending).
-SPR_HD bool spr_verify_cell(const SprView &V, int32_t l, int32_t nx, int32_t ny, double rx, double ry,
+// Exact verification of one occupied cell (given by its spr_cell_code) of label l for a query
+// point whose rotated coordinates are (rx, ry), under translation (tx, ty).  Returns true iff
+// some reference landmark passes the reference's predicate (PR.cpp:299-355); *first_ref receives
+// the smallest such reference index (a cell's candidates are chained in ascending order).
+SPR_HD bool spr_verify_cell(const SprView &V, int32_t l, uint32_t code, double rx, double ry,
                             double tx, double ty, const double *qd, int32_t *first_ref) {
-  const SprGrid &G = V.grid;
   // rank of the cell among the marked cells (dir-0 plane: rows = x, bits = y)
-  const uint32_t bit = (uint32_t)(ny + 32);
-  const size_t widx = (size_t)l * G.plane_words[0] + (uint32_t)(nx + 1) * (uint32_t)G.W[0] + (bit >> 5);
+  const size_t widx = (size_t)l * V.grid.plane_words[0] + (code >> 5);
   const uint32_t word = V.cellword[2 * widx], before = V.cellword[2 * widx + 1];
-  const uint32_t rank = before + (uint32_t)SPR_POPC(word & ((1u << (bit & 31u)) - 1u));
-  const uint32_t start = V.cellinfo[2 * (size_t)rank], count = V.cellinfo[2 * (size_t)rank + 1];
-  for (uint32_t k = 0; k < count; k++) {
-    const SprCand &c = V.cand[start + k];
-    if (!spr_distance_match(rx, ry, tx, ty, c.x, c.y, V.Tstar)) continue;
-    if (!V.ignore_dim && !spr_dimension_match(c.d1, c.d2, c.d3, qd, V.thr_dim, V.Sstar)) continue;
-    *first_ref = (int32_t)c.ref;
-    return true;
+  uint32_t k = before + (uint32_t)SPR_POPC(word & ((1u << (code & 31u)) - 1u));
+  for (;;) {
+    const SprCand &c = V.cand[k];
+    if (spr_distance_match(rx, ry, tx, ty, c.x, c.y, V.Tstar) &&
+        (V.ignore_dim || spr_dimension_match(c.d1, c.d2, c.d3, qd, V.thr_dim, V.Sstar))) {
+      *first_ref = (int32_t)c.ref;
+      return true;
+    }
+    if (c.next == 0u) return false;
+    k = c.next;
   }
-  return false;
 }
 
 // Verification of one filter hit of the lattice kernel: query js (sorted order) under yaw a and
 // the translation of bit b of `ch`.  a_sum / b_sum are the biased sums that produced the hit.
 SPR_HD bool spr_verify_hit(const SprView &V, const SprChunk &ch, int32_t a, int32_t js, int32_t a_sum,
                            int32_t b_sum, int32_t b, int32_t *first_ref) {
-  const int32_t F = V.grid.F;
-  const int32_t na = (a_sum >> F) - 1, nalong = (b_sum >> F) - 32 + b;
-  const int32_t nx = ch.dir ? nalong : na;
-  const int32_t ny = ch.dir ? na : nalong;
   // the hypothesis' translation, exactly as the reference's accumulated lattice value
   const double along = V.lat[ch.along_off + (uint32_t)b];
   const double tx = ch.dir ? along : ch.across;
   const double ty = ch.dir ? ch.across : along;
   const size_t qi = (size_t)a * (size_t)V.nqp + (size_t)js;
-  return spr_verify_cell(V, V.qlabel[js], nx, ny, V.qrot[2 * qi], V.qrot[2 * qi + 1], tx, ty,
-                         V.qdims + 3 * (size_t)js, first_ref);
+  return spr_verify_cell(V, V.qlabel[js], spr_cell_code(V.grid, ch.dir, a_sum, b_sum, b), V.qrot[2 * qi],
+                         V.qrot[2 * qi + 1], tx, ty, V.qdims + 3 * (size_t)js, first_ref);
 }
 
 // Occupancy test of a single point (general hypothesis lists): fixed-point cell of
 // (xt - g0x, yt - g0y); returns false when the cell is outside the grid or unmarked.
-SPR_HD bool spr_point_cell(const SprView &V, int32_t l, double xt, double yt, int32_t *nx, int32_t *ny) {
+SPR_HD bool spr_point_cell(const SprView &V, int32_t l, double xt, double yt, uint32_t *code) {
   const SprGrid &G = V.grid;
   const double ux = SPR_DMUL(SPR_DSUB(xt, G.g0x), G.S), uy = SPR_DMUL(SPR_DSUB(yt, G.g0y), G.S);
   if (!(ux >= 0.0 && uy >= 0.0 && ux < 1073741824.0 && uy < 1073741824.0)) return false;
   const int32_t cx = (int32_t)ux >> G.F, cy = (int32_t)uy >> G.F;
   if (cx >= G.GX || cy >= G.GY) return false;
   const uint32_t bit = (uint32_t)(cy + 32);
-  const uint32_t word = V.bitmap[(size_t)l * G.label_stride + (uint32_t)(cx + 1) * (uint32_t)G.W[0] + (bit >> 5)];
-  *nx = cx;
-  *ny = cy;
+  const uint32_t wloc = (uint32_t)(cx + 1) * (uint32_t)G.W[0] + (bit >> 5);
+  const uint32_t word = V.bitmap[(size_t)l * G.label_stride + wloc];
+  *code = (wloc << 5) | (bit & 31u);
   return (word >> (bit & 31u)) & 1u;
 }
 

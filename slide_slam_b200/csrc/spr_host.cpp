@@ -269,7 +269,7 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
     G.W[d] = W;
     G.maxbit[d] = 32 * (W - 2);
     const uint64_t words = (uint64_t)G.R[d] * (uint64_t)W;
-    if (words >= (1ull << 31)) { err = "occupancy bitmap too large"; return SLIDE_PR_ERR_UNSUPPORTED; }
+    if (words >= (1ull << 27)) { err = "occupancy bitmap too large (step too fine for this map extent)"; return SLIDE_PR_ERR_UNSUPPORTED; }
     G.plane_words[d] = (uint32_t)words;
   }
   G.label_stride = G.plane_words[0] + G.plane_words[1];
@@ -318,12 +318,25 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
     return a.key != b.key ? a.key < b.key : a.ref < b.ref;
   });
   if (entries.size() >= (1ull << 32)) { err = "candidate lists exceed 2^32 entries"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  // cand[rank] = first candidate of the cell of that rank; extra candidates of a cell are
+  // appended behind the n_cells first ones and chained in ascending reference order
+  size_t n_cells = 0;
+  for (size_t e = 0; e < entries.size(); e++)
+    if (e == 0 || entries[e].key != entries[e - 1].key) n_cells++;
   R.cand.resize(entries.size());
-  for (size_t e = 0; e < entries.size(); e++) {
-    if (e == 0 || entries[e].key != entries[e - 1].key) { R.cellinfo.push_back((uint32_t)e); R.cellinfo.push_back(0u); }
-    R.cellinfo.back()++;
-    const double *r = ref7 + 7 * (size_t)entries[e].ref;
-    R.cand[e] = SprCand{r[1], r[2], r[4], r[5], r[6], entries[e].ref, 0u};
+  {
+    size_t rank = 0, extra = n_cells, prev = 0;
+    for (size_t e = 0; e < entries.size(); e++) {
+      const double *r = ref7 + 7 * (size_t)entries[e].ref;
+      const SprCand c{r[1], r[2], r[4], r[5], r[6], entries[e].ref, 0u};
+      if (e == 0 || entries[e].key != entries[e - 1].key) {
+        prev = rank++;
+      } else {
+        R.cand[prev].next = (uint32_t)extra;
+        prev = extra++;
+      }
+      R.cand[prev] = c;
+    }
   }
   // (word, set bits before it) over the dir-0 planes, label-major == rank order of the marked cells
   uint32_t running = 0;
@@ -336,13 +349,12 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
       running += (uint32_t)__builtin_popcount(pl0[w]);
     }
   }
-  if ((size_t)running * 2 != R.cellinfo.size()) { err = "internal: rank / cell list mismatch"; return SLIDE_PR_ERR_INTERNAL; }
+  if ((size_t)running != n_cells) { err = "internal: rank / cell list mismatch"; return SLIDE_PR_ERR_INTERNAL; }
   R.labelbox.resize((size_t)std::max(n_labels, 1));
   for (int l = 0; l < std::max(n_labels, 1); l++) {
     if (cb[l].x0 > cb[l].x1) { R.labelbox[l] = SprBox{0, -(1 << 30), 0, -(1 << 30)}; continue; }  // empty: never visible
     R.labelbox[l] = SprBox{cb[l].x0 << F, (cb[l].x1 + 1) << F, cb[l].y0 << F, (cb[l].y1 + 1) << F};
   }
-  if (R.cellinfo.empty()) { R.cellinfo.assign(2, 0u); }
   if (R.cand.empty()) R.cand.assign(1, SprCand{0, 0, 0, 0, 0, 0u, 0u});
   return SLIDE_PR_OK;
 }

@@ -43,8 +43,7 @@ struct RefIndex {
   SprGrid grid{};
   std::vector<uint32_t> bitmap;     // [n_labels][plane0 | plane1]
   std::vector<uint32_t> cellword;   // [n_labels][plane_words[0]][2] (bits, set bits before)
-  std::vector<uint32_t> cellinfo;   // [n_cells][2] (start, count)
-  std::vector<SprCand> cand;        // candidates of every marked cell, reference index ascending
+  std::vector<SprCand> cand;        // [n_cells] first candidate per cell rank, then chained extras
   std::vector<SprBox> labelbox;     // [n_labels] fixed-point bounds of the label's marked cells
   double Tstar = 0, Sstar = 0;
   int n_ref = 0;

@@ -12,7 +12,7 @@
 //     bitmap and obtains the 32 hypotheses' filter bits with one funnel shift (spr_probe);
 //   * set bits ("filter hits", well under 1 % of the probes) are compacted through a per-warp
 //     shared-memory queue (warp prefix-sum over popcounts) and verified 32 at a time in exact,
-//     non-fused fp64 against the cell's candidate list (spr_verify_cell) -- the reference's own
+//     non-fused fp64 against the cell's candidates (spr_verify_cell) -- the reference's own
 //     predicate, so every hypothesis gets its exact inlier count;
 //   * per-hypothesis counters live in shared memory; the best (count, canonical index) key is
 //     reduced with shuffles and one 64-bit atomicMax per warp.
@@ -26,7 +26,9 @@
 
 #define SPR_BLOCK 256
 #define SPR_WARPS (SPR_BLOCK / 32)
-#define SPR_QCAP 512            // per-warp hit queue, records
+#define SPR_QCAP 512             // per-warp hit queue, records (2 words each)
+#define SPR_CNT_PITCH 33         // counters: cnt[lane * 33 + bit] -> conflict-free for bit runs of one lane
+#define SPR_WARP_SMEM (32 * SPR_CNT_PITCH + 2 * SPR_QCAP)  // words per warp
 #define SPR_FULL 0xffffffffu
 
 // ---------------------------------------------------------------------------------------------
@@ -54,45 +56,38 @@ cudaError_t spr_launch_rotate(const SprView &V, int32_t *qrotq_xy, int32_t *qrot
 // lattice scoring
 // ---------------------------------------------------------------------------------------------
 struct WarpState {
-  uint32_t *cnt;    // [32 bits][32 lanes] inlier counters of the warp's 1024 hypotheses
-  uint32_t *queue;  // [SPR_QCAP] pending filter hits: js << 10 | owner lane << 5 | bit
+  uint32_t *cnt;    // [32 lanes][33] inlier counters of the warp's 1024 hypotheses
+  uint2 *queue;     // [SPR_QCAP] pending filter hits: x = js << 10 | owner lane << 5 | bit, y = cell code
   int qcount;       // warp-uniform
 };
 
-// exact verification of one hit given the owning chunk's parameters
-__device__ __forceinline__ bool spr_verify_owned(const SprView &V, int a, int js, int b, int32_t o_aqb, int32_t o_bqb,
+// exact verification of one hit: query js (label l) under yaw a against the cell `code`, for the
+// translation (bit b) of the chunk described by (dir, along_off, across)
+__device__ __forceinline__ bool spr_verify_owned(const SprView &V, int l, int a, int js, int b, uint32_t code,
                                                  uint32_t o_dir, uint32_t o_off, double o_across) {
-  const SprGrid &G = V.grid;
   const size_t qi = (size_t)a * (size_t)V.nqp + (size_t)js;
-  const int2 qq = __ldg(reinterpret_cast<const int2 *>(V.qrotq_xy) + qi);
   const double2 r = __ldg(reinterpret_cast<const double2 *>(V.qrot) + qi);
-  const int l = __ldg(V.qlabel + js);
   const double along = __ldg(V.lat + o_off + b);
-  const int32_t na = ((o_aqb + (o_dir ? qq.y : qq.x)) >> G.F) - 1;
-  const int32_t nb = ((o_bqb + (o_dir ? qq.x : qq.y)) >> G.F) - 32 + b;
-  const int32_t nx = o_dir ? nb : na, ny = o_dir ? na : nb;
   const double tx = o_dir ? along : o_across, ty = o_dir ? o_across : along;
   int32_t first;
-  return spr_verify_cell(V, l, nx, ny, r.x, r.y, tx, ty, V.qdims + 3 * (size_t)js, &first);
+  return spr_verify_cell(V, l, code, r.x, r.y, tx, ty, V.qdims + 3 * (size_t)js, &first);
 }
 
 // Verify up to 32 queued hits, one per lane.  Chunk parameters of the owning lane come through
 // shuffles; every lane executes the shuffles.
-__device__ __forceinline__ void spr_drain32(const SprView &V, WarpState &ws, int a, int lane, int32_t aqb,
-                                            int32_t bqb, uint32_t dir, uint32_t along_off, double across,
-                                            unsigned long long &n_inl) {
+__device__ __forceinline__ void spr_drain32(const SprView &V, WarpState &ws, int l, int a, int lane, uint32_t dir,
+                                            uint32_t along_off, double across, unsigned long long &n_inl) {
   const int n = ws.qcount < 32 ? ws.qcount : 32;
   const bool active = lane < n;
-  const uint32_t rec = active ? ws.queue[ws.qcount - n + lane] : 0u;
-  const int owner = (rec >> 5) & 31, b = rec & 31;
-  const int js = (int)(rec >> 10);
-  const int32_t o_aqb = __shfl_sync(SPR_FULL, aqb, owner);
-  const int32_t o_bqb = __shfl_sync(SPR_FULL, bqb, owner);
+  uint2 rec = make_uint2(0u, 0u);
+  if (active) rec = ws.queue[ws.qcount - n + lane];
+  const int owner = (rec.x >> 5) & 31, b = rec.x & 31;
+  const int js = (int)(rec.x >> 10);
   const uint32_t o_dir = __shfl_sync(SPR_FULL, dir, owner);
   const uint32_t o_off = __shfl_sync(SPR_FULL, along_off, owner);
   const double o_across = __shfl_sync(SPR_FULL, across, owner);
-  if (active && spr_verify_owned(V, a, js, b, o_aqb, o_bqb, o_dir, o_off, o_across)) {
-    atomicAdd(&ws.cnt[b * 32 + owner], 1u);
+  if (active && spr_verify_owned(V, l, a, js, b, rec.y, o_dir, o_off, o_across)) {
+    atomicAdd(&ws.cnt[owner * SPR_CNT_PITCH + b], 1u);
     n_inl++;
   }
   ws.qcount -= n;
@@ -105,8 +100,8 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
   extern __shared__ uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpState ws;
-  ws.cnt = smem + warp * 1024;
-  ws.queue = smem + SPR_WARPS * 1024 + warp * SPR_QCAP;
+  ws.cnt = smem + warp * SPR_WARP_SMEM;
+  ws.queue = reinterpret_cast<uint2 *>(ws.cnt + 32 * SPR_CNT_PITCH);  // 1056 words: 8-byte aligned
   ws.qcount = 0;
   const SprGrid &G = V.grid;
   const int32_t F = G.F;
@@ -129,7 +124,7 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
       ord_base = ch.ord_base; ord_stride = ch.ord_stride; dir = ch.dir;
     }
 #pragma unroll
-    for (int b = 0; b < 32; b++) ws.cnt[b * 32 + lane] = 0u;
+    for (int b = 0; b < 32; b++) ws.cnt[lane * SPR_CNT_PITCH + b] = 0u;
     const int32_t aq0 = spr_fx(across, G.S);
     const int32_t bq0 = spr_fx(__ldg(V.lat + along_off), G.S);
     const int32_t aqb = spr_bias_across(aq0, F), bqb = spr_bias_along(bq0, F);
@@ -142,20 +137,23 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
     const int32_t Y0 = __reduce_min_sync(SPR_FULL, live ? ly0 : big), Y1 = __reduce_max_sync(SPR_FULL, live ? ly1 : -big);
     __syncwarp();
     const uint32_t W = (uint32_t)G.W[dir], Rm1 = (uint32_t)G.R[dir] - 1u, maxbit = (uint32_t)G.maxbit[dir];
-    const uint32_t *__restrict__ plane0 = V.bitmap + (dir ? G.plane_words[0] : 0u);
-    const int4 *__restrict__ qa =
-        reinterpret_cast<const int4 *>((dir ? V.qrotq_yx : V.qrotq_xy) + 2 * (size_t)a * (size_t)V.nqp);
-    const int4 *__restrict__ gb = reinterpret_cast<const int4 *>(V.gbox) + (size_t)a * (size_t)V.n_groups;
+    const int2 *__restrict__ qa2 =
+        reinterpret_cast<const int2 *>((dir ? V.qrotq_yx : V.qrotq_xy) + 2 * (size_t)a * (size_t)V.nqp);
+    const int4 *__restrict__ qa = reinterpret_cast<const int4 *>(qa2);
 
     if (X0 <= X1) {  // at least one live lane
       for (int l = 0; l < V.n_labels; l++) {
-        const uint32_t *__restrict__ plane = plane0 + (size_t)l * G.label_stride;
+        // this lane's bitmap plane as a materialised 64-bit pointer: one IMAD.WIDE per probe
+        const uint32_t *plane = V.bitmap + ((size_t)l * G.label_stride + (dir ? G.plane_words[0] : 0u));
+        asm volatile("" : "+l"(plane));
         const SprBox lb = V.labelbox[l];
         // a group is visible iff gx1 > tx_lo && gx0 < tx_hi && gy1 > ty_lo && gy0 < ty_hi
         const int32_t tx_lo = lb.x0 - X1, tx_hi = lb.x1 - X0, ty_lo = lb.y0 - Y1, ty_hi = lb.y1 - Y0;
-        const int g1 = V.label_gseg[l + 1];
-        for (int g = V.label_gseg[l]; g < g1; g++) {
-          const int4 box = __ldg(gb + g);  // (x0, x1, y0, y1), same address for the whole warp
+        const int g0 = V.label_gseg[l], g1 = V.label_gseg[l + 1];
+        const int4 *gbp = reinterpret_cast<const int4 *>(V.gbox) + ((size_t)a * (size_t)V.n_groups + (size_t)g0);
+        const int4 *qgp = qa + (size_t)g0 * (SPR_QGROUP / 2);
+        for (int g = g0; g < g1; g++, gbp++, qgp += SPR_QGROUP / 2) {
+          const int4 box = __ldg(gbp);  // (x0, x1, y0, y1), same address for the whole warp
           if (!(box.y > tx_lo && box.x < tx_hi && box.w > ty_lo && box.z < ty_hi)) {
             if (STATS) n_skipped++;
             continue;
@@ -164,7 +162,7 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
           uint32_t H[SPR_QGROUP];
 #pragma unroll
           for (int u = 0; u < SPR_QGROUP / 2; u++) {
-            const int4 v = __ldg(qa + (size_t)g * (SPR_QGROUP / 2) + u);  // two queries: (across, along) x 2
+            const int4 v = __ldg(qgp + u);  // two queries: (across, along) x 2
             H[2 * u] = spr_probe(plane, W, Rm1, maxbit, F, aqb + v.x, bqb + v.y, SPR_FULL);
             H[2 * u + 1] = spr_probe(plane, W, Rm1, maxbit, F, aqb + v.z, bqb + v.w, SPR_FULL);
           }
@@ -194,41 +192,52 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
 #pragma unroll
             for (int u = 0; u < SPR_QGROUP; u++) {
               uint32_t h = H[u];
+              if (h == 0u) continue;
+              const int2 q = __ldg(qa2 + js0 + u);
               while (h) {
                 const int b = __ffs(h) - 1;
                 h &= h - 1;
-                if (spr_verify_owned(V, a, js0 + u, b, aqb, bqb, dir, along_off, across)) {
-                  atomicAdd(&ws.cnt[b * 32 + lane], 1u);  // atomics: queued hits may target our column
+                if (spr_verify_owned(V, l, a, js0 + u, b, spr_cell_code(G, dir, aqb + q.x, bqb + q.y, b), dir, along_off,
+                                     across)) {
+                  atomicAdd(&ws.cnt[lane * SPR_CNT_PITCH + b], 1u);  // atomics: queued hits may target our counters
                   n_inl++;
                 }
               }
             }
             continue;
           }
-          while (ws.qcount + total > SPR_QCAP) spr_drain32(V, ws, a, lane, aqb, bqb, dir, along_off, across, n_inl);
+          while (ws.qcount + total > SPR_QCAP) spr_drain32(V, ws, l, a, lane, dir, along_off, across, n_inl);
           int pos = ws.qcount + incl - n;
 #pragma unroll
           for (int u = 0; u < SPR_QGROUP; u++) {
             uint32_t h = H[u];
+            if (h == 0u) continue;
+            const int2 q = __ldg(qa2 + js0 + u);  // L1 hit: loaded a moment ago by the probe
+            // a cell code is the cell's linear bit address in the dir-0 plane: bit b of the chunk
+            // is b bits further along the same row (dir 0) or b rows further (dir 1)
+            const uint32_t code0 = spr_cell_code(G, dir, aqb + q.x, bqb + q.y, 0);
+            const uint32_t code_step = dir ? ((uint32_t)G.W[0] << 5) : 1u;
+            const uint32_t rec0 = ((uint32_t)(js0 + u) << 10) | ((uint32_t)lane << 5);
             while (h) {
               const int b = __ffs(h) - 1;
               h &= h - 1;
-              ws.queue[pos++] = ((uint32_t)(js0 + u) << 10) | ((uint32_t)lane << 5) | (uint32_t)b;
+              ws.queue[pos++] = make_uint2(rec0 | (uint32_t)b, code0 + (uint32_t)b * code_step);
             }
           }
           ws.qcount += total;
           __syncwarp();
-          while (ws.qcount >= 32) spr_drain32(V, ws, a, lane, aqb, bqb, dir, along_off, across, n_inl);
+          while (ws.qcount >= 32) spr_drain32(V, ws, l, a, lane, dir, along_off, across, n_inl);
         }
+        // the queue only ever holds hits of the current label
+        while (ws.qcount > 0) spr_drain32(V, ws, l, a, lane, dir, along_off, across, n_inl);
       }
-      while (ws.qcount > 0) spr_drain32(V, ws, a, lane, aqb, bqb, dir, along_off, across, n_inl);
       __syncwarp();
       // each lane scans the 32 hypotheses of its chunk
       uint32_t v = valid;
       while (v) {
         const int b = __ffs(v) - 1;
         v &= v - 1;
-        const uint32_t c = ws.cnt[b * 32 + lane];
+        const uint32_t c = ws.cnt[lane * SPR_CNT_PITCH + b];
         const unsigned long long ord = (unsigned long long)ord_base + (unsigned long long)b * ord_stride;
         const unsigned long long key = spr_make_key(c, ord * (unsigned long long)V.n_yaw + (unsigned long long)a);
         best = key > best ? key : best;
@@ -292,7 +301,7 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int v
   K2.shard_index = si;
   K2.shard_count = sc;
   const long long n_items = (long long)n_wg_local * V.n_yaw;
-  const size_t smem = (size_t)SPR_WARPS * (1024 + SPR_QCAP) * sizeof(uint32_t);
+  const size_t smem = (size_t)SPR_WARPS * SPR_WARP_SMEM * sizeof(uint32_t);
   const long long max_grid = (long long)sm_count * 4;
   const long long want = (n_items + SPR_WARPS - 1) / SPR_WARPS;
   const int grid = (int)(want < max_grid ? want : max_grid);
@@ -304,178 +313,3 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int v
 }
 
 // ---------------------------------------------------------------------------------------------
-// explicit hypothesis list: warp per hypothesis, lanes stride over the query landmarks
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-spr_score_list_kernel(SprView V, const double *__restrict__ hyps4, long long n, int32_t *__restrict__ counts_out,
-                      unsigned long long *best_key) {
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  unsigned long long best = 0ull;
-  for (long long h = warp0; h < n; h += n_warps) {
-    const double c = hyps4[4 * h], s = hyps4[4 * h + 1], tx = hyps4[4 * h + 2], ty = hyps4[4 * h + 3];
-    int cnt = 0;
-    for (int js = lane; js < V.nqp; js += 32) {
-      const int l = V.qlabel[js];
-      if (l < 0) continue;  // padding
-      double rx, ry;
-      spr_rotate(c, s, V.qxy[2 * (size_t)js], V.qxy[2 * (size_t)js + 1], &rx, &ry);
-      const double xt = SPR_DADD(rx, tx), yt = SPR_DADD(ry, ty);
-      int32_t nx, ny, first;
-      if (spr_point_cell(V, l, xt, yt, &nx, &ny) &&
-          spr_verify_cell(V, l, nx, ny, rx, ry, tx, ty, V.qdims + 3 * (size_t)js, &first))
-        cnt++;
-    }
-#pragma unroll
-    for (int dlt = 16; dlt > 0; dlt >>= 1) cnt += __shfl_xor_sync(SPR_FULL, cnt, dlt);
-    if (lane == 0) {
-      if (counts_out) counts_out[h] = cnt;
-      const unsigned long long key = spr_make_key((uint32_t)cnt, (unsigned long long)h);
-      best = key > best ? key : best;
-    }
-  }
-  if (lane == 0 && best != 0ull) atomicMax(best_key, best);
-}
-
-cudaError_t spr_launch_score_list(const SprView &V, const double *hyps4, long long n, int32_t *counts_out,
-                                  unsigned long long *best_key, int sm_count, cudaStream_t st) {
-  if (n <= 0) return cudaSuccess;
-  const long long want = (n + 7) / 8;
-  const long long cap = (long long)sm_count * 8;
-  spr_score_list_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(V, hyps4, n, counts_out, best_key);
-  return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------
-// correspondences of the winner: the reference's own double loop (PR.cpp:281-357), one thread
-// per query object, reference objects in ascending order, first match wins.
-// ---------------------------------------------------------------------------------------------
-__global__ void spr_extract_kernel(const double *__restrict__ ref7, int n_ref, const double *__restrict__ qry7,
-                                   int n_qry, double c, double s, double tx, double ty, double Tstar,
-                                   double Sstar, double thr_dim, int ignore_dim, int32_t *__restrict__ match_ref) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_qry) return;
-  const double *q = qry7 + 7 * (size_t)j;
-  const double label = q[0];
-  double rx, ry;
-  spr_rotate(c, s, q[1], q[2], &rx, &ry);
-  const double qd[3] = {q[4], q[5], q[6]};
-  int32_t found = -1;
-  for (int i = 0; i < n_ref; i++) {
-    const double *r = ref7 + 7 * (size_t)i;
-    if (r[0] != label) continue;                                         // PR.cpp:306
-    if (!spr_distance_match(rx, ry, tx, ty, r[1], r[2], Tstar)) continue;  // PR.cpp:332
-    if (!ignore_dim && !spr_dimension_match(r[4], r[5], r[6], qd, thr_dim, Sstar)) continue;  // PR.cpp:334-339
-    found = i;
-    break;                                                               // PR.cpp:353
-  }
-  match_ref[j] = found;
-}
-
-cudaError_t spr_launch_extract(const double *ref7, int n_ref, const double *qry7, int n_qry, double c,
-                               double s, double tx, double ty, double Tstar, double Sstar, double thr_dim,
-                               int ignore_dim, int32_t *match_ref, cudaStream_t st) {
-  if (n_qry <= 0) return cudaSuccess;
-  const int block = 128;
-  spr_extract_kernel<<<(n_qry + block - 1) / block, block, 0, st>>>(ref7, n_ref, qry7, n_qry, c, s, tx, ty, Tstar,
-                                                                    Sstar, thr_dim, ignore_dim, match_ref);
-  return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------
-// SlideGraph descriptor half: triangle descriptors + all-pairs matching
-// (semantic_clipper.cpp:49-118).  The reference recomputes both descriptors for each of the
-// T1 x T2 pairs; here they are built once per triangle, then every model triangle (one warp)
-// sweeps the data descriptors 32 at a time and compacts its matches with ballot + popc so the
-// output keeps the reference's order (model-major, data-minor).
-// ---------------------------------------------------------------------------------------------
-__global__ void spr_tri_desc_kernel(const double *__restrict__ tris6, int t, double *__restrict__ desc,
-                                    int32_t *__restrict__ perm) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= t) return;
-  double tri[6], d[3];
-  int32_t p[3];
-#pragma unroll
-  for (int k = 0; k < 6; k++) tri[k] = tris6[6 * (size_t)i + k];
-  spr_triangle_descriptor(tri, d, p);
-#pragma unroll
-  for (int k = 0; k < 3; k++) { desc[3 * (size_t)i + k] = d[k]; perm[3 * (size_t)i + k] = p[k]; }
-}
-
-template <bool FILL>
-__global__ void __launch_bounds__(256)
-spr_tri_match_kernel(const double *__restrict__ dm, int tm, const double *__restrict__ dd, int td, double thr,
-                     unsigned long long *__restrict__ counts, const unsigned long long *__restrict__ offsets,
-                     int32_t *__restrict__ model_idx, int32_t *__restrict__ data_idx, long long cap) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (int i = warp; i < tm; i += n_warps) {
-    const double m[3] = {dm[3 * (size_t)i], dm[3 * (size_t)i + 1], dm[3 * (size_t)i + 2]};
-    unsigned long long base = FILL ? offsets[i] : 0ull;
-    for (int j0 = 0; j0 < td; j0 += 32) {
-      const int j = j0 + lane;
-      bool hit = false;
-      if (j < td) {
-        const double d[3] = {dd[3 * (size_t)j], dd[3 * (size_t)j + 1], dd[3 * (size_t)j + 2]};
-        hit = spr_descriptor_match(m, d, thr);
-      }
-      const unsigned mask = __ballot_sync(SPR_FULL, hit);
-      if (FILL && hit) {
-        const unsigned long long pos = base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
-        if ((long long)pos < cap) { model_idx[pos] = i; data_idx[pos] = j; }
-      }
-      base += (unsigned long long)__popc(mask);
-    }
-    if (!FILL && lane == 0) counts[i] = base;
-  }
-}
-
-// exclusive prefix sum of n counters, one block (n <= a few 10^5 triangles)
-__global__ void spr_scan_kernel(const unsigned long long *__restrict__ counts, int n,
-                                unsigned long long *__restrict__ offsets, unsigned long long *__restrict__ total) {
-  __shared__ unsigned long long tile[1024];
-  __shared__ unsigned long long carry;
-  if (threadIdx.x == 0) carry = 0ull;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + threadIdx.x;
-    const unsigned long long v = i < n ? counts[i] : 0ull;
-    tile[threadIdx.x] = v;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-      const unsigned long long t = threadIdx.x >= d ? tile[threadIdx.x - d] : 0ull;
-      __syncthreads();
-      tile[threadIdx.x] += t;
-      __syncthreads();
-    }
-    if (i < n) offsets[i] = carry + tile[threadIdx.x] - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += tile[1023];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total = carry;
-}
-
-cudaError_t spr_launch_tri_desc(const double *tris6, int t, double *desc, int32_t *perm, cudaStream_t st) {
-  if (t <= 0) return cudaSuccess;
-  spr_tri_desc_kernel<<<(t + 255) / 256, 256, 0, st>>>(tris6, t, desc, perm);
-  return cudaGetLastError();
-}
-
-cudaError_t spr_launch_tri_match(const double *dm, int tm, const double *dd, int td, double thr,
-                                 unsigned long long *counts, unsigned long long *offsets, unsigned long long *total,
-                                 int32_t *model_idx, int32_t *data_idx, long long cap, bool fill, int sm_count,
-                                 cudaStream_t st) {
-  if (tm <= 0) return cudaSuccess;
-  const int want = (tm + 7) / 8, capg = sm_count * 8;
-  const int grid = want < capg ? want : capg;
-  if (!fill) {
-    spr_tri_match_kernel<false><<<grid, 256, 0, st>>>(dm, tm, dd, td, thr, counts, offsets, model_idx, data_idx, cap);
-    spr_scan_kernel<<<1, 1024, 0, st>>>(counts, tm, offsets, total);
-  } else {
-    spr_tri_match_kernel<true><<<grid, 256, 0, st>>>(dm, tm, dd, td, thr, counts, offsets, model_idx, data_idx, cap);
-  }
-  return cudaGetLastError();
-}

@@ -49,8 +49,10 @@ struct SprGrid {
 
 struct SprBox { int32_t x0, x1, y0, y1; };  // fixed-point, [x0, x1) x [y0, y1); empty if x0 >= x1
 
-// one candidate of a marked cell: everything the exact test needs, in one 48-byte record
-struct SprCand { double x, y, d1, d2, d3; uint32_t ref; uint32_t pad; };
+// one candidate of a marked cell: everything the exact test needs, in one 48-byte record.
+// cand[rank] is the first (lowest reference index) candidate of the cell of that rank; further
+// candidates of the same cell are chained through `next` (index into cand, 0 = end).
+struct SprCand { double x, y, d1, d2, d3; uint32_t ref; uint32_t next; };
 
 // Everything the scoring code reads.  Pointers are valid in the executing address space
 // (device pointers for the kernels; host pointers for the test-only emulation).
@@ -76,8 +78,7 @@ struct SprView {
   const SprBox   *labelbox;   // [n_labels] fixed-point bounds of the label's marked cells
   const uint32_t *bitmap;     // [n_labels][plane dir0 | plane dir1]
   const uint32_t *cellword;   // [n_labels][plane_words[0]][2] (bits, set bits before this word)
-  const uint32_t *cellinfo;   // [n_marked_cells][2] (start, count) into cand
-  const SprCand  *cand;       // candidates, reference index ascending inside a cell
+  const SprCand  *cand;       // [n_marked_cells + overflow] first candidate of each cell by rank, then chained extras
   SprGrid         grid;
   double          Tstar;      // sqrt(d2) < match_threshold_  <=>  d2 < Tstar   (PR.cpp:332-333)
   double          Sstar;      // (sum / 3) < thr_dim          <=>  sum < Sstar  (PR.cpp:329,338)

@@ -50,7 +50,7 @@ extern "C" int spr_emu_match_maps(const slide_pr_params *p, const double *ref7, 
   V.qrotq_xy = qxy_fx.data(); V.qrotq_yx = qyx_fx.data(); V.gbox = gbox.data(); V.qrot = qrot.data();
   V.qxy = Q.qxy.data(); V.qdims = Q.qdims.data(); V.label_gseg = Q.label_gseg.data(); V.qlabel = Q.qlabel.data();
   V.n_labels = (int)R.labels.size(); V.n_ref = n_ref; V.labelbox = R.labelbox.data();
-  V.bitmap = R.bitmap.data(); V.cellword = R.cellword.data(); V.cellinfo = R.cellinfo.data(); V.cand = R.cand.data();
+  V.bitmap = R.bitmap.data(); V.cellword = R.cellword.data(); V.cand = R.cand.data();
   V.grid = R.grid; V.Tstar = R.Tstar; V.Sstar = R.Sstar; V.thr_dim = p->match_threshold_dimension;
   V.ignore_dim = p->ignore_dimension;
   const SprGrid &G = V.grid;
