@@ -26,9 +26,31 @@
 
 #define SPR_BLOCK 256
 #define SPR_WARPS (SPR_BLOCK / 32)
-#define SPR_QCAP 512             // per-warp hit queue, records (2 words each)
-#define SPR_CNT_PITCH 33         // counters: cnt[lane * 33 + bit] -> conflict-free for bit runs of one lane
-#define SPR_WARP_SMEM (32 * SPR_CNT_PITCH + 2 * SPR_QCAP)  // words per warp
+#define SPR_QCAP 192             // per-warp hit queue, records (2 words each)
+// Per-hypothesis inlier counters, [32 lanes][32 bits] per warp.  Counts are bounded by the number
+// of query landmarks, so they are packed two per word (pitch 17 words per lane) unless the query
+// map has more than 65535 landmarks (pitch 33 words per lane).  Shared memory is kept small on
+// purpose: what the CTAs do not take stays L1 cache for the occupancy bitmaps.
+#define SPR_CNT_WORDS(CNT32) ((CNT32) ? 32 * 33 : 32 * 17)
+#define SPR_WARP_SMEM(CNT32) (SPR_CNT_WORDS(CNT32) + 2 * SPR_QCAP)  // words per warp
+
+template <bool CNT32> __device__ __forceinline__ void spr_cnt_zero(uint32_t *cnt, int lane) {
+  if (CNT32) {
+#pragma unroll
+    for (int b = 0; b < 32; b++) cnt[lane * 33 + b] = 0u;
+  } else {
+#pragma unroll
+    for (int w = 0; w < 16; w++) cnt[lane * 17 + w] = 0u;
+  }
+}
+template <bool CNT32> __device__ __forceinline__ void spr_cnt_inc(uint32_t *cnt, int owner, int b) {
+  if (CNT32) atomicAdd(&cnt[owner * 33 + b], 1u);
+  else atomicAdd(&cnt[owner * 17 + (b >> 1)], 1u << ((b & 1) << 4));
+}
+template <bool CNT32> __device__ __forceinline__ uint32_t spr_cnt_get(const uint32_t *cnt, int lane, int b) {
+  if (CNT32) return cnt[lane * 33 + b];
+  return (cnt[lane * 17 + (b >> 1)] >> ((b & 1) << 4)) & 0xffffu;
+}
 #define SPR_FULL 0xffffffffu
 
 // ---------------------------------------------------------------------------------------------
@@ -56,7 +78,7 @@ cudaError_t spr_launch_rotate(const SprView &V, int32_t *qrotq_xy, int32_t *qrot
 // lattice scoring
 // ---------------------------------------------------------------------------------------------
 struct WarpState {
-  uint32_t *cnt;    // [32 lanes][33] inlier counters of the warp's 1024 hypotheses
+  uint32_t *cnt;    // inlier counters of the warp's 1024 hypotheses (spr_cnt_*)
   uint2 *queue;     // [SPR_QCAP] pending filter hits: x = js << 10 | owner lane << 5 | bit, y = cell code
   int qcount;       // warp-uniform
 };
@@ -75,6 +97,7 @@ __device__ __forceinline__ bool spr_verify_owned(const SprView &V, int l, int a,
 
 // Verify up to 32 queued hits, one per lane.  Chunk parameters of the owning lane come through
 // shuffles; every lane executes the shuffles.
+template <bool CNT32>
 __device__ __forceinline__ void spr_drain32(const SprView &V, WarpState &ws, int l, int a, int lane, uint32_t dir,
                                             uint32_t along_off, double across, unsigned long long &n_inl) {
   const int n = ws.qcount < 32 ? ws.qcount : 32;
@@ -87,21 +110,21 @@ __device__ __forceinline__ void spr_drain32(const SprView &V, WarpState &ws, int
   const uint32_t o_off = __shfl_sync(SPR_FULL, along_off, owner);
   const double o_across = __shfl_sync(SPR_FULL, across, owner);
   if (active && spr_verify_owned(V, l, a, js, b, rec.y, o_dir, o_off, o_across)) {
-    atomicAdd(&ws.cnt[owner * SPR_CNT_PITCH + b], 1u);
+    spr_cnt_inc<CNT32>(ws.cnt, owner, b);
     n_inl++;
   }
   ws.qcount -= n;
   __syncwarp();
 }
 
-template <int VARIANT, bool WRITE_COUNTS, bool STATS>
+template <int VARIANT, bool WRITE_COUNTS, bool STATS, bool CNT32>
 __global__ void __launch_bounds__(SPR_BLOCK, 4)
 spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_local, const long long n_items) {
   extern __shared__ uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpState ws;
-  ws.cnt = smem + warp * SPR_WARP_SMEM;
-  ws.queue = reinterpret_cast<uint2 *>(ws.cnt + 32 * SPR_CNT_PITCH);  // 1056 words: 8-byte aligned
+  ws.cnt = smem + warp * SPR_WARP_SMEM(CNT32);
+  ws.queue = reinterpret_cast<uint2 *>(ws.cnt + SPR_CNT_WORDS(CNT32));  // even word offset: 8-byte aligned
   ws.qcount = 0;
   const SprGrid &G = V.grid;
   const int32_t F = G.F;
@@ -123,8 +146,7 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
       across = ch.across; along_off = ch.along_off; valid = ch.valid;
       ord_base = ch.ord_base; ord_stride = ch.ord_stride; dir = ch.dir;
     }
-#pragma unroll
-    for (int b = 0; b < 32; b++) ws.cnt[lane * SPR_CNT_PITCH + b] = 0u;
+    spr_cnt_zero<CNT32>(ws.cnt, lane);
     const int32_t aq0 = spr_fx(across, G.S);
     const int32_t bq0 = spr_fx(__ldg(V.lat + along_off), G.S);
     const int32_t aqb = spr_bias_across(aq0, F), bqb = spr_bias_along(bq0, F);
@@ -199,14 +221,14 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
                 h &= h - 1;
                 if (spr_verify_owned(V, l, a, js0 + u, b, spr_cell_code(G, dir, aqb + q.x, bqb + q.y, b), dir, along_off,
                                      across)) {
-                  atomicAdd(&ws.cnt[lane * SPR_CNT_PITCH + b], 1u);  // atomics: queued hits may target our counters
+                  spr_cnt_inc<CNT32>(ws.cnt, lane, b);  // atomic: queued hits may target our counters
                   n_inl++;
                 }
               }
             }
             continue;
           }
-          while (ws.qcount + total > SPR_QCAP) spr_drain32(V, ws, l, a, lane, dir, along_off, across, n_inl);
+          while (ws.qcount + total > SPR_QCAP) spr_drain32<CNT32>(V, ws, l, a, lane, dir, along_off, across, n_inl);
           int pos = ws.qcount + incl - n;
 #pragma unroll
           for (int u = 0; u < SPR_QGROUP; u++) {
@@ -226,10 +248,10 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
           }
           ws.qcount += total;
           __syncwarp();
-          while (ws.qcount >= 32) spr_drain32(V, ws, l, a, lane, dir, along_off, across, n_inl);
+          while (ws.qcount >= 32) spr_drain32<CNT32>(V, ws, l, a, lane, dir, along_off, across, n_inl);
         }
         // the queue only ever holds hits of the current label
-        while (ws.qcount > 0) spr_drain32(V, ws, l, a, lane, dir, along_off, across, n_inl);
+        while (ws.qcount > 0) spr_drain32<CNT32>(V, ws, l, a, lane, dir, along_off, across, n_inl);
       }
       __syncwarp();
       // each lane scans the 32 hypotheses of its chunk
@@ -237,7 +259,7 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
       while (v) {
         const int b = __ffs(v) - 1;
         v &= v - 1;
-        const uint32_t c = ws.cnt[lane * SPR_CNT_PITCH + b];
+        const uint32_t c = spr_cnt_get<CNT32>(ws.cnt, lane, b);
         const unsigned long long ord = (unsigned long long)ord_base + (unsigned long long)b * ord_stride;
         const unsigned long long key = spr_make_key(c, ord * (unsigned long long)V.n_yaw + (unsigned long long)a);
         best = key > best ? key : best;
@@ -269,16 +291,17 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
   }
 }
 
-template <int VARIANT>
+template <int VARIANT, bool CNT32>
 static cudaError_t launch_variant(const SprView &V, const SprLaunch &K, int n_wg_local, long long n_items,
-                                  int grid, size_t smem, cudaStream_t st) {
+                                  int grid, cudaStream_t st) {
   const bool wc = K.counts_out != nullptr, stt = K.stats != nullptr;
-#define SPR_GO(WC, ST)                                                                                     \
-  do {                                                                                                     \
-    cudaError_t e = cudaFuncSetAttribute(spr_score_lattice_kernel<VARIANT, WC, ST>,                        \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-    if (e != cudaSuccess) return e;                                                                        \
-    spr_score_lattice_kernel<VARIANT, WC, ST><<<grid, SPR_BLOCK, smem, st>>>(V, K, n_wg_local, n_items);    \
+  const size_t smem = (size_t)SPR_WARPS * SPR_WARP_SMEM(CNT32) * sizeof(uint32_t);
+#define SPR_GO(WC, ST)                                                                                            \
+  do {                                                                                                            \
+    cudaError_t e = cudaFuncSetAttribute(spr_score_lattice_kernel<VARIANT, WC, ST, CNT32>,                        \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+    if (e != cudaSuccess) return e;                                                                               \
+    spr_score_lattice_kernel<VARIANT, WC, ST, CNT32><<<grid, SPR_BLOCK, smem, st>>>(V, K, n_wg_local, n_items);    \
   } while (0)
   if (wc && stt) SPR_GO(true, true);
   else if (wc) SPR_GO(true, false);
@@ -301,15 +324,18 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int v
   K2.shard_index = si;
   K2.shard_count = sc;
   const long long n_items = (long long)n_wg_local * V.n_yaw;
-  const size_t smem = (size_t)SPR_WARPS * SPR_WARP_SMEM * sizeof(uint32_t);
   const long long max_grid = (long long)sm_count * 4;
   const long long want = (n_items + SPR_WARPS - 1) / SPR_WARPS;
   const int grid = (int)(want < max_grid ? want : max_grid);
   cudaError_t e = cudaMemsetAsync(K.work_counter, 0, sizeof(unsigned long long), st);
   if (e != cudaSuccess) return e;
   if (n_launches) (*n_launches)++;
-  if (variant == SPR_VARIANT_DIRECT) return launch_variant<SPR_VARIANT_DIRECT>(V, K2, n_wg_local, n_items, grid, smem, st);
-  return launch_variant<SPR_VARIANT_QUEUED>(V, K2, n_wg_local, n_items, grid, smem, st);
+  const bool cnt32 = V.nqp > 65535;  // a count can reach the number of query landmarks
+  if (variant == SPR_VARIANT_DIRECT)
+    return cnt32 ? launch_variant<SPR_VARIANT_DIRECT, true>(V, K2, n_wg_local, n_items, grid, st)
+                 : launch_variant<SPR_VARIANT_DIRECT, false>(V, K2, n_wg_local, n_items, grid, st);
+  return cnt32 ? launch_variant<SPR_VARIANT_QUEUED, true>(V, K2, n_wg_local, n_items, grid, st)
+               : launch_variant<SPR_VARIANT_QUEUED, false>(V, K2, n_wg_local, n_items, grid, st);
 }
 
 // ---------------------------------------------------------------------------------------------
