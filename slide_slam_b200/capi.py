@@ -13,7 +13,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libslide_pr.so")
+# SLIDE_PR_LIB: developer override used to A/B-test kernel build variants (tools/build_variants.sh)
+LIB_PATH = os.environ.get("SLIDE_PR_LIB") or os.path.join(_HERE, "libslide_pr.so")
 
 OK, NOT_FOUND, SANITY_RETURN = 0, 1, 2
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NONFINITE, ERR_INTERNAL = -1, -2, -3, -4, -5

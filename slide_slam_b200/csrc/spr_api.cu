@@ -63,8 +63,8 @@ struct slide_pr_handle {
   spr::RefIndex R;
   spr::QuerySet Q;
   // device side
-  DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_cellword,
-      d_cand, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
+  DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_cellword, d_cellword1,
+      d_cand, d_cand1, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
   SprView V{};
   std::vector<int32_t> h_match;
 };
@@ -155,7 +155,7 @@ void slide_pr_destroy(slide_pr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (DevBuf *b : {&h->d_lat, &h->d_chunks, &h->d_cs, &h->d_qxy, &h->d_qdims, &h->d_labelseg, &h->d_qlabel,
-                    &h->d_labelbox, &h->d_gbox, &h->d_bitmap, &h->d_cellword, &h->d_cand, &h->d_qrot,
+                    &h->d_labelbox, &h->d_gbox, &h->d_bitmap, &h->d_cellword, &h->d_cellword1, &h->d_cand, &h->d_cand1, &h->d_qrot,
                     &h->d_qrotq, &h->d_qrotq_yx, &h->d_work, &h->d_ref7, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps, &h->d_tri, &h->d_tri_out})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -219,8 +219,10 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   if ((rc = upload(h, h->d_qlabel, h->Q.qlabel, st))) return rc;
   if ((rc = upload(h, h->d_labelbox, h->R.labelbox, st))) return rc;
   if ((rc = upload(h, h->d_bitmap, h->R.bitmap, st))) return rc;
-  if ((rc = upload(h, h->d_cellword, h->R.cellword, st))) return rc;
-  if ((rc = upload(h, h->d_cand, h->R.cand, st))) return rc;
+  if ((rc = upload(h, h->d_cellword, h->R.cellword[0], st))) return rc;
+  if ((rc = upload(h, h->d_cellword1, h->R.cellword[1], st))) return rc;
+  if ((rc = upload(h, h->d_cand, h->R.cand[0], st))) return rc;
+  if ((rc = upload(h, h->d_cand1, h->R.cand[1], st))) return rc;
   if ((rc = upload_raw(h, h->d_ref7, ref7, (size_t)n_ref * 7 * sizeof(double), st))) return rc;
   if ((rc = upload_raw(h, h->d_qry7, qry7, (size_t)n_qry * 7 * sizeof(double), st))) return rc;
   const size_t nrot = (size_t)std::max<size_t>((size_t)h->L.yaw.size() * (size_t)h->Q.nqp, 1);
@@ -249,8 +251,10 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   V.n_ref = n_ref;
   V.labelbox = h->d_labelbox.as<SprBox>();
   V.bitmap = h->d_bitmap.as<uint32_t>();
-  V.cellword = h->d_cellword.as<uint32_t>();
-  V.cand = h->d_cand.as<SprCand>();
+  V.cellword[0] = h->d_cellword.as<uint32_t>();
+  V.cellword[1] = h->d_cellword1.as<uint32_t>();
+  V.cand[0] = h->d_cand.as<SprCand>();
+  V.cand[1] = h->d_cand1.as<SprCand>();
   V.grid = h->R.grid;
   V.Tstar = h->R.Tstar;
   V.Sstar = h->R.Sstar;

@@ -115,14 +115,10 @@ SPR_HD uint32_t spr_probe(const uint32_t *plane, uint32_t W, uint32_t Rm1, uint3
   return SPR_FUNNEL_R(p[0], p[1], bit) & valid;  // the funnel shift uses the low 5 bits of `bit`
 }
 
-// Address of a hit's cell in the dir-0 ("canonical") plane, packed as (word index << 5) | bit:
-// what the verification needs to rank the cell.  a / b are the biased sums of the probe, bitno
-// the hit's bit inside the chunk.
-SPR_HD uint32_t spr_cell_code(const SprGrid &G, uint32_t dir, int32_t a, int32_t b, int32_t bitno) {
-  const uint32_t row = (uint32_t)(a >> G.F), bit = (uint32_t)(b >> G.F) + (uint32_t)bitno;
-  // dir 0: x + 1 = row, y + 32 = bit.   dir 1: y + 32 = row + 31, x + 1 = bit - 31.
-  const uint32_t xrow = dir ? bit - 31u : row, ybit = dir ? row + 31u : bit;
-  return ((xrow * (uint32_t)G.W[0] + (ybit >> 5)) << 5) | (ybit & 31u);
+// Linear bit address, inside the chunk's own plane, of the cell under bit 0 of a probe that hit
+// (no clamping: a hit implies the sums are inside the grid).  Bit b of the chunk is cell code + b.
+SPR_HD uint32_t spr_cell_code(uint32_t W, int32_t F, int32_t a, int32_t b) {
+  return (((uint32_t)(a >> F) * W) << 5) + (uint32_t)(b >> F);
 }
 
 // May query group `g` (box of its fixed coords) land on label box `lb` for any translation of a
@@ -132,18 +128,13 @@ SPR_HD bool spr_group_visible(const SprBox &g, const SprBox &lb, int32_t X0, int
   return (g.x1 > lb.x0 - X1) && (g.x0 < lb.x1 - X0) && (g.y1 > lb.y0 - Y1) && (g.y0 < lb.y1 - Y0);
 }
 
-// Exact verification of one occupied cell (given by its spr_cell_code) of label l for a query
-// point whose rotated coordinates are (rx, ry), under translation (tx, ty).  Returns true iff
-// some reference landmark passes the reference's predicate (PR.cpp:299-355); *first_ref receives
-// the smallest such reference index (a cell's candidates are chained in ascending order).
-SPR_HD bool spr_verify_cell(const SprView &V, int32_t l, uint32_t code, double rx, double ry,
-                            double tx, double ty, const double *qd, int32_t *first_ref) {
-  // rank of the cell among the marked cells (dir-0 plane: rows = x, bits = y)
-  const size_t widx = (size_t)l * V.grid.plane_words[0] + (code >> 5);
-  const uint32_t word = V.cellword[2 * widx], before = V.cellword[2 * widx + 1];
-  uint32_t k = before + (uint32_t)SPR_POPC(word & ((1u << (code & 31u)) - 1u));
+// Exact test of one marked cell, given its rank in plane d: walks the cell's candidates in
+// ascending reference order with the reference's predicate (PR.cpp:299-355).
+SPR_HD bool spr_verify_rank(const SprView &V, uint32_t d, uint32_t rank, double rx, double ry, double tx,
+                            double ty, const double *qd, int32_t *first_ref) {
+  uint32_t k = rank;
   for (;;) {
-    const SprCand &c = V.cand[k];
+    const SprCand &c = V.cand[d][k];
     if (spr_distance_match(rx, ry, tx, ty, c.x, c.y, V.Tstar) &&
         (V.ignore_dim || spr_dimension_match(c.d1, c.d2, c.d3, qd, V.thr_dim, V.Sstar))) {
       *first_ref = (int32_t)c.ref;
@@ -154,17 +145,36 @@ SPR_HD bool spr_verify_cell(const SprView &V, int32_t l, uint32_t code, double r
   }
 }
 
-// Verification of one filter hit of the lattice kernel: query js (sorted order) under yaw a and
-// the translation of bit b of `ch`.  a_sum / b_sum are the biased sums that produced the hit.
-SPR_HD bool spr_verify_hit(const SprView &V, const SprChunk &ch, int32_t a, int32_t js, int32_t a_sum,
-                           int32_t b_sum, int32_t b, int32_t *first_ref) {
-  // the hypothesis' translation, exactly as the reference's accumulated lattice value
-  const double along = V.lat[ch.along_off + (uint32_t)b];
-  const double tx = ch.dir ? along : ch.across;
-  const double ty = ch.dir ? ch.across : along;
-  const size_t qi = (size_t)a * (size_t)V.nqp + (size_t)js;
-  return spr_verify_cell(V, V.qlabel[js], spr_cell_code(V.grid, ch.dir, a_sum, b_sum, b), V.qrot[2 * qi],
-                         V.qrot[2 * qi + 1], tx, ty, V.qdims + 3 * (size_t)js, first_ref);
+// Exact verification of one occupied cell (linear bit address `code` in plane d) of label l for a
+// query point with rotated coordinates (rx, ry), under translation (tx, ty).
+SPR_HD bool spr_verify_cell(const SprView &V, uint32_t d, int32_t l, uint32_t code, double rx, double ry,
+                            double tx, double ty, const double *qd, int32_t *first_ref) {
+  const uint32_t *cw = V.cellword[d] + 2 * ((size_t)l * V.grid.plane_words[d] + (code >> 5));
+  const uint32_t rank = cw[1] + (uint32_t)SPR_POPC(cw[0] & ((1u << (code & 31u)) - 1u));
+  return spr_verify_rank(V, d, rank, rx, ry, tx, ty, qd, first_ref);
+}
+
+// Exact verification of all filter hits H of ONE query landmark against the 32 consecutive cells
+// starting at bit address code0 of plane d (= the 32 translations of a chunk).  The translation of
+// bit b is (across, along[b]) (dir 0) or (along[b], across) (dir 1), exactly the reference's
+// accumulated lattice values.  Returns the mask of hypotheses for which the landmark is an inlier.
+SPR_HD uint32_t spr_verify_mask(const SprView &V, uint32_t d, int32_t l, uint32_t code0, uint32_t H, double rx,
+                                double ry, double across, const double *along, const double *qd) {
+  const uint32_t *cw = V.cellword[d] + 2 * ((size_t)l * V.grid.plane_words[d] + (code0 >> 5));
+  const uint32_t w0 = cw[0], before0 = cw[1], w1 = cw[2], before1 = cw[3];
+  const uint32_t off = code0 & 31u;
+  uint32_t P = 0u;
+  while (H) {
+    const int b = SPR_FFS(H) - 1;
+    H &= H - 1;
+    const uint32_t pos = off + (uint32_t)b;  // 0..62: the 32 cells span at most two words
+    const uint32_t rank = pos < 32u ? before0 + (uint32_t)SPR_POPC(w0 & ((1u << pos) - 1u))
+                                    : before1 + (uint32_t)SPR_POPC(w1 & ((1u << (pos - 32u)) - 1u));
+    const double t = along[b];
+    int32_t first;
+    if (spr_verify_rank(V, d, rank, rx, ry, d ? t : across, d ? across : t, qd, &first)) P |= 1u << b;
+  }
+  return P;
 }
 
 // Occupancy test of a single point (general hypothesis lists): fixed-point cell of
@@ -178,7 +188,7 @@ SPR_HD bool spr_point_cell(const SprView &V, int32_t l, double xt, double yt, ui
   const uint32_t bit = (uint32_t)(cy + 32);
   const uint32_t wloc = (uint32_t)(cx + 1) * (uint32_t)G.W[0] + (bit >> 5);
   const uint32_t word = V.bitmap[(size_t)l * G.label_stride + wloc];
-  *code = (wloc << 5) | (bit & 31u);
+  *code = (wloc << 5) | (bit & 31u);  // linear bit address in plane 0
   return (word >> (bit & 31u)) & 1u;
 }
 

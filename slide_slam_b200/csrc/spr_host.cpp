@@ -276,13 +276,12 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
   const uint64_t total_words = (uint64_t)G.label_stride * (uint64_t)std::max(n_labels, 1);
   if (total_words >= (1ull << 28)) { err = "occupancy bitmaps exceed 1 GiB (step too fine for this map extent)"; return SLIDE_PR_ERR_UNSUPPORTED; }
   R.bitmap.assign((size_t)total_words, 0u);
-  R.cellword.assign(2 * (size_t)G.plane_words[0] * (size_t)std::max(n_labels, 1), 0u);
   // per-label bounds of the marked cells (empty until a cell is marked)
   struct CellBounds { int x0, x1, y0, y1; };
   std::vector<CellBounds> cb((size_t)std::max(n_labels, 1), CellBounds{INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN});
 
   // mark every cell whose (slightly dilated) box a landmark's match disc touches
-  struct Entry { uint64_t key; uint32_t ref; };
+  struct Entry { uint64_t key[2]; uint32_t ref; };  // key[d]: rank order of plane d = (label, across, along)
   std::vector<Entry> entries;
   if (matchable) {
     const double eps_cells = 3.0 / std::ldexp(1.0, F) + 1e-9 / c;  // fixed-point truncation + lattice drift
@@ -307,55 +306,57 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
           pl1[(size_t)(ny + 1) * G.W[1] + ((uint32_t)(nx + 32) >> 5)] |= 1u << ((nx + 32) & 31);
           cb[l].x0 = std::min(cb[l].x0, nx); cb[l].x1 = std::max(cb[l].x1, nx);
           cb[l].y0 = std::min(cb[l].y0, ny); cb[l].y1 = std::max(cb[l].y1, ny);
-          // rank order == (label, x, y)
-          const uint64_t key = ((uint64_t)l << 44) | ((uint64_t)nx << 22) | (uint64_t)ny;
-          entries.push_back({key, (uint32_t)i});
+          entries.push_back({{((uint64_t)l << 44) | ((uint64_t)nx << 22) | (uint64_t)ny,
+                              ((uint64_t)l << 44) | ((uint64_t)ny << 22) | (uint64_t)nx}, (uint32_t)i});
         }
       }
     }
   }
-  std::sort(entries.begin(), entries.end(), [](const Entry &a, const Entry &b) {
-    return a.key != b.key ? a.key < b.key : a.ref < b.ref;
-  });
   if (entries.size() >= (1ull << 32)) { err = "candidate lists exceed 2^32 entries"; return SLIDE_PR_ERR_UNSUPPORTED; }
-  // cand[rank] = first candidate of the cell of that rank; extra candidates of a cell are
-  // appended behind the n_cells first ones and chained in ascending reference order
-  size_t n_cells = 0;
-  for (size_t e = 0; e < entries.size(); e++)
-    if (e == 0 || entries[e].key != entries[e - 1].key) n_cells++;
-  R.cand.resize(entries.size());
-  {
+  for (int d = 0; d < 2; d++) {
+    std::sort(entries.begin(), entries.end(), [d](const Entry &a, const Entry &b) {
+      return a.key[d] != b.key[d] ? a.key[d] < b.key[d] : a.ref < b.ref;
+    });
+    // cand[d][rank] = first candidate of the cell of that rank in plane d; extra candidates of a
+    // cell are appended behind the n_cells first ones and chained in ascending reference order
+    size_t n_cells = 0;
+    for (size_t e = 0; e < entries.size(); e++)
+      if (e == 0 || entries[e].key[d] != entries[e - 1].key[d]) n_cells++;
+    std::vector<SprCand> &cand = R.cand[d];
+    cand.resize(entries.size());
     size_t rank = 0, extra = n_cells, prev = 0;
     for (size_t e = 0; e < entries.size(); e++) {
       const double *r = ref7 + 7 * (size_t)entries[e].ref;
       const SprCand c{r[1], r[2], r[4], r[5], r[6], entries[e].ref, 0u};
-      if (e == 0 || entries[e].key != entries[e - 1].key) {
+      if (e == 0 || entries[e].key[d] != entries[e - 1].key[d]) {
         prev = rank++;
       } else {
-        R.cand[prev].next = (uint32_t)extra;
+        cand[prev].next = (uint32_t)extra;
         prev = extra++;
       }
-      R.cand[prev] = c;
+      cand[prev] = c;
     }
-  }
-  // (word, set bits before it) over the dir-0 planes, label-major == rank order of the marked cells
-  uint32_t running = 0;
-  for (int l = 0; l < n_labels; l++) {
-    const uint32_t *pl0 = R.bitmap.data() + (size_t)l * G.label_stride;
-    uint32_t *cw = R.cellword.data() + 2 * (size_t)l * G.plane_words[0];
-    for (uint32_t w = 0; w < G.plane_words[0]; w++) {
-      cw[2 * (size_t)w] = pl0[w];
-      cw[2 * (size_t)w + 1] = running;
-      running += (uint32_t)__builtin_popcount(pl0[w]);
+    if (cand.empty()) cand.assign(1, SprCand{0, 0, 0, 0, 0, 0u, 0u});
+    // (word, set bits before it) over the planes of direction d, label-major == rank order
+    std::vector<uint32_t> &cellword = R.cellword[d];
+    cellword.assign(2 * (size_t)G.plane_words[d] * (size_t)std::max(n_labels, 1) + 4, 0u);
+    uint32_t running = 0;
+    for (int l = 0; l < n_labels; l++) {
+      const uint32_t *pl = R.bitmap.data() + (size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u);
+      uint32_t *cw = cellword.data() + 2 * (size_t)l * G.plane_words[d];
+      for (uint32_t w = 0; w < G.plane_words[d]; w++) {
+        cw[2 * (size_t)w] = pl[w];
+        cw[2 * (size_t)w + 1] = running;
+        running += (uint32_t)__builtin_popcount(pl[w]);
+      }
     }
+    if ((size_t)running != n_cells) { err = "internal: rank / cell list mismatch"; return SLIDE_PR_ERR_INTERNAL; }
   }
-  if ((size_t)running != n_cells) { err = "internal: rank / cell list mismatch"; return SLIDE_PR_ERR_INTERNAL; }
   R.labelbox.resize((size_t)std::max(n_labels, 1));
   for (int l = 0; l < std::max(n_labels, 1); l++) {
     if (cb[l].x0 > cb[l].x1) { R.labelbox[l] = SprBox{0, -(1 << 30), 0, -(1 << 30)}; continue; }  // empty: never visible
     R.labelbox[l] = SprBox{cb[l].x0 << F, (cb[l].x1 + 1) << F, cb[l].y0 << F, (cb[l].y1 + 1) << F};
   }
-  if (R.cand.empty()) R.cand.assign(1, SprCand{0, 0, 0, 0, 0, 0u, 0u});
   return SLIDE_PR_OK;
 }
 

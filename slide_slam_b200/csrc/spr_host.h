@@ -42,8 +42,8 @@ struct RefIndex {
   std::vector<double> labels;       // distinct finite reference labels, ascending
   SprGrid grid{};
   std::vector<uint32_t> bitmap;     // [n_labels][plane0 | plane1]
-  std::vector<uint32_t> cellword;   // [n_labels][plane_words[0]][2] (bits, set bits before)
-  std::vector<SprCand> cand;        // [n_cells] first candidate per cell rank, then chained extras
+  std::vector<uint32_t> cellword[2]; // per plane direction d: [n_labels][plane_words[d]][2] (bits, set bits before)
+  std::vector<SprCand> cand[2];      // per plane direction d: [n_cells] first candidate per cell rank, then chained extras
   std::vector<SprBox> labelbox;     // [n_labels] fixed-point bounds of the label's marked cells
   double Tstar = 0, Sstar = 0;
   int n_ref = 0;

@@ -24,15 +24,21 @@
 #include "spr_core.h"
 #include "spr_kernels.h"
 
-#define SPR_BLOCK 256
+#ifndef SPR_BLOCK
+#define SPR_BLOCK 256   // threads per CTA (8 independent warps)
+#endif
+#ifndef SPR_MINB
+#define SPR_MINB 4      // CTAs per SM the register allocation is tuned for
+#endif
 #define SPR_WARPS (SPR_BLOCK / 32)
-#define SPR_QCAP 192             // per-warp hit queue, records (2 words each)
+#define SPR_QHALF 4              // queries probed per push
+#define SPR_QCAP (32 * SPR_QHALF + 32)  // per-warp hit queue, records (3 words each): residual < 32 + one push
 // Per-hypothesis inlier counters, [32 lanes][32 bits] per warp.  Counts are bounded by the number
 // of query landmarks, so they are packed two per word (pitch 17 words per lane) unless the query
 // map has more than 65535 landmarks (pitch 33 words per lane).  Shared memory is kept small on
 // purpose: what the CTAs do not take stays L1 cache for the occupancy bitmaps.
 #define SPR_CNT_WORDS(CNT32) ((CNT32) ? 32 * 33 : 32 * 17)
-#define SPR_WARP_SMEM(CNT32) (SPR_CNT_WORDS(CNT32) + 2 * SPR_QCAP)  // words per warp
+#define SPR_WARP_SMEM(CNT32) (SPR_CNT_WORDS(CNT32) + 3 * SPR_QCAP)  // words per warp
 
 template <bool CNT32> __device__ __forceinline__ void spr_cnt_zero(uint32_t *cnt, int lane) {
   if (CNT32) {
@@ -79,52 +85,59 @@ cudaError_t spr_launch_rotate(const SprView &V, int32_t *qrotq_xy, int32_t *qrot
 // ---------------------------------------------------------------------------------------------
 struct WarpState {
   uint32_t *cnt;    // inlier counters of the warp's 1024 hypotheses (spr_cnt_*)
-  uint2 *queue;     // [SPR_QCAP] pending filter hits: x = js << 10 | owner lane << 5 | bit, y = cell code
+  uint32_t *q_meta; // [SPR_QCAP] pending records: query index js << 5 | owner lane
+  uint32_t *q_code; // [SPR_QCAP] bit address (own plane) of the cell under bit 0 of the probe
+  uint32_t *q_mask; // [SPR_QCAP] the probe's hit bits
   int qcount;       // warp-uniform
 };
 
-// exact verification of one hit: query js (label l) under yaw a against the cell `code`, for the
-// translation (bit b) of the chunk described by (dir, along_off, across)
-__device__ __forceinline__ bool spr_verify_owned(const SprView &V, int l, int a, int js, int b, uint32_t code,
-                                                 uint32_t o_dir, uint32_t o_off, double o_across) {
+// One queued record = all filter hits of ONE query landmark on ONE chunk (lane): verify its bits
+// in exact fp64 and add the survivors to the owner's counters.
+template <bool CNT32>
+__device__ __forceinline__ void spr_verify_record(const SprView &V, uint32_t *cnt, int l, int a, int js, int owner,
+                                                  uint32_t code0, uint32_t H, uint32_t o_dir, uint32_t o_off,
+                                                  double o_across, unsigned long long &n_inl) {
   const size_t qi = (size_t)a * (size_t)V.nqp + (size_t)js;
   const double2 r = __ldg(reinterpret_cast<const double2 *>(V.qrot) + qi);
-  const double along = __ldg(V.lat + o_off + b);
-  const double tx = o_dir ? along : o_across, ty = o_dir ? o_across : along;
-  int32_t first;
-  return spr_verify_cell(V, l, code, r.x, r.y, tx, ty, V.qdims + 3 * (size_t)js, &first);
+  uint32_t P = spr_verify_mask(V, o_dir, l, code0, H, r.x, r.y, o_across, V.lat + o_off, V.qdims + 3 * (size_t)js);
+  n_inl += (unsigned long long)__popc(P);
+  while (P) {
+    const int b = __ffs(P) - 1;
+    P &= P - 1;
+    spr_cnt_inc<CNT32>(cnt, owner, b);
+  }
 }
 
-// Verify up to 32 queued hits, one per lane.  Chunk parameters of the owning lane come through
-// shuffles; every lane executes the shuffles.
+// Verify up to 32 queued records, one per lane.  Chunk parameters of the owning lane come
+// through shuffles; every lane executes the shuffles.
 template <bool CNT32>
 __device__ __forceinline__ void spr_drain32(const SprView &V, WarpState &ws, int l, int a, int lane, uint32_t dir,
                                             uint32_t along_off, double across, unsigned long long &n_inl) {
   const int n = ws.qcount < 32 ? ws.qcount : 32;
   const bool active = lane < n;
-  uint2 rec = make_uint2(0u, 0u);
-  if (active) rec = ws.queue[ws.qcount - n + lane];
-  const int owner = (rec.x >> 5) & 31, b = rec.x & 31;
-  const int js = (int)(rec.x >> 10);
+  const int slot = ws.qcount - n + lane;
+  const uint32_t meta = active ? ws.q_meta[slot] : 0u;
+  const uint32_t code0 = active ? ws.q_code[slot] : 0u;
+  const uint32_t H = active ? ws.q_mask[slot] : 0u;
+  const int owner = meta & 31;
   const uint32_t o_dir = __shfl_sync(SPR_FULL, dir, owner);
   const uint32_t o_off = __shfl_sync(SPR_FULL, along_off, owner);
   const double o_across = __shfl_sync(SPR_FULL, across, owner);
-  if (active && spr_verify_owned(V, l, a, js, b, rec.y, o_dir, o_off, o_across)) {
-    spr_cnt_inc<CNT32>(ws.cnt, owner, b);
-    n_inl++;
-  }
+  if (active) spr_verify_record<CNT32>(V, ws.cnt, l, a, (int)(meta >> 5), owner, code0, H, o_dir, o_off, o_across, n_inl);
   ws.qcount -= n;
   __syncwarp();
 }
 
 template <int VARIANT, bool WRITE_COUNTS, bool STATS, bool CNT32>
-__global__ void __launch_bounds__(SPR_BLOCK, 4)
+__global__ void __launch_bounds__(SPR_BLOCK, SPR_MINB)
 spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_local, const long long n_items) {
   extern __shared__ uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpState ws;
   ws.cnt = smem + warp * SPR_WARP_SMEM(CNT32);
-  ws.queue = reinterpret_cast<uint2 *>(ws.cnt + SPR_CNT_WORDS(CNT32));  // even word offset: 8-byte aligned
+  ws.q_meta = ws.cnt + SPR_CNT_WORDS(CNT32);
+  ws.q_code = ws.q_meta + SPR_QCAP;
+  ws.q_mask = ws.q_code + SPR_QCAP;
   ws.qcount = 0;
   const SprGrid &G = V.grid;
   const int32_t F = G.F;
@@ -181,74 +194,63 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
             continue;
           }
           if (STATS) n_probed++;
-          uint32_t H[SPR_QGROUP];
+          // the group is probed in two halves of SPR_QHALF queries: at most 32 * SPR_QHALF new
+          // records per push, so the queue (drained below 32 after every push) cannot overflow
+#pragma unroll 1
+          for (int hq = 0; hq < SPR_QGROUP / SPR_QHALF; hq++) {
+            uint32_t H[SPR_QHALF];
 #pragma unroll
-          for (int u = 0; u < SPR_QGROUP / 2; u++) {
-            const int4 v = __ldg(qgp + u);  // two queries: (across, along) x 2
-            H[2 * u] = spr_probe(plane, W, Rm1, maxbit, F, aqb + v.x, bqb + v.y, SPR_FULL);
-            H[2 * u + 1] = spr_probe(plane, W, Rm1, maxbit, F, aqb + v.z, bqb + v.w, SPR_FULL);
-          }
-          uint32_t any = 0u;
+            for (int u = 0; u < SPR_QHALF / 2; u++) {
+              const int4 v = __ldg(qgp + hq * (SPR_QHALF / 2) + u);  // two queries: (across, along) x 2
+              H[2 * u] = spr_probe(plane, W, Rm1, maxbit, F, aqb + v.x, bqb + v.y, SPR_FULL);
+              H[2 * u + 1] = spr_probe(plane, W, Rm1, maxbit, F, aqb + v.z, bqb + v.w, SPR_FULL);
+            }
+            uint32_t any = 0u;
 #pragma unroll
-          for (int u = 0; u < SPR_QGROUP; u++) any |= H[u];
-          any &= valid;
-          if (__ballot_sync(SPR_FULL, any != 0u) == 0u) continue;
-          int n = 0;
+            for (int u = 0; u < SPR_QHALF; u++) any |= H[u];
+            any &= valid;
+            if (__ballot_sync(SPR_FULL, any != 0u) == 0u) continue;
+            // one record per (lane, query) with hits
+            int n = 0;
 #pragma unroll
-          for (int u = 0; u < SPR_QGROUP; u++) { H[u] &= valid; n += __popc(H[u]); }
-          if (STATS) n_hits += (unsigned long long)n;
-          const int js0 = g * SPR_QGROUP;
-          bool in_place = VARIANT == SPR_VARIANT_DIRECT;
-          int incl = n, total = 0;
-          if (!in_place) {
-            // warp inclusive prefix sum of the per-lane hit counts
+            for (int u = 0; u < SPR_QHALF; u++) { H[u] &= valid; n += H[u] != 0u; }
+            if (STATS) {
+#pragma unroll
+              for (int u = 0; u < SPR_QHALF; u++) n_hits += (unsigned long long)__popc(H[u]);
+            }
+            const int js0 = g * SPR_QGROUP + hq * SPR_QHALF;
+            if (VARIANT == SPR_VARIANT_DIRECT) {  // test variant: every lane verifies its own hits
+#pragma unroll
+              for (int u = 0; u < SPR_QHALF; u++) {
+                if (H[u] == 0u) continue;
+                const int2 q = __ldg(qa2 + js0 + u);
+                spr_verify_record<CNT32>(V, ws.cnt, l, a, js0 + u, lane, spr_cell_code(W, F, aqb + q.x, bqb + q.y), H[u], dir,
+                                         along_off, across, n_inl);
+              }
+              continue;
+            }
+            // warp inclusive prefix sum of the per-lane record counts
+            int incl = n;
 #pragma unroll
             for (int dlt = 1; dlt < 32; dlt <<= 1) {
               const int t = __shfl_up_sync(SPR_FULL, incl, dlt);
               if (lane >= dlt) incl += t;
             }
-            total = __shfl_sync(SPR_FULL, incl, 31);
-            in_place = total > SPR_QCAP;  // pathological density: verify in place
-          }
-          if (in_place) {
+            const int total = __shfl_sync(SPR_FULL, incl, 31);
+            int pos = ws.qcount + incl - n;
 #pragma unroll
-            for (int u = 0; u < SPR_QGROUP; u++) {
-              uint32_t h = H[u];
-              if (h == 0u) continue;
-              const int2 q = __ldg(qa2 + js0 + u);
-              while (h) {
-                const int b = __ffs(h) - 1;
-                h &= h - 1;
-                if (spr_verify_owned(V, l, a, js0 + u, b, spr_cell_code(G, dir, aqb + q.x, bqb + q.y, b), dir, along_off,
-                                     across)) {
-                  spr_cnt_inc<CNT32>(ws.cnt, lane, b);  // atomic: queued hits may target our counters
-                  n_inl++;
-                }
-              }
+            for (int u = 0; u < SPR_QHALF; u++) {
+              if (H[u] == 0u) continue;
+              const int2 q = __ldg(qa2 + js0 + u);  // L1 hit: loaded a moment ago by the probe
+              ws.q_meta[pos] = ((uint32_t)(js0 + u) << 5) | (uint32_t)lane;
+              ws.q_code[pos] = spr_cell_code(W, F, aqb + q.x, bqb + q.y);
+              ws.q_mask[pos] = H[u];
+              pos++;
             }
-            continue;
+            ws.qcount += total;
+            __syncwarp();
+            while (ws.qcount >= 32) spr_drain32<CNT32>(V, ws, l, a, lane, dir, along_off, across, n_inl);
           }
-          while (ws.qcount + total > SPR_QCAP) spr_drain32<CNT32>(V, ws, l, a, lane, dir, along_off, across, n_inl);
-          int pos = ws.qcount + incl - n;
-#pragma unroll
-          for (int u = 0; u < SPR_QGROUP; u++) {
-            uint32_t h = H[u];
-            if (h == 0u) continue;
-            const int2 q = __ldg(qa2 + js0 + u);  // L1 hit: loaded a moment ago by the probe
-            // a cell code is the cell's linear bit address in the dir-0 plane: bit b of the chunk
-            // is b bits further along the same row (dir 0) or b rows further (dir 1)
-            const uint32_t code0 = spr_cell_code(G, dir, aqb + q.x, bqb + q.y, 0);
-            const uint32_t code_step = dir ? ((uint32_t)G.W[0] << 5) : 1u;
-            const uint32_t rec0 = ((uint32_t)(js0 + u) << 10) | ((uint32_t)lane << 5);
-            while (h) {
-              const int b = __ffs(h) - 1;
-              h &= h - 1;
-              ws.queue[pos++] = make_uint2(rec0 | (uint32_t)b, code0 + (uint32_t)b * code_step);
-            }
-          }
-          ws.qcount += total;
-          __syncwarp();
-          while (ws.qcount >= 32) spr_drain32<CNT32>(V, ws, l, a, lane, dir, along_off, across, n_inl);
         }
         // the queue only ever holds hits of the current label
         while (ws.qcount > 0) spr_drain32<CNT32>(V, ws, l, a, lane, dir, along_off, across, n_inl);
@@ -324,7 +326,7 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int v
   K2.shard_index = si;
   K2.shard_count = sc;
   const long long n_items = (long long)n_wg_local * V.n_yaw;
-  const long long max_grid = (long long)sm_count * 4;
+  const long long max_grid = (long long)sm_count * SPR_MINB;
   const long long want = (n_items + SPR_WARPS - 1) / SPR_WARPS;
   const int grid = (int)(want < max_grid ? want : max_grid);
   cudaError_t e = cudaMemsetAsync(K.work_counter, 0, sizeof(unsigned long long), st);

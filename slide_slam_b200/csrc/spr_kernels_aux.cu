@@ -31,7 +31,7 @@ spr_score_list_kernel(SprView V, const double *__restrict__ hyps4, long long n, 
       uint32_t code;
       int32_t first;
       if (spr_point_cell(V, l, xt, yt, &code) &&
-          spr_verify_cell(V, l, code, rx, ry, tx, ty, V.qdims + 3 * (size_t)js, &first))
+          spr_verify_cell(V, 0u, l, code, rx, ry, tx, ty, V.qdims + 3 * (size_t)js, &first))
         cnt++;
     }
 #pragma unroll

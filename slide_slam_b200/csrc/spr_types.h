@@ -77,8 +77,8 @@ struct SprView {
   int32_t         n_ref;
   const SprBox   *labelbox;   // [n_labels] fixed-point bounds of the label's marked cells
   const uint32_t *bitmap;     // [n_labels][plane dir0 | plane dir1]
-  const uint32_t *cellword;   // [n_labels][plane_words[0]][2] (bits, set bits before this word)
-  const SprCand  *cand;       // [n_marked_cells + overflow] first candidate of each cell by rank, then chained extras
+  const uint32_t *cellword[2];// per plane direction d: [n_labels][plane_words[d]][2] (bits, set bits before this word)
+  const SprCand  *cand[2];    // per plane direction d: first candidate of each marked cell by rank, then chained extras
   SprGrid         grid;
   double          Tstar;      // sqrt(d2) < match_threshold_  <=>  d2 < Tstar   (PR.cpp:332-333)
   double          Sstar;      // (sum / 3) < thr_dim          <=>  sum < Sstar  (PR.cpp:329,338)

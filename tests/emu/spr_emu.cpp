@@ -50,7 +50,8 @@ extern "C" int spr_emu_match_maps(const slide_pr_params *p, const double *ref7, 
   V.qrotq_xy = qxy_fx.data(); V.qrotq_yx = qyx_fx.data(); V.gbox = gbox.data(); V.qrot = qrot.data();
   V.qxy = Q.qxy.data(); V.qdims = Q.qdims.data(); V.label_gseg = Q.label_gseg.data(); V.qlabel = Q.qlabel.data();
   V.n_labels = (int)R.labels.size(); V.n_ref = n_ref; V.labelbox = R.labelbox.data();
-  V.bitmap = R.bitmap.data(); V.cellword = R.cellword.data(); V.cand = R.cand.data();
+  V.bitmap = R.bitmap.data();
+  for (int d = 0; d < 2; d++) { V.cellword[d] = R.cellword[d].data(); V.cand[d] = R.cand[d].data(); }
   V.grid = R.grid; V.Tstar = R.Tstar; V.Sstar = R.Sstar; V.thr_dim = p->match_threshold_dimension;
   V.ignore_dim = p->ignore_dimension;
   const SprGrid &G = V.grid;
@@ -76,14 +77,12 @@ extern "C" int spr_emu_match_maps(const slide_pr_params *p, const double *ref7, 
             const int s = g * SPR_QGROUP + k;
             const size_t qi = (size_t)a * nqp + s;
             const int32_t asum = aqb + qfx[2 * qi], bsum = bqb + qfx[2 * qi + 1];
-            uint32_t H = spr_probe(plane, (uint32_t)G.W[d], (uint32_t)G.R[d] - 1u, (uint32_t)G.maxbit[d], G.F, asum, bsum, ch.valid);
-            while (H) {
-              const int b = SPR_FFS(H) - 1;
-              H &= H - 1;
-              hits++;
-              int32_t first;
-              if (spr_verify_hit(V, ch, a, s, asum, bsum, b, &first)) cnt[b]++;
-            }
+            const uint32_t H = spr_probe(plane, (uint32_t)G.W[d], (uint32_t)G.R[d] - 1u, (uint32_t)G.maxbit[d], G.F, asum, bsum, ch.valid);
+            if (!H) continue;
+            hits += __builtin_popcount(H);
+            uint32_t P = spr_verify_mask(V, (uint32_t)d, l, spr_cell_code((uint32_t)G.W[d], G.F, asum, bsum), H, qrot[2 * qi],
+                                         qrot[2 * qi + 1], ch.across, V.lat + ch.along_off, V.qdims + 3 * (size_t)s);
+            while (P) { cnt[SPR_FFS(P) - 1]++; P &= P - 1; }
           }
         }
       }
