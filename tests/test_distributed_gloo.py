@@ -1,0 +1,85 @@
+"""CPU suite: the multi-rank host logic (record all-gather + deterministic merge, pair dealing)
+over the gloo backend with world_size 2 and 3 -- the same code path bench.py runs over NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from slide_slam_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, cases, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        got = []
+        for per_rank in cases:
+            h, n = per_rank[rank]
+            w = parallel.allgather_winner(h, n)
+            got.append((w.inliers, w.hyp_index, w.rank))
+        # all-pairs gather: each rank fills only its own pairs
+        rows = torch.zeros((7, 2), dtype=torch.float64)
+        for p in parallel.pairs_of_rank(7, rank, world):
+            rows[p] = torch.tensor([float(p), float(rank)])
+        dist.all_reduce(rows)
+        out_q.put((rank, got, rows.numpy().tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_allgather_winner_is_deterministic_and_first_wins(world):
+    cases = [
+        [(50, 7), (20, 9), (10, 9)][:world],            # max inliers wins
+        [(50, 9), (20, 9), (10, 9)][:world],            # tie -> smallest canonical index (PR.cpp:361)
+        [(-1, -10000), (33, 0), (-1, -10000)][:world],  # empty shards never win, a 0-inlier hypothesis does
+        [(-1, -10000)] * world,                         # nothing scored anywhere
+    ]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cases, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = []
+    for per_rank in cases:
+        w = parallel.merge_records(per_rank)
+        expect.append((-10000, -1, -1) if w < 0 else (per_rank[w][1], per_rank[w][0], w))
+    for rank, got, rows in results:
+        assert got == expect                              # identical on every rank
+        for p in range(7):
+            assert rows[p] == [float(p), float(p % world)]  # pair p was handled by rank p % world
+    assert expect[0][1] == (20 if world == 2 else 10)
+    assert expect[1][1] == (20 if world == 2 else 10)
+    assert expect[2] == (0, 33, 1) and expect[3] == (-10000, -1, -1)
+
+
+def test_merge_matches_the_c_abi():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n = int(rng.integers(1, 9))
+        recs = [(int(rng.integers(-1, 6)), int(rng.integers(0, 4))) for _ in range(n)]
+        assert parallel.merge_records(recs) == parallel.merge_records_native(recs)
+
+
+def test_pairs_are_dealt_round_robin():
+    counts = [len(parallel.pairs_of_rank(28, r, 8)) for r in range(8)]
+    assert counts == [4, 4, 4, 4, 3, 3, 3, 3]
+    assert sorted(sum((parallel.pairs_of_rank(28, r, 8) for r in range(8)), [])) == list(range(28))
