@@ -127,6 +127,8 @@ class PlaceRecognition {
     double tf[16];
     const int rc = slide_pr_find_inter_loop_closure(h_, rows(reference_objects), (int32_t)reference_objects.size(),
                                                     rows(query_objects), (int32_t)query_objects.size(), tf, &last_);
+    match_x_half_range_ = last_.half_x;  // the members findTransformation leaves behind (PR.cpp:786-787)
+    match_y_half_range_ = last_.half_y;
     if (rc != SLIDE_PR_OK) return false;
     for (int r = 0; r < 4; r++)
       for (int c = 0; c < 4; c++) tfFromQueryToRef(r, c) = tf[r * 4 + c];
@@ -144,6 +146,8 @@ class PlaceRecognition {
       for (int c = 0; c < 4; c++) { qp[r * 4 + c] = query_pose(r, c); cp[r * 4 + c] = candidate_pose(r, c); }
     const int rc = slide_pr_find_intra_loop_closure(h_, rows(measurements), (int32_t)measurements.size(), rows(submap),
                                                     (int32_t)submap.size(), qp, cp, tf, &last_);
+    match_x_half_range_ = last_.half_x;  // PR.cpp:808-809
+    match_y_half_range_ = last_.half_y;
     if (rc != SLIDE_PR_OK) return false;
     for (int r = 0; r < 4; r++)
       for (int c = 0; c < 4; c++) tfFromQuery2Candidate(r, c) = tf[r * 4 + c];

@@ -48,7 +48,7 @@ struct slide_pr_handle {
   slide_pr_params p{};
   int device = 0;
   int sm_count = 148;
-  int variant = SPR_VARIANT_QUEUED;
+  int tables_mode = SPR_TABLES_AUTO;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -63,7 +63,7 @@ struct slide_pr_handle {
   spr::RefIndex R;
   spr::QuerySet Q;
   // device side
-  DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_cellword, d_cellword1,
+  DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_rank16, d_rank16b, d_rowrank, d_rowrankb, d_gcnt,
       d_cand, d_cand1, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
   SprView V{};
   std::vector<int32_t> h_match;
@@ -146,7 +146,8 @@ int slide_pr_create(const slide_pr_params *p, slide_pr_handle **out) {
     return SLIDE_PR_ERR_CUDA;
   }
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
-  if (const char *v = std::getenv("SLIDE_PR_VARIANT")) h->variant = std::atoi(v) == 0 ? SPR_VARIANT_DIRECT : SPR_VARIANT_QUEUED;
+  // SLIDE_PR_VARIANT=0 forces the global-memory table path (tests cover both paths)
+  if (const char *v = std::getenv("SLIDE_PR_VARIANT")) h->tables_mode = std::atoi(v) == 0 ? SPR_TABLES_GLOBAL : SPR_TABLES_AUTO;
   *out = h;
   return SLIDE_PR_OK;
 }
@@ -155,7 +156,7 @@ void slide_pr_destroy(slide_pr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (DevBuf *b : {&h->d_lat, &h->d_chunks, &h->d_cs, &h->d_qxy, &h->d_qdims, &h->d_labelseg, &h->d_qlabel,
-                    &h->d_labelbox, &h->d_gbox, &h->d_bitmap, &h->d_cellword, &h->d_cellword1, &h->d_cand, &h->d_cand1, &h->d_qrot,
+                    &h->d_labelbox, &h->d_gbox, &h->d_bitmap, &h->d_rank16, &h->d_rank16b, &h->d_rowrank, &h->d_rowrankb, &h->d_gcnt, &h->d_cand, &h->d_cand1, &h->d_qrot,
                     &h->d_qrotq, &h->d_qrotq_yx, &h->d_work, &h->d_ref7, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps, &h->d_tri, &h->d_tri_out})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -200,7 +201,7 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   h->yaw_half = h->p.inter_loop_closure ? h->p.match_yaw_half_range : h->p.match_yaw_half_range_intra;
   h->n_ref = n_ref; h->n_qry = n_qry;
   h->lat_tb = 0; h->lat_te = -1;
-  int rc = spr::build_lattice(h->p, half_x, half_y, h->yaw_half, 0, -1, h->L, h->err);
+  int rc = spr::build_lattice(h->p, half_x, half_y, h->yaw_half, 0, -1, h->p.compute_budget_sec > 0, h->L, h->err);
   if (rc != SLIDE_PR_OK) return rc;
   double qrad = 0;
   for (int j = 0; j < n_qry; j++) {
@@ -219,8 +220,10 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   if ((rc = upload(h, h->d_qlabel, h->Q.qlabel, st))) return rc;
   if ((rc = upload(h, h->d_labelbox, h->R.labelbox, st))) return rc;
   if ((rc = upload(h, h->d_bitmap, h->R.bitmap, st))) return rc;
-  if ((rc = upload(h, h->d_cellword, h->R.cellword[0], st))) return rc;
-  if ((rc = upload(h, h->d_cellword1, h->R.cellword[1], st))) return rc;
+  if ((rc = upload(h, h->d_rank16, h->R.rank16[0], st))) return rc;
+  if ((rc = upload(h, h->d_rank16b, h->R.rank16[1], st))) return rc;
+  if ((rc = upload(h, h->d_rowrank, h->R.row_rank[0], st))) return rc;
+  if ((rc = upload(h, h->d_rowrankb, h->R.row_rank[1], st))) return rc;
   if ((rc = upload(h, h->d_cand, h->R.cand[0], st))) return rc;
   if ((rc = upload(h, h->d_cand1, h->R.cand[1], st))) return rc;
   if ((rc = upload_raw(h, h->d_ref7, ref7, (size_t)n_ref * 7 * sizeof(double), st))) return rc;
@@ -251,8 +254,10 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   V.n_ref = n_ref;
   V.labelbox = h->d_labelbox.as<SprBox>();
   V.bitmap = h->d_bitmap.as<uint32_t>();
-  V.cellword[0] = h->d_cellword.as<uint32_t>();
-  V.cellword[1] = h->d_cellword1.as<uint32_t>();
+  V.rank16[0] = h->d_rank16.as<uint16_t>();
+  V.rank16[1] = h->d_rank16b.as<uint16_t>();
+  V.row_rank[0] = h->d_rowrank.as<uint32_t>();
+  V.row_rank[1] = h->d_rowrankb.as<uint32_t>();
   V.cand[0] = h->d_cand.as<SprCand>();
   V.cand[1] = h->d_cand1.as<SprCand>();
   V.grid = h->R.grid;
@@ -294,7 +299,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   int rc;
   const int64_t tb = o.trans_begin < 0 ? 0 : o.trans_begin, te = o.trans_end;
   if (tb != h->lat_tb || te != h->lat_te) {  // re-chunk the lattice for the requested slice
-    if ((rc = spr::build_lattice(h->p, h->half_x, h->half_y, h->yaw_half, tb, te, h->L, h->err)) != SLIDE_PR_OK) return rc;
+    if ((rc = spr::build_lattice(h->p, h->half_x, h->half_y, h->yaw_half, tb, te, h->p.compute_budget_sec > 0, h->L, h->err)) != SLIDE_PR_OK) return rc;
     h->lat_tb = tb; h->lat_te = te;
     if ((rc = upload_lattice(h, st))) return rc;
   }
@@ -328,6 +333,29 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
                                   h->d_gbox.as<SprBox>(), st));
     launches++;
   }
+  // one pass per (chunk range, bitmap direction, label with queries); the per-hypothesis counters
+  // travel between the label passes of a range in d_gcnt
+  std::vector<int> active;
+  for (int l = 0; l < h->V.n_labels; l++)
+    if (h->Q.label_gseg[l + 1] > h->Q.label_gseg[l]) active.push_back(l);
+  if (active.empty()) active.push_back(-1);  // no query can match: every hypothesis scores 0
+  K.n_chunks_total = (uint32_t)h->L.chunks.size();
+  if (active.size() > 1) {
+    const size_t per = h->V.nqp > 65535 ? 4 : 2;
+    SPR_CUDA(h, h->d_gcnt.ensure((size_t)n_yaw * (size_t)K.n_chunks_total * 32 * per + 64));
+  }
+  K.gcnt = h->d_gcnt.p;
+  auto run_range = [&](const uint32_t begin[2], const uint32_t end[2]) -> int {
+    for (uint32_t d = 0; d < 2; d++) {
+      if (end[d] <= begin[d]) continue;
+      for (size_t i = 0; i < active.size(); i++) {
+        K.chunk_begin = begin[d]; K.chunk_end = end[d]; K.dir = d; K.label = active[i];
+        K.first = i == 0; K.last = i + 1 == active.size();
+        SPR_CUDA(h, spr_launch_score_lattice(h->V, K, h->tables_mode, h->sm_count, st, &launches));
+      }
+    }
+    return SLIDE_PR_OK;
+  };
   int rings_scored = 0;
   if (h->p.compute_budget_sec > 0) {
     // anytime behaviour of PR.cpp:181-191: whole seconds, checked before every ring
@@ -336,16 +364,12 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
       const double duration = (double)std::chrono::duration_cast<std::chrono::seconds>(
                                   std::chrono::high_resolution_clock::now() - start).count();
       if (duration > h->p.compute_budget_sec) break;
-      K.chunk_begin = h->L.ring[k].chunk_begin;
-      K.chunk_end = h->L.ring[k].chunk_end;
-      SPR_CUDA(h, spr_launch_score_lattice(h->V, K, h->variant, h->sm_count, st, &launches));
+      if ((rc = run_range(h->L.ring[k].dbegin, h->L.ring[k].dend)) != SLIDE_PR_OK) return rc;
       SPR_CUDA(h, cudaStreamSynchronize(st));
       rings_scored++;
     }
   } else {
-    K.chunk_begin = 0;
-    K.chunk_end = (uint32_t)h->L.chunks.size();
-    SPR_CUDA(h, spr_launch_score_lattice(h->V, K, h->variant, h->sm_count, st, &launches));
+    if ((rc = run_range(h->L.dir_begin, h->L.dir_end)) != SLIDE_PR_OK) return rc;
     rings_scored = h->L.rings;
   }
   SPR_CUDA(h, cudaEventRecord(h->ev1, st));
@@ -365,21 +389,19 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   out->groups_skipped = (int64_t)stats[3];
   out->h2d_bytes = h->h2d_bytes;
   out->d2h_bytes = (int64_t)sizeof(key) + (o.collect_stats ? (int64_t)sizeof(stats) : 0) + n_counts * (int64_t)sizeof(int32_t);
-  // hypotheses scored by this shard = valid bits of its chunk groups x yaw candidates
+  // hypotheses scored by this shard = valid bits of its 32-chunk work-item columns x yaw candidates
   {
     const int sc = o.shard_count > 1 ? o.shard_count : 1, si = o.shard_count > 1 ? o.shard_index : 0;
     uint64_t bits = 0;
-    const uint32_t cend = h->p.compute_budget_sec > 0 && rings_scored > 0 ? h->L.ring[rings_scored - 1].chunk_end
-                          : (h->p.compute_budget_sec > 0 ? 0u : (uint32_t)h->L.chunks.size());
+    auto count_range = [&](uint32_t cb, uint32_t ce) {
+      for (uint32_t c = cb; c < ce; c++)
+        if ((int)(((c - cb) / SPR_WARP_CHUNKS) % sc) == si) bits += (uint64_t)__builtin_popcount(h->L.chunks[c].valid);
+    };
     if (h->p.compute_budget_sec > 0) {
-      for (int k = 0; k < rings_scored; k++) {
-        const uint32_t cb = h->L.ring[k].chunk_begin, ce = h->L.ring[k].chunk_end;
-        for (uint32_t c = cb; c < ce; c++)
-          if ((int)(((c - cb) / SPR_WARP_CHUNKS) % sc) == si) bits += (uint64_t)__builtin_popcount(h->L.chunks[c].valid);
-      }
+      for (int k = 0; k < rings_scored; k++)
+        for (int d = 0; d < 2; d++) count_range(h->L.ring[k].dbegin[d], h->L.ring[k].dend[d]);
     } else {
-      for (uint32_t c = 0; c < cend; c++)
-        if ((int)((c / SPR_WARP_CHUNKS) % sc) == si) bits += (uint64_t)__builtin_popcount(h->L.chunks[c].valid);
+      for (int d = 0; d < 2; d++) count_range(h->L.dir_begin[d], h->L.dir_end[d]);
     }
     out->hypotheses_scored = (int64_t)(bits * (uint64_t)n_yaw);
   }

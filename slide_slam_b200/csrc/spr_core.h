@@ -115,10 +115,22 @@ SPR_HD uint32_t spr_probe(const uint32_t *plane, uint32_t W, uint32_t Rm1, uint3
   return SPR_FUNNEL_R(p[0], p[1], bit) & valid;  // the funnel shift uses the low 5 bits of `bit`
 }
 
-// Linear bit address, inside the chunk's own plane, of the cell under bit 0 of a probe that hit
-// (no clamping: a hit implies the sums are inside the grid).  Bit b of the chunk is cell code + b.
-SPR_HD uint32_t spr_cell_code(uint32_t W, int32_t F, int32_t a, int32_t b) {
-  return (((uint32_t)(a >> F) * W) << 5) + (uint32_t)(b >> F);
+// Row and bit offset (inside the chunk's own plane) of the cell under bit 0 of a probe that hit
+// (no clamping: a hit implies the sums are inside the grid).  Bit b of the chunk is `bit + b`.
+SPR_HD void spr_cell_of(int32_t F, int32_t a, int32_t b, uint32_t *row, uint32_t *bit) {
+  *row = (uint32_t)(a >> F);
+  *bit = (uint32_t)(b >> F);
+}
+
+// rank tables of plane (l, d) in global memory
+SPR_HD SprTables spr_global_tables(const SprView &V, uint32_t d, int32_t l) {
+  const SprGrid &G = V.grid;
+  SprTables t;
+  t.bits = V.bitmap + ((size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u));
+  t.r16 = V.rank16[d] + (size_t)l * G.plane_words[d];
+  t.row_rank = V.row_rank[d] + (size_t)l * (size_t)G.R[d];
+  t.W = (uint32_t)G.W[d];
+  return t;
 }
 
 // May query group `g` (box of its fixed coords) land on label box `lb` for any translation of a
@@ -145,24 +157,26 @@ SPR_HD bool spr_verify_rank(const SprView &V, uint32_t d, uint32_t rank, double 
   }
 }
 
-// Exact verification of one occupied cell (linear bit address `code` in plane d) of label l for a
-// query point with rotated coordinates (rx, ry), under translation (tx, ty).
-SPR_HD bool spr_verify_cell(const SprView &V, uint32_t d, int32_t l, uint32_t code, double rx, double ry,
-                            double tx, double ty, const double *qd, int32_t *first_ref) {
-  const uint32_t *cw = V.cellword[d] + 2 * ((size_t)l * V.grid.plane_words[d] + (code >> 5));
-  const uint32_t rank = cw[1] + (uint32_t)SPR_POPC(cw[0] & ((1u << (code & 31u)) - 1u));
+// Exact verification of one occupied cell (row, bit) of the plane described by T (direction d).
+SPR_HD bool spr_verify_cell(const SprView &V, const SprTables &T, uint32_t d, uint32_t row, uint32_t bit, double rx,
+                            double ry, double tx, double ty, const double *qd, int32_t *first_ref) {
+  const uint32_t wi = row * T.W + (bit >> 5);
+  const uint32_t rank = T.row_rank[row] + T.r16[wi] + (uint32_t)SPR_POPC(T.bits[wi] & ((1u << (bit & 31u)) - 1u));
   return spr_verify_rank(V, d, rank, rx, ry, tx, ty, qd, first_ref);
 }
 
 // Exact verification of all filter hits H of ONE query landmark against the 32 consecutive cells
-// starting at bit address code0 of plane d (= the 32 translations of a chunk).  The translation of
-// bit b is (across, along[b]) (dir 0) or (along[b], across) (dir 1), exactly the reference's
-// accumulated lattice values.  Returns the mask of hypotheses for which the landmark is an inlier.
-SPR_HD uint32_t spr_verify_mask(const SprView &V, uint32_t d, int32_t l, uint32_t code0, uint32_t H, double rx,
-                                double ry, double across, const double *along, const double *qd) {
-  const uint32_t *cw = V.cellword[d] + 2 * ((size_t)l * V.grid.plane_words[d] + (code0 >> 5));
-  const uint32_t w0 = cw[0], before0 = cw[1], w1 = cw[2], before1 = cw[3];
-  const uint32_t off = code0 & 31u;
+// starting at (row, bit) of the plane described by T (= the 32 translations of a chunk of
+// direction d).  The translation of bit b is (across, along[b]) (dir 0) or (along[b], across)
+// (dir 1), exactly the reference's accumulated lattice values.  Returns the mask of hypotheses
+// for which the landmark is an inlier.
+SPR_HD uint32_t spr_verify_mask(const SprView &V, const SprTables &T, uint32_t d, uint32_t row, uint32_t bit, uint32_t H,
+                                double rx, double ry, double across, const double *along, const double *qd) {
+  const uint32_t wi = row * T.W + (bit >> 5);
+  const uint32_t w0 = T.bits[wi], w1 = T.bits[wi + 1];
+  const uint32_t base = T.row_rank[row];
+  const uint32_t before0 = base + T.r16[wi], before1 = base + T.r16[wi + 1];
+  const uint32_t off = bit & 31u;
   uint32_t P = 0u;
   while (H) {
     const int b = SPR_FFS(H) - 1;
@@ -179,7 +193,7 @@ SPR_HD uint32_t spr_verify_mask(const SprView &V, uint32_t d, int32_t l, uint32_
 
 // Occupancy test of a single point (general hypothesis lists): fixed-point cell of
 // (xt - g0x, yt - g0y); returns false when the cell is outside the grid or unmarked.
-SPR_HD bool spr_point_cell(const SprView &V, int32_t l, double xt, double yt, uint32_t *code) {
+SPR_HD bool spr_point_cell(const SprView &V, int32_t l, double xt, double yt, uint32_t *row, uint32_t *bitpos) {
   const SprGrid &G = V.grid;
   const double ux = SPR_DMUL(SPR_DSUB(xt, G.g0x), G.S), uy = SPR_DMUL(SPR_DSUB(yt, G.g0y), G.S);
   if (!(ux >= 0.0 && uy >= 0.0 && ux < 1073741824.0 && uy < 1073741824.0)) return false;
@@ -188,7 +202,8 @@ SPR_HD bool spr_point_cell(const SprView &V, int32_t l, double xt, double yt, ui
   const uint32_t bit = (uint32_t)(cy + 32);
   const uint32_t wloc = (uint32_t)(cx + 1) * (uint32_t)G.W[0] + (bit >> 5);
   const uint32_t word = V.bitmap[(size_t)l * G.label_stride + wloc];
-  *code = (wloc << 5) | (bit & 31u);  // linear bit address in plane 0
+  *row = (uint32_t)(cx + 1);
+  *bitpos = bit;
   return (word >> (bit & 31u)) & 1u;
 }
 

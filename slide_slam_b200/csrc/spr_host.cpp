@@ -93,7 +93,7 @@ struct RectEmitter {
 }  // namespace
 
 int build_lattice(const slide_pr_params &p, double half_x, double half_y, double yaw_half,
-                  int64_t trans_begin, int64_t trans_end, Lattice &L, std::string &err) {
+                  int64_t trans_begin, int64_t trans_end, bool ring_major, Lattice &L, std::string &err) {
   L = Lattice();
   const double step = p.match_xy_step_size;
   if (!(step > 0) || !std::isfinite(step)) { err = "match_xy_step_size must be positive and finite"; return SLIDE_PR_ERR_INVALID; }
@@ -188,6 +188,36 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
   if (ord * (uint64_t)std::max<size_t>(L.yaw.size(), 1) >= (1ull << SPR_KEY_IDX_BITS)) {
     err = "more than 2^40 hypotheses"; return SLIDE_PR_ERR_UNSUPPORTED;
   }
+  // Group the chunks by direction (every warp = 32 consecutive chunks probes ONE bitmap plane),
+  // padding each group to a whole number of warps with empty chunks.  ring_major keeps the
+  // chunks of a ring together (needed by the anytime budget, PR.cpp:181-191).
+  std::vector<SprChunk> out;
+  out.reserve(L.chunks.size() + 64 * (ring_major ? L.ring.size() + 1 : 2));
+  auto pad32 = [&out](uint32_t d) {
+    SprChunk z{};
+    z.dir = d;
+    while (out.size() % 32) out.push_back(z);
+  };
+  if (ring_major) {
+    for (Lattice::Ring &R : L.ring)
+      for (uint32_t d = 0; d < 2; d++) {
+        R.dbegin[d] = (uint32_t)out.size();
+        for (uint32_t c = R.chunk_begin; c < R.chunk_end; c++)
+          if (L.chunks[c].dir == d) out.push_back(L.chunks[c]);
+        pad32(d);
+        R.dend[d] = (uint32_t)out.size();
+      }
+  } else {
+    for (uint32_t d = 0; d < 2; d++) {
+      L.dir_begin[d] = (uint32_t)out.size();
+      for (const SprChunk &c : L.chunks)
+        if (c.dir == d) out.push_back(c);
+      pad32(d);
+      L.dir_end[d] = (uint32_t)out.size();
+    }
+  }
+  L.ring_major = ring_major;
+  L.chunks.swap(out);
   return SLIDE_PR_OK;
 }
 
@@ -337,17 +367,25 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
       cand[prev] = c;
     }
     if (cand.empty()) cand.assign(1, SprCand{0, 0, 0, 0, 0, 0u, 0u});
-    // (word, set bits before it) over the planes of direction d, label-major == rank order
-    std::vector<uint32_t> &cellword = R.cellword[d];
-    cellword.assign(2 * (size_t)G.plane_words[d] * (size_t)std::max(n_labels, 1) + 4, 0u);
+    // rank tables of direction d, label-major == rank order of the marked cells:
+    //   row_rank[l][row]  = rank of the first marked cell of the row (absolute, index into cand[d])
+    //   rank16[l][word]   = marked cells of the same row before the word
+    R.rank16[d].assign((size_t)G.plane_words[d] * (size_t)std::max(n_labels, 1) + 8, 0);
+    R.row_rank[d].assign((size_t)G.R[d] * (size_t)std::max(n_labels, 1) + 1, 0u);
     uint32_t running = 0;
     for (int l = 0; l < n_labels; l++) {
       const uint32_t *pl = R.bitmap.data() + (size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u);
-      uint32_t *cw = cellword.data() + 2 * (size_t)l * G.plane_words[d];
-      for (uint32_t w = 0; w < G.plane_words[d]; w++) {
-        cw[2 * (size_t)w] = pl[w];
-        cw[2 * (size_t)w + 1] = running;
-        running += (uint32_t)__builtin_popcount(pl[w]);
+      uint16_t *r16 = R.rank16[d].data() + (size_t)l * G.plane_words[d];
+      uint32_t *rr = R.row_rank[d].data() + (size_t)l * G.R[d];
+      for (int row = 0; row < G.R[d]; row++) {
+        rr[row] = running;
+        uint32_t in_row = 0;
+        for (int w = 0; w < G.W[d]; w++) {
+          if (in_row > 0xffffu) { err = "more than 65535 marked cells in one bitmap row"; return SLIDE_PR_ERR_UNSUPPORTED; }
+          r16[(size_t)row * G.W[d] + w] = (uint16_t)in_row;
+          in_row += (uint32_t)__builtin_popcount(pl[(size_t)row * G.W[d] + w]);
+        }
+        running += in_row;
       }
     }
     if ((size_t)running != n_cells) { err = "internal: rank / cell list mismatch"; return SLIDE_PR_ERR_INTERNAL; }

@@ -23,17 +23,20 @@ struct Lattice {
     int ixl, ixh, iyl, iyh;         // inner (already searched) box as closed index ranges; empty if l > h
     uint64_t ord_base;              // ordinal of the ring's first translation
     uint64_t count;                 // translations in the ring
-    uint32_t chunk_begin, chunk_end;
+    uint32_t chunk_begin, chunk_end;    // emission order (before grouping by direction)
+    uint32_t dbegin[2] = {0, 0}, dend[2] = {0, 0};  // ring_major: this ring's chunks of direction d
   };
   std::vector<Ring> ring;
   uint64_t n_translations = 0;
-  std::vector<SprChunk> chunks;   // ring-major
+  std::vector<SprChunk> chunks;   // grouped by direction (see dir_begin / Ring::dbegin), warp-padded
+  bool ring_major = false;
+  uint32_t dir_begin[2] = {0, 0}, dir_end[2] = {0, 0};  // !ring_major: all chunks of direction d
 };
 
 // PR.cpp:136-241.  yaw_half is match_yaw_half_range_ (inter) or the intra value.
 // trans_begin/trans_end (end < 0: none) restrict the valid bits to a range of ordinals.
 int build_lattice(const slide_pr_params &p, double half_x, double half_y, double yaw_half,
-                  int64_t trans_begin, int64_t trans_end, Lattice &L, std::string &err);
+                  int64_t trans_begin, int64_t trans_end, bool ring_major, Lattice &L, std::string &err);
 
 // translation (x, y) of a canonical ordinal; false if out of range
 bool translation_of(const Lattice &L, uint64_t ordinal, double *x, double *y, int *ring);
@@ -42,8 +45,9 @@ struct RefIndex {
   std::vector<double> labels;       // distinct finite reference labels, ascending
   SprGrid grid{};
   std::vector<uint32_t> bitmap;     // [n_labels][plane0 | plane1]
-  std::vector<uint32_t> cellword[2]; // per plane direction d: [n_labels][plane_words[d]][2] (bits, set bits before)
   std::vector<SprCand> cand[2];      // per plane direction d: [n_cells] first candidate per cell rank, then chained extras
+  std::vector<uint16_t> rank16[2];   // per plane direction d: [n_labels][plane_words[d]] marked cells of the row before the word
+  std::vector<uint32_t> row_rank[2]; // per plane direction d: [n_labels][R[d]] rank (index into cand[d]) of the row's first marked cell
   std::vector<SprBox> labelbox;     // [n_labels] fixed-point bounds of the label's marked cells
   double Tstar = 0, Sstar = 0;
   int n_ref = 0;

@@ -2,43 +2,42 @@
 //
 // Replaces the five nested loops of PlaceRecognition::MatchMaps (place_recognition.cpp:178-372).
 // Work decomposition:
+//   * the search runs as one PASS per (label, bitmap direction): all CTAs work on the same
+//     occupancy plane at the same time, so the plane and its rank tables are staged once per CTA
+//     into SHARED MEMORY when they fit (otherwise they are read through L1/L2); per-hypothesis
+//     inlier counters are carried between the passes in HBM (2 bytes per hypothesis);
 //   * one THREAD owns one chunk = 32 consecutive lattice translations along one axis, for one
 //     yaw candidate; a WARP owns 32 chunks (1024 hypotheses) and is the unit of scheduling: warps
-//     pull (yaw, 32-chunk) work items from a global counter, there is no block-level barrier;
+//     pull (yaw, 32-chunk) work items from a global counter, there is no barrier after staging;
 //   * query landmarks come in groups of 8 (one label, Morton order) with a bounding box per yaw;
 //     a group that cannot reach the label's occupied cells from any of the warp's 1024
 //     translations is skipped with four integer compares;
-//   * for every remaining query landmark the thread reads two words of the label's occupancy
-//     bitmap and obtains the 32 hypotheses' filter bits with one funnel shift (spr_probe);
-//   * set bits ("filter hits", well under 1 % of the probes) are compacted through a per-warp
-//     shared-memory queue (warp prefix-sum over popcounts) and verified 32 at a time in exact,
-//     non-fused fp64 against the cell's candidates (spr_verify_cell) -- the reference's own
+//   * for every remaining query landmark the thread reads two words of the plane and obtains the
+//     32 hypotheses' filter bits with one funnel shift (spr_probe);
+//   * probes with set bits ("filter hits") are compacted through a per-warp shared-memory queue
+//     (warp prefix-sum over the record counts) and verified 32 records at a time in exact,
+//     non-fused fp64 against the cells' candidates (spr_verify_mask) -- the reference's own
 //     predicate, so every hypothesis gets its exact inlier count;
-//   * per-hypothesis counters live in shared memory; the best (count, canonical index) key is
-//     reduced with shuffles and one 64-bit atomicMax per warp.
-// This is integer/bit and fp64 ALU work on L1/L2-resident data; there is no GEMM in it, so no
-// tensor-core path (BASELINE.json north_star).
+//   * after the last pass the best (count, canonical index) key is reduced with shuffles and one
+//     64-bit atomicMax per warp.
+// This is integer/bit and fp64 ALU work on shared-memory / L2-resident data; there is no GEMM in
+// it, so no tensor-core path (BASELINE.json north_star).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "spr_core.h"
 #include "spr_kernels.h"
 
-#ifndef SPR_BLOCK
-#define SPR_BLOCK 256   // threads per CTA (8 independent warps)
-#endif
-#ifndef SPR_MINB
-#define SPR_MINB 4      // CTAs per SM the register allocation is tuned for
-#endif
-#define SPR_WARPS (SPR_BLOCK / 32)
-#define SPR_QHALF 4              // queries probed per push
-#define SPR_QCAP (32 * SPR_QHALF + 32)  // per-warp hit queue, records (3 words each): residual < 32 + one push
-// Per-hypothesis inlier counters, [32 lanes][32 bits] per warp.  Counts are bounded by the number
-// of query landmarks, so they are packed two per word (pitch 17 words per lane) unless the query
-// map has more than 65535 landmarks (pitch 33 words per lane).  Shared memory is kept small on
-// purpose: what the CTAs do not take stays L1 cache for the occupancy bitmaps.
+#define SPR_QHALF 4                      // queries probed per push
+#define SPR_QCAP (32 * SPR_QHALF + 32)   // per-warp queue, records: residual < 32 + one push
+#define SPR_FULL 0xffffffffu
+#define SPR_SMEM_LIMIT (227 * 1024)
+
+// Per-hypothesis inlier counters of one warp's work item, [32 lanes][32 bits].  Counts are
+// bounded by the number of query landmarks, so they are packed two per word (pitch 17 words per
+// lane) unless the query map has more than 65535 landmarks (pitch 33 words per lane).
 #define SPR_CNT_WORDS(CNT32) ((CNT32) ? 32 * 33 : 32 * 17)
-#define SPR_WARP_SMEM(CNT32) (SPR_CNT_WORDS(CNT32) + 3 * SPR_QCAP)  // words per warp
+#define SPR_WARP_WORDS(CNT32) (SPR_CNT_WORDS(CNT32) + 4 * SPR_QCAP)  // multiple of 4 words (16 B)
 
 template <bool CNT32> __device__ __forceinline__ void spr_cnt_zero(uint32_t *cnt, int lane) {
   if (CNT32) {
@@ -57,7 +56,6 @@ template <bool CNT32> __device__ __forceinline__ uint32_t spr_cnt_get(const uint
   if (CNT32) return cnt[lane * 33 + b];
   return (cnt[lane * 17 + (b >> 1)] >> ((b & 1) << 4)) & 0xffffu;
 }
-#define SPR_FULL 0xffffffffu
 
 // ---------------------------------------------------------------------------------------------
 // rotate: one thread per (yaw, query group)
@@ -84,64 +82,81 @@ cudaError_t spr_launch_rotate(const SprView &V, int32_t *qrotq_xy, int32_t *qrot
 // lattice scoring
 // ---------------------------------------------------------------------------------------------
 struct WarpState {
-  uint32_t *cnt;    // inlier counters of the warp's 1024 hypotheses (spr_cnt_*)
-  uint32_t *q_meta; // [SPR_QCAP] pending records: query index js << 5 | owner lane
-  uint32_t *q_code; // [SPR_QCAP] bit address (own plane) of the cell under bit 0 of the probe
-  uint32_t *q_mask; // [SPR_QCAP] the probe's hit bits
-  int qcount;       // warp-uniform
+  uint32_t *cnt;  // inlier counters of the warp's 1024 hypotheses (spr_cnt_*)
+  uint4 *queue;   // [SPR_QCAP] pending records: x = query index js << 5 | owner lane, y = row,
+                  //   z = bit offset of chunk bit 0 in the row, w = the probe's hit bits
+  int qcount;     // warp-uniform
 };
 
-// One queued record = all filter hits of ONE query landmark on ONE chunk (lane): verify its bits
-// in exact fp64 and add the survivors to the owner's counters.
+// Verify up to 32 queued records, one per lane.  A record = all filter hits of ONE query landmark
+// on ONE chunk (lane).  Chunk parameters of the owning lane come through shuffles (executed by
+// every lane); survivors are added to the owner's counters.
 template <bool CNT32>
-__device__ __forceinline__ void spr_verify_record(const SprView &V, uint32_t *cnt, int l, int a, int js, int owner,
-                                                  uint32_t code0, uint32_t H, uint32_t o_dir, uint32_t o_off,
-                                                  double o_across, unsigned long long &n_inl) {
-  const size_t qi = (size_t)a * (size_t)V.nqp + (size_t)js;
-  const double2 r = __ldg(reinterpret_cast<const double2 *>(V.qrot) + qi);
-  uint32_t P = spr_verify_mask(V, o_dir, l, code0, H, r.x, r.y, o_across, V.lat + o_off, V.qdims + 3 * (size_t)js);
-  n_inl += (unsigned long long)__popc(P);
-  while (P) {
-    const int b = __ffs(P) - 1;
-    P &= P - 1;
-    spr_cnt_inc<CNT32>(cnt, owner, b);
-  }
-}
-
-// Verify up to 32 queued records, one per lane.  Chunk parameters of the owning lane come
-// through shuffles; every lane executes the shuffles.
-template <bool CNT32>
-__device__ __forceinline__ void spr_drain32(const SprView &V, WarpState &ws, int l, int a, int lane, uint32_t dir,
-                                            uint32_t along_off, double across, unsigned long long &n_inl) {
+__device__ __forceinline__ void spr_drain32(const SprView &V, const SprTables &T, WarpState &ws, uint32_t d, int a,
+                                            int lane, uint32_t along_off, double across, unsigned long long &n_inl) {
   const int n = ws.qcount < 32 ? ws.qcount : 32;
   const bool active = lane < n;
-  const int slot = ws.qcount - n + lane;
-  const uint32_t meta = active ? ws.q_meta[slot] : 0u;
-  const uint32_t code0 = active ? ws.q_code[slot] : 0u;
-  const uint32_t H = active ? ws.q_mask[slot] : 0u;
-  const int owner = meta & 31;
-  const uint32_t o_dir = __shfl_sync(SPR_FULL, dir, owner);
+  uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+  if (active) rec = ws.queue[ws.qcount - n + lane];
+  const int owner = rec.x & 31;
   const uint32_t o_off = __shfl_sync(SPR_FULL, along_off, owner);
   const double o_across = __shfl_sync(SPR_FULL, across, owner);
-  if (active) spr_verify_record<CNT32>(V, ws.cnt, l, a, (int)(meta >> 5), owner, code0, H, o_dir, o_off, o_across, n_inl);
+  if (active) {
+    const int js = (int)(rec.x >> 5);
+    const double2 r = __ldg(reinterpret_cast<const double2 *>(V.qrot) + ((size_t)a * (size_t)V.nqp + (size_t)js));
+    uint32_t P = spr_verify_mask(V, T, d, rec.y, rec.z, rec.w, r.x, r.y, o_across, V.lat + o_off, V.qdims + 3 * (size_t)js);
+    n_inl += (unsigned long long)__popc(P);
+    while (P) {
+      const int b = __ffs(P) - 1;
+      P &= P - 1;
+      spr_cnt_inc<CNT32>(ws.cnt, owner, b);
+    }
+  }
   ws.qcount -= n;
   __syncwarp();
 }
 
-template <int VARIANT, bool WRITE_COUNTS, bool STATS, bool CNT32>
-__global__ void __launch_bounds__(SPR_BLOCK, SPR_MINB)
-spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_local, const long long n_items) {
-  extern __shared__ uint32_t smem[];
+template <int BLOCK, int MINB, bool SMEM_TAB, bool STATS, bool CNT32>
+__global__ void __launch_bounds__(BLOCK, MINB)
+spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_local, const long long n_items,
+                         const uint32_t tab_bytes) {
+  extern __shared__ __align__(16) uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpState ws;
-  ws.cnt = smem + warp * SPR_WARP_SMEM(CNT32);
-  ws.q_meta = ws.cnt + SPR_CNT_WORDS(CNT32);
-  ws.q_code = ws.q_meta + SPR_QCAP;
-  ws.q_mask = ws.q_code + SPR_QCAP;
-  ws.qcount = 0;
   const SprGrid &G = V.grid;
   const int32_t F = G.F;
+  const uint32_t d = K.dir;
+  const int l = K.label;
+  const uint32_t W = (uint32_t)G.W[d], Rm1 = (uint32_t)G.R[d] - 1u, maxbit = (uint32_t)G.maxbit[d];
+
+  // rank tables of this pass' plane: staged into shared memory once per CTA, or read in place
+  SprTables T;
+  T.W = W;
+  if (SMEM_TAB) {
+    const SprTables GT = spr_global_tables(V, d, l < 0 ? 0 : l);
+    const uint32_t PW = G.plane_words[d];
+    uint32_t *s_bits = smem;
+    uint32_t *s_r16 = s_bits + ((PW + 3u) & ~3u);
+    uint32_t *s_rr = s_r16 + ((((PW + 1u) >> 1) + 3u) & ~3u);
+    for (uint32_t i = threadIdx.x; i < PW; i += blockDim.x) s_bits[i] = GT.bits[i];
+    uint16_t *s_r16h = reinterpret_cast<uint16_t *>(s_r16);
+    for (uint32_t i = threadIdx.x; i < PW; i += blockDim.x) s_r16h[i] = GT.r16[i];
+    for (uint32_t i = threadIdx.x; i <= Rm1; i += blockDim.x) s_rr[i] = GT.row_rank[i];
+    __syncthreads();
+    T.bits = s_bits;
+    T.r16 = reinterpret_cast<const uint16_t *>(s_r16);
+    T.row_rank = s_rr;
+  } else {
+    T = spr_global_tables(V, d, l < 0 ? 0 : l);
+  }
+  WarpState ws;
+  ws.cnt = smem + (tab_bytes >> 2) + warp * SPR_WARP_WORDS(CNT32);
+  ws.queue = reinterpret_cast<uint4 *>(ws.cnt + SPR_CNT_WORDS(CNT32));
+  ws.qcount = 0;
   unsigned long long best = 0ull, n_hits = 0ull, n_inl = 0ull, n_probed = 0ull, n_skipped = 0ull;
+
+  const SprBox lb = l >= 0 ? V.labelbox[l] : SprBox{0, -(1 << 30), 0, -(1 << 30)};
+  const int g0 = l >= 0 ? V.label_gseg[l] : 0, g1 = l >= 0 ? V.label_gseg[l + 1] : 0;
+  const int32_t *q_fx = d ? V.qrotq_yx : V.qrotq_xy;
 
   for (;;) {
     // per-warp dynamic scheduling, yaw-major: warps running at the same time share qrotq[a][*]
@@ -151,14 +166,10 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
     if (item >= n_items) break;
     const int a = (int)(item / n_wg_local);
     const int wg = K.shard_index + (int)(item % n_wg_local) * K.shard_count;
-    const uint32_t cidx = K.chunk_begin + (uint32_t)wg * SPR_WARP_CHUNKS + (uint32_t)lane;
-    double across = 0.0;
-    uint32_t along_off = 0u, valid = 0u, ord_base = 0u, ord_stride = 0u, dir = 0u;
-    if (cidx < K.chunk_end) {
-      const SprChunk ch = V.chunks[cidx];
-      across = ch.across; along_off = ch.along_off; valid = ch.valid;
-      ord_base = ch.ord_base; ord_stride = ch.ord_stride; dir = ch.dir;
-    }
+    const uint32_t cidx = K.chunk_begin + (uint32_t)wg * SPR_WARP_CHUNKS + (uint32_t)lane;  // < chunk_end (padded)
+    const SprChunk ch = V.chunks[cidx];
+    const double across = ch.across;
+    const uint32_t along_off = ch.along_off, valid = ch.valid;
     spr_cnt_zero<CNT32>(ws.cnt, lane);
     const int32_t aq0 = spr_fx(across, G.S);
     const int32_t bq0 = spr_fx(__ldg(V.lat + along_off), G.S);
@@ -166,106 +177,104 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
     // patch window of the warp's 1024 translations (unbiased fixed point)
     const int32_t big = 1 << 30;
     const bool live = valid != 0u;
-    const int32_t lx0 = dir ? bq0 : aq0, lx1 = dir ? bq0 + (32 << F) : aq0;
-    const int32_t ly0 = dir ? aq0 : bq0, ly1 = dir ? aq0 : bq0 + (32 << F);
+    const int32_t lx0 = d ? bq0 : aq0, lx1 = d ? bq0 + (32 << F) : aq0;
+    const int32_t ly0 = d ? aq0 : bq0, ly1 = d ? aq0 : bq0 + (32 << F);
     const int32_t X0 = __reduce_min_sync(SPR_FULL, live ? lx0 : big), X1 = __reduce_max_sync(SPR_FULL, live ? lx1 : -big);
     const int32_t Y0 = __reduce_min_sync(SPR_FULL, live ? ly0 : big), Y1 = __reduce_max_sync(SPR_FULL, live ? ly1 : -big);
     __syncwarp();
-    const uint32_t W = (uint32_t)G.W[dir], Rm1 = (uint32_t)G.R[dir] - 1u, maxbit = (uint32_t)G.maxbit[dir];
-    const int2 *__restrict__ qa2 =
-        reinterpret_cast<const int2 *>((dir ? V.qrotq_yx : V.qrotq_xy) + 2 * (size_t)a * (size_t)V.nqp);
-    const int4 *__restrict__ qa = reinterpret_cast<const int4 *>(qa2);
 
-    if (X0 <= X1) {  // at least one live lane
-      for (int l = 0; l < V.n_labels; l++) {
-        // this lane's bitmap plane as a materialised 64-bit pointer: one IMAD.WIDE per probe
-        const uint32_t *plane = V.bitmap + ((size_t)l * G.label_stride + (dir ? G.plane_words[0] : 0u));
-        asm volatile("" : "+l"(plane));
-        const SprBox lb = V.labelbox[l];
-        // a group is visible iff gx1 > tx_lo && gx0 < tx_hi && gy1 > ty_lo && gy0 < ty_hi
-        const int32_t tx_lo = lb.x0 - X1, tx_hi = lb.x1 - X0, ty_lo = lb.y0 - Y1, ty_hi = lb.y1 - Y0;
-        const int g0 = V.label_gseg[l], g1 = V.label_gseg[l + 1];
-        const int4 *gbp = reinterpret_cast<const int4 *>(V.gbox) + ((size_t)a * (size_t)V.n_groups + (size_t)g0);
-        const int4 *qgp = qa + (size_t)g0 * (SPR_QGROUP / 2);
-        for (int g = g0; g < g1; g++, gbp++, qgp += SPR_QGROUP / 2) {
-          const int4 box = __ldg(gbp);  // (x0, x1, y0, y1), same address for the whole warp
-          if (!(box.y > tx_lo && box.x < tx_hi && box.w > ty_lo && box.z < ty_hi)) {
-            if (STATS) n_skipped++;
-            continue;
-          }
-          if (STATS) n_probed++;
-          // the group is probed in two halves of SPR_QHALF queries: at most 32 * SPR_QHALF new
-          // records per push, so the queue (drained below 32 after every push) cannot overflow
-#pragma unroll 1
-          for (int hq = 0; hq < SPR_QGROUP / SPR_QHALF; hq++) {
-            uint32_t H[SPR_QHALF];
-#pragma unroll
-            for (int u = 0; u < SPR_QHALF / 2; u++) {
-              const int4 v = __ldg(qgp + hq * (SPR_QHALF / 2) + u);  // two queries: (across, along) x 2
-              H[2 * u] = spr_probe(plane, W, Rm1, maxbit, F, aqb + v.x, bqb + v.y, SPR_FULL);
-              H[2 * u + 1] = spr_probe(plane, W, Rm1, maxbit, F, aqb + v.z, bqb + v.w, SPR_FULL);
-            }
-            uint32_t any = 0u;
-#pragma unroll
-            for (int u = 0; u < SPR_QHALF; u++) any |= H[u];
-            any &= valid;
-            if (__ballot_sync(SPR_FULL, any != 0u) == 0u) continue;
-            // one record per (lane, query) with hits
-            int n = 0;
-#pragma unroll
-            for (int u = 0; u < SPR_QHALF; u++) { H[u] &= valid; n += H[u] != 0u; }
-            if (STATS) {
-#pragma unroll
-              for (int u = 0; u < SPR_QHALF; u++) n_hits += (unsigned long long)__popc(H[u]);
-            }
-            const int js0 = g * SPR_QGROUP + hq * SPR_QHALF;
-            if (VARIANT == SPR_VARIANT_DIRECT) {  // test variant: every lane verifies its own hits
-#pragma unroll
-              for (int u = 0; u < SPR_QHALF; u++) {
-                if (H[u] == 0u) continue;
-                const int2 q = __ldg(qa2 + js0 + u);
-                spr_verify_record<CNT32>(V, ws.cnt, l, a, js0 + u, lane, spr_cell_code(W, F, aqb + q.x, bqb + q.y), H[u], dir,
-                                         along_off, across, n_inl);
-              }
-              continue;
-            }
-            // warp inclusive prefix sum of the per-lane record counts
-            int incl = n;
-#pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-              const int t = __shfl_up_sync(SPR_FULL, incl, dlt);
-              if (lane >= dlt) incl += t;
-            }
-            const int total = __shfl_sync(SPR_FULL, incl, 31);
-            int pos = ws.qcount + incl - n;
-#pragma unroll
-            for (int u = 0; u < SPR_QHALF; u++) {
-              if (H[u] == 0u) continue;
-              const int2 q = __ldg(qa2 + js0 + u);  // L1 hit: loaded a moment ago by the probe
-              ws.q_meta[pos] = ((uint32_t)(js0 + u) << 5) | (uint32_t)lane;
-              ws.q_code[pos] = spr_cell_code(W, F, aqb + q.x, bqb + q.y);
-              ws.q_mask[pos] = H[u];
-              pos++;
-            }
-            ws.qcount += total;
-            __syncwarp();
-            while (ws.qcount >= 32) spr_drain32<CNT32>(V, ws, l, a, lane, dir, along_off, across, n_inl);
-          }
+    if (X0 <= X1 && g0 < g1) {  // at least one live lane and at least one query of this label
+      const int2 *__restrict__ qa2 = reinterpret_cast<const int2 *>(q_fx + 2 * (size_t)a * (size_t)V.nqp);
+      // a group is visible iff gx1 > tx_lo && gx0 < tx_hi && gy1 > ty_lo && gy0 < ty_hi
+      const int32_t tx_lo = lb.x0 - X1, tx_hi = lb.x1 - X0, ty_lo = lb.y0 - Y1, ty_hi = lb.y1 - Y0;
+      const int4 *gbp = reinterpret_cast<const int4 *>(V.gbox) + ((size_t)a * (size_t)V.n_groups + (size_t)g0);
+      const int4 *qgp = reinterpret_cast<const int4 *>(qa2) + (size_t)g0 * (SPR_QGROUP / 2);
+      for (int g = g0; g < g1; g++, gbp++, qgp += SPR_QGROUP / 2) {
+        const int4 box = __ldg(gbp);  // (x0, x1, y0, y1), same address for the whole warp
+        if (!(box.y > tx_lo && box.x < tx_hi && box.w > ty_lo && box.z < ty_hi)) {
+          if (STATS) n_skipped++;
+          continue;
         }
-        // the queue only ever holds hits of the current label
-        while (ws.qcount > 0) spr_drain32<CNT32>(V, ws, l, a, lane, dir, along_off, across, n_inl);
+        if (STATS) n_probed++;
+        // the group is probed in halves of SPR_QHALF queries: at most 32 * SPR_QHALF new records
+        // per push, so the queue (drained below 32 after every push) cannot overflow
+#pragma unroll 1
+        for (int hq = 0; hq < SPR_QGROUP / SPR_QHALF; hq++) {
+          uint32_t H[SPR_QHALF];
+#pragma unroll
+          for (int u = 0; u < SPR_QHALF / 2; u++) {
+            const int4 v = __ldg(qgp + hq * (SPR_QHALF / 2) + u);  // two queries: (across, along) x 2
+            H[2 * u] = spr_probe(T.bits, W, Rm1, maxbit, F, aqb + v.x, bqb + v.y, SPR_FULL);
+            H[2 * u + 1] = spr_probe(T.bits, W, Rm1, maxbit, F, aqb + v.z, bqb + v.w, SPR_FULL);
+          }
+          uint32_t any = 0u;
+#pragma unroll
+          for (int u = 0; u < SPR_QHALF; u++) any |= H[u];
+          any &= valid;
+          if (__ballot_sync(SPR_FULL, any != 0u) == 0u) continue;
+          // one record per (lane, query) with hits
+          int n = 0;
+#pragma unroll
+          for (int u = 0; u < SPR_QHALF; u++) { H[u] &= valid; n += H[u] != 0u; }
+          if (STATS) {
+#pragma unroll
+            for (int u = 0; u < SPR_QHALF; u++) n_hits += (unsigned long long)__popc(H[u]);
+          }
+          const int js0 = g * SPR_QGROUP + hq * SPR_QHALF;
+          // warp inclusive prefix sum of the per-lane record counts
+          int incl = n;
+#pragma unroll
+          for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const int t = __shfl_up_sync(SPR_FULL, incl, dlt);
+            if (lane >= dlt) incl += t;
+          }
+          const int total = __shfl_sync(SPR_FULL, incl, 31);
+          int pos = ws.qcount + incl - n;
+#pragma unroll
+          for (int u = 0; u < SPR_QHALF; u++) {
+            if (H[u] == 0u) continue;
+            const int2 q = __ldg(qa2 + js0 + u);  // L1 hit: loaded a moment ago by the probe
+            uint32_t row, bit;
+            spr_cell_of(F, aqb + q.x, bqb + q.y, &row, &bit);
+            ws.queue[pos++] = make_uint4(((uint32_t)(js0 + u) << 5) | (uint32_t)lane, row, bit, H[u]);
+          }
+          ws.qcount += total;
+          __syncwarp();
+          while (ws.qcount >= 32) spr_drain32<CNT32>(V, T, ws, d, a, lane, along_off, across, n_inl);
+        }
       }
-      __syncwarp();
-      // each lane scans the 32 hypotheses of its chunk
+      while (ws.qcount > 0) spr_drain32<CNT32>(V, T, ws, d, a, lane, along_off, across, n_inl);
+    }
+    __syncwarp();
+
+    // merge with the counters of the earlier passes; after the last pass reduce to the best key
+    uint32_t *gw = reinterpret_cast<uint32_t *>(K.gcnt) +
+                   ((size_t)a * (size_t)K.n_chunks_total + (size_t)(cidx - lane)) * (CNT32 ? 32 : 16) +
+                   (size_t)lane * (CNT32 ? 32 : 16);
+    if (!K.first) {
+#pragma unroll
+      for (int w = 0; w < (CNT32 ? 32 : 16); w += 4) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(gw + w);
+        uint32_t *c = ws.cnt + lane * (CNT32 ? 33 : 17) + w;
+        c[0] += v.x; c[1] += v.y; c[2] += v.z; c[3] += v.w;
+      }
+    }
+    if (!K.last) {
+#pragma unroll
+      for (int w = 0; w < (CNT32 ? 32 : 16); w += 4) {
+        const uint32_t *c = ws.cnt + lane * (CNT32 ? 33 : 17) + w;
+        *reinterpret_cast<uint4 *>(gw + w) = make_uint4(c[0], c[1], c[2], c[3]);
+      }
+    } else {
       uint32_t v = valid;
       while (v) {
         const int b = __ffs(v) - 1;
         v &= v - 1;
         const uint32_t c = spr_cnt_get<CNT32>(ws.cnt, lane, b);
-        const unsigned long long ord = (unsigned long long)ord_base + (unsigned long long)b * ord_stride;
+        const unsigned long long ord = (unsigned long long)ch.ord_base + (unsigned long long)b * ch.ord_stride;
         const unsigned long long key = spr_make_key(c, ord * (unsigned long long)V.n_yaw + (unsigned long long)a);
         best = key > best ? key : best;
-        if (WRITE_COUNTS) {
+        if (K.counts_out) {
           const long long slot = ((long long)ord - (long long)K.ord_begin) * V.n_yaw + a;
           if (slot >= 0 && slot < K.counts_cap) K.counts_out[slot] = (int32_t)c;
         }
@@ -273,13 +282,14 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
     }
     __syncwarp();
   }
-  // warp max of the 64-bit key, then one atomic per warp
+  if (K.last) {  // warp max of the 64-bit key, then one atomic per warp
 #pragma unroll
-  for (int dlt = 16; dlt > 0; dlt >>= 1) {
-    const unsigned long long o = __shfl_xor_sync(SPR_FULL, best, dlt);
-    best = o > best ? o : best;
+    for (int dlt = 16; dlt > 0; dlt >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(SPR_FULL, best, dlt);
+      best = o > best ? o : best;
+    }
+    if (lane == 0 && best != 0ull) atomicMax(K.best_key, best);
   }
-  if (lane == 0 && best != 0ull) atomicMax(K.best_key, best);
   if (STATS) {
 #pragma unroll
     for (int dlt = 16; dlt > 0; dlt >>= 1) {
@@ -293,31 +303,36 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
   }
 }
 
-template <int VARIANT, bool CNT32>
-static cudaError_t launch_variant(const SprView &V, const SprLaunch &K, int n_wg_local, long long n_items,
-                                  int grid, cudaStream_t st) {
-  const bool wc = K.counts_out != nullptr, stt = K.stats != nullptr;
-  const size_t smem = (size_t)SPR_WARPS * SPR_WARP_SMEM(CNT32) * sizeof(uint32_t);
-#define SPR_GO(WC, ST)                                                                                            \
-  do {                                                                                                            \
-    cudaError_t e = cudaFuncSetAttribute(spr_score_lattice_kernel<VARIANT, WC, ST, CNT32>,                        \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
-    if (e != cudaSuccess) return e;                                                                               \
-    spr_score_lattice_kernel<VARIANT, WC, ST, CNT32><<<grid, SPR_BLOCK, smem, st>>>(V, K, n_wg_local, n_items);    \
-  } while (0)
-  if (wc && stt) SPR_GO(true, true);
-  else if (wc) SPR_GO(true, false);
-  else if (stt) SPR_GO(false, true);
-  else SPR_GO(false, false);
-#undef SPR_GO
+// shared-memory bytes of the staged tables of direction d (bits, rank16, row_rank; 16-byte aligned parts)
+static uint32_t spr_table_bytes(const SprGrid &G, uint32_t d) {
+  const uint32_t PW = G.plane_words[d];
+  const uint32_t words = ((PW + 3u) & ~3u) + ((((PW + 1u) >> 1) + 3u) & ~3u) + (((uint32_t)G.R[d] + 3u) & ~3u);
+  return words * 4u;
+}
+
+template <int BLOCK, int MINB, bool SMEM_TAB, bool CNT32>
+static cudaError_t spr_launch_cfg(const SprView &V, const SprLaunch &K, int n_wg_local, long long n_items, int grid,
+                                  int threads, size_t smem, uint32_t tab_bytes, cudaStream_t st) {
+  cudaError_t e;
+  if (K.stats) {
+    e = cudaFuncSetAttribute(spr_score_lattice_kernel<BLOCK, MINB, SMEM_TAB, true, CNT32>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    spr_score_lattice_kernel<BLOCK, MINB, SMEM_TAB, true, CNT32><<<grid, threads, smem, st>>>(V, K, n_wg_local, n_items, tab_bytes);
+  } else {
+    e = cudaFuncSetAttribute(spr_score_lattice_kernel<BLOCK, MINB, SMEM_TAB, false, CNT32>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    spr_score_lattice_kernel<BLOCK, MINB, SMEM_TAB, false, CNT32><<<grid, threads, smem, st>>>(V, K, n_wg_local, n_items, tab_bytes);
+  }
   return cudaGetLastError();
 }
 
-cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int variant, int sm_count,
+cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int tables_mode, int sm_count,
                                      cudaStream_t st, int *n_launches) {
   if (K.chunk_end <= K.chunk_begin || V.n_yaw <= 0) return cudaSuccess;
   const uint32_t n_chunks = K.chunk_end - K.chunk_begin;
-  const int n_wg = (int)((n_chunks + SPR_WARP_CHUNKS - 1) / SPR_WARP_CHUNKS);
+  const int n_wg = (int)(n_chunks / SPR_WARP_CHUNKS);
   const int sc = K.shard_count > 1 ? K.shard_count : 1;
   const int si = K.shard_count > 1 ? K.shard_index : 0;
   const int n_wg_local = n_wg > si ? (n_wg - si + sc - 1) / sc : 0;
@@ -326,18 +341,31 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int v
   K2.shard_index = si;
   K2.shard_count = sc;
   const long long n_items = (long long)n_wg_local * V.n_yaw;
-  const long long max_grid = (long long)sm_count * SPR_MINB;
-  const long long want = (n_items + SPR_WARPS - 1) / SPR_WARPS;
-  const int grid = (int)(want < max_grid ? want : max_grid);
+  const bool cnt32 = V.nqp > 65535;  // a count can reach the number of query landmarks
+  const size_t warp_bytes = (size_t)(cnt32 ? SPR_WARP_WORDS(true) : SPR_WARP_WORDS(false)) * 4;
   cudaError_t e = cudaMemsetAsync(K.work_counter, 0, sizeof(unsigned long long), st);
   if (e != cudaSuccess) return e;
   if (n_launches) (*n_launches)++;
-  const bool cnt32 = V.nqp > 65535;  // a count can reach the number of query landmarks
-  if (variant == SPR_VARIANT_DIRECT)
-    return cnt32 ? launch_variant<SPR_VARIANT_DIRECT, true>(V, K2, n_wg_local, n_items, grid, st)
-                 : launch_variant<SPR_VARIANT_DIRECT, false>(V, K2, n_wg_local, n_items, grid, st);
-  return cnt32 ? launch_variant<SPR_VARIANT_QUEUED, true>(V, K2, n_wg_local, n_items, grid, st)
-               : launch_variant<SPR_VARIANT_QUEUED, false>(V, K2, n_wg_local, n_items, grid, st);
-}
 
-// ---------------------------------------------------------------------------------------------
+  // shared-memory-resident plane: one CTA per SM with as many warps as fit next to the tables
+  const uint32_t tab = spr_table_bytes(V.grid, K.dir);
+  int smem_warps = 0;
+  if (tables_mode == SPR_TABLES_AUTO && K.label >= 0 && (size_t)tab + 8 * warp_bytes <= SPR_SMEM_LIMIT) {
+    smem_warps = (int)((SPR_SMEM_LIMIT - tab) / warp_bytes);
+    if (smem_warps > 24) smem_warps = 24;
+  }
+  if (smem_warps >= 8) {
+    const long long want = (n_items + smem_warps - 1) / smem_warps;
+    const int grid = (int)(want < sm_count ? want : sm_count);
+    const size_t smem = (size_t)tab + (size_t)smem_warps * warp_bytes;
+    return cnt32 ? spr_launch_cfg<768, 1, true, true>(V, K2, n_wg_local, n_items, grid, smem_warps * 32, smem, tab, st)
+                 : spr_launch_cfg<768, 1, true, false>(V, K2, n_wg_local, n_items, grid, smem_warps * 32, smem, tab, st);
+  }
+  const int warps = 8;
+  const long long max_grid = (long long)sm_count * 4;
+  const long long want = (n_items + warps - 1) / warps;
+  const int grid = (int)(want < max_grid ? want : max_grid);
+  const size_t smem = (size_t)warps * warp_bytes;
+  return cnt32 ? spr_launch_cfg<256, 4, false, true>(V, K2, n_wg_local, n_items, grid, warps * 32, smem, 0u, st)
+               : spr_launch_cfg<256, 4, false, false>(V, K2, n_wg_local, n_items, grid, warps * 32, smem, 0u, st);
+}

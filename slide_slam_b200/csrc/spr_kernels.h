@@ -1,4 +1,4 @@
-// spr_kernels.h -- launch wrappers of the sm_100a kernels (spr_kernels.cu).
+// spr_kernels.h -- launch wrappers of the sm_100a kernels (spr_kernels.cu, spr_kernels_aux.cu).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -6,9 +6,16 @@
 
 #define SPR_WARP_CHUNKS 32  // chunks per work item (one warp); the sharding granule
 
+// One pass of the lattice search = one (label, direction) pair over a range of chunks.
 struct SprLaunch {
-  uint32_t chunk_begin, chunk_end;  // chunks scored by this launch (ring range or everything)
+  uint32_t chunk_begin, chunk_end;  // chunks of direction `dir` scored by this pass (multiple of 32 apart)
+  uint32_t n_chunks_total;          // size of the chunk list (indexes the global counters)
+  int32_t  label;                   // label bucket probed by this pass; -1: no queries at all
+  uint32_t dir;                     // bitmap direction of every chunk in [chunk_begin, chunk_end)
+  int32_t  first, last;             // first / last pass over these chunks: counters start at 0 / are reduced
   int32_t  shard_index, shard_count;
+  void    *gcnt;                    // device: per-hypothesis inlier counters carried between passes
+                                    //   [(yaw * n_chunks_total + chunk) * 32 + bit], u16 (u32 if nqp > 65535)
   unsigned long long *best_key;     // device: running max of spr_make_key
   unsigned long long *work_counter; // device: next work item (zeroed by the launcher)
   int32_t *counts_out;              // device, optional: [(ordinal - ord_begin) * n_yaw + iyaw]
@@ -18,15 +25,15 @@ struct SprLaunch {
                                     //                   [2] query groups probed, [3] query groups skipped
 };
 
-enum { SPR_VARIANT_DIRECT = 0, SPR_VARIANT_QUEUED = 1 };
+enum { SPR_TABLES_GLOBAL = 0, SPR_TABLES_AUTO = 1 };  // AUTO: shared-memory-resident plane when it fits
 
 // rotated query coordinates for every yaw: exact fp64 + fixed-point cell units in both layouts
 // + per-group bounding boxes (PR.cpp:246-258)
 cudaError_t spr_launch_rotate(const SprView &V, int32_t *qrotq_xy, int32_t *qrotq_yx, double *qrot, SprBox *gbox,
                               cudaStream_t st);
 
-// the lattice search: every hypothesis of the chunks gets its exact inlier count
-cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int variant, int sm_count,
+// one (label, direction) pass of the lattice search
+cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int tables_mode, int sm_count,
                                      cudaStream_t st, int *n_launches);
 
 // explicit hypothesis list (c, s, x, y), warp per hypothesis

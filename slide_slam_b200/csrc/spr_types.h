@@ -47,6 +47,9 @@ struct SprGrid {
   uint32_t label_stride; // plane_words[0] + plane_words[1]
 };
 
+// rank tables of one (label, direction) plane, in global or shared memory
+struct SprTables { const uint32_t *bits; const uint16_t *r16; const uint32_t *row_rank; uint32_t W; };
+
 struct SprBox { int32_t x0, x1, y0, y1; };  // fixed-point, [x0, x1) x [y0, y1); empty if x0 >= x1
 
 // one candidate of a marked cell: everything the exact test needs, in one 48-byte record.
@@ -77,8 +80,9 @@ struct SprView {
   int32_t         n_ref;
   const SprBox   *labelbox;   // [n_labels] fixed-point bounds of the label's marked cells
   const uint32_t *bitmap;     // [n_labels][plane dir0 | plane dir1]
-  const uint32_t *cellword[2];// per plane direction d: [n_labels][plane_words[d]][2] (bits, set bits before this word)
   const SprCand  *cand[2];    // per plane direction d: first candidate of each marked cell by rank, then chained extras
+  const uint16_t *rank16[2];  // per plane direction d: [n_labels][plane_words[d]] marked cells of the row before each word
+  const uint32_t *row_rank[2];// per plane direction d: [n_labels][R[d]] rank of each row's first marked cell
   SprGrid         grid;
   double          Tstar;      // sqrt(d2) < match_threshold_  <=>  d2 < Tstar   (PR.cpp:332-333)
   double          Sstar;      // (sum / 3) < thr_dim          <=>  sum < Sstar  (PR.cpp:329,338)

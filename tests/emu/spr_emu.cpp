@@ -22,7 +22,7 @@ extern "C" int spr_emu_match_maps(const slide_pr_params *p, const double *ref7, 
   std::string err;
   spr::Lattice L;
   const double yaw_half = p->inter_loop_closure ? p->match_yaw_half_range : p->match_yaw_half_range_intra;
-  int rc = spr::build_lattice(*p, half_x, half_y, yaw_half, trans_begin, trans_end, L, err);
+  int rc = spr::build_lattice(*p, half_x, half_y, yaw_half, trans_begin, trans_end, /*ring_major: exercised by the odd-start slices of the tests*/ (trans_begin & 1) != 0, L, err);
   auto fail = [&](int code) { if (errbuf && errcap > 0) { strncpy(errbuf, err.c_str(), errcap - 1); errbuf[errcap - 1] = 0; } return code; };
   if (rc != SLIDE_PR_OK) return fail(rc);
   *best_count = -10000; *best_index = -1; *hyps_scored = 0; *filter_hits = 0;
@@ -51,7 +51,7 @@ extern "C" int spr_emu_match_maps(const slide_pr_params *p, const double *ref7, 
   V.qxy = Q.qxy.data(); V.qdims = Q.qdims.data(); V.label_gseg = Q.label_gseg.data(); V.qlabel = Q.qlabel.data();
   V.n_labels = (int)R.labels.size(); V.n_ref = n_ref; V.labelbox = R.labelbox.data();
   V.bitmap = R.bitmap.data();
-  for (int d = 0; d < 2; d++) { V.cellword[d] = R.cellword[d].data(); V.cand[d] = R.cand[d].data(); }
+  for (int d = 0; d < 2; d++) { V.rank16[d] = R.rank16[d].data(); V.row_rank[d] = R.row_rank[d].data(); V.cand[d] = R.cand[d].data(); }
   V.grid = R.grid; V.Tstar = R.Tstar; V.Sstar = R.Sstar; V.thr_dim = p->match_threshold_dimension;
   V.ignore_dim = p->ignore_dimension;
   const SprGrid &G = V.grid;
@@ -80,7 +80,9 @@ extern "C" int spr_emu_match_maps(const slide_pr_params *p, const double *ref7, 
             const uint32_t H = spr_probe(plane, (uint32_t)G.W[d], (uint32_t)G.R[d] - 1u, (uint32_t)G.maxbit[d], G.F, asum, bsum, ch.valid);
             if (!H) continue;
             hits += __builtin_popcount(H);
-            uint32_t P = spr_verify_mask(V, (uint32_t)d, l, spr_cell_code((uint32_t)G.W[d], G.F, asum, bsum), H, qrot[2 * qi],
+            uint32_t row, bit;
+            spr_cell_of(G.F, asum, bsum, &row, &bit);
+            uint32_t P = spr_verify_mask(V, spr_global_tables(V, (uint32_t)d, l), (uint32_t)d, row, bit, H, qrot[2 * qi],
                                          qrot[2 * qi + 1], ch.across, V.lat + ch.along_off, V.qdims + 3 * (size_t)s);
             while (P) { cnt[SPR_FFS(P) - 1]++; P &= P - 1; }
           }
@@ -111,7 +113,7 @@ extern "C" long long spr_emu_lattice(const slide_pr_params *p, double half_x, do
   std::string err;
   spr::Lattice L;
   const double yaw_half = p->inter_loop_closure ? p->match_yaw_half_range : p->match_yaw_half_range_intra;
-  int rc = spr::build_lattice(*p, half_x, half_y, yaw_half, 0, -1, L, err);
+  int rc = spr::build_lattice(*p, half_x, half_y, yaw_half, 0, -1, false, L, err);
   *status = rc != SLIDE_PR_OK ? rc : L.status;
   if (rc != SLIDE_PR_OK || L.status != 0) return -1;
   *n_yaw = (int)L.yaw.size();
