@@ -63,7 +63,7 @@ struct slide_pr_handle {
   spr::RefIndex R;
   spr::QuerySet Q;
   // device side
-  DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_rank16, d_rank16b, d_rowrank, d_rowrankb, d_gcnt,
+  DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_rank16, d_rank16b, d_rowrank, d_rowrankb, d_gcnt, d_cellref, d_cellrefb, d_cellbase, d_cellbaseb, d_reftab, d_refbase,
       d_cand, d_cand1, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
   SprView V{};
   std::vector<int32_t> h_match;
@@ -156,7 +156,8 @@ void slide_pr_destroy(slide_pr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (DevBuf *b : {&h->d_lat, &h->d_chunks, &h->d_cs, &h->d_qxy, &h->d_qdims, &h->d_labelseg, &h->d_qlabel,
-                    &h->d_labelbox, &h->d_gbox, &h->d_bitmap, &h->d_rank16, &h->d_rank16b, &h->d_rowrank, &h->d_rowrankb, &h->d_gcnt, &h->d_cand, &h->d_cand1, &h->d_qrot,
+                    &h->d_labelbox, &h->d_gbox, &h->d_bitmap, &h->d_rank16, &h->d_rank16b, &h->d_rowrank, &h->d_rowrankb, &h->d_gcnt, &h->d_cellref, &h->d_cellrefb,
+                    &h->d_cellbase, &h->d_cellbaseb, &h->d_reftab, &h->d_refbase, &h->d_cand, &h->d_cand1, &h->d_qrot,
                     &h->d_qrotq, &h->d_qrotq_yx, &h->d_work, &h->d_ref7, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps, &h->d_tri, &h->d_tri_out})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -224,6 +225,12 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   if ((rc = upload(h, h->d_rank16b, h->R.rank16[1], st))) return rc;
   if ((rc = upload(h, h->d_rowrank, h->R.row_rank[0], st))) return rc;
   if ((rc = upload(h, h->d_rowrankb, h->R.row_rank[1], st))) return rc;
+  if ((rc = upload(h, h->d_cellref, h->R.cellref[0], st))) return rc;
+  if ((rc = upload(h, h->d_cellrefb, h->R.cellref[1], st))) return rc;
+  if ((rc = upload(h, h->d_cellbase, h->R.cell_base[0], st))) return rc;
+  if ((rc = upload(h, h->d_cellbaseb, h->R.cell_base[1], st))) return rc;
+  if ((rc = upload(h, h->d_reftab, h->R.reftab, st))) return rc;
+  if ((rc = upload(h, h->d_refbase, h->R.ref_base, st))) return rc;
   if ((rc = upload(h, h->d_cand, h->R.cand[0], st))) return rc;
   if ((rc = upload(h, h->d_cand1, h->R.cand[1], st))) return rc;
   if ((rc = upload_raw(h, h->d_ref7, ref7, (size_t)n_ref * 7 * sizeof(double), st))) return rc;
@@ -258,6 +265,12 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   V.rank16[1] = h->d_rank16b.as<uint16_t>();
   V.row_rank[0] = h->d_rowrank.as<uint32_t>();
   V.row_rank[1] = h->d_rowrankb.as<uint32_t>();
+  V.cellref[0] = h->d_cellref.as<uint16_t>();
+  V.cellref[1] = h->d_cellrefb.as<uint16_t>();
+  V.cell_base[0] = h->d_cellbase.as<uint32_t>();
+  V.cell_base[1] = h->d_cellbaseb.as<uint32_t>();
+  V.reftab = h->d_reftab.as<double>();
+  V.ref_base = h->d_refbase.as<uint32_t>();
   V.cand[0] = h->d_cand.as<SprCand>();
   V.cand[1] = h->d_cand1.as<SprCand>();
   V.grid = h->R.grid;
@@ -351,6 +364,8 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
       for (size_t i = 0; i < active.size(); i++) {
         K.chunk_begin = begin[d]; K.chunk_end = end[d]; K.dir = d; K.label = active[i];
         K.first = i == 0; K.last = i + 1 == active.size();
+        K.tab_cells = K.label >= 0 ? h->R.cell_base[d][K.label + 1] - h->R.cell_base[d][K.label] : 0u;
+        K.tab_refs = K.label >= 0 ? h->R.ref_base[K.label + 1] - h->R.ref_base[K.label] : 0u;
         SPR_CUDA(h, spr_launch_score_lattice(h->V, K, h->tables_mode, h->sm_count, st, &launches));
       }
     }

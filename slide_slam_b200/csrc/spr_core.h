@@ -129,6 +129,9 @@ SPR_HD SprTables spr_global_tables(const SprView &V, uint32_t d, int32_t l) {
   t.bits = V.bitmap + ((size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u));
   t.r16 = V.rank16[d] + (size_t)l * G.plane_words[d];
   t.row_rank = V.row_rank[d] + (size_t)l * (size_t)G.R[d];
+  t.cell_base = V.cell_base[d][l];
+  t.cellref = V.cellref[d] + t.cell_base;
+  t.reftab = V.reftab + 5 * (size_t)V.ref_base[l];
   t.W = (uint32_t)G.W[d];
   return t;
 }
@@ -140,18 +143,24 @@ SPR_HD bool spr_group_visible(const SprBox &g, const SprBox &lb, int32_t X0, int
   return (g.x1 > lb.x0 - X1) && (g.x0 < lb.x1 - X0) && (g.y1 > lb.y0 - Y1) && (g.y0 < lb.y1 - Y0);
 }
 
-// Exact test of one marked cell, given its rank in plane d: walks the cell's candidates in
-// ascending reference order with the reference's predicate (PR.cpp:299-355).
-SPR_HD bool spr_verify_rank(const SprView &V, uint32_t d, uint32_t rank, double rx, double ry, double tx,
-                            double ty, const double *qd, int32_t *first_ref) {
-  uint32_t k = rank;
+// Exact test of one marked cell, given its label-relative rank in the plane described by T
+// (direction d): the reference's predicate (PR.cpp:299-355) on the cell's candidate landmarks in
+// ascending reference order.  The common single-candidate cell is a 16-bit slot into the label's
+// compact landmark table; cells with several candidates walk the chained records of cand[d].
+SPR_HD bool spr_verify_rank(const SprView &V, const SprTables &T, uint32_t d, uint32_t rank, double rx, double ry,
+                            double tx, double ty, const double *qd) {
+  const uint32_t slot = T.cellref[rank];
+  if (slot != SPR_CELL_MULTI) {
+    const double *r = T.reftab + 5 * (size_t)slot;
+    return spr_distance_match(rx, ry, tx, ty, r[0], r[1], V.Tstar) &&
+           (V.ignore_dim || spr_dimension_match(r[2], r[3], r[4], qd, V.thr_dim, V.Sstar));
+  }
+  uint32_t k = T.cell_base + rank;
   for (;;) {
     const SprCand &c = V.cand[d][k];
     if (spr_distance_match(rx, ry, tx, ty, c.x, c.y, V.Tstar) &&
-        (V.ignore_dim || spr_dimension_match(c.d1, c.d2, c.d3, qd, V.thr_dim, V.Sstar))) {
-      *first_ref = (int32_t)c.ref;
+        (V.ignore_dim || spr_dimension_match(c.d1, c.d2, c.d3, qd, V.thr_dim, V.Sstar)))
       return true;
-    }
     if (c.next == 0u) return false;
     k = c.next;
   }
@@ -159,10 +168,10 @@ SPR_HD bool spr_verify_rank(const SprView &V, uint32_t d, uint32_t rank, double 
 
 // Exact verification of one occupied cell (row, bit) of the plane described by T (direction d).
 SPR_HD bool spr_verify_cell(const SprView &V, const SprTables &T, uint32_t d, uint32_t row, uint32_t bit, double rx,
-                            double ry, double tx, double ty, const double *qd, int32_t *first_ref) {
+                            double ry, double tx, double ty, const double *qd) {
   const uint32_t wi = row * T.W + (bit >> 5);
   const uint32_t rank = T.row_rank[row] + T.r16[wi] + (uint32_t)SPR_POPC(T.bits[wi] & ((1u << (bit & 31u)) - 1u));
-  return spr_verify_rank(V, d, rank, rx, ry, tx, ty, qd, first_ref);
+  return spr_verify_rank(V, T, d, rank, rx, ry, tx, ty, qd);
 }
 
 // Exact verification of all filter hits H of ONE query landmark against the 32 consecutive cells
@@ -185,8 +194,7 @@ SPR_HD uint32_t spr_verify_mask(const SprView &V, const SprTables &T, uint32_t d
     const uint32_t rank = pos < 32u ? before0 + (uint32_t)SPR_POPC(w0 & ((1u << pos) - 1u))
                                     : before1 + (uint32_t)SPR_POPC(w1 & ((1u << (pos - 32u)) - 1u));
     const double t = along[b];
-    int32_t first;
-    if (spr_verify_rank(V, d, rank, rx, ry, d ? t : across, d ? across : t, qd, &first)) P |= 1u << b;
+    if (spr_verify_rank(V, T, d, rank, rx, ry, d ? t : across, d ? across : t, qd)) P |= 1u << b;
   }
   return P;
 }

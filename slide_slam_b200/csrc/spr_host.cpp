@@ -343,6 +343,29 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
     }
   }
   if (entries.size() >= (1ull << 32)) { err = "candidate lists exceed 2^32 entries"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  // compact per-label landmark table [x, y, d1, d2, d3] (label-major, ascending index inside a
+  // label) and each landmark's slot inside its label: what a cell's 16-bit reference points at
+  std::vector<uint32_t> slot_of_ref((size_t)std::max(n_ref, 1), 0u);
+  R.ref_base.assign((size_t)n_labels + 1, 0u);
+  {
+    std::vector<uint32_t> per((size_t)std::max(n_labels, 1), 0u);
+    std::vector<int> lab_of((size_t)std::max(n_ref, 1), -1);
+    for (int i = 0; i < n_ref; i++) {
+      const double lv = ref7[7 * (size_t)i];
+      if (!(lv == lv)) continue;
+      const int l = (int)(std::lower_bound(R.labels.begin(), R.labels.end(), lv + 0.0) - R.labels.begin());
+      lab_of[i] = l;
+      slot_of_ref[i] = per[l]++;
+    }
+    for (int l = 0; l < n_labels; l++) R.ref_base[l + 1] = R.ref_base[l] + per[l];
+    R.reftab.assign(5 * (size_t)std::max<uint32_t>(R.ref_base[n_labels], 1), 0.0);
+    for (int i = 0; i < n_ref; i++) {
+      if (lab_of[i] < 0) continue;
+      const double *r = ref7 + 7 * (size_t)i;
+      double *t = R.reftab.data() + 5 * (size_t)(R.ref_base[lab_of[i]] + slot_of_ref[i]);
+      t[0] = r[1]; t[1] = r[2]; t[2] = r[4]; t[3] = r[5]; t[4] = r[6];
+    }
+  }
   for (int d = 0; d < 2; d++) {
     std::sort(entries.begin(), entries.end(), [d](const Entry &a, const Entry &b) {
       return a.key[d] != b.key[d] ? a.key[d] < b.key[d] : a.ref < b.ref;
@@ -354,21 +377,33 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
       if (e == 0 || entries[e].key[d] != entries[e - 1].key[d]) n_cells++;
     std::vector<SprCand> &cand = R.cand[d];
     cand.resize(entries.size());
-    size_t rank = 0, extra = n_cells, prev = 0;
+    // cellref[d][rank]: slot (inside the label's landmark table) of the cell's only candidate, or
+    // SPR_CELL_MULTI when the cell has several candidates (then cand[d] is walked)
+    std::vector<uint16_t> &cellref = R.cellref[d];
+    cellref.assign(n_cells + 8, 0);
+    R.cell_base[d].assign((size_t)n_labels + 1, 0u);
+    size_t rank = 0, extra = n_cells, prev = 0, cell = 0;
     for (size_t e = 0; e < entries.size(); e++) {
       const double *r = ref7 + 7 * (size_t)entries[e].ref;
       const SprCand c{r[1], r[2], r[4], r[5], r[6], entries[e].ref, 0u};
       if (e == 0 || entries[e].key[d] != entries[e - 1].key[d]) {
-        prev = rank++;
+        cell = prev = rank++;
+        const uint32_t slot = slot_of_ref[entries[e].ref];
+        cellref[cell] = slot < SPR_CELL_MULTI ? (uint16_t)slot : (uint16_t)SPR_CELL_MULTI;
+        const size_t l = (size_t)(entries[e].key[d] >> 44);
+        R.cell_base[d][l + 1] = (uint32_t)rank;  // running end of label l's cells
       } else {
         cand[prev].next = (uint32_t)extra;
         prev = extra++;
+        cellref[cell] = (uint16_t)SPR_CELL_MULTI;
       }
       cand[prev] = c;
     }
+    for (int l = 0; l < n_labels; l++)  // labels without cells inherit the previous end
+      if (R.cell_base[d][l + 1] < R.cell_base[d][l]) R.cell_base[d][l + 1] = R.cell_base[d][l];
     if (cand.empty()) cand.assign(1, SprCand{0, 0, 0, 0, 0, 0u, 0u});
     // rank tables of direction d, label-major == rank order of the marked cells:
-    //   row_rank[l][row]  = rank of the first marked cell of the row (absolute, index into cand[d])
+    //   row_rank[l][row]  = rank of the first marked cell of the row, relative to the label's first cell
     //   rank16[l][word]   = marked cells of the same row before the word
     R.rank16[d].assign((size_t)G.plane_words[d] * (size_t)std::max(n_labels, 1) + 8, 0);
     R.row_rank[d].assign((size_t)G.R[d] * (size_t)std::max(n_labels, 1) + 1, 0u);
@@ -377,8 +412,10 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
       const uint32_t *pl = R.bitmap.data() + (size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u);
       uint16_t *r16 = R.rank16[d].data() + (size_t)l * G.plane_words[d];
       uint32_t *rr = R.row_rank[d].data() + (size_t)l * G.R[d];
+      const uint32_t label_start = running;
+      if (label_start != R.cell_base[d][l]) { err = "internal: label cell base mismatch"; return SLIDE_PR_ERR_INTERNAL; }
       for (int row = 0; row < G.R[d]; row++) {
-        rr[row] = running;
+        rr[row] = running - label_start;
         uint32_t in_row = 0;
         for (int w = 0; w < G.W[d]; w++) {
           if (in_row > 0xffffu) { err = "more than 65535 marked cells in one bitmap row"; return SLIDE_PR_ERR_UNSUPPORTED; }

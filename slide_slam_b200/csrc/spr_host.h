@@ -48,6 +48,10 @@ struct RefIndex {
   std::vector<SprCand> cand[2];      // per plane direction d: [n_cells] first candidate per cell rank, then chained extras
   std::vector<uint16_t> rank16[2];   // per plane direction d: [n_labels][plane_words[d]] marked cells of the row before the word
   std::vector<uint32_t> row_rank[2]; // per plane direction d: [n_labels][R[d]] rank (index into cand[d]) of the row's first marked cell
+  std::vector<uint16_t> cellref[2];  // per plane direction d: [n_cells] slot of the cell's only candidate in its label's table, or SPR_CELL_MULTI
+  std::vector<uint32_t> cell_base[2]; // per plane direction d: [n_labels + 1] rank of each label's first cell
+  std::vector<double> reftab;        // [n_ref kept][5] x, y, d1, d2, d3, label-major
+  std::vector<uint32_t> ref_base;    // [n_labels + 1] first row of each label in reftab
   std::vector<SprBox> labelbox;     // [n_labels] fixed-point bounds of the label's marked cells
   double Tstar = 0, Sstar = 0;
   int n_ref = 0;

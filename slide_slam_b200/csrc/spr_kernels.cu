@@ -57,6 +57,20 @@ template <bool CNT32> __device__ __forceinline__ uint32_t spr_cnt_get(const uint
   return (cnt[lane * 17 + (b >> 1)] >> ((b & 1) << 4)) & 0xffffu;
 }
 
+// word offsets of the staged tables inside the CTA's shared memory (every part 16-byte aligned)
+struct SprTabLayout { uint32_t reftab_w, bits_w, r16_w, rr_w, cellref_w, total_w; };
+__host__ __device__ static inline SprTabLayout spr_tab_layout(uint32_t PW, uint32_t R, uint32_t cells, uint32_t refs) {
+  SprTabLayout o;
+  uint32_t w = 0;
+  o.reftab_w = w;  w += (10u * refs + 3u) & ~3u;
+  o.bits_w = w;    w += (PW + 3u) & ~3u;
+  o.r16_w = w;     w += (((PW + 1u) >> 1) + 3u) & ~3u;
+  o.rr_w = w;      w += (R + 3u) & ~3u;
+  o.cellref_w = w; w += (((cells + 1u) >> 1) + 3u) & ~3u;
+  o.total_w = w;
+  return o;
+}
+
 // ---------------------------------------------------------------------------------------------
 // rotate: one thread per (yaw, query group)
 // ---------------------------------------------------------------------------------------------
@@ -128,25 +142,23 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
   const int l = K.label;
   const uint32_t W = (uint32_t)G.W[d], Rm1 = (uint32_t)G.R[d] - 1u, maxbit = (uint32_t)G.maxbit[d];
 
-  // rank tables of this pass' plane: staged into shared memory once per CTA, or read in place
-  SprTables T;
-  T.W = W;
+  // tables of this pass' plane (bits, ranks, per-cell landmark slots, the label's landmark
+  // table): staged into shared memory once per CTA, or read in place
+  SprTables T = spr_global_tables(V, d, l < 0 ? 0 : l);
   if (SMEM_TAB) {
-    const SprTables GT = spr_global_tables(V, d, l < 0 ? 0 : l);
-    const uint32_t PW = G.plane_words[d];
-    uint32_t *s_bits = smem;
-    uint32_t *s_r16 = s_bits + ((PW + 3u) & ~3u);
-    uint32_t *s_rr = s_r16 + ((((PW + 1u) >> 1) + 3u) & ~3u);
-    for (uint32_t i = threadIdx.x; i < PW; i += blockDim.x) s_bits[i] = GT.bits[i];
-    uint16_t *s_r16h = reinterpret_cast<uint16_t *>(s_r16);
-    for (uint32_t i = threadIdx.x; i < PW; i += blockDim.x) s_r16h[i] = GT.r16[i];
+    const SprTables GT = T;
+    const SprTabLayout Lo = spr_tab_layout(G.plane_words[d], (uint32_t)G.R[d], K.tab_cells, K.tab_refs);
+    double *s_ref = reinterpret_cast<double *>(smem + Lo.reftab_w);
+    uint32_t *s_bits = smem + Lo.bits_w;
+    uint16_t *s_r16 = reinterpret_cast<uint16_t *>(smem + Lo.r16_w);
+    uint32_t *s_rr = smem + Lo.rr_w;
+    uint16_t *s_cell = reinterpret_cast<uint16_t *>(smem + Lo.cellref_w);
+    for (uint32_t i = threadIdx.x; i < 5u * K.tab_refs; i += blockDim.x) s_ref[i] = GT.reftab[i];
+    for (uint32_t i = threadIdx.x; i < G.plane_words[d]; i += blockDim.x) { s_bits[i] = GT.bits[i]; s_r16[i] = GT.r16[i]; }
     for (uint32_t i = threadIdx.x; i <= Rm1; i += blockDim.x) s_rr[i] = GT.row_rank[i];
+    for (uint32_t i = threadIdx.x; i < K.tab_cells; i += blockDim.x) s_cell[i] = GT.cellref[i];
     __syncthreads();
-    T.bits = s_bits;
-    T.r16 = reinterpret_cast<const uint16_t *>(s_r16);
-    T.row_rank = s_rr;
-  } else {
-    T = spr_global_tables(V, d, l < 0 ? 0 : l);
+    T.bits = s_bits; T.r16 = s_r16; T.row_rank = s_rr; T.cellref = s_cell; T.reftab = s_ref;
   }
   WarpState ws;
   ws.cnt = smem + (tab_bytes >> 2) + warp * SPR_WARP_WORDS(CNT32);
@@ -303,13 +315,6 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
   }
 }
 
-// shared-memory bytes of the staged tables of direction d (bits, rank16, row_rank; 16-byte aligned parts)
-static uint32_t spr_table_bytes(const SprGrid &G, uint32_t d) {
-  const uint32_t PW = G.plane_words[d];
-  const uint32_t words = ((PW + 3u) & ~3u) + ((((PW + 1u) >> 1) + 3u) & ~3u) + (((uint32_t)G.R[d] + 3u) & ~3u);
-  return words * 4u;
-}
-
 template <int BLOCK, int MINB, bool SMEM_TAB, bool CNT32>
 static cudaError_t spr_launch_cfg(const SprView &V, const SprLaunch &K, int n_wg_local, long long n_items, int grid,
                                   int threads, size_t smem, uint32_t tab_bytes, cudaStream_t st) {
@@ -348,9 +353,9 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int t
   if (n_launches) (*n_launches)++;
 
   // shared-memory-resident plane: one CTA per SM with as many warps as fit next to the tables
-  const uint32_t tab = spr_table_bytes(V.grid, K.dir);
+  const uint32_t tab = spr_tab_layout(V.grid.plane_words[K.dir], (uint32_t)V.grid.R[K.dir], K.tab_cells, K.tab_refs).total_w * 4u;
   int smem_warps = 0;
-  if (tables_mode == SPR_TABLES_AUTO && K.label >= 0 && (size_t)tab + 8 * warp_bytes <= SPR_SMEM_LIMIT) {
+  if (tables_mode == SPR_TABLES_AUTO && K.label >= 0 && K.tab_refs < SPR_CELL_MULTI && (size_t)tab + 8 * warp_bytes <= SPR_SMEM_LIMIT) {
     smem_warps = (int)((SPR_SMEM_LIMIT - tab) / warp_bytes);
     if (smem_warps > 24) smem_warps = 24;
   }

@@ -29,9 +29,8 @@ spr_score_list_kernel(SprView V, const double *__restrict__ hyps4, long long n, 
       spr_rotate(c, s, V.qxy[2 * (size_t)js], V.qxy[2 * (size_t)js + 1], &rx, &ry);
       const double xt = SPR_DADD(rx, tx), yt = SPR_DADD(ry, ty);
       uint32_t row, bit;
-      int32_t first;
       if (spr_point_cell(V, l, xt, yt, &row, &bit) &&
-          spr_verify_cell(V, spr_global_tables(V, 0u, l), 0u, row, bit, rx, ry, tx, ty, V.qdims + 3 * (size_t)js, &first))
+          spr_verify_cell(V, spr_global_tables(V, 0u, l), 0u, row, bit, rx, ry, tx, ty, V.qdims + 3 * (size_t)js))
         cnt++;
     }
 #pragma unroll

@@ -48,7 +48,16 @@ struct SprGrid {
 };
 
 // rank tables of one (label, direction) plane, in global or shared memory
-struct SprTables { const uint32_t *bits; const uint16_t *r16; const uint32_t *row_rank; uint32_t W; };
+#define SPR_CELL_MULTI 0xffffu  // cellref value of a cell with more than one candidate landmark
+struct SprTables {
+  const uint32_t *bits;      // the plane
+  const uint16_t *r16;       // marked cells of the row before each word
+  const uint32_t *row_rank;  // rank of each row's first marked cell, relative to the label's first cell
+  const uint16_t *cellref;   // [cells of the label] slot of the cell's only candidate, or SPR_CELL_MULTI
+  const double   *reftab;    // [landmarks of the label][5] x, y, d1, d2, d3
+  uint32_t W;                // words per row
+  uint32_t cell_base;        // absolute rank (index into cand[d]) of the label's first cell
+};
 
 struct SprBox { int32_t x0, x1, y0, y1; };  // fixed-point, [x0, x1) x [y0, y1); empty if x0 >= x1
 
@@ -82,7 +91,11 @@ struct SprView {
   const uint32_t *bitmap;     // [n_labels][plane dir0 | plane dir1]
   const SprCand  *cand[2];    // per plane direction d: first candidate of each marked cell by rank, then chained extras
   const uint16_t *rank16[2];  // per plane direction d: [n_labels][plane_words[d]] marked cells of the row before each word
-  const uint32_t *row_rank[2];// per plane direction d: [n_labels][R[d]] rank of each row's first marked cell
+  const uint32_t *row_rank[2];// per plane direction d: [n_labels][R[d]] rank of each row's first marked cell (label-relative)
+  const uint16_t *cellref[2]; // per plane direction d: [n_cells] candidate slot per marked cell (rank order)
+  const uint32_t *cell_base[2];// per plane direction d: [n_labels + 1] rank of each label's first cell
+  const double   *reftab;     // [landmarks][5] x, y, d1, d2, d3, label-major
+  const uint32_t *ref_base;   // [n_labels + 1] first row of each label in reftab
   SprGrid         grid;
   double          Tstar;      // sqrt(d2) < match_threshold_  <=>  d2 < Tstar   (PR.cpp:332-333)
   double          Sstar;      // (sum / 3) < thr_dim          <=>  sum < Sstar  (PR.cpp:329,338)

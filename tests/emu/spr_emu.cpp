@@ -51,7 +51,9 @@ extern "C" int spr_emu_match_maps(const slide_pr_params *p, const double *ref7, 
   V.qxy = Q.qxy.data(); V.qdims = Q.qdims.data(); V.label_gseg = Q.label_gseg.data(); V.qlabel = Q.qlabel.data();
   V.n_labels = (int)R.labels.size(); V.n_ref = n_ref; V.labelbox = R.labelbox.data();
   V.bitmap = R.bitmap.data();
-  for (int d = 0; d < 2; d++) { V.rank16[d] = R.rank16[d].data(); V.row_rank[d] = R.row_rank[d].data(); V.cand[d] = R.cand[d].data(); }
+  for (int d = 0; d < 2; d++) { V.rank16[d] = R.rank16[d].data(); V.row_rank[d] = R.row_rank[d].data(); V.cand[d] = R.cand[d].data();
+    V.cellref[d] = R.cellref[d].data(); V.cell_base[d] = R.cell_base[d].data(); }
+  V.reftab = R.reftab.data(); V.ref_base = R.ref_base.data();
   V.grid = R.grid; V.Tstar = R.Tstar; V.Sstar = R.Sstar; V.thr_dim = p->match_threshold_dimension;
   V.ignore_dim = p->ignore_dimension;
   const SprGrid &G = V.grid;
