@@ -213,44 +213,41 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
 #pragma unroll 1
         for (int hq = 0; hq < SPR_QGROUP / SPR_QHALF; hq++) {
           uint32_t H[SPR_QHALF];
+          int4 v[SPR_QHALF / 2];  // two queries each: (across, along) x 2
+#pragma unroll
+          for (int u = 0; u < SPR_QHALF / 2; u++) v[u] = __ldg(qgp + hq * (SPR_QHALF / 2) + u);
 #pragma unroll
           for (int u = 0; u < SPR_QHALF / 2; u++) {
-            const int4 v = __ldg(qgp + hq * (SPR_QHALF / 2) + u);  // two queries: (across, along) x 2
-            H[2 * u] = spr_probe(T.bits, W, Rm1, maxbit, F, aqb + v.x, bqb + v.y, SPR_FULL);
-            H[2 * u + 1] = spr_probe(T.bits, W, Rm1, maxbit, F, aqb + v.z, bqb + v.w, SPR_FULL);
+            H[2 * u] = spr_probe(T.bits, W, Rm1, maxbit, F, aqb + v[u].x, bqb + v[u].y, SPR_FULL);
+            H[2 * u + 1] = spr_probe(T.bits, W, Rm1, maxbit, F, aqb + v[u].z, bqb + v[u].w, SPR_FULL);
           }
           uint32_t any = 0u;
 #pragma unroll
           for (int u = 0; u < SPR_QHALF; u++) any |= H[u];
           any &= valid;
           if (__ballot_sync(SPR_FULL, any != 0u) == 0u) continue;
-          // one record per (lane, query) with hits
-          int n = 0;
-#pragma unroll
-          for (int u = 0; u < SPR_QHALF; u++) { H[u] &= valid; n += H[u] != 0u; }
           if (STATS) {
 #pragma unroll
-            for (int u = 0; u < SPR_QHALF; u++) n_hits += (unsigned long long)__popc(H[u]);
+            for (int u = 0; u < SPR_QHALF; u++) n_hits += (unsigned long long)__popc(H[u] & valid);
           }
+          // one record per (lane, query) with hits; the queue is unordered, so records are laid
+          // out query-major and a lane's slot comes from one ballot per query (no shuffle scan)
           const int js0 = g * SPR_QGROUP + hq * SPR_QHALF;
-          // warp inclusive prefix sum of the per-lane record counts
-          int incl = n;
-#pragma unroll
-          for (int dlt = 1; dlt < 32; dlt <<= 1) {
-            const int t = __shfl_up_sync(SPR_FULL, incl, dlt);
-            if (lane >= dlt) incl += t;
-          }
-          const int total = __shfl_sync(SPR_FULL, incl, 31);
-          int pos = ws.qcount + incl - n;
+          const uint32_t lt = (1u << lane) - 1u;
+          int base = ws.qcount;
 #pragma unroll
           for (int u = 0; u < SPR_QHALF; u++) {
-            if (H[u] == 0u) continue;
-            const int2 q = __ldg(qa2 + js0 + u);  // L1 hit: loaded a moment ago by the probe
-            uint32_t row, bit;
-            spr_cell_of(F, aqb + q.x, bqb + q.y, &row, &bit);
-            ws.queue[pos++] = make_uint4(((uint32_t)(js0 + u) << 5) | (uint32_t)lane, row, bit, H[u]);
+            const uint32_t h = H[u] & valid;
+            const uint32_t m = __ballot_sync(SPR_FULL, h != 0u);
+            if (h != 0u) {
+              const int qa_ = (u & 1) ? v[u >> 1].z : v[u >> 1].x, qb_ = (u & 1) ? v[u >> 1].w : v[u >> 1].y;
+              uint32_t row, bit;
+              spr_cell_of(F, aqb + qa_, bqb + qb_, &row, &bit);
+              ws.queue[base + __popc(m & lt)] = make_uint4(((uint32_t)(js0 + u) << 5) | (uint32_t)lane, row, bit, h);
+            }
+            base += __popc(m);
           }
-          ws.qcount += total;
+          ws.qcount = base;
           __syncwarp();
           while (ws.qcount >= 32) spr_drain32<CNT32>(V, T, ws, d, a, lane, along_off, across, n_inl);
         }
