@@ -300,6 +300,7 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": e2e_hyps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(info.match.h2d_bytes),
                     "d2h_bytes_per_step": int(info.match.d2h_bytes), "ms_per_step": e2e_s / max(args.steps, 1) * 1e3,
+                    "host_index_build_ms": float(info2.match.prepare_ms), "kernel_ms": float(info2.match.kernel_ms),
                     "api": "PlaceRecognition.findTransformation -> slide_pr_find_transformation (host buffers)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,

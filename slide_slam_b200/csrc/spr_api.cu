@@ -241,7 +241,7 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   SPR_CUDA(h, h->d_qrotq.ensure(nrot * 2 * sizeof(int32_t)));
   SPR_CUDA(h, h->d_qrotq_yx.ensure(nrot * 2 * sizeof(int32_t)));
   SPR_CUDA(h, h->d_gbox.ensure(ngb * sizeof(SprBox)));
-  SPR_CUDA(h, h->d_work.ensure(sizeof(unsigned long long)));
+  SPR_CUDA(h, h->d_work.ensure(4096 * sizeof(unsigned long long)));
   SPR_CUDA(h, h->d_best.ensure(sizeof(unsigned long long)));
   SPR_CUDA(h, h->d_stats.ensure(4 * sizeof(unsigned long long)));
   SPR_CUDA(h, h->d_match.ensure(std::max<size_t>(n_qry, 1) * sizeof(int32_t)));
@@ -278,9 +278,8 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   V.Sstar = h->R.Sstar;
   V.thr_dim = h->p.match_threshold_dimension;
   V.ignore_dim = h->p.ignore_dimension;
-  // the uploads read pageable host vectors that stay alive in the handle; make them complete
-  // before the caller may free ref7 / qry7
-  SPR_CUDA(h, cudaStreamSynchronize(st));
+  // no synchronisation here: pageable cudaMemcpyAsync has staged the caller's ref7 / qry7 when it
+  // returns, and the host index vectors stay alive in the handle until the next prepare
   h->prepared = true;
   h->prepare_ms = now_ms() - t0;
   return SLIDE_PR_OK;
@@ -337,7 +336,8 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   K.counts_cap = n_counts;
   K.ord_begin = (unsigned long long)tb;
   K.stats = o.collect_stats ? h->d_stats.as<unsigned long long>() : nullptr;
-  K.work_counter = h->d_work.as<unsigned long long>();
+  K.work_counter = h->d_work.as<unsigned long long>();  // one work-item counter per pass
+  size_t passes_left = 0;
 
   int launches = 0;
   SPR_CUDA(h, cudaEventRecord(h->ev0, st));
@@ -366,7 +366,14 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
         K.first = i == 0; K.last = i + 1 == active.size();
         K.tab_cells = K.label >= 0 ? h->R.cell_base[d][K.label + 1] - h->R.cell_base[d][K.label] : 0u;
         K.tab_refs = K.label >= 0 ? h->R.ref_base[K.label + 1] - h->R.ref_base[K.label] : 0u;
+        if (passes_left == 0) {  // (re)arm a batch of counters with a single memset
+          passes_left = 4096;
+          K.work_counter = h->d_work.as<unsigned long long>();
+          SPR_CUDA(h, cudaMemsetAsync(h->d_work.p, 0, 4096 * sizeof(unsigned long long), st));
+        }
         SPR_CUDA(h, spr_launch_score_lattice(h->V, K, h->tables_mode, h->sm_count, st, &launches));
+        K.work_counter++;
+        passes_left--;
       }
     }
     return SLIDE_PR_OK;

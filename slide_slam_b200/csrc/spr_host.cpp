@@ -94,7 +94,10 @@ struct RectEmitter {
 
 int build_lattice(const slide_pr_params &p, double half_x, double half_y, double yaw_half,
                   int64_t trans_begin, int64_t trans_end, bool ring_major, Lattice &L, std::string &err) {
-  L = Lattice();
+  // reset, keeping the vectors' capacity across calls
+  L.status = 0; L.rings = 0; L.ox = L.oy = 0; L.n_translations = 0; L.ring_major = false;
+  L.yaw.clear(); L.cs.clear(); L.lat.clear(); L.ring.clear(); L.chunks.clear();
+  L.dir_begin[0] = L.dir_begin[1] = L.dir_end[0] = L.dir_end[1] = 0;
   const double step = p.match_xy_step_size;
   if (!(step > 0) || !std::isfinite(step)) { err = "match_xy_step_size must be positive and finite"; return SLIDE_PR_ERR_INVALID; }
   if (!std::isfinite(half_x) || !std::isfinite(half_y)) { err = "non-finite search half range"; return SLIDE_PR_ERR_NONFINITE; }
@@ -191,7 +194,8 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
   // Group the chunks by direction (every warp = 32 consecutive chunks probes ONE bitmap plane),
   // padding each group to a whole number of warps with empty chunks.  ring_major keeps the
   // chunks of a ring together (needed by the anytime budget, PR.cpp:181-191).
-  std::vector<SprChunk> out;
+  std::vector<SprChunk> &out = L.scratch;
+  out.clear();
   out.reserve(L.chunks.size() + 64 * (ring_major ? L.ring.size() + 1 : 2));
   auto pad32 = [&out](uint32_t d) {
     SprChunk z{};
@@ -253,7 +257,7 @@ bool translation_of(const Lattice &L, uint64_t ordinal, double *x, double *y, in
 // ------------------------------------------------------------------------------------------
 int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, double reach,
                     RefIndex &R, std::string &err) {
-  R = RefIndex();
+  R.labels.clear();  // the vectors are reused across calls (no re-allocation / page faults)
   R.n_ref = n_ref;
   const double c = p.match_xy_step_size, thr = p.match_threshold;
   R.Tstar = sqrt_threshold(thr);
@@ -310,46 +314,13 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
   struct CellBounds { int x0, x1, y0, y1; };
   std::vector<CellBounds> cb((size_t)std::max(n_labels, 1), CellBounds{INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN});
 
-  // mark every cell whose (slightly dilated) box a landmark's match disc touches
-  struct Entry { uint64_t key[2]; uint32_t ref; };  // key[d]: rank order of plane d = (label, across, along)
-  std::vector<Entry> entries;
-  if (matchable) {
-    const double eps_cells = 3.0 / std::ldexp(1.0, F) + 1e-9 / c;  // fixed-point truncation + lattice drift
-    const double rc = rad_m / c + eps_cells;
-    const double rc2 = rc * rc * (1.0 + 1e-12);
-    for (int i = 0; i < n_ref; i++) {
-      const double *r = ref7 + 7 * (size_t)i;
-      if (!(r[0] == r[0])) continue;
-      const int l = (int)(std::lower_bound(R.labels.begin(), R.labels.end(), r[0] + 0.0) - R.labels.begin());
-      const double ux = (r[1] - G.g0x) / c, uy = (r[2] - G.g0y) / c;
-      const int x0 = (int)std::floor(ux - rc), x1 = (int)std::floor(ux + rc);
-      const int y0 = (int)std::floor(uy - rc), y1 = (int)std::floor(uy + rc);
-      for (int nx = x0; nx <= x1; nx++) {
-        const double dx = std::max({(double)nx - ux, 0.0, ux - (double)(nx + 1)});
-        for (int ny = y0; ny <= y1; ny++) {
-          const double dy = std::max({(double)ny - uy, 0.0, uy - (double)(ny + 1)});
-          if (dx * dx + dy * dy > rc2) continue;
-          if (nx < 0 || nx >= G.GX || ny < 0 || ny >= G.GY) { err = "internal: match disc leaves the grid"; return SLIDE_PR_ERR_INTERNAL; }
-          uint32_t *pl0 = R.bitmap.data() + (size_t)l * G.label_stride;
-          uint32_t *pl1 = pl0 + G.plane_words[0];
-          pl0[(size_t)(nx + 1) * G.W[0] + ((uint32_t)(ny + 32) >> 5)] |= 1u << ((ny + 32) & 31);
-          pl1[(size_t)(ny + 1) * G.W[1] + ((uint32_t)(nx + 32) >> 5)] |= 1u << ((nx + 32) & 31);
-          cb[l].x0 = std::min(cb[l].x0, nx); cb[l].x1 = std::max(cb[l].x1, nx);
-          cb[l].y0 = std::min(cb[l].y0, ny); cb[l].y1 = std::max(cb[l].y1, ny);
-          entries.push_back({{((uint64_t)l << 44) | ((uint64_t)nx << 22) | (uint64_t)ny,
-                              ((uint64_t)l << 44) | ((uint64_t)ny << 22) | (uint64_t)nx}, (uint32_t)i});
-        }
-      }
-    }
-  }
-  if (entries.size() >= (1ull << 32)) { err = "candidate lists exceed 2^32 entries"; return SLIDE_PR_ERR_UNSUPPORTED; }
-  // compact per-label landmark table [x, y, d1, d2, d3] (label-major, ascending index inside a
-  // label) and each landmark's slot inside its label: what a cell's 16-bit reference points at
+  // label bucket and slot (position inside its label, ascending index) of every landmark; the
+  // compact per-label landmark table [x, y, d1, d2, d3] a cell's 16-bit reference points into
+  std::vector<int32_t> lab_of((size_t)std::max(n_ref, 1), -1);
   std::vector<uint32_t> slot_of_ref((size_t)std::max(n_ref, 1), 0u);
   R.ref_base.assign((size_t)n_labels + 1, 0u);
   {
     std::vector<uint32_t> per((size_t)std::max(n_labels, 1), 0u);
-    std::vector<int> lab_of((size_t)std::max(n_ref, 1), -1);
     for (int i = 0; i < n_ref; i++) {
       const double lv = ref7[7 * (size_t)i];
       if (!(lv == lv)) continue;
@@ -366,66 +337,106 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
       t[0] = r[1]; t[1] = r[2]; t[2] = r[4]; t[3] = r[5]; t[4] = r[6];
     }
   }
-  for (int d = 0; d < 2; d++) {
-    std::sort(entries.begin(), entries.end(), [d](const Entry &a, const Entry &b) {
-      return a.key[d] != b.key[d] ? a.key[d] < b.key[d] : a.ref < b.ref;
-    });
-    // cand[d][rank] = first candidate of the cell of that rank in plane d; extra candidates of a
-    // cell are appended behind the n_cells first ones and chained in ascending reference order
-    size_t n_cells = 0;
-    for (size_t e = 0; e < entries.size(); e++)
-      if (e == 0 || entries[e].key[d] != entries[e - 1].key[d]) n_cells++;
-    std::vector<SprCand> &cand = R.cand[d];
-    cand.resize(entries.size());
-    // cellref[d][rank]: slot (inside the label's landmark table) of the cell's only candidate, or
-    // SPR_CELL_MULTI when the cell has several candidates (then cand[d] is walked)
-    std::vector<uint16_t> &cellref = R.cellref[d];
-    cellref.assign(n_cells + 8, 0);
-    R.cell_base[d].assign((size_t)n_labels + 1, 0u);
-    size_t rank = 0, extra = n_cells, prev = 0, cell = 0;
-    for (size_t e = 0; e < entries.size(); e++) {
-      const double *r = ref7 + 7 * (size_t)entries[e].ref;
-      const SprCand c{r[1], r[2], r[4], r[5], r[6], entries[e].ref, 0u};
-      if (e == 0 || entries[e].key[d] != entries[e - 1].key[d]) {
-        cell = prev = rank++;
-        const uint32_t slot = slot_of_ref[entries[e].ref];
-        cellref[cell] = slot < SPR_CELL_MULTI ? (uint16_t)slot : (uint16_t)SPR_CELL_MULTI;
-        const size_t l = (size_t)(entries[e].key[d] >> 44);
-        R.cell_base[d][l + 1] = (uint32_t)rank;  // running end of label l's cells
-      } else {
-        cand[prev].next = (uint32_t)extra;
-        prev = extra++;
-        cellref[cell] = (uint16_t)SPR_CELL_MULTI;
+  // mark every cell whose (slightly dilated) box a landmark's match disc touches; entries are
+  // produced in ascending landmark order, which is the order a cell's candidates must keep
+  struct Entry { uint32_t ref; int32_t nx, ny; };
+  std::vector<Entry> entries;
+  entries.reserve((size_t)n_ref * 12);
+  if (matchable) {
+    const double eps_cells = 3.0 / std::ldexp(1.0, F) + 1e-9 / c;  // fixed-point truncation + lattice drift
+    const double rc = rad_m / c + eps_cells;
+    const double rc2 = rc * rc * (1.0 + 1e-12);
+    for (int i = 0; i < n_ref; i++) {
+      const int l = lab_of[i];
+      if (l < 0) continue;
+      const double *r = ref7 + 7 * (size_t)i;
+      const double ux = (r[1] - G.g0x) / c, uy = (r[2] - G.g0y) / c;
+      const int x0 = (int)std::floor(ux - rc), x1 = (int)std::floor(ux + rc);
+      const int y0 = (int)std::floor(uy - rc), y1 = (int)std::floor(uy + rc);
+      if (x0 < 0 || x1 >= G.GX || y0 < 0 || y1 >= G.GY) { err = "internal: match disc leaves the grid"; return SLIDE_PR_ERR_INTERNAL; }
+      uint32_t *pl0 = R.bitmap.data() + (size_t)l * G.label_stride;
+      uint32_t *pl1 = pl0 + G.plane_words[0];
+      for (int nx = x0; nx <= x1; nx++) {
+        const double dx = std::fmax(std::fmax((double)nx - ux, 0.0), ux - (double)(nx + 1));
+        for (int ny = y0; ny <= y1; ny++) {
+          const double dy = std::fmax(std::fmax((double)ny - uy, 0.0), uy - (double)(ny + 1));
+          if (dx * dx + dy * dy > rc2) continue;
+          pl0[(size_t)(nx + 1) * G.W[0] + ((uint32_t)(ny + 32) >> 5)] |= 1u << ((ny + 32) & 31);
+          pl1[(size_t)(ny + 1) * G.W[1] + ((uint32_t)(nx + 32) >> 5)] |= 1u << ((nx + 32) & 31);
+          cb[l].x0 = std::min(cb[l].x0, nx); cb[l].x1 = std::max(cb[l].x1, nx);
+          cb[l].y0 = std::min(cb[l].y0, ny); cb[l].y1 = std::max(cb[l].y1, ny);
+          entries.push_back({(uint32_t)i, nx, ny});
+        }
       }
-      cand[prev] = c;
     }
-    for (int l = 0; l < n_labels; l++)  // labels without cells inherit the previous end
-      if (R.cell_base[d][l + 1] < R.cell_base[d][l]) R.cell_base[d][l + 1] = R.cell_base[d][l];
-    if (cand.empty()) cand.assign(1, SprCand{0, 0, 0, 0, 0, 0u, 0u});
+  }
+  if (entries.size() >= (1ull << 32)) { err = "candidate lists exceed 2^32 entries"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  for (int d = 0; d < 2; d++) {
     // rank tables of direction d, label-major == rank order of the marked cells:
     //   row_rank[l][row]  = rank of the first marked cell of the row, relative to the label's first cell
     //   rank16[l][word]   = marked cells of the same row before the word
+    //   cell_base[l]      = absolute rank of the label's first cell
     R.rank16[d].assign((size_t)G.plane_words[d] * (size_t)std::max(n_labels, 1) + 8, 0);
     R.row_rank[d].assign((size_t)G.R[d] * (size_t)std::max(n_labels, 1) + 1, 0u);
+    R.cell_base[d].assign((size_t)n_labels + 1, 0u);
     uint32_t running = 0;
     for (int l = 0; l < n_labels; l++) {
       const uint32_t *pl = R.bitmap.data() + (size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u);
       uint16_t *r16 = R.rank16[d].data() + (size_t)l * G.plane_words[d];
       uint32_t *rr = R.row_rank[d].data() + (size_t)l * G.R[d];
       const uint32_t label_start = running;
-      if (label_start != R.cell_base[d][l]) { err = "internal: label cell base mismatch"; return SLIDE_PR_ERR_INTERNAL; }
+      R.cell_base[d][l] = label_start;
       for (int row = 0; row < G.R[d]; row++) {
         rr[row] = running - label_start;
         uint32_t in_row = 0;
+        const uint32_t *prow = pl + (size_t)row * G.W[d];
+        uint16_t *rrow = r16 + (size_t)row * G.W[d];
         for (int w = 0; w < G.W[d]; w++) {
-          if (in_row > 0xffffu) { err = "more than 65535 marked cells in one bitmap row"; return SLIDE_PR_ERR_UNSUPPORTED; }
-          r16[(size_t)row * G.W[d] + w] = (uint16_t)in_row;
-          in_row += (uint32_t)__builtin_popcount(pl[(size_t)row * G.W[d] + w]);
+          rrow[w] = (uint16_t)in_row;
+          in_row += (uint32_t)__builtin_popcount(prow[w]);
         }
+        if (in_row > 0xffffu) { err = "more than 65535 marked cells in one bitmap row"; return SLIDE_PR_ERR_UNSUPPORTED; }
         running += in_row;
       }
     }
-    if ((size_t)running != n_cells) { err = "internal: rank / cell list mismatch"; return SLIDE_PR_ERR_INTERNAL; }
+    R.cell_base[d][n_labels] = running;
+    const size_t n_cells = running;
+    // cand[d][rank] = first candidate of the cell of that rank; extra candidates of a cell are
+    // appended behind the n_cells first ones and chained in ascending landmark order.
+    // cellref[d][rank] = slot (inside the label's landmark table) of the cell's only candidate,
+    // or SPR_CELL_MULTI when the cell has several candidates (then cand[d] is walked).
+    std::vector<SprCand> &cand = R.cand[d];
+    cand.resize(std::max<size_t>(entries.size(), 1));  // every slot below is overwritten
+    cand[0] = SprCand{0, 0, 0, 0, 0, 0u, 0u};
+    std::vector<uint16_t> &cellref = R.cellref[d];
+    cellref.assign(n_cells + 8, 0);
+    std::vector<uint32_t> tail(n_cells, 0xffffffffu);  // last record of each cell's chain
+    size_t extra = n_cells;
+    for (const Entry &e : entries) {
+      const int l = lab_of[e.ref];
+      const uint32_t row = (uint32_t)((d ? e.ny : e.nx) + 1), bit = (uint32_t)((d ? e.nx : e.ny) + 32);
+      const size_t wi = (size_t)row * G.W[d] + (bit >> 5);
+      const uint32_t *pl = R.bitmap.data() + (size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u);
+      const uint32_t rank = R.cell_base[d][l] + R.row_rank[d][(size_t)l * G.R[d] + row] +
+                            R.rank16[d][(size_t)l * G.plane_words[d] + wi] +
+                            (uint32_t)__builtin_popcount(pl[wi] & ((1u << (bit & 31u)) - 1u));
+      const double *r = ref7 + 7 * (size_t)e.ref;
+      const SprCand c{r[1], r[2], r[4], r[5], r[6], e.ref, 0u};
+      if (tail[rank] == 0xffffffffu) {
+        const uint32_t slot = slot_of_ref[e.ref];
+        cellref[rank] = slot < SPR_CELL_MULTI ? (uint16_t)slot : (uint16_t)SPR_CELL_MULTI;
+        cand[rank] = c;
+        tail[rank] = rank;
+      } else {
+        cellref[rank] = (uint16_t)SPR_CELL_MULTI;
+        cand[tail[rank]].next = (uint32_t)extra;
+        cand[extra] = c;  // c.next == 0
+        tail[rank] = (uint32_t)extra++;
+      }
+    }
+    if (extra != std::max<size_t>(entries.size(), n_cells) && !(entries.empty() && extra == 0)) {
+      if (extra != entries.size()) { err = "internal: rank / cell list mismatch"; return SLIDE_PR_ERR_INTERNAL; }
+    }
   }
   R.labelbox.resize((size_t)std::max(n_labels, 1));
   for (int l = 0; l < std::max(n_labels, 1); l++) {

@@ -29,6 +29,7 @@ struct Lattice {
   std::vector<Ring> ring;
   uint64_t n_translations = 0;
   std::vector<SprChunk> chunks;   // grouped by direction (see dir_begin / Ring::dbegin), warp-padded
+  std::vector<SprChunk> scratch;  // regrouping buffer, kept for its capacity
   bool ring_major = false;
   uint32_t dir_begin[2] = {0, 0}, dir_end[2] = {0, 0};  // !ring_major: all chunks of direction d
 };

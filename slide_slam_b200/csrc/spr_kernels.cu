@@ -345,9 +345,7 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int t
   const long long n_items = (long long)n_wg_local * V.n_yaw;
   const bool cnt32 = V.nqp > 65535;  // a count can reach the number of query landmarks
   const size_t warp_bytes = (size_t)(cnt32 ? SPR_WARP_WORDS(true) : SPR_WARP_WORDS(false)) * 4;
-  cudaError_t e = cudaMemsetAsync(K.work_counter, 0, sizeof(unsigned long long), st);
-  if (e != cudaSuccess) return e;
-  if (n_launches) (*n_launches)++;
+  if (n_launches) (*n_launches)++;  // K.work_counter was zeroed by the caller (one memset for all passes)
 
   // shared-memory-resident plane: one CTA per SM with as many warps as fit next to the tables
   const uint32_t tab = spr_tab_layout(V.grid.plane_words[K.dir], (uint32_t)V.grid.R[K.dir], K.tab_cells, K.tab_refs).total_w * 4u;

@@ -77,7 +77,7 @@ def emu_lib():
         deps = srcs + [os.path.join(ROOT, "slide_slam_b200", "csrc", f) for f in ("spr_core.h", "spr_types.h", "spr_host.h")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
             gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-            subprocess.run([gxx, "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so] + srcs, check=True)
+            subprocess.run([gxx, "-O2", "-mpopcnt", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so] + srcs, check=True)
         L = C.CDLL(so)
         L.spr_emu_match_maps.argtypes = [C.POINTER(capi.Params), _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double,
                                          C.c_longlong, C.c_longlong, _ip, C.c_longlong, _ip, C.POINTER(C.c_longlong),
