@@ -86,6 +86,8 @@ typedef struct slide_pr_match_result {
   int64_t d2h_bytes;           /* bytes copied device->host by search/extract */
   int64_t groups_probed;       /* (warp, query group) pairs probed / skipped by the bounding-box test */
   int64_t groups_skipped;      /*   (0 unless stats were enabled) */
+  int32_t reuse;               /* bit 0: lattice reused from the previous prepare, bit 1: reference-map index reused */
+  int32_t reserved2;
 } slide_pr_match_result;
 
 /* Options for the sharded / sliced search (multi-GPU and tests). */

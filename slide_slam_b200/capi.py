@@ -75,6 +75,8 @@ class MatchResult(C.Structure):
         ("d2h_bytes", C.c_int64),
         ("groups_probed", C.c_int64),
         ("groups_skipped", C.c_int64),
+        ("reuse", C.c_int32),
+        ("reserved2", C.c_int32),
     ]
 
 

@@ -58,6 +58,17 @@ struct slide_pr_handle {
   int n_ref = 0, n_qry = 0;
   int64_t lat_tb = 0, lat_te = -1;
   double prepare_ms = 0;
+  // streaming reuse: the reference-map index and the lattice are rebuilt only when
+  // their inputs change (same map bytes / same search ranges), e.g. many submap queries against one
+  // accumulated map.  `reuse` in the result tells which were reused.
+  std::vector<double> cached_ref;   // the (shifted) reference rows the index in R was built from
+  double cached_reach = -1.0;       // the index' fixed-point format covers |coordinates| up to this
+  slide_pr_params cached_ref_p{};   // parameters the index depends on
+  bool ref_index_valid = false;
+  double lat_hx = 0, lat_hy = 0, lat_yaw_half = 0;
+  slide_pr_params lat_p{};
+  bool lattice_valid = false, lattice_on_device = false;
+  int reuse_flags = 0;
   int64_t h2d_bytes = 0;
   spr::Lattice L;
   spr::RefIndex R;
@@ -202,8 +213,23 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   h->yaw_half = h->p.inter_loop_closure ? h->p.match_yaw_half_range : h->p.match_yaw_half_range_intra;
   h->n_ref = n_ref; h->n_qry = n_qry;
   h->lat_tb = 0; h->lat_te = -1;
-  int rc = spr::build_lattice(h->p, half_x, half_y, h->yaw_half, 0, -1, h->p.compute_budget_sec > 0, h->L, h->err);
-  if (rc != SLIDE_PR_OK) return rc;
+  int rc;
+  h->reuse_flags = 0;
+  // lattice: a function of the scalar search parameters only
+  const bool same_lattice = h->lattice_valid && h->lat_hx == half_x && h->lat_hy == half_y && h->lat_yaw_half == h->yaw_half &&
+                            h->lat_p.match_xy_step_size == h->p.match_xy_step_size &&
+                            h->lat_p.match_yaw_angle_step_size == h->p.match_yaw_angle_step_size &&
+                            h->lat_p.disable_yaw_search == h->p.disable_yaw_search &&
+                            (h->lat_p.compute_budget_sec > 0) == (h->p.compute_budget_sec > 0);
+  if (!same_lattice) {
+    h->lattice_valid = false;
+    if ((rc = spr::build_lattice(h->p, half_x, half_y, h->yaw_half, 0, -1, h->p.compute_budget_sec > 0, h->L, h->err)) != SLIDE_PR_OK) return rc;
+    h->lat_hx = half_x; h->lat_hy = half_y; h->lat_yaw_half = h->yaw_half; h->lat_p = h->p;
+    h->lattice_valid = true;
+    if ((rc = upload_lattice(h, st))) return rc;
+  } else {
+    h->reuse_flags |= 1;
+  }
   double qrad = 0;
   for (int j = 0; j < n_qry; j++) {
     const double r = std::hypot(qry7[7 * (size_t)j + 1], qry7[7 * (size_t)j + 2]);
@@ -211,29 +237,42 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
     qrad = std::max(qrad, r);
   }
   const double reach = qrad + std::max(std::fabs(half_x), std::fabs(half_y)) + h->p.match_xy_step_size;
-  if ((rc = spr::build_ref_index(h->p, ref7, n_ref, reach, h->R, h->err)) != SLIDE_PR_OK) return rc;
+  // reference index: a function of the reference rows, the cell size / thresholds and the reach
+  const bool same_ref = h->ref_index_valid && (int)(h->cached_ref.size() / 7) == n_ref && reach <= h->cached_reach &&
+                        h->cached_ref_p.match_xy_step_size == h->p.match_xy_step_size &&
+                        h->cached_ref_p.match_threshold == h->p.match_threshold &&
+                        h->cached_ref_p.match_threshold_dimension == h->p.match_threshold_dimension &&
+                        (n_ref == 0 || std::memcmp(h->cached_ref.data(), ref7, (size_t)n_ref * 7 * sizeof(double)) == 0);
+  if (!same_ref) {
+    h->ref_index_valid = false;
+    const double reach_cap = reach * 1.25;  // head-room so that slightly larger queries reuse the index
+    if ((rc = spr::build_ref_index(h->p, ref7, n_ref, reach_cap, h->R, h->err)) != SLIDE_PR_OK) return rc;
+    h->cached_ref.assign(ref7, ref7 + (size_t)n_ref * 7);
+    h->cached_reach = reach_cap; h->cached_ref_p = h->p;
+    h->ref_index_valid = true;
+    if ((rc = upload(h, h->d_labelbox, h->R.labelbox, st))) return rc;
+    if ((rc = upload(h, h->d_bitmap, h->R.bitmap, st))) return rc;
+    if ((rc = upload(h, h->d_rank16, h->R.rank16[0], st))) return rc;
+    if ((rc = upload(h, h->d_rank16b, h->R.rank16[1], st))) return rc;
+    if ((rc = upload(h, h->d_rowrank, h->R.row_rank[0], st))) return rc;
+    if ((rc = upload(h, h->d_rowrankb, h->R.row_rank[1], st))) return rc;
+    if ((rc = upload(h, h->d_cellref, h->R.cellref[0], st))) return rc;
+    if ((rc = upload(h, h->d_cellrefb, h->R.cellref[1], st))) return rc;
+    if ((rc = upload(h, h->d_cellbase, h->R.cell_base[0], st))) return rc;
+    if ((rc = upload(h, h->d_cellbaseb, h->R.cell_base[1], st))) return rc;
+    if ((rc = upload(h, h->d_reftab, h->R.reftab, st))) return rc;
+    if ((rc = upload(h, h->d_refbase, h->R.ref_base, st))) return rc;
+    if ((rc = upload(h, h->d_cand, h->R.cand[0], st))) return rc;
+    if ((rc = upload(h, h->d_cand1, h->R.cand[1], st))) return rc;
+    if ((rc = upload_raw(h, h->d_ref7, ref7, (size_t)n_ref * 7 * sizeof(double), st))) return rc;
+  } else {
+    h->reuse_flags |= 2;
+  }
   if ((rc = spr::build_query_set(h->R, qry7, n_qry, h->Q, h->err)) != SLIDE_PR_OK) return rc;
-
-  if ((rc = upload_lattice(h, st))) return rc;
   if ((rc = upload(h, h->d_qxy, h->Q.qxy, st))) return rc;
   if ((rc = upload(h, h->d_qdims, h->Q.qdims, st))) return rc;
   if ((rc = upload(h, h->d_labelseg, h->Q.label_gseg, st))) return rc;
   if ((rc = upload(h, h->d_qlabel, h->Q.qlabel, st))) return rc;
-  if ((rc = upload(h, h->d_labelbox, h->R.labelbox, st))) return rc;
-  if ((rc = upload(h, h->d_bitmap, h->R.bitmap, st))) return rc;
-  if ((rc = upload(h, h->d_rank16, h->R.rank16[0], st))) return rc;
-  if ((rc = upload(h, h->d_rank16b, h->R.rank16[1], st))) return rc;
-  if ((rc = upload(h, h->d_rowrank, h->R.row_rank[0], st))) return rc;
-  if ((rc = upload(h, h->d_rowrankb, h->R.row_rank[1], st))) return rc;
-  if ((rc = upload(h, h->d_cellref, h->R.cellref[0], st))) return rc;
-  if ((rc = upload(h, h->d_cellrefb, h->R.cellref[1], st))) return rc;
-  if ((rc = upload(h, h->d_cellbase, h->R.cell_base[0], st))) return rc;
-  if ((rc = upload(h, h->d_cellbaseb, h->R.cell_base[1], st))) return rc;
-  if ((rc = upload(h, h->d_reftab, h->R.reftab, st))) return rc;
-  if ((rc = upload(h, h->d_refbase, h->R.ref_base, st))) return rc;
-  if ((rc = upload(h, h->d_cand, h->R.cand[0], st))) return rc;
-  if ((rc = upload(h, h->d_cand1, h->R.cand[1], st))) return rc;
-  if ((rc = upload_raw(h, h->d_ref7, ref7, (size_t)n_ref * 7 * sizeof(double), st))) return rc;
   if ((rc = upload_raw(h, h->d_qry7, qry7, (size_t)n_qry * 7 * sizeof(double), st))) return rc;
   const size_t nrot = (size_t)std::max<size_t>((size_t)h->L.yaw.size() * (size_t)h->Q.nqp, 1);
   const size_t ngb = (size_t)std::max<size_t>((size_t)h->L.yaw.size() * (size_t)(h->Q.nqp / SPR_QGROUP), 1);
@@ -296,6 +335,7 @@ static void fill_result_header(slide_pr_handle *h, slide_pr_match_result *out) {
   out->n_translations = (int64_t)h->L.n_translations;
   out->prepare_ms = (float)h->prepare_ms;
   out->h2d_bytes = h->h2d_bytes;
+  out->reuse = h->reuse_flags;
 }
 
 int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_pr_match_result *out) {
@@ -313,6 +353,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   if (tb != h->lat_tb || te != h->lat_te) {  // re-chunk the lattice for the requested slice
     if ((rc = spr::build_lattice(h->p, h->half_x, h->half_y, h->yaw_half, tb, te, h->p.compute_budget_sec > 0, h->L, h->err)) != SLIDE_PR_OK) return rc;
     h->lat_tb = tb; h->lat_te = te;
+    h->lattice_valid = tb == 0 && te < 0;  // a sliced lattice is not the one prepare may reuse
     if ((rc = upload_lattice(h, st))) return rc;
   }
   const int n_yaw = (int)h->L.yaw.size();

@@ -316,3 +316,34 @@ def test_config2_full_size_properties():
     m = pr0.MatchMaps(sref, sqry, info.half_x, info.half_y)
     assert (m.best_num_inliers, m.info.best_hyp_index) == best
     pr0.close()
+
+
+def test_streaming_reuse_of_reference_index_and_lattice():
+    """Many queries against one accumulated map (BASELINE config 5): the reference-map index and
+    the lattice are rebuilt only when their inputs change; reused structures give the same
+    results as a fresh handle."""
+    big, queries = synth.config_stream(n_map=1500, n_queries=4, n_sub=60, seed=77)
+    kw = dict(match_xy_step_size=0.5, yaw_step_deg=15.0, match_threshold=0.5, match_threshold_dimension=1.0,
+              ignore_dimension=0, min_num_inliers=10)
+    op = O.make_params(**kw)
+    pr = make_pr(kw)
+    flags = []
+    for q in queries:
+        found, xyz_yaw, tf, info, ri, qi = pr.findTransformation(big, q)
+        flags.append(info.match.reuse)
+        fresh = make_pr(kw)
+        f2, x2, t2, i2, r2, q2 = fresh.findTransformation(big, q)
+        fresh.close()
+        assert (found, info.best_num_inliers, info.match.best_hyp_index) == (f2, i2.best_num_inliers, i2.match.best_hyp_index)
+        assert ri.tolist() == r2.tolist() and qi.tolist() == q2.tolist() and list(info.R_t) == list(i2.R_t)
+        want = O.find_transformation(op, big, q, n_threads=-1)
+        assert (found, info.best_num_inliers, info.match.best_hyp_index) == (want["found"], want["best_num_inliers"], want["best_hyp_index"])
+        assert ri.tolist() == want["ref_idx"].tolist()
+    assert flags[0] == 0 and all(f & 2 for f in flags[1:])  # the 1500-landmark index is built once
+    # a different reference map must not reuse the index
+    other = big.copy(); other[0, 1] += 0.25
+    found, _, _, info, _, _ = pr.findTransformation(other, queries[0])
+    assert not (info.match.reuse & 2)
+    want = O.find_transformation(op, other, queries[0], n_threads=-1)
+    assert (info.best_num_inliers, info.match.best_hyp_index) == (want["best_num_inliers"], want["best_hyp_index"])
+    pr.close()
