@@ -332,6 +332,55 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_extra(args, rank, world, local_rank):
+    """BASELINE configs 4 and 5 (not the driver's default line): map-pair matches / s for N-robot
+    all-pairs matching, and per-query latency of streaming submap queries against one map."""
+    import torch
+    from slide_slam_b200 import synth
+    from slide_slam_b200.place_recognition import PlaceRecognition
+    torch.cuda.set_device(local_rank)
+    pr = PlaceRecognition(ROS, device=local_rank)
+    if args.config == 4:
+        maps = synth.config_robots(8, args.landmarks or 5000)
+        pairs = [(i, j) for i in range(8) for j in range(i + 1, 8)]
+        mine = pairs[rank::world]
+        for r, q in mine[:1]:
+            pr.findTransformation(maps[r], maps[q])  # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hyps, found = 0, 0
+        for r, q in mine:
+            f, _, _, info, _, _ = pr.findTransformation(maps[r], maps[q])
+            hyps += info.match.hypotheses_scored
+            found += int(f)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print(json.dumps({"metric": "map_pair_matches_per_s", "value": len(mine) / dt, "unit": "pairs/s", "n_gpus": world,
+                          "rank": rank, "pairs": len(mine), "closures_found": found, "hypotheses_per_s": hyps / dt,
+                          "config": {"workload": f"config4: 8 robots, 28 pairs of {len(maps[0])} landmarks, pairs dealt round-robin"},
+                          "data": "synthetic", "dtype": "f64"}), flush=True)
+    else:
+        big, queries = synth.config_stream(args.landmarks or 50000, n_queries=max(args.steps, 1), n_sub=300)
+        pr.findTransformation(big, queries[0])  # builds the map's index (reused by the stream)
+        lat, hyps, found, reuse = [], 0, 0, 0
+        for q in queries:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            f, _, _, info, _, _ = pr.findTransformation(big, q)
+            lat.append((time.perf_counter() - t0) * 1e3)
+            hyps += info.match.hypotheses_scored
+            found += int(f)
+            reuse += int(bool(info.match.reuse & 2))
+        lat = np.array(lat)
+        print(json.dumps({"metric": "streaming_query_latency_ms", "value": float(np.median(lat)), "unit": "ms", "higher_is_better": False,
+                          "n_gpus": 1, "queries": len(queries), "p50": float(np.percentile(lat, 50)), "p95": float(np.percentile(lat, 95)),
+                          "p99": float(np.percentile(lat, 99)), "closures_found": found, "index_reused": reuse,
+                          "hypotheses_per_query": hyps // max(len(queries), 1), "hypotheses_per_s": hyps / (lat.sum() * 1e-3),
+                          "config": {"workload": f"config5: {len(queries)} submap queries of 300 landmarks against a {len(big)}-landmark map"},
+                          "data": "synthetic", "dtype": "f64"}), flush=True)
+    pr.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -342,12 +391,15 @@ def main():
     ap.add_argument("--workload", default="pairs", choices=["pairs", "shard"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--landmarks", type=int, default=0, help="override the landmark count of configs 4 / 5")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.config in (4, 5):
+        run_extra(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

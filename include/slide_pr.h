@@ -206,6 +206,28 @@ int slide_pr_match_triangles(slide_pr_handle *h, const double *tris_model6, int3
                              int32_t *perm_model_out, int32_t *perm_data_out,
                              int64_t cap, int64_t *n_matches);
 
+/* The same with a class signature: labels_*3 hold the semantic label of every triangle vertex
+ * (t x 3).  A pair is kept only if, in addition to the descriptor test, the vertices paired by
+ * the sorted order carry equal labels -- the "semantic label check" the reference leaves as a TODO
+ * (SC.cpp:114,186).  NULL label arrays give slide_pr_match_triangles. */
+int slide_pr_match_triangles_labeled(slide_pr_handle *h, const double *tris_model6, const double *labels_model3,
+                                     int32_t t_model, const double *tris_data6, const double *labels_data3,
+                                     int32_t t_data, double threshold, int32_t *model_idx_out,
+                                     int32_t *data_idx_out, int32_t *perm_model_out, int32_t *perm_data_out,
+                                     int64_t cap, int64_t *n_matches);
+
+/* semantic_clipper::estimate_tf (SC.cpp:122-138): 2-D Kabsch a -> b on k point pairs (k x 2 rows);
+ * tf9 row-major [[R, t], [0, 0, 1]]. */
+int slide_pr_estimate_tf(const double *pts_a2, const double *pts_b2, int32_t k, double *tf9);
+
+/* One rigid-transform hypothesis (c, s, x, y) per triangle match: the 2-D Kabsch fit that maps the
+ * data (query-map) triangle onto the model (reference-map) triangle with the vertices paired in
+ * sorted-descriptor order (perm_*: 3 ints per match, as returned by slide_pr_match_triangles).
+ * hyps4_out: n x 4, ready for slide_pr_score_hypotheses. */
+int slide_pr_triangle_hypotheses(const double *tris_model6, const double *tris_data6, const int32_t *model_idx,
+                                 const int32_t *data_idx, const int32_t *perm_model, const int32_t *perm_data,
+                                 int64_t n, double *hyps4_out);
+
 /* Scores an explicit list of rigid-transform hypotheses (c, s, x, y) -- e.g. the 2-D Kabsch
  * fits of matched triangles (SC.cpp:122-138) -- with the MatchMaps inlier predicate
  * (PR.cpp:272-357) against the maps given to slide_pr_prepare.  hyps: n x 4 doubles.

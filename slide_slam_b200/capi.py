@@ -27,6 +27,7 @@ EXPORTS = [
     "slide_pr_find_inter_loop_closure", "slide_pr_find_intra_loop_closure", "slide_pr_solve_lsq",
     "slide_pr_get_xyz_yaw_from_tf", "slide_pr_find_transformation_batch", "slide_pr_pack_record",
     "slide_pr_merge_records", "slide_pr_match_triangles", "slide_pr_score_hypotheses",
+    "slide_pr_match_triangles_labeled", "slide_pr_estimate_tf", "slide_pr_triangle_hypotheses",
 ]
 
 
@@ -167,6 +168,10 @@ def lib():
     L.slide_pr_merge_records.argtypes = [C.POINTER(TopkRecord), C.c_int32]
     L.slide_pr_match_triangles.argtypes = [C.c_void_p, _dp, C.c_int32, _dp, C.c_int32, C.c_double, _ip, _ip,
                                            _ip, _ip, C.c_int64, C.POINTER(C.c_int64)]
+    L.slide_pr_match_triangles_labeled.argtypes = [C.c_void_p, _dp, _dp, C.c_int32, _dp, _dp, C.c_int32, C.c_double, _ip,
+                                                   _ip, _ip, _ip, C.c_int64, C.POINTER(C.c_int64)]
+    L.slide_pr_estimate_tf.argtypes = [_dp, _dp, C.c_int32, _dp]
+    L.slide_pr_triangle_hypotheses.argtypes = [_dp, _dp, _ip, _ip, _ip, _ip, C.c_int64, _dp]
     L.slide_pr_score_hypotheses.argtypes = [C.c_void_p, _dp, C.c_int64, _ip, C.POINTER(MatchResult)]
     _lib = L
     return L

@@ -713,34 +713,42 @@ int slide_pr_merge_records(const slide_pr_topk_record *recs, int32_t n) {
   return best;
 }
 
-int slide_pr_match_triangles(slide_pr_handle *h, const double *tris_model6, int32_t t_model,
-                             const double *tris_data6, int32_t t_data, double threshold, int32_t *model_idx_out,
-                             int32_t *data_idx_out, int32_t *perm_model_out, int32_t *perm_data_out, int64_t cap,
-                             int64_t *n_matches) {
+int slide_pr_match_triangles_labeled(slide_pr_handle *h, const double *tris_model6, const double *labels_model3,
+                                     int32_t t_model, const double *tris_data6, const double *labels_data3,
+                                     int32_t t_data, double threshold, int32_t *model_idx_out, int32_t *data_idx_out,
+                                     int32_t *perm_model_out, int32_t *perm_data_out, int64_t cap, int64_t *n_matches) {
   if (!h || !n_matches || t_model < 0 || t_data < 0 || cap < 0) return SLIDE_PR_ERR_INVALID;
   if ((t_model > 0 && !tris_model6) || (t_data > 0 && !tris_data6)) { h->err = "null triangle array"; return SLIDE_PR_ERR_INVALID; }
+  if ((labels_model3 == nullptr) != (labels_data3 == nullptr)) { h->err = "labels must be given for both maps or for none"; return SLIDE_PR_ERR_INVALID; }
   *n_matches = 0;
   if (t_model == 0 || t_data == 0) return SLIDE_PR_OK;
+  const bool labeled = labels_model3 != nullptr;
   SPR_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   DevBuf &b = h->d_tri;
-  // layout: tris_m | tris_d | desc_m | desc_d | perm_m | perm_d | counts | offsets | total
+  // layout: tris_m | tris_d | labels_m | labels_d | desc_m | desc_d | sig_m | sig_d | perm_m | perm_d | counts | offsets | total
   const size_t tm = (size_t)t_model, td = (size_t)t_data;
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  const size_t o_tm = take(tm * 6 * 8), o_td = take(td * 6 * 8), o_dm = take(tm * 3 * 8), o_dd = take(td * 3 * 8);
+  const size_t o_tm = take(tm * 6 * 8), o_td = take(td * 6 * 8), o_lm = take(tm * 3 * 8), o_ld = take(td * 3 * 8);
+  const size_t o_dm = take(tm * 3 * 8), o_dd = take(td * 3 * 8), o_sm = take(tm * 3 * 8), o_sd = take(td * 3 * 8);
   const size_t o_pm = take(tm * 3 * 4), o_pd = take(td * 3 * 4), o_cnt = take(tm * 8), o_off = take(tm * 8), o_tot = take(8);
   SPR_CUDA(h, b.ensure(off));
   char *base = b.as<char>();
   SPR_CUDA(h, cudaMemcpyAsync(base + o_tm, tris_model6, tm * 6 * 8, cudaMemcpyHostToDevice, st));
   SPR_CUDA(h, cudaMemcpyAsync(base + o_td, tris_data6, td * 6 * 8, cudaMemcpyHostToDevice, st));
+  if (labeled) {
+    SPR_CUDA(h, cudaMemcpyAsync(base + o_lm, labels_model3, tm * 3 * 8, cudaMemcpyHostToDevice, st));
+    SPR_CUDA(h, cudaMemcpyAsync(base + o_ld, labels_data3, td * 3 * 8, cudaMemcpyHostToDevice, st));
+  }
   double *dm = (double *)(base + o_dm), *dd = (double *)(base + o_dd);
+  double *sm = labeled ? (double *)(base + o_sm) : nullptr, *sd = labeled ? (double *)(base + o_sd) : nullptr;
   int32_t *pm = (int32_t *)(base + o_pm), *pd = (int32_t *)(base + o_pd);
   unsigned long long *cnt = (unsigned long long *)(base + o_cnt), *offs = (unsigned long long *)(base + o_off),
                      *tot = (unsigned long long *)(base + o_tot);
-  SPR_CUDA(h, spr_launch_tri_desc((const double *)(base + o_tm), t_model, dm, pm, st));
-  SPR_CUDA(h, spr_launch_tri_desc((const double *)(base + o_td), t_data, dd, pd, st));
-  SPR_CUDA(h, spr_launch_tri_match(dm, t_model, dd, t_data, threshold, cnt, offs, tot, nullptr, nullptr, 0, false,
+  SPR_CUDA(h, spr_launch_tri_desc((const double *)(base + o_tm), labeled ? (const double *)(base + o_lm) : nullptr, t_model, dm, pm, sm, st));
+  SPR_CUDA(h, spr_launch_tri_desc((const double *)(base + o_td), labeled ? (const double *)(base + o_ld) : nullptr, t_data, dd, pd, sd, st));
+  SPR_CUDA(h, spr_launch_tri_match(dm, t_model, dd, t_data, sm, sd, threshold, cnt, offs, tot, nullptr, nullptr, 0, false,
                                    h->sm_count, st));
   unsigned long long total = 0;
   SPR_CUDA(h, cudaMemcpyAsync(&total, tot, 8, cudaMemcpyDeviceToHost, st));
@@ -750,7 +758,7 @@ int slide_pr_match_triangles(slide_pr_handle *h, const double *tris_model6, int3
   if (n_out > 0 && model_idx_out && data_idx_out) {
     SPR_CUDA(h, h->d_tri_out.ensure((size_t)n_out * 2 * sizeof(int32_t)));
     int32_t *mi = h->d_tri_out.as<int32_t>(), *di = mi + n_out;
-    SPR_CUDA(h, spr_launch_tri_match(dm, t_model, dd, t_data, threshold, cnt, offs, tot, mi, di, n_out, true,
+    SPR_CUDA(h, spr_launch_tri_match(dm, t_model, dd, t_data, sm, sd, threshold, cnt, offs, tot, mi, di, n_out, true,
                                      h->sm_count, st));
     SPR_CUDA(h, cudaMemcpyAsync(model_idx_out, mi, (size_t)n_out * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SPR_CUDA(h, cudaMemcpyAsync(data_idx_out, di, (size_t)n_out * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -766,6 +774,37 @@ int slide_pr_match_triangles(slide_pr_handle *h, const double *tris_model6, int3
         if (perm_model_out) perm_model_out[3 * k + v] = hpm[3 * (size_t)model_idx_out[k] + v];
         if (perm_data_out) perm_data_out[3 * k + v] = hpd[3 * (size_t)data_idx_out[k] + v];
       }
+  }
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_match_triangles(slide_pr_handle *h, const double *tris_model6, int32_t t_model, const double *tris_data6,
+                             int32_t t_data, double threshold, int32_t *model_idx_out, int32_t *data_idx_out,
+                             int32_t *perm_model_out, int32_t *perm_data_out, int64_t cap, int64_t *n_matches) {
+  return slide_pr_match_triangles_labeled(h, tris_model6, nullptr, t_model, tris_data6, nullptr, t_data, threshold,
+                                          model_idx_out, data_idx_out, perm_model_out, perm_data_out, cap, n_matches);
+}
+
+int slide_pr_estimate_tf(const double *pts_a2, const double *pts_b2, int32_t k, double *tf9) {
+  if (!pts_a2 || !pts_b2 || !tf9 || k <= 0) return SLIDE_PR_ERR_INVALID;
+  spr::estimate_tf(pts_a2, pts_b2, k, tf9);
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_triangle_hypotheses(const double *tris_model6, const double *tris_data6, const int32_t *model_idx,
+                                 const int32_t *data_idx, const int32_t *perm_model, const int32_t *perm_data, int64_t n,
+                                 double *hyps4_out) {
+  if (n < 0 || (n > 0 && (!tris_model6 || !tris_data6 || !model_idx || !data_idx || !perm_model || !perm_data || !hyps4_out)))
+    return SLIDE_PR_ERR_INVALID;
+  for (int64_t k = 0; k < n; k++) {
+    const double *tm = tris_model6 + 6 * (size_t)model_idx[k], *td = tris_data6 + 6 * (size_t)data_idx[k];
+    double a[6], b[6], tf[9];
+    for (int v = 0; v < 3; v++) {  // data (query) vertex v  ->  model (reference) vertex v, sorted order
+      a[2 * v] = td[2 * perm_data[3 * k + v]]; a[2 * v + 1] = td[2 * perm_data[3 * k + v] + 1];
+      b[2 * v] = tm[2 * perm_model[3 * k + v]]; b[2 * v + 1] = tm[2 * perm_model[3 * k + v] + 1];
+    }
+    spr::estimate_tf(a, b, 3, tf);
+    hyps4_out[4 * k] = tf[0]; hyps4_out[4 * k + 1] = tf[3]; hyps4_out[4 * k + 2] = tf[2]; hyps4_out[4 * k + 3] = tf[5];
   }
   return SLIDE_PR_OK;
 }

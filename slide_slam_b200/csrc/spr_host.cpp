@@ -638,6 +638,25 @@ void solve_lsq(const double *tgt3, const double *src3, int k, double *xyz_yaw4, 
   xyz_yaw_from_tf(tf16, xyz_yaw4);
 }
 
+void estimate_tf(const double *a, const double *b, int k, double *tf9) {  // SC.cpp:122-138
+  double ca[2] = {0, 0}, cb[2] = {0, 0};
+  for (int i = 0; i < k; i++) { ca[0] += a[2 * i]; ca[1] += a[2 * i + 1]; cb[0] += b[2 * i]; cb[1] += b[2 * i + 1]; }
+  ca[0] /= (double)k; ca[1] /= (double)k; cb[0] /= (double)k; cb[1] /= (double)k;
+  double H[4] = {0, 0, 0, 0};
+  for (int i = 0; i < k; i++) {
+    const double ax = a[2 * i] - ca[0], ay = a[2 * i + 1] - ca[1];
+    const double bx = b[2 * i] - cb[0], by = b[2 * i + 1] - cb[1];
+    H[0] += ax * bx; H[1] += ax * by; H[2] += ay * bx; H[3] += ay * by;
+  }
+  double U[4], S[2], V[4];
+  svd_jacobi(H, 2, U, S, V);
+  double R[4] = {V[0] * U[0] + V[1] * U[1], V[0] * U[2] + V[1] * U[3], V[2] * U[0] + V[3] * U[1], V[2] * U[2] + V[3] * U[3]};  // V U^T
+  if (R[0] * R[3] - R[1] * R[2] < 0) { R[1] = -R[1]; R[3] = -R[3]; }  // R.col(1) *= -1
+  tf9[0] = R[0]; tf9[1] = R[1]; tf9[2] = cb[0] - (R[0] * ca[0] + R[1] * ca[1]);
+  tf9[3] = R[2]; tf9[4] = R[3]; tf9[5] = cb[1] - (R[2] * ca[0] + R[3] * ca[1]);
+  tf9[6] = 0; tf9[7] = 0; tf9[8] = 1;
+}
+
 void mat4_mul(const double *A, const double *B, double *C) {
   double T[16];
   for (int i = 0; i < 4; i++)

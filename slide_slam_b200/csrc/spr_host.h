@@ -81,6 +81,8 @@ double div3_threshold(double thr_dim);
 // PlaceRecognition::solveLSQ (PR.cpp:632-695) / getxyzYawfromTF (PR.cpp:697-711)
 void solve_lsq(const double *tgt3, const double *src3, int k, double *xyz_yaw4, double *tf16);
 void xyz_yaw_from_tf(const double *tf16, double *xyz_yaw4);
+// semantic_clipper::estimate_tf (SC.cpp:122-138): 2-D Kabsch a -> b, tf9 row-major
+void estimate_tf(const double *a2, const double *b2, int k, double *tf9);
 void svd_jacobi(const double *A, int n, double *U, double *S, double *V);
 void mat4_mul(const double *A, const double *B, double *C);
 bool mat4_rigid_inverse(const double *A, double *Ainv);

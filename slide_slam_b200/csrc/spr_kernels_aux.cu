@@ -96,8 +96,8 @@ cudaError_t spr_launch_extract(const double *ref7, int n_ref, const double *qry7
 // sweeps the data descriptors 32 at a time and compacts its matches with ballot + popc so the
 // output keeps the reference's order (model-major, data-minor).
 // ---------------------------------------------------------------------------------------------
-__global__ void spr_tri_desc_kernel(const double *__restrict__ tris6, int t, double *__restrict__ desc,
-                                    int32_t *__restrict__ perm) {
+__global__ void spr_tri_desc_kernel(const double *__restrict__ tris6, const double *__restrict__ labels3, int t,
+                                    double *__restrict__ desc, int32_t *__restrict__ perm, double *__restrict__ sig) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= t) return;
   double tri[6], d[3];
@@ -106,12 +106,19 @@ __global__ void spr_tri_desc_kernel(const double *__restrict__ tris6, int t, dou
   for (int k = 0; k < 6; k++) tri[k] = tris6[6 * (size_t)i + k];
   spr_triangle_descriptor(tri, d, p);
 #pragma unroll
-  for (int k = 0; k < 3; k++) { desc[3 * (size_t)i + k] = d[k]; perm[3 * (size_t)i + k] = p[k]; }
+  for (int k = 0; k < 3; k++) {
+    desc[3 * (size_t)i + k] = d[k];
+    perm[3 * (size_t)i + k] = p[k];
+    // class signature: the vertex labels in sorted-descriptor order (the order in which the
+    // vertices are paired when two triangles match, SC.cpp:102-105)
+    if (labels3) sig[3 * (size_t)i + k] = labels3[3 * (size_t)i + p[k]];
+  }
 }
 
 template <bool FILL>
 __global__ void __launch_bounds__(256)
-spr_tri_match_kernel(const double *__restrict__ dm, int tm, const double *__restrict__ dd, int td, double thr,
+spr_tri_match_kernel(const double *__restrict__ dm, int tm, const double *__restrict__ dd, int td,
+                     const double *__restrict__ sm, const double *__restrict__ sd, double thr,
                      unsigned long long *__restrict__ counts, const unsigned long long *__restrict__ offsets,
                      int32_t *__restrict__ model_idx, int32_t *__restrict__ data_idx, long long cap) {
   const int lane = threadIdx.x & 31;
@@ -119,6 +126,8 @@ spr_tri_match_kernel(const double *__restrict__ dm, int tm, const double *__rest
   const int n_warps = (gridDim.x * blockDim.x) >> 5;
   for (int i = warp; i < tm; i += n_warps) {
     const double m[3] = {dm[3 * (size_t)i], dm[3 * (size_t)i + 1], dm[3 * (size_t)i + 2]};
+    double ms[3] = {0.0, 0.0, 0.0};
+    if (sm) { ms[0] = sm[3 * (size_t)i]; ms[1] = sm[3 * (size_t)i + 1]; ms[2] = sm[3 * (size_t)i + 2]; }
     unsigned long long base = FILL ? offsets[i] : 0ull;
     for (int j0 = 0; j0 < td; j0 += 32) {
       const int j = j0 + lane;
@@ -126,6 +135,10 @@ spr_tri_match_kernel(const double *__restrict__ dm, int tm, const double *__rest
       if (j < td) {
         const double d[3] = {dd[3 * (size_t)j], dd[3 * (size_t)j + 1], dd[3 * (size_t)j + 2]};
         hit = spr_descriptor_match(m, d, thr);
+        // class-consistent pairs only: every paired vertex must carry the same label (the check the
+        // reference leaves as a TODO, SC.cpp:114,186); labels compare as doubles like PR.cpp:306
+        if (hit && sm)
+          hit = ms[0] == sd[3 * (size_t)j] && ms[1] == sd[3 * (size_t)j + 1] && ms[2] == sd[3 * (size_t)j + 2];
       }
       const unsigned mask = __ballot_sync(SPR_FULL, hit);
       if (FILL && hit) {
@@ -164,13 +177,14 @@ __global__ void spr_scan_kernel(const unsigned long long *__restrict__ counts, i
   if (threadIdx.x == 0) *total = carry;
 }
 
-cudaError_t spr_launch_tri_desc(const double *tris6, int t, double *desc, int32_t *perm, cudaStream_t st) {
+cudaError_t spr_launch_tri_desc(const double *tris6, const double *labels3, int t, double *desc, int32_t *perm,
+                                double *sig, cudaStream_t st) {
   if (t <= 0) return cudaSuccess;
-  spr_tri_desc_kernel<<<(t + 255) / 256, 256, 0, st>>>(tris6, t, desc, perm);
+  spr_tri_desc_kernel<<<(t + 255) / 256, 256, 0, st>>>(tris6, labels3, t, desc, perm, sig);
   return cudaGetLastError();
 }
 
-cudaError_t spr_launch_tri_match(const double *dm, int tm, const double *dd, int td, double thr,
+cudaError_t spr_launch_tri_match(const double *dm, int tm, const double *dd, int td, const double *sm, const double *sd, double thr,
                                  unsigned long long *counts, unsigned long long *offsets, unsigned long long *total,
                                  int32_t *model_idx, int32_t *data_idx, long long cap, bool fill, int sm_count,
                                  cudaStream_t st) {
@@ -178,10 +192,10 @@ cudaError_t spr_launch_tri_match(const double *dm, int tm, const double *dd, int
   const int want = (tm + 7) / 8, capg = sm_count * 8;
   const int grid = want < capg ? want : capg;
   if (!fill) {
-    spr_tri_match_kernel<false><<<grid, 256, 0, st>>>(dm, tm, dd, td, thr, counts, offsets, model_idx, data_idx, cap);
+    spr_tri_match_kernel<false><<<grid, 256, 0, st>>>(dm, tm, dd, td, sm, sd, thr, counts, offsets, model_idx, data_idx, cap);
     spr_scan_kernel<<<1, 1024, 0, st>>>(counts, tm, offsets, total);
   } else {
-    spr_tri_match_kernel<true><<<grid, 256, 0, st>>>(dm, tm, dd, td, thr, counts, offsets, model_idx, data_idx, cap);
+    spr_tri_match_kernel<true><<<grid, 256, 0, st>>>(dm, tm, dd, td, sm, sd, thr, counts, offsets, model_idx, data_idx, cap);
   }
   return cudaGetLastError();
 }

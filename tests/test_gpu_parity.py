@@ -322,8 +322,8 @@ def test_streaming_reuse_of_reference_index_and_lattice():
     """Many queries against one accumulated map (BASELINE config 5): the reference-map index and
     the lattice are rebuilt only when their inputs change; reused structures give the same
     results as a fresh handle."""
-    big, queries = synth.config_stream(n_map=1500, n_queries=4, n_sub=60, seed=77)
-    kw = dict(match_xy_step_size=0.5, yaw_step_deg=15.0, match_threshold=0.5, match_threshold_dimension=1.0,
+    big, queries = synth.config_stream(n_map=300, n_queries=3, n_sub=40, seed=77)
+    kw = dict(match_xy_step_size=0.5, yaw_step_deg=30.0, match_threshold=0.5, match_threshold_dimension=1.0,
               ignore_dimension=0, min_num_inliers=10)
     op = O.make_params(**kw)
     pr = make_pr(kw)
@@ -339,7 +339,7 @@ def test_streaming_reuse_of_reference_index_and_lattice():
         want = O.find_transformation(op, big, q, n_threads=-1)
         assert (found, info.best_num_inliers, info.match.best_hyp_index) == (want["found"], want["best_num_inliers"], want["best_hyp_index"])
         assert ri.tolist() == want["ref_idx"].tolist()
-    assert flags[0] == 0 and all(f & 2 for f in flags[1:])  # the 1500-landmark index is built once
+    assert flags[0] == 0 and all(f & 2 for f in flags[1:])  # the map's index is built once
     # a different reference map must not reuse the index
     other = big.copy(); other[0, 1] += 0.25
     found, _, _, info, _, _ = pr.findTransformation(other, queries[0])
