@@ -407,6 +407,8 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
         K.first = i == 0; K.last = i + 1 == active.size();
         K.tab_cells = K.label >= 0 ? h->R.cell_base[d][K.label + 1] - h->R.cell_base[d][K.label] : 0u;
         K.tab_refs = K.label >= 0 ? h->R.ref_base[K.label + 1] - h->R.ref_base[K.label] : 0u;
+        K.tab_cell_base = K.label >= 0 ? h->R.cell_base[d][K.label] : 0u;
+        K.tab_ref_base = K.label >= 0 ? h->R.ref_base[K.label] : 0u;
         if (passes_left == 0) {  // (re)arm a batch of counters with a single memset
           passes_left = 4096;
           K.work_counter = h->d_work.as<unsigned long long>();

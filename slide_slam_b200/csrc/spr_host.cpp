@@ -297,7 +297,7 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
   // plane d: rows = across cells + 2 zero rows; bits = 32 pad + along cells + >= 64 pad
   const int across[2] = {G.GX, G.GY}, along[2] = {G.GY, G.GX};
   for (int d = 0; d < 2; d++) {
-    G.R[d] = across[d] + 2;
+    G.R[d] = (across[d] + 2 + 7) & ~7;  // 2 zero rows + padding rows: plane sizes stay multiples of 32 bytes (bulk copies)
     int W = (32 + along[d] + 32 + 31) / 32 + 1;
     if ((W & 1) == 0) W++;  // odd row pitch: consecutive rows fall in different shared-memory banks
     G.W[d] = W;
@@ -329,7 +329,7 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
       slot_of_ref[i] = per[l]++;
     }
     for (int l = 0; l < n_labels; l++) R.ref_base[l + 1] = R.ref_base[l] + per[l];
-    R.reftab.assign(5 * (size_t)std::max<uint32_t>(R.ref_base[n_labels], 1), 0.0);
+    R.reftab.assign(5 * (size_t)std::max<uint32_t>(R.ref_base[n_labels], 1) + 8, 0.0);  // + slack for aligned bulk copies
     for (int i = 0; i < n_ref; i++) {
       if (lab_of[i] < 0) continue;
       const double *r = ref7 + 7 * (size_t)i;
@@ -409,7 +409,7 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
     cand.resize(std::max<size_t>(entries.size(), 1));  // every slot below is overwritten
     cand[0] = SprCand{0, 0, 0, 0, 0, 0u, 0u};
     std::vector<uint16_t> &cellref = R.cellref[d];
-    cellref.assign(n_cells + 8, 0);
+    cellref.assign(n_cells + 16, 0);  // + slack for aligned bulk copies
     std::vector<uint32_t> tail(n_cells, 0xffffffffu);  // last record of each cell's chain
     size_t extra = n_cells;
     for (const Entry &e : entries) {

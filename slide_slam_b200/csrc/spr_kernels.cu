@@ -57,18 +57,55 @@ template <bool CNT32> __device__ __forceinline__ uint32_t spr_cnt_get(const uint
   return (cnt[lane * 17 + (b >> 1)] >> ((b & 1) << 4)) & 0xffffu;
 }
 
-// word offsets of the staged tables inside the CTA's shared memory (every part 16-byte aligned)
-struct SprTabLayout { uint32_t reftab_w, bits_w, r16_w, rr_w, cellref_w, total_w; };
-__host__ __device__ static inline SprTabLayout spr_tab_layout(uint32_t PW, uint32_t R, uint32_t cells, uint32_t refs) {
+// Byte sizes / word offsets of the tables staged into the CTA's shared memory.  Every part is a
+// multiple of 16 bytes and starts 16-byte aligned, as cp.async.bulk requires; the per-label slices
+// of cellref / reftab start at arbitrary elements, so they are copied from the enclosing aligned
+// window (`*_skip` leading elements are skipped by the pointer the kernel uses).
+struct SprTabLayout {
+  uint32_t reftab_w, bits_w, r16_w, rr_w, cellref_w, total_w;        // word offsets
+  uint32_t reftab_b, bits_b, r16_b, rr_b, cellref_b;                 // bytes to copy
+  uint32_t reftab_skip, cellref_skip;                                // leading elements (doubles / u16) to skip
+};
+__host__ __device__ static inline SprTabLayout spr_tab_layout(uint32_t PW, uint32_t R, uint32_t cell_base, uint32_t cells,
+                                                              uint32_t ref_base, uint32_t refs) {
   SprTabLayout o;
+  o.reftab_skip = 5u * (ref_base & 1u);
+  o.cellref_skip = cell_base & 7u;
+  o.reftab_b = ((5u * ((ref_base & 1u) + refs) * 8u) + 15u) & ~15u;
+  o.bits_b = PW * 4u;                  // PW is a multiple of 8 words
+  o.r16_b = PW * 2u;
+  o.rr_b = R * 4u;                     // R is a multiple of 8 rows
+  o.cellref_b = (((cell_base & 7u) + cells) * 2u + 15u) & ~15u;
   uint32_t w = 0;
-  o.reftab_w = w;  w += (10u * refs + 3u) & ~3u;
-  o.bits_w = w;    w += (PW + 3u) & ~3u;
-  o.r16_w = w;     w += (((PW + 1u) >> 1) + 3u) & ~3u;
-  o.rr_w = w;      w += (R + 3u) & ~3u;
-  o.cellref_w = w; w += (((cells + 1u) >> 1) + 3u) & ~3u;
-  o.total_w = w;
+  o.reftab_w = w;  w += o.reftab_b >> 2;
+  o.bits_w = w;    w += o.bits_b >> 2;
+  o.r16_w = w;     w += o.r16_b >> 2;
+  o.rr_w = w;      w += o.rr_b >> 2;
+  o.cellref_w = w; w += o.cellref_b >> 2;
+  o.total_w = w + 4;                   // + the mbarrier (8 bytes, 16-byte slot)
   return o;
+}
+
+// --- TMA bulk copy (cp.async.bulk) + mbarrier helpers ---------------------------------------------
+__device__ __forceinline__ uint32_t spr_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void spr_mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(spr_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void spr_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(spr_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void spr_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(spr_smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(spr_smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool spr_mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(spr_smem_addr(bar)), "r"(parity)
+               : "memory");
+  return ok != 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -146,19 +183,35 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
   // table): staged into shared memory once per CTA, or read in place
   SprTables T = spr_global_tables(V, d, l < 0 ? 0 : l);
   if (SMEM_TAB) {
+    // One thread arms an mbarrier with the byte count and issues five TMA bulk copies
+    // (cp.async.bulk global -> shared); everybody waits on the barrier's phase.
     const SprTables GT = T;
-    const SprTabLayout Lo = spr_tab_layout(G.plane_words[d], (uint32_t)G.R[d], K.tab_cells, K.tab_refs);
+    const uint32_t ref_base = V.ref_base[l];
+    const SprTabLayout Lo = spr_tab_layout(G.plane_words[d], (uint32_t)G.R[d], GT.cell_base, K.tab_cells, ref_base, K.tab_refs);
     double *s_ref = reinterpret_cast<double *>(smem + Lo.reftab_w);
     uint32_t *s_bits = smem + Lo.bits_w;
     uint16_t *s_r16 = reinterpret_cast<uint16_t *>(smem + Lo.r16_w);
     uint32_t *s_rr = smem + Lo.rr_w;
     uint16_t *s_cell = reinterpret_cast<uint16_t *>(smem + Lo.cellref_w);
-    for (uint32_t i = threadIdx.x; i < 5u * K.tab_refs; i += blockDim.x) s_ref[i] = GT.reftab[i];
-    for (uint32_t i = threadIdx.x; i < G.plane_words[d]; i += blockDim.x) { s_bits[i] = GT.bits[i]; s_r16[i] = GT.r16[i]; }
-    for (uint32_t i = threadIdx.x; i <= Rm1; i += blockDim.x) s_rr[i] = GT.row_rank[i];
-    for (uint32_t i = threadIdx.x; i < K.tab_cells; i += blockDim.x) s_cell[i] = GT.cellref[i];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + Lo.total_w - 4);
+    if (threadIdx.x == 0) {
+      spr_mbar_init(bar, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    T.bits = s_bits; T.r16 = s_r16; T.row_rank = s_rr; T.cellref = s_cell; T.reftab = s_ref;
+    if (threadIdx.x == 0) {
+      spr_mbar_expect_tx(bar, Lo.reftab_b + Lo.bits_b + Lo.r16_b + Lo.rr_b + Lo.cellref_b);
+      spr_bulk_g2s(s_ref, GT.reftab - Lo.reftab_skip, Lo.reftab_b, bar);
+      spr_bulk_g2s(s_bits, GT.bits, Lo.bits_b, bar);
+      spr_bulk_g2s(s_r16, GT.r16, Lo.r16_b, bar);
+      spr_bulk_g2s(s_rr, GT.row_rank, Lo.rr_b, bar);
+      spr_bulk_g2s(s_cell, GT.cellref - Lo.cellref_skip, Lo.cellref_b, bar);
+    }
+    for (uint32_t spin = 0; !spr_mbar_try_wait(bar, 0u); spin++)
+      if (spin > 200000000u) __trap();  // a lost copy must not hang the GPU
+    T.bits = s_bits; T.r16 = s_r16; T.row_rank = s_rr;
+    T.cellref = s_cell + Lo.cellref_skip;
+    T.reftab = s_ref + Lo.reftab_skip;
   }
   WarpState ws;
   ws.cnt = smem + (tab_bytes >> 2) + warp * SPR_WARP_WORDS(CNT32);
@@ -348,7 +401,8 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int t
   if (n_launches) (*n_launches)++;  // K.work_counter was zeroed by the caller (one memset for all passes)
 
   // shared-memory-resident plane: one CTA per SM with as many warps as fit next to the tables
-  const uint32_t tab = spr_tab_layout(V.grid.plane_words[K.dir], (uint32_t)V.grid.R[K.dir], K.tab_cells, K.tab_refs).total_w * 4u;
+  const uint32_t tab = spr_tab_layout(V.grid.plane_words[K.dir], (uint32_t)V.grid.R[K.dir], K.tab_cell_base, K.tab_cells,
+                                      K.tab_ref_base, K.tab_refs).total_w * 4u;
   int smem_warps = 0;
   if (tables_mode == SPR_TABLES_AUTO && K.label >= 0 && K.tab_refs < SPR_CELL_MULTI && (size_t)tab + 8 * warp_bytes <= SPR_SMEM_LIMIT) {
     smem_warps = (int)((SPR_SMEM_LIMIT - tab) / warp_bytes);

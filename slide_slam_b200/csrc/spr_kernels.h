@@ -13,6 +13,7 @@ struct SprLaunch {
   int32_t  label;                   // label bucket probed by this pass; -1: no queries at all
   uint32_t dir;                     // bitmap direction of every chunk in [chunk_begin, chunk_end)
   uint32_t tab_cells, tab_refs;     // marked cells / landmarks of (label, dir): sizes of the staged tables
+  uint32_t tab_cell_base, tab_ref_base; // their first cell / landmark (alignment of the bulk copies)
   int32_t  first, last;             // first / last pass over these chunks: counters start at 0 / are reduced
   int32_t  shard_index, shard_count;
   void    *gcnt;                    // device: per-hypothesis inlier counters carried between passes
