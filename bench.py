@@ -315,7 +315,11 @@ def run_ours(args, rank, world, local_rank):
                     "note": "two distinct map pairs alternate, so every step rebuilds and re-uploads all index structures",
                     "api": "PlaceRecognition.findTransformation -> slide_pr_find_transformation (host buffers)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         # dram__bytes_read + dram__bytes_write of one (label, direction) pass launch, from the
+                         # committed ncu capture profiles/r1_final_score_lattice_summary.txt (the counters
+                         # carried between passes; the maps and index tables stay in L2 / shared memory)
+                         "traffic": 82.3e6, "traffic_source": "profiles/r1_final_score_lattice_summary.txt (ncu --set full, per launch)",
+                         "peak_source": peak_src,
                          "note": "algorithmic 24 B/hypothesis (SURVEY 8d); the kernel is issue-bound on L1/L2-resident bitmaps, "
                                  "see DESIGN.md section 5 for issue-slot utilisation from ncu"},
         }
