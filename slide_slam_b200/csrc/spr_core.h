@@ -183,18 +183,37 @@ SPR_HD uint32_t spr_verify_mask(const SprView &V, const SprTables &T, uint32_t d
                                 double rx, double ry, double across, const double *along, const double *qd) {
   const uint32_t wi = row * T.W + (bit >> 5);
   const uint32_t w0 = T.bits[wi], w1 = T.bits[wi + 1];
-  const uint32_t base = T.row_rank[row];
-  const uint32_t before0 = base + T.r16[wi], before1 = base + T.r16[wi + 1];
   const uint32_t off = bit & 31u;
+  // rank of the cell under chunk bit b = rank0 + marked cells among the window's bits below b
+  const uint32_t rank0 = T.row_rank[row] + T.r16[wi] + (uint32_t)SPR_POPC(w0 & ((1u << off) - 1u));
+  const uint32_t win = SPR_FUNNEL_R(w0, w1, off);  // the 32 cells of the chunk (before the valid mask)
+  // the across coordinate is the same for every bit of the chunk: x' (dir 0) or y' (dir 1) of
+  // PR.cpp:257-258 is computed once; only the along coordinate changes from bit to bit.
+  // dx*dx + dy*dy is evaluated as pa2 + pb2 in either direction (fp64 addition commutes).
+  const double pa = SPR_DADD(d ? ry : rx, across);
+  const double rb = d ? rx : ry;
+  const double *ref_a = T.reftab + (d ? 1 : 0), *ref_b = T.reftab + (d ? 0 : 1);
   uint32_t P = 0u;
   while (H) {
     const int b = SPR_FFS(H) - 1;
     H &= H - 1;
-    const uint32_t pos = off + (uint32_t)b;  // 0..62: the 32 cells span at most two words
-    const uint32_t rank = pos < 32u ? before0 + (uint32_t)SPR_POPC(w0 & ((1u << pos) - 1u))
-                                    : before1 + (uint32_t)SPR_POPC(w1 & ((1u << (pos - 32u)) - 1u));
+    const uint32_t rank = rank0 + (uint32_t)SPR_POPC(win & ((1u << b) - 1u));
+    const uint32_t slot = T.cellref[rank];
     const double t = along[b];
-    if (spr_verify_rank(V, T, d, rank, rx, ry, d ? t : across, d ? across : t, qd)) P |= 1u << b;
+    bool ok;
+    if (slot != SPR_CELL_MULTI) {
+      const uint32_t o = 5u * slot;
+      const double da = SPR_DSUB(ref_a[o], pa);
+      const double db = SPR_DSUB(ref_b[o], SPR_DADD(rb, t));
+      ok = SPR_DADD(SPR_DMUL(da, da), SPR_DMUL(db, db)) < V.Tstar;  // PR.cpp:332-333
+      if (ok && !V.ignore_dim) {
+        const double *r = T.reftab + o;
+        ok = spr_dimension_match(r[2], r[3], r[4], qd, V.thr_dim, V.Sstar);  // PR.cpp:334-339
+      }
+    } else {  // several candidate landmarks: chained records in ascending reference order
+      ok = spr_verify_rank(V, T, d, rank, rx, ry, d ? t : across, d ? across : t, qd);
+    }
+    if (ok) P |= 1u << b;
   }
   return P;
 }

@@ -232,7 +232,13 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
     const int a = (int)(item / n_wg_local);
     const int wg = K.shard_index + (int)(item % n_wg_local) * K.shard_count;
     const uint32_t cidx = K.chunk_begin + (uint32_t)wg * SPR_WARP_CHUNKS + (uint32_t)lane;  // < chunk_end (padded)
-    const SprChunk ch = V.chunks[cidx];
+    SprChunk ch;
+    {
+      const uint4 *cp = reinterpret_cast<const uint4 *>(V.chunks + cidx);
+      const uint4 c0 = __ldcs(cp), c1 = __ldcs(cp + 1);
+      ch.across = __hiloint2double((int)c0.y, (int)c0.x);
+      ch.along_off = c0.z; ch.valid = c0.w; ch.ord_base = c1.x; ch.ord_stride = c1.y; ch.dir = c1.z; ch.ring = c1.w;
+    }
     const double across = ch.across;
     const uint32_t along_off = ch.along_off, valid = ch.valid;
     spr_cnt_zero<CNT32>(ws.cnt, lane);
@@ -254,21 +260,18 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
       const int32_t tx_lo = lb.x0 - X1, tx_hi = lb.x1 - X0, ty_lo = lb.y0 - Y1, ty_hi = lb.y1 - Y0;
       const int4 *gbp = reinterpret_cast<const int4 *>(V.gbox) + ((size_t)a * (size_t)V.n_groups + (size_t)g0);
       const int4 *qgp = reinterpret_cast<const int4 *>(qa2) + (size_t)g0 * (SPR_QGROUP / 2);
-      for (int g = g0; g < g1; g++, gbp++, qgp += SPR_QGROUP / 2) {
-        const int4 box = __ldg(gbp);  // (x0, x1, y0, y1), same address for the whole warp
-        if (!(box.y > tx_lo && box.x < tx_hi && box.w > ty_lo && box.z < ty_hi)) {
-          if (STATS) n_skipped++;
-          continue;
-        }
-        if (STATS) n_probed++;
+      auto probe_group = [&](const int g, const int4 *__restrict__ qgp) {
+        int4 vg[SPR_QGROUP / 2];
+#pragma unroll
+        for (int u = 0; u < SPR_QGROUP / 2; u++) vg[u] = __ldg(qgp + u);
         // the group is probed in halves of SPR_QHALF queries: at most 32 * SPR_QHALF new records
         // per push, so the queue (drained below 32 after every push) cannot overflow
-#pragma unroll 1
+#pragma unroll
         for (int hq = 0; hq < SPR_QGROUP / SPR_QHALF; hq++) {
           uint32_t H[SPR_QHALF];
           int4 v[SPR_QHALF / 2];  // two queries each: (across, along) x 2
 #pragma unroll
-          for (int u = 0; u < SPR_QHALF / 2; u++) v[u] = __ldg(qgp + hq * (SPR_QHALF / 2) + u);
+          for (int u = 0; u < SPR_QHALF / 2; u++) v[u] = vg[hq * (SPR_QHALF / 2) + u];
 #pragma unroll
           for (int u = 0; u < SPR_QHALF / 2; u++) {
             H[2 * u] = spr_probe(T.bits, W, Rm1, maxbit, F, aqb + v[u].x, bqb + v[u].y, SPR_FULL);
@@ -283,9 +286,9 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
 #pragma unroll
             for (int u = 0; u < SPR_QHALF; u++) n_hits += (unsigned long long)__popc(H[u] & valid);
           }
+          const int js0 = g * SPR_QGROUP + hq * SPR_QHALF;
           // one record per (lane, query) with hits; the queue is unordered, so records are laid
           // out query-major and a lane's slot comes from one ballot per query (no shuffle scan)
-          const int js0 = g * SPR_QGROUP + hq * SPR_QHALF;
           const uint32_t lt = (1u << lane) - 1u;
           int base = ws.qcount;
 #pragma unroll
@@ -304,6 +307,21 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
           __syncwarp();
           while (ws.qcount >= 32) spr_drain32<CNT32>(V, T, ws, d, a, lane, along_off, across, n_inl);
         }
+      };
+      // visibility of 32 query groups at a time, one group per lane; only the visible ones are walked
+      for (int gb = g0; gb < g1; gb += 32) {
+        bool vis = false;
+        if (gb + lane < g1) {
+          const int4 box = __ldg(gbp + (gb - g0) + lane);  // (x0, x1, y0, y1)
+          vis = box.y > tx_lo && box.x < tx_hi && box.w > ty_lo && box.z < ty_hi;
+        }
+        uint32_t vm = __ballot_sync(SPR_FULL, vis);
+        if (STATS) { n_probed += __popc(vm); n_skipped += (g1 - gb < 32 ? g1 - gb : 32) - __popc(vm); }
+        while (vm) {
+          const int k = __ffs(vm) - 1;
+          vm &= vm - 1;
+          probe_group(gb + k, qgp + (size_t)(gb - g0 + k) * (SPR_QGROUP / 2));
+        }
       }
       while (ws.qcount > 0) spr_drain32<CNT32>(V, T, ws, d, a, lane, along_off, across, n_inl);
     }
@@ -316,7 +334,7 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
     if (!K.first) {
 #pragma unroll
       for (int w = 0; w < (CNT32 ? 32 : 16); w += 4) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(gw + w);
+        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(gw + w));
         uint32_t *c = ws.cnt + lane * (CNT32 ? 33 : 17) + w;
         c[0] += v.x; c[1] += v.y; c[2] += v.z; c[3] += v.w;
       }
@@ -325,7 +343,7 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
 #pragma unroll
       for (int w = 0; w < (CNT32 ? 32 : 16); w += 4) {
         const uint32_t *c = ws.cnt + lane * (CNT32 ? 33 : 17) + w;
-        *reinterpret_cast<uint4 *>(gw + w) = make_uint4(c[0], c[1], c[2], c[3]);
+        __stcs(reinterpret_cast<uint4 *>(gw + w), make_uint4(c[0], c[1], c[2], c[3]));
       }
     } else {
       uint32_t v = valid;
