@@ -87,7 +87,7 @@ typedef struct slide_pr_match_result {
   int64_t groups_probed;       /* (warp, query group) pairs probed / skipped by the bounding-box test */
   int64_t groups_skipped;      /*   (0 unless stats were enabled) */
   int32_t reuse;               /* bit 0: lattice reused from the previous prepare, bit 1: reference-map index reused */
-  int32_t reserved2;
+  int32_t search_mode;         /* 0: every hypothesis verified exactly (exhaustive); 1: bound-and-verify (same winner) */
 } slide_pr_match_result;
 
 /* Options for the sharded / sliced search (multi-GPU and tests). */
@@ -100,8 +100,11 @@ typedef struct slide_pr_search_opts {
                             counts_out[(t - trans_begin) * n_yaw + iyaw]; needs trans_end >= 0 */
   int64_t counts_cap;    /* capacity of counts_out in entries */
   void   *stream;        /* cudaStream_t to run on; NULL = the handle's own stream */
-  int32_t collect_stats; /* 1: count filter hits (slower) */
-  int32_t reserved;
+  int32_t collect_stats; /* 1: count filter hits (slower; implies exhaustive) */
+  int32_t exhaustive;    /* 1: verify every hypothesis exactly.  0 (default): bound-and-verify -- a cheap upper
+                            bound (bitmap filter hits) for every hypothesis, exact verification only where the
+                            bound reaches the running best; the winner, its count and its correspondences are
+                            the same.  counts_out / collect_stats / compute_budget_sec > 0 imply exhaustive. */
 } slide_pr_search_opts;
 
 typedef struct slide_pr_tf_result {

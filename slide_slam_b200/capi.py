@@ -77,7 +77,7 @@ class MatchResult(C.Structure):
         ("groups_probed", C.c_int64),
         ("groups_skipped", C.c_int64),
         ("reuse", C.c_int32),
-        ("reserved2", C.c_int32),
+        ("search_mode", C.c_int32),
     ]
 
 
@@ -91,7 +91,7 @@ class SearchOpts(C.Structure):
         ("counts_cap", C.c_int64),
         ("stream", C.c_void_p),
         ("collect_stats", C.c_int32),
-        ("reserved", C.c_int32),
+        ("exhaustive", C.c_int32),
     ]
 
 

@@ -42,6 +42,24 @@ double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// SLIDE_PR_TRACE=1: per-phase host timings of every call on stderr (developer aid)
+struct Trace {
+  bool on = std::getenv("SLIDE_PR_TRACE") != nullptr;
+  double t0 = 0, last = 0;
+  std::string line;
+  void start() { if (on) { t0 = last = now_ms(); line.clear(); } }
+  void mark(const char *what) {
+    if (!on) return;
+    const double t = now_ms();
+    char buf[96];
+    std::snprintf(buf, sizeof(buf), " %s=%.3f", what, t - last);
+    line += buf;
+    last = t;
+  }
+  void flush(const char *call) { if (on) std::fprintf(stderr, "[slide_pr] %s total=%.3f ms:%s\n", call, now_ms() - t0, line.c_str()); }
+};
+thread_local Trace g_trace;
+
 }  // namespace
 
 struct slide_pr_handle {
@@ -49,6 +67,7 @@ struct slide_pr_handle {
   int device = 0;
   int sm_count = 148;
   int tables_mode = SPR_TABLES_AUTO;
+  bool force_exhaustive = false;  // env SLIDE_PR_EXHAUSTIVE=1
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
@@ -75,7 +94,7 @@ struct slide_pr_handle {
   spr::QuerySet Q;
   // device side
   DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_rank16, d_rank16b, d_rowrank, d_rowrankb, d_gcnt, d_cellref, d_cellrefb, d_cellbase, d_cellbaseb, d_reftab, d_refbase,
-      d_cand, d_cand1, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
+      d_cand, d_cand1, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ubplanes, d_itemub, d_seed, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
   SprView V{};
   std::vector<int32_t> h_match;
 };
@@ -159,6 +178,8 @@ int slide_pr_create(const slide_pr_params *p, slide_pr_handle **out) {
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
   // SLIDE_PR_VARIANT=0 forces the global-memory table path (tests cover both paths)
   if (const char *v = std::getenv("SLIDE_PR_VARIANT")) h->tables_mode = std::atoi(v) == 0 ? SPR_TABLES_GLOBAL : SPR_TABLES_AUTO;
+  // SLIDE_PR_EXHAUSTIVE=1 verifies every hypothesis exactly (no bound-and-verify pruning)
+  if (const char *v = std::getenv("SLIDE_PR_EXHAUSTIVE")) h->force_exhaustive = std::atoi(v) != 0;
   *out = h;
   return SLIDE_PR_OK;
 }
@@ -226,7 +247,9 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
     if ((rc = spr::build_lattice(h->p, half_x, half_y, h->yaw_half, 0, -1, h->p.compute_budget_sec > 0, h->L, h->err)) != SLIDE_PR_OK) return rc;
     h->lat_hx = half_x; h->lat_hy = half_y; h->lat_yaw_half = h->yaw_half; h->lat_p = h->p;
     h->lattice_valid = true;
+    g_trace.mark("lattice_build");
     if ((rc = upload_lattice(h, st))) return rc;
+    g_trace.mark("lattice_upload");
   } else {
     h->reuse_flags |= 1;
   }
@@ -247,6 +270,7 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
     h->ref_index_valid = false;
     const double reach_cap = reach * 1.25;  // head-room so that slightly larger queries reuse the index
     if ((rc = spr::build_ref_index(h->p, ref7, n_ref, reach_cap, h->R, h->err)) != SLIDE_PR_OK) return rc;
+    g_trace.mark("ref_index_build");
     h->cached_ref.assign(ref7, ref7 + (size_t)n_ref * 7);
     h->cached_reach = reach_cap; h->cached_ref_p = h->p;
     h->ref_index_valid = true;
@@ -265,10 +289,12 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
     if ((rc = upload(h, h->d_cand, h->R.cand[0], st))) return rc;
     if ((rc = upload(h, h->d_cand1, h->R.cand[1], st))) return rc;
     if ((rc = upload_raw(h, h->d_ref7, ref7, (size_t)n_ref * 7 * sizeof(double), st))) return rc;
+    g_trace.mark("ref_index_upload");
   } else {
     h->reuse_flags |= 2;
   }
   if ((rc = spr::build_query_set(h->R, qry7, n_qry, h->Q, h->err)) != SLIDE_PR_OK) return rc;
+  g_trace.mark("query_set_build");
   if ((rc = upload(h, h->d_qxy, h->Q.qxy, st))) return rc;
   if ((rc = upload(h, h->d_qdims, h->Q.qdims, st))) return rc;
   if ((rc = upload(h, h->d_labelseg, h->Q.label_gseg, st))) return rc;
@@ -321,6 +347,7 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   // returns, and the host index vectors stay alive in the handle until the next prepare
   h->prepared = true;
   h->prepare_ms = now_ms() - t0;
+  g_trace.mark("query_upload");
   return SLIDE_PR_OK;
 }
 
@@ -399,6 +426,55 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     SPR_CUDA(h, h->d_gcnt.ensure((size_t)n_yaw * (size_t)K.n_chunks_total * 32 * per + 64));
   }
   K.gcnt = h->d_gcnt.p;
+  auto next_counter = [&]() -> int {  // (re)arm a batch of work-item counters with a single memset
+    if (passes_left == 0) {
+      passes_left = 4096;
+      K.work_counter = h->d_work.as<unsigned long long>();
+      SPR_CUDA(h, cudaMemsetAsync(h->d_work.p, 0, 4096 * sizeof(unsigned long long), st));
+    }
+    return SLIDE_PR_OK;
+  };
+  // bound-and-verify (default): upper bounds of all hypotheses first, then exact verification of
+  // those whose bound reaches the running best.  Exhaustive verification of every hypothesis
+  // when per-hypothesis counts / statistics are requested, with a compute budget (ring by ring),
+  // or on request (opts.exhaustive).
+  const bool prune = !o.exhaustive && !o.counts_out && !o.collect_stats && h->p.compute_budget_sec <= 0 && active[0] >= 0 &&
+                     h->V.nqp > 0 && h->V.nqp < 65536 && !h->force_exhaustive;
+  if (prune) {
+    const int n_planes = spr_bound_planes(h->V.nqp);
+    const size_t n_wg_total = K.n_chunks_total / SPR_WARP_CHUNKS;
+    SPR_CUDA(h, h->d_ubplanes.ensure((size_t)n_yaw * n_wg_total * (size_t)n_planes * 32 * sizeof(uint32_t) + 64));
+    SPR_CUDA(h, h->d_itemub.ensure((size_t)n_yaw * n_wg_total * sizeof(uint32_t) + 64));
+    SPR_CUDA(h, h->d_seed.ensure((size_t)n_yaw * sizeof(unsigned long long)));
+    SPR_CUDA(h, cudaMemsetAsync(h->d_seed.p, 0, (size_t)n_yaw * sizeof(unsigned long long), st));
+    SprBoundLaunch B{};
+    B.n_chunks_total = K.n_chunks_total;
+    B.shard_index = o.shard_index; B.shard_count = o.shard_count;
+    B.planes = h->d_ubplanes.as<uint32_t>();
+    B.item_ub = h->d_itemub.as<uint32_t>();
+    B.seed_key = h->d_seed.as<unsigned long long>();
+    for (uint32_t d = 0; d < 2; d++) {
+      if (h->L.dir_end[d] <= h->L.dir_begin[d]) continue;
+      int per = spr_bound_labels_per_launch(h->V, d);
+      if (per <= 0) per = SPR_BOUND_MAX_LABELS;  // planes too large for shared memory: read in place
+      for (size_t i = 0; i < active.size(); i += (size_t)per) {
+        B.chunk_begin = h->L.dir_begin[d]; B.chunk_end = h->L.dir_end[d]; B.dir = d;
+        B.n_labels = (int32_t)std::min<size_t>((size_t)per, active.size() - i);
+        for (int k = 0; k < B.n_labels; k++) B.labels[k] = active[i + (size_t)k];
+        B.first = i == 0; B.last = i + (size_t)per >= active.size();
+        if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
+        B.work_counter = K.work_counter;
+        SPR_CUDA(h, spr_launch_bound_lattice(h->V, B, n_planes, h->sm_count, st, &launches));
+        K.work_counter++;
+        passes_left--;
+      }
+    }
+    SPR_CUDA(h, spr_launch_seed(h->V, h->d_seed.as<unsigned long long>(), K.best_key, st));
+    launches++;
+    K.ub_planes = h->d_ubplanes.as<uint32_t>();
+    K.item_ub = h->d_itemub.as<uint32_t>();
+    K.ub_nplanes = n_planes;
+  }
   auto run_range = [&](const uint32_t begin[2], const uint32_t end[2]) -> int {
     for (uint32_t d = 0; d < 2; d++) {
       if (end[d] <= begin[d]) continue;
@@ -409,11 +485,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
         K.tab_refs = K.label >= 0 ? h->R.ref_base[K.label + 1] - h->R.ref_base[K.label] : 0u;
         K.tab_cell_base = K.label >= 0 ? h->R.cell_base[d][K.label] : 0u;
         K.tab_ref_base = K.label >= 0 ? h->R.ref_base[K.label] : 0u;
-        if (passes_left == 0) {  // (re)arm a batch of counters with a single memset
-          passes_left = 4096;
-          K.work_counter = h->d_work.as<unsigned long long>();
-          SPR_CUDA(h, cudaMemsetAsync(h->d_work.p, 0, 4096 * sizeof(unsigned long long), st));
-        }
+        if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
         SPR_CUDA(h, spr_launch_score_lattice(h->V, K, h->tables_mode, h->sm_count, st, &launches));
         K.work_counter++;
         passes_left--;
@@ -438,16 +510,19 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     rings_scored = h->L.rings;
   }
   SPR_CUDA(h, cudaEventRecord(h->ev1, st));
+  g_trace.mark("search_launch");
   unsigned long long key = 0, stats[4] = {0, 0, 0, 0};
   SPR_CUDA(h, cudaMemcpyAsync(&key, h->d_best.p, sizeof(key), cudaMemcpyDeviceToHost, st));
   if (o.collect_stats) SPR_CUDA(h, cudaMemcpyAsync(stats, h->d_stats.p, sizeof(stats), cudaMemcpyDeviceToHost, st));
   if (o.counts_out && n_counts > 0)
     SPR_CUDA(h, cudaMemcpyAsync(o.counts_out, h->d_counts.p, (size_t)n_counts * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   SPR_CUDA(h, cudaStreamSynchronize(st));
+  g_trace.mark("search_sync");
   float ms = 0;
   SPR_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   out->kernel_ms = ms;
   out->gpu_launches = launches;
+  out->search_mode = prune ? 1 : 0;
   out->rings_scored = rings_scored;
   out->filter_hits = (int64_t)stats[0];
   out->groups_probed = (int64_t)stats[2];
@@ -510,6 +585,7 @@ int slide_pr_extract(slide_pr_handle *h, int64_t hyp_index, int32_t *ref_idx_out
   h->h_match.resize(std::max(h->n_qry, 1));
   SPR_CUDA(h, cudaMemcpyAsync(h->h_match.data(), h->d_match.p, (size_t)h->n_qry * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   SPR_CUDA(h, cudaStreamSynchronize(st));
+  g_trace.mark("extract");
   int k = 0;
   for (int j = 0; j < h->n_qry; j++)
     if (h->h_match[j] >= 0) {
@@ -554,6 +630,7 @@ int slide_pr_find_transformation(slide_pr_handle *h, const double *ref7_in, int3
   if (!h || !out) return SLIDE_PR_ERR_INVALID;
   if (n_ref < 0 || n_qry < 0 || (n_ref > 0 && !ref7_in) || (n_qry > 0 && !qry7_in)) { h->err = "bad map arguments"; return SLIDE_PR_ERR_INVALID; }
   std::memset(out, 0, sizeof(*out));
+  g_trace.start();
   std::vector<double> ref(ref7_in, ref7_in + (size_t)n_ref * 7), qry(qry7_in, qry7_in + (size_t)n_qry * 7);
   double cref[2] = {0, 0}, cqry[2] = {0, 0};
   double half_x, half_y;
@@ -590,7 +667,9 @@ int slide_pr_find_transformation(slide_pr_handle *h, const double *ref7_in, int3
   int32_t *ri = ref_idx_out, *qi = qry_idx_out;
   if (!ri) { ri_own.resize(std::max(n_qry, 1)); ri = ri_own.data(); }
   if (!qi) { qi_own.resize(std::max(n_qry, 1)); qi = qi_own.data(); }
+  g_trace.mark("centroid_shift");
   int rc = slide_pr_match_maps(h, ref.data(), n_ref, qry.data(), n_qry, half_x, half_y, ri, qi, &out->match);
+  g_trace.flush("find_transformation");
   if (rc != SLIDE_PR_OK) return rc;
   const slide_pr_match_result &m = out->match;
   std::memcpy(out->R_t, m.R_t, sizeof(m.R_t));
@@ -832,6 +911,7 @@ int slide_pr_score_hypotheses(slide_pr_handle *h, const double *hyps4, int64_t n
   SPR_CUDA(h, cudaMemcpyAsync(&key, h->d_best.p, sizeof(key), cudaMemcpyDeviceToHost, st));
   if (counts_out) SPR_CUDA(h, cudaMemcpyAsync(counts_out, h->d_counts.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   SPR_CUDA(h, cudaStreamSynchronize(st));
+  g_trace.mark("search_sync");
   float ms = 0;
   SPR_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   out->kernel_ms = ms;

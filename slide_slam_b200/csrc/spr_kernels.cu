@@ -240,7 +240,26 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
       ch.along_off = c0.z; ch.valid = c0.w; ch.ord_base = c1.x; ch.ord_stride = c1.y; ch.dir = c1.z; ch.ring = c1.w;
     }
     const double across = ch.across;
-    const uint32_t along_off = ch.along_off, valid = ch.valid;
+    const uint32_t along_off = ch.along_off;
+    uint32_t valid = ch.valid;
+    if (K.ub_nplanes) {
+      // bound-and-verify: keep only the hypotheses whose upper bound reaches the running best
+      // (>=: an equal count with a smaller canonical index would still win the tie).  The best only
+      // grows, so a hypothesis dropped in one label pass stays dropped in the later ones.
+      const long long bc = (long long)(*reinterpret_cast<volatile unsigned long long *>(K.best_key) >> SPR_KEY_IDX_BITS) - 1;
+      const uint32_t tau = bc > 0 ? (uint32_t)bc : 0u;
+      const size_t ii = (size_t)a * (size_t)(K.n_chunks_total / SPR_WARP_CHUNKS) + (size_t)(cidx / SPR_WARP_CHUNKS);
+      if (__ldg(K.item_ub + ii) < tau) continue;
+      const uint32_t *up = K.ub_planes + (ii * (size_t)K.ub_nplanes) * 32 + lane;
+      uint32_t gt = 0u, eq = 0xffffffffu;  // plane-wise compare of the 32 bounds with tau, MSB first
+      if ((tau >> K.ub_nplanes) != 0u) eq = 0u;
+      for (int i = K.ub_nplanes - 1; i >= 0; i--) {
+        const uint32_t p = __ldcs(up + i * 32);
+        if ((tau >> i) & 1u) eq &= p;
+        else gt |= eq & p;
+      }
+      valid &= gt | eq;
+    }
     spr_cnt_zero<CNT32>(ws.cnt, lane);
     const int32_t aq0 = spr_fx(across, G.S);
     const int32_t bq0 = spr_fx(__ldg(V.lat + along_off), G.S);

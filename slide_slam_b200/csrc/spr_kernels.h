@@ -25,6 +25,29 @@ struct SprLaunch {
   unsigned long long ord_begin;
   unsigned long long *stats;        // device, optional: [0] filter hits, [1] verified inliers,
                                     //                   [2] query groups probed, [3] query groups skipped
+  // bound-and-verify (optional): upper bounds from spr_launch_bound_lattice.  A hypothesis is
+  // verified only while its bound reaches the inlier count of the running best (*best_key).
+  const uint32_t *ub_planes;        // device: [yaw][chunk / 32][ub_nplanes][32 lanes] bit planes of the bounds
+  const uint32_t *item_ub;          // device: [yaw][chunk / 32] largest bound of the work item
+  int32_t ub_nplanes;               // 0: exhaustive search
+  int32_t pad;
+};
+
+// One launch of the bound phase = one bitmap direction x a set of labels whose planes are staged
+// together in shared memory, over a range of chunks.
+#define SPR_BOUND_MAX_LABELS 8
+struct SprBoundLaunch {
+  uint32_t chunk_begin, chunk_end;  // chunks of direction `dir` (multiple of 32 apart)
+  uint32_t n_chunks_total;
+  uint32_t dir;
+  int32_t  n_labels;
+  int32_t  labels[SPR_BOUND_MAX_LABELS];
+  int32_t  first, last;             // first / last launch over these chunks: planes start at 0 / item maxima are produced
+  int32_t  shard_index, shard_count;
+  uint32_t *planes;                 // device: bit planes of the bounds (layout of SprLaunch::ub_planes)
+  uint32_t *item_ub;                // device: [yaw][chunk / 32]
+  unsigned long long *seed_key;     // device: [n_yaw] (bound + 1) << 40 | chunk * 32 + bit of the best-bounded hypothesis
+  unsigned long long *work_counter; // device: next work item (zeroed by the caller)
 };
 
 enum { SPR_TABLES_GLOBAL = 0, SPR_TABLES_AUTO = 1 };  // AUTO: shared-memory-resident plane when it fits
@@ -37,6 +60,15 @@ cudaError_t spr_launch_rotate(const SprView &V, int32_t *qrotq_xy, int32_t *qrot
 // one (label, direction) pass of the lattice search
 cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int tables_mode, int sm_count,
                                      cudaStream_t st, int *n_launches);
+
+// bound phase of the bound-and-verify search (spr_kernels_bound.cu)
+int spr_bound_planes(int nqp);                                   // bit planes needed for counts <= nqp (12 or 16)
+int spr_bound_labels_per_launch(const SprView &V, uint32_t dir); // label planes that fit in shared memory (0: none)
+cudaError_t spr_launch_bound_lattice(const SprView &V, const SprBoundLaunch &B, int n_planes, int sm_count, cudaStream_t st,
+                                     int *n_launches);
+// exact score of the best-bounded hypothesis of every yaw -> atomicMax on best_key
+cudaError_t spr_launch_seed(const SprView &V, const unsigned long long *seed_key, unsigned long long *best_key,
+                            cudaStream_t st);
 
 // explicit hypothesis list (c, s, x, y), warp per hypothesis
 cudaError_t spr_launch_score_list(const SprView &V, const double *hyps4, long long n, int32_t *counts_out,

@@ -1,0 +1,290 @@
+// spr_kernels_bound.cu -- upper bounds for the bound-and-verify lattice search.
+//
+// MatchMaps only returns the best hypothesis (place_recognition.cpp:361-386).  The number of query
+// landmarks whose occupancy-bitmap probe hits -- the conservative filter that precedes every exact
+// test in spr_kernels.cu -- is an UPPER BOUND of a hypothesis' inlier count, and it costs a third of
+// the exact count (no hit queue, no fp64).  The search therefore runs in two phases:
+//   1. this file: the bound of every hypothesis (same probes, same visibility culling as the exact
+//      kernel), kept bit-sliced in registers -- plane i holds bit i of the 32 counters a lane owns,
+//      adding a probe result is a handful of LOP3 -- and stored as bit planes; the best-bounded
+//      hypothesis of every yaw is scored exactly (spr_seed_kernel) to seed the running best;
+//   2. spr_score_lattice_kernel verifies exactly only the hypotheses whose bound reaches the
+//      running best (a plane-wise compare builds the lane's candidate mask), so the winner -- max
+//      count, ties to the smallest canonical index -- is the one the exhaustive search finds.
+// Several labels are handled per launch: their bitmap planes are staged together in shared
+// memory with TMA bulk copies (as many as fit), the counters never leave the registers in between.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "spr_core.h"
+#include "spr_kernels.h"
+
+#define SPR_FULL 0xffffffffu
+#define SPR_SMEM_LIMIT (227 * 1024)
+
+__device__ __forceinline__ uint32_t spb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void spb_mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(spb_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void spb_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(spb_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void spb_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(spb_smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(spb_smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool spb_mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(spb_smem_addr(bar)), "r"(parity)
+               : "memory");
+  return ok != 0u;
+}
+
+// full adder on 32 independent bit positions
+__device__ __forceinline__ void spb_fa(uint32_t a, uint32_t b, uint32_t c, uint32_t &s, uint32_t &cy) {
+  s = a ^ b ^ c;
+  cy = (a & b) | (c & (a ^ b));
+}
+
+template <int PLANES, bool SMEM_TAB>
+__global__ void __launch_bounds__(SMEM_TAB ? 1024 : 256, SMEM_TAB ? 1 : 4)
+spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constant__ SprBoundLaunch B, const int n_wg_local,
+                         const long long n_items) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int lane = threadIdx.x & 31;
+  const SprGrid &G = V.grid;
+  const int32_t F = G.F;
+  const uint32_t d = B.dir;
+  const uint32_t W = (uint32_t)G.W[d], Rm1 = (uint32_t)G.R[d] - 1u, maxbit = (uint32_t)G.maxbit[d];
+  const uint32_t PW = G.plane_words[d];
+
+  if (SMEM_TAB) {  // the bitmap planes of this launch's labels, one TMA bulk copy each
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)B.n_labels * PW);
+    if (threadIdx.x == 0) {
+      spb_mbar_init(bar, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      spb_mbar_expect_tx(bar, (uint32_t)B.n_labels * PW * 4u);
+      for (int k = 0; k < B.n_labels; k++)
+        spb_bulk_g2s(smem + (size_t)k * PW, V.bitmap + ((size_t)B.labels[k] * G.label_stride + (d ? G.plane_words[0] : 0u)), PW * 4u, bar);
+    }
+    for (uint32_t spin = 0; !spb_mbar_try_wait(bar, 0u); spin++)
+      if (spin > 200000000u) __trap();  // a lost copy must not hang the GPU
+  }
+  const int32_t *q_fx = d ? V.qrotq_yx : V.qrotq_xy;
+  const uint32_t n_wg_total = B.n_chunks_total / SPR_WARP_CHUNKS;
+
+  for (;;) {
+    long long item = 0;
+    if (lane == 0) item = (long long)atomicAdd(B.work_counter, 1ull);
+    item = __shfl_sync(SPR_FULL, item, 0);
+    if (item >= n_items) break;
+    const int a = (int)(item / n_wg_local);
+    const int wg = B.shard_index + (int)(item % n_wg_local) * B.shard_count;
+    const uint32_t cidx = B.chunk_begin + (uint32_t)wg * SPR_WARP_CHUNKS + (uint32_t)lane;
+    const uint4 *cp = reinterpret_cast<const uint4 *>(V.chunks + cidx);
+    const uint4 c0 = __ldcs(cp);
+    const double across = __hiloint2double((int)c0.y, (int)c0.x);
+    const uint32_t along_off = c0.z, valid = c0.w;
+    const int32_t aq0 = spr_fx(across, G.S);
+    const int32_t bq0 = spr_fx(__ldg(V.lat + along_off), G.S);
+    const int32_t aqb = spr_bias_across(aq0, F), bqb = spr_bias_along(bq0, F);
+    const int32_t big = 1 << 30;
+    const bool live = valid != 0u;
+    const int32_t lx0 = d ? bq0 : aq0, lx1 = d ? bq0 + (32 << F) : aq0;
+    const int32_t ly0 = d ? aq0 : bq0, ly1 = d ? aq0 : bq0 + (32 << F);
+    const int32_t X0 = __reduce_min_sync(SPR_FULL, live ? lx0 : big), X1 = __reduce_max_sync(SPR_FULL, live ? lx1 : -big);
+    const int32_t Y0 = __reduce_min_sync(SPR_FULL, live ? ly0 : big), Y1 = __reduce_max_sync(SPR_FULL, live ? ly1 : -big);
+
+    // bit-sliced counters: P[i] = bit i of the 32 bounds of this lane's chunk
+    uint32_t P[PLANES];
+    uint32_t *gp = B.planes + (((size_t)a * n_wg_total + cidx / SPR_WARP_CHUNKS) * PLANES) * 32 + lane;
+    if (B.first) {
+#pragma unroll
+      for (int i = 0; i < PLANES; i++) P[i] = 0u;
+    } else {
+#pragma unroll
+      for (int i = 0; i < PLANES; i++) P[i] = __ldcs(gp + i * 32);
+    }
+
+    if (X0 <= X1) {
+      for (int k = 0; k < B.n_labels; k++) {
+        const int l = B.labels[k];
+        const int g0 = V.label_gseg[l], g1 = V.label_gseg[l + 1];
+        if (g0 >= g1) continue;
+        const uint32_t *bits = SMEM_TAB ? smem + (size_t)k * PW
+                                        : V.bitmap + ((size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u));
+        const SprBox lb = V.labelbox[l];
+        const int32_t tx_lo = lb.x0 - X1, tx_hi = lb.x1 - X0, ty_lo = lb.y0 - Y1, ty_hi = lb.y1 - Y0;
+        const int4 *gbp = reinterpret_cast<const int4 *>(V.gbox) + ((size_t)a * (size_t)V.n_groups + (size_t)g0);
+        const int4 *qgp = reinterpret_cast<const int4 *>(q_fx + 2 * (size_t)a * (size_t)V.nqp) + (size_t)g0 * (SPR_QGROUP / 2);
+        uint32_t A0 = 0u, A1 = 0u, A2 = 0u, A3 = 0u, A4 = 0u;  // low accumulator: up to 3 groups of 8
+        int nA = 0;
+        auto flush = [&]() {
+          uint32_t c = P[0] & A0;
+          P[0] ^= A0;
+          spb_fa(P[1], A1, c, P[1], c);
+          spb_fa(P[2], A2, c, P[2], c);
+          spb_fa(P[3], A3, c, P[3], c);
+          spb_fa(P[4], A4, c, P[4], c);
+#pragma unroll
+          for (int i = 5; i < PLANES; i++) {
+            const uint32_t t = P[i] & c;
+            P[i] ^= c;
+            c = t;
+          }
+          A0 = A1 = A2 = A3 = A4 = 0u;
+          nA = 0;
+        };
+        for (int gb = g0; gb < g1; gb += 32) {
+          bool vis = false;
+          if (gb + lane < g1) {
+            const int4 box = __ldg(gbp + (gb - g0) + lane);  // (x0, x1, y0, y1)
+            vis = box.y > tx_lo && box.x < tx_hi && box.w > ty_lo && box.z < ty_hi;
+          }
+          uint32_t vm = __ballot_sync(SPR_FULL, vis);
+          while (vm) {
+            const int kk = __ffs(vm) - 1;
+            vm &= vm - 1;
+            const int4 *q = qgp + (size_t)(gb - g0 + kk) * (SPR_QGROUP / 2);
+            int4 v[SPR_QGROUP / 2];
+#pragma unroll
+            for (int u = 0; u < SPR_QGROUP / 2; u++) v[u] = __ldg(q + u);
+            uint32_t H[SPR_QGROUP];
+#pragma unroll
+            for (int u = 0; u < SPR_QGROUP / 2; u++) {
+              H[2 * u] = spr_probe(bits, W, Rm1, maxbit, F, aqb + v[u].x, bqb + v[u].y, SPR_FULL);
+              H[2 * u + 1] = spr_probe(bits, W, Rm1, maxbit, F, aqb + v[u].z, bqb + v[u].w, SPR_FULL);
+            }
+            // 8 one-bit addends -> ones / twos / fours / eights
+            uint32_t s0, c0_, s1, c1, s2, c2, t0, f0;
+            spb_fa(H[0], H[1], H[2], s0, c0_);
+            spb_fa(H[3], H[4], H[5], s1, c1);
+            spb_fa(H[6], H[7], s0, s2, c2);
+            const uint32_t o = s1 ^ s2, c3 = s1 & s2;
+            spb_fa(c0_, c1, c2, t0, f0);
+            const uint32_t t = t0 ^ c3, f1 = t0 & c3;
+            const uint32_t f = f0 ^ f1, e = f0 & f1;
+            uint32_t c = A0 & o;
+            A0 ^= o;
+            spb_fa(A1, t, c, A1, c);
+            spb_fa(A2, f, c, A2, c);
+            spb_fa(A3, e, c, A3, c);
+            A4 ^= c;
+            if (++nA == 3) flush();
+          }
+        }
+        if (nA) flush();
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PLANES; i++) {
+      P[i] &= valid;
+      __stcs(gp + i * 32, P[i]);
+    }
+    if (B.last) {
+      // largest bound of the lane (MSB-first narrowing of the candidate bits), then of the warp
+      uint32_t cand = valid, val = 0u;
+#pragma unroll
+      for (int i = PLANES - 1; i >= 0; i--) {
+        const uint32_t t = cand & P[i];
+        if (t) { cand = t; val |= 1u << i; }
+      }
+      const uint32_t packed = live ? ((val << 5) | (uint32_t)(__ffs(cand) - 1)) : 0u;
+      const uint32_t wmax = __reduce_max_sync(SPR_FULL, packed);
+      const uint32_t who = __ballot_sync(SPR_FULL, packed == wmax && live);
+      if (lane == 0) B.item_ub[(size_t)a * n_wg_total + cidx / SPR_WARP_CHUNKS] = wmax >> 5;
+      if (who && lane == __ffs(who) - 1)
+        atomicMax(B.seed_key + a, ((unsigned long long)(val + 1u) << SPR_KEY_IDX_BITS) |
+                                      ((unsigned long long)cidx * 32ull + (unsigned long long)(packed & 31u)));
+    }
+    __syncwarp();
+  }
+}
+
+// Exact score of the best-bounded hypothesis of every yaw candidate (one warp each): seeds the
+// running best of the verification phase.  Same decision code as the hypothesis-list scorer.
+__global__ void __launch_bounds__(256)
+spr_seed_kernel(const SprView V, const unsigned long long *__restrict__ seed_key, unsigned long long *best_key) {
+  const int lane = threadIdx.x & 31;
+  const int a = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (a >= V.n_yaw) return;
+  const unsigned long long sk = seed_key[a];
+  if (sk == 0ull) return;
+  const unsigned long long loc = sk & SPR_KEY_IDX_MASK;
+  const SprChunk ch = V.chunks[loc >> 5];
+  const int b = (int)(loc & 31ull);
+  const double t = V.lat[ch.along_off + b];
+  const double tx = ch.dir ? t : ch.across, ty = ch.dir ? ch.across : t;
+  int cnt = 0;
+  for (int js = lane; js < V.nqp; js += 32) {
+    const int l = V.qlabel[js];
+    if (l < 0) continue;  // padding
+    const double rx = V.qrot[2 * ((size_t)a * (size_t)V.nqp + (size_t)js)], ry = V.qrot[2 * ((size_t)a * (size_t)V.nqp + (size_t)js) + 1];
+    const double xt = SPR_DADD(rx, tx), yt = SPR_DADD(ry, ty);
+    uint32_t row, bit;
+    if (spr_point_cell(V, l, xt, yt, &row, &bit) &&
+        spr_verify_cell(V, spr_global_tables(V, 0u, l), 0u, row, bit, rx, ry, tx, ty, V.qdims + 3 * (size_t)js))
+      cnt++;
+  }
+#pragma unroll
+  for (int dlt = 16; dlt > 0; dlt >>= 1) cnt += __shfl_xor_sync(SPR_FULL, cnt, dlt);
+  if (lane == 0) {
+    const unsigned long long ord = (unsigned long long)ch.ord_base + (unsigned long long)b * ch.ord_stride;
+    atomicMax(best_key, spr_make_key((uint32_t)cnt, ord * (unsigned long long)V.n_yaw + (unsigned long long)a));
+  }
+}
+
+cudaError_t spr_launch_seed(const SprView &V, const unsigned long long *seed_key, unsigned long long *best_key,
+                            cudaStream_t st) {
+  if (V.n_yaw <= 0 || V.nqp <= 0) return cudaSuccess;
+  spr_seed_kernel<<<(V.n_yaw + 7) / 8, 256, 0, st>>>(V, seed_key, best_key);
+  return cudaGetLastError();
+}
+
+int spr_bound_planes(int nqp) { return nqp < 4096 ? 12 : 16; }
+
+int spr_bound_labels_per_launch(const SprView &V, uint32_t dir) {
+  const size_t pb = (size_t)V.grid.plane_words[dir] * 4;
+  const int fit = (int)((SPR_SMEM_LIMIT - 64) / (pb ? pb : 1));
+  return fit < 1 ? 0 : (fit > SPR_BOUND_MAX_LABELS ? SPR_BOUND_MAX_LABELS : fit);
+}
+
+template <int PLANES>
+static cudaError_t spb_launch(const SprView &V, const SprBoundLaunch &B, int n_wg_local, long long n_items, int sm_count,
+                              cudaStream_t st) {
+  const size_t pb = (size_t)V.grid.plane_words[B.dir] * 4;
+  const size_t smem = (size_t)B.n_labels * pb + 16;
+  if (smem <= SPR_SMEM_LIMIT) {
+    cudaError_t e = cudaFuncSetAttribute(spr_bound_lattice_kernel<PLANES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long want = (n_items + 31) / 32;
+    spr_bound_lattice_kernel<PLANES, true><<<(int)(want < sm_count ? want : sm_count), 1024, smem, st>>>(V, B, n_wg_local, n_items);
+  } else {
+    const long long want = (n_items + 7) / 8, cap = (long long)sm_count * 4;
+    spr_bound_lattice_kernel<PLANES, false><<<(int)(want < cap ? want : cap), 256, 0, st>>>(V, B, n_wg_local, n_items);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t spr_launch_bound_lattice(const SprView &V, const SprBoundLaunch &B, int n_planes, int sm_count, cudaStream_t st,
+                                     int *n_launches) {
+  if (B.chunk_end <= B.chunk_begin || V.n_yaw <= 0 || B.n_labels <= 0) return cudaSuccess;
+  const int n_wg = (int)((B.chunk_end - B.chunk_begin) / SPR_WARP_CHUNKS);
+  const int sc = B.shard_count > 1 ? B.shard_count : 1;
+  const int si = B.shard_count > 1 ? B.shard_index : 0;
+  const int n_wg_local = n_wg > si ? (n_wg - si + sc - 1) / sc : 0;
+  if (n_wg_local <= 0) return cudaSuccess;
+  SprBoundLaunch B2 = B;
+  B2.shard_index = si;
+  B2.shard_count = sc;
+  const long long n_items = (long long)n_wg_local * V.n_yaw;
+  if (n_launches) (*n_launches)++;
+  return n_planes == 12 ? spb_launch<12>(V, B2, n_wg_local, n_items, sm_count, st)
+                        : spb_launch<16>(V, B2, n_wg_local, n_items, sm_count, st);
+}

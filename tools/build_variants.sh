@@ -8,6 +8,6 @@ NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c+
 for cfg in "$@"; do
   tag=$(echo "$cfg" | tr ' =-' '___' | tr -d 'D')
   $NV $cfg -c -o /tmp/spr_kernels_$tag.o spr_kernels.cu
-  $NV -shared -o ../../variants/libslide_pr_$tag.so spr_host.o /tmp/spr_kernels_$tag.o spr_kernels_aux.o spr_api.o -cudart static
+  $NV -shared -o ../../variants/libslide_pr_$tag.so spr_host.o /tmp/spr_kernels_$tag.o spr_kernels_bound.o spr_kernels_aux.o spr_api.o -cudart static
   echo "built variants/libslide_pr_$tag.so"
 done

@@ -14,7 +14,7 @@ ROS = {"search_xy_step_size": 0.5, "search_yaw_step_size_degrees": 5.0, "match_t
        "match_threshold_dimension": 1.0, "ignore_dimension": 0, "min_num_inliers": 15}
 
 
-def run(cfg, variant, n=None, reps=3, stats=False):
+def run(cfg, variant, n=None, reps=3, stats=False, exhaustive=False):
     os.environ["SLIDE_PR_VARIANT"] = str(variant)
     pr = PlaceRecognition(ROS)
     ref, qry, truth = synth.config_pair(cfg, n)
@@ -27,10 +27,10 @@ def run(cfg, variant, n=None, reps=3, stats=False):
     pr.prepare(sref, sqry, info.half_x, info.half_y)
     ms = []
     for _ in range(reps):
-        res, _ = pr.search(collect_stats=stats)
+        res, _ = pr.search(collect_stats=stats, exhaustive=exhaustive)
         ms.append(res.kernel_ms)
     hyp = info.match.hypotheses_scored
-    print(f"cfg{cfg} n={len(ref)} variant={variant} found={found} best={info.best_num_inliers} hyp={hyp} "
+    print(f"cfg{cfg} n={len(ref)} variant={variant} mode={res.search_mode} best_search={res.best_num_inliers} idx={res.best_hyp_index} found={found} best={info.best_num_inliers} hyp={hyp} "
           f"kernel_ms={min(ms):.3f} ({hyp / min(ms) * 1e3:.3e} hyp/s) prepare_ms={info.match.prepare_ms:.1f} "
           f"e2e_s={e2e:.3f} hits={res.filter_hits} hit_rate={res.filter_hits / max(hyp * len(qry), 1):.5f} "
           f"yaw_err={xyz_yaw[3] - truth['yaw']:.2e}", flush=True)
@@ -42,4 +42,5 @@ if __name__ == "__main__":
     for cfg in which:
         for variant in (1, 0):
             run(int(cfg), variant)
+            run(int(cfg), variant, exhaustive=True)
         run(int(cfg), 1, stats=True, reps=1)
