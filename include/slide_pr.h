@@ -104,7 +104,8 @@ typedef struct slide_pr_search_opts {
   int32_t exhaustive;    /* 1: verify every hypothesis exactly.  0 (default): bound-and-verify -- a cheap upper
                             bound (bitmap filter hits) for every hypothesis, exact verification only where the
                             bound reaches the running best; the winner, its count and its correspondences are
-                            the same.  counts_out / collect_stats / compute_budget_sec > 0 imply exhaustive. */
+                            the same.  counts_out / collect_stats / compute_budget_sec > 0 imply exhaustive.
+                            2 (test hook): bound phase only, counts_out receives the upper bounds. */
 } slide_pr_search_opts;
 
 typedef struct slide_pr_tf_result {

@@ -94,7 +94,7 @@ struct slide_pr_handle {
   spr::QuerySet Q;
   // device side
   DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_rank16, d_rank16b, d_rowrank, d_rowrankb, d_gcnt, d_cellref, d_cellrefb, d_cellbase, d_cellbaseb, d_reftab, d_refbase,
-      d_cand, d_cand1, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ubplanes, d_itemub, d_seed, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
+      d_cand, d_cand1, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ubplanes, d_itemub, d_seed, d_canditems, d_candcount, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
   SprView V{};
   std::vector<int32_t> h_match;
 };
@@ -438,10 +438,13 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   // those whose bound reaches the running best.  Exhaustive verification of every hypothesis
   // when per-hypothesis counts / statistics are requested, with a compute budget (ring by ring),
   // or on request (opts.exhaustive).
-  const bool prune = !o.exhaustive && !o.counts_out && !o.collect_stats && h->p.compute_budget_sec <= 0 && active[0] >= 0 &&
-                     h->V.nqp > 0 && h->V.nqp < 65536 && !h->force_exhaustive;
+  const bool can_bound = h->p.compute_budget_sec <= 0 && active[0] >= 0 && h->V.nqp > 0 && h->V.nqp < 65536;
+  const bool bounds_only = o.exhaustive == 2;  // test hook: counts_out receives the upper bounds
+  if (bounds_only && !can_bound) { h->err = "bounds-only search not available for this problem"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  const bool prune = bounds_only || (!o.exhaustive && !o.counts_out && !o.collect_stats && can_bound && !h->force_exhaustive);
+  const int n_planes = spr_bound_planes(h->V.nqp);
+  size_t cand_off[2] = {0, 0};
   if (prune) {
-    const int n_planes = spr_bound_planes(h->V.nqp);
     const size_t n_wg_total = K.n_chunks_total / SPR_WARP_CHUNKS;
     SPR_CUDA(h, h->d_ubplanes.ensure((size_t)n_yaw * n_wg_total * (size_t)n_planes * 32 * sizeof(uint32_t) + 64));
     SPR_CUDA(h, h->d_itemub.ensure((size_t)n_yaw * n_wg_total * sizeof(uint32_t) + 64));
@@ -471,6 +474,20 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     }
     SPR_CUDA(h, spr_launch_seed(h->V, h->d_seed.as<unsigned long long>(), K.best_key, st));
     launches++;
+    // candidate work items of each direction (largest bound >= seeded best)
+    size_t cap[2];
+    for (int d = 0; d < 2; d++) cap[d] = (size_t)((h->L.dir_end[d] - h->L.dir_begin[d]) / SPR_WARP_CHUNKS) * (size_t)n_yaw;
+    SPR_CUDA(h, h->d_canditems.ensure((cap[0] + cap[1]) * sizeof(uint32_t) + 64));
+    SPR_CUDA(h, h->d_candcount.ensure(2 * sizeof(uint32_t)));
+    SPR_CUDA(h, cudaMemsetAsync(h->d_candcount.p, 0, 2 * sizeof(uint32_t), st));
+    for (uint32_t d = 0; d < 2; d++) {
+      if (h->L.dir_end[d] <= h->L.dir_begin[d]) continue;
+      B.chunk_begin = h->L.dir_begin[d]; B.chunk_end = h->L.dir_end[d]; B.dir = d;
+      SPR_CUDA(h, spr_launch_select_items(h->V, B, K.best_key, h->d_canditems.as<uint32_t>() + (d ? cap[0] : 0),
+                                          h->d_candcount.as<uint32_t>() + d, h->sm_count, st));
+      launches++;
+    }
+    cand_off[1] = cap[0];
     K.ub_planes = h->d_ubplanes.as<uint32_t>();
     K.item_ub = h->d_itemub.as<uint32_t>();
     K.ub_nplanes = n_planes;
@@ -480,6 +497,10 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
       if (end[d] <= begin[d]) continue;
       for (size_t i = 0; i < active.size(); i++) {
         K.chunk_begin = begin[d]; K.chunk_end = end[d]; K.dir = d; K.label = active[i];
+        if (prune) {
+          K.cand_items = h->d_canditems.as<uint32_t>() + cand_off[d];
+          K.cand_count = h->d_candcount.as<uint32_t>() + d;
+        }
         K.first = i == 0; K.last = i + 1 == active.size();
         K.tab_cells = K.label >= 0 ? h->R.cell_base[d][K.label + 1] - h->R.cell_base[d][K.label] : 0u;
         K.tab_refs = K.label >= 0 ? h->R.ref_base[K.label + 1] - h->R.ref_base[K.label] : 0u;
@@ -494,7 +515,9 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     return SLIDE_PR_OK;
   };
   int rings_scored = 0;
-  if (h->p.compute_budget_sec > 0) {
+  if (bounds_only) {
+    rings_scored = h->L.rings;
+  } else if (h->p.compute_budget_sec > 0) {
     // anytime behaviour of PR.cpp:181-191: whole seconds, checked before every ring
     const auto start = std::chrono::high_resolution_clock::now();
     for (size_t k = 0; k < h->L.ring.size(); k++) {
@@ -514,9 +537,30 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   unsigned long long key = 0, stats[4] = {0, 0, 0, 0};
   SPR_CUDA(h, cudaMemcpyAsync(&key, h->d_best.p, sizeof(key), cudaMemcpyDeviceToHost, st));
   if (o.collect_stats) SPR_CUDA(h, cudaMemcpyAsync(stats, h->d_stats.p, sizeof(stats), cudaMemcpyDeviceToHost, st));
-  if (o.counts_out && n_counts > 0)
+  if (o.counts_out && n_counts > 0 && !bounds_only)
     SPR_CUDA(h, cudaMemcpyAsync(o.counts_out, h->d_counts.p, (size_t)n_counts * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   SPR_CUDA(h, cudaStreamSynchronize(st));
+  if (bounds_only && o.counts_out && n_counts > 0) {  // decode the bit planes of the slice on the host
+    const size_t n_wg_total = K.n_chunks_total / SPR_WARP_CHUNKS;
+    std::vector<uint32_t> planes((size_t)n_yaw * n_wg_total * (size_t)n_planes * 32);
+    SPR_CUDA(h, cudaMemcpy(planes.data(), h->d_ubplanes.p, planes.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n_counts; i++) o.counts_out[i] = -1;
+    for (uint32_t c = 0; c < K.n_chunks_total; c++) {
+      const SprChunk &ch = h->L.chunks[c];
+      for (int b = 0; b < 32; b++) {
+        if (!((ch.valid >> b) & 1u)) continue;
+        const int64_t ord = (int64_t)ch.ord_base + (int64_t)b * ch.ord_stride;
+        for (int a = 0; a < n_yaw; a++) {
+          const int64_t slot = (ord - tb) * n_yaw + a;
+          if (slot < 0 || slot >= n_counts) continue;
+          const uint32_t *pp = planes.data() + (((size_t)a * n_wg_total + c / SPR_WARP_CHUNKS) * (size_t)n_planes) * 32 + (c % SPR_WARP_CHUNKS);
+          int32_t v = 0;
+          for (int i = 0; i < n_planes; i++) v |= (int32_t)((pp[(size_t)i * 32] >> b) & 1u) << i;
+          o.counts_out[slot] = v;
+        }
+      }
+    }
+  }
   g_trace.mark("search_sync");
   float ms = 0;
   SPR_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));

@@ -182,36 +182,30 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
   // tables of this pass' plane (bits, ranks, per-cell landmark slots, the label's landmark
   // table): staged into shared memory once per CTA, or read in place
   SprTables T = spr_global_tables(V, d, l < 0 ? 0 : l);
+  const SprTables GT = T;
+  SprTabLayout Lo{};
+  uint64_t *bar = nullptr;
+  uint32_t *stage_flag = nullptr;
+  bool staged = !SMEM_TAB;
   if (SMEM_TAB) {
-    // One thread arms an mbarrier with the byte count and issues five TMA bulk copies
-    // (cp.async.bulk global -> shared); everybody waits on the barrier's phase.
-    const SprTables GT = T;
-    const uint32_t ref_base = V.ref_base[l];
-    const SprTabLayout Lo = spr_tab_layout(G.plane_words[d], (uint32_t)G.R[d], GT.cell_base, K.tab_cells, ref_base, K.tab_refs);
-    double *s_ref = reinterpret_cast<double *>(smem + Lo.reftab_w);
-    uint32_t *s_bits = smem + Lo.bits_w;
-    uint16_t *s_r16 = reinterpret_cast<uint16_t *>(smem + Lo.r16_w);
-    uint32_t *s_rr = smem + Lo.rr_w;
-    uint16_t *s_cell = reinterpret_cast<uint16_t *>(smem + Lo.cellref_w);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + Lo.total_w - 4);
+    // The tables are staged by the first warp of the CTA that has work (a CTA of the verification
+    // phase may find no candidate item at all): that warp arms an mbarrier with the byte count
+    // and issues five TMA bulk copies (cp.async.bulk global -> shared); every warp with work
+    // waits on the barrier's phase before its first probe.
+    Lo = spr_tab_layout(G.plane_words[d], (uint32_t)G.R[d], GT.cell_base, K.tab_cells, V.ref_base[l], K.tab_refs);
+    bar = reinterpret_cast<uint64_t *>(smem + Lo.total_w - 4);
+    stage_flag = smem + Lo.total_w - 2;
     if (threadIdx.x == 0) {
       spr_mbar_init(bar, 1u);
+      *stage_flag = 0u;
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      spr_mbar_expect_tx(bar, Lo.reftab_b + Lo.bits_b + Lo.r16_b + Lo.rr_b + Lo.cellref_b);
-      spr_bulk_g2s(s_ref, GT.reftab - Lo.reftab_skip, Lo.reftab_b, bar);
-      spr_bulk_g2s(s_bits, GT.bits, Lo.bits_b, bar);
-      spr_bulk_g2s(s_r16, GT.r16, Lo.r16_b, bar);
-      spr_bulk_g2s(s_rr, GT.row_rank, Lo.rr_b, bar);
-      spr_bulk_g2s(s_cell, GT.cellref - Lo.cellref_skip, Lo.cellref_b, bar);
-    }
-    for (uint32_t spin = 0; !spr_mbar_try_wait(bar, 0u); spin++)
-      if (spin > 200000000u) __trap();  // a lost copy must not hang the GPU
-    T.bits = s_bits; T.r16 = s_r16; T.row_rank = s_rr;
-    T.cellref = s_cell + Lo.cellref_skip;
-    T.reftab = s_ref + Lo.reftab_skip;
+    T.bits = smem + Lo.bits_w;
+    T.r16 = reinterpret_cast<uint16_t *>(smem + Lo.r16_w);
+    T.row_rank = smem + Lo.rr_w;
+    T.cellref = reinterpret_cast<uint16_t *>(smem + Lo.cellref_w) + Lo.cellref_skip;
+    T.reftab = reinterpret_cast<double *>(smem + Lo.reftab_w) + Lo.reftab_skip;
   }
   WarpState ws;
   ws.cnt = smem + (tab_bytes >> 2) + warp * SPR_WARP_WORDS(CNT32);
@@ -223,12 +217,14 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
   const int g0 = l >= 0 ? V.label_gseg[l] : 0, g1 = l >= 0 ? V.label_gseg[l + 1] : 0;
   const int32_t *q_fx = d ? V.qrotq_yx : V.qrotq_xy;
 
+  const long long n_todo = K.cand_items ? (long long)__ldg(K.cand_count) : n_items;
   for (;;) {
     // per-warp dynamic scheduling, yaw-major: warps running at the same time share qrotq[a][*]
     long long item = 0;
     if (lane == 0) item = (long long)atomicAdd(K.work_counter, 1ull);
     item = __shfl_sync(SPR_FULL, item, 0);
-    if (item >= n_items) break;
+    if (item >= n_todo) break;
+    if (K.cand_items) item = (long long)__ldg(K.cand_items + item);  // verification phase: candidate items only
     const int a = (int)(item / n_wg_local);
     const int wg = K.shard_index + (int)(item % n_wg_local) * K.shard_count;
     const uint32_t cidx = K.chunk_begin + (uint32_t)wg * SPR_WARP_CHUNKS + (uint32_t)lane;  // < chunk_end (padded)
@@ -259,6 +255,19 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
         else gt |= eq & p;
       }
       valid &= gt | eq;
+    }
+    if (SMEM_TAB && !staged) {
+      if (lane == 0 && atomicExch(stage_flag, 1u) == 0u) {
+        spr_mbar_expect_tx(bar, Lo.reftab_b + Lo.bits_b + Lo.r16_b + Lo.rr_b + Lo.cellref_b);
+        spr_bulk_g2s(smem + Lo.reftab_w, GT.reftab - Lo.reftab_skip, Lo.reftab_b, bar);
+        spr_bulk_g2s(smem + Lo.bits_w, GT.bits, Lo.bits_b, bar);
+        spr_bulk_g2s(smem + Lo.r16_w, GT.r16, Lo.r16_b, bar);
+        spr_bulk_g2s(smem + Lo.rr_w, GT.row_rank, Lo.rr_b, bar);
+        spr_bulk_g2s(smem + Lo.cellref_w, GT.cellref - Lo.cellref_skip, Lo.cellref_b, bar);
+      }
+      for (uint32_t spin = 0; !spr_mbar_try_wait(bar, 0u); spin++)
+        if (spin > 200000000u) __trap();  // a lost copy must not hang the GPU
+      staged = true;
     }
     spr_cnt_zero<CNT32>(ws.cnt, lane);
     const int32_t aq0 = spr_fx(across, G.S);

@@ -31,6 +31,8 @@ struct SprLaunch {
   const uint32_t *item_ub;          // device: [yaw][chunk / 32] largest bound of the work item
   int32_t ub_nplanes;               // 0: exhaustive search
   int32_t pad;
+  const uint32_t *cand_items;       // device, optional: work items (yaw * n_wg_local + k) to verify, built by
+  const uint32_t *cand_count;       //   spr_launch_select_items; *cand_count entries
 };
 
 // One launch of the bound phase = one bitmap direction x a set of labels whose planes are staged
@@ -66,6 +68,9 @@ int spr_bound_planes(int nqp);                                   // bit planes n
 int spr_bound_labels_per_launch(const SprView &V, uint32_t dir); // label planes that fit in shared memory (0: none)
 cudaError_t spr_launch_bound_lattice(const SprView &V, const SprBoundLaunch &B, int n_planes, int sm_count, cudaStream_t st,
                                      int *n_launches);
+// work items of direction `B.dir` whose largest bound reaches the running best -> items[0 .. *count)
+cudaError_t spr_launch_select_items(const SprView &V, const SprBoundLaunch &B, const unsigned long long *best_key,
+                                    uint32_t *items, uint32_t *count, int sm_count, cudaStream_t st);
 // exact score of the best-bounded hypothesis of every yaw -> atomicMax on best_key
 cudaError_t spr_launch_seed(const SprView &V, const unsigned long long *seed_key, unsigned long long *best_key,
                             cudaStream_t st);

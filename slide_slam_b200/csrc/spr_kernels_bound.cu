@@ -207,25 +207,29 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
   }
 }
 
-// Exact score of the best-bounded hypothesis of every yaw candidate (one warp each): seeds the
-// running best of the verification phase.  Same decision code as the hypothesis-list scorer.
+// Exact score of the best-bounded hypothesis of every yaw candidate (one CTA each, the warps
+// stride over the query landmarks): seeds the running best of the verification phase.  Same
+// decision code as the hypothesis-list scorer.
 __global__ void __launch_bounds__(256)
-spr_seed_kernel(const SprView V, const unsigned long long *__restrict__ seed_key, unsigned long long *best_key) {
-  const int lane = threadIdx.x & 31;
-  const int a = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (a >= V.n_yaw) return;
+spr_seed_kernel(const __grid_constant__ SprView V, const unsigned long long *__restrict__ seed_key,
+                unsigned long long *best_key) {
+  __shared__ int s_cnt;
+  const int a = blockIdx.x;
   const unsigned long long sk = seed_key[a];
-  if (sk == 0ull) return;
+  if (sk == 0ull) return;  // uniform for the CTA
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
   const unsigned long long loc = sk & SPR_KEY_IDX_MASK;
   const SprChunk ch = V.chunks[loc >> 5];
   const int b = (int)(loc & 31ull);
   const double t = V.lat[ch.along_off + b];
   const double tx = ch.dir ? t : ch.across, ty = ch.dir ? ch.across : t;
   int cnt = 0;
-  for (int js = lane; js < V.nqp; js += 32) {
+  for (int js = threadIdx.x; js < V.nqp; js += blockDim.x) {
     const int l = V.qlabel[js];
     if (l < 0) continue;  // padding
-    const double rx = V.qrot[2 * ((size_t)a * (size_t)V.nqp + (size_t)js)], ry = V.qrot[2 * ((size_t)a * (size_t)V.nqp + (size_t)js) + 1];
+    const size_t qi = (size_t)a * (size_t)V.nqp + (size_t)js;
+    const double rx = V.qrot[2 * qi], ry = V.qrot[2 * qi + 1];
     const double xt = SPR_DADD(rx, tx), yt = SPR_DADD(ry, ty);
     uint32_t row, bit;
     if (spr_point_cell(V, l, xt, yt, &row, &bit) &&
@@ -234,16 +238,63 @@ spr_seed_kernel(const SprView V, const unsigned long long *__restrict__ seed_key
   }
 #pragma unroll
   for (int dlt = 16; dlt > 0; dlt >>= 1) cnt += __shfl_xor_sync(SPR_FULL, cnt, dlt);
-  if (lane == 0) {
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) {
     const unsigned long long ord = (unsigned long long)ch.ord_base + (unsigned long long)b * ch.ord_stride;
-    atomicMax(best_key, spr_make_key((uint32_t)cnt, ord * (unsigned long long)V.n_yaw + (unsigned long long)a));
+    atomicMax(best_key, spr_make_key((uint32_t)s_cnt, ord * (unsigned long long)V.n_yaw + (unsigned long long)a));
   }
 }
 
 cudaError_t spr_launch_seed(const SprView &V, const unsigned long long *seed_key, unsigned long long *best_key,
                             cudaStream_t st) {
   if (V.n_yaw <= 0 || V.nqp <= 0) return cudaSuccess;
-  spr_seed_kernel<<<(V.n_yaw + 7) / 8, 256, 0, st>>>(V, seed_key, best_key);
+  spr_seed_kernel<<<V.n_yaw, 256, 0, st>>>(V, seed_key, best_key);
+  return cudaGetLastError();
+}
+
+// Candidate work items of the verification phase: those of this shard / direction whose largest
+// bound reaches the running best (seeded by spr_seed_kernel).  Warp-aggregated append.
+__global__ void __launch_bounds__(256)
+spr_select_items_kernel(const SprBoundLaunch B, const int n_wg_local, const long long n_items, const int n_yaw,
+                        const unsigned long long *__restrict__ best_key, uint32_t *__restrict__ items, uint32_t *count) {
+  const long long bc = (long long)(*best_key >> SPR_KEY_IDX_BITS) - 1;
+  const uint32_t tau = bc > 0 ? (uint32_t)bc : 0u;
+  const uint32_t n_wg_total = B.n_chunks_total / SPR_WARP_CHUNKS;
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < n_items; i0 += stride) {
+    const long long i = i0 + lane;
+    bool take = false;
+    if (i < n_items) {
+      const int a = (int)(i / n_wg_local);
+      const int wg = B.shard_index + (int)(i % n_wg_local) * B.shard_count;
+      take = B.item_ub[(size_t)a * n_wg_total + B.chunk_begin / SPR_WARP_CHUNKS + (uint32_t)wg] >= tau;
+    }
+    const uint32_t m = __ballot_sync(SPR_FULL, take);
+    if (m) {
+      uint32_t base = 0u;
+      if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(m));
+      base = __shfl_sync(SPR_FULL, base, 0);
+      if (take) items[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+    }
+  }
+}
+
+cudaError_t spr_launch_select_items(const SprView &V, const SprBoundLaunch &B, const unsigned long long *best_key,
+                                    uint32_t *items, uint32_t *count, int sm_count, cudaStream_t st) {
+  if (B.chunk_end <= B.chunk_begin || V.n_yaw <= 0) return cudaSuccess;
+  const int n_wg = (int)((B.chunk_end - B.chunk_begin) / SPR_WARP_CHUNKS);
+  const int sc = B.shard_count > 1 ? B.shard_count : 1;
+  const int si = B.shard_count > 1 ? B.shard_index : 0;
+  const int n_wg_local = n_wg > si ? (n_wg - si + sc - 1) / sc : 0;
+  if (n_wg_local <= 0) return cudaSuccess;
+  SprBoundLaunch B2 = B;
+  B2.shard_index = si;
+  B2.shard_count = sc;
+  const long long n_items = (long long)n_wg_local * V.n_yaw;
+  const long long want = (n_items + 255) / 256;
+  spr_select_items_kernel<<<(int)(want < sm_count * 4 ? want : sm_count * 4), 256, 0, st>>>(B2, n_wg_local, n_items, V.n_yaw, best_key, items, count);
   return cudaGetLastError();
 }
 

@@ -131,6 +131,78 @@ def test_random_maps_every_hypothesis(seed, variant):
     pr.close()
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("seed", range(6))
+def test_upper_bounds_dominate_exact_counts(seed, variant):
+    """Bound phase of the bound-and-verify search: the bound of EVERY hypothesis is >= its exact
+    inlier count (and <= the number of query landmarks), so pruning can never drop the winner."""
+    rng = np.random.default_rng(700 + seed)
+    n_ref, n_qry = int(rng.integers(5, 200)), int(rng.integers(5, 120))
+    ref, qry = H.random_maps(rng, n_ref, n_qry, extent=float(rng.uniform(5, 20)), n_labels=int(rng.integers(1, 7)),
+                             grid=(0.25 if seed % 3 == 0 else None))
+    kw = dict(match_xy_step_size=float(rng.choice([0.25, 0.5, 1.0])), yaw_step_deg=float(rng.choice([30.0, 45.0])),
+              match_threshold=float(rng.choice([0.5, 0.75, 0.3, 1.1])), match_threshold_dimension=1.0,
+              ignore_dimension=int(seed % 2))
+    hx = float(rng.uniform(4, 12))
+    pr = make_pr(kw, variant=variant)
+    pr.prepare(ref, qry, hx, hx)
+    nt, ny, _ = pr.lattice_info()
+    res_e, exact = pr.search(0, nt, want_counts=True)
+    res_b, bound = pr.search(0, nt, want_counts=True, bounds_only=True)
+    assert res_e.search_mode == 0 and res_b.search_mode == 1
+    assert exact.shape == bound.shape and (exact >= 0).all()
+    assert (bound >= exact).all() and (bound <= n_qry).all()
+    # a slice of the lattice (re-chunked) gives the same bounds
+    lo, hi = nt // 3, nt // 3 + max(nt // 5, 1)
+    _, part = pr.search(lo, hi, want_counts=True, bounds_only=True)
+    assert np.array_equal(part, bound[lo * ny:hi * ny])
+    res_p, _ = pr.search()            # default: bound-and-verify
+    res_x, _ = pr.search(exhaustive=True)
+    assert res_p.search_mode == 1 and res_x.search_mode == 0
+    assert (res_p.best_num_inliers, res_p.best_hyp_index) == (res_x.best_num_inliers, res_x.best_hyp_index)
+    assert (res_x.best_num_inliers, res_x.best_hyp_index) == (res_e.best_num_inliers, res_e.best_hyp_index)
+    pr.close()
+
+
+@pytest.mark.parametrize("kind", ["overlap", "unrelated", "one_label", "tiny_query"])
+def test_bound_and_verify_equals_exhaustive(kind):
+    """Same winner (count, canonical index, correspondences) with and without pruning, with a
+    strong peak, with no peak at all (unrelated maps: pruning barely helps) and sharded."""
+    if kind == "overlap":
+        ref, qry, _ = synth.make_pair(400, seed=31, classes="five", outlier_frac=0.1)
+    elif kind == "unrelated":
+        ref = synth.make_pair(400, seed=32, classes="five")[0]
+        qry = synth.make_pair(400, seed=33, classes="five")[1]
+    elif kind == "one_label":
+        ref, qry, _ = synth.make_pair(300, seed=34, classes="five")
+        ref[:, 0] = 1.0; qry[:, 0] = 1.0
+    else:
+        ref, qry, _ = synth.make_pair(400, seed=35, classes="forest_urban", n_b=12)
+    ros = {"search_xy_step_size": 0.5, "search_yaw_step_size_degrees": 10.0, "match_threshold_position": 0.5,
+           "match_threshold_dimension": 1.0, "ignore_dimension": 0, "min_num_inliers": 5}
+    pr = PlaceRecognition(ros)
+    found, _, _, info, ri, qi = pr.findTransformation(ref, qry)      # default mode
+    assert info.match.search_mode == 1
+    sref, sqry = ref.copy(), qry.copy()
+    sref[:, 1:3] -= np.array(info.centroid_ref[:]); sqry[:, 1:3] -= np.array(info.centroid_qry[:])
+    pr.prepare(sref, sqry, info.half_x, info.half_y)
+    res_x, _ = pr.search(exhaustive=True)
+    assert res_x.search_mode == 0
+    assert (info.match.best_num_inliers, info.match.best_hyp_index) == (res_x.best_num_inliers, res_x.best_hyp_index)
+    _, ri_x, qi_x = pr.extract(res_x.best_hyp_index)
+    assert ri.tolist() == ri_x.tolist() and qi.tolist() == qi_x.tolist()
+    lib = capi.lib()
+    for n_shards in (2, 5):
+        recs = (capi.TopkRecord * n_shards)()
+        for r in range(n_shards):
+            res, _ = pr.search(shard_index=r, shard_count=n_shards)
+            assert res.search_mode == 1
+            lib.slide_pr_pack_record(C.byref(res), r, C.byref(recs[r]))
+        w = lib.slide_pr_merge_records(recs, n_shards)
+        assert (recs[w].inliers, recs[w].hyp_index) == (res_x.best_num_inliers, res_x.best_hyp_index)
+    pr.close()
+
+
 def test_edge_cases_through_the_abi():
     kw = dict(match_xy_step_size=0.5, yaw_step_deg=45.0)
     rng = np.random.default_rng(1)
