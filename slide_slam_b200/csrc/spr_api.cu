@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <string>
 #include <vector>
 
@@ -69,7 +70,10 @@ struct slide_pr_handle {
   int tables_mode = SPR_TABLES_AUTO;
   bool force_exhaustive = false;  // env SLIDE_PR_EXHAUSTIVE=1
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t copy_stream = nullptr;  // uploads that overlap the bound phase of a search
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
+  bool ranks_pending = false;          // stage 2 of the reference index (rank tables) not built / uploaded yet
+  const double *pending_ref7 = nullptr; // == cached_ref.data() while ranks_pending
   std::string err;
   // prepared problem (host side)
   bool prepared = false;
@@ -170,7 +174,9 @@ int slide_pr_create(const slide_pr_params *p, slide_pr_handle **out) {
   if (dev >= n_dev) { g_create_error = "device ordinal out of range"; delete h; return SLIDE_PR_ERR_INVALID; }
   h->device = dev;
   if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
+      (e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming)) != cudaSuccess) {
     g_create_error = std::string("CUDA init: ") + cudaGetErrorString(e);
     delete h;
     return SLIDE_PR_ERR_CUDA;
@@ -190,10 +196,13 @@ void slide_pr_destroy(slide_pr_handle *h) {
   for (DevBuf *b : {&h->d_lat, &h->d_chunks, &h->d_cs, &h->d_qxy, &h->d_qdims, &h->d_labelseg, &h->d_qlabel,
                     &h->d_labelbox, &h->d_gbox, &h->d_bitmap, &h->d_rank16, &h->d_rank16b, &h->d_rowrank, &h->d_rowrankb, &h->d_gcnt, &h->d_cellref, &h->d_cellrefb,
                     &h->d_cellbase, &h->d_cellbaseb, &h->d_reftab, &h->d_refbase, &h->d_cand, &h->d_cand1, &h->d_qrot,
-                    &h->d_qrotq, &h->d_qrotq_yx, &h->d_work, &h->d_ref7, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps, &h->d_tri, &h->d_tri_out})
+                    &h->d_qrotq, &h->d_qrotq_yx, &h->d_work, &h->d_ref7, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps, &h->d_tri, &h->d_tri_out,
+                    &h->d_ubplanes, &h->d_itemub, &h->d_seed, &h->d_canditems, &h->d_candcount})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -220,6 +229,39 @@ static int upload_lattice(slide_pr_handle *h, cudaStream_t st) {
   return SLIDE_PR_OK;
 }
 
+// Stage 2 of the reference index: rank tables / candidate records of both bitmap directions,
+// built from the cached reference rows and uploaded on `st`.
+static int finish_ranks(slide_pr_handle *h, cudaStream_t st) {
+  int rc;
+  for (int d = 0; d < 2; d++)
+    if ((rc = spr::build_ref_ranks(h->cached_ref.data(), d, h->R, h->err)) != SLIDE_PR_OK) return rc;
+  g_trace.mark("ref_ranks_build");
+  if ((rc = upload(h, h->d_rank16, h->R.rank16[0], st))) return rc;
+  if ((rc = upload(h, h->d_rank16b, h->R.rank16[1], st))) return rc;
+  if ((rc = upload(h, h->d_rowrank, h->R.row_rank[0], st))) return rc;
+  if ((rc = upload(h, h->d_rowrankb, h->R.row_rank[1], st))) return rc;
+  if ((rc = upload(h, h->d_cellref, h->R.cellref[0], st))) return rc;
+  if ((rc = upload(h, h->d_cellrefb, h->R.cellref[1], st))) return rc;
+  if ((rc = upload(h, h->d_cellbase, h->R.cell_base[0], st))) return rc;
+  if ((rc = upload(h, h->d_cellbaseb, h->R.cell_base[1], st))) return rc;
+  if ((rc = upload(h, h->d_cand, h->R.cand[0], st))) return rc;
+  if ((rc = upload(h, h->d_cand1, h->R.cand[1], st))) return rc;
+  SprView &V = h->V;
+  V.rank16[0] = h->d_rank16.as<uint16_t>();
+  V.rank16[1] = h->d_rank16b.as<uint16_t>();
+  V.row_rank[0] = h->d_rowrank.as<uint32_t>();
+  V.row_rank[1] = h->d_rowrankb.as<uint32_t>();
+  V.cellref[0] = h->d_cellref.as<uint16_t>();
+  V.cellref[1] = h->d_cellrefb.as<uint16_t>();
+  V.cell_base[0] = h->d_cellbase.as<uint32_t>();
+  V.cell_base[1] = h->d_cellbaseb.as<uint32_t>();
+  V.cand[0] = h->d_cand.as<SprCand>();
+  V.cand[1] = h->d_cand1.as<SprCand>();
+  h->ranks_pending = false;
+  g_trace.mark("ref_ranks_upload");
+  return SLIDE_PR_OK;
+}
+
 int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7, int32_t n_qry,
                      double half_x, double half_y) {
   if (!h) return SLIDE_PR_ERR_INVALID;
@@ -242,21 +284,31 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
                             h->lat_p.match_yaw_angle_step_size == h->p.match_yaw_angle_step_size &&
                             h->lat_p.disable_yaw_search == h->p.disable_yaw_search &&
                             (h->lat_p.compute_budget_sec > 0) == (h->p.compute_budget_sec > 0);
-  if (!same_lattice) {
+  std::string lattice_err;          // declared before the job: the job's destructor joins the thread first
+  std::future<int> lattice_job;
+  if (!same_lattice) {  // built on a helper thread while this one builds the bitmaps and the query set
     h->lattice_valid = false;
-    if ((rc = spr::build_lattice(h->p, half_x, half_y, h->yaw_half, 0, -1, h->p.compute_budget_sec > 0, h->L, h->err)) != SLIDE_PR_OK) return rc;
-    h->lat_hx = half_x; h->lat_hy = half_y; h->lat_yaw_half = h->yaw_half; h->lat_p = h->p;
-    h->lattice_valid = true;
-    g_trace.mark("lattice_build");
-    if ((rc = upload_lattice(h, st))) return rc;
-    g_trace.mark("lattice_upload");
+    lattice_job = std::async(std::launch::async, [h, half_x, half_y, &lattice_err]() {
+      return spr::build_lattice(h->p, half_x, half_y, h->yaw_half, 0, -1, h->p.compute_budget_sec > 0, h->L, lattice_err);
+    });
   } else {
     h->reuse_flags |= 1;
   }
+  auto join_lattice = [&]() -> int {
+    if (!lattice_job.valid()) return SLIDE_PR_OK;
+    const int lrc = lattice_job.get();
+    if (lrc != SLIDE_PR_OK) { h->err = lattice_err; return lrc; }
+    h->lat_hx = half_x; h->lat_hy = half_y; h->lat_yaw_half = h->yaw_half; h->lat_p = h->p;
+    h->lattice_valid = true;
+    g_trace.mark("lattice_join");
+    const int urc = upload_lattice(h, st);
+    g_trace.mark("lattice_upload");
+    return urc;
+  };
   double qrad = 0;
   for (int j = 0; j < n_qry; j++) {
     const double r = std::hypot(qry7[7 * (size_t)j + 1], qry7[7 * (size_t)j + 2]);
-    if (!std::isfinite(r)) { h->err = "non-finite query coordinate"; return SLIDE_PR_ERR_NONFINITE; }
+    if (!std::isfinite(r)) { if (lattice_job.valid()) lattice_job.get(); h->err = "non-finite query coordinate"; return SLIDE_PR_ERR_NONFINITE; }
     qrad = std::max(qrad, r);
   }
   const double reach = qrad + std::max(std::fabs(half_x), std::fabs(half_y)) + h->p.match_xy_step_size;
@@ -267,39 +319,34 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
                         h->cached_ref_p.match_threshold_dimension == h->p.match_threshold_dimension &&
                         (n_ref == 0 || std::memcmp(h->cached_ref.data(), ref7, (size_t)n_ref * 7 * sizeof(double)) == 0);
   if (!same_ref) {
+    // stage 1 of the reference index (bitmaps, landmark tables): all the bound phase needs.  The
+    // rank tables (stage 2) are built and uploaded by the search while the bound phase runs.
     h->ref_index_valid = false;
+    h->ranks_pending = false;
     const double reach_cap = reach * 1.25;  // head-room so that slightly larger queries reuse the index
-    if ((rc = spr::build_ref_index(h->p, ref7, n_ref, reach_cap, h->R, h->err)) != SLIDE_PR_OK) return rc;
-    g_trace.mark("ref_index_build");
+    if ((rc = spr::build_ref_bitmaps(h->p, ref7, n_ref, reach_cap, h->R, h->err)) != SLIDE_PR_OK) { if (lattice_job.valid()) lattice_job.get(); return rc; }
+    g_trace.mark("ref_bitmaps_build");
     h->cached_ref.assign(ref7, ref7 + (size_t)n_ref * 7);
     h->cached_reach = reach_cap; h->cached_ref_p = h->p;
     h->ref_index_valid = true;
+    h->ranks_pending = true;
     if ((rc = upload(h, h->d_labelbox, h->R.labelbox, st))) return rc;
     if ((rc = upload(h, h->d_bitmap, h->R.bitmap, st))) return rc;
-    if ((rc = upload(h, h->d_rank16, h->R.rank16[0], st))) return rc;
-    if ((rc = upload(h, h->d_rank16b, h->R.rank16[1], st))) return rc;
-    if ((rc = upload(h, h->d_rowrank, h->R.row_rank[0], st))) return rc;
-    if ((rc = upload(h, h->d_rowrankb, h->R.row_rank[1], st))) return rc;
-    if ((rc = upload(h, h->d_cellref, h->R.cellref[0], st))) return rc;
-    if ((rc = upload(h, h->d_cellrefb, h->R.cellref[1], st))) return rc;
-    if ((rc = upload(h, h->d_cellbase, h->R.cell_base[0], st))) return rc;
-    if ((rc = upload(h, h->d_cellbaseb, h->R.cell_base[1], st))) return rc;
     if ((rc = upload(h, h->d_reftab, h->R.reftab, st))) return rc;
     if ((rc = upload(h, h->d_refbase, h->R.ref_base, st))) return rc;
-    if ((rc = upload(h, h->d_cand, h->R.cand[0], st))) return rc;
-    if ((rc = upload(h, h->d_cand1, h->R.cand[1], st))) return rc;
     if ((rc = upload_raw(h, h->d_ref7, ref7, (size_t)n_ref * 7 * sizeof(double), st))) return rc;
-    g_trace.mark("ref_index_upload");
+    g_trace.mark("ref_bitmaps_upload");
   } else {
     h->reuse_flags |= 2;
   }
-  if ((rc = spr::build_query_set(h->R, qry7, n_qry, h->Q, h->err)) != SLIDE_PR_OK) return rc;
+  if ((rc = spr::build_query_set(h->R, qry7, n_qry, h->Q, h->err)) != SLIDE_PR_OK) { if (lattice_job.valid()) lattice_job.get(); return rc; }
   g_trace.mark("query_set_build");
   if ((rc = upload(h, h->d_qxy, h->Q.qxy, st))) return rc;
   if ((rc = upload(h, h->d_qdims, h->Q.qdims, st))) return rc;
   if ((rc = upload(h, h->d_labelseg, h->Q.label_gseg, st))) return rc;
   if ((rc = upload(h, h->d_qlabel, h->Q.qlabel, st))) return rc;
   if ((rc = upload_raw(h, h->d_qry7, qry7, (size_t)n_qry * 7 * sizeof(double), st))) return rc;
+  if ((rc = join_lattice()) != SLIDE_PR_OK) return rc;
   const size_t nrot = (size_t)std::max<size_t>((size_t)h->L.yaw.size() * (size_t)h->Q.nqp, 1);
   const size_t ngb = (size_t)std::max<size_t>((size_t)h->L.yaw.size() * (size_t)(h->Q.nqp / SPR_QGROUP), 1);
   SPR_CUDA(h, h->d_qrot.ensure(nrot * 2 * sizeof(double)));
@@ -472,6 +519,13 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
         passes_left--;
       }
     }
+    if (h->ranks_pending) {
+      // the bound launches above keep the GPU busy: build the rank tables now and upload them on
+      // the copy stream; the seed / verification kernels wait for the copies
+      if ((rc = finish_ranks(h, h->copy_stream)) != SLIDE_PR_OK) return rc;
+      SPR_CUDA(h, cudaEventRecord(h->ev_copy, h->copy_stream));
+      SPR_CUDA(h, cudaStreamWaitEvent(st, h->ev_copy, 0));
+    }
     SPR_CUDA(h, spr_launch_seed(h->V, h->d_seed.as<unsigned long long>(), K.best_key, st));
     launches++;
     // candidate work items of each direction (largest bound >= seeded best)
@@ -492,6 +546,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     K.item_ub = h->d_itemub.as<uint32_t>();
     K.ub_nplanes = n_planes;
   }
+  if (h->ranks_pending && !bounds_only && (rc = finish_ranks(h, st)) != SLIDE_PR_OK) return rc;  // exhaustive path
   auto run_range = [&](const uint32_t begin[2], const uint32_t end[2]) -> int {
     for (uint32_t d = 0; d < 2; d++) {
       if (end[d] <= begin[d]) continue;
@@ -939,6 +994,7 @@ int slide_pr_score_hypotheses(slide_pr_handle *h, const double *hyps4, int64_t n
   if (!h || !out || (n > 0 && !hyps4) || n < 0) return SLIDE_PR_ERR_INVALID;
   if (!h->prepared) { h->err = "slide_pr_score_hypotheses before slide_pr_prepare"; return SLIDE_PR_ERR_INVALID; }
   SPR_CUDA(h, cudaSetDevice(h->device));
+  if (h->ranks_pending) { const int rrc = finish_ranks(h, h->stream); if (rrc != SLIDE_PR_OK) return rrc; }
   cudaStream_t st = h->stream;
   fill_result_header(h, out);
   out->status = SLIDE_PR_OK;

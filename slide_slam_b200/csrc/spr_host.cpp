@@ -257,6 +257,15 @@ bool translation_of(const Lattice &L, uint64_t ordinal, double *x, double *y, in
 // ------------------------------------------------------------------------------------------
 int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, double reach,
                     RefIndex &R, std::string &err) {
+  int rc = build_ref_bitmaps(p, ref7, n_ref, reach, R, err);
+  for (int d = 0; d < 2 && rc == SLIDE_PR_OK; d++) rc = build_ref_ranks(ref7, d, R, err);
+  return rc;
+}
+
+// Stage 1: label buckets, grid / fixed-point format, occupancy bitmaps of both directions, the
+// per-label landmark tables and label boxes -- everything the bound phase of the search reads.
+int build_ref_bitmaps(const slide_pr_params &p, const double *ref7, int n_ref, double reach,
+                      RefIndex &R, std::string &err) {
   R.labels.clear();  // the vectors are reused across calls (no re-allocation / page faults)
   R.n_ref = n_ref;
   const double c = p.match_xy_step_size, thr = p.match_threshold;
@@ -316,8 +325,10 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
 
   // label bucket and slot (position inside its label, ascending index) of every landmark; the
   // compact per-label landmark table [x, y, d1, d2, d3] a cell's 16-bit reference points into
-  std::vector<int32_t> lab_of((size_t)std::max(n_ref, 1), -1);
-  std::vector<uint32_t> slot_of_ref((size_t)std::max(n_ref, 1), 0u);
+  std::vector<int32_t> &lab_of = R.lab_of;
+  std::vector<uint32_t> &slot_of_ref = R.slot_of_ref;
+  lab_of.assign((size_t)std::max(n_ref, 1), -1);
+  slot_of_ref.assign((size_t)std::max(n_ref, 1), 0u);
   R.ref_base.assign((size_t)n_labels + 1, 0u);
   {
     std::vector<uint32_t> per((size_t)std::max(n_labels, 1), 0u);
@@ -339,8 +350,8 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
   }
   // mark every cell whose (slightly dilated) box a landmark's match disc touches; entries are
   // produced in ascending landmark order, which is the order a cell's candidates must keep
-  struct Entry { uint32_t ref; int32_t nx, ny; };
-  std::vector<Entry> entries;
+  std::vector<RefIndex::Entry> &entries = R.entries;
+  entries.clear();
   entries.reserve((size_t)n_ref * 12);
   if (matchable) {
     const double eps_cells = 3.0 / std::ldexp(1.0, F) + 1e-9 / c;  // fixed-point truncation + lattice drift
@@ -371,7 +382,23 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
     }
   }
   if (entries.size() >= (1ull << 32)) { err = "candidate lists exceed 2^32 entries"; return SLIDE_PR_ERR_UNSUPPORTED; }
-  for (int d = 0; d < 2; d++) {
+  R.labelbox.resize((size_t)std::max(n_labels, 1));
+  for (int l = 0; l < std::max(n_labels, 1); l++) {
+    if (cb[l].x0 > cb[l].x1) { R.labelbox[l] = SprBox{0, -(1 << 30), 0, -(1 << 30)}; continue; }  // empty: never visible
+    R.labelbox[l] = SprBox{cb[l].x0 << F, (cb[l].x1 + 1) << F, cb[l].y0 << F, (cb[l].y1 + 1) << F};
+  }
+  return SLIDE_PR_OK;
+}
+
+// Stage 2 (per bitmap direction): rank tables, per-cell landmark references and the chained
+// candidate records -- what the exact verification reads.
+int build_ref_ranks(const double *ref7, int d, RefIndex &R, std::string &err) {
+  const SprGrid &G = R.grid;
+  const int n_labels = (int)R.labels.size();
+  const std::vector<int32_t> &lab_of = R.lab_of;
+  const std::vector<uint32_t> &slot_of_ref = R.slot_of_ref;
+  const std::vector<RefIndex::Entry> &entries = R.entries;
+  {
     // rank tables of direction d, label-major == rank order of the marked cells:
     //   row_rank[l][row]  = rank of the first marked cell of the row, relative to the label's first cell
     //   rank16[l][word]   = marked cells of the same row before the word
@@ -412,7 +439,7 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
     cellref.assign(n_cells + 16, 0);  // + slack for aligned bulk copies
     std::vector<uint32_t> tail(n_cells, 0xffffffffu);  // last record of each cell's chain
     size_t extra = n_cells;
-    for (const Entry &e : entries) {
+    for (const RefIndex::Entry &e : entries) {
       const int l = lab_of[e.ref];
       const uint32_t row = (uint32_t)((d ? e.ny : e.nx) + 1), bit = (uint32_t)((d ? e.nx : e.ny) + 32);
       const size_t wi = (size_t)row * G.W[d] + (bit >> 5);
@@ -437,11 +464,6 @@ int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, dou
     if (extra != std::max<size_t>(entries.size(), n_cells) && !(entries.empty() && extra == 0)) {
       if (extra != entries.size()) { err = "internal: rank / cell list mismatch"; return SLIDE_PR_ERR_INTERNAL; }
     }
-  }
-  R.labelbox.resize((size_t)std::max(n_labels, 1));
-  for (int l = 0; l < std::max(n_labels, 1); l++) {
-    if (cb[l].x0 > cb[l].x1) { R.labelbox[l] = SprBox{0, -(1 << 30), 0, -(1 << 30)}; continue; }  // empty: never visible
-    R.labelbox[l] = SprBox{cb[l].x0 << F, (cb[l].x1 + 1) << F, cb[l].y0 << F, (cb[l].y1 + 1) << F};
   }
   return SLIDE_PR_OK;
 }

@@ -56,12 +56,22 @@ struct RefIndex {
   std::vector<SprBox> labelbox;     // [n_labels] fixed-point bounds of the label's marked cells
   double Tstar = 0, Sstar = 0;
   int n_ref = 0;
+  // carried from build_ref_bitmaps to build_ref_ranks
+  struct Entry { uint32_t ref; int32_t nx, ny; };  // landmark `ref` marks cell (nx, ny); ascending landmark order
+  std::vector<Entry> entries;
+  std::vector<int32_t> lab_of;       // [n_ref] label bucket, -1: NaN label
+  std::vector<uint32_t> slot_of_ref; // [n_ref] position inside its label
 };
 
 // reach: max |coordinate| any transformed query point or translation can take (metres);
 // fixes the fixed-point format.  Returns SLIDE_PR_OK or an error code.
 int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, double reach,
                     RefIndex &R, std::string &err);
+// The two stages of build_ref_index: the occupancy bitmaps (all the bound phase of the search
+// needs) and, per bitmap direction, the rank tables / candidate records of the exact verification.
+int build_ref_bitmaps(const slide_pr_params &p, const double *ref7, int n_ref, double reach,
+                      RefIndex &R, std::string &err);
+int build_ref_ranks(const double *ref7, int d, RefIndex &R, std::string &err);
 
 struct QuerySet {
   int nq = 0;                       // kept queries (label present in the reference)
