@@ -43,6 +43,27 @@ double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Page-locked allocation for the host vectors that are uploaded (spr::uvec): a 64-byte header
+// remembers whether cudaHostAlloc succeeded, otherwise the block comes from malloc.
+void *pinned_alloc(size_t n) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, n + 64, cudaHostAllocDefault) == cudaSuccess && p) {
+    *static_cast<uint64_t *>(p) = 1;
+  } else {
+    cudaGetLastError();
+    p = std::malloc(n + 64);
+    if (!p) return nullptr;
+    *static_cast<uint64_t *>(p) = 0;
+  }
+  return static_cast<char *>(p) + 64;
+}
+void pinned_free(void *q) {
+  if (!q) return;
+  void *p = static_cast<char *>(q) - 64;
+  if (*static_cast<uint64_t *>(p) == 1) cudaFreeHost(p);
+  else std::free(p);
+}
+
 // SLIDE_PR_TRACE=1: per-phase host timings of every call on stderr (developer aid)
 struct Trace {
   bool on = std::getenv("SLIDE_PR_TRACE") != nullptr;
@@ -84,7 +105,8 @@ struct slide_pr_handle {
   // streaming reuse: the reference-map index and the lattice are rebuilt only when
   // their inputs change (same map bytes / same search ranges), e.g. many submap queries against one
   // accumulated map.  `reuse` in the result tells which were reused.
-  std::vector<double> cached_ref;   // the (shifted) reference rows the index in R was built from
+  spr::uvec<double> cached_ref;     // the (shifted) reference rows the index in R was built from
+  spr::uvec<double> qry_rows;       // copy of the query rows (source of the asynchronous upload)
   double cached_reach = -1.0;       // the index' fixed-point format covers |coordinates| up to this
   slide_pr_params cached_ref_p{};   // parameters the index depends on
   bool ref_index_valid = false;
@@ -112,8 +134,8 @@ struct slide_pr_handle {
     }                                                                                       \
   } while (0)
 
-template <typename T>
-static int upload(slide_pr_handle *h, DevBuf &b, const std::vector<T> &v, cudaStream_t st) {
+template <typename T, typename A>
+static int upload(slide_pr_handle *h, DevBuf &b, const std::vector<T, A> &v, cudaStream_t st) {
   SPR_CUDA(h, b.ensure(std::max<size_t>(v.size(), 1) * sizeof(T)));
   if (!v.empty()) SPR_CUDA(h, cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
   h->h2d_bytes += (int64_t)(v.size() * sizeof(T));
@@ -167,6 +189,8 @@ int slide_pr_create(const slide_pr_params *p, slide_pr_handle **out) {
                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     return SLIDE_PR_ERR_CUDA;
   }
+  spr::g_upload_alloc = pinned_alloc;  // uploaded host vectors are page-locked from here on
+  spr::g_upload_free = pinned_free;
   slide_pr_handle *h = new slide_pr_handle();
   h->p = *p;
   int dev = p->device;
@@ -308,7 +332,7 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   double qrad = 0;
   for (int j = 0; j < n_qry; j++) {
     const double r = std::hypot(qry7[7 * (size_t)j + 1], qry7[7 * (size_t)j + 2]);
-    if (!std::isfinite(r)) { if (lattice_job.valid()) lattice_job.get(); h->err = "non-finite query coordinate"; return SLIDE_PR_ERR_NONFINITE; }
+    if (!std::isfinite(r)) { h->err = "non-finite query coordinate"; return SLIDE_PR_ERR_NONFINITE; }
     qrad = std::max(qrad, r);
   }
   const double reach = qrad + std::max(std::fabs(half_x), std::fabs(half_y)) + h->p.match_xy_step_size;
@@ -318,13 +342,20 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
                         h->cached_ref_p.match_threshold == h->p.match_threshold &&
                         h->cached_ref_p.match_threshold_dimension == h->p.match_threshold_dimension &&
                         (n_ref == 0 || std::memcmp(h->cached_ref.data(), ref7, (size_t)n_ref * 7 * sizeof(double)) == 0);
+  std::string query_err;
+  std::future<int> query_job;
+  auto start_query_job = [&]() {
+    query_job = std::async(std::launch::async, [h, qry7, n_qry, &query_err]() { return spr::build_query_set(h->R, qry7, n_qry, h->Q, query_err); });
+  };
   if (!same_ref) {
     // stage 1 of the reference index (bitmaps, landmark tables): all the bound phase needs.  The
     // rank tables (stage 2) are built and uploaded by the search while the bound phase runs.
     h->ref_index_valid = false;
     h->ranks_pending = false;
     const double reach_cap = reach * 1.25;  // head-room so that slightly larger queries reuse the index
-    if ((rc = spr::build_ref_bitmaps(h->p, ref7, n_ref, reach_cap, h->R, h->err)) != SLIDE_PR_OK) { if (lattice_job.valid()) lattice_job.get(); return rc; }
+    if ((rc = spr::build_ref_grid(h->p, ref7, n_ref, reach_cap, h->R, h->err)) != SLIDE_PR_OK) return rc;
+    start_query_job();  // the query set only needs the labels and the grid
+    if ((rc = spr::build_ref_marks(h->p, ref7, n_ref, h->R, h->err)) != SLIDE_PR_OK) return rc;
     g_trace.mark("ref_bitmaps_build");
     h->cached_ref.assign(ref7, ref7 + (size_t)n_ref * 7);
     h->cached_reach = reach_cap; h->cached_ref_p = h->p;
@@ -334,18 +365,20 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
     if ((rc = upload(h, h->d_bitmap, h->R.bitmap, st))) return rc;
     if ((rc = upload(h, h->d_reftab, h->R.reftab, st))) return rc;
     if ((rc = upload(h, h->d_refbase, h->R.ref_base, st))) return rc;
-    if ((rc = upload_raw(h, h->d_ref7, ref7, (size_t)n_ref * 7 * sizeof(double), st))) return rc;
+    if ((rc = upload(h, h->d_ref7, h->cached_ref, st))) return rc;
     g_trace.mark("ref_bitmaps_upload");
   } else {
     h->reuse_flags |= 2;
   }
-  if ((rc = spr::build_query_set(h->R, qry7, n_qry, h->Q, h->err)) != SLIDE_PR_OK) { if (lattice_job.valid()) lattice_job.get(); return rc; }
+  if (!query_job.valid()) start_query_job();
+  if ((rc = query_job.get()) != SLIDE_PR_OK) { h->err = query_err; return rc; }
   g_trace.mark("query_set_build");
   if ((rc = upload(h, h->d_qxy, h->Q.qxy, st))) return rc;
   if ((rc = upload(h, h->d_qdims, h->Q.qdims, st))) return rc;
   if ((rc = upload(h, h->d_labelseg, h->Q.label_gseg, st))) return rc;
   if ((rc = upload(h, h->d_qlabel, h->Q.qlabel, st))) return rc;
-  if ((rc = upload_raw(h, h->d_qry7, qry7, (size_t)n_qry * 7 * sizeof(double), st))) return rc;
+  h->qry_rows.assign(qry7, qry7 + (size_t)n_qry * 7);
+  if ((rc = upload(h, h->d_qry7, h->qry_rows, st))) return rc;
   if ((rc = join_lattice()) != SLIDE_PR_OK) return rc;
   const size_t nrot = (size_t)std::max<size_t>((size_t)h->L.yaw.size() * (size_t)h->Q.nqp, 1);
   const size_t ngb = (size_t)std::max<size_t>((size_t)h->L.yaw.size() * (size_t)(h->Q.nqp / SPR_QGROUP), 1);
@@ -390,8 +423,8 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   V.Sstar = h->R.Sstar;
   V.thr_dim = h->p.match_threshold_dimension;
   V.ignore_dim = h->p.ignore_dimension;
-  // no synchronisation here: pageable cudaMemcpyAsync has staged the caller's ref7 / qry7 when it
-  // returns, and the host index vectors stay alive in the handle until the next prepare
+  // no synchronisation here: every upload reads page-locked vectors owned by the handle (the
+  // caller's rows were copied), which stay untouched until the next prepare
   h->prepared = true;
   h->prepare_ms = now_ms() - t0;
   g_trace.mark("query_upload");

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -13,6 +14,9 @@ namespace spr {
 // ------------------------------------------------------------------------------------------
 // thresholds
 // ------------------------------------------------------------------------------------------
+void *(*g_upload_alloc)(size_t) = [](size_t n) -> void * { return std::malloc(n ? n : 1); };
+void (*g_upload_free)(void *) = [](void *p) { std::free(p); };
+
 double sqrt_threshold(double thr) {
   // smallest double T with sqrt(T) >= thr, so that (sqrt(d2) < thr) == (d2 < T)  [PR.cpp:332-333]
   if (!(thr > 0)) return 0.0;  // also NaN: nothing passes
@@ -194,8 +198,8 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
   // Group the chunks by direction (every warp = 32 consecutive chunks probes ONE bitmap plane),
   // padding each group to a whole number of warps with empty chunks.  ring_major keeps the
   // chunks of a ring together (needed by the anytime budget, PR.cpp:181-191).
-  std::vector<SprChunk> &out = L.scratch;
-  out.clear();
+  uvec<SprChunk> &out = L.scratch;
+  if (ring_major) out.clear();
   out.reserve(L.chunks.size() + 64 * (ring_major ? L.ring.size() + 1 : 2));
   auto pad32 = [&out](uint32_t d) {
     SprChunk z{};
@@ -212,12 +216,48 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
         R.dend[d] = (uint32_t)out.size();
       }
   } else {
+    // Within a direction the chunks are bucketed by the 32 x 32-sample tile their first sample
+    // falls in (counting sort, emission order kept inside a bucket): the 32 chunks of a warp then
+    // lie side by side across -- neighbouring bitmap rows at the same word column, i.e. mostly
+    // distinct shared-memory banks (odd row pitch) and a compact patch for the visibility test.
+    const double tile = 32.0 * step;
+    const double lo = -std::max(std::fabs(half_x), std::fabs(half_y)) - tile;
+    const size_t nb1 = (size_t)std::floor((-2.0 * lo) / tile) + 2;
+    if (nb1 > 20000) { err = "search range spans more than 20000 chunk tiles per axis"; return SLIDE_PR_ERR_UNSUPPORTED; }
+    const size_t n_buckets = nb1 * nb1;
+    const double inv_tile = 1.0 / tile;
+    const size_t n_all = L.chunks.size();
+    std::vector<uint32_t> pos(2 * (n_buckets + 1), 0u);
+    std::vector<uint32_t> key(n_all);  // bucket inside its direction
+    const double *lat = L.lat.data();
+    auto tile_of = [&](double v) {
+      const double b = (v - lo) * inv_tile;  // >= 1 by construction of lo
+      const size_t bi = b > 0 ? (size_t)b : 0;
+      return bi >= nb1 ? nb1 - 1 : bi;
+    };
+    for (size_t i = 0; i < n_all; i++) {
+      const SprChunk &c = L.chunks[i];
+      const size_t bi = tile_of(lat[c.along_off]) * nb1 + tile_of(c.across);
+      key[i] = (uint32_t)bi;
+      pos[(size_t)c.dir * (n_buckets + 1) + bi + 1]++;
+    }
+    size_t start[2], used[2];
     for (uint32_t d = 0; d < 2; d++) {
-      L.dir_begin[d] = (uint32_t)out.size();
-      for (const SprChunk &c : L.chunks)
-        if (c.dir == d) out.push_back(c);
-      pad32(d);
-      L.dir_end[d] = (uint32_t)out.size();
+      uint32_t *pd = pos.data() + (size_t)d * (n_buckets + 1);
+      for (size_t b2 = 0; b2 < n_buckets; b2++) pd[b2 + 1] += pd[b2];
+      start[d] = d == 0 ? 0 : ((used[0] + 31) & ~(size_t)31);
+      used[d] = start[d] + pd[n_buckets];
+    }
+    const size_t total = (used[1] + 31) & ~(size_t)31;
+    if (out.size() != total) out.resize(total);  // usually the size of the previous call: nothing to do
+    for (size_t i = 0; i < n_all; i++) {
+      const uint32_t d = L.chunks[i].dir;
+      out[start[d] + pos[(size_t)d * (n_buckets + 1) + key[i]]++] = L.chunks[i];
+    }
+    for (uint32_t d = 0; d < 2; d++) {  // padding chunks (valid == 0) carry their direction
+      L.dir_begin[d] = (uint32_t)start[d];
+      L.dir_end[d] = (uint32_t)((used[d] + 31) & ~(size_t)31);
+      for (size_t i = used[d]; i < L.dir_end[d]; i++) { out[i] = SprChunk{}; out[i].dir = d; }
     }
   }
   L.ring_major = ring_major;
@@ -257,15 +297,15 @@ bool translation_of(const Lattice &L, uint64_t ordinal, double *x, double *y, in
 // ------------------------------------------------------------------------------------------
 int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, double reach,
                     RefIndex &R, std::string &err) {
-  int rc = build_ref_bitmaps(p, ref7, n_ref, reach, R, err);
+  int rc = build_ref_grid(p, ref7, n_ref, reach, R, err);
+  if (rc == SLIDE_PR_OK) rc = build_ref_marks(p, ref7, n_ref, R, err);
   for (int d = 0; d < 2 && rc == SLIDE_PR_OK; d++) rc = build_ref_ranks(ref7, d, R, err);
   return rc;
 }
 
-// Stage 1: label buckets, grid / fixed-point format, occupancy bitmaps of both directions, the
-// per-label landmark tables and label boxes -- everything the bound phase of the search reads.
-int build_ref_bitmaps(const slide_pr_params &p, const double *ref7, int n_ref, double reach,
-                      RefIndex &R, std::string &err) {
+// Stage 1a: label buckets and the grid / fixed-point format (all the query set needs).
+int build_ref_grid(const slide_pr_params &p, const double *ref7, int n_ref, double reach,
+                   RefIndex &R, std::string &err) {
   R.labels.clear();  // the vectors are reused across calls (no re-allocation / page faults)
   R.n_ref = n_ref;
   const double c = p.match_xy_step_size, thr = p.match_threshold;
@@ -318,6 +358,19 @@ int build_ref_bitmaps(const slide_pr_params &p, const double *ref7, int n_ref, d
   G.label_stride = G.plane_words[0] + G.plane_words[1];
   const uint64_t total_words = (uint64_t)G.label_stride * (uint64_t)std::max(n_labels, 1);
   if (total_words >= (1ull << 28)) { err = "occupancy bitmaps exceed 1 GiB (step too fine for this map extent)"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  return SLIDE_PR_OK;
+}
+
+// Stage 1b: marks the occupancy bitmaps of both directions, fills the per-label landmark tables
+// and the label boxes (needs build_ref_grid).
+int build_ref_marks(const slide_pr_params &p, const double *ref7, int n_ref, RefIndex &R, std::string &err) {
+  const double c = p.match_xy_step_size, thr = p.match_threshold;
+  const int n_labels = (int)R.labels.size();
+  const bool matchable = thr > 0 && std::isfinite(thr);
+  const double rad_m = matchable ? thr * (1.0 + 1e-9) + 1e-9 : 0.0;  // covers fp64 rounding of the reference's test
+  SprGrid &G = R.grid;
+  const int F = G.F;
+  const uint64_t total_words = (uint64_t)G.label_stride * (uint64_t)std::max(n_labels, 1);
   R.bitmap.assign((size_t)total_words, 0u);
   // per-label bounds of the marked cells (empty until a cell is marked)
   struct CellBounds { int x0, x1, y0, y1; };
@@ -432,10 +485,10 @@ int build_ref_ranks(const double *ref7, int d, RefIndex &R, std::string &err) {
     // appended behind the n_cells first ones and chained in ascending landmark order.
     // cellref[d][rank] = slot (inside the label's landmark table) of the cell's only candidate,
     // or SPR_CELL_MULTI when the cell has several candidates (then cand[d] is walked).
-    std::vector<SprCand> &cand = R.cand[d];
+    uvec<SprCand> &cand = R.cand[d];
     cand.resize(std::max<size_t>(entries.size(), 1));  // every slot below is overwritten
     cand[0] = SprCand{0, 0, 0, 0, 0, 0u, 0u};
-    std::vector<uint16_t> &cellref = R.cellref[d];
+    uvec<uint16_t> &cellref = R.cellref[d];
     cellref.assign(n_cells + 16, 0);  // + slack for aligned bulk copies
     std::vector<uint32_t> tail(n_cells, 0xffffffffu);  // last record of each cell's chain
     size_t extra = n_cells;

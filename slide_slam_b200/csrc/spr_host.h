@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <new>
 #include <vector>
 
 #include "../../include/slide_pr.h"
@@ -11,13 +12,34 @@
 
 namespace spr {
 
+// Host buffers that are copied to the device are allocated through a pair of hooks so that the
+// library can make them page-locked (true asynchronous DMA, no staging copy); the default hooks
+// are malloc / free (tests, emulation).
+extern void *(*g_upload_alloc)(size_t bytes);
+extern void (*g_upload_free)(void *p);
+template <class T>
+struct UploadAlloc {
+  using value_type = T;
+  UploadAlloc() = default;
+  template <class U> UploadAlloc(const UploadAlloc<U> &) {}
+  T *allocate(size_t n) {
+    void *p = g_upload_alloc(n * sizeof(T));
+    if (!p) throw std::bad_alloc();
+    return static_cast<T *>(p);
+  }
+  void deallocate(T *p, size_t) { g_upload_free(p); }
+  template <class U> bool operator==(const UploadAlloc<U> &) const { return true; }
+  template <class U> bool operator!=(const UploadAlloc<U> &) const { return false; }
+};
+template <class T> using uvec = std::vector<T, UploadAlloc<T>>;
+
 struct Lattice {
   int status = 0;                 // 0 ok, SLIDE_PR_SANITY_RETURN on PR.cpp:169-175
   int rings = 0;
   double ox = 0, oy = 0;          // outer_loop_step_size_{x,y}
   std::vector<double> yaw;        // PR.cpp:136-146
   std::vector<double> cs;         // cos, sin per yaw (libm)
-  std::vector<double> lat;        // per ring: xs then ys
+  uvec<double> lat;        // per ring: xs then ys
   struct Ring {
     uint32_t x_off, nx, y_off, ny;  // into lat
     int ixl, ixh, iyl, iyh;         // inner (already searched) box as closed index ranges; empty if l > h
@@ -28,8 +50,8 @@ struct Lattice {
   };
   std::vector<Ring> ring;
   uint64_t n_translations = 0;
-  std::vector<SprChunk> chunks;   // grouped by direction (see dir_begin / Ring::dbegin), warp-padded
-  std::vector<SprChunk> scratch;  // regrouping buffer, kept for its capacity
+  uvec<SprChunk> chunks;   // grouped by direction (see dir_begin / Ring::dbegin), warp-padded
+  uvec<SprChunk> scratch;  // regrouping buffer, kept for its capacity
   bool ring_major = false;
   uint32_t dir_begin[2] = {0, 0}, dir_end[2] = {0, 0};  // !ring_major: all chunks of direction d
 };
@@ -45,13 +67,13 @@ bool translation_of(const Lattice &L, uint64_t ordinal, double *x, double *y, in
 struct RefIndex {
   std::vector<double> labels;       // distinct finite reference labels, ascending
   SprGrid grid{};
-  std::vector<uint32_t> bitmap;     // [n_labels][plane0 | plane1]
-  std::vector<SprCand> cand[2];      // per plane direction d: [n_cells] first candidate per cell rank, then chained extras
-  std::vector<uint16_t> rank16[2];   // per plane direction d: [n_labels][plane_words[d]] marked cells of the row before the word
-  std::vector<uint32_t> row_rank[2]; // per plane direction d: [n_labels][R[d]] rank (index into cand[d]) of the row's first marked cell
-  std::vector<uint16_t> cellref[2];  // per plane direction d: [n_cells] slot of the cell's only candidate in its label's table, or SPR_CELL_MULTI
+  uvec<uint32_t> bitmap;     // [n_labels][plane0 | plane1]
+  uvec<SprCand> cand[2];      // per plane direction d: [n_cells] first candidate per cell rank, then chained extras
+  uvec<uint16_t> rank16[2];   // per plane direction d: [n_labels][plane_words[d]] marked cells of the row before the word
+  uvec<uint32_t> row_rank[2]; // per plane direction d: [n_labels][R[d]] rank (index into cand[d]) of the row's first marked cell
+  uvec<uint16_t> cellref[2];  // per plane direction d: [n_cells] slot of the cell's only candidate in its label's table, or SPR_CELL_MULTI
   std::vector<uint32_t> cell_base[2]; // per plane direction d: [n_labels + 1] rank of each label's first cell
-  std::vector<double> reftab;        // [n_ref kept][5] x, y, d1, d2, d3, label-major
+  uvec<double> reftab;        // [n_ref kept][5] x, y, d1, d2, d3, label-major
   std::vector<uint32_t> ref_base;    // [n_labels + 1] first row of each label in reftab
   std::vector<SprBox> labelbox;     // [n_labels] fixed-point bounds of the label's marked cells
   double Tstar = 0, Sstar = 0;
@@ -67,10 +89,12 @@ struct RefIndex {
 // fixes the fixed-point format.  Returns SLIDE_PR_OK or an error code.
 int build_ref_index(const slide_pr_params &p, const double *ref7, int n_ref, double reach,
                     RefIndex &R, std::string &err);
-// The two stages of build_ref_index: the occupancy bitmaps (all the bound phase of the search
-// needs) and, per bitmap direction, the rank tables / candidate records of the exact verification.
-int build_ref_bitmaps(const slide_pr_params &p, const double *ref7, int n_ref, double reach,
-                      RefIndex &R, std::string &err);
+// The stages of build_ref_index: labels + grid (all build_query_set needs), the occupancy bitmaps
+// (all the bound phase of the search needs) and, per bitmap direction, the rank tables / candidate
+// records of the exact verification.
+int build_ref_grid(const slide_pr_params &p, const double *ref7, int n_ref, double reach,
+                   RefIndex &R, std::string &err);
+int build_ref_marks(const slide_pr_params &p, const double *ref7, int n_ref, RefIndex &R, std::string &err);
 int build_ref_ranks(const double *ref7, int d, RefIndex &R, std::string &err);
 
 struct QuerySet {

@@ -112,6 +112,8 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
       for (int i = 0; i < PLANES; i++) P[i] = __ldcs(gp + i * 32);
     }
 
+    uint32_t pend8 = 0u, pend16 = 0u;
+    bool have8 = false, have16 = false;
     if (X0 <= X1) {
       for (int k = 0; k < B.n_labels; k++) {
         const int l = B.labels[k];
@@ -123,24 +125,6 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
         const int32_t tx_lo = lb.x0 - X1, tx_hi = lb.x1 - X0, ty_lo = lb.y0 - Y1, ty_hi = lb.y1 - Y0;
         const int4 *gbp = reinterpret_cast<const int4 *>(V.gbox) + ((size_t)a * (size_t)V.n_groups + (size_t)g0);
         const int4 *qgp = reinterpret_cast<const int4 *>(q_fx + 2 * (size_t)a * (size_t)V.nqp) + (size_t)g0 * (SPR_QGROUP / 2);
-        uint32_t A0 = 0u, A1 = 0u, A2 = 0u, A3 = 0u, A4 = 0u;  // low accumulator: up to 3 groups of 8
-        int nA = 0;
-        auto flush = [&]() {
-          uint32_t c = P[0] & A0;
-          P[0] ^= A0;
-          spb_fa(P[1], A1, c, P[1], c);
-          spb_fa(P[2], A2, c, P[2], c);
-          spb_fa(P[3], A3, c, P[3], c);
-          spb_fa(P[4], A4, c, P[4], c);
-#pragma unroll
-          for (int i = 5; i < PLANES; i++) {
-            const uint32_t t = P[i] & c;
-            P[i] ^= c;
-            c = t;
-          }
-          A0 = A1 = A2 = A3 = A4 = 0u;
-          nA = 0;
-        };
         for (int gb = g0; gb < g1; gb += 32) {
           bool vis = false;
           if (gb + lane < g1) {
@@ -161,26 +145,53 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
               H[2 * u] = spr_probe(bits, W, Rm1, maxbit, F, aqb + v[u].x, bqb + v[u].y, SPR_FULL);
               H[2 * u + 1] = spr_probe(bits, W, Rm1, maxbit, F, aqb + v[u].z, bqb + v[u].w, SPR_FULL);
             }
-            // 8 one-bit addends -> ones / twos / fours / eights
-            uint32_t s0, c0_, s1, c1, s2, c2, t0, f0;
-            spb_fa(H[0], H[1], H[2], s0, c0_);
-            spb_fa(H[3], H[4], H[5], s1, c1);
-            spb_fa(H[6], H[7], s0, s2, c2);
-            const uint32_t o = s1 ^ s2, c3 = s1 & s2;
-            spb_fa(c0_, c1, c2, t0, f0);
-            const uint32_t t = t0 ^ c3, f1 = t0 & c3;
-            const uint32_t f = f0 ^ f1, e = f0 & f1;
-            uint32_t c = A0 & o;
-            A0 ^= o;
-            spb_fa(A1, t, c, A1, c);
-            spb_fa(A2, f, c, A2, c);
-            spb_fa(A3, e, c, A3, c);
-            A4 ^= c;
-            if (++nA == 3) flush();
+            // carry-save counting: P[0..4] are the running ones / twos / fours / eights / sixteens
+            // planes; every group folds its 8 one-bit addends in with 7 carry-save adders and emits
+            // one plane of weight 8, two of those make one of weight 16, two of those one of weight
+            // 32, which ripples into the upper planes
+            uint32_t tA, tB, fA, fB, e8;
+            spb_fa(P[0], H[0], H[1], P[0], tA);
+            spb_fa(P[0], H[2], H[3], P[0], tB);
+            spb_fa(P[1], tA, tB, P[1], fA);
+            spb_fa(P[0], H[4], H[5], P[0], tA);
+            spb_fa(P[0], H[6], H[7], P[0], tB);
+            spb_fa(P[1], tA, tB, P[1], fB);
+            spb_fa(P[2], fA, fB, P[2], e8);
+            if (have8) {
+              uint32_t s16;
+              spb_fa(P[3], pend8, e8, P[3], s16);
+              have8 = false;
+              if (have16) {
+                uint32_t c;
+                spb_fa(P[4], pend16, s16, P[4], c);
+                have16 = false;
+#pragma unroll
+                for (int i = 5; i < PLANES; i++) {
+                  const uint32_t t = P[i] & c;
+                  P[i] ^= c;
+                  c = t;
+                }
+              } else {
+                pend16 = s16;
+                have16 = true;
+              }
+            } else {
+              pend8 = e8;
+              have8 = true;
+            }
           }
         }
-        if (nA) flush();
       }
+    }
+    if (have8) {  // pending planes back into the binary counter
+      uint32_t c = pend8;
+#pragma unroll
+      for (int i = 3; i < PLANES; i++) { const uint32_t t = P[i] & c; P[i] ^= c; c = t; }
+    }
+    if (have16) {
+      uint32_t c = pend16;
+#pragma unroll
+      for (int i = 4; i < PLANES; i++) { const uint32_t t = P[i] & c; P[i] ^= c; c = t; }
     }
 #pragma unroll
     for (int i = 0; i < PLANES; i++) {
