@@ -538,18 +538,26 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     B.seed_key = h->d_seed.as<unsigned long long>();
     for (uint32_t d = 0; d < 2; d++) {
       if (h->L.dir_end[d] <= h->L.dir_begin[d]) continue;
-      int per = spr_bound_labels_per_launch(h->V, d);
-      if (per <= 0) per = SPR_BOUND_MAX_LABELS;  // planes too large for shared memory: read in place
-      for (size_t i = 0; i < active.size(); i += (size_t)per) {
-        B.chunk_begin = h->L.dir_begin[d]; B.chunk_end = h->L.dir_end[d]; B.dir = d;
-        B.n_labels = (int32_t)std::min<size_t>((size_t)per, active.size() - i);
-        for (int k = 0; k < B.n_labels; k++) B.labels[k] = active[i + (size_t)k];
-        B.first = i == 0; B.last = i + (size_t)per >= active.size();
-        if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
-        B.work_counter = K.work_counter;
-        SPR_CUDA(h, spr_launch_bound_lattice(h->V, B, n_planes, h->sm_count, st, &launches));
-        K.work_counter++;
-        passes_left--;
+      int per = 1;
+      uint32_t band_rows = 0;
+      spr_bound_plan(h->V, d, (int)active.size(), &per, &band_rows);
+      const uint32_t R = (uint32_t)h->V.grid.R[d];
+      const uint32_t n_bands = band_rows ? (R + band_rows - 1) / band_rows : 1;
+      for (uint32_t band = 0; band < n_bands; band++) {
+        for (size_t i = 0; i < active.size(); i += (size_t)per) {
+          B.chunk_begin = h->L.dir_begin[d]; B.chunk_end = h->L.dir_end[d]; B.dir = d;
+          B.row_begin = band_rows ? band * band_rows : 0u;
+          B.row_end = band_rows ? std::min(R, (band + 1) * band_rows) : 0u;
+          B.n_labels = (int32_t)std::min<size_t>((size_t)per, active.size() - i);
+          for (int k = 0; k < B.n_labels; k++) B.labels[k] = active[i + (size_t)k];
+          B.first = band == 0 && i == 0;
+          B.last = band + 1 == n_bands && i + (size_t)per >= active.size();
+          if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
+          B.work_counter = K.work_counter;
+          SPR_CUDA(h, spr_launch_bound_lattice(h->V, B, n_planes, h->sm_count, st, &launches));
+          K.work_counter++;
+          passes_left--;
+        }
       }
     }
     if (h->ranks_pending) {

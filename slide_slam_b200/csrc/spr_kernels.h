@@ -46,6 +46,7 @@ struct SprBoundLaunch {
   int32_t  labels[SPR_BOUND_MAX_LABELS];
   int32_t  first, last;             // first / last launch over these chunks: planes start at 0 / item maxima are produced
   int32_t  shard_index, shard_count;
+  uint32_t row_begin, row_end;      // rows of the planes staged in shared memory (row_end == row_begin: read in place)
   uint32_t *planes;                 // device: bit planes of the bounds (layout of SprLaunch::ub_planes)
   uint32_t *item_ub;                // device: [yaw][chunk / 32]
   unsigned long long *seed_key;     // device: [n_yaw] (bound + 1) << 40 | chunk * 32 + bit of the best-bounded hypothesis
@@ -65,7 +66,7 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int t
 
 // bound phase of the bound-and-verify search (spr_kernels_bound.cu)
 int spr_bound_planes(int nqp);                                   // bit planes needed for counts <= nqp (12 or 16)
-int spr_bound_labels_per_launch(const SprView &V, uint32_t dir); // label planes that fit in shared memory (0: none)
+void spr_bound_plan(const SprView &V, uint32_t dir, int n_active, int *labels_per_launch, uint32_t *band_rows);
 cudaError_t spr_launch_bound_lattice(const SprView &V, const SprBoundLaunch &B, int n_planes, int sm_count, cudaStream_t st,
                                      int *n_launches);
 // work items of direction `B.dir` whose largest bound reaches the running best -> items[0 .. *count)

@@ -21,6 +21,9 @@
 
 #define SPR_FULL 0xffffffffu
 #define SPR_SMEM_LIMIT (227 * 1024)
+#ifndef SPB_THREADS
+#define SPB_THREADS 1024
+#endif
 
 __device__ __forceinline__ uint32_t spb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void spb_mbar_init(uint64_t *bar, uint32_t count) {
@@ -50,7 +53,7 @@ __device__ __forceinline__ void spb_fa(uint32_t a, uint32_t b, uint32_t c, uint3
 }
 
 template <int PLANES, bool SMEM_TAB>
-__global__ void __launch_bounds__(SMEM_TAB ? 1024 : 256, SMEM_TAB ? 1 : 4)
+__global__ void __launch_bounds__(SMEM_TAB ? SPB_THREADS : 256, SMEM_TAB ? 1 : 4)
 spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constant__ SprBoundLaunch B, const int n_wg_local,
                          const long long n_items) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -58,24 +61,37 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
   const SprGrid &G = V.grid;
   const int32_t F = G.F;
   const uint32_t d = B.dir;
-  const uint32_t W = (uint32_t)G.W[d], Rm1 = (uint32_t)G.R[d] - 1u, maxbit = (uint32_t)G.maxbit[d];
-  const uint32_t PW = G.plane_words[d];
+  const uint32_t W = (uint32_t)G.W[d], maxbit = (uint32_t)G.maxbit[d];
+  // Row band [row_begin, row_end) of the planes handled by this launch (the whole plane unless it
+  // does not fit in shared memory).  Staged as band_rows rows + one all-zero row per label; rows
+  // outside the band clamp onto the zero row (unsigned min), so the probe code is unchanged.
+  const uint32_t band_rows = SMEM_TAB ? B.row_end - B.row_begin : (uint32_t)G.R[d];
+  const uint32_t Rm1 = SMEM_TAB ? band_rows : (uint32_t)G.R[d] - 1u;
+  const uint32_t BW = ((band_rows + 1u) * W + 3u) & ~3u;  // words per staged label (16-byte aligned bulk-copy targets)
+  const int32_t row_shift = SMEM_TAB ? (int32_t)(B.row_begin << F) : 0;
 
-  if (SMEM_TAB) {  // the bitmap planes of this launch's labels, one TMA bulk copy each
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)B.n_labels * PW);
+  if (SMEM_TAB) {  // one TMA bulk copy per label
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (((size_t)B.n_labels * BW + 3) & ~(size_t)3));
     if (threadIdx.x == 0) {
       spb_mbar_init(bar, 1u);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (uint32_t i = threadIdx.x; i < (uint32_t)B.n_labels * W; i += blockDim.x)
+      smem[(size_t)(i / W) * BW + (size_t)band_rows * W + (i % W)] = 0u;
     __syncthreads();
     if (threadIdx.x == 0) {
-      spb_mbar_expect_tx(bar, (uint32_t)B.n_labels * PW * 4u);
+      spb_mbar_expect_tx(bar, (uint32_t)B.n_labels * band_rows * W * 4u);
       for (int k = 0; k < B.n_labels; k++)
-        spb_bulk_g2s(smem + (size_t)k * PW, V.bitmap + ((size_t)B.labels[k] * G.label_stride + (d ? G.plane_words[0] : 0u)), PW * 4u, bar);
+        spb_bulk_g2s(smem + (size_t)k * BW,
+                     V.bitmap + ((size_t)B.labels[k] * G.label_stride + (d ? G.plane_words[0] : 0u) + (size_t)B.row_begin * W),
+                     band_rows * W * 4u, bar);
     }
     for (uint32_t spin = 0; !spb_mbar_try_wait(bar, 0u); spin++)
       if (spin > 200000000u) __trap();  // a lost copy must not hang the GPU
   }
+  // across range (fixed point) covered by the band: plane row r holds across cell r - 1
+  const int32_t band_lo = SMEM_TAB ? ((int32_t)B.row_begin - 1) << F : -(1 << 30);
+  const int32_t band_hi = SMEM_TAB ? ((int32_t)B.row_end - 1) << F : (1 << 30);
   const int32_t *q_fx = d ? V.qrotq_yx : V.qrotq_xy;
   const uint32_t n_wg_total = B.n_chunks_total / SPR_WARP_CHUNKS;
 
@@ -93,7 +109,7 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
     const uint32_t along_off = c0.z, valid = c0.w;
     const int32_t aq0 = spr_fx(across, G.S);
     const int32_t bq0 = spr_fx(__ldg(V.lat + along_off), G.S);
-    const int32_t aqb = spr_bias_across(aq0, F), bqb = spr_bias_along(bq0, F);
+    const int32_t aqb = spr_bias_across(aq0, F) - row_shift, bqb = spr_bias_along(bq0, F);
     const int32_t big = 1 << 30;
     const bool live = valid != 0u;
     const int32_t lx0 = d ? bq0 : aq0, lx1 = d ? bq0 + (32 << F) : aq0;
@@ -119,9 +135,12 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
         const int l = B.labels[k];
         const int g0 = V.label_gseg[l], g1 = V.label_gseg[l + 1];
         if (g0 >= g1) continue;
-        const uint32_t *bits = SMEM_TAB ? smem + (size_t)k * PW
+        const uint32_t *bits = SMEM_TAB ? smem + (size_t)k * BW
                                         : V.bitmap + ((size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u));
-        const SprBox lb = V.labelbox[l];
+        SprBox lb = V.labelbox[l];
+        if (d == 0) { lb.x0 = max(lb.x0, band_lo); lb.x1 = min(lb.x1, band_hi); }  // marked cells inside the band
+        else        { lb.y0 = max(lb.y0, band_lo); lb.y1 = min(lb.y1, band_hi); }
+        if (lb.x0 >= lb.x1 || lb.y0 >= lb.y1) continue;
         const int32_t tx_lo = lb.x0 - X1, tx_hi = lb.x1 - X0, ty_lo = lb.y0 - Y1, ty_hi = lb.y1 - Y0;
         const int4 *gbp = reinterpret_cast<const int4 *>(V.gbox) + ((size_t)a * (size_t)V.n_groups + (size_t)g0);
         const int4 *qgp = reinterpret_cast<const int4 *>(q_fx + 2 * (size_t)a * (size_t)V.nqp) + (size_t)g0 * (SPR_QGROUP / 2);
@@ -132,13 +151,35 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
             vis = box.y > tx_lo && box.x < tx_hi && box.w > ty_lo && box.z < ty_hi;
           }
           uint32_t vm = __ballot_sync(SPR_FULL, vis);
+#ifdef SPB_DB
+          int4 nx[SPR_QGROUP / 2];
+          if (vm) {
+            const int4 *q = qgp + (size_t)(gb - g0 + (__ffs(vm) - 1)) * (SPR_QGROUP / 2);
+#pragma unroll
+            for (int u = 0; u < SPR_QGROUP / 2; u++) nx[u] = __ldg(q + u);
+          }
+#endif
           while (vm) {
             const int kk = __ffs(vm) - 1;
             vm &= vm - 1;
             const int4 *q = qgp + (size_t)(gb - g0 + kk) * (SPR_QGROUP / 2);
+#ifdef SPB_PREFETCH
+            if (vm) asm volatile("prefetch.global.L1 [%0];" ::"l"(qgp + (size_t)(gb - g0 + (__ffs(vm) - 1)) * (SPR_QGROUP / 2)));
+#endif
             int4 v[SPR_QGROUP / 2];
+#ifdef SPB_DB
+#pragma unroll
+            for (int u = 0; u < SPR_QGROUP / 2; u++) v[u] = nx[u];
+            if (vm) {  // the next visible group's coordinates are in flight while this one is probed
+              const int4 *qn = qgp + (size_t)(gb - g0 + (__ffs(vm) - 1)) * (SPR_QGROUP / 2);
+#pragma unroll
+              for (int u = 0; u < SPR_QGROUP / 2; u++) nx[u] = __ldg(qn + u);
+            }
+            (void)q;
+#else
 #pragma unroll
             for (int u = 0; u < SPR_QGROUP / 2; u++) v[u] = __ldg(q + u);
+#endif
             uint32_t H[SPR_QGROUP];
 #pragma unroll
             for (int u = 0; u < SPR_QGROUP / 2; u++) {
@@ -311,22 +352,44 @@ cudaError_t spr_launch_select_items(const SprView &V, const SprBoundLaunch &B, c
 
 int spr_bound_planes(int nqp) { return nqp < 4096 ? 12 : 16; }
 
-int spr_bound_labels_per_launch(const SprView &V, uint32_t dir) {
-  const size_t pb = (size_t)V.grid.plane_words[dir] * 4;
-  const int fit = (int)((SPR_SMEM_LIMIT - 64) / (pb ? pb : 1));
-  return fit < 1 ? 0 : (fit > SPR_BOUND_MAX_LABELS ? SPR_BOUND_MAX_LABELS : fit);
+// Splits the planes of direction `dir` for the bound launches: as many whole label planes per
+// launch as fit in shared memory, or -- when one plane does not fit -- one label per launch and
+// row bands (multiples of 4 rows: 16-byte aligned bulk copies).  band_rows == 0: planes stay in
+// global memory (a single row does not fit).
+void spr_bound_plan(const SprView &V, uint32_t dir, int n_active, int *labels_per_launch, uint32_t *band_rows) {
+  const size_t W4 = (size_t)V.grid.W[dir] * 4, R = (size_t)V.grid.R[dir];
+  const size_t limit = SPR_SMEM_LIMIT - 64;
+  if ((R + 1) * W4 + 16 <= limit) {
+    int per = (int)(limit / ((R + 1) * W4 + 16));
+    if (per > SPR_BOUND_MAX_LABELS) per = SPR_BOUND_MAX_LABELS;
+    if (per > n_active) per = n_active;
+    // spread the labels evenly over the launches (5 labels, 4 fit -> 3 + 2)
+    const int launches = (n_active + per - 1) / per;
+    *labels_per_launch = (n_active + launches - 1) / launches;
+    *band_rows = (uint32_t)R;
+    return;
+  }
+  *labels_per_launch = 1;
+  size_t max_rows = limit / W4;
+  // Row bands cost one launch (and one pass over the counters of every work item) per band: they
+  // pay off when a work item has many query landmarks to probe; small query maps against a large
+  // reference map (streaming submap queries) read the planes in place through L1 / L2 instead.
+  if (max_rows < 9 || V.nqp < 2048) { *band_rows = 0; *labels_per_launch = SPR_BOUND_MAX_LABELS; return; }
+  max_rows = (max_rows - 1) & ~(size_t)3;
+  const size_t bands = (R + max_rows - 1) / max_rows;
+  *band_rows = (uint32_t)((((R + bands - 1) / bands) + 3) & ~(size_t)3);
 }
 
 template <int PLANES>
 static cudaError_t spb_launch(const SprView &V, const SprBoundLaunch &B, int n_wg_local, long long n_items, int sm_count,
                               cudaStream_t st) {
-  const size_t pb = (size_t)V.grid.plane_words[B.dir] * 4;
-  const size_t smem = (size_t)B.n_labels * pb + 16;
-  if (smem <= SPR_SMEM_LIMIT) {
+  const size_t BW4 = (((size_t)(B.row_end - B.row_begin + 1) * (size_t)V.grid.W[B.dir] + 3) & ~(size_t)3) * 4;
+  const size_t smem = (((size_t)B.n_labels * BW4 + 15) & ~(size_t)15) + 16;
+  if (B.row_end > B.row_begin && smem <= SPR_SMEM_LIMIT) {
     cudaError_t e = cudaFuncSetAttribute(spr_bound_lattice_kernel<PLANES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const long long want = (n_items + 31) / 32;
-    spr_bound_lattice_kernel<PLANES, true><<<(int)(want < sm_count ? want : sm_count), 1024, smem, st>>>(V, B, n_wg_local, n_items);
+    const long long want = (n_items + SPB_THREADS / 32 - 1) / (SPB_THREADS / 32);
+    spr_bound_lattice_kernel<PLANES, true><<<(int)(want < sm_count ? want : sm_count), SPB_THREADS, smem, st>>>(V, B, n_wg_local, n_items);
   } else {
     const long long want = (n_items + 7) / 8, cap = (long long)sm_count * 4;
     spr_bound_lattice_kernel<PLANES, false><<<(int)(want < cap ? want : cap), 256, 0, st>>>(V, B, n_wg_local, n_items);

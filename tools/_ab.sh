@@ -1,4 +1,4 @@
-python -m pytest tests -x -q -m gpu > gpurun_out/ab_t.log 2>&1; tail -3 gpurun_out/ab_t.log
-python tools/quick_bench.py 2 2>&1 | grep cfg2
-for v in variants/libslide_pr_b_SPB_CSA.so; do SLIDE_PR_LIB=$v python tools/quick_bench.py 2 2>&1 | grep cfg2 | head -1; done
-SLIDE_PR_TRACE=1 python tools/_trace.py 2>&1 | tail -4
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_c3.csv python tools/profile_target.py 3 20000 1 > gpurun_out/ncu_c3.log 2>&1
+tail -3 gpurun_out/ncu_c3.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c5.csv python bench.py --config 5 --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_c5.log 2>&1
+tail -2 gpurun_out/ncu_c5.log | cut -c1-300
