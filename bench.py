@@ -37,6 +37,8 @@ ROS = {"search_xy_step_size": 0.5, "search_yaw_step_size_degrees": 5.0, "match_t
        "match_threshold_dimension": 1.0, "ignore_dimension": 0, "min_num_inliers": 15, "dilation_factor": 1.2}
 ORACLE_KW = dict(match_xy_step_size=0.5, yaw_step_deg=5.0, match_threshold=0.5, match_threshold_dimension=1.0,
                  ignore_dimension=0, min_num_inliers=15)
+ROOFLINE_TRAFFIC_BYTES = 6.7e6   # per launch, profiles/r1_m_bound_lattice_summary.txt
+ROOFLINE_TRAFFIC_SOURCE = "profiles/r1_m_bound_lattice_summary.txt (ncu --set full, per launch)"
 ALG_BYTES_PER_HYP = 24.0  # 16 B hypothesis record + 8 B packed score
 METRIC = "hypotheses_scored_per_s"
 UNIT = "hypotheses/s"
@@ -261,6 +263,19 @@ def run_ours(args, rank, world, local_rank):
         hyps_all, launches_all, kernel_total_ms = float(hyps), int(launches), float(sum(kern_ms))
     clocks = sampler.stop() if rank == 0 else None
 
+    # the same search with EVERY hypothesis verified exactly (no bound-and-verify pruning), rank 0's GPU
+    exh_ms = []
+    if rank == 0:
+        for i in range(2 + min(args.steps, 5)):
+            flush.fill_(1)
+            r_x, _ = pr.search(stream=stream.cuda_stream, exhaustive=True)
+            if i >= 2:
+                exh_ms.append(r_x.kernel_ms)
+        exh = {"value_per_gpu": float(r_x.hypotheses_scored) / (float(np.mean(exh_ms)) * 1e-3), "unit": UNIT,
+               "kernel_ms_per_step": float(np.mean(exh_ms)), "best_num_inliers": int(r_x.best_num_inliers),
+               "same_winner": bool(r_x.best_hyp_index == res.best_hyp_index and r_x.best_num_inliers == res.best_num_inliers),
+               "note": "slide_pr_search_opts.exhaustive = 1: exact inlier count of every hypothesis (the mode used with counts_out)"}
+
     # end-to-end through the public API with host buffers.  Two DISTINCT map pairs alternate so that
     # nothing (lattice, reference-map index) can be reused from the previous step: every step pays
     # the full host index build, the H2D copies, the kernels, the D2H of the result and the refinement.
@@ -303,9 +318,12 @@ def run_ours(args, rank, world, local_rank):
                        "lattice": "0.5 m / 5 deg, dilation 1.2 (sloam-forest-parking-lot.yaml)",
                        "parallelism": ("hypothesis space of one pair sharded over %d GPUs, NCCL all-gather of top-1" % world) if shard_mode
                        else ("one map pair per GPU (the same synthetic pair on every rank), NCCL all-gather of results" if world > 1 else "single GPU"),
-                       "l2": "flushed between timed steps (256 MiB write)", "decision_arithmetic": "fp64, non-fused (bit-exact vs reference)"},
+                       "l2": "flushed between timed steps (256 MiB write)", "decision_arithmetic": "fp64, non-fused (bit-exact vs reference)",
+                       "search": "bound-and-verify (library default): bitmap-filter upper bound of every hypothesis, exact fp64 verification of "
+                                 "those whose bound reaches the running best; winner, inlier count and correspondences identical to the exhaustive search"},
             "best_num_inliers": int(info.best_num_inliers), "closure_found": bool(found),
             "kernel_ms_per_step": kernel_total_ms / max(args.steps, 1),
+            "exhaustive": exh,
             "gpu_launches": launches_all,
             "clocks": clocks,
             "e2e": {"value": e2e_hyps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(info.match.h2d_bytes),
@@ -315,13 +333,15 @@ def run_ours(args, rank, world, local_rank):
                     "note": "two distinct map pairs alternate, so every step rebuilds and re-uploads all index structures",
                     "api": "PlaceRecognition.findTransformation -> slide_pr_find_transformation (host buffers)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read + dram__bytes_write of one (label, direction) pass launch, from the
-                         # committed ncu capture profiles/r1_final_score_lattice_summary.txt (the counters
-                         # carried between passes; the maps and index tables stay in L2 / shared memory)
-                         "traffic": 82.3e6, "traffic_source": "profiles/r1_final_score_lattice_summary.txt (ncu --set full, per launch)",
-                         "peak_source": peak_src,
-                         "note": "algorithmic 24 B/hypothesis (SURVEY 8d); the kernel is issue-bound on L1/L2-resident bitmaps, "
-                                 "see DESIGN.md section 5 for issue-slot utilisation from ncu"},
+                         # dram__bytes_read + dram__bytes_write per launch of the dominant kernel
+                         # (spr_bound_lattice_kernel, 4 launches per step) from the committed ncu capture:
+                         # the bit planes of the bounds carried between the launches; maps and bitmaps
+                         # stay in L2 / shared memory
+                         "traffic": ROOFLINE_TRAFFIC_BYTES, "traffic_source": ROOFLINE_TRAFFIC_SOURCE,
+                         "peak_source": peak_src, "kernel": "spr_bound_lattice_kernel",
+                         "note": "algorithmic 24 B/hypothesis (SURVEY 8d) x hypotheses of a step / summed kernel time of the step; "
+                                 "the kernel is ALU-pipe / shared-memory bound on bitmaps staged in shared memory, not HBM-bound: "
+                                 "see DESIGN.md section 5 for the issue-slot and pipe utilisation from ncu"},
         }
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pyoracle as O

@@ -10,9 +10,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
-#include <future>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/slide_pr.h"
@@ -64,6 +67,50 @@ void pinned_free(void *q) {
   else std::free(p);
 }
 
+// One persistent helper thread: runs one job at a time (submit, then wait).  The handle owns two,
+// so that the lattice and the query set are built while the calling thread marks the bitmaps.
+class Worker {
+ public:
+  Worker() : th_([this] { loop(); }) {}
+  ~Worker() {
+    { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+    cv_.notify_all();
+    th_.join();
+  }
+  void submit(std::function<int()> job) {
+    { std::lock_guard<std::mutex> g(m_); job_ = std::move(job); busy_ = true; }
+    cv_.notify_all();
+  }
+  bool pending() const { return busy_; }
+  int wait() {  // result of the last submitted job (0 if none)
+    std::unique_lock<std::mutex> g(m_);
+    cv_.wait(g, [this] { return !busy_; });
+    return result_;
+  }
+ private:
+  void loop() {
+    std::unique_lock<std::mutex> g(m_);
+    for (;;) {
+      cv_.wait(g, [this] { return stop_ || (busy_ && job_); });
+      if (stop_) return;
+      std::function<int()> job = std::move(job_);
+      job_ = nullptr;
+      g.unlock();
+      const int r = job();
+      g.lock();
+      result_ = r;
+      busy_ = false;
+      cv_.notify_all();
+    }
+  }
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::function<int()> job_;
+  bool busy_ = false, stop_ = false;
+  int result_ = 0;
+  std::thread th_;
+};
+
 // SLIDE_PR_TRACE=1: per-phase host timings of every call on stderr (developer aid)
 struct Trace {
   bool on = std::getenv("SLIDE_PR_TRACE") != nullptr;
@@ -92,7 +139,10 @@ struct slide_pr_handle {
   bool force_exhaustive = false;  // env SLIDE_PR_EXHAUSTIVE=1
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // uploads that overlap the bound phase of a search
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
+  cudaStream_t side_stream = nullptr;  // verification passes of the second bitmap direction
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr, ev_prep = nullptr;  // ev_prep: prepare's uploads enqueued
+  Worker worker_lattice, worker_query;  // helper threads of slide_pr_prepare
   bool ranks_pending = false;          // stage 2 of the reference index (rank tables) not built / uploaded yet
   const double *pending_ref7 = nullptr; // == cached_ref.data() while ranks_pending
   std::string err;
@@ -199,8 +249,12 @@ int slide_pr_create(const slide_pr_params *p, slide_pr_handle **out) {
   h->device = dev;
   if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming)) != cudaSuccess) {
+      (e = cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->ev_prep, cudaEventDisableTiming)) != cudaSuccess) {
     g_create_error = std::string("CUDA init: ") + cudaGetErrorString(e);
     delete h;
     return SLIDE_PR_ERR_CUDA;
@@ -226,6 +280,10 @@ void slide_pr_destroy(slide_pr_handle *h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  if (h->ev_prep) cudaEventDestroy(h->ev_prep);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -308,19 +366,26 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
                             h->lat_p.match_yaw_angle_step_size == h->p.match_yaw_angle_step_size &&
                             h->lat_p.disable_yaw_search == h->p.disable_yaw_search &&
                             (h->lat_p.compute_budget_sec > 0) == (h->p.compute_budget_sec > 0);
-  std::string lattice_err;          // declared before the job: the job's destructor joins the thread first
-  std::future<int> lattice_job;
-  if (!same_lattice) {  // built on a helper thread while this one builds the bitmaps and the query set
+  std::string lattice_err, query_err;
+  bool lattice_started = false, query_started = false;
+  // every exit path waits for the helper threads (they write into the handle)
+  struct Joiner {
+    slide_pr_handle *h; bool *l, *q;
+    ~Joiner() { if (*l) h->worker_lattice.wait(); if (*q) h->worker_query.wait(); }
+  } joiner{h, &lattice_started, &query_started};
+  if (!same_lattice) {  // built on a helper thread while this one builds the bitmaps
     h->lattice_valid = false;
-    lattice_job = std::async(std::launch::async, [h, half_x, half_y, &lattice_err]() {
+    h->worker_lattice.submit([h, half_x, half_y, &lattice_err]() {
       return spr::build_lattice(h->p, half_x, half_y, h->yaw_half, 0, -1, h->p.compute_budget_sec > 0, h->L, lattice_err);
     });
+    lattice_started = true;
   } else {
     h->reuse_flags |= 1;
   }
   auto join_lattice = [&]() -> int {
-    if (!lattice_job.valid()) return SLIDE_PR_OK;
-    const int lrc = lattice_job.get();
+    if (!lattice_started) return SLIDE_PR_OK;
+    const int lrc = h->worker_lattice.wait();
+    lattice_started = false;
     if (lrc != SLIDE_PR_OK) { h->err = lattice_err; return lrc; }
     h->lat_hx = half_x; h->lat_hy = half_y; h->lat_yaw_half = h->yaw_half; h->lat_p = h->p;
     h->lattice_valid = true;
@@ -342,10 +407,9 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
                         h->cached_ref_p.match_threshold == h->p.match_threshold &&
                         h->cached_ref_p.match_threshold_dimension == h->p.match_threshold_dimension &&
                         (n_ref == 0 || std::memcmp(h->cached_ref.data(), ref7, (size_t)n_ref * 7 * sizeof(double)) == 0);
-  std::string query_err;
-  std::future<int> query_job;
   auto start_query_job = [&]() {
-    query_job = std::async(std::launch::async, [h, qry7, n_qry, &query_err]() { return spr::build_query_set(h->R, qry7, n_qry, h->Q, query_err); });
+    h->worker_query.submit([h, qry7, n_qry, &query_err]() { return spr::build_query_set(h->R, qry7, n_qry, h->Q, query_err); });
+    query_started = true;
   };
   if (!same_ref) {
     // stage 1 of the reference index (bitmaps, landmark tables): all the bound phase needs.  The
@@ -370,8 +434,10 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   } else {
     h->reuse_flags |= 2;
   }
-  if (!query_job.valid()) start_query_job();
-  if ((rc = query_job.get()) != SLIDE_PR_OK) { h->err = query_err; return rc; }
+  if (!query_started) start_query_job();
+  rc = h->worker_query.wait();
+  query_started = false;
+  if (rc != SLIDE_PR_OK) { h->err = query_err; return rc; }
   g_trace.mark("query_set_build");
   if ((rc = upload(h, h->d_qxy, h->Q.qxy, st))) return rc;
   if ((rc = upload(h, h->d_qdims, h->Q.qdims, st))) return rc;
@@ -425,6 +491,7 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   V.ignore_dim = h->p.ignore_dimension;
   // no synchronisation here: every upload reads page-locked vectors owned by the handle (the
   // caller's rows were copied), which stay untouched until the next prepare
+  SPR_CUDA(h, cudaEventRecord(h->ev_prep, st));  // a search on another stream waits for these uploads
   h->prepared = true;
   h->prepare_ms = now_ms() - t0;
   g_trace.mark("query_upload");
@@ -453,6 +520,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   o.trans_end = -1;
   if (opts) o = *opts;
   cudaStream_t st = o.stream ? (cudaStream_t)o.stream : h->stream;
+  if (st != h->stream) SPR_CUDA(h, cudaStreamWaitEvent(st, h->ev_prep, 0));  // the uploads are asynchronous (page-locked sources)
   fill_result_header(h, out);
   if (h->L.status == SLIDE_PR_SANITY_RETURN) return SLIDE_PR_OK;
   int rc;
@@ -589,8 +657,18 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   }
   if (h->ranks_pending && !bounds_only && (rc = finish_ranks(h, st)) != SLIDE_PR_OK) return rc;  // exhaustive path
   auto run_range = [&](const uint32_t begin[2], const uint32_t end[2]) -> int {
+    // verification phase of the pruned search: few candidate items per pass, so the label passes
+    // of the two bitmap directions (disjoint counters) run concurrently on two streams
+    const bool fork = prune && end[0] > begin[0] && end[1] > begin[1];
+    if (fork) {
+      if (passes_left < 2 * active.size()) passes_left = 0;  // re-arm the work counters before the fork
+      if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
+      SPR_CUDA(h, cudaEventRecord(h->ev_fork, st));
+      SPR_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    }
     for (uint32_t d = 0; d < 2; d++) {
       if (end[d] <= begin[d]) continue;
+      cudaStream_t sd = fork && d == 1 ? h->side_stream : st;
       for (size_t i = 0; i < active.size(); i++) {
         K.chunk_begin = begin[d]; K.chunk_end = end[d]; K.dir = d; K.label = active[i];
         if (prune) {
@@ -603,10 +681,14 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
         K.tab_cell_base = K.label >= 0 ? h->R.cell_base[d][K.label] : 0u;
         K.tab_ref_base = K.label >= 0 ? h->R.ref_base[K.label] : 0u;
         if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
-        SPR_CUDA(h, spr_launch_score_lattice(h->V, K, h->tables_mode, h->sm_count, st, &launches));
+        SPR_CUDA(h, spr_launch_score_lattice(h->V, K, h->tables_mode, h->sm_count, sd, &launches));
         K.work_counter++;
         passes_left--;
       }
+    }
+    if (fork) {
+      SPR_CUDA(h, cudaEventRecord(h->ev_join, h->side_stream));
+      SPR_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
     }
     return SLIDE_PR_OK;
   };

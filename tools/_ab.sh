@@ -1,4 +1,5 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_c3.csv python tools/profile_target.py 3 20000 1 > gpurun_out/ncu_c3.log 2>&1
-tail -3 gpurun_out/ncu_c3.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c5.csv python bench.py --config 5 --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_c5.log 2>&1
-tail -2 gpurun_out/ncu_c5.log | cut -c1-300
+python -m pytest tests -x -q -m gpu > gpurun_out/ab_t.log 2>&1; tail -2 gpurun_out/ab_t.log
+python tools/quick_bench.py 2 2>&1 | grep cfg2 | head -2
+SLIDE_PR_TRACE=1 python tools/_trace.py 2>&1 | tail -6
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('bench value %.3e ms %.3f e2e %.3e ms %.3f host %.3f'%(d['value'],d['ms_per_step'],d['e2e']['value'],d['e2e']['ms_per_step'],d['e2e']['host_index_build_ms']))"
