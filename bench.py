@@ -208,16 +208,20 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    rec_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+    rec_dev = torch.zeros(2, dtype=torch.int64, device=dev)
+    rec_all = torch.zeros(2 * max(world, 1), dtype=torch.int64, device=dev)
+
     def gather_and_merge(res):
-        """all-gather of the 16-byte (inliers, canonical index) records + deterministic merge"""
+        """all-gather of the 16-byte (canonical index, inliers) records + deterministic merge"""
         if world == 1:
             return
-        rec = torch.tensor([res.best_hyp_index, res.best_num_inliers], dtype=torch.int64, device=dev)
-        out = [torch.empty_like(rec) for _ in range(world)]
-        dist.all_gather(out, rec)
+        rec_host[0], rec_host[1] = int(res.best_hyp_index), int(res.best_num_inliers)
+        rec_dev.copy_(rec_host, non_blocking=True)
+        dist.all_gather_into_tensor(rec_all, rec_dev)
         if shard_mode:
             recs = (capi.TopkRecord * world)()
-            for i, t in enumerate(torch.stack(out).cpu().tolist()):
+            for i, t in enumerate(rec_all.view(world, 2).cpu().tolist()):
                 recs[i].hyp_index, recs[i].inliers, recs[i].rank = int(t[0]), int(t[1]), i
             return lib.slide_pr_merge_records(recs, world)
 
