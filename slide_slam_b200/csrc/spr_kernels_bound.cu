@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "spr_core.h"
 #include "spr_kernels.h"
 
@@ -358,7 +360,14 @@ int spr_bound_planes(int nqp) { return nqp < 4096 ? 12 : 16; }
 // global memory (a single row does not fit).
 void spr_bound_plan(const SprView &V, uint32_t dir, int n_active, int *labels_per_launch, uint32_t *band_rows) {
   const size_t W4 = (size_t)V.grid.W[dir] * 4, R = (size_t)V.grid.R[dir];
-  const size_t limit = SPR_SMEM_LIMIT - 64;
+  size_t limit = SPR_SMEM_LIMIT - 64;
+  int min_nqp = 2048;
+  // test hook: SLIDE_PR_BOUND_SMEM=<bytes> shrinks the shared-memory budget of the planner (and drops
+  // the query-count threshold) so that small maps exercise the label-batch / row-band / in-place paths
+  if (const char *e = std::getenv("SLIDE_PR_BOUND_SMEM")) {
+    const long v = std::atol(e);
+    if (v > 0 && (size_t)v < limit) { limit = (size_t)v; min_nqp = 0; }
+  }
   if ((R + 1) * W4 + 16 <= limit) {
     int per = (int)(limit / ((R + 1) * W4 + 16));
     if (per > SPR_BOUND_MAX_LABELS) per = SPR_BOUND_MAX_LABELS;
@@ -374,7 +383,7 @@ void spr_bound_plan(const SprView &V, uint32_t dir, int n_active, int *labels_pe
   // Row bands cost one launch (and one pass over the counters of every work item) per band: they
   // pay off when a work item has many query landmarks to probe; small query maps against a large
   // reference map (streaming submap queries) read the planes in place through L1 / L2 instead.
-  if (max_rows < 9 || V.nqp < 2048) { *band_rows = 0; *labels_per_launch = SPR_BOUND_MAX_LABELS; return; }
+  if (max_rows < 9 || V.nqp < min_nqp) { *band_rows = 0; *labels_per_launch = SPR_BOUND_MAX_LABELS; return; }
   max_rows = (max_rows - 1) & ~(size_t)3;
   const size_t bands = (R + max_rows - 1) / max_rows;
   *band_rows = (uint32_t)((((R + bands - 1) / bands) + 3) & ~(size_t)3);

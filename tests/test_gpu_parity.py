@@ -203,6 +203,63 @@ def test_bound_and_verify_equals_exhaustive(kind):
     pr.close()
 
 
+@pytest.mark.parametrize("smem", [60000, 9000, 1200, 300])
+def test_bound_phase_planner_paths(smem):
+    """The bound phase stages the bitmap planes in label batches, in row bands, or reads them in
+    place, depending on the shared-memory budget (SLIDE_PR_BOUND_SMEM shrinks it for the test).
+    Every path must give the same bounds and the same winner."""
+    ref, qry, _ = synth.make_pair(600, seed=41, classes="five", outlier_frac=0.1)
+    ros = {"search_xy_step_size": 0.5, "search_yaw_step_size_degrees": 15.0, "match_threshold_position": 0.5,
+           "match_threshold_dimension": 1.0, "ignore_dimension": 0, "min_num_inliers": 5}
+    ref = ref.copy(); qry = qry.copy()
+    ref[:, 1:3] -= ref[:, 1:3].mean(0); qry[:, 1:3] -= qry[:, 1:3].mean(0)
+    half = 1.2 * max(np.abs(ref[:, 1:3]).max(), np.abs(qry[:, 1:3]).max())
+
+    def run(budget):
+        if budget:
+            os.environ["SLIDE_PR_BOUND_SMEM"] = str(budget)
+        else:
+            os.environ.pop("SLIDE_PR_BOUND_SMEM", None)
+        try:
+            pr = PlaceRecognition(ros)
+            pr.prepare(ref, qry, half, half)
+            nt = pr.lattice_info()[0]
+            lo, hi = nt // 2, nt // 2 + 4000
+            res, _ = pr.search()
+            _, bound = pr.search(lo, hi, want_counts=True, bounds_only=True)
+            res_x, _ = pr.search(exhaustive=True)
+            pr.close()
+        finally:
+            os.environ.pop("SLIDE_PR_BOUND_SMEM", None)
+        assert res.search_mode == 1 and res_x.search_mode == 0
+        assert (res.best_num_inliers, res.best_hyp_index) == (res_x.best_num_inliers, res_x.best_hyp_index)
+        return res.best_hyp_index, bound
+
+    want_idx, want_bound = run(0)
+    got_idx, got_bound = run(smem)
+    assert got_idx == want_idx and np.array_equal(got_bound, want_bound)
+
+
+def test_bound_and_verify_with_many_query_landmarks():
+    """More than 4095 query landmarks: 16 bit planes per bound; more than 2047: row bands allowed."""
+    ref, qry, _ = synth.make_pair(4500, seed=43, classes="forest_urban")
+    ros = {"search_xy_step_size": 2.0, "search_yaw_step_size_degrees": 30.0, "match_threshold_position": 0.5,
+           "match_threshold_dimension": 1.0, "ignore_dimension": 0, "min_num_inliers": 5}
+    pr = PlaceRecognition(ros)
+    found, _, _, info, ri, qi = pr.findTransformation(ref, qry)
+    assert info.match.search_mode == 1
+    sref, sqry = ref.copy(), qry.copy()
+    sref[:, 1:3] -= np.array(info.centroid_ref[:]); sqry[:, 1:3] -= np.array(info.centroid_qry[:])
+    pr.prepare(sref, sqry, info.half_x, info.half_y)
+    res_x, _ = pr.search(exhaustive=True)
+    assert (info.match.best_num_inliers, info.match.best_hyp_index) == (res_x.best_num_inliers, res_x.best_hyp_index)
+    nt = pr.lattice_info()[0]
+    _, exact = pr.search(nt // 2, nt // 2 + 300, want_counts=True)
+    _, bound = pr.search(nt // 2, nt // 2 + 300, want_counts=True, bounds_only=True)
+    assert (bound >= exact).all() and (bound <= len(qry)).all()
+    pr.close()
+
+
 def test_edge_cases_through_the_abi():
     kw = dict(match_xy_step_size=0.5, yaw_step_deg=45.0)
     rng = np.random.default_rng(1)
