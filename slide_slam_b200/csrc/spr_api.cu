@@ -172,7 +172,8 @@ struct slide_pr_handle {
   DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_rank16, d_rank16b, d_rowrank, d_rowrankb, d_gcnt, d_cellref, d_cellrefb, d_cellbase, d_cellbaseb, d_reftab, d_refbase,
       d_cand, d_cand1, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ubplanes, d_itemub, d_seed, d_canditems, d_candcount, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
   SprView V{};
-  std::vector<int32_t> h_match;
+  spr::uvec<int32_t> h_match;          // page-locked D2H targets
+  spr::uvec<unsigned long long> h_scalars;
 };
 
 #define SPR_CUDA(h, call)                                                                   \
@@ -596,8 +597,8 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     const size_t n_wg_total = K.n_chunks_total / SPR_WARP_CHUNKS;
     SPR_CUDA(h, h->d_ubplanes.ensure((size_t)n_yaw * n_wg_total * (size_t)n_planes * 32 * sizeof(uint32_t) + 64));
     SPR_CUDA(h, h->d_itemub.ensure((size_t)n_yaw * n_wg_total * sizeof(uint32_t) + 64));
-    SPR_CUDA(h, h->d_seed.ensure((size_t)n_yaw * sizeof(unsigned long long)));
-    SPR_CUDA(h, cudaMemsetAsync(h->d_seed.p, 0, (size_t)n_yaw * sizeof(unsigned long long), st));
+    SPR_CUDA(h, h->d_seed.ensure((size_t)n_yaw * SPR_SEED_SLOTS * sizeof(unsigned long long)));
+    SPR_CUDA(h, cudaMemsetAsync(h->d_seed.p, 0, (size_t)n_yaw * SPR_SEED_SLOTS * sizeof(unsigned long long), st));
     SprBoundLaunch B{};
     B.n_chunks_total = K.n_chunks_total;
     B.shard_index = o.shard_index; B.shard_count = o.shard_count;
@@ -712,9 +713,11 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   }
   SPR_CUDA(h, cudaEventRecord(h->ev1, st));
   g_trace.mark("search_launch");
-  unsigned long long key = 0, stats[4] = {0, 0, 0, 0};
-  SPR_CUDA(h, cudaMemcpyAsync(&key, h->d_best.p, sizeof(key), cudaMemcpyDeviceToHost, st));
-  if (o.collect_stats) SPR_CUDA(h, cudaMemcpyAsync(stats, h->d_stats.p, sizeof(stats), cudaMemcpyDeviceToHost, st));
+  if (h->h_scalars.size() < 8) h->h_scalars.assign(8, 0ull);
+  unsigned long long *hs = h->h_scalars.data();
+  for (int i = 0; i < 5; i++) hs[i] = 0ull;
+  SPR_CUDA(h, cudaMemcpyAsync(hs, h->d_best.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (o.collect_stats) SPR_CUDA(h, cudaMemcpyAsync(hs + 1, h->d_stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   if (o.counts_out && n_counts > 0 && !bounds_only)
     SPR_CUDA(h, cudaMemcpyAsync(o.counts_out, h->d_counts.p, (size_t)n_counts * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   SPR_CUDA(h, cudaStreamSynchronize(st));
@@ -740,6 +743,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     }
   }
   g_trace.mark("search_sync");
+  const unsigned long long key = hs[0], stats[4] = {hs[1], hs[2], hs[3], hs[4]};
   float ms = 0;
   SPR_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   out->kernel_ms = ms;
@@ -804,7 +808,7 @@ int slide_pr_extract(slide_pr_handle *h, int64_t hyp_index, int32_t *ref_idx_out
                                  h->R.Tstar, h->R.Sstar, h->p.match_threshold_dimension, h->p.ignore_dimension,
                                  h->d_match.as<int32_t>(), st));
   io->gpu_launches += 1;
-  h->h_match.resize(std::max(h->n_qry, 1));
+  if ((int)h->h_match.size() < std::max(h->n_qry, 1)) h->h_match.resize(std::max(h->n_qry, 1));
   SPR_CUDA(h, cudaMemcpyAsync(h->h_match.data(), h->d_match.p, (size_t)h->n_qry * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   SPR_CUDA(h, cudaStreamSynchronize(st));
   g_trace.mark("extract");
@@ -1134,7 +1138,6 @@ int slide_pr_score_hypotheses(slide_pr_handle *h, const double *hyps4, int64_t n
   SPR_CUDA(h, cudaMemcpyAsync(&key, h->d_best.p, sizeof(key), cudaMemcpyDeviceToHost, st));
   if (counts_out) SPR_CUDA(h, cudaMemcpyAsync(counts_out, h->d_counts.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   SPR_CUDA(h, cudaStreamSynchronize(st));
-  g_trace.mark("search_sync");
   float ms = 0;
   SPR_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   out->kernel_ms = ms;

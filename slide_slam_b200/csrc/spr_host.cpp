@@ -420,11 +420,26 @@ int build_ref_marks(const slide_pr_params &p, const double *ref7, int n_ref, Ref
       if (x0 < 0 || x1 >= G.GX || y0 < 0 || y1 >= G.GY) { err = "internal: match disc leaves the grid"; return SLIDE_PR_ERR_INTERNAL; }
       uint32_t *pl0 = R.bitmap.data() + (size_t)l * G.label_stride;
       uint32_t *pl1 = pl0 + G.plane_words[0];
+      // squared distance from the landmark to the cell's box along y, once per column
+      double dy2[64];
+      const int ny_n = y1 - y0 + 1;
+      const bool small = ny_n <= 64;
+      for (int ny = y0; small && ny <= y1; ny++) {
+        const double dy = std::fmax(std::fmax((double)ny - uy, 0.0), uy - (double)(ny + 1));
+        dy2[ny - y0] = dy * dy;
+      }
       for (int nx = x0; nx <= x1; nx++) {
         const double dx = std::fmax(std::fmax((double)nx - ux, 0.0), ux - (double)(nx + 1));
+        const double dx2 = dx * dx;
         for (int ny = y0; ny <= y1; ny++) {
-          const double dy = std::fmax(std::fmax((double)ny - uy, 0.0), uy - (double)(ny + 1));
-          if (dx * dx + dy * dy > rc2) continue;
+          double d2;
+          if (small) {
+            d2 = dx2 + dy2[ny - y0];
+          } else {
+            const double dy = std::fmax(std::fmax((double)ny - uy, 0.0), uy - (double)(ny + 1));
+            d2 = dx2 + dy * dy;
+          }
+          if (d2 > rc2) continue;
           pl0[(size_t)(nx + 1) * G.W[0] + ((uint32_t)(ny + 32) >> 5)] |= 1u << ((ny + 32) & 31);
           pl1[(size_t)(ny + 1) * G.W[1] + ((uint32_t)(nx + 32) >> 5)] |= 1u << ((nx + 32) & 31);
           cb[l].x0 = std::min(cb[l].x0, nx); cb[l].x1 = std::max(cb[l].x1, nx);

@@ -38,6 +38,7 @@ struct SprLaunch {
 // One launch of the bound phase = one bitmap direction x a set of labels whose planes are staged
 // together in shared memory, over a range of chunks.
 #define SPR_BOUND_MAX_LABELS 8
+#define SPR_SEED_SLOTS 32            // seeds per yaw: the best-bounded hypothesis of every 32nd work item column
 struct SprBoundLaunch {
   uint32_t chunk_begin, chunk_end;  // chunks of direction `dir` (multiple of 32 apart)
   uint32_t n_chunks_total;
@@ -49,7 +50,7 @@ struct SprBoundLaunch {
   uint32_t row_begin, row_end;      // rows of the planes staged in shared memory (row_end == row_begin: read in place)
   uint32_t *planes;                 // device: bit planes of the bounds (layout of SprLaunch::ub_planes)
   uint32_t *item_ub;                // device: [yaw][chunk / 32]
-  unsigned long long *seed_key;     // device: [n_yaw] (bound + 1) << 40 | chunk * 32 + bit of the best-bounded hypothesis
+  unsigned long long *seed_key;     // device: [n_yaw][SPR_SEED_SLOTS] (bound + 1) << 40 | chunk * 32 + bit of the best-bounded hypothesis
   unsigned long long *work_counter; // device: next work item (zeroed by the caller)
 };
 

@@ -57,43 +57,44 @@ cudaError_t spr_launch_score_list(const SprView &V, const double *hyps4, long lo
 // correspondences of the winner: the reference's own double loop (PR.cpp:281-357) over the raw
 // maps, reference objects in ascending order, first match wins.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 spr_extract_kernel(const double *__restrict__ ref7, int n_ref, const double *__restrict__ qry7, int n_qry, double c,
                    double s, double tx, double ty, double Tstar, double Sstar, double thr_dim, int ignore_dim,
                    int32_t *__restrict__ match_ref) {
-  // one WARP per query object: the lanes test 32 consecutive reference objects, the lowest
-  // matching lane of the first batch with a match is the reference's "first match, then break"
-  const int lane = threadIdx.x & 31;
-  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (j >= n_qry) return;
+  // one CTA per query object: thread t tests reference objects t, t + 128, ... in ascending order
+  // and stops at its first match; the smallest index over the CTA is the reference's "first
+  // match, then break" (PR.cpp:299-355)
+  __shared__ int s_first;
+  const int j = blockIdx.x;
+  if (threadIdx.x == 0) s_first = 0x7fffffff;
+  __syncthreads();
   const double *q = qry7 + 7 * (size_t)j;
   const double label = q[0];
   double rx, ry;
   spr_rotate(c, s, q[1], q[2], &rx, &ry);
   const double qd[3] = {q[4], q[5], q[6]};
-  int32_t found = -1;
-  for (int i0 = 0; i0 < n_ref; i0 += 32) {
-    const int i = i0 + lane;
-    bool hit = false;
-    if (i < n_ref) {
-      const double *r = ref7 + 7 * (size_t)i;
-      hit = r[0] == label &&                                                     // PR.cpp:306
-            spr_distance_match(rx, ry, tx, ty, r[1], r[2], Tstar) &&             // PR.cpp:332
-            (ignore_dim || spr_dimension_match(r[4], r[5], r[6], qd, thr_dim, Sstar));  // PR.cpp:334-339
+  int first = 0x7fffffff;
+  for (int i = threadIdx.x; i < n_ref; i += blockDim.x) {
+    const double *r = ref7 + 7 * (size_t)i;
+    if (r[0] == label &&                                                         // PR.cpp:306
+        spr_distance_match(rx, ry, tx, ty, r[1], r[2], Tstar) &&                 // PR.cpp:332
+        (ignore_dim || spr_dimension_match(r[4], r[5], r[6], qd, thr_dim, Sstar))) {  // PR.cpp:334-339
+      first = i;
+      break;                                                                     // PR.cpp:353
     }
-    const unsigned m = __ballot_sync(SPR_FULL, hit);
-    if (m) { found = i0 + __ffs(m) - 1; break; }                                 // PR.cpp:353
   }
-  if (lane == 0) match_ref[j] = found;
+  first = __reduce_min_sync(SPR_FULL, first);
+  if ((threadIdx.x & 31) == 0 && first != 0x7fffffff) atomicMin(&s_first, first);
+  __syncthreads();
+  if (threadIdx.x == 0) match_ref[j] = s_first == 0x7fffffff ? -1 : s_first;
 }
 
 cudaError_t spr_launch_extract(const double *ref7, int n_ref, const double *qry7, int n_qry, double c,
                                double s, double tx, double ty, double Tstar, double Sstar, double thr_dim,
                                int ignore_dim, int32_t *match_ref, cudaStream_t st) {
   if (n_qry <= 0) return cudaSuccess;
-  const int block = 256;  // 8 queries per CTA
-  spr_extract_kernel<<<(n_qry + 7) / 8, block, 0, st>>>(ref7, n_ref, qry7, n_qry, c, s, tx, ty, Tstar, Sstar, thr_dim,
-                                                        ignore_dim, match_ref);
+  spr_extract_kernel<<<n_qry, 128, 0, st>>>(ref7, n_ref, qry7, n_qry, c, s, tx, ty, Tstar, Sstar, thr_dim, ignore_dim,
+                                            match_ref);
   return cudaGetLastError();
 }
 

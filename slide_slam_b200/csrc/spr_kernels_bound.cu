@@ -254,22 +254,23 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
       const uint32_t who = __ballot_sync(SPR_FULL, packed == wmax && live);
       if (lane == 0) B.item_ub[(size_t)a * n_wg_total + cidx / SPR_WARP_CHUNKS] = wmax >> 5;
       if (who && lane == __ffs(who) - 1)
-        atomicMax(B.seed_key + a, ((unsigned long long)(val + 1u) << SPR_KEY_IDX_BITS) |
+        atomicMax(B.seed_key + (size_t)a * SPR_SEED_SLOTS + (cidx / SPR_WARP_CHUNKS) % SPR_SEED_SLOTS,
+                  ((unsigned long long)(val + 1u) << SPR_KEY_IDX_BITS) |
                                       ((unsigned long long)cidx * 32ull + (unsigned long long)(packed & 31u)));
     }
     __syncwarp();
   }
 }
 
-// Exact score of the best-bounded hypothesis of every yaw candidate (one CTA each, the warps
-// stride over the query landmarks): seeds the running best of the verification phase.  Same
+// Exact score of the best-bounded hypotheses -- SPR_SEED_SLOTS per yaw candidate, one per residue
+// class of the work-item columns -- (one CTA each, the warps stride over the query landmarks): seeds the running best of the verification phase.  Same
 // decision code as the hypothesis-list scorer.
 __global__ void __launch_bounds__(256)
 spr_seed_kernel(const __grid_constant__ SprView V, const unsigned long long *__restrict__ seed_key,
                 unsigned long long *best_key) {
   __shared__ int s_cnt;
-  const int a = blockIdx.x;
-  const unsigned long long sk = seed_key[a];
+  const int a = blockIdx.x / SPR_SEED_SLOTS;
+  const unsigned long long sk = seed_key[blockIdx.x];
   if (sk == 0ull) return;  // uniform for the CTA
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
@@ -303,7 +304,7 @@ spr_seed_kernel(const __grid_constant__ SprView V, const unsigned long long *__r
 cudaError_t spr_launch_seed(const SprView &V, const unsigned long long *seed_key, unsigned long long *best_key,
                             cudaStream_t st) {
   if (V.n_yaw <= 0 || V.nqp <= 0) return cudaSuccess;
-  spr_seed_kernel<<<V.n_yaw, 256, 0, st>>>(V, seed_key, best_key);
+  spr_seed_kernel<<<V.n_yaw * SPR_SEED_SLOTS, 256, 0, st>>>(V, seed_key, best_key);
   return cudaGetLastError();
 }
 

@@ -1,3 +1,5 @@
+"""Developer aid: kernel time of the default (bound-and-verify) and the exhaustive search on
+config-2-sized maps with and without overlap."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

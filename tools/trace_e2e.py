@@ -1,3 +1,5 @@
+"""Developer aid: per-phase host timings of findTransformation on two alternating config-2 pairs
+(run with SLIDE_PR_TRACE=1)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from slide_slam_b200 import synth
