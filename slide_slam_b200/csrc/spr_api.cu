@@ -427,7 +427,14 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
     h->ref_index_valid = true;
     h->ranks_pending = true;
     if ((rc = upload(h, h->d_labelbox, h->R.labelbox, st))) return rc;
-    if ((rc = upload(h, h->d_bitmap, h->R.bitmap, st))) return rc;
+    // 4 zero words in front of (and slack behind) the planes: the bound kernel reads the word before
+    // and the word after a probe's base word
+    SPR_CUDA(h, h->d_bitmap.ensure(h->R.bitmap.size() * sizeof(uint32_t) + 64));
+    SPR_CUDA(h, cudaMemsetAsync(h->d_bitmap.p, 0, 16, st));
+    SPR_CUDA(h, cudaMemsetAsync(static_cast<char *>(h->d_bitmap.p) + 16 + h->R.bitmap.size() * sizeof(uint32_t), 0, 32, st));
+    if (!h->R.bitmap.empty())
+      SPR_CUDA(h, cudaMemcpyAsync(static_cast<char *>(h->d_bitmap.p) + 16, h->R.bitmap.data(), h->R.bitmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    h->h2d_bytes += (int64_t)(h->R.bitmap.size() * sizeof(uint32_t));
     if ((rc = upload(h, h->d_reftab, h->R.reftab, st))) return rc;
     if ((rc = upload(h, h->d_refbase, h->R.ref_base, st))) return rc;
     if ((rc = upload(h, h->d_ref7, h->cached_ref, st))) return rc;
@@ -472,7 +479,7 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   V.n_labels = (int32_t)h->R.labels.size();
   V.n_ref = n_ref;
   V.labelbox = h->d_labelbox.as<SprBox>();
-  V.bitmap = h->d_bitmap.as<uint32_t>();
+  V.bitmap = h->d_bitmap.as<uint32_t>() + 4;  // behind the zero words in front
   V.rank16[0] = h->d_rank16.as<uint16_t>();
   V.rank16[1] = h->d_rank16b.as<uint16_t>();
   V.row_rank[0] = h->d_rowrank.as<uint32_t>();
@@ -755,13 +762,13 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   out->groups_skipped = (int64_t)stats[3];
   out->h2d_bytes = h->h2d_bytes;
   out->d2h_bytes = (int64_t)sizeof(key) + (o.collect_stats ? (int64_t)sizeof(stats) : 0) + n_counts * (int64_t)sizeof(int32_t);
-  // hypotheses scored by this shard = valid bits of its 32-chunk work-item columns x yaw candidates
+  // hypotheses scored by this shard = valid bits of its double groups (64 chunks) x yaw candidates
   {
     const int sc = o.shard_count > 1 ? o.shard_count : 1, si = o.shard_count > 1 ? o.shard_index : 0;
     uint64_t bits = 0;
     auto count_range = [&](uint32_t cb, uint32_t ce) {
       for (uint32_t c = cb; c < ce; c++)
-        if ((int)(((c - cb) / SPR_WARP_CHUNKS) % sc) == si) bits += (uint64_t)__builtin_popcount(h->L.chunks[c].valid);
+        if ((int)(((c - cb) / (2 * SPR_WARP_CHUNKS)) % sc) == si) bits += (uint64_t)__builtin_popcount(h->L.chunks[c].valid);
     };
     if (h->p.compute_budget_sec > 0) {
       for (int k = 0; k < rings_scored; k++)

@@ -49,7 +49,10 @@ struct RectEmitter {
   const double *xs, *ys;
   int64_t tb, te;  // ordinal filter, te < 0: none
 
-  void push(double across, uint32_t along_off, int n, uint64_t ord0, uint64_t stride, uint32_t dir) {
+  std::vector<int32_t> *succ = nullptr;  // optional: index of the chunk that continues chunk i along its row, or -1
+  std::vector<int32_t> prev;             // scratch: chunks of the previous block of the current rectangle
+
+  int push(double across, uint32_t along_off, int n, uint64_t ord0, uint64_t stride, uint32_t dir) {
     // restrict to ordinals in [tb, te)
     int b_lo = 0, b_hi = n;
     if (tb > 0 || te >= 0) {
@@ -57,7 +60,7 @@ struct RectEmitter {
       if (tb > o0) b_lo = (int)std::min<int64_t>(n, (tb - o0 + st - 1) / st);
       if (te >= 0) b_hi = (te <= o0) ? 0 : (int)std::min<int64_t>(n, (te - o0 + st - 1) / st);
     }
-    if (b_lo >= b_hi) return;
+    if (b_lo >= b_hi) return -1;
     SprChunk c;
     c.across = across;
     c.along_off = along_off;
@@ -69,6 +72,8 @@ struct RectEmitter {
     c.dir = dir;
     c.ring = (uint32_t)ring;
     L.chunks.push_back(c);
+    if (succ) succ->push_back(-1);
+    return (int)L.chunks.size() - 1;
   }
 
   // rectangle ix in [ix0, ix1), iy in [iy0, iy1); ordinal(ix, iy) = ord0 + (ix-ix0)*row_stride + (iy-iy0)
@@ -79,16 +84,24 @@ struct RectEmitter {
     const int64_t cost_x = (int64_t)h * ((w + 31) / 32);
     if (cost_y <= cost_x) {
       // bits along y; consecutive chunks = consecutive x rows of the same y block
+      prev.assign((size_t)w, -1);
       for (int by = iy0; by < iy1; by += 32) {
         const int n = std::min(32, iy1 - by);
-        for (int ix = ix0; ix < ix1; ix++)
-          push(xs[ix], y_off + (uint32_t)by, n, ord0 + (uint64_t)(ix - ix0) * row_stride + (uint64_t)(by - iy0), 1, 0);
+        for (int ix = ix0; ix < ix1; ix++) {
+          const int i = push(xs[ix], y_off + (uint32_t)by, n, ord0 + (uint64_t)(ix - ix0) * row_stride + (uint64_t)(by - iy0), 1, 0);
+          if (succ && i >= 0 && prev[ix - ix0] >= 0) (*succ)[prev[ix - ix0]] = i;
+          prev[ix - ix0] = i;
+        }
       }
     } else {
+      prev.assign((size_t)h, -1);
       for (int bx = ix0; bx < ix1; bx += 32) {
         const int n = std::min(32, ix1 - bx);
-        for (int iy = iy0; iy < iy1; iy++)
-          push(ys[iy], x_off + (uint32_t)bx, n, ord0 + (uint64_t)(bx - ix0) * row_stride + (uint64_t)(iy - iy0), row_stride, 1);
+        for (int iy = iy0; iy < iy1; iy++) {
+          const int i = push(ys[iy], x_off + (uint32_t)bx, n, ord0 + (uint64_t)(bx - ix0) * row_stride + (uint64_t)(iy - iy0), row_stride, 1);
+          if (succ && i >= 0 && prev[iy - iy0] >= 0) (*succ)[prev[iy - iy0]] = i;
+          prev[iy - iy0] = i;
+        }
       }
     }
   }
@@ -134,6 +147,8 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
   if (L.ox < step || L.oy < step) { L.status = SLIDE_PR_SANITY_RETURN; return SLIDE_PR_OK; }
 
   uint64_t ord = 0;
+  std::vector<int32_t> &succ = L.succ;  // along-successor of every emitted chunk (pairing for the bound kernel)
+  succ.clear();
   for (int k = 0; k < rings; k++) {
     const double kd = static_cast<double>(k);
     const double x_right_prev = kd * L.ox, x_left_prev = -kd * L.ox;        // PR.cpp:204,210
@@ -174,6 +189,7 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
     R.count = (uint64_t)R.nx * R.ny - (has_box ? (uint64_t)n_in_x * n_in_y : 0);
     R.chunk_begin = (uint32_t)L.chunks.size();
     RectEmitter E{L, k, R.x_off, R.y_off, xs, ys, trans_begin, trans_end};
+    E.succ = ring_major ? nullptr : &succ;
     const int nx = (int)R.nx, ny = (int)R.ny;
     if (!has_box) {
       E.rect(0, nx, 0, ny, ord, (uint64_t)ny);
@@ -200,11 +216,11 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
   // chunks of a ring together (needed by the anytime budget, PR.cpp:181-191).
   uvec<SprChunk> &out = L.scratch;
   if (ring_major) out.clear();
-  out.reserve(L.chunks.size() + 64 * (ring_major ? L.ring.size() + 1 : 2));
-  auto pad32 = [&out](uint32_t d) {
+  out.reserve(L.chunks.size() + 128 * (ring_major ? L.ring.size() + 1 : 2));
+  auto pad32 = [&out](uint32_t d) {  // whole double groups (the sharding granule)
     SprChunk z{};
     z.dir = d;
-    while (out.size() % 32) out.push_back(z);
+    while (out.size() % 64) out.push_back(z);
   };
   if (ring_major) {
     for (Lattice::Ring &R : L.ring)
@@ -216,10 +232,14 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
         R.dend[d] = (uint32_t)out.size();
       }
   } else {
-    // Within a direction the chunks are bucketed by the 32 x 32-sample tile their first sample
-    // falls in (counting sort, emission order kept inside a bucket): the 32 chunks of a warp then
-    // lie side by side across -- neighbouring bitmap rows at the same word column, i.e. mostly
-    // distinct shared-memory banks (odd row pitch) and a compact patch for the visibility test.
+    // Chunks are paired along their row (chunk + the chunk that continues it 32 samples further:
+    // the bound kernel probes both with three bitmap words instead of four) and the pairs are
+    // bucketed by the 32 x 32-sample tile the first chunk starts in (counting sort, emission
+    // order kept inside a bucket).  A work item of the bound kernel is a DOUBLE GROUP of 64
+    // chunks = [32 first chunks][their 32 continuations, empty where a row ends]; the 32 chunks
+    // of each half lie side by side across -- neighbouring bitmap rows at the same word column
+    // (mostly distinct shared-memory banks with the odd row pitch) and a compact patch for the
+    // visibility test.  The exact kernel sees two ordinary groups of 32 chunks.
     const double tile = 32.0 * step;
     const double lo = -std::max(std::fabs(half_x), std::fabs(half_y)) - tile;
     const size_t nb1 = (size_t)std::floor((-2.0 * lo) / tile) + 2;
@@ -227,37 +247,51 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
     const size_t n_buckets = nb1 * nb1;
     const double inv_tile = 1.0 / tile;
     const size_t n_all = L.chunks.size();
-    std::vector<uint32_t> pos(2 * (n_buckets + 1), 0u);
-    std::vector<uint32_t> key(n_all);  // bucket inside its direction
+    std::vector<uint32_t> &pos = L.sort_pos, &key = L.sort_key;  // scratch kept across calls
+    std::vector<uint8_t> &second = L.sort_second;
+    pos.assign(2 * (n_buckets + 1), 0u);
+    key.resize(n_all);                        // bucket of a pair's first chunk
+    second.assign(n_all, 0);                  // chunk is the continuation of an earlier one
     const double *lat = L.lat.data();
-    auto tile_of = [&](double v) {
-      const double b = (v - lo) * inv_tile;  // >= 1 by construction of lo
-      const size_t bi = b > 0 ? (size_t)b : 0;
-      return bi >= nb1 ? nb1 - 1 : bi;
-    };
+    const double nb1_max = (double)(nb1 - 1);
     for (size_t i = 0; i < n_all; i++) {
+      if (second[i]) continue;
       const SprChunk &c = L.chunks[i];
-      const size_t bi = tile_of(lat[c.along_off]) * nb1 + tile_of(c.across);
-      key[i] = (uint32_t)bi;
+      if (succ[i] >= 0) second[(size_t)succ[i]] = 1;
+      // tile indices: (v - lo) / tile >= 1 by construction of lo
+      const double ta = std::min((lat[c.along_off] - lo) * inv_tile, nb1_max);
+      const double tc = std::min((c.across - lo) * inv_tile, nb1_max);
+      const uint32_t bi = (uint32_t)(ta > 0 ? ta : 0) * (uint32_t)nb1 + (uint32_t)(tc > 0 ? tc : 0);
+      key[i] = bi;
       pos[(size_t)c.dir * (n_buckets + 1) + bi + 1]++;
     }
-    size_t start[2], used[2];
+    size_t start[2], units[2];
     for (uint32_t d = 0; d < 2; d++) {
       uint32_t *pd = pos.data() + (size_t)d * (n_buckets + 1);
       for (size_t b2 = 0; b2 < n_buckets; b2++) pd[b2 + 1] += pd[b2];
-      start[d] = d == 0 ? 0 : ((used[0] + 31) & ~(size_t)31);
-      used[d] = start[d] + pd[n_buckets];
+      units[d] = pd[n_buckets];
+      start[d] = d == 0 ? 0 : start[0] + ((units[0] + 31) / 32) * 64;
     }
-    const size_t total = (used[1] + 31) & ~(size_t)31;
-    if (out.size() != total) out.resize(total);  // usually the size of the previous call: nothing to do
+    const size_t total = start[1] + ((units[1] + 31) / 32) * 64;
+    if (out.size() != total) out.resize(total);  // usually the size of the previous call
+    SprChunk empty[2] = {SprChunk{}, SprChunk{}};  // empty chunks (valid == 0) carry their direction
+    empty[1].dir = 1;
     for (size_t i = 0; i < n_all; i++) {
+      if (second[i]) continue;
       const uint32_t d = L.chunks[i].dir;
-      out[start[d] + pos[(size_t)d * (n_buckets + 1) + key[i]]++] = L.chunks[i];
+      const size_t u = pos[(size_t)d * (n_buckets + 1) + key[i]]++;
+      const size_t slot = start[d] + (u / 32) * 64 + (u % 32);
+      out[slot] = L.chunks[i];
+      out[slot + 32] = succ[i] >= 0 ? L.chunks[(size_t)succ[i]] : empty[d];
     }
-    for (uint32_t d = 0; d < 2; d++) {  // padding chunks (valid == 0) carry their direction
+    for (uint32_t d = 0; d < 2; d++) {
       L.dir_begin[d] = (uint32_t)start[d];
-      L.dir_end[d] = (uint32_t)((used[d] + 31) & ~(size_t)31);
-      for (size_t i = used[d]; i < L.dir_end[d]; i++) { out[i] = SprChunk{}; out[i].dir = d; }
+      L.dir_end[d] = (uint32_t)(d == 0 ? start[1] : total);
+      for (size_t u = units[d]; u < ((units[d] + 31) / 32) * 32; u++) {  // unused lanes of the last double group
+        const size_t slot = start[d] + (u / 32) * 64 + (u % 32);
+        out[slot] = empty[d];
+        out[slot + 32] = empty[d];
+      }
     }
   }
   L.ring_major = ring_major;

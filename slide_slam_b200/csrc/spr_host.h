@@ -52,6 +52,9 @@ struct Lattice {
   uint64_t n_translations = 0;
   uvec<SprChunk> chunks;   // grouped by direction (see dir_begin / Ring::dbegin), warp-padded
   uvec<SprChunk> scratch;  // regrouping buffer, kept for its capacity
+  std::vector<int32_t> succ;      // scratch of build_lattice (kept for their capacity)
+  std::vector<uint32_t> sort_pos, sort_key;
+  std::vector<uint8_t> sort_second;
   bool ring_major = false;
   uint32_t dir_begin[2] = {0, 0}, dir_end[2] = {0, 0};  // !ring_major: all chunks of direction d
 };

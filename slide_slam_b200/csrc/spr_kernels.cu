@@ -226,7 +226,7 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
     if (item >= n_todo) break;
     if (K.cand_items) item = (long long)__ldg(K.cand_items + item);  // verification phase: candidate items only
     const int a = (int)(item / n_wg_local);
-    const int wg = K.shard_index + (int)(item % n_wg_local) * K.shard_count;
+    const int wg = spr_shard_group((int)(item % n_wg_local), K.shard_index, K.shard_count);
     const uint32_t cidx = K.chunk_begin + (uint32_t)wg * SPR_WARP_CHUNKS + (uint32_t)lane;  // < chunk_end (padded)
     SprChunk ch;
     {
@@ -436,7 +436,7 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int t
   const int n_wg = (int)(n_chunks / SPR_WARP_CHUNKS);
   const int sc = K.shard_count > 1 ? K.shard_count : 1;
   const int si = K.shard_count > 1 ? K.shard_index : 0;
-  const int n_wg_local = n_wg > si ? (n_wg - si + sc - 1) / sc : 0;
+  const int n_wg_local = spr_shard_local_groups(n_wg, si, sc);
   if (n_wg_local <= 0) return cudaSuccess;
   SprLaunch K2 = K;
   K2.shard_index = si;

@@ -4,7 +4,16 @@
 
 #include "spr_types.h"
 
-#define SPR_WARP_CHUNKS 32  // chunks per work item (one warp); the sharding granule
+#define SPR_WARP_CHUNKS 32  // chunks per group (one warp of the exact kernel)
+
+// Sharding granule = a DOUBLE GROUP (64 chunks: 32 chunks + their 32 continuations along the row,
+// one work item of the bound kernel).  Double groups are dealt round-robin to the shards; the
+// k-th local group of shard si (of sc) is group spr_shard_group(k, si, sc) of the chunk range.
+SPR_HD int spr_shard_group(int k_local, int si, int sc) { return (((k_local >> 1) * sc + si) << 1) | (k_local & 1); }
+static inline int spr_shard_local_groups(int n_groups, int si, int sc) {  // n_groups is even
+  const int n_dg = n_groups / 2;
+  return n_dg > si ? 2 * ((n_dg - si + sc - 1) / sc) : 0;
+}
 
 // One pass of the lattice search = one (label, direction) pair over a range of chunks.
 struct SprLaunch {

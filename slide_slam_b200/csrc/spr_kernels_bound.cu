@@ -24,7 +24,7 @@
 #define SPR_FULL 0xffffffffu
 #define SPR_SMEM_LIMIT (227 * 1024)
 #ifndef SPB_THREADS
-#define SPB_THREADS 1024
+#define SPB_THREADS 768
 #endif
 
 __device__ __forceinline__ uint32_t spb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -54,16 +54,32 @@ __device__ __forceinline__ void spb_fa(uint32_t a, uint32_t b, uint32_t c, uint3
   cy = (a & b) | (c & (a ^ b));
 }
 
+// add plane `c` (weight 2^from) into the binary counter P
+template <int PLANES>
+__device__ __forceinline__ void spb_ripple(uint32_t (&P)[PLANES], uint32_t c, int from) {
+#pragma unroll
+  for (int i = 0; i < PLANES; i++) {
+    if (i < from) continue;
+    const uint32_t t = P[i] & c;
+    P[i] ^= c;
+    c = t;
+  }
+}
+
+// Work item = (yaw, DOUBLE GROUP): lane k owns chunk k of the group (32 lattice samples along its
+// row) and chunk k of the next group, which continues it for another 32 samples (empty where the
+// row ends).  One probe = three consecutive bitmap words of the row and two funnel shifts = the
+// filter bits of 64 hypotheses.
 template <int PLANES, bool SMEM_TAB>
-__global__ void __launch_bounds__(SMEM_TAB ? SPB_THREADS : 256, SMEM_TAB ? 1 : 4)
-spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constant__ SprBoundLaunch B, const int n_wg_local,
+__global__ void __launch_bounds__(SMEM_TAB ? SPB_THREADS : 256, SMEM_TAB ? 1 : 3)
+spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constant__ SprBoundLaunch B, const int n_dg_local,
                          const long long n_items) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const SprGrid &G = V.grid;
   const int32_t F = G.F;
   const uint32_t d = B.dir;
-  const uint32_t W = (uint32_t)G.W[d], maxbit = (uint32_t)G.maxbit[d];
+  const uint32_t W = (uint32_t)G.W[d], maxbit2 = (uint32_t)G.maxbit[d] + 32u;
   // Row band [row_begin, row_end) of the planes handled by this launch (the whole plane unless it
   // does not fit in shared memory).  Staged as band_rows rows + one all-zero row per label; rows
   // outside the band clamp onto the zero row (unsigned min), so the probe code is unchanged.
@@ -73,18 +89,25 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
   const int32_t row_shift = SMEM_TAB ? (int32_t)(B.row_begin << F) : 0;
 
   if (SMEM_TAB) {  // one TMA bulk copy per label
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (((size_t)B.n_labels * BW + 3) & ~(size_t)3));
+    // [4 zero words][labels x BW words][4 zero words][mbarrier]: a probe reads the word before and
+    // the word after its base word, also for the first row of the first label / the last zero row
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 4 + (size_t)B.n_labels * BW + 4);
     if (threadIdx.x == 0) {
       spb_mbar_init(bar, 1u);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = threadIdx.x; i < (uint32_t)B.n_labels * W; i += blockDim.x)
-      smem[(size_t)(i / W) * BW + (size_t)band_rows * W + (i % W)] = 0u;
+      smem[4 + (size_t)(i / W) * BW + (size_t)band_rows * W + (i % W)] = 0u;
+    if (threadIdx.x < 4) { smem[threadIdx.x] = 0u; smem[4 + (size_t)B.n_labels * BW + threadIdx.x] = 0u; }
+    if (threadIdx.x < (uint32_t)B.n_labels * 4u) {  // alignment words behind each label's zero row
+      const uint32_t k = threadIdx.x >> 2, j = threadIdx.x & 3u;
+      if ((band_rows + 1u) * W + j < BW) smem[4 + (size_t)k * BW + (band_rows + 1u) * W + j] = 0u;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       spb_mbar_expect_tx(bar, (uint32_t)B.n_labels * band_rows * W * 4u);
       for (int k = 0; k < B.n_labels; k++)
-        spb_bulk_g2s(smem + (size_t)k * BW,
+        spb_bulk_g2s(smem + 4 + (size_t)k * BW,
                      V.bitmap + ((size_t)B.labels[k] * G.label_stride + (d ? G.plane_words[0] : 0u) + (size_t)B.row_begin * W),
                      band_rows * W * 4u, bar);
     }
@@ -102,42 +125,46 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
     if (lane == 0) item = (long long)atomicAdd(B.work_counter, 1ull);
     item = __shfl_sync(SPR_FULL, item, 0);
     if (item >= n_items) break;
-    const int a = (int)(item / n_wg_local);
-    const int wg = B.shard_index + (int)(item % n_wg_local) * B.shard_count;
-    const uint32_t cidx = B.chunk_begin + (uint32_t)wg * SPR_WARP_CHUNKS + (uint32_t)lane;
-    const uint4 *cp = reinterpret_cast<const uint4 *>(V.chunks + cidx);
-    const uint4 c0 = __ldcs(cp);
+    const int a = (int)(item / n_dg_local);
+    const int dg = B.shard_index + (int)(item % n_dg_local) * B.shard_count;
+    const uint32_t cidx = B.chunk_begin + (uint32_t)dg * (2 * SPR_WARP_CHUNKS) + (uint32_t)lane;  // first chunk; + 32: its continuation
+    const uint4 c0 = __ldcs(reinterpret_cast<const uint4 *>(V.chunks + cidx));
     const double across = __hiloint2double((int)c0.y, (int)c0.x);
-    const uint32_t along_off = c0.z, valid = c0.w;
+    const uint32_t along_off = c0.z, validA = c0.w;
+    const uint32_t validB = __ldcs(reinterpret_cast<const uint4 *>(V.chunks + cidx + SPR_WARP_CHUNKS)).w;
     const int32_t aq0 = spr_fx(across, G.S);
     const int32_t bq0 = spr_fx(__ldg(V.lat + along_off), G.S);
-    const int32_t aqb = spr_bias_across(aq0, F) - row_shift, bqb = spr_bias_along(bq0, F);
+    const int32_t aqb = spr_bias_across(aq0, F) - row_shift, bqb2 = spr_bias_along(bq0, F) + (32 << F);
     const int32_t big = 1 << 30;
-    const bool live = valid != 0u;
-    const int32_t lx0 = d ? bq0 : aq0, lx1 = d ? bq0 + (32 << F) : aq0;
-    const int32_t ly0 = d ? aq0 : bq0, ly1 = d ? aq0 : bq0 + (32 << F);
+    const bool live = validA != 0u;  // a continuation exists only behind a first chunk
+    const int32_t ext = (validB ? 64 : 32) << F;
+    const int32_t lx0 = d ? bq0 : aq0, lx1 = d ? bq0 + ext : aq0;
+    const int32_t ly0 = d ? aq0 : bq0, ly1 = d ? aq0 : bq0 + ext;
     const int32_t X0 = __reduce_min_sync(SPR_FULL, live ? lx0 : big), X1 = __reduce_max_sync(SPR_FULL, live ? lx1 : -big);
     const int32_t Y0 = __reduce_min_sync(SPR_FULL, live ? ly0 : big), Y1 = __reduce_max_sync(SPR_FULL, live ? ly1 : -big);
 
-    // bit-sliced counters: P[i] = bit i of the 32 bounds of this lane's chunk
-    uint32_t P[PLANES];
-    uint32_t *gp = B.planes + (((size_t)a * n_wg_total + cidx / SPR_WARP_CHUNKS) * PLANES) * 32 + lane;
+    // bit-sliced counters: PA[i] / PB[i] = bit i of the 32 bounds of the lane's first / second chunk
+    uint32_t PA[PLANES], PB[PLANES];
+    uint32_t *gpA = B.planes + (((size_t)a * n_wg_total + cidx / SPR_WARP_CHUNKS) * PLANES) * 32 + lane;
+    uint32_t *gpB = gpA + (size_t)PLANES * 32;
     if (B.first) {
 #pragma unroll
-      for (int i = 0; i < PLANES; i++) P[i] = 0u;
+      for (int i = 0; i < PLANES; i++) PA[i] = PB[i] = 0u;
     } else {
 #pragma unroll
-      for (int i = 0; i < PLANES; i++) P[i] = __ldcs(gp + i * 32);
+      for (int i = 0; i < PLANES; i++) { PA[i] = __ldcs(gpA + i * 32); PB[i] = __ldcs(gpB + i * 32); }
     }
+    // carry-save state: planes 0..1 absorb four probe results per step and emit one plane of weight
+    // 4; two of those make one of weight 8 (into plane 2), ... up to weight 32, which ripples on
+    uint32_t p4A = 0u, p8A = 0u, p16A = 0u, p4B = 0u, p8B = 0u, p16B = 0u;
+    bool have4 = false, have8 = false, have16 = false;
 
-    uint32_t pend8 = 0u, pend16 = 0u;
-    bool have8 = false, have16 = false;
     if (X0 <= X1) {
       for (int k = 0; k < B.n_labels; k++) {
         const int l = B.labels[k];
         const int g0 = V.label_gseg[l], g1 = V.label_gseg[l + 1];
         if (g0 >= g1) continue;
-        const uint32_t *bits = SMEM_TAB ? smem + (size_t)k * BW
+        const uint32_t *bits = SMEM_TAB ? smem + 4 + (size_t)k * BW
                                         : V.bitmap + ((size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u));
         SprBox lb = V.labelbox[l];
         if (d == 0) { lb.x0 = max(lb.x0, band_lo); lb.x1 = min(lb.x1, band_hi); }  // marked cells inside the band
@@ -153,110 +180,91 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
             vis = box.y > tx_lo && box.x < tx_hi && box.w > ty_lo && box.z < ty_hi;
           }
           uint32_t vm = __ballot_sync(SPR_FULL, vis);
-#ifdef SPB_DB
-          int4 nx[SPR_QGROUP / 2];
-          if (vm) {
-            const int4 *q = qgp + (size_t)(gb - g0 + (__ffs(vm) - 1)) * (SPR_QGROUP / 2);
-#pragma unroll
-            for (int u = 0; u < SPR_QGROUP / 2; u++) nx[u] = __ldg(q + u);
-          }
-#endif
           while (vm) {
             const int kk = __ffs(vm) - 1;
             vm &= vm - 1;
             const int4 *q = qgp + (size_t)(gb - g0 + kk) * (SPR_QGROUP / 2);
-#ifdef SPB_PREFETCH
-            if (vm) asm volatile("prefetch.global.L1 [%0];" ::"l"(qgp + (size_t)(gb - g0 + (__ffs(vm) - 1)) * (SPR_QGROUP / 2)));
-#endif
             int4 v[SPR_QGROUP / 2];
-#ifdef SPB_DB
-#pragma unroll
-            for (int u = 0; u < SPR_QGROUP / 2; u++) v[u] = nx[u];
-            if (vm) {  // the next visible group's coordinates are in flight while this one is probed
-              const int4 *qn = qgp + (size_t)(gb - g0 + (__ffs(vm) - 1)) * (SPR_QGROUP / 2);
-#pragma unroll
-              for (int u = 0; u < SPR_QGROUP / 2; u++) nx[u] = __ldg(qn + u);
-            }
-            (void)q;
-#else
 #pragma unroll
             for (int u = 0; u < SPR_QGROUP / 2; u++) v[u] = __ldg(q + u);
-#endif
-            uint32_t H[SPR_QGROUP];
 #pragma unroll
-            for (int u = 0; u < SPR_QGROUP / 2; u++) {
-              H[2 * u] = spr_probe(bits, W, Rm1, maxbit, F, aqb + v[u].x, bqb + v[u].y, SPR_FULL);
-              H[2 * u + 1] = spr_probe(bits, W, Rm1, maxbit, F, aqb + v[u].z, bqb + v[u].w, SPR_FULL);
-            }
-            // carry-save counting: P[0..4] are the running ones / twos / fours / eights / sixteens
-            // planes; every group folds its 8 one-bit addends in with 7 carry-save adders and emits
-            // one plane of weight 8, two of those make one of weight 16, two of those one of weight
-            // 32, which ripples into the upper planes
-            uint32_t tA, tB, fA, fB, e8;
-            spb_fa(P[0], H[0], H[1], P[0], tA);
-            spb_fa(P[0], H[2], H[3], P[0], tB);
-            spb_fa(P[1], tA, tB, P[1], fA);
-            spb_fa(P[0], H[4], H[5], P[0], tA);
-            spb_fa(P[0], H[6], H[7], P[0], tB);
-            spb_fa(P[1], tA, tB, P[1], fB);
-            spb_fa(P[2], fA, fB, P[2], e8);
-            if (have8) {
-              uint32_t s16;
-              spb_fa(P[3], pend8, e8, P[3], s16);
-              have8 = false;
-              if (have16) {
-                uint32_t c;
-                spb_fa(P[4], pend16, s16, P[4], c);
-                have16 = false;
+            for (int hq = 0; hq < 2; hq++) {  // four queries at a time
+              uint32_t HA[4], HB[4];
 #pragma unroll
-                for (int i = 5; i < PLANES; i++) {
-                  const uint32_t t = P[i] & c;
-                  P[i] ^= c;
-                  c = t;
-                }
-              } else {
-                pend16 = s16;
-                have16 = true;
+              for (int u = 0; u < 4; u++) {
+                const int4 vv = v[2 * hq + (u >> 1)];
+                const int32_t qa_ = (u & 1) ? vv.z : vv.x, qb_ = (u & 1) ? vv.w : vv.y;
+                const uint32_t row = min((uint32_t)((aqb + qa_) >> F), Rm1);     // rows 0 and Rm1 are all-zero
+                // bit = plane bit of the SECOND chunk's first sample (the first chunk starts 32 bits
+                // earlier, possibly before the row: the word in front of a row is a zero pad word)
+                const uint32_t bit = min((uint32_t)((bqb2 + qb_) >> F), maxbit2);  // words >= maxbit/32 are all-zero
+                const uint32_t *p = bits + (row * W + (bit >> 5));
+                const uint32_t w0 = p[-1], w1 = p[0], w2 = p[1];
+                HA[u] = __funnelshift_r(w0, w1, bit);
+                HB[u] = __funnelshift_r(w1, w2, bit);
               }
-            } else {
-              pend8 = e8;
-              have8 = true;
+              uint32_t tA, tB, f4A, f4B;
+              spb_fa(PA[0], HA[0], HA[1], PA[0], tA);
+              spb_fa(PA[0], HA[2], HA[3], PA[0], tB);
+              spb_fa(PA[1], tA, tB, PA[1], f4A);
+              spb_fa(PB[0], HB[0], HB[1], PB[0], tA);
+              spb_fa(PB[0], HB[2], HB[3], PB[0], tB);
+              spb_fa(PB[1], tA, tB, PB[1], f4B);
+              if (!have4) { p4A = f4A; p4B = f4B; have4 = true; continue; }
+              uint32_t e8A, e8B;
+              spb_fa(PA[2], p4A, f4A, PA[2], e8A);
+              spb_fa(PB[2], p4B, f4B, PB[2], e8B);
+              have4 = false;
+              if (!have8) { p8A = e8A; p8B = e8B; have8 = true; continue; }
+              uint32_t s16A, s16B;
+              spb_fa(PA[3], p8A, e8A, PA[3], s16A);
+              spb_fa(PB[3], p8B, e8B, PB[3], s16B);
+              have8 = false;
+              if (!have16) { p16A = s16A; p16B = s16B; have16 = true; continue; }
+              uint32_t cA, cB;
+              spb_fa(PA[4], p16A, s16A, PA[4], cA);
+              spb_fa(PB[4], p16B, s16B, PB[4], cB);
+              have16 = false;
+              spb_ripple<PLANES>(PA, cA, 5);
+              spb_ripple<PLANES>(PB, cB, 5);
             }
           }
         }
       }
     }
-    if (have8) {  // pending planes back into the binary counter
-      uint32_t c = pend8;
-#pragma unroll
-      for (int i = 3; i < PLANES; i++) { const uint32_t t = P[i] & c; P[i] ^= c; c = t; }
-    }
-    if (have16) {
-      uint32_t c = pend16;
-#pragma unroll
-      for (int i = 4; i < PLANES; i++) { const uint32_t t = P[i] & c; P[i] ^= c; c = t; }
-    }
+    // pending planes back into the binary counters
+    if (have4) { spb_ripple<PLANES>(PA, p4A, 2); spb_ripple<PLANES>(PB, p4B, 2); }
+    if (have8) { spb_ripple<PLANES>(PA, p8A, 3); spb_ripple<PLANES>(PB, p8B, 3); }
+    if (have16) { spb_ripple<PLANES>(PA, p16A, 4); spb_ripple<PLANES>(PB, p16B, 4); }
 #pragma unroll
     for (int i = 0; i < PLANES; i++) {
-      P[i] &= valid;
-      __stcs(gp + i * 32, P[i]);
+      PA[i] &= validA;
+      PB[i] &= validB;
+      __stcs(gpA + i * 32, PA[i]);
+      __stcs(gpB + i * 32, PB[i]);
     }
     if (B.last) {
-      // largest bound of the lane (MSB-first narrowing of the candidate bits), then of the warp
-      uint32_t cand = valid, val = 0u;
+      // largest bound of each chunk (MSB-first narrowing of the candidate bits), then of each group
 #pragma unroll
-      for (int i = PLANES - 1; i >= 0; i--) {
-        const uint32_t t = cand & P[i];
-        if (t) { cand = t; val |= 1u << i; }
+      for (int half = 0; half < 2; half++) {
+        const uint32_t valid = half ? validB : validA;
+        uint32_t cand = valid, val = 0u;
+#pragma unroll
+        for (int i = PLANES - 1; i >= 0; i--) {
+          const uint32_t t = cand & (half ? PB[i] : PA[i]);
+          if (t) { cand = t; val |= 1u << i; }
+        }
+        const bool lv = valid != 0u;
+        const uint32_t packed = lv ? ((val << 5) | (uint32_t)(__ffs(cand) - 1)) : 0u;
+        const uint32_t wmax = __reduce_max_sync(SPR_FULL, packed);
+        const uint32_t who = __ballot_sync(SPR_FULL, packed == wmax && lv);
+        const uint32_t grp = cidx / SPR_WARP_CHUNKS + (uint32_t)half;
+        if (lane == 0) B.item_ub[(size_t)a * n_wg_total + grp] = wmax >> 5;
+        if (who && lane == __ffs(who) - 1)
+          atomicMax(B.seed_key + (size_t)a * SPR_SEED_SLOTS + grp % SPR_SEED_SLOTS,
+                    ((unsigned long long)(val + 1u) << SPR_KEY_IDX_BITS) |
+                        ((unsigned long long)(cidx + (uint32_t)half * SPR_WARP_CHUNKS) * 32ull + (unsigned long long)(packed & 31u)));
       }
-      const uint32_t packed = live ? ((val << 5) | (uint32_t)(__ffs(cand) - 1)) : 0u;
-      const uint32_t wmax = __reduce_max_sync(SPR_FULL, packed);
-      const uint32_t who = __ballot_sync(SPR_FULL, packed == wmax && live);
-      if (lane == 0) B.item_ub[(size_t)a * n_wg_total + cidx / SPR_WARP_CHUNKS] = wmax >> 5;
-      if (who && lane == __ffs(who) - 1)
-        atomicMax(B.seed_key + (size_t)a * SPR_SEED_SLOTS + (cidx / SPR_WARP_CHUNKS) % SPR_SEED_SLOTS,
-                  ((unsigned long long)(val + 1u) << SPR_KEY_IDX_BITS) |
-                                      ((unsigned long long)cidx * 32ull + (unsigned long long)(packed & 31u)));
     }
     __syncwarp();
   }
@@ -323,7 +331,7 @@ spr_select_items_kernel(const SprBoundLaunch B, const int n_wg_local, const long
     bool take = false;
     if (i < n_items) {
       const int a = (int)(i / n_wg_local);
-      const int wg = B.shard_index + (int)(i % n_wg_local) * B.shard_count;
+      const int wg = spr_shard_group((int)(i % n_wg_local), B.shard_index, B.shard_count);
       take = B.item_ub[(size_t)a * n_wg_total + B.chunk_begin / SPR_WARP_CHUNKS + (uint32_t)wg] >= tau;
     }
     const uint32_t m = __ballot_sync(SPR_FULL, take);
@@ -342,7 +350,7 @@ cudaError_t spr_launch_select_items(const SprView &V, const SprBoundLaunch &B, c
   const int n_wg = (int)((B.chunk_end - B.chunk_begin) / SPR_WARP_CHUNKS);
   const int sc = B.shard_count > 1 ? B.shard_count : 1;
   const int si = B.shard_count > 1 ? B.shard_index : 0;
-  const int n_wg_local = n_wg > si ? (n_wg - si + sc - 1) / sc : 0;
+  const int n_wg_local = spr_shard_local_groups(n_wg, si, sc);
   if (n_wg_local <= 0) return cudaSuccess;
   SprBoundLaunch B2 = B;
   B2.shard_index = si;
@@ -369,8 +377,8 @@ void spr_bound_plan(const SprView &V, uint32_t dir, int n_active, int *labels_pe
     const long v = std::atol(e);
     if (v > 0 && (size_t)v < limit) { limit = (size_t)v; min_nqp = 0; }
   }
-  if ((R + 1) * W4 + 16 <= limit) {
-    int per = (int)(limit / ((R + 1) * W4 + 16));
+  if ((R + 1) * W4 + 64 <= limit) {
+    int per = (int)((limit - 48) / ((R + 1) * W4 + 16));
     if (per > SPR_BOUND_MAX_LABELS) per = SPR_BOUND_MAX_LABELS;
     if (per > n_active) per = n_active;
     // spread the labels evenly over the launches (5 labels, 4 fit -> 3 + 2)
@@ -391,18 +399,18 @@ void spr_bound_plan(const SprView &V, uint32_t dir, int n_active, int *labels_pe
 }
 
 template <int PLANES>
-static cudaError_t spb_launch(const SprView &V, const SprBoundLaunch &B, int n_wg_local, long long n_items, int sm_count,
+static cudaError_t spb_launch(const SprView &V, const SprBoundLaunch &B, int n_dg_local, long long n_items, int sm_count,
                               cudaStream_t st) {
   const size_t BW4 = (((size_t)(B.row_end - B.row_begin + 1) * (size_t)V.grid.W[B.dir] + 3) & ~(size_t)3) * 4;
-  const size_t smem = (((size_t)B.n_labels * BW4 + 15) & ~(size_t)15) + 16;
+  const size_t smem = 16 + (size_t)B.n_labels * BW4 + 16 + 16;  // 4 zero words in front and behind + the mbarrier
   if (B.row_end > B.row_begin && smem <= SPR_SMEM_LIMIT) {
     cudaError_t e = cudaFuncSetAttribute(spr_bound_lattice_kernel<PLANES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long want = (n_items + SPB_THREADS / 32 - 1) / (SPB_THREADS / 32);
-    spr_bound_lattice_kernel<PLANES, true><<<(int)(want < sm_count ? want : sm_count), SPB_THREADS, smem, st>>>(V, B, n_wg_local, n_items);
+    spr_bound_lattice_kernel<PLANES, true><<<(int)(want < sm_count ? want : sm_count), SPB_THREADS, smem, st>>>(V, B, n_dg_local, n_items);
   } else {
-    const long long want = (n_items + 7) / 8, cap = (long long)sm_count * 4;
-    spr_bound_lattice_kernel<PLANES, false><<<(int)(want < cap ? want : cap), 256, 0, st>>>(V, B, n_wg_local, n_items);
+    const long long want = (n_items + 7) / 8, cap = (long long)sm_count * 3;
+    spr_bound_lattice_kernel<PLANES, false><<<(int)(want < cap ? want : cap), 256, 0, st>>>(V, B, n_dg_local, n_items);
   }
   return cudaGetLastError();
 }
@@ -413,13 +421,13 @@ cudaError_t spr_launch_bound_lattice(const SprView &V, const SprBoundLaunch &B, 
   const int n_wg = (int)((B.chunk_end - B.chunk_begin) / SPR_WARP_CHUNKS);
   const int sc = B.shard_count > 1 ? B.shard_count : 1;
   const int si = B.shard_count > 1 ? B.shard_index : 0;
-  const int n_wg_local = n_wg > si ? (n_wg - si + sc - 1) / sc : 0;
-  if (n_wg_local <= 0) return cudaSuccess;
+  const int n_dg_local = spr_shard_local_groups(n_wg, si, sc) / 2;
+  if (n_dg_local <= 0) return cudaSuccess;
   SprBoundLaunch B2 = B;
   B2.shard_index = si;
   B2.shard_count = sc;
-  const long long n_items = (long long)n_wg_local * V.n_yaw;
+  const long long n_items = (long long)n_dg_local * V.n_yaw;
   if (n_launches) (*n_launches)++;
-  return n_planes == 12 ? spb_launch<12>(V, B2, n_wg_local, n_items, sm_count, st)
-                        : spb_launch<16>(V, B2, n_wg_local, n_items, sm_count, st);
+  return n_planes == 12 ? spb_launch<12>(V, B2, n_dg_local, n_items, sm_count, st)
+                        : spb_launch<16>(V, B2, n_dg_local, n_items, sm_count, st);
 }
