@@ -37,8 +37,8 @@ ROS = {"search_xy_step_size": 0.5, "search_yaw_step_size_degrees": 5.0, "match_t
        "match_threshold_dimension": 1.0, "ignore_dimension": 0, "min_num_inliers": 15, "dilation_factor": 1.2}
 ORACLE_KW = dict(match_xy_step_size=0.5, yaw_step_deg=5.0, match_threshold=0.5, match_threshold_dimension=1.0,
                  ignore_dimension=0, min_num_inliers=15)
-ROOFLINE_TRAFFIC_BYTES = 6.1e6   # dram read 1.65 MB + write 4.46 MB per launch, profiles/r1_n_bound_lattice_summary.txt
-ROOFLINE_TRAFFIC_SOURCE = "profiles/r1_n_bound_lattice_summary.txt (ncu --set full, per launch)"
+ROOFLINE_TRAFFIC_BYTES = 6.1e6   # dram read 1.63 MB + write 4.51 MB per launch, profiles/r1_q_bound_lattice_summary.txt
+ROOFLINE_TRAFFIC_SOURCE = "profiles/r1_q_bound_lattice_summary.txt (ncu --set full, per launch)"
 ALG_BYTES_PER_HYP = 24.0  # 16 B hypothesis record + 8 B packed score
 METRIC = "hypotheses_scored_per_s"
 UNIT = "hypotheses/s"

@@ -80,6 +80,7 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
   const int32_t F = G.F;
   const uint32_t d = B.dir;
   const uint32_t W = (uint32_t)G.W[d], maxbit2 = (uint32_t)G.maxbit[d] + 32u;
+  const uint32_t W4 = W * 4u;
   // Row band [row_begin, row_end) of the planes handled by this launch (the whole plane unless it
   // does not fit in shared memory).  Staged as band_rows rows + one all-zero row per label; rows
   // outside the band clamp onto the zero row (unsigned min), so the probe code is unchanged.
@@ -198,7 +199,10 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
                 // bit = plane bit of the SECOND chunk's first sample (the first chunk starts 32 bits
                 // earlier, possibly before the row: the word in front of a row is a zero pad word)
                 const uint32_t bit = min((uint32_t)((bqb2 + qb_) >> F), maxbit2);  // words >= maxbit/32 are all-zero
-                const uint32_t *p = bits + (row * W + (bit >> 5));
+                // byte offset with two multiply-adds (FMA pipe) instead of LEA.HI + LEA (ALU pipe, the busy one)
+                uint32_t boff;
+                asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(boff) : "r"(bit >> 5), "r"(row * W4));
+                const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(bits) + boff);
                 const uint32_t w0 = p[-1], w1 = p[0], w2 = p[1];
                 HA[u] = __funnelshift_r(w0, w1, bit);
                 HB[u] = __funnelshift_r(w1, w2, bit);
