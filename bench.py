@@ -208,22 +208,26 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    rec_host = torch.zeros(2, dtype=torch.int64).pin_memory()
-    rec_dev = torch.zeros(2, dtype=torch.int64, device=dev)
-    rec_all = torch.zeros(2 * max(world, 1), dtype=torch.int64, device=dev)
+    # results: one 16-byte (canonical index, inliers) record per searched pair.  Weak scaling (every
+    # GPU matches its own pairs): the ranks run independently and the records of all timed steps
+    # are all-gathered once at the end of the timed region.  Shard mode (one pair split over the
+    # GPUs): the top-1 records are all-gathered and merged after every search.
+    n_rec = 1 if shard_mode else max(args.steps, 1)
+    rec_host = torch.zeros(2 * n_rec, dtype=torch.int64).pin_memory()
+    rec_dev = torch.zeros(2 * n_rec, dtype=torch.int64, device=dev)
+    rec_all = torch.zeros(2 * n_rec * max(world, 1), dtype=torch.int64, device=dev)
 
     def gather_and_merge(res):
-        """all-gather of the 16-byte (canonical index, inliers) records + deterministic merge"""
-        if world == 1:
+        """shard mode: all-gather of the top-1 records + deterministic merge"""
+        if world == 1 or not shard_mode:
             return
         rec_host[0], rec_host[1] = int(res.best_hyp_index), int(res.best_num_inliers)
         rec_dev.copy_(rec_host, non_blocking=True)
         dist.all_gather_into_tensor(rec_all, rec_dev)
-        if shard_mode:
-            recs = (capi.TopkRecord * world)()
-            for i, t in enumerate(rec_all.view(world, 2).cpu().tolist()):
-                recs[i].hyp_index, recs[i].inliers, recs[i].rank = int(t[0]), int(t[1]), i
-            return lib.slide_pr_merge_records(recs, world)
+        recs = (capi.TopkRecord * world)()
+        for i, t in enumerate(rec_all.view(world, 2).cpu().tolist()):
+            recs[i].hyp_index, recs[i].inliers, recs[i].rank = int(t[0]), int(t[1]), i
+        return lib.slide_pr_merge_records(recs, world)
 
     def one_step():
         if shard_mode:
@@ -242,7 +246,7 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier()
     torch.cuda.synchronize()
     step_ms, kern_ms, hyps, launches = [], [], 0, 0
-    for _ in range(args.steps):
+    for i in range(args.steps):
         flush.fill_(1)                      # L2 flush between timed iterations (not timed)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -253,6 +257,17 @@ def run_ours(args, rank, world, local_rank):
         kern_ms.append(res.kernel_ms)
         hyps += res.hypotheses_scored
         launches += res.gpu_launches
+        if not shard_mode:
+            rec_host[2 * i], rec_host[2 * i + 1] = int(res.best_hyp_index), int(res.best_num_inliers)
+    if world > 1 and not shard_mode:        # timed: the one exchange of the weak-scaling job
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rec_dev.copy_(rec_host, non_blocking=True)
+        dist.all_gather_into_tensor(rec_all, rec_dev)
+        e1.record(stream)
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        assert bool((rec_all.view(world, -1, 2)[:, :, 1] == int(res.best_num_inliers)).all())  # same pair on every rank
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -321,7 +336,7 @@ def run_ours(args, rank, world, local_rank):
                        "hypotheses_per_pair": int(info.match.hypotheses_scored),
                        "lattice": "0.5 m / 5 deg, dilation 1.2 (sloam-forest-parking-lot.yaml)",
                        "parallelism": ("hypothesis space of one pair sharded over %d GPUs, NCCL all-gather of top-1" % world) if shard_mode
-                       else ("one map pair per GPU (the same synthetic pair on every rank), NCCL all-gather of results" if world > 1 else "single GPU"),
+                       else ("one map pair per GPU and step (the same synthetic pair on every rank), ranks independent, one NCCL all-gather of all result records at the end of the timed region" if world > 1 else "single GPU"),
                        "l2": "flushed between timed steps (256 MiB write)", "decision_arithmetic": "fp64, non-fused (bit-exact vs reference)",
                        "search": "bound-and-verify (library default): bitmap-filter upper bound of every hypothesis, exact fp64 verification of "
                                  "those whose bound reaches the running best; winner, inlier count and correspondences identical to the exhaustive search"},
