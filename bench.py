@@ -260,6 +260,8 @@ def run_ours(args, rank, world, local_rank):
         if not shard_mode:
             rec_host[2 * i], rec_host[2 * i + 1] = int(res.best_hyp_index), int(res.best_num_inliers)
     if world > 1 and not shard_mode:        # timed: the one exchange of the weak-scaling job
+        torch.cuda.synchronize()
+        dist.barrier()                      # untimed, like the L2 flushes: the ranks' untimed host work differs
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         rec_dev.copy_(rec_host, non_blocking=True)
