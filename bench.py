@@ -239,6 +239,11 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         one_step()
+    if world > 1 and not shard_mode:        # warm-up of the exchange too (NCCL sets its channels up lazily)
+        for _ in range(2):
+            rec_dev.copy_(rec_host, non_blocking=True)
+            dist.all_gather_into_tensor(rec_all, rec_dev)
+        torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
