@@ -137,6 +137,8 @@ struct slide_pr_handle {
   int sm_count = 148;
   int tables_mode = SPR_TABLES_AUTO;
   bool force_exhaustive = false;  // env SLIDE_PR_EXHAUSTIVE=1
+  int refine_min = 32;            // candidate double groups from which the bounds are refined (env SLIDE_PR_REFINE_MIN; < 0: never)
+  bool refine_forced = false;     // env SLIDE_PR_REFINE_MIN given: refine whenever there are that many candidates
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // uploads that overlap the bound phase of a search
   cudaStream_t side_stream = nullptr;  // verification passes of the second bitmap direction
@@ -170,7 +172,7 @@ struct slide_pr_handle {
   spr::QuerySet Q;
   // device side
   DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_rank16, d_rank16b, d_rowrank, d_rowrankb, d_gcnt, d_cellref, d_cellrefb, d_cellbase, d_cellbaseb, d_reftab, d_refbase,
-      d_cand, d_cand1, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ubplanes, d_itemub, d_seed, d_canditems, d_candcount, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
+      d_cand, d_cand1, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ubplanes, d_itemub, d_seed, d_canditems, d_candcount, d_vbitmap, d_labof, d_dgitems, d_dgcount, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
   SprView V{};
   spr::uvec<int32_t> h_match;          // page-locked D2H targets
   spr::uvec<unsigned long long> h_scalars;
@@ -265,6 +267,7 @@ int slide_pr_create(const slide_pr_params *p, slide_pr_handle **out) {
   if (const char *v = std::getenv("SLIDE_PR_VARIANT")) h->tables_mode = std::atoi(v) == 0 ? SPR_TABLES_GLOBAL : SPR_TABLES_AUTO;
   // SLIDE_PR_EXHAUSTIVE=1 verifies every hypothesis exactly (no bound-and-verify pruning)
   if (const char *v = std::getenv("SLIDE_PR_EXHAUSTIVE")) h->force_exhaustive = std::atoi(v) != 0;
+  if (const char *v = std::getenv("SLIDE_PR_REFINE_MIN")) { h->refine_min = std::atoi(v); h->refine_forced = true; }
   *out = h;
   return SLIDE_PR_OK;
 }
@@ -276,7 +279,8 @@ void slide_pr_destroy(slide_pr_handle *h) {
                     &h->d_labelbox, &h->d_gbox, &h->d_bitmap, &h->d_rank16, &h->d_rank16b, &h->d_rowrank, &h->d_rowrankb, &h->d_gcnt, &h->d_cellref, &h->d_cellrefb,
                     &h->d_cellbase, &h->d_cellbaseb, &h->d_reftab, &h->d_refbase, &h->d_cand, &h->d_cand1, &h->d_qrot,
                     &h->d_qrotq, &h->d_qrotq_yx, &h->d_work, &h->d_ref7, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps, &h->d_tri, &h->d_tri_out,
-                    &h->d_ubplanes, &h->d_itemub, &h->d_seed, &h->d_canditems, &h->d_candcount})
+                    &h->d_ubplanes, &h->d_itemub, &h->d_seed, &h->d_canditems, &h->d_candcount,
+                    &h->d_vbitmap, &h->d_labof, &h->d_dgitems, &h->d_dgcount})
     b->release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -437,6 +441,7 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
     h->h2d_bytes += (int64_t)(h->R.bitmap.size() * sizeof(uint32_t));
     if ((rc = upload(h, h->d_reftab, h->R.reftab, st))) return rc;
     if ((rc = upload(h, h->d_refbase, h->R.ref_base, st))) return rc;
+    if ((rc = upload(h, h->d_labof, h->R.lab_of, st))) return rc;
     if ((rc = upload(h, h->d_ref7, h->cached_ref, st))) return rc;
     g_trace.mark("ref_bitmaps_upload");
   } else {
@@ -645,6 +650,64 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     }
     SPR_CUDA(h, spr_launch_seed(h->V, h->d_seed.as<unsigned long long>(), K.best_key, st));
     launches++;
+    // refinement: when many double groups stay candidates (no sharp peak, dense maps), their bounds
+    // are recomputed against half-cell variants of the bitmaps (built on the device on demand); all
+    // three kernels return at once when there are fewer than refine_min candidates
+    // Worth its cost (about one more bound phase over the candidates) only when the exact
+    // verification is expensive, i.e. when some pass has to read its tables in place (planes too
+    // large for shared memory, e.g. 20 000-landmark maps); SLIDE_PR_REFINE_MIN=0 forces it.
+    bool slow_verify = h->refine_forced;
+    for (uint32_t d = 0; d < 2 && !slow_verify; d++)
+      for (size_t i = 0; i < active.size() && !slow_verify; i++) {
+        SprLaunch T = K;
+        T.dir = d; T.label = active[i];
+        T.tab_cells = h->R.cell_base[d][T.label + 1] - h->R.cell_base[d][T.label];
+        T.tab_refs = h->R.ref_base[T.label + 1] - h->R.ref_base[T.label];
+        T.tab_cell_base = h->R.cell_base[d][T.label];
+        T.tab_ref_base = h->R.ref_base[T.label];
+        slow_verify = spr_score_smem_warps(h->V, T, h->tables_mode) == 0;
+      }
+    if (h->refine_min >= 0 && h->R.mark_rc2 > 0 && slow_verify) {
+      size_t dcap[2];
+      for (int d = 0; d < 2; d++) dcap[d] = (size_t)((h->L.dir_end[d] - h->L.dir_begin[d]) / (2 * SPR_WARP_CHUNKS)) * (size_t)n_yaw;
+      const size_t vwords = 4 * (size_t)h->V.grid.label_stride * (size_t)std::max(h->V.n_labels, 1) + 16;
+      SPR_CUDA(h, h->d_dgitems.ensure((dcap[0] + dcap[1]) * sizeof(uint32_t) + 64));
+      SPR_CUDA(h, h->d_dgcount.ensure(2 * sizeof(uint32_t)));
+      SPR_CUDA(h, h->d_vbitmap.ensure(vwords * sizeof(uint32_t)));
+      SPR_CUDA(h, cudaMemsetAsync(h->d_dgcount.p, 0, 2 * sizeof(uint32_t), st));
+      h->V.vbitmap = h->d_vbitmap.as<uint32_t>() + 4;
+      for (uint32_t d = 0; d < 2; d++) {
+        if (h->L.dir_end[d] <= h->L.dir_begin[d]) continue;
+        B.chunk_begin = h->L.dir_begin[d]; B.chunk_end = h->L.dir_end[d]; B.dir = d;
+        SPR_CUDA(h, spr_launch_select_dgroups(h->V, B, K.best_key, h->d_dgitems.as<uint32_t>() + (d ? dcap[0] : 0),
+                                              h->d_dgcount.as<uint32_t>() + d, h->sm_count, st));
+        launches++;
+      }
+      SPR_CUDA(h, spr_launch_variant_planes(h->V, h->d_vbitmap.as<uint32_t>(), vwords, h->d_ref7.as<double>(), h->d_labof.as<int32_t>(),
+                                            h->n_ref, h->p.match_xy_step_size, h->R.mark_rc, h->R.mark_rc2,
+                                            h->d_dgcount.as<uint32_t>(), (uint32_t)h->refine_min, h->sm_count, st));
+      launches += 2;
+      for (uint32_t d = 0; d < 2; d++) {
+        if (h->L.dir_end[d] <= h->L.dir_begin[d]) continue;
+        for (size_t i = 0; i < active.size(); i += SPR_BOUND_MAX_LABELS) {
+          B.chunk_begin = h->L.dir_begin[d]; B.chunk_end = h->L.dir_end[d]; B.dir = d;
+          B.row_begin = B.row_end = 0;
+          B.n_labels = (int32_t)std::min<size_t>((size_t)SPR_BOUND_MAX_LABELS, active.size() - i);
+          for (int k = 0; k < B.n_labels; k++) B.labels[k] = active[i + (size_t)k];
+          B.first = i == 0;
+          B.last = i + SPR_BOUND_MAX_LABELS >= active.size();
+          B.cand_items = h->d_dgitems.as<uint32_t>() + (d ? dcap[0] : 0);
+          B.cand_count = h->d_dgcount.as<uint32_t>() + d;
+          B.refine_min = (uint32_t)h->refine_min;
+          if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
+          B.work_counter = K.work_counter;
+          SPR_CUDA(h, spr_launch_bound_lattice(h->V, B, n_planes, h->sm_count, st, &launches));
+          K.work_counter++;
+          passes_left--;
+        }
+      }
+      B.cand_items = nullptr; B.cand_count = nullptr;
+    }
     // candidate work items of each direction (largest bound >= seeded best)
     size_t cap[2];
     for (int d = 0; d < 2; d++) cap[d] = (size_t)((h->L.dir_end[d] - h->L.dir_begin[d]) / SPR_WARP_CHUNKS) * (size_t)n_yaw;

@@ -439,11 +439,13 @@ int build_ref_marks(const slide_pr_params &p, const double *ref7, int n_ref, Ref
   // produced in ascending landmark order, which is the order a cell's candidates must keep
   std::vector<RefIndex::Entry> &entries = R.entries;
   entries.clear();
+  R.mark_rc = R.mark_rc2 = 0.0;
   entries.reserve((size_t)n_ref * 12);
   if (matchable) {
     const double eps_cells = 3.0 / std::ldexp(1.0, F) + 1e-9 / c;  // fixed-point truncation + lattice drift
     const double rc = rad_m / c + eps_cells;
     const double rc2 = rc * rc * (1.0 + 1e-12);
+    R.mark_rc = rc; R.mark_rc2 = rc2;
     for (int i = 0; i < n_ref; i++) {
       const int l = lab_of[i];
       if (l < 0) continue;

@@ -80,6 +80,7 @@ struct RefIndex {
   std::vector<uint32_t> ref_base;    // [n_labels + 1] first row of each label in reftab
   std::vector<SprBox> labelbox;     // [n_labels] fixed-point bounds of the label's marked cells
   double Tstar = 0, Sstar = 0;
+  double mark_rc = 0, mark_rc2 = 0; // radius (cells) / squared radius of the marking predicate (0: nothing matches)
   int n_ref = 0;
   // carried from build_ref_bitmaps to build_ref_ranks
   struct Entry { uint32_t ref; int32_t nx, ny; };  // landmark `ref` marks cell (nx, ny); ascending landmark order

@@ -429,6 +429,20 @@ static cudaError_t spr_launch_cfg(const SprView &V, const SprLaunch &K, int n_wg
   return cudaGetLastError();
 }
 
+// warps per CTA of the shared-memory-resident variant for this pass; 0: the tables are read in place
+int spr_score_smem_warps(const SprView &V, const SprLaunch &K, int tables_mode) {
+  const bool cnt32 = V.nqp > 65535;
+  const size_t warp_bytes = (size_t)(cnt32 ? SPR_WARP_WORDS(true) : SPR_WARP_WORDS(false)) * 4;
+  const uint32_t tab = spr_tab_layout(V.grid.plane_words[K.dir], (uint32_t)V.grid.R[K.dir], K.tab_cell_base, K.tab_cells,
+                                      K.tab_ref_base, K.tab_refs).total_w * 4u;
+  int smem_warps = 0;
+  if (tables_mode == SPR_TABLES_AUTO && K.label >= 0 && K.tab_refs < SPR_CELL_MULTI && (size_t)tab + 8 * warp_bytes <= SPR_SMEM_LIMIT) {
+    smem_warps = (int)((SPR_SMEM_LIMIT - tab) / warp_bytes);
+    if (smem_warps > 24) smem_warps = 24;
+  }
+  return smem_warps >= 8 ? smem_warps : 0;
+}
+
 cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int tables_mode, int sm_count,
                                      cudaStream_t st, int *n_launches) {
   if (K.chunk_end <= K.chunk_begin || V.n_yaw <= 0) return cudaSuccess;
@@ -449,11 +463,7 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int t
   // shared-memory-resident plane: one CTA per SM with as many warps as fit next to the tables
   const uint32_t tab = spr_tab_layout(V.grid.plane_words[K.dir], (uint32_t)V.grid.R[K.dir], K.tab_cell_base, K.tab_cells,
                                       K.tab_ref_base, K.tab_refs).total_w * 4u;
-  int smem_warps = 0;
-  if (tables_mode == SPR_TABLES_AUTO && K.label >= 0 && K.tab_refs < SPR_CELL_MULTI && (size_t)tab + 8 * warp_bytes <= SPR_SMEM_LIMIT) {
-    smem_warps = (int)((SPR_SMEM_LIMIT - tab) / warp_bytes);
-    if (smem_warps > 24) smem_warps = 24;
-  }
+  const int smem_warps = spr_score_smem_warps(V, K, tables_mode);
   if (smem_warps >= 8) {
     const long long want = (n_items + smem_warps - 1) / smem_warps;
     const int grid = (int)(want < sm_count ? want : sm_count);

@@ -61,6 +61,11 @@ struct SprBoundLaunch {
   uint32_t *item_ub;                // device: [yaw][chunk / 32]
   unsigned long long *seed_key;     // device: [n_yaw][SPR_SEED_SLOTS] (bound + 1) << 40 | chunk * 32 + bit of the best-bounded hypothesis
   unsigned long long *work_counter; // device: next work item (zeroed by the caller)
+  // refinement launches only: candidate double groups (local item numbers) from spr_launch_select_dgroups;
+  // the kernel does nothing when there are fewer than refine_min of them
+  const uint32_t *cand_items;
+  const uint32_t *cand_count;
+  uint32_t refine_min, pad;
 };
 
 enum { SPR_TABLES_GLOBAL = 0, SPR_TABLES_AUTO = 1 };  // AUTO: shared-memory-resident plane when it fits
@@ -71,6 +76,7 @@ cudaError_t spr_launch_rotate(const SprView &V, int32_t *qrotq_xy, int32_t *qrot
                               cudaStream_t st);
 
 // one (label, direction) pass of the lattice search
+int spr_score_smem_warps(const SprView &V, const SprLaunch &K, int tables_mode);  // 0: this pass reads its tables in place
 cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int tables_mode, int sm_count,
                                      cudaStream_t st, int *n_launches);
 
@@ -82,6 +88,14 @@ cudaError_t spr_launch_bound_lattice(const SprView &V, const SprBoundLaunch &B, 
 // work items of direction `B.dir` whose largest bound reaches the running best -> items[0 .. *count)
 cudaError_t spr_launch_select_items(const SprView &V, const SprBoundLaunch &B, const unsigned long long *best_key,
                                     uint32_t *items, uint32_t *count, int sm_count, cudaStream_t st);
+// double groups of direction `B.dir` with a group whose largest bound reaches the running best
+cudaError_t spr_launch_select_dgroups(const SprView &V, const SprBoundLaunch &B, const unsigned long long *best_key,
+                                      uint32_t *items, uint32_t *count, int sm_count, cudaStream_t st);
+// half-cell variants of the occupancy bitmaps (V.vbitmap, `words` 32-bit words incl. 4 in front), built on the
+// device from the raw reference rows; both kernels return at once unless counts[0] or counts[1] >= min_count
+cudaError_t spr_launch_variant_planes(const SprView &V, uint32_t *vbuf, size_t words, const double *ref7, const int32_t *lab_of,
+                                      int n_ref, double cell, double rc, double rc2, const uint32_t *counts, uint32_t min_count,
+                                      int sm_count, cudaStream_t st);
 // exact score of the best-bounded hypothesis of every yaw -> atomicMax on best_key
 cudaError_t spr_launch_seed(const SprView &V, const unsigned long long *seed_key, unsigned long long *best_key,
                             cudaStream_t st);

@@ -70,7 +70,10 @@ __device__ __forceinline__ void spb_ripple(uint32_t (&P)[PLANES], uint32_t c, in
 // row) and chunk k of the next group, which continues it for another 32 samples (empty where the
 // row ends).  One probe = three consecutive bitmap words of the row and two funnel shifts = the
 // filter bits of 64 hypotheses.
-template <int PLANES, bool SMEM_TAB>
+// REFINE: second, tighter bound of the candidate double groups only (B.cand_items): the probe
+// picks one of four bitmap variants by the half-cell the point falls in (spr_variant_mark_kernel),
+// planes read in place; the counters start from zero and replace the first bound.
+template <int PLANES, bool SMEM_TAB, bool REFINE>
 __global__ void __launch_bounds__(SMEM_TAB ? SPB_THREADS : 256, SMEM_TAB ? 1 : 3)
 spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constant__ SprBoundLaunch B, const int n_dg_local,
                          const long long n_items) {
@@ -81,6 +84,7 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
   const uint32_t d = B.dir;
   const uint32_t W = (uint32_t)G.W[d], maxbit2 = (uint32_t)G.maxbit[d] + 32u;
   const uint32_t W4 = W * 4u;
+  const uint32_t PW4 = G.plane_words[d] * 4u;
   // Row band [row_begin, row_end) of the planes handled by this launch (the whole plane unless it
   // does not fit in shared memory).  Staged as band_rows rows + one all-zero row per label; rows
   // outside the band clamp onto the zero row (unsigned min), so the probe code is unchanged.
@@ -125,7 +129,13 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
     long long item = 0;
     if (lane == 0) item = (long long)atomicAdd(B.work_counter, 1ull);
     item = __shfl_sync(SPR_FULL, item, 0);
-    if (item >= n_items) break;
+    if (REFINE) {
+      const uint32_t n_cand = __ldg(B.cand_count);
+      if (n_cand < B.refine_min || item >= (long long)n_cand) break;  // few candidates: not worth refining
+      item = (long long)__ldg(B.cand_items + item);
+    } else if (item >= n_items) {
+      break;
+    }
     const int a = (int)(item / n_dg_local);
     const int dg = B.shard_index + (int)(item % n_dg_local) * B.shard_count;
     const uint32_t cidx = B.chunk_begin + (uint32_t)dg * (2 * SPR_WARP_CHUNKS) + (uint32_t)lane;  // first chunk; + 32: its continuation
@@ -166,6 +176,7 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
         const int g0 = V.label_gseg[l], g1 = V.label_gseg[l + 1];
         if (g0 >= g1) continue;
         const uint32_t *bits = SMEM_TAB ? smem + 4 + (size_t)k * BW
+                               : REFINE ? V.vbitmap + (4 * ((size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u)))
                                         : V.bitmap + ((size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u));
         SprBox lb = V.labelbox[l];
         if (d == 0) { lb.x0 = max(lb.x0, band_lo); lb.x1 = min(lb.x1, band_hi); }  // marked cells inside the band
@@ -202,6 +213,10 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
                 // byte offset with two multiply-adds (FMA pipe) instead of LEA.HI + LEA (ALU pipe, the busy one)
                 uint32_t boff;
                 asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(boff) : "r"(bit >> 5), "r"(row * W4));
+                if (REFINE) {  // variant = 2 * (upper half of the cell across) + (upper half of the cell along)
+                  const uint32_t var = ((uint32_t)((aqb + qa_) >> (F - 1)) & 1u) * 2u + ((uint32_t)((bqb2 + qb_) >> (F - 1)) & 1u);
+                  boff += var * PW4;
+                }
                 const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(bits) + boff);
                 const uint32_t w0 = p[-1], w1 = p[0], w2 = p[1];
                 HA[u] = __funnelshift_r(w0, w1, bit);
@@ -264,7 +279,7 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
         const uint32_t who = __ballot_sync(SPR_FULL, packed == wmax && lv);
         const uint32_t grp = cidx / SPR_WARP_CHUNKS + (uint32_t)half;
         if (lane == 0) B.item_ub[(size_t)a * n_wg_total + grp] = wmax >> 5;
-        if (who && lane == __ffs(who) - 1)
+        if (!REFINE && who && lane == __ffs(who) - 1)
           atomicMax(B.seed_key + (size_t)a * SPR_SEED_SLOTS + grp % SPR_SEED_SLOTS,
                     ((unsigned long long)(val + 1u) << SPR_KEY_IDX_BITS) |
                         ((unsigned long long)(cidx + (uint32_t)half * SPR_WARP_CHUNKS) * 32ull + (unsigned long long)(packed & 31u)));
@@ -365,6 +380,107 @@ cudaError_t spr_launch_select_items(const SprView &V, const SprBoundLaunch &B, c
   return cudaGetLastError();
 }
 
+// Candidate double groups for the refinement: either of the two groups has a bound >= the running best.
+__global__ void __launch_bounds__(256)
+spr_select_dgroups_kernel(const SprBoundLaunch B, const int n_dg_local, const long long n_items,
+                          const unsigned long long *__restrict__ best_key, uint32_t *__restrict__ items, uint32_t *count) {
+  const long long bc = (long long)(*best_key >> SPR_KEY_IDX_BITS) - 1;
+  const uint32_t tau = bc > 0 ? (uint32_t)bc : 0u;
+  const uint32_t n_wg_total = B.n_chunks_total / SPR_WARP_CHUNKS;
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < n_items; i0 += stride) {
+    const long long i = i0 + lane;
+    bool take = false;
+    if (i < n_items) {
+      const int a = (int)(i / n_dg_local);
+      const int dg = B.shard_index + (int)(i % n_dg_local) * B.shard_count;
+      const uint32_t *ub = B.item_ub + (size_t)a * n_wg_total + B.chunk_begin / SPR_WARP_CHUNKS + 2u * (uint32_t)dg;
+      take = ub[0] >= tau || ub[1] >= tau;
+    }
+    const uint32_t m = __ballot_sync(SPR_FULL, take);
+    if (m) {
+      uint32_t base = 0u;
+      if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(m));
+      base = __shfl_sync(SPR_FULL, base, 0);
+      if (take) items[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+    }
+  }
+}
+
+cudaError_t spr_launch_select_dgroups(const SprView &V, const SprBoundLaunch &B, const unsigned long long *best_key,
+                                      uint32_t *items, uint32_t *count, int sm_count, cudaStream_t st) {
+  if (B.chunk_end <= B.chunk_begin || V.n_yaw <= 0) return cudaSuccess;
+  const int n_wg = (int)((B.chunk_end - B.chunk_begin) / SPR_WARP_CHUNKS);
+  const int sc = B.shard_count > 1 ? B.shard_count : 1;
+  const int si = B.shard_count > 1 ? B.shard_index : 0;
+  const int n_dg_local = spr_shard_local_groups(n_wg, si, sc) / 2;
+  if (n_dg_local <= 0) return cudaSuccess;
+  SprBoundLaunch B2 = B;
+  B2.shard_index = si;
+  B2.shard_count = sc;
+  const long long n_items = (long long)n_dg_local * V.n_yaw;
+  const long long want = (n_items + 255) / 256;
+  spr_select_dgroups_kernel<<<(int)(want < sm_count * 4 ? want : sm_count * 4), 256, 0, st>>>(B2, n_dg_local, n_items, best_key, items, count);
+  return cudaGetLastError();
+}
+
+// Half-cell variants of the occupancy bitmaps, built on the device.  Variant (sa, sb) of a cell is
+// marked when a landmark's match disc touches the (slightly dilated) half-cell box
+// [n + s/2, n + (s+1)/2] on both axes -- the same predicate as spr::build_ref_marks on a quarter
+// of the cell, so a probe that knows the half-cell its point falls in gets a tighter bound.
+__global__ void __launch_bounds__(256)
+spr_variant_clear_kernel(uint4 *__restrict__ buf, size_t n16, const uint32_t *__restrict__ counts, uint32_t min_count) {
+  if (counts[0] < min_count && counts[1] < min_count) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+    buf[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+__global__ void __launch_bounds__(128)
+spr_variant_mark_kernel(const __grid_constant__ SprView V, uint32_t *__restrict__ vb, const double *__restrict__ ref7,
+                        const int32_t *__restrict__ lab_of, int n_ref, double cell, double rc, double rc2,
+                        const uint32_t *__restrict__ counts, uint32_t min_count) {
+  if (counts[0] < min_count && counts[1] < min_count) return;
+  const SprGrid &G = V.grid;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ref; i += gridDim.x * blockDim.x) {
+    const int l = lab_of[i];
+    if (l < 0) continue;
+    const double ux = (ref7[7 * (size_t)i + 1] - G.g0x) / cell, uy = (ref7[7 * (size_t)i + 2] - G.g0y) / cell;
+    const int x0 = (int)floor(ux - rc), x1 = (int)floor(ux + rc), y0 = (int)floor(uy - rc), y1 = (int)floor(uy + rc);
+    uint32_t *pl0 = vb + 4 * ((size_t)l * G.label_stride);
+    uint32_t *pl1 = pl0 + 4 * (size_t)G.plane_words[0];
+    for (int nx = x0; nx <= x1; nx++)
+      for (int ny = y0; ny <= y1; ny++) {
+        if (nx < 0 || nx >= G.GX || ny < 0 || ny >= G.GY) continue;  // cannot happen (grid margins), kept as a guard
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          const int sx = v >> 1, sy = v & 1;
+          const double bx0 = (double)nx + 0.5 * sx, by0 = (double)ny + 0.5 * sy;
+          const double dx = fmax(fmax(bx0 - ux, 0.0), ux - (bx0 + 0.5));
+          const double dy = fmax(fmax(by0 - uy, 0.0), uy - (by0 + 0.5));
+          if (dx * dx + dy * dy > rc2) continue;
+          // plane dir 0: across = x, along = y -> variant 2 * sx + sy; plane dir 1: across = y, along = x -> 2 * sy + sx
+          atomicOr(pl0 + (size_t)(2 * sx + sy) * G.plane_words[0] + (size_t)(nx + 1) * G.W[0] + ((uint32_t)(ny + 32) >> 5),
+                   1u << ((ny + 32) & 31));
+          atomicOr(pl1 + (size_t)(2 * sy + sx) * G.plane_words[1] + (size_t)(ny + 1) * G.W[1] + ((uint32_t)(nx + 32) >> 5),
+                   1u << ((nx + 32) & 31));
+        }
+      }
+  }
+}
+
+cudaError_t spr_launch_variant_planes(const SprView &V, uint32_t *vbuf, size_t words, const double *ref7, const int32_t *lab_of,
+                                      int n_ref, double cell, double rc, double rc2, const uint32_t *counts, uint32_t min_count,
+                                      int sm_count, cudaStream_t st) {
+  const size_t n16 = words / 4;
+  const long long want = (long long)((n16 + 255) / 256);
+  spr_variant_clear_kernel<<<(int)(want < sm_count * 8 ? (want > 0 ? want : 1) : sm_count * 8), 256, 0, st>>>(
+      reinterpret_cast<uint4 *>(vbuf), n16, counts, min_count);
+  if (n_ref > 0)
+    spr_variant_mark_kernel<<<(n_ref + 127) / 128, 128, 0, st>>>(V, vbuf + 4, ref7, lab_of, n_ref, cell, rc, rc2, counts, min_count);
+  return cudaGetLastError();
+}
+
 int spr_bound_planes(int nqp) { return nqp < 4096 ? 12 : 16; }
 
 // Splits the planes of direction `dir` for the bound launches: as many whole label planes per
@@ -407,14 +523,17 @@ static cudaError_t spb_launch(const SprView &V, const SprBoundLaunch &B, int n_d
                               cudaStream_t st) {
   const size_t BW4 = (((size_t)(B.row_end - B.row_begin + 1) * (size_t)V.grid.W[B.dir] + 3) & ~(size_t)3) * 4;
   const size_t smem = 16 + (size_t)B.n_labels * BW4 + 16 + 16;  // 4 zero words in front and behind + the mbarrier
-  if (B.row_end > B.row_begin && smem <= SPR_SMEM_LIMIT) {
-    cudaError_t e = cudaFuncSetAttribute(spr_bound_lattice_kernel<PLANES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (!B.cand_items && B.row_end > B.row_begin && smem <= SPR_SMEM_LIMIT) {
+    cudaError_t e = cudaFuncSetAttribute(spr_bound_lattice_kernel<PLANES, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long want = (n_items + SPB_THREADS / 32 - 1) / (SPB_THREADS / 32);
-    spr_bound_lattice_kernel<PLANES, true><<<(int)(want < sm_count ? want : sm_count), SPB_THREADS, smem, st>>>(V, B, n_dg_local, n_items);
+    spr_bound_lattice_kernel<PLANES, true, false><<<(int)(want < sm_count ? want : sm_count), SPB_THREADS, smem, st>>>(V, B, n_dg_local, n_items);
   } else {
     const long long want = (n_items + 7) / 8, cap = (long long)sm_count * 3;
-    spr_bound_lattice_kernel<PLANES, false><<<(int)(want < cap ? want : cap), 256, 0, st>>>(V, B, n_dg_local, n_items);
+    if (B.cand_items)
+      spr_bound_lattice_kernel<PLANES, false, true><<<(int)(want < cap ? want : cap), 256, 0, st>>>(V, B, n_dg_local, n_items);
+    else
+      spr_bound_lattice_kernel<PLANES, false, false><<<(int)(want < cap ? want : cap), 256, 0, st>>>(V, B, n_dg_local, n_items);
   }
   return cudaGetLastError();
 }

@@ -89,6 +89,7 @@ struct SprView {
   int32_t         n_ref;
   const SprBox   *labelbox;   // [n_labels] fixed-point bounds of the label's marked cells
   const uint32_t *bitmap;     // [n_labels][plane dir0 | plane dir1]
+  const uint32_t *vbitmap;    // [n_labels][4 half-cell variants of plane dir0 | 4 variants of plane dir1] (refined bounds; device only)
   const SprCand  *cand[2];    // per plane direction d: first candidate of each marked cell by rank, then chained extras
   const uint16_t *rank16[2];  // per plane direction d: [n_labels][plane_words[d]] marked cells of the row before each word
   const uint32_t *row_rank[2];// per plane direction d: [n_labels][R[d]] rank of each row's first marked cell (label-relative)

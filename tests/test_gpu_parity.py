@@ -131,9 +131,22 @@ def test_random_maps_every_hypothesis(seed, variant):
     pr.close()
 
 
+@pytest.fixture(params=["default", "always_refine", "never_refine"])
+def refine_mode(request):
+    """The bounds of the candidate double groups are refined against half-cell bitmap variants when
+    many of them remain (SLIDE_PR_REFINE_MIN, default 32): run with the default, always and never."""
+    val = {"default": None, "always_refine": "0", "never_refine": "-1"}[request.param]
+    if val is None:
+        os.environ.pop("SLIDE_PR_REFINE_MIN", None)
+    else:
+        os.environ["SLIDE_PR_REFINE_MIN"] = val
+    yield request.param
+    os.environ.pop("SLIDE_PR_REFINE_MIN", None)
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("seed", range(6))
-def test_upper_bounds_dominate_exact_counts(seed, variant):
+def test_upper_bounds_dominate_exact_counts(seed, variant, refine_mode):
     """Bound phase of the bound-and-verify search: the bound of EVERY hypothesis is >= its exact
     inlier count (and <= the number of query landmarks), so pruning can never drop the winner."""
     rng = np.random.default_rng(700 + seed)
@@ -155,7 +168,10 @@ def test_upper_bounds_dominate_exact_counts(seed, variant):
     # a slice of the lattice (re-chunked) gives the same bounds
     lo, hi = nt // 3, nt // 3 + max(nt // 5, 1)
     _, part = pr.search(lo, hi, want_counts=True, bounds_only=True)
-    assert np.array_equal(part, bound[lo * ny:hi * ny])
+    if refine_mode == "never_refine":
+        assert np.array_equal(part, bound[lo * ny:hi * ny])
+    else:  # which groups get the refined (tighter) bound depends on the running best of the searched slice
+        assert (part >= exact[lo * ny:hi * ny]).all() and (part <= n_qry).all()
     res_p, _ = pr.search()            # default: bound-and-verify
     res_x, _ = pr.search(exhaustive=True)
     assert res_p.search_mode == 1 and res_x.search_mode == 0
@@ -165,7 +181,7 @@ def test_upper_bounds_dominate_exact_counts(seed, variant):
 
 
 @pytest.mark.parametrize("kind", ["overlap", "unrelated", "one_label", "tiny_query"])
-def test_bound_and_verify_equals_exhaustive(kind):
+def test_bound_and_verify_equals_exhaustive(kind, refine_mode):
     """Same winner (count, canonical index, correspondences) with and without pruning, with a
     strong peak, with no peak at all (unrelated maps: pruning barely helps) and sharded."""
     if kind == "overlap":
