@@ -50,7 +50,7 @@ double now_ms() {
 // remembers whether cudaHostAlloc succeeded, otherwise the block comes from malloc.
 void *pinned_alloc(size_t n) {
   void *p = nullptr;
-  if (cudaHostAlloc(&p, n + 64, cudaHostAllocDefault) == cudaSuccess && p) {
+  if (cudaHostAlloc(&p, n + 64, cudaHostAllocPortable) == cudaSuccess && p) {
     *static_cast<uint64_t *>(p) = 1;
   } else {
     cudaGetLastError();
