@@ -216,6 +216,8 @@ def run_ours(args, rank, world, local_rank):
     rec_host = torch.zeros(2 * n_rec, dtype=torch.int64).pin_memory()
     rec_dev = torch.zeros(2 * n_rec, dtype=torch.int64, device=dev)
     rec_all = torch.zeros(2 * n_rec * max(world, 1), dtype=torch.int64, device=dev)
+    inc_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+    inc_dev = torch.zeros(1, dtype=torch.int64, device=dev)
 
     def gather_and_merge(res):
         """shard mode: all-gather of the top-1 records + deterministic merge"""
@@ -231,7 +233,16 @@ def run_ours(args, rank, world, local_rank):
 
     def one_step():
         if shard_mode:
-            res, _ = pr.search(shard_index=rank, shard_count=world, stream=stream.cuda_stream)
+            # two-phase sharded search: bound phase, all-reduce(max) of the seeds' inlier counts (the
+            # incumbent of the branch-and-bound), verification against the shared incumbent
+            seed, _ = pr.search(shard_index=rank, shard_count=world, stream=stream.cuda_stream, bounds_only=True)
+            inc_host[0] = max(int(seed.best_num_inliers), 0)
+            inc_dev.copy_(inc_host, non_blocking=True)
+            dist.all_reduce(inc_dev, op=dist.ReduceOp.MAX)
+            res, _ = pr.search(shard_index=rank, shard_count=world, stream=stream.cuda_stream,
+                               incumbent_inliers=int(inc_dev.item()), reuse_bounds=True)
+            res.gpu_launches += seed.gpu_launches
+            res.kernel_ms += seed.kernel_ms
         else:
             res, _ = pr.search(stream=stream.cuda_stream)
         gather_and_merge(res)
@@ -342,7 +353,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": wname, "landmarks": [int(len(ref)), int(len(qry))],
                        "hypotheses_per_pair": int(info.match.hypotheses_scored),
                        "lattice": "0.5 m / 5 deg, dilation 1.2 (sloam-forest-parking-lot.yaml)",
-                       "parallelism": ("hypothesis space of one pair sharded over %d GPUs, NCCL all-gather of top-1" % world) if shard_mode
+                       "parallelism": ("hypothesis space of one pair sharded over %d GPUs: bound phase, NCCL all-reduce(max) of the incumbent, verification, NCCL all-gather of top-1" % world) if shard_mode
                        else ("one map pair per GPU and step (the same synthetic pair on every rank), ranks independent, one NCCL all-gather of all result records at the end of the timed region" if world > 1 else "single GPU"),
                        "l2": "flushed between timed steps (256 MiB write)", "decision_arithmetic": "fp64, non-fused (bit-exact vs reference)",
                        "search": "bound-and-verify (library default): bitmap-filter upper bound of every hypothesis, exact fp64 verification of "

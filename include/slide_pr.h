@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SLIDE_PR_ABI_VERSION 1
+#define SLIDE_PR_ABI_VERSION 2
 
 enum {
   SLIDE_PR_OK = 0,
@@ -105,7 +105,13 @@ typedef struct slide_pr_search_opts {
                             bound (bitmap filter hits) for every hypothesis, exact verification only where the
                             bound reaches the running best; the winner, its count and its correspondences are
                             the same.  counts_out / collect_stats / compute_budget_sec > 0 imply exhaustive.
-                            2 (test hook): bound phase only, counts_out receives the upper bounds. */
+                            2: bound phase only (first half of a sharded search, and a test hook): the result holds
+                            the best exactly scored seed hypothesis; counts_out, if given, receives the upper bounds. */
+  int32_t incumbent_inliers; /* > 0: an inlier count already reached elsewhere (another shard of the same pair, after an
+                            all-reduce(max) of the shards' bound-phase results): hypotheses whose bound is below it are
+                            not verified.  A shard that finds nothing >= the incumbent reports best_hyp_index = -1. */
+  int32_t reuse_bounds;  /* 1: the bounds of the preceding exhaustive = 2 call on the same prepared problem and shard are
+                            still on the device: skip the bound phase and go straight to the verification */
 } slide_pr_search_opts;
 
 typedef struct slide_pr_tf_result {

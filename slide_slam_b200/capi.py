@@ -92,6 +92,8 @@ class SearchOpts(C.Structure):
         ("stream", C.c_void_p),
         ("collect_stats", C.c_int32),
         ("exhaustive", C.c_int32),
+        ("incumbent_inliers", C.c_int32),
+        ("reuse_bounds", C.c_int32),
     ]
 
 

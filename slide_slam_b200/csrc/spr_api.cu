@@ -145,6 +145,8 @@ struct slide_pr_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr, ev_prep = nullptr;  // ev_prep: prepare's uploads enqueued
   Worker worker_lattice, worker_query;  // helper threads of slide_pr_prepare
+  bool bounds_valid = false;           // the bound planes of the last exhaustive = 2 search are still valid ...
+  int bounds_shard_index = 0, bounds_shard_count = 0;  // ... for this shard of the prepared problem
   bool ranks_pending = false;          // stage 2 of the reference index (rank tables) not built / uploaded yet
   const double *pending_ref7 = nullptr; // == cached_ref.data() while ranks_pending
   std::string err;
@@ -353,6 +355,7 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
                      double half_x, double half_y) {
   if (!h) return SLIDE_PR_ERR_INVALID;
   h->prepared = false;
+  h->bounds_valid = false;
   if (n_ref < 0 || n_qry < 0 || (n_ref > 0 && !ref7) || (n_qry > 0 && !qry7)) { h->err = "bad map arguments"; return SLIDE_PR_ERR_INVALID; }
   if (n_qry >= (1 << 22)) { h->err = "more than 2^22 query landmarks"; return SLIDE_PR_ERR_UNSUPPORTED; }
   const double t0 = now_ms();
@@ -555,6 +558,14 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     SPR_CUDA(h, cudaMemsetAsync(h->d_counts.p, 0xff, std::max<size_t>((size_t)n_counts, 1) * sizeof(int32_t), st));
   }
   SPR_CUDA(h, cudaMemsetAsync(h->d_best.p, 0, sizeof(unsigned long long), st));
+  // an inlier count reached elsewhere (another shard): a synthetic best with that count and an
+  // impossible index, so that an equal count found here still wins and anything below is pruned
+  const unsigned long long incumbent_key = o.incumbent_inliers > 0 ? ((unsigned long long)(o.incumbent_inliers + 1) << SPR_KEY_IDX_BITS) : 0ull;
+  if (incumbent_key) {
+    if (h->h_scalars.size() < 8) h->h_scalars.assign(8, 0ull);
+    h->h_scalars[7] = incumbent_key;
+    SPR_CUDA(h, cudaMemcpyAsync(h->d_best.p, h->h_scalars.data() + 7, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+  }
   if (o.collect_stats) SPR_CUDA(h, cudaMemsetAsync(h->d_stats.p, 0, 4 * sizeof(unsigned long long), st));
 
   SprLaunch K{};
@@ -617,7 +628,11 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     B.planes = h->d_ubplanes.as<uint32_t>();
     B.item_ub = h->d_itemub.as<uint32_t>();
     B.seed_key = h->d_seed.as<unsigned long long>();
-    for (uint32_t d = 0; d < 2; d++) {
+    // second half of a two-phase (sharded) search: the bounds of the preceding bound-only call are reused
+    const bool reuse = o.reuse_bounds && !bounds_only && h->bounds_valid && tb == 0 && te < 0 &&
+                       h->bounds_shard_index == o.shard_index && h->bounds_shard_count == o.shard_count;
+    h->bounds_valid = false;
+    for (uint32_t d = 0; d < 2 && !reuse; d++) {
       if (h->L.dir_end[d] <= h->L.dir_begin[d]) continue;
       int per = 1;
       uint32_t band_rows = 0;
@@ -648,8 +663,14 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
       SPR_CUDA(h, cudaEventRecord(h->ev_copy, h->copy_stream));
       SPR_CUDA(h, cudaStreamWaitEvent(st, h->ev_copy, 0));
     }
-    SPR_CUDA(h, spr_launch_seed(h->V, h->d_seed.as<unsigned long long>(), K.best_key, st));
-    launches++;
+    if (!reuse) {
+      SPR_CUDA(h, spr_launch_seed(h->V, h->d_seed.as<unsigned long long>(), K.best_key, st));
+      launches++;
+    }
+    if (bounds_only && tb == 0 && te < 0) {
+      h->bounds_valid = true;
+      h->bounds_shard_index = o.shard_index; h->bounds_shard_count = o.shard_count;
+    }
     // refinement: when many double groups stay candidates (no sharp peak, dense maps), their bounds
     // are recomputed against half-cell variants of the bitmaps (built on the device on demand); all
     // three kernels return at once when there are fewer than refine_min candidates
@@ -841,7 +862,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     }
     out->hypotheses_scored = (int64_t)(bits * (uint64_t)n_yaw);
   }
-  if (key != 0ull) {
+  if (key != 0ull && key != incumbent_key) {  // the synthetic incumbent itself: nothing at least as good here
     out->best_num_inliers = spr_key_count(key);
     out->best_hyp_index = spr_key_index(key);
   }

@@ -56,12 +56,29 @@ def allgather_winner(local_hyp_index: int, local_inliers: int, device=None, grou
     return ShardWinner(recs[w][1], recs[w][0], w)
 
 
+def sharded_search(pr, rank: int, world: int, device=None, group=None):
+    """One shard of a prepared search, in two phases: the bound phase of every shard (with its
+    exactly scored seed hypotheses), an all-reduce(max) of the seeds' inlier counts -- the one
+    exchange branch-and-bound needs: the incumbent -- and the verification of the shard's
+    hypotheses whose bound reaches that incumbent.  Shards that cannot hold the winner verify
+    (almost) nothing.  A shard without anything >= the incumbent reports best_hyp_index = -1."""
+    if world <= 1:
+        return pr.search()[0]
+    seed, _ = pr.search(shard_index=rank, shard_count=world, bounds_only=True)
+    inc = torch.tensor([max(int(seed.best_num_inliers), 0)], dtype=torch.int64, device=device)
+    dist.all_reduce(inc, op=dist.ReduceOp.MAX, group=group)
+    res, _ = pr.search(shard_index=rank, shard_count=world, incumbent_inliers=int(inc.item()), reuse_bounds=True)
+    res.gpu_launches += seed.gpu_launches
+    res.kernel_ms += seed.kernel_ms
+    return res
+
+
 def sharded_match_maps(pr, reference_objects, query_objects, half_x: float, half_y: float, device=None, group=None):
     """MatchMaps (PR.cpp:98-387) with the hypothesis space sharded over the ranks of `group`.
     Every rank must call it with the same maps.  Returns (winner, ref_idx, qry_idx, R_t, local_result)."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     pr.prepare(reference_objects, query_objects, half_x, half_y)
-    res, _ = pr.search(shard_index=rank, shard_count=world)
+    res = sharded_search(pr, rank, world, device=device, group=group)
     win = allgather_winner(res.best_hyp_index, res.best_num_inliers, device=device, group=group)
     if win.hyp_index < 0:
         return win, np.zeros(0, np.int32), np.zeros(0, np.int32), np.eye(3), res

@@ -146,14 +146,17 @@ class PlaceRecognition:
 
     def search(self, trans_begin: int = 0, trans_end: int = -1, shard_index: int = 0, shard_count: int = 1,
                want_counts: bool = False, stream: int | None = None, collect_stats: bool = False,
-               exhaustive: bool = False, bounds_only: bool = False):
+               exhaustive: bool = False, bounds_only: bool = False, incumbent_inliers: int = 0,
+               reuse_bounds: bool = False):
         """exhaustive=False (default): bound-and-verify -- same winner, count and correspondences as
         verifying every hypothesis exactly (exhaustive=True; implied by want_counts / collect_stats)."""
         o = capi.SearchOpts()
         o.trans_begin, o.trans_end, o.shard_index, o.shard_count = trans_begin, trans_end, shard_index, shard_count
         o.stream = stream
         o.collect_stats = int(collect_stats)
-        o.exhaustive = 2 if bounds_only else int(exhaustive)  # 2: test hook, counts = upper bounds
+        o.exhaustive = 2 if bounds_only else int(exhaustive)  # 2: bound phase only (counts = upper bounds)
+        o.incumbent_inliers = int(incumbent_inliers)
+        o.reuse_bounds = int(reuse_bounds)
         counts = None
         res = capi.MatchResult()
         if want_counts:

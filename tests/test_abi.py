@@ -19,14 +19,14 @@ def test_library_exports_every_declared_symbol():
     lib = capi.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.slide_pr_abi_version() == 1
+    assert lib.slide_pr_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
     # sizes implied by include/slide_pr.h on LP64
     assert C.sizeof(capi.Params) == 10 * 8 + 8 * 4
     assert C.sizeof(capi.MatchResult) == 8 + 72 + 16 + 24 + 8 + 16 + 16 + 16 + 8
-    assert C.sizeof(capi.SearchOpts) == 16 + 8 + 8 + 8 + 8 + 8
+    assert C.sizeof(capi.SearchOpts) == 16 + 8 + 8 + 8 + 8 + 8 + 8
     assert C.sizeof(capi.TopkRecord) == 16
     assert C.sizeof(capi.TfResult) == 16 + 72 + 32 + 128 + 32 + 24 + C.sizeof(capi.MatchResult)
 

@@ -276,6 +276,46 @@ def test_bound_and_verify_with_many_query_landmarks():
     pr.close()
 
 
+def test_two_phase_sharded_search_with_shared_incumbent(gold):
+    """Sharded search as slide_slam_b200.parallel.sharded_search runs it: bound phase of every shard,
+    max of the seeds' inlier counts (the all-reduce), verification against that incumbent with the
+    bounds reused.  Shards without anything >= the incumbent report -1; the merge is the winner."""
+    maps, cases, _ = gold
+    for name in ("parking01_forest_yaml", "c1_forest_yaml"):
+        c = cases[name]
+        ref, qry = H.shifted_maps(maps, c)
+        lib = capi.lib()
+        for n_shards in (2, 3, 8):
+            prs = [make_pr(c["params"]) for _ in range(n_shards)]   # one handle per "rank"
+            seeds = []
+            for r, pr in enumerate(prs):
+                pr.prepare(ref, qry, c["half_x"], c["half_y"])
+                seeds.append(pr.search(shard_index=r, shard_count=n_shards, bounds_only=True)[0])
+            inc = max(max(int(s.best_num_inliers), 0) for s in seeds)
+            recs = (capi.TopkRecord * n_shards)()
+            total, n_none = 0, 0
+            for r, pr in enumerate(prs):
+                res, _ = pr.search(shard_index=r, shard_count=n_shards, incumbent_inliers=inc, reuse_bounds=True)
+                assert res.search_mode == 1
+                lib.slide_pr_pack_record(C.byref(res), r, C.byref(recs[r]))
+                total += res.hypotheses_scored
+                n_none += int(res.best_hyp_index < 0)
+                if res.best_hyp_index >= 0:
+                    assert res.best_num_inliers >= inc
+            w = lib.slide_pr_merge_records(recs, n_shards)
+            assert total == c["hypotheses_scored"]
+            assert recs[w].hyp_index == c["best_hyp_index"] and recs[w].inliers == c["best_num_inliers"]
+            assert n_none <= n_shards - 1
+            # an incumbent above the true best: nothing anywhere reaches it
+            res, _ = prs[0].search(incumbent_inliers=c["best_num_inliers"] + 1)
+            assert res.best_hyp_index == -1 and res.best_num_inliers == -10000
+            # an incumbent equal to the true best still finds the winner (ties go to the real index)
+            res, _ = prs[0].search(incumbent_inliers=c["best_num_inliers"])
+            assert (res.best_hyp_index, res.best_num_inliers) == (c["best_hyp_index"], c["best_num_inliers"])
+            for pr in prs:
+                pr.close()
+
+
 def test_edge_cases_through_the_abi():
     kw = dict(match_xy_step_size=0.5, yaw_step_deg=45.0)
     rng = np.random.default_rng(1)
