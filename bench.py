@@ -248,6 +248,11 @@ def run_ours(args, rank, world, local_rank):
         gather_and_merge(res)
         return res
 
+    # clocks / throttle reasons are sampled from the warm-up to the end of the end-to-end leg: the
+    # timed steps alone (milliseconds) are shorter than one nvidia-smi query
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         one_step()
     if world > 1 and not shard_mode:        # warm-up of the exchange too (NCCL sets its channels up lazily)
@@ -255,9 +260,6 @@ def run_ours(args, rank, world, local_rank):
             rec_dev.copy_(rec_host, non_blocking=True)
             dist.all_gather_into_tensor(rec_all, rec_dev)
         torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -298,8 +300,6 @@ def run_ours(args, rank, world, local_rank):
         kernel_total_ms = float(mx[2])
     else:
         hyps_all, launches_all, kernel_total_ms = float(hyps), int(launches), float(sum(kern_ms))
-    clocks = sampler.stop() if rank == 0 else None
-
     # the same search with EVERY hypothesis verified exactly (no bound-and-verify pruning), rank 0's GPU
     exh_ms = []
     if rank == 0:
@@ -332,6 +332,7 @@ def run_ours(args, rank, world, local_rank):
         reused |= info2.match.reuse
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
     e2e = torch.tensor([e2e_s, float(e2e_hyps)], dtype=torch.float64, device=dev)
     if world > 1:
         a = e2e.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
