@@ -71,6 +71,65 @@ def test_allgather_winner_is_deterministic_and_first_wins(world):
     assert expect[2] == (0, 33, 1) and expect[3] == (-10000, -1, -1)
 
 
+class _FakeResult:
+    def __init__(self, inliers, index, launches=1, ms=1.0):
+        self.best_num_inliers, self.best_hyp_index, self.gpu_launches, self.kernel_ms = inliers, index, launches, ms
+
+
+class _FakeShardedSearch:
+    """Stands in for PlaceRecognition.search: every rank owns some (inliers, index) hypotheses; the
+    bound phase reports the rank's seed, the verification everything >= the incumbent."""
+    def __init__(self, hyps, seed):
+        self.hyps, self.seed, self.calls = hyps, seed, []
+
+    def search(self, shard_index=0, shard_count=1, bounds_only=False, incumbent_inliers=0, reuse_bounds=False, **kw):
+        self.calls.append((shard_index, shard_count, bounds_only, incumbent_inliers, reuse_bounds))
+        if bounds_only:
+            return _FakeResult(*self.seed), None
+        ok = [h for h in self.hyps if h[0] >= incumbent_inliers]
+        if not ok:
+            return _FakeResult(-10000, -1), None
+        best = max(ok, key=lambda h: (h[0], -h[1]))
+        return _FakeResult(*best), None
+
+
+def _sharded_worker(rank, world, port, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # rank 0: weak hypotheses and a weak seed; rank 1: the winner, but its seed missed it
+        hyps = [[(12, 40), (9, 3)], [(30, 77), (30, 90), (11, 5)]][rank]
+        seed = [(9, 3), (11, 5)][rank]
+        pr = _FakeShardedSearch(hyps, seed)
+        res = parallel.sharded_search(pr, rank, world)
+        win = parallel.allgather_winner(res.best_hyp_index, res.best_num_inliers)
+        out_q.put((rank, pr.calls, (res.best_num_inliers, res.best_hyp_index, res.gpu_launches), (win.inliers, win.hyp_index, win.rank)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_phase_sharded_search_shares_the_incumbent():
+    """bound phase -> all-reduce(max) of the seeds' inlier counts -> verification with that incumbent
+    and reuse_bounds; the shard without anything >= the incumbent reports 'none'."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, calls, local, win in results:
+        assert calls == [(rank, world, True, 0, False), (rank, world, False, 11, True)]  # incumbent = max(9, 11)
+        assert win == (30, 77, 1)                     # ties to the smallest canonical index
+    assert results[0][2] == (12, 40, 2)               # rank 0 still reports its own best (>= incumbent)
+    assert results[1][2] == (30, 77, 2)
+
+
 def test_merge_matches_the_c_abi():
     rng = np.random.default_rng(0)
     for _ in range(200):
