@@ -48,6 +48,7 @@ struct RectEmitter {
   uint32_t x_off, y_off;
   const double *xs, *ys;
   int64_t tb, te;  // ordinal filter, te < 0: none
+  size_t &n_out;   // chunks emitted so far (L.chunks / succ are sized to capacity while emitting)
 
   std::vector<int32_t> *succ = nullptr;  // optional: index of the chunk that continues chunk i along its row, or -1
   std::vector<int32_t> prev;             // scratch: chunks of the previous block of the current rectangle
@@ -71,9 +72,14 @@ struct RectEmitter {
     c.ord_stride = (uint32_t)stride;
     c.dir = dir;
     c.ring = (uint32_t)ring;
-    L.chunks.push_back(c);
-    if (succ) succ->push_back(-1);
-    return (int)L.chunks.size() - 1;
+    if (n_out == L.chunks.size()) {  // grow geometrically; the vectors keep their size across calls
+      const size_t cap = std::max<size_t>(2 * n_out, 4096);
+      L.chunks.resize(cap);
+      if (succ) succ->resize(cap);
+    }
+    L.chunks[n_out] = c;
+    if (succ) (*succ)[n_out] = -1;
+    return (int)n_out++;
   }
 
   // rectangle ix in [ix0, ix1), iy in [iy0, iy1); ordinal(ix, iy) = ord0 + (ix-ix0)*row_stride + (iy-iy0)
@@ -113,7 +119,14 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
                   int64_t trans_begin, int64_t trans_end, bool ring_major, Lattice &L, std::string &err) {
   // reset, keeping the vectors' capacity across calls
   L.status = 0; L.rings = 0; L.ox = L.oy = 0; L.n_translations = 0; L.ring_major = false;
-  L.yaw.clear(); L.cs.clear(); L.lat.clear(); L.ring.clear(); L.chunks.clear();
+  L.yaw.clear(); L.cs.clear(); L.lat.clear(); L.ring.clear();
+  // L.chunks keeps its size while chunks are emitted (n_emitted tracks the fill level); every exit
+  // before the emission is complete leaves it empty
+  size_t n_emitted = 0;
+  struct ChunkGuard {
+    Lattice &L; bool done = false;
+    ~ChunkGuard() { if (!done) L.chunks.clear(); }
+  } chunk_guard{L};
   L.dir_begin[0] = L.dir_begin[1] = L.dir_end[0] = L.dir_end[1] = 0;
   const double step = p.match_xy_step_size;
   if (!(step > 0) || !std::isfinite(step)) { err = "match_xy_step_size must be positive and finite"; return SLIDE_PR_ERR_INVALID; }
@@ -148,7 +161,7 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
 
   uint64_t ord = 0;
   std::vector<int32_t> &succ = L.succ;  // along-successor of every emitted chunk (pairing for the bound kernel)
-  succ.clear();
+  if (succ.size() < L.chunks.size()) succ.resize(L.chunks.size());
   for (int k = 0; k < rings; k++) {
     const double kd = static_cast<double>(k);
     const double x_right_prev = kd * L.ox, x_left_prev = -kd * L.ox;        // PR.cpp:204,210
@@ -156,18 +169,29 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
     const double y_right_prev = kd * L.oy, y_left_prev = -kd * L.oy;
     const double y_pos_end = (kd + 1) * L.oy, y_neg_start = -(kd + 1) * L.oy;
     Lattice::Ring R;
-    R.x_off = (uint32_t)L.lat.size();
+    // the samples come from repeated fp64 addition, exactly as the reference's loops; the arrays are
+    // sized from the (generous) expected count first so that the loops write through a pointer
+    const double est_x = (x_pos_end - x_neg_start) / step + 4.0, est_y = (y_pos_end - y_neg_start) / step + 4.0;
+    if (!(est_x < 4194304.0) || !(est_y < 4194304.0)) { err = "more than 2^22 lattice samples per axis"; return SLIDE_PR_ERR_UNSUPPORTED; }
+    const size_t lat0 = L.lat.size();
+    L.lat.resize(lat0 + (size_t)est_x + (size_t)est_y);
+    double *lp = L.lat.data() + lat0;
+    R.x_off = (uint32_t)lat0;
+    uint32_t n = 0;
     for (double x = x_neg_start; x <= x_pos_end; x += step) {                // PR.cpp:230
-      L.lat.push_back(x);
-      if (L.lat.size() - R.x_off > (1u << 22)) { err = "more than 2^22 lattice samples per axis"; return SLIDE_PR_ERR_UNSUPPORTED; }
+      if (n >= (uint32_t)est_x) { err = "internal: lattice sample estimate too small"; return SLIDE_PR_ERR_INTERNAL; }
+      lp[n++] = x;
     }
-    R.nx = (uint32_t)L.lat.size() - R.x_off;
-    R.y_off = (uint32_t)L.lat.size();
+    R.nx = n;
+    R.y_off = R.x_off + n;
+    lp += n;
+    n = 0;
     for (double y = y_neg_start; y <= y_pos_end; y += step) {                // PR.cpp:232
-      L.lat.push_back(y);
-      if (L.lat.size() - R.y_off > (1u << 22)) { err = "more than 2^22 lattice samples per axis"; return SLIDE_PR_ERR_UNSUPPORTED; }
+      if (n >= (uint32_t)est_y) { err = "internal: lattice sample estimate too small"; return SLIDE_PR_ERR_INTERNAL; }
+      lp[n++] = y;
     }
-    R.ny = (uint32_t)L.lat.size() - R.y_off;
+    R.ny = n;
+    L.lat.resize((size_t)R.y_off + n);
     // lat may have been reallocated: take pointers now
     const double *xs = L.lat.data() + R.x_off, *ys = L.lat.data() + R.y_off;
     // already-searched centre box as closed index ranges, PR.cpp:238-239
@@ -187,8 +211,8 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
     const bool has_box = n_in_x > 0 && n_in_y > 0;
     R.ord_base = ord;
     R.count = (uint64_t)R.nx * R.ny - (has_box ? (uint64_t)n_in_x * n_in_y : 0);
-    R.chunk_begin = (uint32_t)L.chunks.size();
-    RectEmitter E{L, k, R.x_off, R.y_off, xs, ys, trans_begin, trans_end};
+    R.chunk_begin = (uint32_t)n_emitted;
+    RectEmitter E{L, k, R.x_off, R.y_off, xs, ys, trans_begin, trans_end, n_emitted};
     E.succ = ring_major ? nullptr : &succ;
     const int nx = (int)R.nx, ny = (int)R.ny;
     if (!has_box) {
@@ -202,11 +226,13 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
       E.rect(R.ixl, R.ixh + 1, R.iyh + 1, ny, base_b + (uint64_t)R.iyl, cnt_in);     // y above the box
       E.rect(R.ixh + 1, nx, 0, ny, base_c, (uint64_t)ny);                           // x above the box
     }
-    R.chunk_end = (uint32_t)L.chunks.size();
+    R.chunk_end = (uint32_t)n_emitted;
     ord += R.count;
     L.ring.push_back(R);
     if (ord >= (1ull << 32)) { err = "more than 2^32 lattice translations"; return SLIDE_PR_ERR_UNSUPPORTED; }
   }
+  L.chunks.resize(n_emitted);
+  chunk_guard.done = true;
   L.n_translations = ord;
   if (ord * (uint64_t)std::max<size_t>(L.yaw.size(), 1) >= (1ull << SPR_KEY_IDX_BITS)) {
     err = "more than 2^40 hypotheses"; return SLIDE_PR_ERR_UNSUPPORTED;
