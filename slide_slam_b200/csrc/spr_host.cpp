@@ -75,6 +75,7 @@ struct RectEmitter {
     if (n_out == L.chunks.size()) {  // grow geometrically; the vectors keep their size across calls
       const size_t cap = std::max<size_t>(2 * n_out, 4096);
       L.chunks.resize(cap);
+      L.scratch.reserve(cap + 128);  // the two buffers swap roles every call: grow them together
       if (succ) succ->resize(cap);
     }
     L.chunks[n_out] = c;
