@@ -1,23 +1,29 @@
 // spr_kernels.cu -- sm_100a kernels of the SlideMatch lattice search.
 //
-// Replaces the five nested loops of PlaceRecognition::MatchMaps (place_recognition.cpp:178-372).
+// Replaces the five nested loops of PlaceRecognition::MatchMaps (place_recognition.cpp:178-372):
+// the EXACT inlier count of hypotheses -- all of them in the exhaustive mode, the candidates that
+// survive the bound phase (spr_kernels_bound.cu) in the default bound-and-verify mode.
 // Work decomposition:
 //   * the search runs as one PASS per (label, bitmap direction): all CTAs work on the same
 //     occupancy plane at the same time, so the plane and its rank tables are staged once per CTA
-//     into SHARED MEMORY when they fit (otherwise they are read through L1/L2); per-hypothesis
-//     inlier counters are carried between the passes in HBM (2 bytes per hypothesis);
+//     into SHARED MEMORY with TMA bulk copies when they fit (lazily, by the first warp that has
+//     work; otherwise they are read through L1/L2); per-hypothesis inlier counters are carried
+//     between the passes in HBM (2 bytes per hypothesis);
 //   * one THREAD owns one chunk = 32 consecutive lattice translations along one axis, for one
-//     yaw candidate; a WARP owns 32 chunks (1024 hypotheses) and is the unit of scheduling: warps
-//     pull (yaw, 32-chunk) work items from a global counter, there is no barrier after staging;
+//     yaw candidate; a WARP owns a group of 32 chunks (1024 hypotheses) and is the unit of
+//     scheduling: warps pull (yaw, group) work items from a global counter -- or from the
+//     candidate list of the verification phase -- there is no barrier after staging;
+//   * in the verification phase a lane first rebuilds its candidate mask by comparing the bit planes
+//     of the bounds with the running best and drops the other hypotheses;
 //   * query landmarks come in groups of 8 (one label, Morton order) with a bounding box per yaw;
-//     a group that cannot reach the label's occupied cells from any of the warp's 1024
-//     translations is skipped with four integer compares;
+//     the visibility of 32 groups is tested at once (one group per lane, one ballot) against the
+//     1024 translations of the warp, only the visible groups are walked;
 //   * for every remaining query landmark the thread reads two words of the plane and obtains the
 //     32 hypotheses' filter bits with one funnel shift (spr_probe);
 //   * probes with set bits ("filter hits") are compacted through a per-warp shared-memory queue
-//     (warp prefix-sum over the record counts) and verified 32 records at a time in exact,
-//     non-fused fp64 against the cells' candidates (spr_verify_mask) -- the reference's own
-//     predicate, so every hypothesis gets its exact inlier count;
+//     (one record per (chunk, query), slots from ballots) and verified 32 records at a time in
+//     exact, non-fused fp64 against the cells' candidates (spr_verify_mask) -- the reference's own
+//     predicate, so every verified hypothesis gets its exact inlier count;
 //   * after the last pass the best (count, canonical index) key is reduced with shuffles and one
 //     64-bit atomicMax per warp.
 // This is integer/bit and fp64 ALU work on shared-memory / L2-resident data; there is no GEMM in
