@@ -710,21 +710,30 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
       launches += 2;
       for (uint32_t d = 0; d < 2; d++) {
         if (h->L.dir_end[d] <= h->L.dir_begin[d]) continue;
-        for (size_t i = 0; i < active.size(); i += SPR_BOUND_MAX_LABELS) {
-          B.chunk_begin = h->L.dir_begin[d]; B.chunk_end = h->L.dir_end[d]; B.dir = d;
-          B.row_begin = B.row_end = 0;
-          B.n_labels = (int32_t)std::min<size_t>((size_t)SPR_BOUND_MAX_LABELS, active.size() - i);
-          for (int k = 0; k < B.n_labels; k++) B.labels[k] = active[i + (size_t)k];
-          B.first = i == 0;
-          B.last = i + SPR_BOUND_MAX_LABELS >= active.size();
-          B.cand_items = h->d_dgitems.as<uint32_t>() + (d ? dcap[0] : 0);
-          B.cand_count = h->d_dgcount.as<uint32_t>() + d;
-          B.refine_min = (uint32_t)h->refine_min;
-          if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
-          B.work_counter = K.work_counter;
-          SPR_CUDA(h, spr_launch_bound_lattice(h->V, B, n_planes, h->sm_count, st, &launches));
-          K.work_counter++;
-          passes_left--;
+        // one label per launch with its four variant planes staged in row bands, or -- small query
+        // maps, planes too wide -- up to 8 labels per launch reading the variants in place
+        const uint32_t band_rows = spr_refine_band_rows(h->V, d);
+        const uint32_t R = (uint32_t)h->V.grid.R[d];
+        const uint32_t n_bands = band_rows ? (R + band_rows - 1) / band_rows : 1;
+        const size_t per = band_rows ? 1 : SPR_BOUND_MAX_LABELS;
+        for (size_t i = 0; i < active.size(); i += per) {
+          for (uint32_t band = 0; band < n_bands; band++) {
+            B.chunk_begin = h->L.dir_begin[d]; B.chunk_end = h->L.dir_end[d]; B.dir = d;
+            B.row_begin = band_rows ? band * band_rows : 0u;
+            B.row_end = band_rows ? std::min(R, (band + 1) * band_rows) : 0u;
+            B.n_labels = (int32_t)std::min<size_t>(per, active.size() - i);
+            for (int k = 0; k < B.n_labels; k++) B.labels[k] = active[i + (size_t)k];
+            B.first = i == 0 && band == 0;
+            B.last = i + per >= active.size() && band + 1 == n_bands;
+            B.cand_items = h->d_dgitems.as<uint32_t>() + (d ? dcap[0] : 0);
+            B.cand_count = h->d_dgcount.as<uint32_t>() + d;
+            B.refine_min = (uint32_t)h->refine_min;
+            if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
+            B.work_counter = K.work_counter;
+            SPR_CUDA(h, spr_launch_bound_lattice(h->V, B, n_planes, h->sm_count, st, &launches));
+            K.work_counter++;
+            passes_left--;
+          }
         }
       }
       B.cand_items = nullptr; B.cand_count = nullptr;

@@ -93,28 +93,32 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
   const uint32_t BW = ((band_rows + 1u) * W + 3u) & ~3u;  // words per staged label (16-byte aligned bulk-copy targets)
   const int32_t row_shift = SMEM_TAB ? (int32_t)(B.row_begin << F) : 0;
 
-  if (SMEM_TAB) {  // one TMA bulk copy per label
-    // [4 zero words][labels x BW words][4 zero words][mbarrier]: a probe reads the word before and
-    // the word after its base word, also for the first row of the first label / the last zero row
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 4 + (size_t)B.n_labels * BW + 4);
+  if (REFINE && __ldg(B.cand_count) < B.refine_min) return;  // few candidates: not worth refining (uniform for the grid)
+  // staged planes: the launch's labels, or (refinement) the four half-cell variants of its one label
+  const uint32_t NP = REFINE ? 4u : (uint32_t)B.n_labels;
+  if (SMEM_TAB) {  // one TMA bulk copy per plane
+    // [4 zero words][planes x BW words][4 zero words][mbarrier]: a probe reads the word before and
+    // the word after its base word, also for the first row of the first plane / the last zero row
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 4 + (size_t)NP * BW + 4);
     if (threadIdx.x == 0) {
       spb_mbar_init(bar, 1u);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (uint32_t i = threadIdx.x; i < (uint32_t)B.n_labels * W; i += blockDim.x)
+    for (uint32_t i = threadIdx.x; i < NP * W; i += blockDim.x)
       smem[4 + (size_t)(i / W) * BW + (size_t)band_rows * W + (i % W)] = 0u;
-    if (threadIdx.x < 4) { smem[threadIdx.x] = 0u; smem[4 + (size_t)B.n_labels * BW + threadIdx.x] = 0u; }
-    if (threadIdx.x < (uint32_t)B.n_labels * 4u) {  // alignment words behind each label's zero row
+    if (threadIdx.x < 4) { smem[threadIdx.x] = 0u; smem[4 + (size_t)NP * BW + threadIdx.x] = 0u; }
+    if (threadIdx.x < NP * 4u) {  // alignment words behind each plane's zero row
       const uint32_t k = threadIdx.x >> 2, j = threadIdx.x & 3u;
       if ((band_rows + 1u) * W + j < BW) smem[4 + (size_t)k * BW + (band_rows + 1u) * W + j] = 0u;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      spb_mbar_expect_tx(bar, (uint32_t)B.n_labels * band_rows * W * 4u);
-      for (int k = 0; k < B.n_labels; k++)
-        spb_bulk_g2s(smem + 4 + (size_t)k * BW,
-                     V.bitmap + ((size_t)B.labels[k] * G.label_stride + (d ? G.plane_words[0] : 0u) + (size_t)B.row_begin * W),
-                     band_rows * W * 4u, bar);
+      spb_mbar_expect_tx(bar, NP * band_rows * W * 4u);
+      for (uint32_t k = 0; k < NP; k++) {
+        const uint32_t *src = REFINE ? V.vbitmap + (4 * ((size_t)B.labels[0] * G.label_stride + (d ? G.plane_words[0] : 0u)) + (size_t)k * G.plane_words[d])
+                                     : V.bitmap + ((size_t)B.labels[k] * G.label_stride + (d ? G.plane_words[0] : 0u));
+        spb_bulk_g2s(smem + 4 + (size_t)k * BW, src + (size_t)B.row_begin * W, band_rows * W * 4u, bar);
+      }
     }
     for (uint32_t spin = 0; !spb_mbar_try_wait(bar, 0u); spin++)
       if (spin > 200000000u) __trap();  // a lost copy must not hang the GPU
@@ -175,7 +179,7 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
         const int l = B.labels[k];
         const int g0 = V.label_gseg[l], g1 = V.label_gseg[l + 1];
         if (g0 >= g1) continue;
-        const uint32_t *bits = SMEM_TAB ? smem + 4 + (size_t)k * BW
+        const uint32_t *bits = SMEM_TAB ? smem + 4 + (REFINE ? (size_t)0 : (size_t)k * BW)
                                : REFINE ? V.vbitmap + (4 * ((size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u)))
                                         : V.bitmap + ((size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u));
         SprBox lb = V.labelbox[l];
@@ -215,7 +219,7 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
                 asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(boff) : "r"(bit >> 5), "r"(row * W4));
                 if (REFINE) {  // variant = 2 * (upper half of the cell across) + (upper half of the cell along)
                   const uint32_t var = ((uint32_t)((aqb + qa_) >> (F - 1)) & 1u) * 2u + ((uint32_t)((bqb2 + qb_) >> (F - 1)) & 1u);
-                  boff += var * PW4;
+                  boff += var * (SMEM_TAB ? BW * 4u : PW4);
                 }
                 const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(bits) + boff);
                 const uint32_t w0 = p[-1], w1 = p[0], w2 = p[1];
@@ -518,12 +522,37 @@ void spr_bound_plan(const SprView &V, uint32_t dir, int n_active, int *labels_pe
   *band_rows = (uint32_t)((((R + bands - 1) / bands) + 3) & ~(size_t)3);
 }
 
+// Row bands for the refinement launches (four variant planes of one label staged per launch);
+// 0: read the variant planes in place.
+uint32_t spr_refine_band_rows(const SprView &V, uint32_t dir) {
+  const size_t W4 = (size_t)V.grid.W[dir] * 4, R = (size_t)V.grid.R[dir];
+  size_t limit = SPR_SMEM_LIMIT - 64;
+  int min_nqp = 2048;
+  if (const char *e = std::getenv("SLIDE_PR_BOUND_SMEM")) {  // test hook, as in spr_bound_plan
+    const long v = std::atol(e);
+    if (v > 0 && (size_t)v < limit) { limit = (size_t)v; min_nqp = 0; }
+  }
+  if (V.nqp < min_nqp) return 0;  // few query landmarks per work item: not worth one launch per band
+  size_t max_rows = (limit - 48) / (4 * (W4 + 4));
+  if (max_rows < 9) return 0;
+  max_rows = (max_rows - 1) & ~(size_t)3;
+  if (max_rows >= R) return (uint32_t)R;
+  const size_t bands = (R + max_rows - 1) / max_rows;
+  return (uint32_t)((((R + bands - 1) / bands) + 3) & ~(size_t)3);
+}
+
 template <int PLANES>
 static cudaError_t spb_launch(const SprView &V, const SprBoundLaunch &B, int n_dg_local, long long n_items, int sm_count,
                               cudaStream_t st) {
   const size_t BW4 = (((size_t)(B.row_end - B.row_begin + 1) * (size_t)V.grid.W[B.dir] + 3) & ~(size_t)3) * 4;
-  const size_t smem = 16 + (size_t)B.n_labels * BW4 + 16 + 16;  // 4 zero words in front and behind + the mbarrier
-  if (!B.cand_items && B.row_end > B.row_begin && smem <= SPR_SMEM_LIMIT) {
+  const size_t n_staged = B.cand_items ? 4 : (size_t)B.n_labels;  // refinement: the four variants of one label
+  const size_t smem = 16 + n_staged * BW4 + 16 + 16;  // 4 zero words in front and behind + the mbarrier
+  if (B.cand_items && B.row_end > B.row_begin && smem <= SPR_SMEM_LIMIT && B.n_labels == 1) {
+    cudaError_t e = cudaFuncSetAttribute(spr_bound_lattice_kernel<PLANES, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long want = (n_items + SPB_THREADS / 32 - 1) / (SPB_THREADS / 32);
+    spr_bound_lattice_kernel<PLANES, true, true><<<(int)(want < sm_count ? want : sm_count), SPB_THREADS, smem, st>>>(V, B, n_dg_local, n_items);
+  } else if (!B.cand_items && B.row_end > B.row_begin && smem <= SPR_SMEM_LIMIT) {
     cudaError_t e = cudaFuncSetAttribute(spr_bound_lattice_kernel<PLANES, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long want = (n_items + SPB_THREADS / 32 - 1) / (SPB_THREADS / 32);

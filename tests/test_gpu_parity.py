@@ -256,6 +256,47 @@ def test_bound_phase_planner_paths(smem):
     assert got_idx == want_idx and np.array_equal(got_bound, want_bound)
 
 
+@pytest.mark.parametrize("smem", [0, 100000, 20000, 3000])
+def test_refinement_paths(smem):
+    """Refined bounds (half-cell bitmap variants) forced on: variants read in place (default for small
+    query maps) or staged in row bands of shrinking size.  Bounds stay upper bounds, the winner is
+    the exhaustive one."""
+    ref, qry, _ = synth.make_pair(500, seed=47, classes="five", outlier_frac=0.2)
+    ros = {"search_xy_step_size": 0.5, "search_yaw_step_size_degrees": 20.0, "match_threshold_position": 0.5,
+           "match_threshold_dimension": 1.0, "ignore_dimension": 0, "min_num_inliers": 5}
+    ref = ref.copy(); qry = qry.copy()
+    ref[:, 1:3] -= ref[:, 1:3].mean(0); qry[:, 1:3] -= qry[:, 1:3].mean(0)
+    half = 1.2 * max(np.abs(ref[:, 1:3]).max(), np.abs(qry[:, 1:3]).max())
+    os.environ["SLIDE_PR_REFINE_MIN"] = "0"
+    if smem:
+        os.environ["SLIDE_PR_BOUND_SMEM"] = str(smem)
+    try:
+        pr = PlaceRecognition(ros)
+        pr.prepare(ref, qry, half, half)
+        nt, ny, _ = pr.lattice_info()
+        lo, hi = nt // 2, nt // 2 + 3000
+        res, _ = pr.search()
+        res_x, _ = pr.search(exhaustive=True)
+        _, exact = pr.search(lo, hi, want_counts=True)
+        _, bound = pr.search(lo, hi, want_counts=True, bounds_only=True)
+        pr.close()
+    finally:
+        os.environ.pop("SLIDE_PR_REFINE_MIN", None)
+        os.environ.pop("SLIDE_PR_BOUND_SMEM", None)
+    assert (res.best_num_inliers, res.best_hyp_index) == (res_x.best_num_inliers, res_x.best_hyp_index)
+    assert (bound >= exact).all() and (bound <= len(qry)).all()
+    # the refinement really tightened something: fewer filter-level false positives than the plain bound
+    os.environ["SLIDE_PR_REFINE_MIN"] = "-1"
+    try:
+        pr = PlaceRecognition(ros)
+        pr.prepare(ref, qry, half, half)
+        _, plain = pr.search(lo, hi, want_counts=True, bounds_only=True)
+        pr.close()
+    finally:
+        os.environ.pop("SLIDE_PR_REFINE_MIN", None)
+    assert (bound <= plain).all() and bound.sum() < plain.sum()
+
+
 def test_bound_and_verify_with_many_query_landmarks():
     """More than 4095 query landmarks: 16 bit planes per bound; more than 2047: row bands allowed."""
     ref, qry, _ = synth.make_pair(4500, seed=43, classes="forest_urban")
