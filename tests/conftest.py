@@ -14,6 +14,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """The built library is git-ignored: compile it in-tree when a fresh checkout runs the tests
+    (nvcc cross-compiles without a GPU).  A failed build surfaces in the tests that load it."""
+    try:
+        from slide_slam_b200 import capi
+        if not os.path.exists(capi.LIB_PATH):
+            capi.build()
+    except Exception:
+        pass
+
+
 def _has_gpu():
     try:
         import torch
