@@ -5,6 +5,7 @@ cpu_baseline / --impl reference leg.  The product package (slide_slam_b200) neve
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import subprocess
@@ -13,6 +14,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libslide_oracle.so")
+_ALT_PATH = os.path.join(_HERE, "libslide_oracle_alt.so")  # -DSLIDE_ORACLE_ALT_SUM_ORDER (see slide_oracle.c)
 
 
 class Params(C.Structure):
@@ -72,24 +74,36 @@ class TfResult(C.Structure):
 
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "slide_oracle.c")
-    stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(
-        os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "slide_oracle.h")))
+    newest = max(os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "slide_oracle.h")))
+    stale = any((not os.path.exists(q)) or os.path.getmtime(q) < newest for q in (_LIB_PATH, _ALT_PATH))
     if force or stale:
-        subprocess.run(["make", "-C", _HERE, "-B", "libslide_oracle.so"], check=True,
+        subprocess.run(["make", "-C", _HERE, "-B", "libslide_oracle.so", "libslide_oracle_alt.so"], check=True,
                        stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
 
-_lib = None
+_libs = {}
+_use_alt = False
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
 
+@contextlib.contextmanager
+def alt_sum_order():
+    """Inside the block every call goes to the oracle built with the OTHER candidate for Eigen's
+    summation order in PR.cpp:257-258: x' = c*qx + ((-s)*qy + x)."""
+    global _use_alt
+    old, _use_alt = _use_alt, True
+    try:
+        yield
+    finally:
+        _use_alt = old
+
+
 def lib():
-    global _lib
-    if _lib is None:
+    if _use_alt not in _libs:
         build()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(_ALT_PATH if _use_alt else _LIB_PATH)
         L.slide_oracle_deg2rad.restype = C.c_double
         L.slide_oracle_deg2rad.argtypes = [C.c_double]
         L.slide_oracle_enumerate_lattice.restype = C.c_longlong
@@ -115,8 +129,10 @@ def lib():
         L.slide_oracle_match_triangles.argtypes = [
             _dp, C.c_int, _dp, C.c_int, C.c_double, _ip, _ip, _dp, C.c_longlong]
         L.slide_oracle_estimate_tf.argtypes = [_dp, _dp, C.c_int, _dp]
-        _lib = L
-    return _lib
+        L.slide_oracle_find_intra_loop_closure.argtypes = [
+            C.POINTER(Params), _dp, C.c_int, _dp, C.c_int, _dp, _dp, C.c_int, _dp, C.POINTER(TfResult)]
+        _libs[_use_alt] = L
+    return _libs[_use_alt]
 
 
 def deg2rad(deg: float) -> float:
@@ -250,6 +266,19 @@ def find_inter_loop_closure(p: Params, ref7, qry7, n_threads=1):
     found = lib().slide_oracle_find_inter_loop_closure(
         C.byref(p), rp, ref7.shape[0], qp, qry7.shape[0], n_threads, tf.ctypes.data_as(_dp),
         C.byref(res))
+    return bool(found), tf.reshape(4, 4), _tf_dict(res)
+
+
+def find_intra_loop_closure(p: Params, meas7, submap7, query_pose, candidate_pose, n_threads=1):
+    meas7, mp = _d(meas7)
+    submap7, sp = _d(submap7)
+    qp_, qpp = _d(np.reshape(query_pose, 16))
+    cp_, cpp = _d(np.reshape(candidate_pose, 16))
+    tf = np.zeros(16, np.float64)
+    res = TfResult()
+    found = lib().slide_oracle_find_intra_loop_closure(
+        C.byref(p), mp, meas7.shape[0] if meas7.size else 0, sp, submap7.shape[0] if submap7.size else 0,
+        qpp, cpp, n_threads, tf.ctypes.data_as(_dp), C.byref(res))
     return bool(found), tf.reshape(4, 4), _tf_dict(res)
 
 

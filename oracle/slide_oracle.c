@@ -76,9 +76,20 @@ int slide_oracle_score_one(const slide_oracle_params *p, const double *ref7, int
   const double ms = -s; /* cur_R_t(0,1) = -sin(yaw)  PR.cpp:247 */
   for (int j = 0; j < n_qry; j++) {
     const double *q = qry7 + 7 * (size_t)j;
-    /* PR.cpp:257-261: R_t * [qx qy 1]^T, left-to-right, then / 1.0 */
+    /* PR.cpp:257-261: R_t * [qx qy 1]^T, then / 1.0.  Eigen evaluates this fixed 3x3 times
+     * (dynamic) 3x1 product coefficient-based (product_type_selector<Small,1,Small>); with its
+     * default packet path (SSE2 / NEON, EIGEN_UNALIGNED_VECTORIZE) rows 0..1 come out of
+     * etor_product_packet_impl = pmul, pmadd, pmadd: LEFT TO RIGHT (the contract adopted here).
+     * Built with EIGEN_DONT_VECTORIZE the scalar path is a 3-term redux e0 + (e1 + e2): that
+     * variant is compiled with -DSLIDE_ORACLE_ALT_SUM_ORDER into libslide_oracle_alt.so and
+     * tests/test_oracle_pins.py checks that no golden result depends on the choice. */
+#ifdef SLIDE_ORACLE_ALT_SUM_ORDER
+    double xt = c * q[1] + (ms * q[2] + x);
+    double yt = s * q[1] + (c * q[2] + y);
+#else
     double xt = (c * q[1] + ms * q[2]) + x;
     double yt = (s * q[1] + c * q[2]) + y;
+#endif
     int i = first_match(p, ref7, n_ref, q[0], xt, yt, q + 4);
     if (i >= 0) {
       if (ref_idx_out) ref_idx_out[inliers] = i;
@@ -582,6 +593,52 @@ int slide_oracle_find_inter_loop_closure(const slide_oracle_params *p, const dou
   tf16[0] = cos(yaw); tf16[1] = -sin(yaw); tf16[4] = sin(yaw); tf16[5] = cos(yaw);
   tf16[10] = 1; tf16[15] = 1;
   tf16[3] = x; tf16[7] = y; tf16[11] = z;
+  return 1;
+}
+
+static int mat4_rigid_inverse(const double *A, double *Ainv) { /* Sophus SE3::inverse(): [R^T, -R^T t] */
+  double T[16] = {0};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) T[i * 4 + j] = A[j * 4 + i];
+  for (int i = 0; i < 3; i++) T[i * 4 + 3] = -(T[i * 4] * A[3] + T[i * 4 + 1] * A[7] + T[i * 4 + 2] * A[11]);
+  T[15] = 1;
+  memcpy(Ainv, T, sizeof(T));
+  return 1;
+}
+
+int slide_oracle_find_intra_loop_closure(const slide_oracle_params *p, const double *meas7, int n_meas,
+                                         const double *submap7, int n_sub, const double *query_pose16,
+                                         const double *candidate_pose16, int n_threads, double *tf16,
+                                         slide_oracle_tf_result *res_out) { /* PR.cpp:389-496 */
+  slide_oracle_tf_result local, *res = res_out ? res_out : &local;
+  memset(res, 0, sizeof(*res));
+  if (n_meas == 0 || n_sub == 0) return 0;                         /* :395-398 */
+  if (n_meas < 4) return 0;                                        /* :400-403 */
+  double *moved = (double *)malloc(sizeof(double) * 7 * (size_t)n_meas);
+  const double *P = query_pose16;
+  for (int i = 0; i < n_meas; i++) {                               /* :421-439 */
+    const double *m = meas7 + 7 * (size_t)i;
+    double v[4];
+    /* Matrix4d * Vector4d, all sizes fixed: Eigen's packet product accumulates column by column */
+    for (int r = 0; r < 4; r++) v[r] = ((P[r * 4] * m[1] + P[r * 4 + 1] * m[2]) + P[r * 4 + 2] * m[3]) + P[r * 4 + 3] * 1.0;
+    double *o = moved + 7 * (size_t)i;
+    o[0] = m[0]; o[1] = v[0] / v[3]; o[2] = v[1] / v[3]; o[3] = v[2] / v[3];
+    o[4] = m[4]; o[5] = m[5]; o[6] = m[6];
+  }
+  slide_oracle_params pp = *p;
+  pp.inter_loop_closure = 0;  /* the intra instance is constructed with inter_loop_closure = false (sloamNode.cpp:23) */
+  int found = slide_oracle_find_transformation(&pp, submap7, n_sub, moved, n_meas, NULL, NULL, n_threads, res); /* :446 */
+  free(moved);
+  if (!found) return 0;                                            /* :449-453 */
+  double yaw = res->xyz_yaw[3];
+  double lc[16] = {0};                                             /* :455-470, z forced to 0 (:466) */
+  lc[0] = cos(yaw); lc[1] = -sin(yaw); lc[4] = sin(yaw); lc[5] = cos(yaw);
+  lc[10] = 1; lc[15] = 1;
+  lc[3] = res->xyz_yaw[0]; lc[7] = res->xyz_yaw[1]; lc[11] = 0.0;
+  double cinv[16], drift[16];
+  mat4_rigid_inverse(candidate_pose16, cinv);
+  mat4_mul(cinv, query_pose16, drift);                             /* :478 candidate^-1 * query */
+  mat4_mul(drift, lc, tf16);                                       /* :483-494 */
   return 1;
 }
 

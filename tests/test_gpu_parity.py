@@ -419,8 +419,14 @@ def test_inter_and_intra_loop_closure(gold):
     inv = np.linalg.inv(qp)
     meas_local[:, 1:4] = (meas_local[:, 1:4] - qp[:3, 3]) @ inv[:3, :3].T
     found, tf2 = pri.findIntraLoopClosure(meas_local, maps[ci["ref"]], qp, cp)
-    assert found
-    np.testing.assert_allclose(tf2, np.linalg.inv(cp) @ qp @ want, rtol=1e-4, atol=1e-6)
+    ofound, otf2, oinfo = O.find_intra_loop_closure(O.make_params(**ci["params"]), meas_local, maps[ci["ref"]], qp, cp)
+    assert found and ofound
+    np.testing.assert_allclose(tf2, otf2, rtol=RTOL, atol=1e-9)  # the oracle's findIntraLoopClosure (PR.cpp:389-496)
+    np.testing.assert_allclose(tf2, np.linalg.inv(cp) @ qp @ want, rtol=1e-4, atol=1e-6)  # and the scene's own truth
+    # identity poses through the oracle as well
+    ofound, otf, _ = O.find_intra_loop_closure(O.make_params(**ci["params"]), maps[ci["qry"]], maps[ci["ref"]], np.eye(4), np.eye(4))
+    assert ofound
+    np.testing.assert_allclose(tf, otf, rtol=RTOL, atol=1e-9)
     pr.close(); pri.close()
 
 
