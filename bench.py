@@ -239,10 +239,13 @@ def run_ours(args, rank, world, local_rank):
             inc_host[0] = max(int(seed.best_num_inliers), 0)
             inc_dev.copy_(inc_host, non_blocking=True)
             dist.all_reduce(inc_dev, op=dist.ReduceOp.MAX)
-            res, _ = pr.search(shard_index=rank, shard_count=world, stream=stream.cuda_stream,
-                               incumbent_inliers=int(inc_dev.item()), reuse_bounds=True)
-            res.gpu_launches += seed.gpu_launches
-            res.kernel_ms += seed.kernel_ms
+            if seed.search_mode == 0:       # no bound phase for this problem: already searched exhaustively
+                res = seed
+            else:
+                res, _ = pr.search(shard_index=rank, shard_count=world, stream=stream.cuda_stream,
+                                   incumbent_inliers=int(inc_dev.item()), reuse_bounds=True)
+                res.gpu_launches += seed.gpu_launches
+                res.kernel_ms += seed.kernel_ms
         else:
             res, _ = pr.search(stream=stream.cuda_stream)
         gather_and_merge(res)

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -48,6 +49,7 @@ double now_ms() {
 
 // Page-locked allocation for the host vectors that are uploaded (spr::uvec): a 64-byte header
 // remembers whether cudaHostAlloc succeeded, otherwise the block comes from malloc.
+std::atomic<int> g_pageable_uploads{0};  // page-locking failed at least once: see slide_pr_prepare
 void *pinned_alloc(size_t n) {
   void *p = nullptr;
   if (cudaHostAlloc(&p, n + 64, cudaHostAllocPortable) == cudaSuccess && p) {
@@ -57,6 +59,8 @@ void *pinned_alloc(size_t n) {
     p = std::malloc(n + 64);
     if (!p) return nullptr;
     *static_cast<uint64_t *>(p) = 0;
+    if (g_pageable_uploads.fetch_add(1) == 0)
+      std::fprintf(stderr, "[slide_pr] warning: cudaHostAlloc failed, uploads fall back to pageable memory (synchronous staging)\n");
   }
   return static_cast<char *>(p) + 64;
 }
@@ -139,6 +143,8 @@ struct slide_pr_handle {
   bool force_exhaustive = false;  // env SLIDE_PR_EXHAUSTIVE=1
   int refine_min = 32;            // candidate double groups from which the bounds are refined (env SLIDE_PR_REFINE_MIN; < 0: never)
   bool refine_forced = false;     // env SLIDE_PR_REFINE_MIN given: refine whenever there are that many candidates
+  size_t bound_smem = 0;          // env SLIDE_PR_BOUND_SMEM (test hook): shared-memory budget of the bound planner, 0 = all
+  bool ring_major = false;        // lattice of the prepared problem is chunked ring by ring (anytime budget may bind)
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // uploads that overlap the bound phase of a search
   cudaStream_t side_stream = nullptr;  // verification passes of the second bitmap direction
@@ -188,6 +194,22 @@ struct slide_pr_handle {
       return SLIDE_PR_ERR_CUDA;                                                             \
     }                                                                                       \
   } while (0)
+
+// compute_budget_sec (PR.cpp:181-191) is tested before every ring, in whole seconds, with '>': a search
+// that ends within the budget scores every ring and returns what the unlimited search returns.  The
+// GPU search takes milliseconds where the reference takes its full budget, so the default
+// bound-and-verify search stays in place whenever a (deliberately pessimistic: ~1/8 of the measured
+// rate) estimate of the search time is below the budget; only then-unrealistic problems fall back to
+// the ring-by-ring exhaustive search that can stop between rings.
+static bool budget_may_bind(const slide_pr_params &p, double half_x, double half_y, double yaw_half, int n_qry) {
+  if (!(p.compute_budget_sec > 0)) return false;
+  const double step = p.match_xy_step_size;
+  if (!(step > 0)) return true;
+  const double n_trans = (2.0 * half_x / step + 1.0) * (2.0 * half_y / step + 1.0);
+  const double n_yaw = p.disable_yaw_search ? 1.0 : (p.match_yaw_angle_step_size > 0 ? 2.0 * yaw_half / p.match_yaw_angle_step_size + 1.0 : 1e30);
+  const double est_sec = n_trans * n_yaw * (double)std::max(n_qry, 1) / 2.0e12;
+  return !(est_sec < p.compute_budget_sec);
+}
 
 template <typename T, typename A>
 static int upload(slide_pr_handle *h, DevBuf &b, const std::vector<T, A> &v, cudaStream_t st) {
@@ -270,6 +292,7 @@ int slide_pr_create(const slide_pr_params *p, slide_pr_handle **out) {
   // SLIDE_PR_EXHAUSTIVE=1 verifies every hypothesis exactly (no bound-and-verify pruning)
   if (const char *v = std::getenv("SLIDE_PR_EXHAUSTIVE")) h->force_exhaustive = std::atoi(v) != 0;
   if (const char *v = std::getenv("SLIDE_PR_REFINE_MIN")) { h->refine_min = std::atoi(v); h->refine_forced = true; }
+  if (const char *v = std::getenv("SLIDE_PR_BOUND_SMEM")) { const long b = std::atol(v); if (b > 0) h->bound_smem = (size_t)b; }
   *out = h;
   return SLIDE_PR_OK;
 }
@@ -361,10 +384,15 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   const double t0 = now_ms();
   SPR_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
+  // the previous prepare's uploads read the handle's page-locked vectors asynchronously: they must have
+  // been consumed before those vectors are rebuilt (a search in between has already waited for them)
+  SPR_CUDA(h, cudaEventSynchronize(h->ev_prep));
   h->half_x = half_x; h->half_y = half_y;
   h->h2d_bytes = 0;
   h->yaw_half = h->p.inter_loop_closure ? h->p.match_yaw_half_range : h->p.match_yaw_half_range_intra;
   h->n_ref = n_ref; h->n_qry = n_qry;
+  const bool ring_major = budget_may_bind(h->p, half_x, half_y, h->yaw_half, n_qry);
+  h->ring_major = ring_major;
   h->lat_tb = 0; h->lat_te = -1;
   int rc;
   h->reuse_flags = 0;
@@ -373,7 +401,7 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
                             h->lat_p.match_xy_step_size == h->p.match_xy_step_size &&
                             h->lat_p.match_yaw_angle_step_size == h->p.match_yaw_angle_step_size &&
                             h->lat_p.disable_yaw_search == h->p.disable_yaw_search &&
-                            (h->lat_p.compute_budget_sec > 0) == (h->p.compute_budget_sec > 0);
+                            h->L.ring_major == ring_major;
   std::string lattice_err, query_err;
   bool lattice_started = false, query_started = false;
   // every exit path waits for the helper threads (they write into the handle)
@@ -383,8 +411,9 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   } joiner{h, &lattice_started, &query_started};
   if (!same_lattice) {  // built on a helper thread while this one builds the bitmaps
     h->lattice_valid = false;
-    h->worker_lattice.submit([h, half_x, half_y, &lattice_err]() {
-      return spr::build_lattice(h->p, half_x, half_y, h->yaw_half, 0, -1, h->p.compute_budget_sec > 0, h->L, lattice_err);
+    h->worker_lattice.submit([h, half_x, half_y, ring_major, &lattice_err]() {
+      cudaSetDevice(h->device);  // the page-locked buffers grown by this job belong to the handle's device (one process may drive several GPUs)
+      return spr::build_lattice(h->p, half_x, half_y, h->yaw_half, 0, -1, ring_major, h->L, lattice_err);
     });
     lattice_started = true;
   } else {
@@ -416,7 +445,10 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
                         h->cached_ref_p.match_threshold_dimension == h->p.match_threshold_dimension &&
                         (n_ref == 0 || std::memcmp(h->cached_ref.data(), ref7, (size_t)n_ref * 7 * sizeof(double)) == 0);
   auto start_query_job = [&]() {
-    h->worker_query.submit([h, qry7, n_qry, &query_err]() { return spr::build_query_set(h->R, qry7, n_qry, h->Q, query_err); });
+    h->worker_query.submit([h, qry7, n_qry, &query_err]() {
+      cudaSetDevice(h->device);
+      return spr::build_query_set(h->R, qry7, n_qry, h->Q, query_err);
+    });
     query_started = true;
   };
   if (!same_ref) {
@@ -508,6 +540,7 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   // no synchronisation here: every upload reads page-locked vectors owned by the handle (the
   // caller's rows were copied), which stay untouched until the next prepare
   SPR_CUDA(h, cudaEventRecord(h->ev_prep, st));  // a search on another stream waits for these uploads
+  if (g_pageable_uploads.load() > 0) SPR_CUDA(h, cudaStreamSynchronize(st));  // page-locking failed somewhere: do not rely on it
   h->prepared = true;
   h->prepare_ms = now_ms() - t0;
   g_trace.mark("query_upload");
@@ -542,7 +575,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   int rc;
   const int64_t tb = o.trans_begin < 0 ? 0 : o.trans_begin, te = o.trans_end;
   if (tb != h->lat_tb || te != h->lat_te) {  // re-chunk the lattice for the requested slice
-    if ((rc = spr::build_lattice(h->p, h->half_x, h->half_y, h->yaw_half, tb, te, h->p.compute_budget_sec > 0, h->L, h->err)) != SLIDE_PR_OK) return rc;
+    if ((rc = spr::build_lattice(h->p, h->half_x, h->half_y, h->yaw_half, tb, te, h->ring_major, h->L, h->err)) != SLIDE_PR_OK) return rc;
     h->lat_tb = tb; h->lat_te = te;
     h->lattice_valid = tb == 0 && te < 0;  // a sliced lattice is not the one prepare may reuse
     if ((rc = upload_lattice(h, st))) return rc;
@@ -610,9 +643,13 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   // those whose bound reaches the running best.  Exhaustive verification of every hypothesis
   // when per-hypothesis counts / statistics are requested, with a compute budget (ring by ring),
   // or on request (opts.exhaustive).
-  const bool can_bound = h->p.compute_budget_sec <= 0 && active[0] >= 0 && h->V.nqp > 0 && h->V.nqp < 65536;
-  const bool bounds_only = o.exhaustive == 2;  // test hook: counts_out receives the upper bounds
-  if (bounds_only && !can_bound) { h->err = "bounds-only search not available for this problem"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  const bool can_bound = !h->ring_major && active[0] >= 0 && h->V.nqp > 0 && h->V.nqp < 65536;
+  // exhaustive = 2: bound phase only (first half of a sharded search; test hook when counts_out is given: it
+  // receives the upper bounds).  Problems without a bound phase (no query label occurs in the reference map,
+  // >= 65536 query landmarks, a compute budget that may bind) are searched exhaustively at once instead:
+  // the result says so (search_mode = 0) and the caller skips the verification half.
+  if (o.exhaustive == 2 && !can_bound && o.counts_out) { h->err = "upper bounds are not available for this problem"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  const bool bounds_only = o.exhaustive == 2 && can_bound;
   const bool prune = bounds_only || (!o.exhaustive && !o.counts_out && !o.collect_stats && can_bound && !h->force_exhaustive);
   const int n_planes = spr_bound_planes(h->V.nqp);
   size_t cand_off[2] = {0, 0};
@@ -636,7 +673,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
       if (h->L.dir_end[d] <= h->L.dir_begin[d]) continue;
       int per = 1;
       uint32_t band_rows = 0;
-      spr_bound_plan(h->V, d, (int)active.size(), &per, &band_rows);
+      spr_bound_plan(h->V, d, (int)active.size(), h->bound_smem, &per, &band_rows);
       const uint32_t R = (uint32_t)h->V.grid.R[d];
       const uint32_t n_bands = band_rows ? (R + band_rows - 1) / band_rows : 1;
       for (uint32_t band = 0; band < n_bands; band++) {
@@ -712,7 +749,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
         if (h->L.dir_end[d] <= h->L.dir_begin[d]) continue;
         // one label per launch with its four variant planes staged in row bands, or -- small query
         // maps, planes too wide -- up to 8 labels per launch reading the variants in place
-        const uint32_t band_rows = spr_refine_band_rows(h->V, d);
+        const uint32_t band_rows = spr_refine_band_rows(h->V, d, h->bound_smem);
         const uint32_t R = (uint32_t)h->V.grid.R[d];
         const uint32_t n_bands = band_rows ? (R + band_rows - 1) / band_rows : 1;
         const size_t per = band_rows ? 1 : SPR_BOUND_MAX_LABELS;
@@ -796,7 +833,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   int rings_scored = 0;
   if (bounds_only) {
     rings_scored = h->L.rings;
-  } else if (h->p.compute_budget_sec > 0) {
+  } else if (h->ring_major) {
     // anytime behaviour of PR.cpp:181-191: whole seconds, checked before every ring
     const auto start = std::chrono::high_resolution_clock::now();
     for (size_t k = 0; k < h->L.ring.size(); k++) {
@@ -860,10 +897,9 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     const int sc = o.shard_count > 1 ? o.shard_count : 1, si = o.shard_count > 1 ? o.shard_index : 0;
     uint64_t bits = 0;
     auto count_range = [&](uint32_t cb, uint32_t ce) {
-      for (uint32_t c = cb; c < ce; c++)
-        if ((int)(((c - cb) / (2 * SPR_WARP_CHUNKS)) % sc) == si) bits += (uint64_t)__builtin_popcount(h->L.chunks[c].valid);
+      for (uint32_t g = cb / 64 + (uint32_t)si; g < ce / 64; g += (uint32_t)sc) bits += h->L.dg_bits[g];
     };
-    if (h->p.compute_budget_sec > 0) {
+    if (h->ring_major) {
       for (int k = 0; k < rings_scored; k++)
         for (int d = 0; d < 2; d++) count_range(h->L.ring[k].dbegin[d], h->L.ring[k].dend[d]);
     } else {

@@ -323,6 +323,12 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
   }
   L.ring_major = ring_major;
   L.chunks.swap(out);
+  L.dg_bits.assign(L.chunks.size() / 64, 0u);  // every direction / ring segment is padded to whole double groups
+  for (size_t g = 0; g < L.dg_bits.size(); g++) {
+    uint32_t bits = 0;
+    for (size_t c = 64 * g; c < 64 * g + 64; c++) bits += (uint32_t)__builtin_popcount(L.chunks[c].valid);
+    L.dg_bits[g] = bits;
+  }
   return SLIDE_PR_OK;
 }
 
@@ -439,7 +445,7 @@ int build_ref_marks(const slide_pr_params &p, const double *ref7, int n_ref, Ref
 
   // label bucket and slot (position inside its label, ascending index) of every landmark; the
   // compact per-label landmark table [x, y, d1, d2, d3] a cell's 16-bit reference points into
-  std::vector<int32_t> &lab_of = R.lab_of;
+  uvec<int32_t> &lab_of = R.lab_of;
   std::vector<uint32_t> &slot_of_ref = R.slot_of_ref;
   lab_of.assign((size_t)std::max(n_ref, 1), -1);
   slot_of_ref.assign((size_t)std::max(n_ref, 1), 0u);
@@ -526,7 +532,7 @@ int build_ref_marks(const slide_pr_params &p, const double *ref7, int n_ref, Ref
 int build_ref_ranks(const double *ref7, int d, RefIndex &R, std::string &err) {
   const SprGrid &G = R.grid;
   const int n_labels = (int)R.labels.size();
-  const std::vector<int32_t> &lab_of = R.lab_of;
+  const uvec<int32_t> &lab_of = R.lab_of;
   const std::vector<uint32_t> &slot_of_ref = R.slot_of_ref;
   const std::vector<RefIndex::Entry> &entries = R.entries;
   {
@@ -612,7 +618,7 @@ static inline uint32_t part1by1(uint32_t x) {
 }
 
 int build_query_set(const RefIndex &R, const double *qry7, int n_qry, QuerySet &Q, std::string &err) {
-  Q = QuerySet();
+  Q.nq = Q.nqp = 0;  // the (page-locked) vectors keep their capacity across calls
   const int n_labels = (int)R.labels.size();
   struct Item { int l; uint32_t morton; int j; };
   std::vector<Item> items;

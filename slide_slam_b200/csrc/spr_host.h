@@ -38,7 +38,7 @@ struct Lattice {
   int rings = 0;
   double ox = 0, oy = 0;          // outer_loop_step_size_{x,y}
   std::vector<double> yaw;        // PR.cpp:136-146
-  std::vector<double> cs;         // cos, sin per yaw (libm)
+  uvec<double> cs;         // cos, sin per yaw (libm)
   uvec<double> lat;        // per ring: xs then ys
   struct Ring {
     uint32_t x_off, nx, y_off, ny;  // into lat
@@ -55,6 +55,7 @@ struct Lattice {
   std::vector<int32_t> succ;      // scratch of build_lattice (kept for their capacity)
   std::vector<uint32_t> sort_pos, sort_key;
   std::vector<uint8_t> sort_second;
+  std::vector<uint32_t> dg_bits;  // [chunks / 64] valid bits (lattice translations) of every double group
   bool ring_major = false;
   uint32_t dir_begin[2] = {0, 0}, dir_end[2] = {0, 0};  // !ring_major: all chunks of direction d
 };
@@ -75,17 +76,17 @@ struct RefIndex {
   uvec<uint16_t> rank16[2];   // per plane direction d: [n_labels][plane_words[d]] marked cells of the row before the word
   uvec<uint32_t> row_rank[2]; // per plane direction d: [n_labels][R[d]] rank (index into cand[d]) of the row's first marked cell
   uvec<uint16_t> cellref[2];  // per plane direction d: [n_cells] slot of the cell's only candidate in its label's table, or SPR_CELL_MULTI
-  std::vector<uint32_t> cell_base[2]; // per plane direction d: [n_labels + 1] rank of each label's first cell
+  uvec<uint32_t> cell_base[2]; // per plane direction d: [n_labels + 1] rank of each label's first cell
   uvec<double> reftab;        // [n_ref kept][5] x, y, d1, d2, d3, label-major
-  std::vector<uint32_t> ref_base;    // [n_labels + 1] first row of each label in reftab
-  std::vector<SprBox> labelbox;     // [n_labels] fixed-point bounds of the label's marked cells
+  uvec<uint32_t> ref_base;    // [n_labels + 1] first row of each label in reftab
+  uvec<SprBox> labelbox;     // [n_labels] fixed-point bounds of the label's marked cells
   double Tstar = 0, Sstar = 0;
   double mark_rc = 0, mark_rc2 = 0; // radius (cells) / squared radius of the marking predicate (0: nothing matches)
   int n_ref = 0;
   // carried from build_ref_bitmaps to build_ref_ranks
   struct Entry { uint32_t ref; int32_t nx, ny; };  // landmark `ref` marks cell (nx, ny); ascending landmark order
   std::vector<Entry> entries;
-  std::vector<int32_t> lab_of;       // [n_ref] label bucket, -1: NaN label
+  uvec<int32_t> lab_of;       // [n_ref] label bucket, -1: NaN label
   std::vector<uint32_t> slot_of_ref; // [n_ref] position inside its label
 };
 
@@ -105,10 +106,10 @@ struct QuerySet {
   int nq = 0;                       // kept queries (label present in the reference)
   int nqp = 0;                      // with every label segment padded to SPR_QGROUP
   std::vector<int32_t> orig;        // [nqp] original index, -1 for padding
-  std::vector<double> qxy;          // [nqp][2]
-  std::vector<double> qdims;        // [nqp][3]
-  std::vector<int32_t> qlabel;      // [nqp] label bucket, -1 for padding
-  std::vector<int32_t> label_gseg;  // [n_labels + 1] group (SPR_QGROUP queries) boundaries
+  uvec<double> qxy;          // [nqp][2]
+  uvec<double> qdims;        // [nqp][3]
+  uvec<int32_t> qlabel;      // [nqp] label bucket, -1 for padding
+  uvec<int32_t> label_gseg;  // [n_labels + 1] group (SPR_QGROUP queries) boundaries
 };
 int build_query_set(const RefIndex &R, const double *qry7, int n_qry, QuerySet &Q, std::string &err);
 

@@ -82,8 +82,8 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int t
 
 // bound phase of the bound-and-verify search (spr_kernels_bound.cu)
 int spr_bound_planes(int nqp);                                   // bit planes needed for counts <= nqp (12 or 16)
-void spr_bound_plan(const SprView &V, uint32_t dir, int n_active, int *labels_per_launch, uint32_t *band_rows);
-uint32_t spr_refine_band_rows(const SprView &V, uint32_t dir);  // 0: refinement reads the variant planes in place
+void spr_bound_plan(const SprView &V, uint32_t dir, int n_active, size_t smem_budget, int *labels_per_launch, uint32_t *band_rows);
+uint32_t spr_refine_band_rows(const SprView &V, uint32_t dir, size_t smem_budget);  // 0: refinement reads the variant planes in place
 cudaError_t spr_launch_bound_lattice(const SprView &V, const SprBoundLaunch &B, int n_planes, int sm_count, cudaStream_t st,
                                      int *n_launches);
 // work items of direction `B.dir` whose largest bound reaches the running best -> items[0 .. *count)

@@ -16,8 +16,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include <cstdlib>
-
 #include "spr_core.h"
 #include "spr_kernels.h"
 
@@ -491,16 +489,14 @@ int spr_bound_planes(int nqp) { return nqp < 4096 ? 12 : 16; }
 // launch as fit in shared memory, or -- when one plane does not fit -- one label per launch and
 // row bands (multiples of 4 rows: 16-byte aligned bulk copies).  band_rows == 0: planes stay in
 // global memory (a single row does not fit).
-void spr_bound_plan(const SprView &V, uint32_t dir, int n_active, int *labels_per_launch, uint32_t *band_rows) {
+// smem_budget: 0 = the whole shared memory of an SM; the handle passes a smaller value (read once
+// from SLIDE_PR_BOUND_SMEM at slide_pr_create, a test hook) to shrink the planner's budget and drop
+// the query-count threshold, so that small maps exercise the label-batch / row-band / in-place paths
+void spr_bound_plan(const SprView &V, uint32_t dir, int n_active, size_t smem_budget, int *labels_per_launch, uint32_t *band_rows) {
   const size_t W4 = (size_t)V.grid.W[dir] * 4, R = (size_t)V.grid.R[dir];
   size_t limit = SPR_SMEM_LIMIT - 64;
   int min_nqp = 2048;
-  // test hook: SLIDE_PR_BOUND_SMEM=<bytes> shrinks the shared-memory budget of the planner (and drops
-  // the query-count threshold) so that small maps exercise the label-batch / row-band / in-place paths
-  if (const char *e = std::getenv("SLIDE_PR_BOUND_SMEM")) {
-    const long v = std::atol(e);
-    if (v > 0 && (size_t)v < limit) { limit = (size_t)v; min_nqp = 0; }
-  }
+  if (smem_budget > 0 && smem_budget < limit) { limit = smem_budget; min_nqp = 0; }
   if ((R + 1) * W4 + 64 <= limit) {
     int per = (int)((limit - 48) / ((R + 1) * W4 + 16));
     if (per > SPR_BOUND_MAX_LABELS) per = SPR_BOUND_MAX_LABELS;
@@ -524,14 +520,11 @@ void spr_bound_plan(const SprView &V, uint32_t dir, int n_active, int *labels_pe
 
 // Row bands for the refinement launches (four variant planes of one label staged per launch);
 // 0: read the variant planes in place.
-uint32_t spr_refine_band_rows(const SprView &V, uint32_t dir) {
+uint32_t spr_refine_band_rows(const SprView &V, uint32_t dir, size_t smem_budget) {
   const size_t W4 = (size_t)V.grid.W[dir] * 4, R = (size_t)V.grid.R[dir];
   size_t limit = SPR_SMEM_LIMIT - 64;
   int min_nqp = 2048;
-  if (const char *e = std::getenv("SLIDE_PR_BOUND_SMEM")) {  // test hook, as in spr_bound_plan
-    const long v = std::atol(e);
-    if (v > 0 && (size_t)v < limit) { limit = (size_t)v; min_nqp = 0; }
-  }
+  if (smem_budget > 0 && smem_budget < limit) { limit = smem_budget; min_nqp = 0; }  // as in spr_bound_plan
   if (V.nqp < min_nqp) return 0;  // few query landmarks per work item: not worth one launch per band
   size_t max_rows = (limit - 48) / (4 * (W4 + 4));
   if (max_rows < 9) return 0;

@@ -67,6 +67,11 @@ def sharded_search(pr, rank: int, world: int, device=None, group=None):
     seed, _ = pr.search(shard_index=rank, shard_count=world, bounds_only=True)
     inc = torch.tensor([max(int(seed.best_num_inliers), 0)], dtype=torch.int64, device=device)
     dist.all_reduce(inc, op=dist.ReduceOp.MAX, group=group)
+    if seed.search_mode == 0:
+        # no bound phase for this problem (no query label occurs in the reference map, >= 65536 query
+        # landmarks, a binding compute budget): the first call already searched the shard exhaustively.
+        # The same on every rank (the problem is replicated), so the collective above stays matched.
+        return seed
     res, _ = pr.search(shard_index=rank, shard_count=world, incumbent_inliers=int(inc.item()), reuse_bounds=True)
     res.gpu_launches += seed.gpu_launches
     res.kernel_ms += seed.kernel_ms

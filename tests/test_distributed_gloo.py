@@ -72,18 +72,23 @@ def test_allgather_winner_is_deterministic_and_first_wins(world):
 
 
 class _FakeResult:
-    def __init__(self, inliers, index, launches=1, ms=1.0):
+    def __init__(self, inliers, index, launches=1, ms=1.0, search_mode=1):
         self.best_num_inliers, self.best_hyp_index, self.gpu_launches, self.kernel_ms = inliers, index, launches, ms
+        self.search_mode = search_mode
 
 
 class _FakeShardedSearch:
     """Stands in for PlaceRecognition.search: every rank owns some (inliers, index) hypotheses; the
     bound phase reports the rank's seed, the verification everything >= the incumbent."""
-    def __init__(self, hyps, seed):
-        self.hyps, self.seed, self.calls = hyps, seed, []
+    def __init__(self, hyps, seed, can_bound=True):
+        self.hyps, self.seed, self.calls, self.can_bound = hyps, seed, [], can_bound
 
     def search(self, shard_index=0, shard_count=1, bounds_only=False, incumbent_inliers=0, reuse_bounds=False, **kw):
         self.calls.append((shard_index, shard_count, bounds_only, incumbent_inliers, reuse_bounds))
+        if bounds_only and not self.can_bound:
+            # slide_pr_search: a problem without a bound phase is searched exhaustively by the first call
+            best = max(self.hyps, key=lambda h: (h[0], -h[1])) if self.hyps else (-10000, -1)
+            return _FakeResult(*best, search_mode=0), None
         if bounds_only:
             return _FakeResult(*self.seed), None
         ok = [h for h in self.hyps if h[0] >= incumbent_inliers]
@@ -104,7 +109,12 @@ def _sharded_worker(rank, world, port, out_q):
         pr = _FakeShardedSearch(hyps, seed)
         res = parallel.sharded_search(pr, rank, world)
         win = parallel.allgather_winner(res.best_hyp_index, res.best_num_inliers)
-        out_q.put((rank, pr.calls, (res.best_num_inliers, res.best_hyp_index, res.gpu_launches), (win.inliers, win.hyp_index, win.rank)))
+        # the same shards when the problem has no bound phase (e.g. disjoint label sets: every count is 0)
+        pr0 = _FakeShardedSearch([[(0, 8)], [(0, 2)]][rank], None, can_bound=False)
+        res0 = parallel.sharded_search(pr0, rank, world)
+        win0 = parallel.allgather_winner(res0.best_hyp_index, res0.best_num_inliers)
+        out_q.put((rank, pr.calls, (res.best_num_inliers, res.best_hyp_index, res.gpu_launches), (win.inliers, win.hyp_index, win.rank),
+                   pr0.calls, (win0.inliers, win0.hyp_index, win0.rank)))
     finally:
         dist.destroy_process_group()
 
@@ -123,9 +133,11 @@ def test_two_phase_sharded_search_shares_the_incumbent():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, calls, local, win in results:
+    for rank, calls, local, win, calls0, win0 in results:
         assert calls == [(rank, world, True, 0, False), (rank, world, False, 11, True)]  # incumbent = max(9, 11)
         assert win == (30, 77, 1)                     # ties to the smallest canonical index
+        assert calls0 == [(rank, world, True, 0, False)]  # exhaustive fallback: no second call
+        assert win0 == (0, 2, 1)                      # all counts 0: the smallest canonical index wins
     assert results[0][2] == (12, 40, 2)               # rank 0 still reports its own best (>= incumbent)
     assert results[1][2] == (30, 77, 2)
 
