@@ -74,7 +74,7 @@ class TfResult(C.Structure):
 
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "slide_oracle.c")
-    newest = max(os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "slide_oracle.h")))
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("slide_oracle.c", "slide_oracle.h", "clipper_oracle.c", "clipper_oracle.h"))
     stale = any((not os.path.exists(q)) or os.path.getmtime(q) < newest for q in (_LIB_PATH, _ALT_PATH))
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B", "libslide_oracle.so", "libslide_oracle_alt.so"], check=True,
@@ -115,6 +115,9 @@ def lib():
         L.slide_oracle_match_maps_mt.argtypes = [
             C.POINTER(Params), _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double,
             C.c_longlong, C.c_longlong, _ip, _ip, C.c_int, C.POINTER(MatchResult)]
+        L.slide_oracle_match_maps_mt_counts.argtypes = [
+            C.POINTER(Params), _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double,
+            C.c_longlong, C.c_longlong, _ip, _ip, C.c_int, _ip, C.c_longlong, C.POINTER(MatchResult)]
         L.slide_oracle_score_one.argtypes = [
             C.POINTER(Params), _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, C.c_double,
             C.c_double, _ip, _ip]
@@ -188,25 +191,26 @@ def match_maps(p: Params, ref7, qry7, half_x, half_y, hyp_begin=0, hyp_end=-1,
     qi = np.full(max(n_qry, 1), -1, np.int32)
     res = MatchResult()
     counts = None
+    cp, cap = None, 0
+    if want_counts:
+        lat = enumerate_lattice(p, half_x, half_y)
+        total = 0 if lat is None else len(lat[0]) * len(lat[3])
+        end = total if hyp_end < 0 else min(hyp_end, total)
+        cap = max(end - hyp_begin, 0)
+        counts = np.full(max(cap, 1), -1, np.int32)
+        cp = counts.ctypes.data_as(_ip)
     if n_threads == 1:
-        cp, cap = None, 0
-        if want_counts:
-            lat = enumerate_lattice(p, half_x, half_y)
-            total = 0 if lat is None else len(lat[0]) * len(lat[3])
-            end = total if hyp_end < 0 else min(hyp_end, total)
-            cap = max(end - hyp_begin, 0)
-            counts = np.full(max(cap, 1), -1, np.int32)
-            cp = counts.ctypes.data_as(_ip)
         lib().slide_oracle_match_maps(C.byref(p), rp, n_ref, qp, n_qry, half_x, half_y, hyp_begin,
                                       hyp_end, ri.ctypes.data_as(_ip), qi.ctypes.data_as(_ip),
                                       cp, cap, C.byref(res))
         if counts is not None:
             counts = counts[:cap]
     else:
-        assert not want_counts
-        lib().slide_oracle_match_maps_mt(C.byref(p), rp, n_ref, qp, n_qry, half_x, half_y,
-                                         hyp_begin, hyp_end, ri.ctypes.data_as(_ip),
-                                         qi.ctypes.data_as(_ip), n_threads, C.byref(res))
+        lib().slide_oracle_match_maps_mt_counts(C.byref(p), rp, n_ref, qp, n_qry, half_x, half_y,
+                                                hyp_begin, hyp_end, ri.ctypes.data_as(_ip),
+                                                qi.ctypes.data_as(_ip), n_threads, cp, cap, C.byref(res))
+        if counts is not None:
+            counts = counts[:cap]
     k = max(res.n_matched, 0)
     return {
         "status": res.status, "best_num_inliers": res.best_num_inliers,
@@ -327,3 +331,111 @@ def estimate_tf(a2, b2):
     tf = np.zeros(9)
     lib().slide_oracle_estimate_tf(ap, bp, a2.shape[0], tf.ctypes.data_as(_dp))
     return tf.reshape(3, 3)
+
+
+# ---------------------------------------------------------------------------------------------
+# SlideGraph half: CLIPPER affinity + dense clique (oracle/clipper_oracle.c)
+# ---------------------------------------------------------------------------------------------
+ROUND_NONZERO, ROUND_DSD, ROUND_DSD_HEU = 0, 1, 2
+
+
+class ClipperParams(C.Structure):
+    """clipper_oracle_params: clipper::Params (clipper.h:28-60) + EuclideanDistance::Params."""
+    _fields_ = [("sigma", C.c_double), ("epsilon", C.c_double), ("mindist", C.c_double),
+                ("tol_u", C.c_double), ("tol_F", C.c_double), ("tol_Fop", C.c_double),
+                ("maxiniters", C.c_int), ("maxoliters", C.c_int), ("beta", C.c_double), ("maxlsiters", C.c_int),
+                ("eps", C.c_double), ("affinityeps", C.c_double), ("rescale_u0", C.c_int), ("rounding", C.c_int)]
+
+
+class ClipperSolution(C.Structure):
+    _fields_ = [("ifinal", C.c_int), ("n_nodes", C.c_int), ("score", C.c_double)]
+
+
+class ScInfo(C.Structure):
+    _fields_ = [("found", C.c_int), ("n_triangle_matches", C.c_longlong), ("n_associations", C.c_int),
+                ("nnz", C.c_longlong), ("n_inliers", C.c_int), ("score", C.c_double)]
+
+
+def clipper_params(**kw) -> ClipperParams:
+    p = ClipperParams()
+    lib().clipper_oracle_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+def _cols(D):
+    """points as columns of a dim x n matrix (Eigen's invariants::Data), handed over column-major"""
+    D = np.asarray(D, np.float64)
+    flat = np.ascontiguousarray(D.T)  # n x dim row-major == dim x n column-major
+    return flat, flat.ctypes.data_as(_dp), D.shape[0], D.shape[1]
+
+
+def clipper_all_to_all(n1, n2):
+    A = np.zeros((n1 * n2, 2), np.int32)
+    lib().clipper_oracle_all_to_all(n1, n2, A.ctypes.data_as(_ip))
+    return A
+
+
+def clipper_score_pairwise(p: ClipperParams, D1, D2, A=None):
+    """scorePairwiseConsistency (clipper.cpp:21-65).  Returns (A, M_upper)."""
+    f1, p1, dim, n1 = _cols(D1)
+    f2, p2, dim2, n2 = _cols(D2)
+    assert dim == dim2
+    A = clipper_all_to_all(n1, n2) if A is None or len(A) == 0 else np.ascontiguousarray(A, np.int32)
+    m = len(A)
+    M = np.zeros((m, m), np.float64)
+    L = lib()
+    L.clipper_oracle_score_pairwise.restype = C.c_longlong
+    L.clipper_oracle_score_pairwise(C.byref(p), p1, n1, p2, n2, dim, A.ctypes.data_as(_ip), m, M.ctypes.data_as(_dp))
+    return A, M
+
+
+def clipper_affinity_matrix(M_upper):
+    m = len(M_upper)
+    out = np.zeros((m, m), np.float64)
+    Mu = np.ascontiguousarray(M_upper, np.float64)
+    lib().clipper_oracle_affinity_matrix(Mu.ctypes.data_as(_dp), m, out.ctypes.data_as(_dp))
+    return out
+
+
+def clipper_find_dense_clique(p: ClipperParams, M_upper, u0):
+    Mu = np.ascontiguousarray(M_upper, np.float64)
+    n = len(Mu)
+    u0 = np.ascontiguousarray(u0, np.float64)
+    nodes = np.zeros(max(n, 1), np.int32)
+    u = np.zeros(max(n, 1), np.float64)
+    sol = ClipperSolution()
+    k = lib().clipper_oracle_find_dense_clique(C.byref(p), Mu.ctypes.data_as(_dp), n, u0.ctypes.data_as(_dp), C.byref(sol),
+                                               nodes.ctypes.data_as(_ip), u.ctypes.data_as(_dp))
+    return {"nodes": nodes[:k].copy(), "u": u[:n], "score": sol.score, "ifinal": sol.ifinal}
+
+
+def clipper_dsd(M_upper, S=None):
+    Mu = np.ascontiguousarray(M_upper, np.float64)
+    n = len(Mu)
+    nodes = np.zeros(max(n, 1), np.int32)
+    if S is None or len(S) == 0:
+        k = lib().clipper_oracle_dsd(Mu.ctypes.data_as(_dp), n, None, 0, nodes.ctypes.data_as(_ip))
+    else:
+        S = np.ascontiguousarray(S, np.int32)
+        k = lib().clipper_oracle_dsd(Mu.ctypes.data_as(_dp), n, S.ctypes.data_as(_ip), len(S), nodes.ctypes.data_as(_ip))
+    return nodes[:k].copy()
+
+
+def run_semantic_clipper(tris_model, tris_data, sigma, epsilon, min_num_pairs, matching_threshold, u0):
+    """semantic_clipper::run_semantic_clipper (SC.cpp:140-275) from the triangle lists on."""
+    tm, mp = _d(np.reshape(tris_model, (-1, 6)))
+    td, dp = _d(np.reshape(tris_data, (-1, 6)))
+    u0 = np.ascontiguousarray(u0, np.float64)
+    tf = np.zeros(16)
+    info = ScInfo()
+    L = lib()
+    L.clipper_oracle_run_semantic_clipper.argtypes = [_dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double,
+                                                      _dp, C.c_int, _dp, C.POINTER(ScInfo)]
+    found = L.clipper_oracle_run_semantic_clipper(mp, tm.shape[0], dp, td.shape[0], sigma, epsilon, min_num_pairs,
+                                                  matching_threshold, u0.ctypes.data_as(_dp), len(u0), tf.ctypes.data_as(_dp), C.byref(info))
+    return bool(found), tf.reshape(4, 4), {"n_triangle_matches": info.n_triangle_matches, "n_associations": info.n_associations,
+                                           "nnz": info.nnz, "n_inliers": info.n_inliers, "score": info.score}

@@ -257,6 +257,15 @@ int slide_oracle_match_maps_mt(const slide_oracle_params *p, const double *ref7,
                                long long hyp_begin, long long hyp_end, int *ref_idx_out,
                                int *qry_idx_out, int n_threads,
                                slide_oracle_match_result *res) {
+  return slide_oracle_match_maps_mt_counts(p, ref7, n_ref, qry7, n_qry, half_x, half_y, hyp_begin, hyp_end,
+                                           ref_idx_out, qry_idx_out, n_threads, NULL, 0, res);
+}
+
+int slide_oracle_match_maps_mt_counts(const slide_oracle_params *p, const double *ref7, int n_ref,
+                                      const double *qry7, int n_qry, double half_x, double half_y,
+                                      long long hyp_begin, long long hyp_end, int *ref_idx_out,
+                                      int *qry_idx_out, int n_threads, int *counts_out,
+                                      long long counts_cap, slide_oracle_match_result *res) {
   result_init(res);
   int n_yaw = 0;
   long long nt = slide_oracle_enumerate_lattice(p, half_x, half_y, NULL, NULL, NULL, 0, NULL, 0, &n_yaw);
@@ -293,6 +302,7 @@ int slide_oracle_match_maps_mt(const slide_oracle_params *p, const double *ref7,
       int cur = slide_oracle_score_one(p, ref7, n_ref, qry7, n_qry, cs[2 * a], cs[2 * a + 1],
                                        tx[t], ty[t], NULL, NULL);
       lscored++;
+      if (counts_out && (h - hb) < counts_cap) counts_out[h - hb] = cur;
       if (cur > lbest || (cur == lbest && h < lbest_h)) { lbest = cur; lbest_h = h; }
     }
 #pragma omp critical

@@ -1,0 +1,130 @@
+"""GPU parity at the FULL sizes of BASELINE.json configs 3, 4 and 5 (-m gpu), with the library's
+defaults -- no environment hooks -- so that the code paths only these sizes reach run at their real
+extents: occupancy planes too large for shared memory (row-band staging in the bound phase, rank
+tables read in place by the exact kernel), the refinement of the bounds against half-cell
+variants, 16 bit planes per bound (>= 4096 query landmarks), and the coarser fixed-point formats
+of 894 m / 1414 m maps.
+
+The oracle (all host threads) cannot search these lattices completely (config 3: 5e8 hypotheses of
+4e8 pair tests each), so it checks
+  * EVERY per-hypothesis count of slices of the lattice: around the winner, in the first ring and
+    in the outermost ring (exact counts bit-identical; upper bounds of the bound phase dominate),
+  * the winner of the default (bound-and-verify) search: its inlier count and its correspondences
+    against the oracle's single-hypothesis scorer (PR.cpp:246-357),
+and the GPU checks itself where the oracle cannot: the exhaustive search (every hypothesis verified
+exactly) must select the same winner as the default search, and the planted SE(2) offset of the
+synthetic scene must be recovered.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from slide_slam_b200 import synth
+from slide_slam_b200.place_recognition import PlaceRecognition
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(match_xy_step_size=0.5, yaw_step_deg=5.0, match_threshold=0.5, match_threshold_dimension=1.0,
+          ignore_dimension=0, min_num_inliers=15)
+ROS = {"search_xy_step_size": 0.5, "search_yaw_step_size_degrees": 5.0, "match_threshold_position": 0.5,
+       "match_threshold_dimension": 1.0, "ignore_dimension": 0, "min_num_inliers": 15}
+
+
+def _shifted(ref, qry, info):
+    sref, sqry = ref.copy(), qry.copy()
+    sref[:, 1:3] -= np.array(info.centroid_ref[:])
+    sqry[:, 1:3] -= np.array(info.centroid_qry[:])
+    return sref, sqry
+
+
+def _check_winner(op, sref, sqry, info, ri, qi):
+    R = np.array(info.R_t[:]).reshape(3, 3)
+    n, ori, oqi = O.score_one(op, sref, sqry, R[0, 0], R[1, 0], R[0, 2], R[1, 2])
+    assert n == info.best_num_inliers == len(ri)
+    assert ori.tolist() == ri.tolist() and oqi.tolist() == qi.tolist()
+
+
+def _check_slices(pr, op, sref, sqry, info, half_width, best):
+    """every count of three slices of translations: around the winner, first ring, outermost ring"""
+    ny = info.match.n_yaw
+    nt = info.match.n_translations
+    t_win = info.match.best_hyp_index // ny
+    edge = max(2, half_width // 2)
+    slices = [(max(t_win - half_width, 0), min(t_win + half_width + 1, nt)), (0, edge), (nt - edge, nt)]
+    pr.prepare(sref, sqry, info.half_x, info.half_y)
+    for tb, te in slices:
+        want = O.match_maps(op, sref, sqry, info.half_x, info.half_y, tb * ny, te * ny, want_counts=True, n_threads=-1)
+        res, got = pr.search(tb, te, want_counts=True)
+        assert got.shape == want["counts"].shape
+        assert np.array_equal(got, want["counts"]), f"slice [{tb}, {te})"
+        assert int(got.max()) <= best
+        assert (res.best_num_inliers, res.best_hyp_index) == (want["best_num_inliers"], want["best_hyp_index"])
+        _, bound = pr.search(tb, te, want_counts=True, bounds_only=True)
+        assert (bound >= got).all(), f"slice [{tb}, {te}): an upper bound is below the exact count"
+    return slices
+
+
+def test_config3_20000_landmarks_full_size():
+    ref, qry, truth = synth.config_pair(3)
+    assert len(ref) == len(qry) == 20000
+    pr = PlaceRecognition(ROS)
+    found, xyz_yaw, tf, info, ri, qi = pr.findTransformation(ref, qry)
+    assert found and info.match.search_mode == 1          # the default bound-and-verify search
+    assert info.match.hypotheses_scored > 4e8 and info.match.n_yaw == 73
+    assert abs(np.angle(np.exp(1j * (xyz_yaw[3] - truth["yaw"])))) < 0.02
+    op = O.make_params(**KW)
+    sref, sqry = _shifted(ref, qry, info)
+    _check_winner(op, sref, sqry, info, ri, qi)
+    best = (info.best_num_inliers, info.match.best_hyp_index)
+    _check_slices(pr, op, sref, sqry, info, 2, best[0])
+    # every hypothesis verified exactly (global-table exact kernel at full size): same winner
+    pr.prepare(sref, sqry, info.half_x, info.half_y)
+    res_x, _ = pr.search(exhaustive=True)
+    assert res_x.search_mode == 0 and (res_x.best_num_inliers, res_x.best_hyp_index) == best
+    # sharded over 8: the merge of the shards' winners is the winner
+    got = []
+    for r in range(8):
+        res, _ = pr.search(shard_index=r, shard_count=8)
+        got.append((res.best_num_inliers, -res.best_hyp_index))
+    assert max(got) == (best[0], -best[1])
+    pr.close()
+
+
+def test_config4_5000_landmark_pairs_full_size():
+    maps = synth.config_robots(8, 5000)
+    op = O.make_params(**KW)
+    pr = PlaceRecognition(ROS)
+    n_found = 0
+    for r, q in ((0, 1), (3, 4), (0, 4)):   # two neighbouring pairs (~30 % overlap) and one without overlap
+        found, xyz_yaw, tf, info, ri, qi = pr.findTransformation(maps[r], maps[q])
+        n_found += int(found)
+        assert info.match.search_mode == 1
+        sref, sqry = _shifted(maps[r], maps[q], info)
+        _check_winner(op, sref, sqry, info, ri, qi)
+        best = (info.best_num_inliers, info.match.best_hyp_index)
+        _check_slices(pr, op, sref, sqry, info, 6 if (r, q) == (0, 1) else 2, best[0])
+        pr.prepare(sref, sqry, info.half_x, info.half_y)
+        res_x, _ = pr.search(exhaustive=True)
+        assert (res_x.best_num_inliers, res_x.best_hyp_index) == best
+    assert n_found >= 2
+    pr.close()
+
+
+def test_config5_streaming_queries_against_50000_landmarks_full_size():
+    big, queries = synth.config_stream(50000, n_queries=3, n_sub=300)
+    op = O.make_params(**KW)
+    pr = PlaceRecognition(ROS)
+    for k, q in enumerate(queries):
+        found, xyz_yaw, tf, info, ri, qi = pr.findTransformation(big, q)
+        assert found and info.match.search_mode == 1
+        assert bool(info.match.reuse & 2) == (k > 0)      # the 50000-landmark index is built once
+        assert info.match.hypotheses_scored > 5e8
+        sref, sqry = _shifted(big, q, info)
+        _check_winner(op, sref, sqry, info, ri, qi)
+        best = (info.best_num_inliers, info.match.best_hyp_index)
+        if k < 2:
+            _check_slices(pr, op, sref, sqry, info, 6, best[0])
+            pr.prepare(sref, sqry, info.half_x, info.half_y)
+            res_x, _ = pr.search(exhaustive=True)
+            assert (res_x.best_num_inliers, res_x.best_hyp_index) == best
+    pr.close()
