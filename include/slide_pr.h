@@ -245,6 +245,57 @@ int slide_pr_triangle_hypotheses(const double *tris_model6, const double *tris_d
 int slide_pr_score_hypotheses(slide_pr_handle *h, const double *hyps4, int64_t n,
                               int32_t *counts_out, slide_pr_match_result *out);
 
+/* ---- SlideGraph: CLIPPER affinity scoring + dense-clique solver (clipper.cpp) ---------------- */
+enum { SLIDE_CLIPPER_ROUND_NONZERO = 0, SLIDE_CLIPPER_ROUND_DSD = 1, SLIDE_CLIPPER_ROUND_DSD_HEU = 2 };  /* clipper.h:50 */
+
+/* clipper::Params (clipper.h:28-60) + invariants::EuclideanDistance::Params (euclidean_distance.h:27-30) */
+typedef struct slide_clipper_params {
+  double sigma;        /* 0.01  spread of the exponential kernel */
+  double epsilon;      /* 0.06  bound on the consistency score */
+  double mindist;      /* 0     minimum distance between points of one dataset */
+  double tol_u, tol_F, tol_Fop;   /* 1e-8, 1e-9, 1e-10 */
+  int32_t maxiniters, maxoliters; /* 200, 1000 */
+  double beta;         /* 0.25 */
+  int32_t maxlsiters;  /* 99 */
+  double eps;          /* 1e-9 */
+  double affinityeps;  /* 1e-4 */
+  int32_t rescale_u0;  /* 1 */
+  int32_t rounding;    /* SLIDE_CLIPPER_ROUND_DSD_HEU */
+} slide_clipper_params;
+
+typedef struct slide_clipper_solution {   /* clipper::Solution (clipper.h:65-73) */
+  int32_t n_nodes;     /* entries written to nodes_out */
+  int32_t ifinal;      /* outer iterations */
+  double  score;       /* objective value F */
+  double  d;           /* final homotopy parameter */
+  int64_t line_search_steps;
+  float   kernel_ms;   /* device time of the persistent solver kernel */
+  int32_t reserved;
+} slide_clipper_solution;
+
+void slide_clipper_default_params(slide_clipper_params *p);
+
+/* CLIPPER::scorePairwiseConsistency (clipper.h:93-95, clipper.cpp:21-65) with the EuclideanDistance
+ * invariant (euclidean_distance.cpp:13-30).  D1 / D2: dim x n1 / dim x n2, column-major -- the memory
+ * of the reference's Eigen::MatrixXd arguments; dim <= 3.  A: m x 2 row-major associations, or NULL
+ * (m ignored) for the all-to-all hypothesis.  The affinity matrix stays on the device in CSR form;
+ * *nnz_upper receives the non-zeros of the reference's upper-triangular M_. */
+int slide_pr_clipper_score_pairwise_consistency(slide_pr_handle *h, const slide_clipper_params *p, const double *D1, int32_t n1,
+                                                const double *D2, int32_t n2, int32_t dim, const int32_t *A, int32_t m,
+                                                int64_t *nnz_upper);
+/* CLIPPER::getInitialAssociations (clipper.cpp:107-110): returns m; writes min(m, cap) rows */
+int32_t slide_pr_clipper_get_initial_associations(slide_pr_handle *h, int32_t *A_out, int32_t cap);
+/* CLIPPER::getAffinityMatrix (clipper.cpp:121-126): dense m x m row-major, symmetric, identity diagonal */
+int slide_pr_clipper_get_affinity_matrix(slide_pr_handle *h, double *M_out, int64_t cap);
+/* the same matrix as the device holds it: symmetric CSR without the diagonal; row_ptr has m + 1 entries.
+ * col / val may be NULL to query sizes (row_ptr[m] = entries). */
+int slide_pr_clipper_get_affinity_csr(slide_pr_handle *h, int64_t *row_ptr, int32_t *col, double *val, int64_t cap);
+/* CLIPPER::solve + findDenseClique (clipper.cpp:69-78, 172-323).  u0: m doubles, or NULL for a
+ * deterministic stand-in of the reference's std::random_device vector (utils.cpp:22-29): U[0,1)
+ * from a splitmix64 stream seeded with `seed`.  nodes_out: capacity cap; u_out (optional): m. */
+int slide_pr_clipper_solve(slide_pr_handle *h, const slide_clipper_params *p, const double *u0, uint64_t seed,
+                           int32_t *nodes_out, int32_t cap, slide_clipper_solution *sol, double *u_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,9 @@ EXPORTS = [
     "slide_pr_get_xyz_yaw_from_tf", "slide_pr_find_transformation_batch", "slide_pr_pack_record",
     "slide_pr_merge_records", "slide_pr_match_triangles", "slide_pr_score_hypotheses",
     "slide_pr_match_triangles_labeled", "slide_pr_estimate_tf", "slide_pr_triangle_hypotheses",
+    "slide_clipper_default_params", "slide_pr_clipper_score_pairwise_consistency",
+    "slide_pr_clipper_get_initial_associations", "slide_pr_clipper_get_affinity_matrix",
+    "slide_pr_clipper_get_affinity_csr", "slide_pr_clipper_solve",
 ]
 
 
@@ -119,8 +122,22 @@ class TopkRecord(C.Structure):
     _fields_ = [("hyp_index", C.c_int64), ("inliers", C.c_int32), ("rank", C.c_int32)]
 
 
+class ClipperParams(C.Structure):
+    """slide_clipper_params: clipper::Params (clipper.h:28-60) + EuclideanDistance::Params."""
+    _fields_ = [("sigma", C.c_double), ("epsilon", C.c_double), ("mindist", C.c_double),
+                ("tol_u", C.c_double), ("tol_F", C.c_double), ("tol_Fop", C.c_double),
+                ("maxiniters", C.c_int32), ("maxoliters", C.c_int32), ("beta", C.c_double), ("maxlsiters", C.c_int32),
+                ("eps", C.c_double), ("affinityeps", C.c_double), ("rescale_u0", C.c_int32), ("rounding", C.c_int32)]
+
+
+class ClipperSolution(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("ifinal", C.c_int32), ("score", C.c_double), ("d", C.c_double),
+                ("line_search_steps", C.c_int64), ("kernel_ms", C.c_float), ("reserved", C.c_int32)]
+
+
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
 _lib = None
 
 
@@ -175,6 +192,15 @@ def lib():
     L.slide_pr_estimate_tf.argtypes = [_dp, _dp, C.c_int32, _dp]
     L.slide_pr_triangle_hypotheses.argtypes = [_dp, _dp, _ip, _ip, _ip, _ip, C.c_int64, _dp]
     L.slide_pr_score_hypotheses.argtypes = [C.c_void_p, _dp, C.c_int64, _ip, C.POINTER(MatchResult)]
+    L.slide_clipper_default_params.argtypes = [C.POINTER(ClipperParams)]
+    L.slide_pr_clipper_score_pairwise_consistency.argtypes = [C.c_void_p, C.POINTER(ClipperParams), _dp, C.c_int32, _dp, C.c_int32,
+                                                              C.c_int32, _ip, C.c_int32, _lp]
+    L.slide_pr_clipper_get_initial_associations.restype = C.c_int32
+    L.slide_pr_clipper_get_initial_associations.argtypes = [C.c_void_p, _ip, C.c_int32]
+    L.slide_pr_clipper_get_affinity_matrix.argtypes = [C.c_void_p, _dp, C.c_int64]
+    L.slide_pr_clipper_get_affinity_csr.argtypes = [C.c_void_p, _lp, _ip, _dp, C.c_int64]
+    L.slide_pr_clipper_solve.argtypes = [C.c_void_p, C.POINTER(ClipperParams), _dp, C.c_uint64, _ip, C.c_int32,
+                                         C.POINTER(ClipperSolution), _dp]
     _lib = L
     return L
 

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/slide_pr.h"
+#include "spr_clipper.h"
 #include "spr_host.h"
 #include "spr_kernels.h"
 
@@ -182,6 +183,7 @@ struct slide_pr_handle {
   DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_rank16, d_rank16b, d_rowrank, d_rowrankb, d_gcnt, d_cellref, d_cellrefb, d_cellbase, d_cellbaseb, d_reftab, d_refbase,
       d_cand, d_cand1, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ubplanes, d_itemub, d_seed, d_canditems, d_candcount, d_vbitmap, d_labof, d_dgitems, d_dgcount, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
   SprView V{};
+  SprClipper *clipper = nullptr;       // SlideGraph half: device-resident CLIPPER problem (created on first use)
   spr::uvec<int32_t> h_match;          // page-locked D2H targets
   spr::uvec<unsigned long long> h_scalars;
 };
@@ -307,6 +309,7 @@ void slide_pr_destroy(slide_pr_handle *h) {
                     &h->d_ubplanes, &h->d_itemub, &h->d_seed, &h->d_canditems, &h->d_candcount,
                     &h->d_vbitmap, &h->d_labof, &h->d_dgitems, &h->d_dgcount})
     b->release();
+  spr_clipper_destroy(h->clipper);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_copy) cudaEventDestroy(h->ev_copy);
@@ -1287,6 +1290,94 @@ int slide_pr_score_hypotheses(slide_pr_handle *h, const double *hyps4, int64_t n
     out->R_t[3] = hp[1]; out->R_t[4] = hp[0];  out->R_t[5] = hp[3];
   }
   return SLIDE_PR_OK;
+}
+
+// ---- SlideGraph: CLIPPER ------------------------------------------------------------------------
+void slide_clipper_default_params(slide_clipper_params *p) {  // clipper.h:28-60, euclidean_distance.h:27-30
+  std::memset(p, 0, sizeof(*p));
+  p->sigma = 0.01; p->epsilon = 0.06; p->mindist = 0;
+  p->tol_u = 1e-8; p->tol_F = 1e-9; p->tol_Fop = 1e-10;
+  p->maxiniters = 200; p->maxoliters = 1000;
+  p->beta = 0.25; p->maxlsiters = 99;
+  p->eps = 1e-9; p->affinityeps = 1e-4;
+  p->rescale_u0 = 1;
+  p->rounding = SLIDE_CLIPPER_ROUND_DSD_HEU;
+}
+
+static SprClipper *clipper_of(slide_pr_handle *h) {
+  if (!h->clipper) h->clipper = spr_clipper_create();
+  return h->clipper;
+}
+
+int slide_pr_clipper_score_pairwise_consistency(slide_pr_handle *h, const slide_clipper_params *p, const double *D1, int32_t n1,
+                                                const double *D2, int32_t n2, int32_t dim, const int32_t *A, int32_t m,
+                                                int64_t *nnz_upper) {
+  if (!h || !p || (n1 > 0 && !D1) || (n2 > 0 && !D2)) return SLIDE_PR_ERR_INVALID;
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  long long nnz = 0;
+  const int rc = spr_clipper_score(clipper_of(h), *p, D1, n1, D2, n2, dim, A, m, false, h->sm_count, h->stream, &nnz, nullptr, h->err);
+  if (nnz_upper) *nnz_upper = nnz;
+  return rc;
+}
+
+int32_t slide_pr_clipper_get_initial_associations(slide_pr_handle *h, int32_t *A_out, int32_t cap) {
+  if (!h || !h->clipper) return 0;
+  int m = 0;
+  spr_clipper_size(h->clipper, &m, nullptr);
+  if (A_out && cap > 0) std::memcpy(A_out, spr_clipper_associations(h->clipper), sizeof(int32_t) * 2 * (size_t)std::min(m, cap));
+  return m;
+}
+
+int slide_pr_clipper_get_affinity_csr(slide_pr_handle *h, int64_t *row_ptr, int32_t *col, double *val, int64_t cap) {
+  if (!h || !row_ptr) return SLIDE_PR_ERR_INVALID;
+  if (!h->clipper) { h->err = "no pairwise consistency has been scored on this handle"; return SLIDE_PR_ERR_INVALID; }
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  return spr_clipper_get_csr(h->clipper, row_ptr, col, val, cap, h->stream, h->err);
+}
+
+int slide_pr_clipper_get_affinity_matrix(slide_pr_handle *h, double *M_out, int64_t cap) {
+  if (!h || !M_out) return SLIDE_PR_ERR_INVALID;
+  if (!h->clipper) { h->err = "no pairwise consistency has been scored on this handle"; return SLIDE_PR_ERR_INVALID; }
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  int m = 0;
+  long long nnz = 0;
+  spr_clipper_size(h->clipper, &m, &nnz);
+  if ((int64_t)m * m > cap) { h->err = "dense affinity matrix does not fit the given capacity"; return SLIDE_PR_ERR_INVALID; }
+  std::vector<int64_t> rp((size_t)m + 1);
+  std::vector<int32_t> col((size_t)std::max<long long>(nnz, 1));
+  std::vector<double> val((size_t)std::max<long long>(nnz, 1));
+  const int rc = spr_clipper_get_csr(h->clipper, rp.data(), col.data(), val.data(), nnz, h->stream, h->err);
+  if (rc != SLIDE_PR_OK) return rc;
+  std::fill(M_out, M_out + (size_t)m * m, 0.0);
+  for (int i = 0; i < m; i++) {
+    M_out[(size_t)i * m + i] = 1.0;  // + Identity (clipper.cpp:124)
+    for (int64_t k = rp[i]; k < rp[i + 1]; k++) M_out[(size_t)i * m + col[k]] = val[k];
+  }
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_clipper_solve(slide_pr_handle *h, const slide_clipper_params *p, const double *u0, uint64_t seed, int32_t *nodes_out,
+                           int32_t cap, slide_clipper_solution *sol, double *u_out) {
+  if (!h || !p || !sol) return SLIDE_PR_ERR_INVALID;
+  if (!h->clipper) { h->err = "no pairwise consistency has been scored on this handle"; return SLIDE_PR_ERR_INVALID; }
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  int m = 0;
+  spr_clipper_size(h->clipper, &m, nullptr);
+  std::vector<double> own;
+  if (!u0) {  // stand-in for utils::randvec (utils.cpp:22-29): U[0, 1) from a splitmix64 stream
+    own.resize((size_t)std::max(m, 1));
+    uint64_t x = seed;
+    for (int i = 0; i < m; i++) {
+      x += 0x9e3779b97f4a7c15ull;
+      uint64_t z = x;
+      z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+      z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+      z ^= z >> 31;
+      own[i] = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    }
+    u0 = own.data();
+  }
+  return spr_clipper_solve(h->clipper, *p, u0, h->sm_count, h->stream, nodes_out, cap, sol, u_out, h->err);
 }
 
 #pragma GCC visibility pop

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "slide_pr.h")).read()
-    declared = sorted(set(re.findall(r"\b(slide_pr_[a-z0-9_]+)\s*\(", header)))
+    declared = sorted(set(re.findall(r"\b(slide_(?:pr|clipper)_[a-z0-9_]+)\s*\(", header)))
     assert sorted(capi.EXPORTS) == declared
     lib = capi.lib()
     for name in declared:
@@ -29,6 +29,12 @@ def test_struct_layout_matches_header():
     assert C.sizeof(capi.SearchOpts) == 16 + 8 + 8 + 8 + 8 + 8 + 8
     assert C.sizeof(capi.TopkRecord) == 16
     assert C.sizeof(capi.TfResult) == 16 + 72 + 32 + 128 + 32 + 24 + C.sizeof(capi.MatchResult)
+    assert C.sizeof(capi.ClipperParams) == 6 * 8 + 8 + 8 + 8 + 16 + 8      # ints padded to the doubles' alignment
+    assert C.sizeof(capi.ClipperSolution) == 8 + 8 + 8 + 8 + 8
+    p = capi.ClipperParams()
+    capi.lib().slide_clipper_default_params(C.byref(p))                      # clipper.h:28-60, euclidean_distance.h:27-30
+    assert (p.sigma, p.epsilon, p.mindist, p.tol_u, p.tol_F, p.maxiniters, p.maxoliters, p.beta, p.maxlsiters, p.eps,
+            p.affinityeps, p.rescale_u0, p.rounding) == (0.01, 0.06, 0.0, 1e-8, 1e-9, 200, 1000, 0.25, 99, 1e-9, 1e-4, 1, 2)
 
 
 def test_default_params_are_the_reference_defaults():

@@ -13,7 +13,8 @@ The oracle (all host threads) cannot search these lattices completely (config 3:
     against the oracle's single-hypothesis scorer (PR.cpp:246-357),
 and the GPU checks itself where the oracle cannot: the exhaustive search (every hypothesis verified
 exactly) must select the same winner as the default search, and the planted SE(2) offset of the
-synthetic scene must be recovered.
+synthetic scene must be recovered where the score has a real peak (configs 4 and 5; config 3's
+maximum is a chance peak of the dense maps, see the test).
 """
 import numpy as np
 import pytest
@@ -71,7 +72,11 @@ def test_config3_20000_landmarks_full_size():
     found, xyz_yaw, tf, info, ri, qi = pr.findTransformation(ref, qry)
     assert found and info.match.search_mode == 1          # the default bound-and-verify search
     assert info.match.hypotheses_scored > 4e8 and info.match.n_yaw == 73
-    assert abs(np.angle(np.exp(1j * (xyz_yaw[3] - truth["yaw"])))) < 0.02
+    # No assertion on the planted offset here: with 20 000 landmarks per map a RANDOM hypothesis already
+    # collects ~270 chance inliers (0.025 landmarks/m^2 x 0.79 m^2 disc x 70 % same class x 20 000), while
+    # the 5 deg yaw lattice aligns only the ~30 shared landmarks within ~11 m of the pivot: the maximum of
+    # the reference's score (278) is a chance peak.  Parity is about reproducing that maximum exactly.
+    assert info.best_num_inliers > 200
     op = O.make_params(**KW)
     sref, sqry = _shifted(ref, qry, info)
     _check_winner(op, sref, sqry, info, ri, qi)
@@ -116,7 +121,7 @@ def test_config5_streaming_queries_against_50000_landmarks_full_size():
     pr = PlaceRecognition(ROS)
     for k, q in enumerate(queries):
         found, xyz_yaw, tf, info, ri, qi = pr.findTransformation(big, q)
-        assert found and info.match.search_mode == 1
+        assert found and info.match.search_mode == 1 and info.best_num_inliers >= 100   # a real peak: most of the 300 match
         assert bool(info.match.reuse & 2) == (k > 0)      # the 50000-landmark index is built once
         assert info.match.hypotheses_scored > 5e8
         sref, sqry = _shifted(big, q, info)
