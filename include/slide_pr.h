@@ -207,7 +207,8 @@ int  slide_pr_merge_records(const slide_pr_topk_record *recs, int32_t n);
 /* ---- SlideGraph descriptor half (semantic_clipper.cpp) ------------------------------------- */
 /* compute_triangle_diff / match_triangles (SC.cpp:49-118) on the GPU: descriptors of all
  * triangles are built once, binned by their first component, and matched; output order is the
- * reference's (model-major, data-minor).  tris: t x 6 [x0,y0,x1,y1,x2,y2].  model_idx_out /
+ * reference's (model-major, data-minor; restored by a radix sort of the match keys).  tris: t x 6
+ * [x0,y0,x1,y1,x2,y2].  model_idx_out /
  * data_idx_out / perm_out (3 ints per match per side: the sorted vertex order) have capacity
  * cap matches; returns the total match count in *n_matches (may exceed cap). */
 int slide_pr_match_triangles(slide_pr_handle *h, const double *tris_model6, int32_t t_model,
@@ -244,6 +245,26 @@ int slide_pr_triangle_hypotheses(const double *tris_model6, const double *tris_d
  * counts_out (optional, n ints).  The winner (max count, lowest index) goes to *out. */
 int slide_pr_score_hypotheses(slide_pr_handle *h, const double *hyps4, int64_t n,
                               int32_t *counts_out, slide_pr_match_result *out);
+
+/* The generator half in one call, entirely on the device: descriptors -> binning of the data
+ * triangles by their first descriptor component -> windowed matching -> radix sort into the reference's
+ * order (SC.cpp:111-118) -> one 2-D Kabsch hypothesis per match (SC.cpp:122-138) -> the MatchMaps
+ * predicate on every hypothesis (PR.cpp:272-357) -> best hypothesis (max count, lowest match index).
+ * Needs the map pair given to slide_pr_prepare.  Optional outputs (capacity cap matches each):
+ * the match list, the hypotheses (4 doubles each: c, s, x, y) and their inlier counts. */
+typedef struct slide_pr_generate_info {
+  int64_t n_matches;
+  int32_t n_triangles_model, n_triangles_data;
+  float   match_ms;    /* descriptors + binning + matching + sort (device time) */
+  float   kabsch_ms;
+  float   score_ms;
+  int32_t reserved;
+} slide_pr_generate_info;
+int slide_pr_generate_and_score(slide_pr_handle *h, const double *tris_model6, const double *labels_model3, int32_t t_model,
+                                const double *tris_data6, const double *labels_data3, int32_t t_data, double threshold,
+                                slide_pr_match_result *out, slide_pr_generate_info *info /* may be NULL */,
+                                int32_t *model_idx_out, int32_t *data_idx_out, double *hyps4_out, int32_t *counts_out,
+                                int64_t cap);
 
 /* ---- SlideGraph: CLIPPER affinity scoring + dense-clique solver (clipper.cpp) ---------------- */
 enum { SLIDE_CLIPPER_ROUND_NONZERO = 0, SLIDE_CLIPPER_ROUND_DSD = 1, SLIDE_CLIPPER_ROUND_DSD_HEU = 2 };  /* clipper.h:50 */

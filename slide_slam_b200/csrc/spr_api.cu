@@ -21,6 +21,7 @@
 
 #include "../../include/slide_pr.h"
 #include "spr_clipper.h"
+#include "spr_generate.h"
 #include "spr_host.h"
 #include "spr_kernels.h"
 
@@ -183,6 +184,7 @@ struct slide_pr_handle {
   DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_rank16, d_rank16b, d_rowrank, d_rowrankb, d_gcnt, d_cellref, d_cellrefb, d_cellbase, d_cellbaseb, d_reftab, d_refbase,
       d_cand, d_cand1, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ubplanes, d_itemub, d_seed, d_canditems, d_candcount, d_vbitmap, d_labof, d_dgitems, d_dgcount, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
   SprView V{};
+  unsigned long long gen_cap = 0;      // capacity (entries) of the generator's match-key buffer, kept across calls
   SprClipper *clipper = nullptr;       // SlideGraph half: device-resident CLIPPER problem (created on first use)
   spr::uvec<int32_t> h_match;          // page-locked D2H targets
   spr::uvec<unsigned long long> h_scalars;
@@ -1159,28 +1161,54 @@ int slide_pr_merge_records(const slide_pr_topk_record *recs, int32_t n) {
   return best;
 }
 
-int slide_pr_match_triangles_labeled(slide_pr_handle *h, const double *tris_model6, const double *labels_model3,
-                                     int32_t t_model, const double *tris_data6, const double *labels_data3,
-                                     int32_t t_data, double threshold, int32_t *model_idx_out, int32_t *data_idx_out,
-                                     int32_t *perm_model_out, int32_t *perm_data_out, int64_t cap, int64_t *n_matches) {
-  if (!h || !n_matches || t_model < 0 || t_data < 0 || cap < 0) return SLIDE_PR_ERR_INVALID;
-  if ((t_model > 0 && !tris_model6) || (t_data > 0 && !tris_data6)) { h->err = "null triangle array"; return SLIDE_PR_ERR_INVALID; }
-  if ((labels_model3 == nullptr) != (labels_data3 == nullptr)) { h->err = "labels must be given for both maps or for none"; return SLIDE_PR_ERR_INVALID; }
-  *n_matches = 0;
-  if (t_model == 0 || t_data == 0) return SLIDE_PR_OK;
+// Device-side generator front (spr_generate.cu): descriptors, binning of the data triangles by their
+// first descriptor component, windowed matching, radix sort back into the reference's order.  Leaves on
+// the device (h->d_tri arena): both triangle lists, descriptors, vertex permutations, class signatures and
+// the sorted match list as (model_idx, data_idx) arrays.
+struct GenDevice {
+  const double *tris_m, *tris_d;
+  const int32_t *perm_m, *perm_d;
+  int32_t *model_idx, *data_idx;
+  long long n_matches;
+  float match_ms;
+};
+
+static int gen_match_on_device(slide_pr_handle *h, const double *tris_model6, const double *labels_model3, int32_t t_model,
+                               const double *tris_data6, const double *labels_data3, int32_t t_data, double threshold,
+                               GenDevice *G) {
+  std::memset(G, 0, sizeof(*G));
   const bool labeled = labels_model3 != nullptr;
-  SPR_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
-  DevBuf &b = h->d_tri;
-  // layout: tris_m | tris_d | labels_m | labels_d | desc_m | desc_d | sig_m | sig_d | perm_m | perm_d | counts | offsets | total
   const size_t tm = (size_t)t_model, td = (size_t)t_data;
+  // bins: width >= the matching window, at most 2^20 of them over the data descriptors' possible range
+  // (a vertex is never farther from its triangle's centroid than the bounding box' diagonal)
+  double lo[2] = {HUGE_VAL, HUGE_VAL}, hi[2] = {-HUGE_VAL, -HUGE_VAL};
+  for (size_t k = 0; k < td * 3; k++)
+    for (int c = 0; c < 2; c++) {
+      const double v = tris_data6[2 * k + c];
+      if (v < lo[c]) lo[c] = v;
+      if (v > hi[c]) hi[c] = v;
+    }
+  double diag = std::hypot(hi[0] - lo[0], hi[1] - lo[1]);
+  if (!std::isfinite(diag)) diag = 0.0;  // non-finite coordinates give NaN descriptors, which never match
+  const bool can_match = threshold > 0 && threshold == threshold;
+  const double window = can_match && std::isfinite(threshold) ? threshold * (1.0 + 1e-9) + 1e-300 : HUGE_VAL;
+  const double Tstar = std::isinf(threshold) && threshold > 0 ? HUGE_VAL : spr::sqrt_threshold(threshold);
+  double width = std::isfinite(window) ? window : diag + 1.0;
+  if (diag / width > 1048000.0) width = diag / 1048000.0;
+  if (!(width > 0)) width = 1.0;
+  const uint32_t n_bins = (uint32_t)std::min(1048576.0, std::floor(diag / width) + 2.0);
+  const double inv_w = 1.0 / width;
+  // arena
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_tm = take(tm * 6 * 8), o_td = take(td * 6 * 8), o_lm = take(tm * 3 * 8), o_ld = take(td * 3 * 8);
   const size_t o_dm = take(tm * 3 * 8), o_dd = take(td * 3 * 8), o_sm = take(tm * 3 * 8), o_sd = take(td * 3 * 8);
-  const size_t o_pm = take(tm * 3 * 4), o_pd = take(td * 3 * 4), o_cnt = take(tm * 8), o_off = take(tm * 8), o_tot = take(8);
-  SPR_CUDA(h, b.ensure(off));
-  char *base = b.as<char>();
+  const size_t o_pm = take(tm * 3 * 4), o_pd = take(td * 3 * 4);
+  const size_t o_bs = take(((size_t)n_bins + 2) * 4), o_bf = take(((size_t)n_bins + 1) * 4), o_bn = take(spr_gen_binned_bytes(t_data));
+  const size_t o_tot = take(8);
+  SPR_CUDA(h, h->d_tri.ensure(off));
+  char *base = h->d_tri.as<char>();
   SPR_CUDA(h, cudaMemcpyAsync(base + o_tm, tris_model6, tm * 6 * 8, cudaMemcpyHostToDevice, st));
   SPR_CUDA(h, cudaMemcpyAsync(base + o_td, tris_data6, td * 6 * 8, cudaMemcpyHostToDevice, st));
   if (labeled) {
@@ -1190,29 +1218,65 @@ int slide_pr_match_triangles_labeled(slide_pr_handle *h, const double *tris_mode
   double *dm = (double *)(base + o_dm), *dd = (double *)(base + o_dd);
   double *sm = labeled ? (double *)(base + o_sm) : nullptr, *sd = labeled ? (double *)(base + o_sd) : nullptr;
   int32_t *pm = (int32_t *)(base + o_pm), *pd = (int32_t *)(base + o_pd);
-  unsigned long long *cnt = (unsigned long long *)(base + o_cnt), *offs = (unsigned long long *)(base + o_off),
-                     *tot = (unsigned long long *)(base + o_tot);
+  unsigned long long *tot = (unsigned long long *)(base + o_tot);
+  SPR_CUDA(h, cudaEventRecord(h->ev0, st));
   SPR_CUDA(h, spr_launch_tri_desc((const double *)(base + o_tm), labeled ? (const double *)(base + o_lm) : nullptr, t_model, dm, pm, sm, st));
   SPR_CUDA(h, spr_launch_tri_desc((const double *)(base + o_td), labeled ? (const double *)(base + o_ld) : nullptr, t_data, dd, pd, sd, st));
-  SPR_CUDA(h, spr_launch_tri_match(dm, t_model, dd, t_data, sm, sd, threshold, cnt, offs, tot, nullptr, nullptr, 0, false,
-                                   h->sm_count, st));
+  SPR_CUDA(h, spr_launch_gen_bin(dd, t_data, inv_w, n_bins, (uint32_t *)(base + o_bs), (uint32_t *)(base + o_bf), base + o_bn, st));
+  // match keys: capacity grows on overflow (one retry with the exact count)
+  unsigned long long cap = std::max<unsigned long long>(h->gen_cap, 1ull << 16);
   unsigned long long total = 0;
-  SPR_CUDA(h, cudaMemcpyAsync(&total, tot, 8, cudaMemcpyDeviceToHost, st));
-  SPR_CUDA(h, cudaStreamSynchronize(st));
-  *n_matches = (int64_t)total;
-  const int64_t n_out = std::min<int64_t>((int64_t)total, cap);
+  for (int attempt = 0; attempt < 2; attempt++) {
+    SPR_CUDA(h, h->d_tri_out.ensure((size_t)cap * 8 * 3 + spr_radix_sort_hist_words((long long)cap) * 4 + 1024));
+    SPR_CUDA(h, cudaMemsetAsync(tot, 0, 8, st));
+    SPR_CUDA(h, spr_launch_gen_match(dm, t_model, base + o_bn, (const uint32_t *)(base + o_bs), n_bins, inv_w, window, Tstar, sm, sd,
+                                     t_data, h->d_tri_out.as<unsigned long long>(), cap, tot, h->sm_count, st));
+    SPR_CUDA(h, cudaMemcpyAsync(&total, tot, 8, cudaMemcpyDeviceToHost, st));
+    SPR_CUDA(h, cudaStreamSynchronize(st));
+    if (total <= cap) break;
+    cap = total + total / 8 + 1024;
+  }
+  h->gen_cap = cap;
+  unsigned long long *keys = h->d_tri_out.as<unsigned long long>(), *tmp = keys + cap;
+  int32_t *mi = (int32_t *)(tmp + cap), *di = mi + cap;
+  uint32_t *hist = (uint32_t *)(di + cap);
+  int bits = 1;
+  while (bits < 64 && ((unsigned long long)t_model * (unsigned long long)std::max(t_data, 1)) >> bits) bits++;
+  SPR_CUDA(h, spr_radix_sort_u64(keys, tmp, (long long)total, bits, hist, st));
+  SPR_CUDA(h, spr_launch_gen_unpack(keys, (long long)total, t_data, mi, di, st));
+  SPR_CUDA(h, cudaEventRecord(h->ev1, st));
+  G->tris_m = (const double *)(base + o_tm); G->tris_d = (const double *)(base + o_td);
+  G->perm_m = pm; G->perm_d = pd;
+  G->model_idx = mi; G->data_idx = di;
+  G->n_matches = (long long)total;
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_match_triangles_labeled(slide_pr_handle *h, const double *tris_model6, const double *labels_model3,
+                                     int32_t t_model, const double *tris_data6, const double *labels_data3,
+                                     int32_t t_data, double threshold, int32_t *model_idx_out, int32_t *data_idx_out,
+                                     int32_t *perm_model_out, int32_t *perm_data_out, int64_t cap, int64_t *n_matches) {
+  if (!h || !n_matches || t_model < 0 || t_data < 0 || cap < 0) return SLIDE_PR_ERR_INVALID;
+  if ((t_model > 0 && !tris_model6) || (t_data > 0 && !tris_data6)) { h->err = "null triangle array"; return SLIDE_PR_ERR_INVALID; }
+  if ((labels_model3 == nullptr) != (labels_data3 == nullptr)) { h->err = "labels must be given for both maps or for none"; return SLIDE_PR_ERR_INVALID; }
+  *n_matches = 0;
+  if (t_model == 0 || t_data == 0) return SLIDE_PR_OK;
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  GenDevice G;
+  const int rc = gen_match_on_device(h, tris_model6, labels_model3, t_model, tris_data6, labels_data3, t_data, threshold, &G);
+  if (rc != SLIDE_PR_OK) return rc;
+  *n_matches = (int64_t)G.n_matches;
+  const int64_t n_out = std::min<int64_t>((int64_t)G.n_matches, cap);
   if (n_out > 0 && model_idx_out && data_idx_out) {
-    SPR_CUDA(h, h->d_tri_out.ensure((size_t)n_out * 2 * sizeof(int32_t)));
-    int32_t *mi = h->d_tri_out.as<int32_t>(), *di = mi + n_out;
-    SPR_CUDA(h, spr_launch_tri_match(dm, t_model, dd, t_data, sm, sd, threshold, cnt, offs, tot, mi, di, n_out, true,
-                                     h->sm_count, st));
-    SPR_CUDA(h, cudaMemcpyAsync(model_idx_out, mi, (size_t)n_out * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    SPR_CUDA(h, cudaMemcpyAsync(data_idx_out, di, (size_t)n_out * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    const size_t tm = (size_t)t_model, td = (size_t)t_data;
+    SPR_CUDA(h, cudaMemcpyAsync(model_idx_out, G.model_idx, (size_t)n_out * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SPR_CUDA(h, cudaMemcpyAsync(data_idx_out, G.data_idx, (size_t)n_out * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     std::vector<int32_t> hpm, hpd;
     if (perm_model_out || perm_data_out) {
       hpm.resize(tm * 3); hpd.resize(td * 3);
-      SPR_CUDA(h, cudaMemcpyAsync(hpm.data(), pm, tm * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-      SPR_CUDA(h, cudaMemcpyAsync(hpd.data(), pd, td * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      SPR_CUDA(h, cudaMemcpyAsync(hpm.data(), G.perm_m, tm * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      SPR_CUDA(h, cudaMemcpyAsync(hpd.data(), G.perm_d, td * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     }
     SPR_CUDA(h, cudaStreamSynchronize(st));
     for (int64_t k = 0; k < n_out; k++)
@@ -1220,6 +1284,72 @@ int slide_pr_match_triangles_labeled(slide_pr_handle *h, const double *tris_mode
         if (perm_model_out) perm_model_out[3 * k + v] = hpm[3 * (size_t)model_idx_out[k] + v];
         if (perm_data_out) perm_data_out[3 * k + v] = hpd[3 * (size_t)data_idx_out[k] + v];
       }
+  }
+  return SLIDE_PR_OK;
+}
+
+// The whole generator half on the device: matched triangles -> one 2-D Kabsch hypothesis per match ->
+// MatchMaps predicate on every hypothesis (spr_score_list_kernel) -> best hypothesis.  Needs a
+// slide_pr_prepare'd map pair (the maps the triangles were built from).
+int slide_pr_generate_and_score(slide_pr_handle *h, const double *tris_model6, const double *labels_model3, int32_t t_model,
+                                const double *tris_data6, const double *labels_data3, int32_t t_data, double threshold,
+                                slide_pr_match_result *out, slide_pr_generate_info *info, int32_t *model_idx_out,
+                                int32_t *data_idx_out, double *hyps4_out, int32_t *counts_out, int64_t cap) {
+  if (!h || !out || t_model < 0 || t_data < 0 || cap < 0) return SLIDE_PR_ERR_INVALID;
+  if (!h->prepared) { h->err = "slide_pr_generate_and_score before slide_pr_prepare"; return SLIDE_PR_ERR_INVALID; }
+  if ((t_model > 0 && !tris_model6) || (t_data > 0 && !tris_data6)) { h->err = "null triangle array"; return SLIDE_PR_ERR_INVALID; }
+  if ((labels_model3 == nullptr) != (labels_data3 == nullptr)) { h->err = "labels must be given for both maps or for none"; return SLIDE_PR_ERR_INVALID; }
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  fill_result_header(h, out);
+  out->status = SLIDE_PR_OK;
+  slide_pr_generate_info local{}, *I = info ? info : &local;
+  std::memset(I, 0, sizeof(*I));
+  if (t_model == 0 || t_data == 0) return SLIDE_PR_OK;
+  if (h->ranks_pending) { const int rrc = finish_ranks(h, st); if (rrc != SLIDE_PR_OK) return rrc; }
+  GenDevice G;
+  int rc = gen_match_on_device(h, tris_model6, labels_model3, t_model, tris_data6, labels_data3, t_data, threshold, &G);
+  if (rc != SLIDE_PR_OK) return rc;
+  const long long n = G.n_matches;
+  I->n_matches = n;
+  I->n_triangles_model = t_model; I->n_triangles_data = t_data;
+  if (n == 0) { SPR_CUDA(h, cudaStreamSynchronize(st)); SPR_CUDA(h, cudaEventElapsedTime(&I->match_ms, h->ev0, h->ev1)); return SLIDE_PR_OK; }
+  SPR_CUDA(h, h->d_hyps.ensure((size_t)n * 4 * sizeof(double)));
+  SPR_CUDA(h, h->d_counts.ensure((size_t)n * sizeof(int32_t)));
+  SPR_CUDA(h, cudaMemsetAsync(h->d_best.p, 0, sizeof(unsigned long long), st));
+  cudaEvent_t e2, e3;
+  SPR_CUDA(h, cudaEventCreate(&e2)); SPR_CUDA(h, cudaEventCreate(&e3));
+  SPR_CUDA(h, spr_launch_gen_kabsch(G.tris_m, G.tris_d, G.perm_m, G.perm_d, G.model_idx, G.data_idx, n, h->d_hyps.as<double>(),
+                                    nullptr, nullptr, st));
+  SPR_CUDA(h, cudaEventRecord(e2, st));
+  SPR_CUDA(h, spr_launch_score_list(h->V, h->d_hyps.as<double>(), n, h->d_counts.as<int32_t>(), h->d_best.as<unsigned long long>(),
+                                    h->sm_count, st));
+  SPR_CUDA(h, cudaEventRecord(e3, st));
+  if (h->h_scalars.size() < 8) h->h_scalars.assign(8, 0ull);
+  SPR_CUDA(h, cudaMemcpyAsync(h->h_scalars.data(), h->d_best.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  const int64_t n_out = std::min<int64_t>(n, cap);
+  if (n_out > 0) {
+    if (model_idx_out) SPR_CUDA(h, cudaMemcpyAsync(model_idx_out, G.model_idx, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
+    if (data_idx_out) SPR_CUDA(h, cudaMemcpyAsync(data_idx_out, G.data_idx, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
+    if (hyps4_out) SPR_CUDA(h, cudaMemcpyAsync(hyps4_out, h->d_hyps.p, (size_t)n_out * 32, cudaMemcpyDeviceToHost, st));
+    if (counts_out) SPR_CUDA(h, cudaMemcpyAsync(counts_out, h->d_counts.p, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
+  }
+  SPR_CUDA(h, cudaStreamSynchronize(st));
+  SPR_CUDA(h, cudaEventElapsedTime(&I->match_ms, h->ev0, h->ev1));
+  SPR_CUDA(h, cudaEventElapsedTime(&I->kabsch_ms, h->ev1, e2));
+  SPR_CUDA(h, cudaEventElapsedTime(&I->score_ms, e2, e3));
+  cudaEventDestroy(e2); cudaEventDestroy(e3);
+  const unsigned long long key = h->h_scalars[0];
+  out->kernel_ms = I->match_ms + I->kabsch_ms + I->score_ms;
+  out->gpu_launches = 2 + 3 + 1 + 3 * ((64 + 7) / 8) + 3;  // upper bound; the sort passes depend on the key width
+  out->hypotheses_scored = n;
+  if (key) {
+    out->best_num_inliers = spr_key_count(key);
+    out->best_hyp_index = spr_key_index(key);
+    double hp[4];
+    SPR_CUDA(h, cudaMemcpy(hp, h->d_hyps.as<double>() + 4 * (size_t)out->best_hyp_index, sizeof(hp), cudaMemcpyDeviceToHost));
+    out->R_t[0] = hp[0]; out->R_t[1] = -hp[1]; out->R_t[2] = hp[2];
+    out->R_t[3] = hp[1]; out->R_t[4] = hp[0];  out->R_t[5] = hp[3];
   }
   return SLIDE_PR_OK;
 }
