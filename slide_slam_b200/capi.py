@@ -28,6 +28,7 @@ EXPORTS = [
     "slide_pr_get_xyz_yaw_from_tf", "slide_pr_find_transformation_batch", "slide_pr_pack_record",
     "slide_pr_merge_records", "slide_pr_match_triangles", "slide_pr_score_hypotheses",
     "slide_pr_match_triangles_labeled", "slide_pr_estimate_tf", "slide_pr_triangle_hypotheses",
+    "slide_pr_generate_and_score",
     "slide_clipper_default_params", "slide_pr_clipper_score_pairwise_consistency",
     "slide_pr_clipper_get_initial_associations", "slide_pr_clipper_get_affinity_matrix",
     "slide_pr_clipper_get_affinity_csr", "slide_pr_clipper_solve",
@@ -135,6 +136,11 @@ class ClipperSolution(C.Structure):
                 ("line_search_steps", C.c_int64), ("kernel_ms", C.c_float), ("reserved", C.c_int32)]
 
 
+class GenerateInfo(C.Structure):
+    _fields_ = [("n_matches", C.c_int64), ("n_triangles_model", C.c_int32), ("n_triangles_data", C.c_int32),
+                ("match_ms", C.c_float), ("kabsch_ms", C.c_float), ("score_ms", C.c_float), ("reserved", C.c_int32)]
+
+
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _lp = C.POINTER(C.c_int64)
@@ -192,6 +198,8 @@ def lib():
     L.slide_pr_estimate_tf.argtypes = [_dp, _dp, C.c_int32, _dp]
     L.slide_pr_triangle_hypotheses.argtypes = [_dp, _dp, _ip, _ip, _ip, _ip, C.c_int64, _dp]
     L.slide_pr_score_hypotheses.argtypes = [C.c_void_p, _dp, C.c_int64, _ip, C.POINTER(MatchResult)]
+    L.slide_pr_generate_and_score.argtypes = [C.c_void_p, _dp, _dp, C.c_int32, _dp, _dp, C.c_int32, C.c_double, C.POINTER(MatchResult),
+                                              C.POINTER(GenerateInfo), _ip, _ip, _dp, _ip, C.c_int64]
     L.slide_clipper_default_params.argtypes = [C.POINTER(ClipperParams)]
     L.slide_pr_clipper_score_pairwise_consistency.argtypes = [C.c_void_p, C.POINTER(ClipperParams), _dp, C.c_int32, _dp, C.c_int32,
                                                               C.c_int32, _ip, C.c_int32, _lp]

@@ -1445,7 +1445,7 @@ int slide_pr_clipper_score_pairwise_consistency(slide_pr_handle *h, const slide_
   if (!h || !p || (n1 > 0 && !D1) || (n2 > 0 && !D2)) return SLIDE_PR_ERR_INVALID;
   SPR_CUDA(h, cudaSetDevice(h->device));
   long long nnz = 0;
-  const int rc = spr_clipper_score(clipper_of(h), *p, D1, n1, D2, n2, dim, A, m, false, h->sm_count, h->stream, &nnz, nullptr, h->err);
+  const int rc = spr_clipper_score(clipper_of(h), *p, D1, n1, D2, n2, dim, A, m, nullptr, h->sm_count, h->stream, &nnz, nullptr, h->err);
   if (nnz_upper) *nnz_upper = nnz;
   return rc;
 }

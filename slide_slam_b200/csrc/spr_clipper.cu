@@ -471,8 +471,9 @@ int spr_clipper_size(const SprClipper *c, int *m, long long *nnz_sym) {
 const int32_t *spr_clipper_associations(const SprClipper *c) { return c->A.data(); }
 
 int spr_clipper_score(SprClipper *c, const slide_clipper_params &p, const double *D1, int n1, const double *D2, int n2,
-                      int dim, const int32_t *A_in, int m, bool from_device, int sm_count, cudaStream_t st,
+                      int dim, const int32_t *A_in, int m, const double *device_hint, int sm_count, cudaStream_t st,
                       long long *nnz_upper, float *kernel_ms, std::string &err) {
+  const bool from_device = device_hint != nullptr;
   if (dim < 1 || dim > 3) { err = "the EuclideanDistance invariant is built for 1 to 3 dimensions"; return SLIDE_PR_ERR_UNSUPPORTED; }
   if (n1 < 0 || n2 < 0) { err = "negative point count"; return SLIDE_PR_ERR_INVALID; }
   c->m = 0; c->nnz = 0; c->dim = dim;
@@ -495,30 +496,29 @@ int spr_clipper_score(SprClipper *c, const slide_clipper_params &p, const double
   if (m == 0) return SLIDE_PR_OK;
   // centroids (fp32 prefilter works on centred coordinates) and the extent that scales its margin
   double c1[3] = {0, 0, 0}, c2[3] = {0, 0, 0}, R = 0;
-  std::vector<double> h1, h2;
-  const double *H1 = D1, *H2 = D2;
-  if (from_device) {  // points already on the device: fetch them once for the centroid / extent (m x dim doubles)
-    h1.resize((size_t)n1 * dim); h2.resize((size_t)n2 * dim);
-    CLP_CUDA(cudaMemcpyAsync(h1.data(), D1, h1.size() * 8, cudaMemcpyDeviceToHost, st));
-    CLP_CUDA(cudaMemcpyAsync(h2.data(), D2, h2.size() * 8, cudaMemcpyDeviceToHost, st));
-    CLP_CUDA(cudaStreamSynchronize(st));
-    H1 = h1.data(); H2 = h2.data();
-  }
-  for (int k = 0; k < dim; k++) {
-    for (int i = 0; i < n1; i++) c1[k] += H1[(size_t)dim * i + k];
-    for (int i = 0; i < n2; i++) c2[k] += H2[(size_t)dim * i + k];
-    c1[k] /= (double)std::max(n1, 1); c2[k] /= (double)std::max(n2, 1);
-  }
-  for (int k = 0; k < dim; k++) {
-    for (int i = 0; i < n1; i++) {
-      const double v = H1[(size_t)dim * i + k];
-      if (!std::isfinite(v)) { err = "non-finite coordinate in dataset 1"; return SLIDE_PR_ERR_NONFINITE; }
-      R = std::max(R, std::fabs(v - c1[k]));
+  if (from_device) {
+    // the points are already on the device (gathered per association by the generator); the caller knows a
+    // centre for each cloud and a bound on the distance of any point from it (the maps' bounding boxes)
+    for (int k = 0; k < 3; k++) { c1[k] = device_hint[k]; c2[k] = device_hint[3 + k]; }
+    R = device_hint[6];
+    if (!std::isfinite(R)) { err = "non-finite coordinate in a dataset"; return SLIDE_PR_ERR_NONFINITE; }
+  } else {
+    for (int k = 0; k < dim; k++) {
+      for (int i = 0; i < n1; i++) c1[k] += D1[(size_t)dim * i + k];
+      for (int i = 0; i < n2; i++) c2[k] += D2[(size_t)dim * i + k];
+      c1[k] /= (double)std::max(n1, 1); c2[k] /= (double)std::max(n2, 1);
     }
-    for (int i = 0; i < n2; i++) {
-      const double v = H2[(size_t)dim * i + k];
-      if (!std::isfinite(v)) { err = "non-finite coordinate in dataset 2"; return SLIDE_PR_ERR_NONFINITE; }
-      R = std::max(R, std::fabs(v - c2[k]));
+    for (int k = 0; k < dim; k++) {
+      for (int i = 0; i < n1; i++) {
+        const double v = D1[(size_t)dim * i + k];
+        if (!std::isfinite(v)) { err = "non-finite coordinate in dataset 1"; return SLIDE_PR_ERR_NONFINITE; }
+        R = std::max(R, std::fabs(v - c1[k]));
+      }
+      for (int i = 0; i < n2; i++) {
+        const double v = D2[(size_t)dim * i + k];
+        if (!std::isfinite(v)) { err = "non-finite coordinate in dataset 2"; return SLIDE_PR_ERR_NONFINITE; }
+        R = std::max(R, std::fabs(v - c2[k]));
+      }
     }
   }
   const double *dD1 = D1, *dD2 = D2;

@@ -13,11 +13,12 @@ SprClipper *spr_clipper_create();
 void spr_clipper_destroy(SprClipper *c);
 
 // scorePairwiseConsistency (clipper.cpp:21-65).  D1 / D2: dim x n column-major HOST arrays (Eigen's
-// invariants::Data), or -- from_device -- m x dim row-major DEVICE arrays already gathered per
-// association (A is then the identity pairing (i, i), as run_semantic_clipper builds it).
+// invariants::Data), or -- device_hint != NULL -- DEVICE arrays of the same layout (the generator's matched
+// point lists); device_hint = {centre of cloud 1 [3], centre of cloud 2 [3], bound on |coordinate - centre|}
+// then replaces the host pass that scales the fp32 prefilter's rounding margin.
 // A: m x 2 host array, or NULL for the all-to-all hypothesis (utils.h:60-70).
 int spr_clipper_score(SprClipper *c, const slide_clipper_params &p, const double *D1, int n1, const double *D2, int n2,
-                      int dim, const int32_t *A, int m, bool from_device, int sm_count, cudaStream_t st,
+                      int dim, const int32_t *A, int m, const double *device_hint, int sm_count, cudaStream_t st,
                       long long *nnz_upper, float *kernel_ms, std::string &err);
 int spr_clipper_size(const SprClipper *c, int *m, long long *nnz_sym);
 const int32_t *spr_clipper_associations(const SprClipper *c);

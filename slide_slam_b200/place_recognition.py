@@ -188,6 +188,47 @@ class PlaceRecognition:
                                                         capi.iptr(counts) if want_counts else None, C.byref(res)))
         return res, (counts[: len(hyps)] if want_counts else None)
 
+    def match_triangles(self, tris_model6, tris_data6, threshold: float, labels_model3=None, labels_data3=None):
+        """semantic_clipper::match_triangles (SC.cpp:111-118) on the device; returns (model_idx, data_idx,
+        perm_model k x 3, perm_data k x 3) in the reference's order."""
+        tm = np.ascontiguousarray(tris_model6, np.float64).reshape(-1, 6)
+        td = np.ascontiguousarray(tris_data6, np.float64).reshape(-1, 6)
+        lm = None if labels_model3 is None else np.ascontiguousarray(labels_model3, np.float64).reshape(-1, 3)
+        ld = None if labels_data3 is None else np.ascontiguousarray(labels_data3, np.float64).reshape(-1, 3)
+        n = C.c_int64(0)
+        args = (self._h, capi.dptr(tm), None if lm is None else capi.dptr(lm), len(tm), capi.dptr(td),
+                None if ld is None else capi.dptr(ld), len(td), float(threshold))
+        self._check(self._lib.slide_pr_match_triangles_labeled(*args, None, None, None, None, 0, C.byref(n)))
+        k = n.value
+        mi, di = np.zeros(max(k, 1), np.int32), np.zeros(max(k, 1), np.int32)
+        pm, pd = np.zeros((max(k, 1), 3), np.int32), np.zeros((max(k, 1), 3), np.int32)
+        self._check(self._lib.slide_pr_match_triangles_labeled(*args, capi.iptr(mi), capi.iptr(di), capi.iptr(pm), capi.iptr(pd), k, C.byref(n)))
+        return mi[:k], di[:k], pm[:k], pd[:k]
+
+    def generate_and_score(self, tris_model6, tris_data6, threshold: float, labels_model3=None, labels_data3=None,
+                           want_lists: bool = True, cap: int | None = None):
+        """The generator half on the device (slide_pr_generate_and_score): matched triangles -> 2-D Kabsch
+        hypotheses -> MatchMaps predicate -> best hypothesis, for the map pair given to prepare().
+        Returns (MatchResult, GenerateInfo, lists) with lists = dict(model_idx, data_idx, hyps, counts) or None."""
+        tm = np.ascontiguousarray(tris_model6, np.float64).reshape(-1, 6)
+        td = np.ascontiguousarray(tris_data6, np.float64).reshape(-1, 6)
+        lm = None if labels_model3 is None else np.ascontiguousarray(labels_model3, np.float64).reshape(-1, 3)
+        ld = None if labels_data3 is None else np.ascontiguousarray(labels_data3, np.float64).reshape(-1, 3)
+        res, info = capi.MatchResult(), capi.GenerateInfo()
+        args = (self._h, capi.dptr(tm), None if lm is None else capi.dptr(lm), len(tm), capi.dptr(td),
+                None if ld is None else capi.dptr(ld), len(td), float(threshold), C.byref(res), C.byref(info))
+        if not want_lists:
+            self._check(self._lib.slide_pr_generate_and_score(*args, None, None, None, None, 0))
+            return res, info, None
+        if cap is None:  # size the outputs with a first call
+            self._check(self._lib.slide_pr_generate_and_score(*args, None, None, None, None, 0))
+            cap = int(info.n_matches)
+        mi, di = np.zeros(max(cap, 1), np.int32), np.zeros(max(cap, 1), np.int32)
+        hyps, counts = np.zeros((max(cap, 1), 4)), np.zeros(max(cap, 1), np.int32)
+        self._check(self._lib.slide_pr_generate_and_score(*args, capi.iptr(mi), capi.iptr(di), capi.dptr(hyps), capi.iptr(counts), cap))
+        k = min(int(info.n_matches), cap)
+        return res, info, {"model_idx": mi[:k], "data_idx": di[:k], "hyps": hyps[:k], "counts": counts[:k]}
+
     # -- PlaceRecognition::findTransformation (PR.cpp:736-945) ---------------------------------
     def findTransformation(self, reference_objects, query_objects):
         """Returns (found, xyzYaw[4], transform_out 4x4, TfResult, ref_idx, qry_idx)."""

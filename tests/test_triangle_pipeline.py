@@ -120,3 +120,56 @@ def test_triangle_hypotheses_recover_the_planted_transform():
 
 def H_make_pr(kw):
     return PlaceRecognition(H.rosparams_from_golden(kw))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_landmarks,thr", [(2000, 0.05), (20000, 0.02)])
+def test_generator_half_on_the_device(n_landmarks, thr):
+    """BASELINE config 2 / config 3 sized maps (T ~ 4 000 / 40 000 Delaunay triangles per map): the
+    binned + windowed + radix-sorted device matching gives the oracle's all-pairs match list in the
+    reference's order; the fused device pipeline (Kabsch per match, list scoring) gives the host
+    pipeline's hypotheses (1e-9), the oracle's counts and the same winner."""
+    ref, qry, truth = synth.make_pair(n_landmarks, seed=900 + n_landmarks, classes="five", overlap=0.5, sigma=0.005)
+    tr, ir = delaunay_triangles(np.ascontiguousarray(ref[:, 1:3]))
+    tq, iq = delaunay_triangles(np.ascontiguousarray(qry[:, 1:3]))
+    lr, lq = np.ascontiguousarray(ref[ir, 0]), np.ascontiguousarray(qry[iq, 0])
+    kw = dict(match_xy_step_size=0.5, match_threshold=0.5, match_threshold_dimension=1.0)
+    pr = H_make_pr(kw)
+    # (1) unlabeled match list == the oracle's, order included
+    omi, odi, _ = O.match_triangles(tr, tq, thr)
+    mi, di, pm, pd = pr.match_triangles(tr, tq, thr)
+    assert len(omi) > 100 and mi.tolist() == omi.tolist() and di.tolist() == odi.tolist()
+    for k in range(0, len(mi), max(len(mi) // 200, 1)):
+        assert pm[k].tolist() == O.triangle_descriptor(tr[mi[k]])[1].tolist()
+        assert pd[k].tolist() == O.triangle_descriptor(tq[di[k]])[1].tolist()
+    # (2) fused pipeline with the class signature
+    pr.prepare(ref, qry, 200.0, 200.0)
+    res, info, L = pr.generate_and_score(tr, tq, thr, lr, lq)
+    lmi, ldi, lpm, lpd = pr.match_triangles(tr, tq, thr, lr, lq)
+    assert info.n_matches == len(lmi) and L["model_idx"].tolist() == lmi.tolist() and L["data_idx"].tolist() == ldi.tolist()
+    keep = set(zip(omi.tolist(), odi.tolist()))
+    assert all((a, b) in keep for a, b in zip(lmi.tolist(), ldi.tolist())) and 0 < len(lmi) < len(omi)
+    lib = capi.lib()
+    m = len(lmi)
+    hyps = np.zeros((m, 4))
+    lpm_c, lpd_c = np.ascontiguousarray(lpm.reshape(-1)), np.ascontiguousarray(lpd.reshape(-1))
+    assert lib.slide_pr_triangle_hypotheses(capi.dptr(tr), capi.dptr(tq), capi.iptr(np.ascontiguousarray(lmi)), capi.iptr(np.ascontiguousarray(ldi)),
+                                            capi.iptr(lpm_c), capi.iptr(lpd_c), m, capi.dptr(hyps)) == 0
+    np.testing.assert_allclose(L["hyps"], hyps, rtol=1e-9, atol=1e-9)     # closed-form 2 x 2 polar factor vs Jacobi SVD
+    op = O.make_params(**kw)
+    for k in np.unique(np.concatenate([np.arange(0, m, max(m // (150 if n_landmarks <= 2000 else 24), 1)), [res.best_hyp_index]])):
+        a, b = tq[ldi[k]].reshape(3, 2)[lpd[k]], tr[lmi[k]].reshape(3, 2)[lpm[k]]
+        tf = O.estimate_tf(a, b)                                         # the oracle's estimate_tf (SC.cpp:122-138)
+        np.testing.assert_allclose(L["hyps"][k], [tf[0, 0], tf[1, 0], tf[0, 2], tf[1, 2]], rtol=1e-9, atol=1e-9)
+        assert L["counts"][k] == O.score_one(op, ref, qry, *L["hyps"][k])[0]
+    assert res.best_num_inliers == L["counts"].max() and res.best_hyp_index == int(np.argmax(L["counts"]))
+    c, s, x, y = L["hyps"][res.best_hyp_index]
+    assert res.best_num_inliers >= 0.3 * n_landmarks                        # half the landmarks are shared
+    assert abs(math.atan2(s, c) - truth["yaw"]) < 2e-3
+    assert abs(x - truth["t"][0]) < 0.3 and abs(y - truth["t"][1]) < 0.3
+    # (3) edge cases: no matches, empty lists
+    r0, i0, _ = pr.generate_and_score(tr, tq, 1e-12, lr, lq, want_lists=False)
+    assert i0.n_matches == 0 and r0.best_hyp_index == -1
+    r1, i1, _ = pr.generate_and_score(tr[:0], tq, thr, want_lists=False)
+    assert i1.n_matches == 0
+    pr.close()
