@@ -317,6 +317,57 @@ int slide_pr_clipper_get_affinity_csr(slide_pr_handle *h, int64_t *row_ptr, int3
 int slide_pr_clipper_solve(slide_pr_handle *h, const slide_clipper_params *p, const double *u0, uint64_t seed,
                            int32_t *nodes_out, int32_t cap, slide_clipper_solution *sol, double *u_out);
 
+/* ---- SlideGraph entry points ------------------------------------------------------------------ */
+/* Observation::delaunayTriangulation (clipper_semantic_object/src/triangulation/observation.cpp:13-88,
+ * qhull "Qt Qbb Qc Qz Q12 d"): Delaunay triangulation of n points (xy2: n x 2) on the host.  tri3_out
+ * receives 3 vertex ids per triangle (counter-clockwise), capacity cap triangles; *n_tri the total.
+ * Same triangle SET as qhull for points in general position; the triangle / vertex ORDER is not qhull's. */
+int slide_pr_delaunay(const double *xy2, int32_t n, int32_t *tri3_out, int64_t cap, int64_t *n_tri);
+
+/* rosparams sloam/place_recognition_slidegraph/ * (PR.cpp:64-75) */
+typedef struct slide_pr_slidegraph_params {
+  double  sigma;                          /* 0.1 */
+  double  epsilon;                        /* 0.1 */
+  double  matching_threshold;             /* descriptor_matching_threshold, 0.1 */
+  int32_t num_inliers_threshold;          /* num_inliners_threshold, 10 */
+  int32_t min_num_map_objects_to_start;   /* 20 */
+  int32_t use_class_signature;            /* 0 = the reference (no label check: the TODO at SC.cpp:114,186);
+                                             1 = matched triangles must also agree label by label */
+  int32_t reserved;
+  uint64_t seed;                          /* seed of the deterministic u0 that stands in for std::random_device */
+} slide_pr_slidegraph_params;
+void slide_pr_slidegraph_default_params(slide_pr_slidegraph_params *p);
+
+typedef struct slide_pr_sc_info {
+  int32_t found;
+  int32_t n_inliers;                /* associations selected by CLIPPER */
+  int32_t n_triangles_model, n_triangles_data;
+  int64_t n_triangle_matches;
+  int64_t n_associations;           /* 3 per triangle match (SC.cpp:102-105) */
+  int64_t nnz_upper;                /* non-zeros of the affinity matrix (upper triangle) */
+  double  score;                    /* CLIPPER objective of the solution */
+  float   delaunay_ms;              /* host */
+  float   match_ms, affinity_ms, solve_ms;   /* device */
+} slide_pr_sc_info;
+
+/* semantic_clipper::run_semantic_clipper (semantic_clipper.h:38, semantic_clipper.cpp:140-275):
+ * Delaunay triangles of both maps' (x, y) -> descriptor matching -> CLIPPER on the matched points ->
+ * 2-D Kabsch of the selected pairs.  tris_*6 (t x 6 coordinates) replace the internal triangulation
+ * when given (e.g. qhull's own facets in the caller's order); u0 (n_associations doubles) replaces the
+ * seeded initial vector.  tf16 (row-major 4x4) is written only when found: the reference's
+ * tfFromQuery2Ref, which maps MODEL (reference map) points onto DATA (query map) points -- the
+ * caller inverts it (PR.cpp:622-623).  Returns SLIDE_PR_OK / SLIDE_PR_NOT_FOUND. */
+int slide_pr_run_semantic_clipper(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7, int32_t n_qry,
+                                  const slide_pr_slidegraph_params *sp, const double *tris_model6, int32_t t_model,
+                                  const double *tris_data6, int32_t t_data, const double *u0, int64_t u0_len, double *tf16,
+                                  slide_pr_sc_info *info /* may be NULL */);
+
+/* PlaceRecognition::findInterLoopClosureWithClipper (PR.h:109-112, PR.cpp:541-630): drops objects at
+ * exactly (0, 0), size gate, run_semantic_clipper, inverse of the result.  tf16: tfFromQueryToRef. */
+int slide_pr_find_inter_loop_closure_with_clipper(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7,
+                                                  int32_t n_qry, const slide_pr_slidegraph_params *sp, double *tf16,
+                                                  slide_pr_sc_info *info /* may be NULL */);
+
 #ifdef __cplusplus
 }
 #endif

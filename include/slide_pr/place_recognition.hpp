@@ -1,6 +1,7 @@
 // place_recognition.hpp -- header-only C++ adapter with the reference's own signatures.
 //
-// Drop-in for the SlideMatch half of `class PlaceRecognition`
+// Drop-in for `class PlaceRecognition` -- the SlideMatch half and the SlideGraph entry
+// (findInterLoopClosureWithClipper, semantic_clipper::run_semantic_clipper) --
 // (backend/sloam/include/core/place_recognition.h:31-237) on top of the C-ABI in slide_pr.h.
 // It is templated on the vector / matrix types so that it works with the reference's
 //   std::vector<Eigen::Vector7d>, Eigen::Matrix3d, Eigen::Matrix4d, std::vector<Eigen::Vector4d>
@@ -135,6 +136,30 @@ class PlaceRecognition {
     return true;
   }
 
+  // rosparams sloam/place_recognition_slidegraph/* (PR.cpp:64-75); public so that ParamInit can fill them
+  slide_pr_slidegraph_params slidegraph = slidegraph_defaults();
+  static slide_pr_slidegraph_params slidegraph_defaults() {
+    slide_pr_slidegraph_params p;
+    slide_pr_slidegraph_default_params(&p);
+    return p;
+  }
+  const slide_pr_sc_info &last_slidegraph() const { return last_sc_; }
+
+  // bool findInterLoopClosureWithClipper(reference_objects, query_objects, tfFromQueryToRef)   PR.h:109-112
+  // (SlideGraph: Delaunay triangles -> descriptor matching -> CLIPPER -> 2-D Kabsch, PR.cpp:541-630)
+  template <class Vec7List, class Mat4>
+  bool findInterLoopClosureWithClipper(const Vec7List &reference_objects, const Vec7List &query_objects,
+                                       Mat4 &tfFromQueryToRef) {
+    double tf[16];
+    const int rc = slide_pr_find_inter_loop_closure_with_clipper(h_, rows(reference_objects), (int32_t)reference_objects.size(),
+                                                                 rows(query_objects), (int32_t)query_objects.size(), &slidegraph,
+                                                                 tf, &last_sc_);
+    if (rc != SLIDE_PR_OK) return false;  // the reference inverts whatever the caller passed in (identity, sloamNode.cpp:620); left as is
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) tfFromQueryToRef(r, c) = tf[r * 4 + c];
+    return true;
+  }
+
   // bool findIntraLoopClosure(measurements, submap, query_pose, candidate_pose, tf)   PR.h:88-91
   // Pose4: the SE3's 4x4 matrix (query_pose.matrix()).
   template <class Vec7List, class Pose4, class Mat4>
@@ -196,6 +221,37 @@ class PlaceRecognition {
   slide_pr_params p_;
   slide_pr_handle *h_ = nullptr;
   slide_pr_tf_result last_{};
+  slide_pr_sc_info last_sc_{};
+  friend struct semantic_clipper_access;
 };
+
+// semantic_clipper::run_semantic_clipper(reference_map, query_map, tfFromQuery2Ref, sigma, epsilon,
+// min_num_pairs, matching_threshold)   clipper_semantic_object/include/semantic_clipper.h:38
+// Maps are std::vector<std::vector<double>> rows [label, x, y, z, d1, d2, d3] (semantic_clipper.cpp:144).
+struct semantic_clipper_access {
+  static slide_pr_handle *handle(PlaceRecognition &pr) { return pr.h_; }
+};
+namespace semantic_clipper {
+template <class Mat4>
+inline bool run_semantic_clipper(PlaceRecognition &gpu, const std::vector<std::vector<double>> &reference_map,
+                                 const std::vector<std::vector<double>> &query_map, Mat4 &tfFromQuery2Ref, double sigma,
+                                 double epsilon, int min_num_pairs, double matching_threshold) {
+  std::vector<double> ref(7 * reference_map.size()), qry(7 * query_map.size());
+  for (size_t i = 0; i < reference_map.size(); i++)
+    for (int c = 0; c < 7; c++) ref[7 * i + c] = c < (int)reference_map[i].size() ? reference_map[i][c] : 0.0;
+  for (size_t i = 0; i < query_map.size(); i++)
+    for (int c = 0; c < 7; c++) qry[7 * i + c] = c < (int)query_map[i].size() ? query_map[i][c] : 0.0;
+  slide_pr_slidegraph_params sp = gpu.slidegraph;
+  sp.sigma = sigma; sp.epsilon = epsilon; sp.num_inliers_threshold = min_num_pairs; sp.matching_threshold = matching_threshold;
+  double tf[16];
+  slide_pr_sc_info info;
+  const int rc = slide_pr_run_semantic_clipper(semantic_clipper_access::handle(gpu), ref.data(), (int32_t)reference_map.size(), qry.data(),
+                                               (int32_t)query_map.size(), &sp, nullptr, 0, nullptr, 0, nullptr, 0, tf, &info);
+  if (rc != SLIDE_PR_OK) return false;
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) tfFromQuery2Ref(r, c) = tf[r * 4 + c];
+  return true;
+}
+}  // namespace semantic_clipper
 
 }  // namespace slide_pr

@@ -29,6 +29,8 @@ EXPORTS = [
     "slide_pr_merge_records", "slide_pr_match_triangles", "slide_pr_score_hypotheses",
     "slide_pr_match_triangles_labeled", "slide_pr_estimate_tf", "slide_pr_triangle_hypotheses",
     "slide_pr_generate_and_score",
+    "slide_pr_delaunay", "slide_pr_slidegraph_default_params", "slide_pr_run_semantic_clipper",
+    "slide_pr_find_inter_loop_closure_with_clipper",
     "slide_clipper_default_params", "slide_pr_clipper_score_pairwise_consistency",
     "slide_pr_clipper_get_initial_associations", "slide_pr_clipper_get_affinity_matrix",
     "slide_pr_clipper_get_affinity_csr", "slide_pr_clipper_solve",
@@ -136,6 +138,19 @@ class ClipperSolution(C.Structure):
                 ("line_search_steps", C.c_int64), ("kernel_ms", C.c_float), ("reserved", C.c_int32)]
 
 
+class SlidegraphParams(C.Structure):
+    """slide_pr_slidegraph_params: rosparams sloam/place_recognition_slidegraph/* (PR.cpp:64-75)."""
+    _fields_ = [("sigma", C.c_double), ("epsilon", C.c_double), ("matching_threshold", C.c_double),
+                ("num_inliers_threshold", C.c_int32), ("min_num_map_objects_to_start", C.c_int32),
+                ("use_class_signature", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64)]
+
+
+class ScInfo(C.Structure):
+    _fields_ = [("found", C.c_int32), ("n_inliers", C.c_int32), ("n_triangles_model", C.c_int32), ("n_triangles_data", C.c_int32),
+                ("n_triangle_matches", C.c_int64), ("n_associations", C.c_int64), ("nnz_upper", C.c_int64), ("score", C.c_double),
+                ("delaunay_ms", C.c_float), ("match_ms", C.c_float), ("affinity_ms", C.c_float), ("solve_ms", C.c_float)]
+
+
 class GenerateInfo(C.Structure):
     _fields_ = [("n_matches", C.c_int64), ("n_triangles_model", C.c_int32), ("n_triangles_data", C.c_int32),
                 ("match_ms", C.c_float), ("kabsch_ms", C.c_float), ("score_ms", C.c_float), ("reserved", C.c_int32)]
@@ -200,6 +215,12 @@ def lib():
     L.slide_pr_score_hypotheses.argtypes = [C.c_void_p, _dp, C.c_int64, _ip, C.POINTER(MatchResult)]
     L.slide_pr_generate_and_score.argtypes = [C.c_void_p, _dp, _dp, C.c_int32, _dp, _dp, C.c_int32, C.c_double, C.POINTER(MatchResult),
                                               C.POINTER(GenerateInfo), _ip, _ip, _dp, _ip, C.c_int64]
+    L.slide_pr_delaunay.argtypes = [_dp, C.c_int32, _ip, C.c_int64, _lp]
+    L.slide_pr_slidegraph_default_params.argtypes = [C.POINTER(SlidegraphParams)]
+    L.slide_pr_run_semantic_clipper.argtypes = [C.c_void_p, _dp, C.c_int32, _dp, C.c_int32, C.POINTER(SlidegraphParams), _dp, C.c_int32,
+                                                _dp, C.c_int32, _dp, C.c_int64, _dp, C.POINTER(ScInfo)]
+    L.slide_pr_find_inter_loop_closure_with_clipper.argtypes = [C.c_void_p, _dp, C.c_int32, _dp, C.c_int32, C.POINTER(SlidegraphParams),
+                                                                _dp, C.POINTER(ScInfo)]
     L.slide_clipper_default_params.argtypes = [C.POINTER(ClipperParams)]
     L.slide_pr_clipper_score_pairwise_consistency.argtypes = [C.c_void_p, C.POINTER(ClipperParams), _dp, C.c_int32, _dp, C.c_int32,
                                                               C.c_int32, _ip, C.c_int32, _lp]

@@ -21,6 +21,7 @@
 
 #include "../../include/slide_pr.h"
 #include "spr_clipper.h"
+#include "spr_delaunay.h"
 #include "spr_generate.h"
 #include "spr_host.h"
 #include "spr_kernels.h"
@@ -1508,6 +1509,167 @@ int slide_pr_clipper_solve(slide_pr_handle *h, const slide_clipper_params *p, co
     u0 = own.data();
   }
   return spr_clipper_solve(h->clipper, *p, u0, h->sm_count, h->stream, nodes_out, cap, sol, u_out, h->err);
+}
+
+// ---- SlideGraph entry points -----------------------------------------------------------------------
+int slide_pr_delaunay(const double *xy2, int32_t n, int32_t *tri3_out, int64_t cap, int64_t *n_tri) {
+  if (n < 0 || (n > 0 && !xy2) || !n_tri || cap < 0) return SLIDE_PR_ERR_INVALID;
+  std::vector<int32_t> tri;
+  const int k = spr::delaunay_triangulate(xy2, n, tri);
+  if (k < 0) return SLIDE_PR_ERR_NONFINITE;
+  *n_tri = k;
+  if (tri3_out) std::memcpy(tri3_out, tri.data(), sizeof(int32_t) * 3 * (size_t)std::min<int64_t>(k, cap));
+  return SLIDE_PR_OK;
+}
+
+void slide_pr_slidegraph_default_params(slide_pr_slidegraph_params *p) {  // PR.cpp:64-75
+  std::memset(p, 0, sizeof(*p));
+  p->sigma = 0.1; p->epsilon = 0.1; p->matching_threshold = 0.1;
+  p->num_inliers_threshold = 10; p->min_num_map_objects_to_start = 20;
+}
+
+static void triangles_of_map(const double *rows7, int n, std::vector<double> &tris6, std::vector<double> &labels3, bool want_labels) {
+  std::vector<double> xy(2 * (size_t)std::max(n, 1));
+  for (int i = 0; i < n; i++) { xy[2 * (size_t)i] = rows7[7 * (size_t)i + 1]; xy[2 * (size_t)i + 1] = rows7[7 * (size_t)i + 2]; }  // SC.cpp:150-166
+  std::vector<int32_t> tri;
+  const int k = spr::delaunay_triangulate(xy.data(), n, tri);
+  tris6.resize(6 * (size_t)std::max(k, 0));
+  labels3.resize(want_labels ? 3 * (size_t)std::max(k, 0) : 0);
+  for (int t = 0; t < k; t++)
+    for (int v = 0; v < 3; v++) {
+      const int id = tri[3 * (size_t)t + v];
+      tris6[6 * (size_t)t + 2 * v] = xy[2 * (size_t)id];
+      tris6[6 * (size_t)t + 2 * v + 1] = xy[2 * (size_t)id + 1];
+      if (want_labels) labels3[3 * (size_t)t + v] = rows7[7 * (size_t)id];
+    }
+}
+
+int slide_pr_run_semantic_clipper(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7, int32_t n_qry,
+                                  const slide_pr_slidegraph_params *sp, const double *tris_model6, int32_t t_model,
+                                  const double *tris_data6, int32_t t_data, const double *u0, int64_t u0_len, double *tf16,
+                                  slide_pr_sc_info *info_opt) {
+  if (!h || !sp || !tf16 || n_ref < 0 || n_qry < 0 || (n_ref > 0 && !ref7) || (n_qry > 0 && !qry7)) return SLIDE_PR_ERR_INVALID;
+  slide_pr_sc_info local, *I = info_opt ? info_opt : &local;
+  std::memset(I, 0, sizeof(*I));
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  // triangles: the caller's (e.g. qhull facets in the reference's order) or our own Delaunay triangulation
+  const bool own_tris = !tris_model6 && !tris_data6;
+  if ((tris_model6 == nullptr) != (tris_data6 == nullptr)) { h->err = "give the triangles of both maps or of none"; return SLIDE_PR_ERR_INVALID; }
+  std::vector<double> tm_own, td_own, lm, ld;
+  const double t0 = now_ms();
+  if (own_tris) {
+    for (int i = 0; i < n_ref; i++) if (!std::isfinite(ref7[7 * (size_t)i + 1]) || !std::isfinite(ref7[7 * (size_t)i + 2])) { h->err = "non-finite reference coordinate"; return SLIDE_PR_ERR_NONFINITE; }
+    for (int i = 0; i < n_qry; i++) if (!std::isfinite(qry7[7 * (size_t)i + 1]) || !std::isfinite(qry7[7 * (size_t)i + 2])) { h->err = "non-finite query coordinate"; return SLIDE_PR_ERR_NONFINITE; }
+    triangles_of_map(ref7, n_ref, tm_own, lm, sp->use_class_signature != 0);
+    triangles_of_map(qry7, n_qry, td_own, ld, sp->use_class_signature != 0);
+    tris_model6 = tm_own.data(); t_model = (int32_t)(tm_own.size() / 6);
+    tris_data6 = td_own.data(); t_data = (int32_t)(td_own.size() / 6);
+  } else if (sp->use_class_signature) {
+    h->err = "the class signature needs the internal triangulation (vertex labels are not part of caller-supplied triangles)";
+    return SLIDE_PR_ERR_UNSUPPORTED;
+  }
+  I->delaunay_ms = (float)(now_ms() - t0);
+  I->n_triangles_model = t_model; I->n_triangles_data = t_data;
+  if (t_model <= 0 || t_data <= 0) return SLIDE_PR_NOT_FOUND;
+  // match_triangles (SC.cpp:111-118) on the device, reference order
+  GenDevice G;
+  int rc = gen_match_on_device(h, tris_model6, lm.empty() ? nullptr : lm.data(), t_model, tris_data6, ld.empty() ? nullptr : ld.data(),
+                               t_data, sp->matching_threshold, &G);
+  if (rc != SLIDE_PR_OK) return rc;
+  I->n_triangle_matches = G.n_matches;
+  const long long m = 3 * G.n_matches;     // 3 matched points per triangle pair (SC.cpp:102-105)
+  I->n_associations = m;
+  if (m == 0) { SPR_CUDA(h, cudaStreamSynchronize(st)); return SLIDE_PR_NOT_FOUND; }
+  if (m > 0x3fffffffLL) { h->err = "more than 2^30 putative associations"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  // matched point lists (model / data, m x 2 each) straight from the match list, on the device
+  SPR_CUDA(h, h->d_hyps.ensure((size_t)m * 2 * 2 * sizeof(double)));
+  double *pm = h->d_hyps.as<double>(), *pd = pm + 2 * (size_t)m;
+  SPR_CUDA(h, spr_launch_gen_kabsch(G.tris_m, G.tris_d, G.perm_m, G.perm_d, G.model_idx, G.data_idx, G.n_matches, nullptr, pm, pd, st));
+  SPR_CUDA(h, cudaStreamSynchronize(st));
+  SPR_CUDA(h, cudaEventElapsedTime(&I->match_ms, h->ev0, h->ev1));
+  // CLIPPER: associations (i, i) (SC.cpp:203-207), EuclideanDistance with sigma / epsilon (SC.cpp:210-212)
+  slide_clipper_params cp;
+  slide_clipper_default_params(&cp);
+  cp.sigma = sp->sigma; cp.epsilon = sp->epsilon;
+  std::vector<int32_t> A(2 * (size_t)m);
+  for (long long i = 0; i < m; i++) { A[2 * (size_t)i] = (int32_t)i; A[2 * (size_t)i + 1] = (int32_t)i; }
+  // centre + extent of each cloud for the fp32 prefilter: the triangles' bounding boxes
+  double hint[7] = {0, 0, 0, 0, 0, 0, 0};
+  {
+    double lo[2][2] = {{HUGE_VAL, HUGE_VAL}, {HUGE_VAL, HUGE_VAL}}, hi[2][2] = {{-HUGE_VAL, -HUGE_VAL}, {-HUGE_VAL, -HUGE_VAL}};
+    const double *src[2] = {tris_model6, tris_data6};
+    const size_t cnt[2] = {3 * (size_t)t_model, 3 * (size_t)t_data};
+    for (int s = 0; s < 2; s++)
+      for (size_t k = 0; k < cnt[s]; k++)
+        for (int c = 0; c < 2; c++) { const double v = src[s][2 * k + c]; lo[s][c] = std::min(lo[s][c], v); hi[s][c] = std::max(hi[s][c], v); }
+    for (int s = 0; s < 2; s++)
+      for (int c = 0; c < 2; c++) { hint[3 * s + c] = 0.5 * (lo[s][c] + hi[s][c]); hint[6] = std::max(hint[6], 0.5 * (hi[s][c] - lo[s][c])); }
+  }
+  long long nnz = 0;
+  rc = spr_clipper_score(clipper_of(h), cp, pm, (int)m, pd, (int)m, 2, A.data(), (int)m, hint, h->sm_count, st, &nnz, &I->affinity_ms, h->err);
+  if (rc != SLIDE_PR_OK) return rc;
+  I->nnz_upper = nnz;
+  std::vector<double> u0_own;
+  if (!u0 || u0_len < m) {  // stand-in for utils::randvec (std::random_device, utils.cpp:22-29)
+    u0_own.resize((size_t)m);
+    uint64_t x = sp->seed;
+    for (long long i = 0; i < m; i++) {
+      x += 0x9e3779b97f4a7c15ull;
+      uint64_t z = x;
+      z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+      z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+      z ^= z >> 31;
+      u0_own[(size_t)i] = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    }
+    u0 = u0_own.data();
+  }
+  std::vector<int32_t> nodes((size_t)m);
+  slide_clipper_solution sol;
+  rc = spr_clipper_solve(h->clipper, cp, u0, h->sm_count, st, nodes.data(), (int32_t)m, &sol, nullptr, h->err);
+  if (rc != SLIDE_PR_OK) return rc;
+  I->solve_ms = sol.kernel_ms;
+  I->n_inliers = sol.n_nodes;
+  I->score = sol.score;
+  if (sol.n_nodes < sp->num_inliers_threshold) return SLIDE_PR_NOT_FOUND;           // SC.cpp:249-255
+  // estimate_tf on the selected pairs (SC.cpp:238-258): model -> data
+  std::vector<double> hp((size_t)m * 4);
+  SPR_CUDA(h, cudaMemcpy(hp.data(), pm, (size_t)m * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+  std::vector<double> a(2 * (size_t)sol.n_nodes), b(2 * (size_t)sol.n_nodes);
+  for (int k = 0; k < sol.n_nodes; k++) {
+    const size_t nd = (size_t)nodes[k];
+    a[2 * k] = hp[2 * nd]; a[2 * k + 1] = hp[2 * nd + 1];
+    b[2 * k] = hp[2 * (size_t)m + 2 * nd]; b[2 * k + 1] = hp[2 * (size_t)m + 2 * nd + 1];
+  }
+  double tf9[9];
+  spr::estimate_tf(a.data(), b.data(), sol.n_nodes, tf9);
+  const double yaw = std::atan2(tf9[3], tf9[0]);                                    // SC.cpp:261-268
+  for (int i = 0; i < 16; i++) tf16[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  tf16[3] = tf9[2]; tf16[7] = tf9[5];
+  tf16[0] = std::cos(yaw); tf16[1] = -std::sin(yaw); tf16[4] = std::sin(yaw); tf16[5] = std::cos(yaw);
+  I->found = 1;
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_find_inter_loop_closure_with_clipper(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7,
+                                                  int32_t n_qry, const slide_pr_slidegraph_params *sp, double *tf16,
+                                                  slide_pr_sc_info *info_opt) {
+  if (!h || !sp || !tf16 || n_ref < 0 || n_qry < 0 || (n_ref > 0 && !ref7) || (n_qry > 0 && !qry7)) return SLIDE_PR_ERR_INVALID;
+  if (info_opt) std::memset(info_opt, 0, sizeof(*info_opt));
+  // objects at exactly (0, 0) are invalid (PR.cpp:576-612)
+  std::vector<double> ref, qry;
+  ref.reserve(7 * (size_t)n_ref); qry.reserve(7 * (size_t)n_qry);
+  for (int i = 0; i < n_ref; i++)
+    if (!(ref7[7 * (size_t)i + 1] == 0.0 && ref7[7 * (size_t)i + 2] == 0.0)) ref.insert(ref.end(), ref7 + 7 * (size_t)i, ref7 + 7 * (size_t)i + 7);
+  for (int i = 0; i < n_qry; i++)
+    if (!(qry7[7 * (size_t)i + 1] == 0.0 && qry7[7 * (size_t)i + 2] == 0.0)) qry.insert(qry.end(), qry7 + 7 * (size_t)i, qry7 + 7 * (size_t)i + 7);
+  const int nr = (int)(ref.size() / 7), nq = (int)(qry.size() / 7);
+  if (nr < sp->min_num_map_objects_to_start || nq < sp->min_num_map_objects_to_start) return SLIDE_PR_NOT_FOUND;  // PR.cpp:618
+  double fwd[16];
+  const int rc = slide_pr_run_semantic_clipper(h, ref.data(), nr, qry.data(), nq, sp, nullptr, 0, nullptr, 0, nullptr, 0, fwd, info_opt);
+  if (rc != SLIDE_PR_OK) return rc;
+  spr::mat4_rigid_inverse(fwd, tf16);                                                // PR.cpp:622-623 (a yaw + translation matrix)
+  return SLIDE_PR_OK;
 }
 
 #pragma GCC visibility pop

@@ -35,6 +35,25 @@ _ROSPARAMS = {
 }
 
 
+# rosparam name under sloam/place_recognition_slidegraph/  ->  SlidegraphParams field   PR.cpp:64-75
+_SLIDEGRAPH = {"num_inliners_threshold": "num_inliers_threshold", "descriptor_matching_threshold": "matching_threshold",
+               "sigma": "sigma", "epsilon": "epsilon", "min_num_map_objects_to_start": "min_num_map_objects_to_start",
+               "use_class_signature": "use_class_signature", "seed": "seed"}
+
+
+def delaunay(xy) -> np.ndarray:
+    """Observation::delaunayTriangulation (observation.cpp:13-88) on the host: t x 3 vertex ids."""
+    xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+    n = C.c_int64(0)
+    lib = capi.lib()
+    rc = lib.slide_pr_delaunay(capi.dptr(xy), len(xy), None, 0, C.byref(n))
+    if rc < 0:
+        raise capi.SlidePrError(rc, "non-finite coordinate")
+    tri = np.zeros((max(n.value, 1), 3), np.int32)
+    lib.slide_pr_delaunay(capi.dptr(xy), len(xy), capi.iptr(tri), n.value, C.byref(n))
+    return tri[:n.value]
+
+
 @dataclass
 class MatchMapsResult:
     """Outputs of MatchMaps (PR.h:70-74)."""
@@ -52,10 +71,16 @@ class PlaceRecognition:
     """Drop-in for the reference class on the SlideMatch path.  `params` uses the rosparam names
     of place_recognition.cpp:24-75 (angles in degrees, like the yaml files)."""
 
-    def __init__(self, params: dict | None = None, device: int = -1):
+    def __init__(self, params: dict | None = None, device: int = -1, slidegraph: dict | None = None):
         self._lib = capi.lib()
         self._p = capi.default_params()
         self._p.device = device
+        self._sg = capi.SlidegraphParams()
+        self._lib.slide_pr_slidegraph_default_params(C.byref(self._sg))
+        for k, v in (slidegraph or {}).items():
+            if k not in _SLIDEGRAPH:
+                raise KeyError(f"unknown place_recognition_slidegraph rosparam {k!r}")
+            setattr(self._sg, _SLIDEGRAPH[k], v)
         # public members of the reference class (PR.h:34-43)
         self.visualize_matching_results = False
         self.min_loop_closure_overlap_percentage_ = 0.1
@@ -252,6 +277,37 @@ class PlaceRecognition:
                                                                     len(qry), capi.dptr(tf), C.byref(out)))
         self.last = out
         return rc == capi.OK, tf.reshape(4, 4)
+
+    # -- PlaceRecognition::findInterLoopClosureWithClipper (PR.cpp:541-630) --------------------------
+    def findInterLoopClosureWithClipper(self, reference_objects, query_objects):
+        """SlideGraph: Delaunay triangles -> descriptor matching -> CLIPPER -> 2-D Kabsch.
+        Returns (closure_found, tfFromQueryToRef 4x4); self.last_sc holds the stage statistics."""
+        ref, qry = capi.as_rows7(reference_objects), capi.as_rows7(query_objects)
+        tf = np.eye(4).reshape(16).copy()
+        info = capi.ScInfo()
+        rc = self._check(self._lib.slide_pr_find_inter_loop_closure_with_clipper(self._h, capi.dptr(ref), len(ref), capi.dptr(qry),
+                                                                                 len(qry), C.byref(self._sg), capi.dptr(tf), C.byref(info)))
+        self.last_sc = info
+        return rc == capi.OK, tf.reshape(4, 4)
+
+    def run_semantic_clipper(self, reference_map, query_map, sigma, epsilon, min_num_pairs, matching_threshold,
+                             tris_model6=None, tris_data6=None, u0=None):
+        """semantic_clipper::run_semantic_clipper (semantic_clipper.h:38).  Returns (found, tfFromQuery2Ref 4x4
+        as the reference names it: model -> data, info)."""
+        ref, qry = capi.as_rows7(reference_map), capi.as_rows7(query_map)
+        sp = capi.SlidegraphParams()
+        C.memmove(C.byref(sp), C.byref(self._sg), C.sizeof(sp))
+        sp.sigma, sp.epsilon, sp.num_inliers_threshold, sp.matching_threshold = sigma, epsilon, int(min_num_pairs), matching_threshold
+        tm = None if tris_model6 is None else np.ascontiguousarray(tris_model6, np.float64).reshape(-1, 6)
+        td = None if tris_data6 is None else np.ascontiguousarray(tris_data6, np.float64).reshape(-1, 6)
+        u = None if u0 is None else np.ascontiguousarray(u0, np.float64)
+        tf = np.eye(4).reshape(16).copy()
+        info = capi.ScInfo()
+        rc = self._check(self._lib.slide_pr_run_semantic_clipper(
+            self._h, capi.dptr(ref), len(ref), capi.dptr(qry), len(qry), C.byref(sp),
+            None if tm is None else capi.dptr(tm), 0 if tm is None else len(tm), None if td is None else capi.dptr(td),
+            0 if td is None else len(td), None if u is None else capi.dptr(u), 0 if u is None else len(u), capi.dptr(tf), C.byref(info)))
+        return rc == capi.OK, tf.reshape(4, 4), info
 
     # -- PlaceRecognition::findIntraLoopClosure (PR.cpp:389-496) --------------------------------
     def findIntraLoopClosure(self, measurements, submap, query_pose, candidate_pose):

@@ -47,6 +47,21 @@ int main(int argc, char **argv) {
     for (auto &o : sref) { o[1] -= last.centroid_ref[0]; o[2] -= last.centroid_ref[1]; }
     for (auto &o : sqry) { o[1] -= last.centroid_qry[0]; o[2] -= last.centroid_qry[1]; }
     place_recoger.MatchMaps(sref, sqry, R_t, best, map_matched, det_matched);
+    // SlideGraph entry points (PR.h:109-112, semantic_clipper.h:38) with the reference's call pattern
+    place_recoger.slidegraph.matching_threshold = 0.1;
+    place_recoger.slidegraph.min_num_map_objects_to_start = 20;
+    slide_pr::Mat<4, 4> tfClipper = slide_pr::Mat<4, 4>::Identity();
+    const bool sg_found = place_recoger.findInterLoopClosureWithClipper(reference_objects, query_objects, tfClipper);
+    const slide_pr_sc_info sg = place_recoger.last_slidegraph();
+    std::vector<std::vector<double>> ref_rows, qry_rows;
+    for (const auto &o : reference_objects) ref_rows.emplace_back(o.begin(), o.end());
+    for (const auto &o : query_objects) qry_rows.emplace_back(o.begin(), o.end());
+    slide_pr::Mat<4, 4> tfSc = slide_pr::Mat<4, 4>::Identity();
+    const bool sc_found = slide_pr::semantic_clipper::run_semantic_clipper(place_recoger, ref_rows, qry_rows, tfSc, 0.1, 0.1, 10, 0.1);
+    std::printf("{\"sg_found\": %s, \"sc_found\": %s, \"sg_triangles\": [%d, %d], \"sg_matches\": %lld, \"sg_inliers\": %d, "
+                "\"sg_yaw\": %.17g, \"sc_yaw\": %.17g}\n", sg_found ? "true" : "false", sc_found ? "true" : "false",
+                sg.n_triangles_model, sg.n_triangles_data, (long long)sg.n_triangle_matches, sg.n_inliers,
+                std::atan2(tfClipper(1, 0), tfClipper(0, 0)), std::atan2(tfSc(1, 0), tfSc(0, 0)));
     std::printf("{\"found\": %s, \"xyz_yaw\": [%.17g, %.17g, %.17g, %.17g], \"best\": %d, \"n_matched\": %zu, "
                 "\"R_t\": [%.17g, %.17g, %.17g, %.17g, %.17g, %.17g], \"hyp\": %lld}\n",
                 closure_found ? "true" : "false", xyzYawOut[0], xyzYawOut[1], xyzYawOut[2], xyzYawOut[3], best,

@@ -55,3 +55,7 @@ def test_adapter_reproduces_golden(tmp_path):
     assert out["R_t"] == c["R_t"][:6]
     # findInterLoopClosure rebuilds a yaw + xyz transform from xyzYaw (PR.cpp:523-536)
     np.testing.assert_allclose(out["xyz_yaw"], c["xyz_yaw"], rtol=1e-5, atol=1e-9)
+    # the SlideGraph entry points ran through the same adapter (indoor maps: 32 / 35 objects, gate 20)
+    sg = json.loads(r.stdout.strip().splitlines()[-2])
+    assert sg["sg_triangles"][0] > 40 and sg["sg_triangles"][1] > 40 and sg["sg_matches"] >= 0
+    assert isinstance(sg["sg_found"], bool) and sg["sg_found"] == sg["sc_found"]
