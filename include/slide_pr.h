@@ -61,7 +61,8 @@ typedef struct slide_pr_params {
   int32_t min_num_map_objects_to_start; /* 1 */
   int32_t inter_loop_closure;         /* 1 (public member PR.h:43) */
   int32_t device;                     /* CUDA device ordinal; -1 = current device */
-  int32_t reserved;
+  int32_t exhaustive_search;          /* not a rosparam.  0 (default): bound-and-verify search; 1: every hypothesis of the
+                                         lattice is verified exactly, as the reference does (same winner either way) */
 } slide_pr_params;
 
 typedef struct slide_pr_handle slide_pr_handle;
@@ -316,6 +317,13 @@ int slide_pr_clipper_get_affinity_csr(slide_pr_handle *h, int64_t *row_ptr, int3
  * from a splitmix64 stream seeded with `seed`.  nodes_out: capacity cap; u_out (optional): m. */
 int slide_pr_clipper_solve(slide_pr_handle *h, const slide_clipper_params *p, const double *u0, uint64_t seed,
                            int32_t *nodes_out, int32_t cap, slide_clipper_solution *sol, double *u_out);
+
+/* ---- measurement support ------------------------------------------------------------------------ */
+/* Issue-rate micro-benchmark on the handle's device (about 10 ms): warp instructions per second of
+ * independent LOP3 chains (the ALU / logic pipe the search kernels are bound by), of IMAD chains (FMA
+ * pipe) and of both interleaved (every scheduler issuing every cycle).  bench.py's roofline uses them
+ * as the measured compute peaks; MEASURED_PEAKS.json only holds HBM and tensor-core figures. */
+int slide_pr_measure_issue_peaks(slide_pr_handle *h, double *alu_winst_per_s, double *fma_winst_per_s, double *mixed_winst_per_s);
 
 /* ---- SlideGraph entry points ------------------------------------------------------------------ */
 /* Observation::delaunayTriangulation (clipper_semantic_object/src/triangulation/observation.cpp:13-88,

@@ -656,7 +656,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   // the result says so (search_mode = 0) and the caller skips the verification half.
   if (o.exhaustive == 2 && !can_bound && o.counts_out) { h->err = "upper bounds are not available for this problem"; return SLIDE_PR_ERR_UNSUPPORTED; }
   const bool bounds_only = o.exhaustive == 2 && can_bound;
-  const bool prune = bounds_only || (!o.exhaustive && !o.counts_out && !o.collect_stats && can_bound && !h->force_exhaustive);
+  const bool prune = bounds_only || (!o.exhaustive && !o.counts_out && !o.collect_stats && can_bound && !h->force_exhaustive && !h->p.exhaustive_search);
   const int n_planes = spr_bound_planes(h->V.nqp);
   size_t cand_off[2] = {0, 0};
   if (prune) {
@@ -1509,6 +1509,13 @@ int slide_pr_clipper_solve(slide_pr_handle *h, const slide_clipper_params *p, co
     u0 = own.data();
   }
   return spr_clipper_solve(h->clipper, *p, u0, h->sm_count, h->stream, nodes_out, cap, sol, u_out, h->err);
+}
+
+int slide_pr_measure_issue_peaks(slide_pr_handle *h, double *alu_winst_per_s, double *fma_winst_per_s, double *mixed_winst_per_s) {
+  if (!h || !alu_winst_per_s || !fma_winst_per_s || !mixed_winst_per_s) return SLIDE_PR_ERR_INVALID;
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  SPR_CUDA(h, spr_measure_issue_peaks(h->sm_count, alu_winst_per_s, fma_winst_per_s, mixed_winst_per_s, h->stream));
+  return SLIDE_PR_OK;
 }
 
 // ---- SlideGraph entry points -----------------------------------------------------------------------

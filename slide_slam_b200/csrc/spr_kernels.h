@@ -111,14 +111,10 @@ cudaError_t spr_launch_extract(const double *ref7, int n_ref, const double *qry7
                                double s, double tx, double ty, double Tstar, double Sstar, double thr_dim,
                                int ignore_dim, int32_t *match_ref, cudaStream_t st);
 
-// SlideGraph descriptor half (semantic_clipper.cpp:49-118)
+// SlideGraph descriptor half (semantic_clipper.cpp:49-99); the matching is in spr_generate.cu
 // labels3 (optional): vertex labels; sig receives them in sorted-descriptor order (class signature)
 cudaError_t spr_launch_tri_desc(const double *tris6, const double *labels3, int t, double *desc, int32_t *perm,
                                 double *sig, cudaStream_t st);
-// fill == false: per-model-triangle match counts + exclusive scan (offsets, *total);
-// fill == true : writes (model_idx, data_idx) of every match at its reference-order position
-// sm / sd (optional): class signatures; when given, a pair must also agree label by label
-cudaError_t spr_launch_tri_match(const double *dm, int tm, const double *dd, int td, const double *sm, const double *sd, double thr,
-                                 unsigned long long *counts, unsigned long long *offsets, unsigned long long *total,
-                                 int32_t *model_idx, int32_t *data_idx, long long cap, bool fill, int sm_count,
-                                 cudaStream_t st);
+
+// issue-rate micro-benchmark: warp instructions / s of LOP3 chains (ALU pipe), IMAD chains (FMA pipe) and both interleaved
+cudaError_t spr_measure_issue_peaks(int sm_count, double *alu, double *fma, double *mixed, cudaStream_t st);

@@ -1,8 +1,10 @@
 // spr_kernels_aux.cu -- the smaller sm_100a kernels around the lattice search: explicit
-// hypothesis lists (warp per hypothesis), correspondence extraction of the winner, and the
-// SlideGraph triangle-descriptor matching (semantic_clipper.cpp:49-118).
+// hypothesis lists (warp per hypothesis), correspondence extraction of the winner, the triangle
+// descriptors of the SlideGraph half (semantic_clipper.cpp:49-99) and the issue-rate micro-benchmark.
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <algorithm>
 
 #include "spr_core.h"
 #include "spr_kernels.h"
@@ -99,11 +101,10 @@ cudaError_t spr_launch_extract(const double *ref7, int n_ref, const double *qry7
 }
 
 // ---------------------------------------------------------------------------------------------
-// SlideGraph descriptor half: triangle descriptors + all-pairs matching
-// (semantic_clipper.cpp:49-118).  The reference recomputes both descriptors for each of the
-// T1 x T2 pairs; here they are built once per triangle, then every model triangle (one warp)
-// sweeps the data descriptors 32 at a time and compacts its matches with ballot + popc so the
-// output keeps the reference's order (model-major, data-minor).
+// SlideGraph descriptor half: triangle descriptors (semantic_clipper.cpp:49-99).  The reference
+// recomputes both descriptors for each of the T1 x T2 pairs; here they are built once per triangle.
+// The matching itself (binning, windowed sweep, radix sort into the reference's order) is in
+// spr_generate.cu.
 // ---------------------------------------------------------------------------------------------
 __global__ void spr_tri_desc_kernel(const double *__restrict__ tris6, const double *__restrict__ labels3, int t,
                                     double *__restrict__ desc, int32_t *__restrict__ perm, double *__restrict__ sig) {
@@ -124,68 +125,6 @@ __global__ void spr_tri_desc_kernel(const double *__restrict__ tris6, const doub
   }
 }
 
-template <bool FILL>
-__global__ void __launch_bounds__(256)
-spr_tri_match_kernel(const double *__restrict__ dm, int tm, const double *__restrict__ dd, int td,
-                     const double *__restrict__ sm, const double *__restrict__ sd, double thr,
-                     unsigned long long *__restrict__ counts, const unsigned long long *__restrict__ offsets,
-                     int32_t *__restrict__ model_idx, int32_t *__restrict__ data_idx, long long cap) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (int i = warp; i < tm; i += n_warps) {
-    const double m[3] = {dm[3 * (size_t)i], dm[3 * (size_t)i + 1], dm[3 * (size_t)i + 2]};
-    double ms[3] = {0.0, 0.0, 0.0};
-    if (sm) { ms[0] = sm[3 * (size_t)i]; ms[1] = sm[3 * (size_t)i + 1]; ms[2] = sm[3 * (size_t)i + 2]; }
-    unsigned long long base = FILL ? offsets[i] : 0ull;
-    for (int j0 = 0; j0 < td; j0 += 32) {
-      const int j = j0 + lane;
-      bool hit = false;
-      if (j < td) {
-        const double d[3] = {dd[3 * (size_t)j], dd[3 * (size_t)j + 1], dd[3 * (size_t)j + 2]};
-        hit = spr_descriptor_match(m, d, thr);
-        // class-consistent pairs only: every paired vertex must carry the same label (the check the
-        // reference leaves as a TODO, SC.cpp:114,186); labels compare as doubles like PR.cpp:306
-        if (hit && sm)
-          hit = ms[0] == sd[3 * (size_t)j] && ms[1] == sd[3 * (size_t)j + 1] && ms[2] == sd[3 * (size_t)j + 2];
-      }
-      const unsigned mask = __ballot_sync(SPR_FULL, hit);
-      if (FILL && hit) {
-        const unsigned long long pos = base + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
-        if ((long long)pos < cap) { model_idx[pos] = i; data_idx[pos] = j; }
-      }
-      base += (unsigned long long)__popc(mask);
-    }
-    if (!FILL && lane == 0) counts[i] = base;
-  }
-}
-
-// exclusive prefix sum of n counters, one block (n <= a few 10^5 triangles)
-__global__ void spr_scan_kernel(const unsigned long long *__restrict__ counts, int n,
-                                unsigned long long *__restrict__ offsets, unsigned long long *__restrict__ total) {
-  __shared__ unsigned long long tile[1024];
-  __shared__ unsigned long long carry;
-  if (threadIdx.x == 0) carry = 0ull;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + threadIdx.x;
-    const unsigned long long v = i < n ? counts[i] : 0ull;
-    tile[threadIdx.x] = v;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-      const unsigned long long t = threadIdx.x >= d ? tile[threadIdx.x - d] : 0ull;
-      __syncthreads();
-      tile[threadIdx.x] += t;
-      __syncthreads();
-    }
-    if (i < n) offsets[i] = carry + tile[threadIdx.x] - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += tile[1023];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total = carry;
-}
-
 cudaError_t spr_launch_tri_desc(const double *tris6, const double *labels3, int t, double *desc, int32_t *perm,
                                 double *sig, cudaStream_t st) {
   if (t <= 0) return cudaSuccess;
@@ -193,18 +132,62 @@ cudaError_t spr_launch_tri_desc(const double *tris6, const double *labels3, int 
   return cudaGetLastError();
 }
 
-cudaError_t spr_launch_tri_match(const double *dm, int tm, const double *dd, int td, const double *sm, const double *sd, double thr,
-                                 unsigned long long *counts, unsigned long long *offsets, unsigned long long *total,
-                                 int32_t *model_idx, int32_t *data_idx, long long cap, bool fill, int sm_count,
-                                 cudaStream_t st) {
-  if (tm <= 0) return cudaSuccess;
-  const int want = (tm + 7) / 8, capg = sm_count * 8;
-  const int grid = want < capg ? want : capg;
-  if (!fill) {
-    spr_tri_match_kernel<false><<<grid, 256, 0, st>>>(dm, tm, dd, td, sm, sd, thr, counts, offsets, model_idx, data_idx, cap);
-    spr_scan_kernel<<<1, 1024, 0, st>>>(counts, tm, offsets, total);
-  } else {
-    spr_tri_match_kernel<true><<<grid, 256, 0, st>>>(dm, tm, dd, td, sm, sd, thr, counts, offsets, model_idx, data_idx, cap);
+// ---------------------------------------------------------------------------------------------
+// Issue-rate micro-benchmark (bench.py's roofline denominator).  MEASURED_PEAKS.json only holds the
+// HBM and bf16 tensor peaks; the search kernels are bound by the SM's instruction issue (integer /
+// logic pipe), so the peak they are compared with is measured in the same run: independent
+// dependency chains of LOP3 (ALU pipe), of IMAD (FMA pipe), and both interleaved (all four
+// schedulers issuing every cycle), counted in warp instructions per second.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(1024) spr_issue_peak_kernel(uint32_t *out, int iters, uint32_t seed) {
+  uint32_t a[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { a[k] = seed + threadIdx.x * 8u + k; b[k] = seed * 3u + threadIdx.x + k; }
+  const uint32_t c = seed | 1u, d = seed ^ 0x9e3779b9u;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        if (MODE == 0 || MODE == 2) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(c), "r"(d));
+        if (MODE == 1 || MODE == 2) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b[k]) : "r"(c), "r"(d));
+      }
+    }
   }
-  return cudaGetLastError();
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s ^= a[k] ^ b[k];
+  if (s == 0x12345678u) out[blockIdx.x] = s;  // keeps the chains alive
+}
+
+// warp instructions per second of the three instruction mixes; each launch runs ~1 ms
+cudaError_t spr_measure_issue_peaks(int sm_count, double *alu, double *fma, double *mixed, cudaStream_t st) {
+  uint32_t *d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_out, 4096 * sizeof(uint32_t));
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int grid = sm_count * 2, iters = 4096;
+  double *res[3] = {alu, fma, mixed};
+  for (int mode = 0; mode < 3 && e == cudaSuccess; mode++) {
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {  // the first repetition warms the clocks up
+      cudaEventRecord(e0, st);
+      if (mode == 0) spr_issue_peak_kernel<0><<<grid, 1024, 0, st>>>(d_out, iters, 12345u + rep);
+      else if (mode == 1) spr_issue_peak_kernel<1><<<grid, 1024, 0, st>>>(d_out, iters, 12345u + rep);
+      else spr_issue_peak_kernel<2><<<grid, 1024, 0, st>>>(d_out, iters, 12345u + rep);
+      cudaEventRecord(e1, st);
+      e = cudaEventSynchronize(e1);
+      if (e != cudaSuccess) break;
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double insts = (double)grid * 32.0 /* warps */ * (double)iters * 32.0 * (mode == 2 ? 2.0 : 1.0);
+      if (rep > 0 && ms > 0) best = std::max(best, insts / (ms * 1e-3));
+    }
+    *res[mode] = best;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_out);
+  return e != cudaSuccess ? e : cudaGetLastError();
 }

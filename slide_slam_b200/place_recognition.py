@@ -32,6 +32,8 @@ _ROSPARAMS = {
     "match_x_half_range_intra": ("match_x_half_range_intra", float),
     "match_y_half_range_intra": ("match_y_half_range_intra", float),
     "match_yaw_half_range_intra": ("match_yaw_half_range_intra", "deg"),
+    # not a rosparam of the reference: 1 = verify every hypothesis exactly instead of bound-and-verify
+    "exhaustive_search": ("exhaustive_search", int),
 }
 
 
