@@ -24,9 +24,6 @@
 #ifndef SPB_THREADS
 #define SPB_THREADS 768
 #endif
-#ifndef SPB_MULHI
-#define SPB_MULHI 1   // probe coordinates through IMAD.HI (FMA pipe) instead of add + shift (ALU pipe); 0: A/B builds only
-#endif
 
 __device__ __forceinline__ uint32_t spb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void spb_mbar_init(uint64_t *bar, uint32_t count) {
@@ -83,8 +80,7 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
   const SprGrid &G = V.grid;
   const int32_t F = G.F;
   const uint32_t d = B.dir;
-  const uint32_t W = (uint32_t)G.W[d], maxbit2 = (uint32_t)G.maxbit[d] + 32u, maxword2 = maxbit2 >> 5;
-  const int32_t KF = 1 << (32 - F), KW = 1 << (27 - F);  // F <= 16 (host): 2^(32-F) and 2^(32-F-5) fit an int32
+  const uint32_t W = (uint32_t)G.W[d], maxbit2 = (uint32_t)G.maxbit[d] + 32u;
   const uint32_t W4 = W * 4u;
   const uint32_t PW4 = G.plane_words[d] * 4u;
   // Row band [row_begin, row_end) of the planes handled by this launch (the whole plane unless it
@@ -212,29 +208,18 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
               for (int u = 0; u < 4; u++) {
                 const int4 vv = v[2 * hq + (u >> 1)];
                 const int32_t qa_ = (u & 1) ? vv.z : vv.x, qb_ = (u & 1) ? vv.w : vv.y;
-                uint32_t row, bit, boff;
-                if (!REFINE && SPB_MULHI) {
-                  // (origin + query) >> F as the HIGH word of a signed 32 x 32 -> 64 bit multiply by 2^(32-F)
-                  // (IMAD.WIDE / IMAD.HI, FMA pipe) instead of a shift: the shift / logic (ALU) pipe is the one
-                  // that binds this kernel.  mulhi(v, 2^(32-F)) == v >> F (arithmetic), exactly.
-                  const int32_t sb = bqb2 + qb_;
-                  row = min((uint32_t)__mulhi(aqb + qa_, KF), Rm1);                 // rows 0 and Rm1 are all-zero
-                  bit = (uint32_t)__mulhi(sb, KF);                                    // only its low 5 bits are used (funnel shift)
-                  const uint32_t word = min((uint32_t)__mulhi(sb, KW), maxword2);     // words >= maxbit / 32 are all-zero
-                  asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(boff) : "r"(word), "r"(row * W4));
-                } else {
-                  (void)KF; (void)KW; (void)maxword2;
-                  row = min((uint32_t)((aqb + qa_) >> F), Rm1);
-                  // bit = plane bit of the SECOND chunk's first sample (the first chunk starts 32 bits
-                  // earlier, possibly before the row: the word in front of a row is a zero pad word)
-                  bit = min((uint32_t)((bqb2 + qb_) >> F), maxbit2);
-                  // byte offset with two multiply-adds (FMA pipe) instead of LEA.HI + LEA (ALU pipe, the busy one)
-                  asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(boff) : "r"(bit >> 5), "r"(row * W4));
-                  // variant = 2 * (upper half of the cell across) + (upper half of the cell along)
-                  if (REFINE) {
-                    const uint32_t var = ((uint32_t)((aqb + qa_) >> (F - 1)) & 1u) * 2u + ((uint32_t)((bqb2 + qb_) >> (F - 1)) & 1u);
-                    boff += var * (SMEM_TAB ? BW * 4u : PW4);
-                  }
+                const uint32_t row = min((uint32_t)((aqb + qa_) >> F), Rm1);     // rows 0 and Rm1 are all-zero
+                // bit = plane bit of the SECOND chunk's first sample (the first chunk starts 32 bits
+                // earlier, possibly before the row: the word in front of a row is a zero pad word)
+                const uint32_t bit = min((uint32_t)((bqb2 + qb_) >> F), maxbit2);  // words >= maxbit/32 are all-zero
+                // byte offset with two multiply-adds (FMA pipe) instead of LEA.HI + LEA (ALU pipe, the busy one).
+                // (Measured and rejected: the shifts as IMAD.HI / IMAD.WIDE by 2^(32-F) -- same instruction
+                // count, 17 % slower: the high-word multiply is a quarter-rate instruction on sm_100.)
+                uint32_t boff;
+                asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(boff) : "r"(bit >> 5), "r"(row * W4));
+                if (REFINE) {  // variant = 2 * (upper half of the cell across) + (upper half of the cell along)
+                  const uint32_t var = ((uint32_t)((aqb + qa_) >> (F - 1)) & 1u) * 2u + ((uint32_t)((bqb2 + qb_) >> (F - 1)) & 1u);
+                  boff += var * (SMEM_TAB ? BW * 4u : PW4);
                 }
                 const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(bits) + boff);
                 const uint32_t w0 = p[-1], w1 = p[0], w2 = p[1];
