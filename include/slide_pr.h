@@ -190,12 +190,25 @@ void slide_pr_get_xyz_yaw_from_tf(const double *tf16, double *xyz_yaw4);
 /* ---- batches (BASELINE configs 4 and 5) --------------------------------------------------- */
 /* n_pairs independent findTransformation calls (all-pairs multi-robot matching / streaming
  * submap queries).  maps: array of n_maps pointers to n x 7 rows; pair p matches reference
- * maps[ref_of[p]] against query maps[qry_of[p]].  Index structures of a reference map are
- * built once and reused by consecutive pairs that share it. */
+ * maps[ref_of[p]] against query maps[qry_of[p]].  Every map goes through the map cache once: the
+ * index structures of a reference map are built once, however many pairs use it and in whatever order. */
 int slide_pr_find_transformation_batch(slide_pr_handle *h, const double *const *maps,
                                        const int32_t *map_sizes, int32_t n_maps,
                                        const int32_t *ref_of, const int32_t *qry_of, int32_t n_pairs,
                                        slide_pr_tf_result *out /* n_pairs */);
+
+/* ---- device-resident map cache (one slot per robot) ---------------------------------------------- */
+/* The reference keeps one object map per robot (databaseManager::robotMapDict_, databaseManager.h:99-102)
+ * and deep-copies both maps for every attempt (sloamNode.cpp:603-614).  slide_pr_map_cache_put hands a map
+ * over once per version; its reference-side index is built the first time the map is searched as a
+ * reference and reused by every later pair.  Least recently used slots are dropped beyond 64 maps. */
+int slide_pr_map_cache_put(slide_pr_handle *h, int64_t robot_id, uint64_t version, const double *rows7, int32_t n);
+int slide_pr_map_cache_drop(slide_pr_handle *h, int64_t robot_id);   /* SLIDE_PR_NOT_FOUND if absent */
+int32_t slide_pr_map_cache_size(const slide_pr_handle *h);
+/* PlaceRecognition::findTransformation on two cached maps (inter-robot mode); same outputs as
+ * slide_pr_find_transformation.  out->match.reuse bit 1 tells whether the reference index was reused. */
+int slide_pr_find_transformation_cached(slide_pr_handle *h, int64_t ref_robot_id, int64_t qry_robot_id, int32_t *ref_idx_out,
+                                        int32_t *qry_idx_out, slide_pr_tf_result *out);
 
 /* ---- multi-GPU merge ---------------------------------------------------------------------- */
 /* Packs a local result into the 16-byte record exchanged by the all-gather, and merges

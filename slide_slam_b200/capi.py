@@ -29,6 +29,7 @@ EXPORTS = [
     "slide_pr_merge_records", "slide_pr_match_triangles", "slide_pr_score_hypotheses",
     "slide_pr_match_triangles_labeled", "slide_pr_estimate_tf", "slide_pr_triangle_hypotheses",
     "slide_pr_generate_and_score",
+    "slide_pr_map_cache_put", "slide_pr_map_cache_drop", "slide_pr_map_cache_size", "slide_pr_find_transformation_cached",
     "slide_pr_measure_issue_peaks", "slide_pr_delaunay", "slide_pr_slidegraph_default_params", "slide_pr_run_semantic_clipper",
     "slide_pr_find_inter_loop_closure_with_clipper",
     "slide_clipper_default_params", "slide_pr_clipper_score_pairwise_consistency",
@@ -215,6 +216,11 @@ def lib():
     L.slide_pr_score_hypotheses.argtypes = [C.c_void_p, _dp, C.c_int64, _ip, C.POINTER(MatchResult)]
     L.slide_pr_generate_and_score.argtypes = [C.c_void_p, _dp, _dp, C.c_int32, _dp, _dp, C.c_int32, C.c_double, C.POINTER(MatchResult),
                                               C.POINTER(GenerateInfo), _ip, _ip, _dp, _ip, C.c_int64]
+    L.slide_pr_map_cache_put.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, _dp, C.c_int32]
+    L.slide_pr_map_cache_drop.argtypes = [C.c_void_p, C.c_int64]
+    L.slide_pr_map_cache_size.restype = C.c_int32
+    L.slide_pr_map_cache_size.argtypes = [C.c_void_p]
+    L.slide_pr_find_transformation_cached.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _ip, _ip, C.POINTER(TfResult)]
     L.slide_pr_measure_issue_peaks.argtypes = [C.c_void_p, _dp, _dp, _dp]
     L.slide_pr_delaunay.argtypes = [_dp, C.c_int32, _ip, C.c_int64, _lp]
     L.slide_pr_slidegraph_default_params.argtypes = [C.POINTER(SlidegraphParams)]

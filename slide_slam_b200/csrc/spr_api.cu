@@ -12,8 +12,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <condition_variable>
+#include <climits>
+#include <cstdint>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -138,6 +142,35 @@ thread_local Trace g_trace;
 
 }  // namespace
 
+// Everything derived from ONE reference map: the host index, its device copies and the rows it was built
+// from.  The handle keeps one anonymous slot (maps handed over by value, reused when the same bytes come
+// again) and a cache of slots keyed by robot id (the reference keeps one map per
+// robot in databaseManager::robotMapDict_, databaseManager.h:99-102, and deep-copies it for every attempt,
+// sloamNode.cpp:603-614).
+struct RefSide {
+  spr::RefIndex R;
+  spr::uvec<double> cached_ref;      // the (shifted) reference rows the index in R was built from
+  double cached_reach = -1.0;        // the index' fixed-point format covers |coordinates| up to this
+  slide_pr_params cached_ref_p{};    // parameters the index depends on
+  bool ref_index_valid = false;
+  bool ranks_pending = false;        // stage 2 of the index (rank tables) not built / uploaded yet
+  const double *pending_ref7 = nullptr;
+  DevBuf d_labelbox, d_bitmap, d_rank16, d_rank16b, d_rowrank, d_rowrankb, d_cellref, d_cellrefb, d_cellbase, d_cellbaseb,
+      d_reftab, d_refbase, d_cand, d_cand1, d_vbitmap, d_labof, d_ref7;
+  // cache bookkeeping (unused by the anonymous slot)
+  int64_t robot_id = -1;
+  uint64_t version = 0;
+  int n_rows = 0;
+  bool shifted = false;              // rows are centroid-shifted (inter-robot mode, PR.cpp:752-765)
+  double centroid[2] = {0, 0}, max_abs[2] = {0, 0};   // getCentroid / getMapBoundaries of the map (PR.cpp:713-734)
+  uint64_t last_use = 0;
+  void release() {
+    for (DevBuf *b : {&d_labelbox, &d_bitmap, &d_rank16, &d_rank16b, &d_rowrank, &d_rowrankb, &d_cellref, &d_cellrefb, &d_cellbase,
+                      &d_cellbaseb, &d_reftab, &d_refbase, &d_cand, &d_cand1, &d_vbitmap, &d_labof, &d_ref7})
+      b->release();
+  }
+};
+
 struct slide_pr_handle {
   slide_pr_params p{};
   int device = 0;
@@ -156,8 +189,6 @@ struct slide_pr_handle {
   Worker worker_lattice, worker_query;  // helper threads of slide_pr_prepare
   bool bounds_valid = false;           // the bound planes of the last exhaustive = 2 search are still valid ...
   int bounds_shard_index = 0, bounds_shard_count = 0;  // ... for this shard of the prepared problem
-  bool ranks_pending = false;          // stage 2 of the reference index (rank tables) not built / uploaded yet
-  const double *pending_ref7 = nullptr; // == cached_ref.data() while ranks_pending
   std::string err;
   // prepared problem (host side)
   bool prepared = false;
@@ -168,22 +199,22 @@ struct slide_pr_handle {
   // streaming reuse: the reference-map index and the lattice are rebuilt only when
   // their inputs change (same map bytes / same search ranges), e.g. many submap queries against one
   // accumulated map.  `reuse` in the result tells which were reused.
-  spr::uvec<double> cached_ref;     // the (shifted) reference rows the index in R was built from
   spr::uvec<double> qry_rows;       // copy of the query rows (source of the asynchronous upload)
-  double cached_reach = -1.0;       // the index' fixed-point format covers |coordinates| up to this
-  slide_pr_params cached_ref_p{};   // parameters the index depends on
-  bool ref_index_valid = false;
   double lat_hx = 0, lat_hy = 0, lat_yaw_half = 0;
   slide_pr_params lat_p{};
   bool lattice_valid = false, lattice_on_device = false;
   int reuse_flags = 0;
   int64_t h2d_bytes = 0;
   spr::Lattice L;
-  spr::RefIndex R;
+  RefSide anon;                        // slot of maps handed over by value (slide_pr_prepare & co.)
+  std::map<int64_t, std::unique_ptr<RefSide>> cache;   // slots keyed by robot id (slide_pr_map_cache_put)
+  RefSide *rs = &anon;                 // the slot of the prepared problem
+  uint64_t use_clock = 0;
+  size_t cache_capacity = 64;          // least recently used slots beyond this many are dropped
   spr::QuerySet Q;
   // device side
-  DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_labelbox, d_gbox, d_bitmap, d_rank16, d_rank16b, d_rowrank, d_rowrankb, d_gcnt, d_cellref, d_cellrefb, d_cellbase, d_cellbaseb, d_reftab, d_refbase,
-      d_cand, d_cand1, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ubplanes, d_itemub, d_seed, d_canditems, d_candcount, d_vbitmap, d_labof, d_dgitems, d_dgcount, d_ref7, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
+  DevBuf d_lat, d_chunks, d_cs, d_qxy, d_qdims, d_labelseg, d_qlabel, d_gbox, d_gcnt, d_qrot, d_qrotq, d_qrotq_yx, d_work, d_ubplanes,
+      d_itemub, d_seed, d_canditems, d_candcount, d_dgitems, d_dgcount, d_qry7, d_best, d_counts, d_match, d_stats, d_hyps, d_tri, d_tri_out;
   SprView V{};
   unsigned long long gen_cap = 0;      // capacity (entries) of the generator's match-key buffer, kept across calls
   SprClipper *clipper = nullptr;       // SlideGraph half: device-resident CLIPPER problem (created on first use)
@@ -305,13 +336,14 @@ int slide_pr_create(const slide_pr_params *p, slide_pr_handle **out) {
 void slide_pr_destroy(slide_pr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  for (DevBuf *b : {&h->d_lat, &h->d_chunks, &h->d_cs, &h->d_qxy, &h->d_qdims, &h->d_labelseg, &h->d_qlabel,
-                    &h->d_labelbox, &h->d_gbox, &h->d_bitmap, &h->d_rank16, &h->d_rank16b, &h->d_rowrank, &h->d_rowrankb, &h->d_gcnt, &h->d_cellref, &h->d_cellrefb,
-                    &h->d_cellbase, &h->d_cellbaseb, &h->d_reftab, &h->d_refbase, &h->d_cand, &h->d_cand1, &h->d_qrot,
-                    &h->d_qrotq, &h->d_qrotq_yx, &h->d_work, &h->d_ref7, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps, &h->d_tri, &h->d_tri_out,
-                    &h->d_ubplanes, &h->d_itemub, &h->d_seed, &h->d_canditems, &h->d_candcount,
-                    &h->d_vbitmap, &h->d_labof, &h->d_dgitems, &h->d_dgcount})
+  for (DevBuf *b : {&h->d_lat, &h->d_chunks, &h->d_cs, &h->d_qxy, &h->d_qdims, &h->d_labelseg, &h->d_qlabel, &h->d_gbox, &h->d_gcnt, &h->d_qrot,
+                    &h->d_qrotq, &h->d_qrotq_yx, &h->d_work, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps,
+                    &h->d_tri, &h->d_tri_out, &h->d_ubplanes, &h->d_itemub, &h->d_seed, &h->d_canditems, &h->d_candcount, &h->d_dgitems,
+                    &h->d_dgcount})
     b->release();
+  h->anon.release();
+  for (auto &kv : h->cache) kv.second->release();
+  h->cache.clear();
   spr_clipper_destroy(h->clipper);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -352,37 +384,40 @@ static int upload_lattice(slide_pr_handle *h, cudaStream_t st) {
 static int finish_ranks(slide_pr_handle *h, cudaStream_t st) {
   int rc;
   for (int d = 0; d < 2; d++)
-    if ((rc = spr::build_ref_ranks(h->cached_ref.data(), d, h->R, h->err)) != SLIDE_PR_OK) return rc;
+    if ((rc = spr::build_ref_ranks(h->rs->cached_ref.data(), d, h->rs->R, h->err)) != SLIDE_PR_OK) return rc;
   g_trace.mark("ref_ranks_build");
-  if ((rc = upload(h, h->d_rank16, h->R.rank16[0], st))) return rc;
-  if ((rc = upload(h, h->d_rank16b, h->R.rank16[1], st))) return rc;
-  if ((rc = upload(h, h->d_rowrank, h->R.row_rank[0], st))) return rc;
-  if ((rc = upload(h, h->d_rowrankb, h->R.row_rank[1], st))) return rc;
-  if ((rc = upload(h, h->d_cellref, h->R.cellref[0], st))) return rc;
-  if ((rc = upload(h, h->d_cellrefb, h->R.cellref[1], st))) return rc;
-  if ((rc = upload(h, h->d_cellbase, h->R.cell_base[0], st))) return rc;
-  if ((rc = upload(h, h->d_cellbaseb, h->R.cell_base[1], st))) return rc;
-  if ((rc = upload(h, h->d_cand, h->R.cand[0], st))) return rc;
-  if ((rc = upload(h, h->d_cand1, h->R.cand[1], st))) return rc;
+  if ((rc = upload(h, h->rs->d_rank16, h->rs->R.rank16[0], st))) return rc;
+  if ((rc = upload(h, h->rs->d_rank16b, h->rs->R.rank16[1], st))) return rc;
+  if ((rc = upload(h, h->rs->d_rowrank, h->rs->R.row_rank[0], st))) return rc;
+  if ((rc = upload(h, h->rs->d_rowrankb, h->rs->R.row_rank[1], st))) return rc;
+  if ((rc = upload(h, h->rs->d_cellref, h->rs->R.cellref[0], st))) return rc;
+  if ((rc = upload(h, h->rs->d_cellrefb, h->rs->R.cellref[1], st))) return rc;
+  if ((rc = upload(h, h->rs->d_cellbase, h->rs->R.cell_base[0], st))) return rc;
+  if ((rc = upload(h, h->rs->d_cellbaseb, h->rs->R.cell_base[1], st))) return rc;
+  if ((rc = upload(h, h->rs->d_cand, h->rs->R.cand[0], st))) return rc;
+  if ((rc = upload(h, h->rs->d_cand1, h->rs->R.cand[1], st))) return rc;
   SprView &V = h->V;
-  V.rank16[0] = h->d_rank16.as<uint16_t>();
-  V.rank16[1] = h->d_rank16b.as<uint16_t>();
-  V.row_rank[0] = h->d_rowrank.as<uint32_t>();
-  V.row_rank[1] = h->d_rowrankb.as<uint32_t>();
-  V.cellref[0] = h->d_cellref.as<uint16_t>();
-  V.cellref[1] = h->d_cellrefb.as<uint16_t>();
-  V.cell_base[0] = h->d_cellbase.as<uint32_t>();
-  V.cell_base[1] = h->d_cellbaseb.as<uint32_t>();
-  V.cand[0] = h->d_cand.as<SprCand>();
-  V.cand[1] = h->d_cand1.as<SprCand>();
-  h->ranks_pending = false;
+  V.rank16[0] = h->rs->d_rank16.as<uint16_t>();
+  V.rank16[1] = h->rs->d_rank16b.as<uint16_t>();
+  V.row_rank[0] = h->rs->d_rowrank.as<uint32_t>();
+  V.row_rank[1] = h->rs->d_rowrankb.as<uint32_t>();
+  V.cellref[0] = h->rs->d_cellref.as<uint16_t>();
+  V.cellref[1] = h->rs->d_cellrefb.as<uint16_t>();
+  V.cell_base[0] = h->rs->d_cellbase.as<uint32_t>();
+  V.cell_base[1] = h->rs->d_cellbaseb.as<uint32_t>();
+  V.cand[0] = h->rs->d_cand.as<SprCand>();
+  V.cand[1] = h->rs->d_cand1.as<SprCand>();
+  h->rs->ranks_pending = false;
   g_trace.mark("ref_ranks_upload");
   return SLIDE_PR_OK;
 }
 
-int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7, int32_t n_qry,
-                     double half_x, double half_y) {
+// slot: where the reference-map index lives (the anonymous slot or a cache entry).  trusted: ref7 IS the
+// slot's cached rows (a cache entry at its current version), so the byte comparison is skipped.
+static int prepare_impl(slide_pr_handle *h, RefSide *slot, bool trusted, const double *ref7, int32_t n_ref, const double *qry7,
+                        int32_t n_qry, double half_x, double half_y) {
   if (!h) return SLIDE_PR_ERR_INVALID;
+  h->rs = slot;
   h->prepared = false;
   h->bounds_valid = false;
   if (n_ref < 0 || n_qry < 0 || (n_ref > 0 && !ref7) || (n_qry > 0 && !qry7)) { h->err = "bad map arguments"; return SLIDE_PR_ERR_INVALID; }
@@ -445,45 +480,45 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   }
   const double reach = qrad + std::max(std::fabs(half_x), std::fabs(half_y)) + h->p.match_xy_step_size;
   // reference index: a function of the reference rows, the cell size / thresholds and the reach
-  const bool same_ref = h->ref_index_valid && (int)(h->cached_ref.size() / 7) == n_ref && reach <= h->cached_reach &&
-                        h->cached_ref_p.match_xy_step_size == h->p.match_xy_step_size &&
-                        h->cached_ref_p.match_threshold == h->p.match_threshold &&
-                        h->cached_ref_p.match_threshold_dimension == h->p.match_threshold_dimension &&
-                        (n_ref == 0 || std::memcmp(h->cached_ref.data(), ref7, (size_t)n_ref * 7 * sizeof(double)) == 0);
+  const bool same_ref = h->rs->ref_index_valid && (int)(h->rs->cached_ref.size() / 7) == n_ref && reach <= h->rs->cached_reach &&
+                        h->rs->cached_ref_p.match_xy_step_size == h->p.match_xy_step_size &&
+                        h->rs->cached_ref_p.match_threshold == h->p.match_threshold &&
+                        h->rs->cached_ref_p.match_threshold_dimension == h->p.match_threshold_dimension &&
+                        (trusted || n_ref == 0 || std::memcmp(h->rs->cached_ref.data(), ref7, (size_t)n_ref * 7 * sizeof(double)) == 0);
   auto start_query_job = [&]() {
     h->worker_query.submit([h, qry7, n_qry, &query_err]() {
       cudaSetDevice(h->device);
-      return spr::build_query_set(h->R, qry7, n_qry, h->Q, query_err);
+      return spr::build_query_set(h->rs->R, qry7, n_qry, h->Q, query_err);
     });
     query_started = true;
   };
   if (!same_ref) {
     // stage 1 of the reference index (bitmaps, landmark tables): all the bound phase needs.  The
     // rank tables (stage 2) are built and uploaded by the search while the bound phase runs.
-    h->ref_index_valid = false;
-    h->ranks_pending = false;
+    h->rs->ref_index_valid = false;
+    h->rs->ranks_pending = false;
     const double reach_cap = reach * 1.25;  // head-room so that slightly larger queries reuse the index
-    if ((rc = spr::build_ref_grid(h->p, ref7, n_ref, reach_cap, h->R, h->err)) != SLIDE_PR_OK) return rc;
+    if ((rc = spr::build_ref_grid(h->p, ref7, n_ref, reach_cap, h->rs->R, h->err)) != SLIDE_PR_OK) return rc;
     start_query_job();  // the query set only needs the labels and the grid
-    if ((rc = spr::build_ref_marks(h->p, ref7, n_ref, h->R, h->err)) != SLIDE_PR_OK) return rc;
+    if ((rc = spr::build_ref_marks(h->p, ref7, n_ref, h->rs->R, h->err)) != SLIDE_PR_OK) return rc;
     g_trace.mark("ref_bitmaps_build");
-    h->cached_ref.assign(ref7, ref7 + (size_t)n_ref * 7);
-    h->cached_reach = reach_cap; h->cached_ref_p = h->p;
-    h->ref_index_valid = true;
-    h->ranks_pending = true;
-    if ((rc = upload(h, h->d_labelbox, h->R.labelbox, st))) return rc;
+    if (!trusted) h->rs->cached_ref.assign(ref7, ref7 + (size_t)n_ref * 7);
+    h->rs->cached_reach = h->rs->R.reach_limit; h->rs->cached_ref_p = h->p;
+    h->rs->ref_index_valid = true;
+    h->rs->ranks_pending = true;
+    if ((rc = upload(h, h->rs->d_labelbox, h->rs->R.labelbox, st))) return rc;
     // 4 zero words in front of (and slack behind) the planes: the bound kernel reads the word before
     // and the word after a probe's base word
-    SPR_CUDA(h, h->d_bitmap.ensure(h->R.bitmap.size() * sizeof(uint32_t) + 64));
-    SPR_CUDA(h, cudaMemsetAsync(h->d_bitmap.p, 0, 16, st));
-    SPR_CUDA(h, cudaMemsetAsync(static_cast<char *>(h->d_bitmap.p) + 16 + h->R.bitmap.size() * sizeof(uint32_t), 0, 32, st));
-    if (!h->R.bitmap.empty())
-      SPR_CUDA(h, cudaMemcpyAsync(static_cast<char *>(h->d_bitmap.p) + 16, h->R.bitmap.data(), h->R.bitmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    h->h2d_bytes += (int64_t)(h->R.bitmap.size() * sizeof(uint32_t));
-    if ((rc = upload(h, h->d_reftab, h->R.reftab, st))) return rc;
-    if ((rc = upload(h, h->d_refbase, h->R.ref_base, st))) return rc;
-    if ((rc = upload(h, h->d_labof, h->R.lab_of, st))) return rc;
-    if ((rc = upload(h, h->d_ref7, h->cached_ref, st))) return rc;
+    SPR_CUDA(h, h->rs->d_bitmap.ensure(h->rs->R.bitmap.size() * sizeof(uint32_t) + 64));
+    SPR_CUDA(h, cudaMemsetAsync(h->rs->d_bitmap.p, 0, 16, st));
+    SPR_CUDA(h, cudaMemsetAsync(static_cast<char *>(h->rs->d_bitmap.p) + 16 + h->rs->R.bitmap.size() * sizeof(uint32_t), 0, 32, st));
+    if (!h->rs->R.bitmap.empty())
+      SPR_CUDA(h, cudaMemcpyAsync(static_cast<char *>(h->rs->d_bitmap.p) + 16, h->rs->R.bitmap.data(), h->rs->R.bitmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    h->h2d_bytes += (int64_t)(h->rs->R.bitmap.size() * sizeof(uint32_t));
+    if ((rc = upload(h, h->rs->d_reftab, h->rs->R.reftab, st))) return rc;
+    if ((rc = upload(h, h->rs->d_refbase, h->rs->R.ref_base, st))) return rc;
+    if ((rc = upload(h, h->rs->d_labof, h->rs->R.lab_of, st))) return rc;
+    if ((rc = upload(h, h->rs->d_ref7, h->rs->cached_ref, st))) return rc;
     g_trace.mark("ref_bitmaps_upload");
   } else {
     h->reuse_flags |= 2;
@@ -522,25 +557,25 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   V.qdims = h->d_qdims.as<double>();
   V.label_gseg = h->d_labelseg.as<int32_t>();
   V.qlabel = h->d_qlabel.as<int32_t>();
-  V.n_labels = (int32_t)h->R.labels.size();
+  V.n_labels = (int32_t)h->rs->R.labels.size();
   V.n_ref = n_ref;
-  V.labelbox = h->d_labelbox.as<SprBox>();
-  V.bitmap = h->d_bitmap.as<uint32_t>() + 4;  // behind the zero words in front
-  V.rank16[0] = h->d_rank16.as<uint16_t>();
-  V.rank16[1] = h->d_rank16b.as<uint16_t>();
-  V.row_rank[0] = h->d_rowrank.as<uint32_t>();
-  V.row_rank[1] = h->d_rowrankb.as<uint32_t>();
-  V.cellref[0] = h->d_cellref.as<uint16_t>();
-  V.cellref[1] = h->d_cellrefb.as<uint16_t>();
-  V.cell_base[0] = h->d_cellbase.as<uint32_t>();
-  V.cell_base[1] = h->d_cellbaseb.as<uint32_t>();
-  V.reftab = h->d_reftab.as<double>();
-  V.ref_base = h->d_refbase.as<uint32_t>();
-  V.cand[0] = h->d_cand.as<SprCand>();
-  V.cand[1] = h->d_cand1.as<SprCand>();
-  V.grid = h->R.grid;
-  V.Tstar = h->R.Tstar;
-  V.Sstar = h->R.Sstar;
+  V.labelbox = h->rs->d_labelbox.as<SprBox>();
+  V.bitmap = h->rs->d_bitmap.as<uint32_t>() + 4;  // behind the zero words in front
+  V.rank16[0] = h->rs->d_rank16.as<uint16_t>();
+  V.rank16[1] = h->rs->d_rank16b.as<uint16_t>();
+  V.row_rank[0] = h->rs->d_rowrank.as<uint32_t>();
+  V.row_rank[1] = h->rs->d_rowrankb.as<uint32_t>();
+  V.cellref[0] = h->rs->d_cellref.as<uint16_t>();
+  V.cellref[1] = h->rs->d_cellrefb.as<uint16_t>();
+  V.cell_base[0] = h->rs->d_cellbase.as<uint32_t>();
+  V.cell_base[1] = h->rs->d_cellbaseb.as<uint32_t>();
+  V.reftab = h->rs->d_reftab.as<double>();
+  V.ref_base = h->rs->d_refbase.as<uint32_t>();
+  V.cand[0] = h->rs->d_cand.as<SprCand>();
+  V.cand[1] = h->rs->d_cand1.as<SprCand>();
+  V.grid = h->rs->R.grid;
+  V.Tstar = h->rs->R.Tstar;
+  V.Sstar = h->rs->R.Sstar;
   V.thr_dim = h->p.match_threshold_dimension;
   V.ignore_dim = h->p.ignore_dimension;
   // no synchronisation here: every upload reads page-locked vectors owned by the handle (the
@@ -551,6 +586,12 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
   h->prepare_ms = now_ms() - t0;
   g_trace.mark("query_upload");
   return SLIDE_PR_OK;
+}
+
+int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7, int32_t n_qry,
+                     double half_x, double half_y) {
+  if (!h) return SLIDE_PR_ERR_INVALID;
+  return prepare_impl(h, &h->anon, false, ref7, n_ref, qry7, n_qry, half_x, half_y);
 }
 
 static void fill_result_header(slide_pr_handle *h, slide_pr_match_result *out) {
@@ -699,7 +740,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
         }
       }
     }
-    if (h->ranks_pending) {
+    if (h->rs->ranks_pending) {
       // the bound launches above keep the GPU busy: build the rank tables now and upload them on
       // the copy stream; the seed / verification kernels wait for the copies
       if ((rc = finish_ranks(h, h->copy_stream)) != SLIDE_PR_OK) return rc;
@@ -725,21 +766,21 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
       for (size_t i = 0; i < active.size() && !slow_verify; i++) {
         SprLaunch T = K;
         T.dir = d; T.label = active[i];
-        T.tab_cells = h->R.cell_base[d][T.label + 1] - h->R.cell_base[d][T.label];
-        T.tab_refs = h->R.ref_base[T.label + 1] - h->R.ref_base[T.label];
-        T.tab_cell_base = h->R.cell_base[d][T.label];
-        T.tab_ref_base = h->R.ref_base[T.label];
+        T.tab_cells = h->rs->R.cell_base[d][T.label + 1] - h->rs->R.cell_base[d][T.label];
+        T.tab_refs = h->rs->R.ref_base[T.label + 1] - h->rs->R.ref_base[T.label];
+        T.tab_cell_base = h->rs->R.cell_base[d][T.label];
+        T.tab_ref_base = h->rs->R.ref_base[T.label];
         slow_verify = spr_score_smem_warps(h->V, T, h->tables_mode) == 0;
       }
-    if (h->refine_min >= 0 && h->R.mark_rc2 > 0 && slow_verify) {
+    if (h->refine_min >= 0 && h->rs->R.mark_rc2 > 0 && slow_verify) {
       size_t dcap[2];
       for (int d = 0; d < 2; d++) dcap[d] = (size_t)((h->L.dir_end[d] - h->L.dir_begin[d]) / (2 * SPR_WARP_CHUNKS)) * (size_t)n_yaw;
       const size_t vwords = 4 * (size_t)h->V.grid.label_stride * (size_t)std::max(h->V.n_labels, 1) + 16;
       SPR_CUDA(h, h->d_dgitems.ensure((dcap[0] + dcap[1]) * sizeof(uint32_t) + 64));
       SPR_CUDA(h, h->d_dgcount.ensure(2 * sizeof(uint32_t)));
-      SPR_CUDA(h, h->d_vbitmap.ensure(vwords * sizeof(uint32_t)));
+      SPR_CUDA(h, h->rs->d_vbitmap.ensure(vwords * sizeof(uint32_t)));
       SPR_CUDA(h, cudaMemsetAsync(h->d_dgcount.p, 0, 2 * sizeof(uint32_t), st));
-      h->V.vbitmap = h->d_vbitmap.as<uint32_t>() + 4;
+      h->V.vbitmap = h->rs->d_vbitmap.as<uint32_t>() + 4;
       for (uint32_t d = 0; d < 2; d++) {
         if (h->L.dir_end[d] <= h->L.dir_begin[d]) continue;
         B.chunk_begin = h->L.dir_begin[d]; B.chunk_end = h->L.dir_end[d]; B.dir = d;
@@ -747,8 +788,8 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
                                               h->d_dgcount.as<uint32_t>() + d, h->sm_count, st));
         launches++;
       }
-      SPR_CUDA(h, spr_launch_variant_planes(h->V, h->d_vbitmap.as<uint32_t>(), vwords, h->d_ref7.as<double>(), h->d_labof.as<int32_t>(),
-                                            h->n_ref, h->p.match_xy_step_size, h->R.mark_rc, h->R.mark_rc2,
+      SPR_CUDA(h, spr_launch_variant_planes(h->V, h->rs->d_vbitmap.as<uint32_t>(), vwords, h->rs->d_ref7.as<double>(), h->rs->d_labof.as<int32_t>(),
+                                            h->n_ref, h->p.match_xy_step_size, h->rs->R.mark_rc, h->rs->R.mark_rc2,
                                             h->d_dgcount.as<uint32_t>(), (uint32_t)h->refine_min, h->sm_count, st));
       launches += 2;
       for (uint32_t d = 0; d < 2; d++) {
@@ -799,7 +840,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     K.item_ub = h->d_itemub.as<uint32_t>();
     K.ub_nplanes = n_planes;
   }
-  if (h->ranks_pending && !bounds_only && (rc = finish_ranks(h, st)) != SLIDE_PR_OK) return rc;  // exhaustive path
+  if (h->rs->ranks_pending && !bounds_only && (rc = finish_ranks(h, st)) != SLIDE_PR_OK) return rc;  // exhaustive path
   auto run_range = [&](const uint32_t begin[2], const uint32_t end[2]) -> int {
     // verification phase of the pruned search: few candidate items per pass, so the label passes
     // of the two bitmap directions (disjoint counters) run concurrently on two streams
@@ -820,10 +861,10 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
           K.cand_count = h->d_candcount.as<uint32_t>() + d;
         }
         K.first = i == 0; K.last = i + 1 == active.size();
-        K.tab_cells = K.label >= 0 ? h->R.cell_base[d][K.label + 1] - h->R.cell_base[d][K.label] : 0u;
-        K.tab_refs = K.label >= 0 ? h->R.ref_base[K.label + 1] - h->R.ref_base[K.label] : 0u;
-        K.tab_cell_base = K.label >= 0 ? h->R.cell_base[d][K.label] : 0u;
-        K.tab_ref_base = K.label >= 0 ? h->R.ref_base[K.label] : 0u;
+        K.tab_cells = K.label >= 0 ? h->rs->R.cell_base[d][K.label + 1] - h->rs->R.cell_base[d][K.label] : 0u;
+        K.tab_refs = K.label >= 0 ? h->rs->R.ref_base[K.label + 1] - h->rs->R.ref_base[K.label] : 0u;
+        K.tab_cell_base = K.label >= 0 ? h->rs->R.cell_base[d][K.label] : 0u;
+        K.tab_ref_base = K.label >= 0 ? h->rs->R.ref_base[K.label] : 0u;
         if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
         SPR_CUDA(h, spr_launch_score_lattice(h->V, K, h->tables_mode, h->sm_count, sd, &launches));
         K.work_counter++;
@@ -946,8 +987,8 @@ int slide_pr_extract(slide_pr_handle *h, int64_t hyp_index, int32_t *ref_idx_out
   io->R_t[3] = s; io->R_t[4] = c;  io->R_t[5] = ty;
   io->R_t[6] = 0; io->R_t[7] = 0;  io->R_t[8] = 1;
   cudaStream_t st = h->stream;
-  SPR_CUDA(h, spr_launch_extract(h->d_ref7.as<double>(), h->n_ref, h->d_qry7.as<double>(), h->n_qry, c, s, tx, ty,
-                                 h->R.Tstar, h->R.Sstar, h->p.match_threshold_dimension, h->p.ignore_dimension,
+  SPR_CUDA(h, spr_launch_extract(h->rs->d_ref7.as<double>(), h->n_ref, h->d_qry7.as<double>(), h->n_qry, c, s, tx, ty,
+                                 h->rs->R.Tstar, h->rs->R.Sstar, h->p.match_threshold_dimension, h->p.ignore_dimension,
                                  h->d_match.as<int32_t>(), st));
   io->gpu_launches += 1;
   if ((int)h->h_match.size() < std::max(h->n_qry, 1)) h->h_match.resize(std::max(h->n_qry, 1));
@@ -966,11 +1007,11 @@ int slide_pr_extract(slide_pr_handle *h, int64_t hyp_index, int32_t *ref_idx_out
   return SLIDE_PR_OK;
 }
 
-int slide_pr_match_maps(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7, int32_t n_qry,
-                        double half_x, double half_y, int32_t *ref_idx_out, int32_t *qry_idx_out,
-                        slide_pr_match_result *out) {
+static int match_maps_impl(slide_pr_handle *h, RefSide *slot, bool trusted, const double *ref7, int32_t n_ref, const double *qry7,
+                           int32_t n_qry, double half_x, double half_y, int32_t *ref_idx_out, int32_t *qry_idx_out,
+                           slide_pr_match_result *out) {
   if (!h || !out) return SLIDE_PR_ERR_INVALID;
-  int rc = slide_pr_prepare(h, ref7, n_ref, qry7, n_qry, half_x, half_y);
+  int rc = prepare_impl(h, slot, trusted, ref7, n_ref, qry7, n_qry, half_x, half_y);
   if (rc != SLIDE_PR_OK) return rc;
   if ((rc = slide_pr_search(h, nullptr, out)) != SLIDE_PR_OK) return rc;
   if (out->status == SLIDE_PR_SANITY_RETURN || out->best_hyp_index < 0) return SLIDE_PR_OK;
@@ -985,11 +1026,64 @@ int slide_pr_match_maps(slide_pr_handle *h, const double *ref7, int32_t n_ref, c
   return SLIDE_PR_OK;
 }
 
+int slide_pr_match_maps(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7, int32_t n_qry,
+                        double half_x, double half_y, int32_t *ref_idx_out, int32_t *qry_idx_out,
+                        slide_pr_match_result *out) {
+  if (!h || !out) return SLIDE_PR_ERR_INVALID;
+  return match_maps_impl(h, &h->anon, false, ref7, n_ref, qry7, n_qry, half_x, half_y, ref_idx_out, qry_idx_out, out);
+}
+
 void slide_pr_get_xyz_yaw_from_tf(const double *tf16, double *xyz_yaw4) { spr::xyz_yaw_from_tf(tf16, xyz_yaw4); }
 
 int slide_pr_solve_lsq(const double *tgt3, const double *src3, int32_t k, double *xyz_yaw4, double *transform16) {
   if (!tgt3 || !src3 || !xyz_yaw4 || !transform16 || k < 0) return SLIDE_PR_ERR_INVALID;
   spr::solve_lsq(tgt3, src3, k, xyz_yaw4, transform16);
+  return SLIDE_PR_OK;
+}
+
+// findTransformation after MatchMaps (PR.cpp:845-944): inlier gate, then the raw lattice transform with the
+// centroid shift reverted, or the closed-form refinement on the matched pairs.  ref / qry: the rows MatchMaps
+// saw (centroid-shifted in inter-robot mode).
+static int finish_transformation(const slide_pr_params &p, const double *ref, const double *qry, const double *cref, const double *cqry,
+                                 const int32_t *ri, const int32_t *qi, slide_pr_tf_result *out) {
+  const slide_pr_match_result &m = out->match;
+  std::memcpy(out->R_t, m.R_t, sizeof(m.R_t));
+  // findTransformation starts from best_num_inliers_out = 0 and MatchMaps leaves it untouched on
+  // its sanity-check return (PR.cpp:819, 169-175)
+  out->best_num_inliers = m.status == SLIDE_PR_SANITY_RETURN ? 0 : m.best_num_inliers;
+  out->n_matched = m.status == SLIDE_PR_SANITY_RETURN ? 0 : m.n_matched;
+  if (out->best_num_inliers < p.min_num_inliers) { out->found = 0; return SLIDE_PR_NOT_FOUND; }  // PR.cpp:849
+  out->found = 1;
+  if (!p.use_lsq) {                                                    // PR.cpp:882-905
+    double raw[16] = {0};
+    raw[0] = m.R_t[0]; raw[1] = m.R_t[1]; raw[4] = m.R_t[3]; raw[5] = m.R_t[4];
+    raw[10] = 1; raw[15] = 1;
+    raw[3] = m.R_t[2]; raw[7] = m.R_t[5]; raw[11] = 0;
+    if (p.inter_loop_closure) {                                        // PR.cpp:947-967
+      double H1[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, H2[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+      H1[3] = cref[0]; H1[7] = cref[1];
+      H2[3] = -cqry[0]; H2[7] = -cqry[1];
+      double T1[16];
+      spr::mat4_mul(H1, raw, T1);
+      spr::mat4_mul(T1, H2, out->transform);
+    } else {
+      std::memcpy(out->transform, raw, sizeof(raw));
+    }
+    spr::xyz_yaw_from_tf(out->transform, out->xyz_yaw);
+  } else {                                                             // PR.cpp:906-944
+    const int k = out->n_matched;
+    std::vector<double> tgt(3 * (size_t)std::max(k, 1)), src(3 * (size_t)std::max(k, 1));
+    for (int i = 0; i < k; i++) {
+      const double *r = ref + 7 * (size_t)ri[i], *q = qry + 7 * (size_t)qi[i];
+      tgt[3 * i] = r[1]; tgt[3 * i + 1] = r[2]; tgt[3 * i + 2] = r[3];
+      src[3 * i] = q[1]; src[3 * i + 1] = q[2]; src[3 * i + 2] = q[3];
+      if (p.inter_loop_closure) {                                      // PR.cpp:925-937
+        tgt[3 * i] += cref[0]; tgt[3 * i + 1] += cref[1];
+        src[3 * i] += cqry[0]; src[3 * i + 1] += cqry[1];
+      }
+    }
+    spr::solve_lsq(tgt.data(), src.data(), k, out->xyz_yaw, out->transform);
+  }
   return SLIDE_PR_OK;
 }
 
@@ -1039,45 +1133,7 @@ int slide_pr_find_transformation(slide_pr_handle *h, const double *ref7_in, int3
   int rc = slide_pr_match_maps(h, ref.data(), n_ref, qry.data(), n_qry, half_x, half_y, ri, qi, &out->match);
   g_trace.flush("find_transformation");
   if (rc != SLIDE_PR_OK) return rc;
-  const slide_pr_match_result &m = out->match;
-  std::memcpy(out->R_t, m.R_t, sizeof(m.R_t));
-  // findTransformation starts from best_num_inliers_out = 0 and MatchMaps leaves it untouched on
-  // its sanity-check return (PR.cpp:819, 169-175)
-  out->best_num_inliers = m.status == SLIDE_PR_SANITY_RETURN ? 0 : m.best_num_inliers;
-  out->n_matched = m.status == SLIDE_PR_SANITY_RETURN ? 0 : m.n_matched;
-  if (out->best_num_inliers < p.min_num_inliers) { out->found = 0; return SLIDE_PR_NOT_FOUND; }  // PR.cpp:849
-  out->found = 1;
-  if (!p.use_lsq) {                                                    // PR.cpp:882-905
-    double raw[16] = {0};
-    raw[0] = m.R_t[0]; raw[1] = m.R_t[1]; raw[4] = m.R_t[3]; raw[5] = m.R_t[4];
-    raw[10] = 1; raw[15] = 1;
-    raw[3] = m.R_t[2]; raw[7] = m.R_t[5]; raw[11] = 0;
-    if (p.inter_loop_closure) {                                        // PR.cpp:947-967
-      double H1[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, H2[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-      H1[3] = cref[0]; H1[7] = cref[1];
-      H2[3] = -cqry[0]; H2[7] = -cqry[1];
-      double T1[16];
-      spr::mat4_mul(H1, raw, T1);
-      spr::mat4_mul(T1, H2, out->transform);
-    } else {
-      std::memcpy(out->transform, raw, sizeof(raw));
-    }
-    spr::xyz_yaw_from_tf(out->transform, out->xyz_yaw);
-  } else {                                                             // PR.cpp:906-944
-    const int k = out->n_matched;
-    std::vector<double> tgt(3 * (size_t)std::max(k, 1)), src(3 * (size_t)std::max(k, 1));
-    for (int i = 0; i < k; i++) {
-      const double *r = ref.data() + 7 * (size_t)ri[i], *q = qry.data() + 7 * (size_t)qi[i];
-      tgt[3 * i] = r[1]; tgt[3 * i + 1] = r[2]; tgt[3 * i + 2] = r[3];
-      src[3 * i] = q[1]; src[3 * i + 1] = q[2]; src[3 * i + 2] = q[3];
-      if (p.inter_loop_closure) {                                      // PR.cpp:925-937
-        tgt[3 * i] += cref[0]; tgt[3 * i + 1] += cref[1];
-        src[3 * i] += cqry[0]; src[3 * i + 1] += cqry[1];
-      }
-    }
-    spr::solve_lsq(tgt.data(), src.data(), k, out->xyz_yaw, out->transform);
-  }
-  return SLIDE_PR_OK;
+  return finish_transformation(p, ref.data(), qry.data(), cref, cqry, ri, qi, out);
 }
 
 int slide_pr_find_inter_loop_closure(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7,
@@ -1132,17 +1188,130 @@ int slide_pr_find_intra_loop_closure(slide_pr_handle *h, const double *meas7, in
   return SLIDE_PR_OK;
 }
 
+// ---- device-resident map cache ---------------------------------------------
+// The reference keeps one object map per robot (databaseManager::robotMapDict_, databaseManager.h:99-102)
+// and deep-copies both maps of a pair for every attempt (sloamNode.cpp:603-614).  Here a map is handed
+// over once per version: its centroid-shifted rows stay page-locked on the host and on the device, and
+// the reference-side index (occupancy bitmaps, rank tables) is built the first time the map is searched
+// AS A REFERENCE and reused by every later pair until the version changes.
+int slide_pr_map_cache_put(slide_pr_handle *h, int64_t robot_id, uint64_t version, const double *rows7, int32_t n) {
+  if (!h || n < 0 || (n > 0 && !rows7)) return SLIDE_PR_ERR_INVALID;
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  auto it = h->cache.find(robot_id);
+  if (it != h->cache.end() && it->second->version == version && it->second->n_rows == n &&
+      it->second->shifted == (h->p.inter_loop_closure != 0)) {
+    it->second->last_use = ++h->use_clock;
+    return SLIDE_PR_OK;
+  }
+  for (int i = 0; i < n; i++)
+    if (!std::isfinite(rows7[7 * (size_t)i + 1]) || !std::isfinite(rows7[7 * (size_t)i + 2])) { h->err = "non-finite map coordinate"; return SLIDE_PR_ERR_NONFINITE; }
+  // uploads of the slot being replaced may still be in flight on the handle's stream
+  SPR_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (it == h->cache.end()) {
+    while (h->cache.size() >= h->cache_capacity) {   // drop the least recently used slot
+      auto lru = h->cache.begin();
+      for (auto k = h->cache.begin(); k != h->cache.end(); ++k)
+        if (k->second->last_use < lru->second->last_use) lru = k;
+      if (h->rs == lru->second.get()) { h->rs = &h->anon; h->prepared = false; }
+      lru->second->release();
+      h->cache.erase(lru);
+    }
+    it = h->cache.emplace(robot_id, std::unique_ptr<RefSide>(new RefSide())).first;
+  }
+  RefSide &E = *it->second;
+  if (h->rs == &E) h->prepared = false;
+  E.robot_id = robot_id; E.version = version; E.n_rows = n;
+  E.ref_index_valid = false; E.ranks_pending = false;
+  E.shifted = h->p.inter_loop_closure != 0;
+  E.cached_ref.assign(rows7, rows7 + (size_t)n * 7);
+  double c[2] = {0, 0}, b[2] = {0, 0};
+  if (E.shifted) {                                                     // getCentroid / getMapBoundaries, PR.cpp:713-734, 752-765
+    for (int i = 0; i < n; i++) { c[0] += rows7[7 * (size_t)i + 1]; c[1] += rows7[7 * (size_t)i + 2]; }
+    c[0] /= (double)n; c[1] /= (double)n;
+    for (int i = 0; i < n; i++) {
+      double *r = E.cached_ref.data() + 7 * (size_t)i;
+      r[1] -= c[0]; r[2] -= c[1];
+      b[0] = std::max(b[0], std::abs(r[1])); b[1] = std::max(b[1], std::abs(r[2]));
+    }
+  }
+  E.centroid[0] = c[0]; E.centroid[1] = c[1]; E.max_abs[0] = b[0]; E.max_abs[1] = b[1];
+  E.last_use = ++h->use_clock;
+  return SLIDE_PR_OK;
+}
+
+int slide_pr_map_cache_drop(slide_pr_handle *h, int64_t robot_id) {
+  if (!h) return SLIDE_PR_ERR_INVALID;
+  auto it = h->cache.find(robot_id);
+  if (it == h->cache.end()) return SLIDE_PR_NOT_FOUND;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->rs == it->second.get()) { h->rs = &h->anon; h->prepared = false; }
+  it->second->release();
+  h->cache.erase(it);
+  return SLIDE_PR_OK;
+}
+
+int32_t slide_pr_map_cache_size(const slide_pr_handle *h) { return h ? (int32_t)h->cache.size() : 0; }
+
+// findTransformation (PR.cpp:736-945) on two cached maps; inter-robot mode (the cache holds centroid-shifted rows)
+int slide_pr_find_transformation_cached(slide_pr_handle *h, int64_t ref_robot_id, int64_t qry_robot_id, int32_t *ref_idx_out,
+                                        int32_t *qry_idx_out, slide_pr_tf_result *out) {
+  if (!h || !out) return SLIDE_PR_ERR_INVALID;
+  std::memset(out, 0, sizeof(*out));
+  const slide_pr_params &p = h->p;
+  if (!p.inter_loop_closure) { h->err = "the map cache serves the inter-robot search (inter_loop_closure = 1)"; return SLIDE_PR_ERR_INVALID; }
+  auto ir = h->cache.find(ref_robot_id), iq = h->cache.find(qry_robot_id);
+  if (ir == h->cache.end() || iq == h->cache.end()) { h->err = "robot id not in the map cache"; return SLIDE_PR_ERR_INVALID; }
+  RefSide &Rf = *ir->second, &Qr = *iq->second;
+  if (!Rf.shifted || !Qr.shifted) { h->err = "cached map was stored in intra-robot mode: put it again"; return SLIDE_PR_ERR_INVALID; }
+  g_trace.start();
+  Rf.last_use = ++h->use_clock; Qr.last_use = ++h->use_clock;
+  double max_x = std::max(Rf.max_abs[0], Qr.max_abs[0]), max_y = std::max(Rf.max_abs[1], Qr.max_abs[1]);   // PR.cpp:771-774
+  if (!p.disable_yaw_search) { const double m = std::max(max_x, max_y); max_x = m; max_y = m; }           // :777-782
+  out->half_x = max_x * p.dilation_factor; out->half_y = max_y * p.dilation_factor;                       // :786-787
+  out->yaw_half = p.match_yaw_half_range;
+  out->centroid_ref[0] = Rf.centroid[0]; out->centroid_ref[1] = Rf.centroid[1];
+  out->centroid_qry[0] = Qr.centroid[0]; out->centroid_qry[1] = Qr.centroid[1];
+  std::vector<int32_t> ri_own, qi_own;
+  int32_t *ri = ref_idx_out, *qi = qry_idx_out;
+  if (!ri) { ri_own.resize(std::max(Qr.n_rows, 1)); ri = ri_own.data(); }
+  if (!qi) { qi_own.resize(std::max(Qr.n_rows, 1)); qi = qi_own.data(); }
+  const int rc = match_maps_impl(h, &Rf, true, Rf.cached_ref.data(), Rf.n_rows, Qr.cached_ref.data(), Qr.n_rows, out->half_x, out->half_y,
+                                 ri, qi, &out->match);
+  g_trace.flush("find_transformation_cached");
+  if (rc != SLIDE_PR_OK) return rc;
+  return finish_transformation(p, Rf.cached_ref.data(), Qr.cached_ref.data(), out->centroid_ref, out->centroid_qry, ri, qi, out);
+}
+
+// n_pairs findTransformation calls over n_maps maps (all-pairs multi-robot matching, BASELINE config 4): every
+// map goes through the cache once, so a map's reference-side index is built once however many pairs use it.
 int slide_pr_find_transformation_batch(slide_pr_handle *h, const double *const *maps, const int32_t *map_sizes,
                                        int32_t n_maps, const int32_t *ref_of, const int32_t *qry_of, int32_t n_pairs,
                                        slide_pr_tf_result *out) {
-  if (!h || !maps || !map_sizes || !ref_of || !qry_of || !out) return SLIDE_PR_ERR_INVALID;
-  for (int p = 0; p < n_pairs; p++) {
+  if (!h || !maps || !map_sizes || !ref_of || !qry_of || !out || n_maps < 0 || n_pairs < 0) return SLIDE_PR_ERR_INVALID;
+  for (int p = 0; p < n_pairs; p++)
     if (ref_of[p] < 0 || ref_of[p] >= n_maps || qry_of[p] < 0 || qry_of[p] >= n_maps) { h->err = "pair index out of range"; return SLIDE_PR_ERR_INVALID; }
-    const int rc = slide_pr_find_transformation(h, maps[ref_of[p]], map_sizes[ref_of[p]], maps[qry_of[p]],
-                                                map_sizes[qry_of[p]], nullptr, nullptr, &out[p]);
-    if (rc < 0) return rc;
+  if (!h->p.inter_loop_closure) {   // intra-robot mode keeps raw frames: no shared index, plain calls
+    for (int p = 0; p < n_pairs; p++) {
+      const int rc = slide_pr_find_transformation(h, maps[ref_of[p]], map_sizes[ref_of[p]], maps[qry_of[p]], map_sizes[qry_of[p]], nullptr, nullptr, &out[p]);
+      if (rc < 0) return rc;
+    }
+    return SLIDE_PR_OK;
   }
-  return SLIDE_PR_OK;
+  const int64_t id0 = INT64_MIN / 2;   // private id range of this call
+  const size_t keep = h->cache_capacity;
+  h->cache_capacity = std::max<size_t>(keep, h->cache.size() + (size_t)n_maps);
+  int rc = SLIDE_PR_OK;
+  for (int m = 0; m < n_maps && rc >= 0; m++) rc = slide_pr_map_cache_put(h, id0 + m, 1, maps[m], map_sizes[m]);
+  // pairs in the caller's order; consecutive pairs with the same reference map reuse its index at once,
+  // later ones find it in the cache
+  for (int p = 0; p < n_pairs && rc >= 0; p++) {
+    rc = slide_pr_find_transformation_cached(h, id0 + ref_of[p], id0 + qry_of[p], nullptr, nullptr, &out[p]);
+    if (rc > 0) rc = SLIDE_PR_OK;  // "not found" is a per-pair result
+  }
+  for (int m = 0; m < n_maps; m++) slide_pr_map_cache_drop(h, id0 + m);
+  h->cache_capacity = keep;
+  return rc < 0 ? rc : SLIDE_PR_OK;
 }
 
 void slide_pr_pack_record(const slide_pr_match_result *r, int32_t rank, slide_pr_topk_record *rec) {
@@ -1307,7 +1476,7 @@ int slide_pr_generate_and_score(slide_pr_handle *h, const double *tris_model6, c
   slide_pr_generate_info local{}, *I = info ? info : &local;
   std::memset(I, 0, sizeof(*I));
   if (t_model == 0 || t_data == 0) return SLIDE_PR_OK;
-  if (h->ranks_pending) { const int rrc = finish_ranks(h, st); if (rrc != SLIDE_PR_OK) return rrc; }
+  if (h->rs->ranks_pending) { const int rrc = finish_ranks(h, st); if (rrc != SLIDE_PR_OK) return rrc; }
   GenDevice G;
   int rc = gen_match_on_device(h, tris_model6, labels_model3, t_model, tris_data6, labels_data3, t_data, threshold, &G);
   if (rc != SLIDE_PR_OK) return rc;
@@ -1391,7 +1560,7 @@ int slide_pr_score_hypotheses(slide_pr_handle *h, const double *hyps4, int64_t n
   if (!h || !out || (n > 0 && !hyps4) || n < 0) return SLIDE_PR_ERR_INVALID;
   if (!h->prepared) { h->err = "slide_pr_score_hypotheses before slide_pr_prepare"; return SLIDE_PR_ERR_INVALID; }
   SPR_CUDA(h, cudaSetDevice(h->device));
-  if (h->ranks_pending) { const int rrc = finish_ranks(h, h->stream); if (rrc != SLIDE_PR_OK) return rrc; }
+  if (h->rs->ranks_pending) { const int rrc = finish_ranks(h, h->stream); if (rrc != SLIDE_PR_OK) return rrc; }
   cudaStream_t st = h->stream;
   fill_result_header(h, out);
   out->status = SLIDE_PR_OK;

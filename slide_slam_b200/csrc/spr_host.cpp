@@ -410,6 +410,10 @@ int build_ref_grid(const slide_pr_params &p, const double *ref7, int n_ref, doub
   if (F < 6) { err = "search region too large relative to match_xy_step_size for the fixed-point cell format"; return SLIDE_PR_ERR_UNSUPPORTED; }
   G.F = F;
   G.S = std::ldexp(1.0, F) / c;
+  // the largest reach this fixed-point format still covers: a cached index stays valid for any query map /
+  // search range up to it (the grid itself does not depend on the reach)
+  R.reach_limit = reach + ((std::ldexp(1.0, 30 - F) - 3.0) * c - far);
+  if (!(R.reach_limit > reach)) R.reach_limit = reach;
   // plane d: rows = across cells + 2 zero rows; bits = 32 pad + along cells + >= 64 pad
   const int across[2] = {G.GX, G.GY}, along[2] = {G.GY, G.GX};
   for (int d = 0; d < 2; d++) {

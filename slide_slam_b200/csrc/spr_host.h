@@ -83,6 +83,7 @@ struct RefIndex {
   double Tstar = 0, Sstar = 0;
   double mark_rc = 0, mark_rc2 = 0; // radius (cells) / squared radius of the marking predicate (0: nothing matches)
   int n_ref = 0;
+  double reach_limit = 0;           // largest reach covered by grid.F (set by build_ref_grid)
   // carried from build_ref_bitmaps to build_ref_ranks
   struct Entry { uint32_t ref; int32_t nx, ny; };  // landmark `ref` marks cell (nx, ny); ascending landmark order
   std::vector<Entry> entries;

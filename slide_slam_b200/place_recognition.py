@@ -280,6 +280,40 @@ class PlaceRecognition:
         self.last = out
         return rc == capi.OK, tf.reshape(4, 4)
 
+    # -- device-resident map cache (databaseManager::robotMapDict_, databaseManager.h:99-102) -------
+    def cache_put(self, robot_id: int, version: int, objects):
+        rows = capi.as_rows7(objects)
+        self._check(self._lib.slide_pr_map_cache_put(self._h, int(robot_id), int(version), capi.dptr(rows), len(rows)))
+        self._cache_sizes = getattr(self, "_cache_sizes", {})
+        self._cache_sizes[int(robot_id)] = len(rows)
+
+    def cache_drop(self, robot_id: int) -> bool:
+        return self._lib.slide_pr_map_cache_drop(self._h, int(robot_id)) == capi.OK
+
+    def cache_size(self) -> int:
+        return int(self._lib.slide_pr_map_cache_size(self._h))
+
+    def findTransformationCached(self, ref_robot_id: int, qry_robot_id: int):
+        """findTransformation on two cached maps; returns what findTransformation returns."""
+        nq = max(getattr(self, "_cache_sizes", {}).get(int(qry_robot_id), 1), 1)
+        ri, qi = np.zeros(nq, np.int32), np.zeros(nq, np.int32)
+        out = capi.TfResult()
+        rc = self._check(self._lib.slide_pr_find_transformation_cached(self._h, int(ref_robot_id), int(qry_robot_id), capi.iptr(ri),
+                                                                       capi.iptr(qi), C.byref(out)))
+        k = max(out.n_matched, 0)
+        return (rc == capi.OK, np.array(out.xyz_yaw[:]), np.array(out.transform[:]).reshape(4, 4), out, ri[:k].copy(), qi[:k].copy())
+
+    def findTransformationBatch(self, maps, pairs):
+        """slide_pr_find_transformation_batch: maps = list of n x 7 arrays, pairs = [(ref_index, qry_index), ...]."""
+        rows = [capi.as_rows7(m) for m in maps]
+        ptrs = (C.POINTER(C.c_double) * len(rows))(*[capi.dptr(r) for r in rows])
+        sizes = np.array([len(r) for r in rows], np.int32)
+        ro = np.array([p[0] for p in pairs], np.int32); qo = np.array([p[1] for p in pairs], np.int32)
+        out = (capi.TfResult * max(len(pairs), 1))()
+        self._check(self._lib.slide_pr_find_transformation_batch(self._h, ptrs, capi.iptr(sizes), len(rows), capi.iptr(ro), capi.iptr(qo),
+                                                                 len(pairs), out))
+        return [out[i] for i in range(len(pairs))]
+
     # -- PlaceRecognition::findInterLoopClosureWithClipper (PR.cpp:541-630) --------------------------
     def findInterLoopClosureWithClipper(self, reference_objects, query_objects):
         """SlideGraph: Delaunay triangles -> descriptor matching -> CLIPPER -> 2-D Kabsch.
