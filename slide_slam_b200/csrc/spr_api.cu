@@ -608,6 +608,41 @@ static void fill_result_header(slide_pr_handle *h, slide_pr_match_result *out) {
   out->reuse = h->reuse_flags;
 }
 
+// Exact passes over plane (label l, direction d): row bands whose tables fit in shared memory.  Fills the band
+// fields of K for band b; band_rows == 0 means "tables read in place" (one pass).  The rank tables must have
+// been built (finish_ranks).
+struct PlanePlan { uint32_t band_rows; int stage_reftab; uint32_t n_bands; };
+static void set_band(slide_pr_handle *h, SprLaunch &K, uint32_t d, int l, const PlanePlan &P, uint32_t b) {
+  const spr::RefIndex &R = h->rs->R;
+  const uint32_t Rr = (uint32_t)R.grid.R[d];
+  K.dir = d; K.label = l;
+  const uint32_t label_cells = l >= 0 ? R.cell_base[d][l + 1] - R.cell_base[d][l] : 0u;
+  K.tab_refs = l >= 0 ? R.ref_base[l + 1] - R.ref_base[l] : 0u;
+  K.tab_cell_base = l >= 0 ? R.cell_base[d][l] : 0u;
+  K.tab_ref_base = l >= 0 ? R.ref_base[l] : 0u;
+  K.stage_reftab = P.stage_reftab;
+  if (!P.band_rows || l < 0) { K.row_begin = K.row_end = 0; K.tab_rank_lo = 0; K.tab_cells = label_cells; return; }
+  const uint32_t *rr = R.row_rank[d].data() + (size_t)l * Rr;
+  K.row_begin = b * P.band_rows;
+  K.row_end = std::min(Rr, (b + 1) * P.band_rows);
+  K.tab_rank_lo = rr[K.row_begin];
+  K.tab_cells = (K.row_end < Rr ? rr[K.row_end] : label_cells) - K.tab_rank_lo;
+}
+static PlanePlan plan_plane(slide_pr_handle *h, const SprLaunch &K0, uint32_t d, int l) {
+  PlanePlan P{0u, 0, 1u};
+  if (l < 0 || h->tables_mode != SPR_TABLES_AUTO) return P;
+  const spr::RefIndex &R = h->rs->R;
+  spr_score_plan(h->V, d, R.cell_base[d][l + 1] - R.cell_base[d][l], R.ref_base[l + 1] - R.ref_base[l], &P.band_rows, &P.stage_reftab);
+  if (!P.band_rows) return P;
+  P.n_bands = ((uint32_t)R.grid.R[d] + P.band_rows - 1) / P.band_rows;
+  SprLaunch T = K0;
+  for (uint32_t b = 0; b < P.n_bands; b++) {   // every band must really fit (the slot table is not spread evenly)
+    set_band(h, T, d, l, P, b);
+    if (spr_score_smem_warps(h->V, T, h->tables_mode) < 8) return PlanePlan{0u, 0, 1u};
+  }
+  return P;
+}
+
 int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_pr_match_result *out) {
   if (!h || !out) return SLIDE_PR_ERR_INVALID;
   if (!h->prepared) { h->err = "slide_pr_search before slide_pr_prepare"; return SLIDE_PR_ERR_INVALID; }
@@ -673,11 +708,6 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     if (h->Q.label_gseg[l + 1] > h->Q.label_gseg[l]) active.push_back(l);
   if (active.empty()) active.push_back(-1);  // no query can match: every hypothesis scores 0
   K.n_chunks_total = (uint32_t)h->L.chunks.size();
-  if (active.size() > 1) {
-    const size_t per = h->V.nqp > 65535 ? 4 : 2;
-    SPR_CUDA(h, h->d_gcnt.ensure((size_t)n_yaw * (size_t)K.n_chunks_total * 32 * per + 64));
-  }
-  K.gcnt = h->d_gcnt.p;
   auto next_counter = [&]() -> int {  // (re)arm a batch of work-item counters with a single memset
     if (passes_left == 0) {
       passes_left = 4096;
@@ -761,18 +791,16 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     // Worth its cost (about one more bound phase over the candidates) only when the exact
     // verification is expensive, i.e. when some pass has to read its tables in place (planes too
     // large for shared memory, e.g. 20 000-landmark maps); SLIDE_PR_REFINE_MIN=0 forces it.
+    // (expensive = some plane does not fit in shared memory as a whole: it is verified in row bands or in place)
     bool slow_verify = h->refine_forced;
     for (uint32_t d = 0; d < 2 && !slow_verify; d++)
       for (size_t i = 0; i < active.size() && !slow_verify; i++) {
-        SprLaunch T = K;
-        T.dir = d; T.label = active[i];
-        T.tab_cells = h->rs->R.cell_base[d][T.label + 1] - h->rs->R.cell_base[d][T.label];
-        T.tab_refs = h->rs->R.ref_base[T.label + 1] - h->rs->R.ref_base[T.label];
-        T.tab_cell_base = h->rs->R.cell_base[d][T.label];
-        T.tab_ref_base = h->rs->R.ref_base[T.label];
-        slow_verify = spr_score_smem_warps(h->V, T, h->tables_mode) == 0;
+        const PlanePlan P = plan_plane(h, K, d, active[i]);
+        slow_verify = P.band_rows == 0 || P.n_bands > 1;
       }
-    if (h->refine_min >= 0 && h->rs->R.mark_rc2 > 0 && slow_verify) {
+    // (not in the bound-only first half of a sharded search: the second half refines against the shared
+    // incumbent, which is at least as good as this shard's own seeds)
+    if (h->refine_min >= 0 && h->rs->R.mark_rc2 > 0 && slow_verify && !(bounds_only && !o.counts_out)) {
       size_t dcap[2];
       for (int d = 0; d < 2; d++) dcap[d] = (size_t)((h->L.dir_end[d] - h->L.dir_begin[d]) / (2 * SPR_WARP_CHUNKS)) * (size_t)n_yaw;
       const size_t vwords = 4 * (size_t)h->V.grid.label_stride * (size_t)std::max(h->V.n_labels, 1) + 16;
@@ -846,7 +874,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     // of the two bitmap directions (disjoint counters) run concurrently on two streams
     const bool fork = prune && end[0] > begin[0] && end[1] > begin[1];
     if (fork) {
-      if (passes_left < 2 * active.size()) passes_left = 0;  // re-arm the work counters before the fork
+      if (passes_left < 1024) passes_left = 0;  // re-arm the work counters before the fork (one per pass: label x row band)
       if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
       SPR_CUDA(h, cudaEventRecord(h->ev_fork, st));
       SPR_CUDA(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
@@ -855,20 +883,20 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
       if (end[d] <= begin[d]) continue;
       cudaStream_t sd = fork && d == 1 ? h->side_stream : st;
       for (size_t i = 0; i < active.size(); i++) {
-        K.chunk_begin = begin[d]; K.chunk_end = end[d]; K.dir = d; K.label = active[i];
-        if (prune) {
-          K.cand_items = h->d_canditems.as<uint32_t>() + cand_off[d];
-          K.cand_count = h->d_candcount.as<uint32_t>() + d;
+        const PlanePlan P = plan_plane(h, K, d, active[i]);
+        for (uint32_t b = 0; b < P.n_bands; b++) {
+          K.chunk_begin = begin[d]; K.chunk_end = end[d];
+          set_band(h, K, d, active[i], P, b);
+          if (prune) {
+            K.cand_items = h->d_canditems.as<uint32_t>() + cand_off[d];
+            K.cand_count = h->d_candcount.as<uint32_t>() + d;
+          }
+          K.first = i == 0 && b == 0; K.last = i + 1 == active.size() && b + 1 == P.n_bands;
+          if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
+          SPR_CUDA(h, spr_launch_score_lattice(h->V, K, h->tables_mode, h->sm_count, sd, &launches));
+          K.work_counter++;
+          passes_left--;
         }
-        K.first = i == 0; K.last = i + 1 == active.size();
-        K.tab_cells = K.label >= 0 ? h->rs->R.cell_base[d][K.label + 1] - h->rs->R.cell_base[d][K.label] : 0u;
-        K.tab_refs = K.label >= 0 ? h->rs->R.ref_base[K.label + 1] - h->rs->R.ref_base[K.label] : 0u;
-        K.tab_cell_base = K.label >= 0 ? h->rs->R.cell_base[d][K.label] : 0u;
-        K.tab_ref_base = K.label >= 0 ? h->rs->R.ref_base[K.label] : 0u;
-        if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
-        SPR_CUDA(h, spr_launch_score_lattice(h->V, K, h->tables_mode, h->sm_count, sd, &launches));
-        K.work_counter++;
-        passes_left--;
       }
     }
     if (fork) {
@@ -877,6 +905,16 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     }
     return SLIDE_PR_OK;
   };
+  if (!bounds_only) {
+    // per-hypothesis counters carried between the passes of a chunk range (labels x row bands) in HBM
+    bool carry = active.size() > 1;
+    for (uint32_t d = 0; d < 2 && !carry; d++) carry = plan_plane(h, K, d, active[0]).n_bands > 1;
+    if (carry) {
+      const size_t per = h->V.nqp > 65535 ? 4 : 2;
+      SPR_CUDA(h, h->d_gcnt.ensure((size_t)n_yaw * (size_t)K.n_chunks_total * 32 * per + 64));
+    }
+    K.gcnt = h->d_gcnt.p;
+  }
   int rings_scored = 0;
   if (bounds_only) {
     rings_scored = h->L.rings;

@@ -72,19 +72,22 @@ struct SprTabLayout {
   uint32_t reftab_b, bits_b, r16_b, rr_b, cellref_b;                 // bytes to copy
   uint32_t reftab_skip, cellref_skip;                                // leading elements (doubles / u16) to skip
 };
-__host__ __device__ static inline SprTabLayout spr_tab_layout(uint32_t PW, uint32_t R, uint32_t cell_base, uint32_t cells,
+// band_rows rows of the plane (a multiple of 8, starting at a multiple of 8) + one all-zero row behind them;
+// cell_first / cells: absolute rank of the band's first marked cell and their number; refs == 0: the
+// landmark table is not staged (read in place).
+__host__ __device__ static inline SprTabLayout spr_tab_layout(uint32_t W, uint32_t band_rows, uint32_t cell_first, uint32_t cells,
                                                               uint32_t ref_base, uint32_t refs) {
   SprTabLayout o;
   o.reftab_skip = 5u * (ref_base & 1u);
-  o.cellref_skip = cell_base & 7u;
-  o.reftab_b = ((5u * ((ref_base & 1u) + refs) * 8u) + 15u) & ~15u;
-  o.bits_b = PW * 4u;                  // PW is a multiple of 8 words
-  o.r16_b = PW * 2u;
-  o.rr_b = R * 4u;                     // R is a multiple of 8 rows
-  o.cellref_b = (((cell_base & 7u) + cells) * 2u + 15u) & ~15u;
+  o.cellref_skip = cell_first & 7u;
+  o.reftab_b = refs ? ((5u * ((ref_base & 1u) + refs) * 8u) + 15u) & ~15u : 0u;
+  o.bits_b = band_rows * W * 4u;
+  o.r16_b = band_rows * W * 2u;
+  o.rr_b = band_rows * 4u;
+  o.cellref_b = (((cell_first & 7u) + cells) * 2u + 15u) & ~15u;
   uint32_t w = 0;
   o.reftab_w = w;  w += o.reftab_b >> 2;
-  o.bits_w = w;    w += o.bits_b >> 2;
+  o.bits_w = w;    w += (o.bits_b >> 2) + ((W + 3u) & ~3u);   // + the zero row (kept 16-byte aligned)
   o.r16_w = w;     w += o.r16_b >> 2;
   o.rr_w = w;      w += o.rr_b >> 2;
   o.cellref_w = w; w += o.cellref_b >> 2;
@@ -183,10 +186,16 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
   const int32_t F = G.F;
   const uint32_t d = K.dir;
   const int l = K.label;
-  const uint32_t W = (uint32_t)G.W[d], Rm1 = (uint32_t)G.R[d] - 1u, maxbit = (uint32_t)G.maxbit[d];
+  const uint32_t W = (uint32_t)G.W[d], maxbit = (uint32_t)G.maxbit[d];
+  // Row band [row_begin, row_end) of the plane handled by this pass: staged as band_rows rows + one all-zero
+  // row; rows outside the band clamp onto the zero row (unsigned min), so the probe code is the same as for
+  // a whole plane.  Tables read in place cover the whole plane (rows 0 and R - 1 are its zero rows).
+  const uint32_t band_rows = SMEM_TAB ? K.row_end - K.row_begin : (uint32_t)G.R[d];
+  const uint32_t Rm1 = SMEM_TAB ? band_rows : (uint32_t)G.R[d] - 1u;
+  const int32_t row_shift = SMEM_TAB ? (int32_t)(K.row_begin << F) : 0;
 
   // tables of this pass' plane (bits, ranks, per-cell landmark slots, the label's landmark
-  // table): staged into shared memory once per CTA, or read in place
+  // table): a row band of them staged into shared memory once per CTA, or read in place
   SprTables T = spr_global_tables(V, d, l < 0 ? 0 : l);
   const SprTables GT = T;
   SprTabLayout Lo{};
@@ -196,9 +205,9 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
   if (SMEM_TAB) {
     // The tables are staged by the first warp of the CTA that has work (a CTA of the verification
     // phase may find no candidate item at all): that warp arms an mbarrier with the byte count
-    // and issues five TMA bulk copies (cp.async.bulk global -> shared); every warp with work
+    // and issues the TMA bulk copies (cp.async.bulk global -> shared); every warp with work
     // waits on the barrier's phase before its first probe.
-    Lo = spr_tab_layout(G.plane_words[d], (uint32_t)G.R[d], GT.cell_base, K.tab_cells, V.ref_base[l], K.tab_refs);
+    Lo = spr_tab_layout(W, band_rows, GT.cell_base + K.tab_rank_lo, K.tab_cells, V.ref_base[l], K.stage_reftab ? K.tab_refs : 0u);
     bar = reinterpret_cast<uint64_t *>(smem + Lo.total_w - 4);
     stage_flag = smem + Lo.total_w - 2;
     if (threadIdx.x == 0) {
@@ -206,12 +215,14 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
       *stage_flag = 0u;
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (uint32_t i = threadIdx.x; i < ((W + 3u) & ~3u); i += blockDim.x) smem[Lo.bits_w + band_rows * W + i] = 0u;  // the zero row
     __syncthreads();
     T.bits = smem + Lo.bits_w;
     T.r16 = reinterpret_cast<uint16_t *>(smem + Lo.r16_w);
     T.row_rank = smem + Lo.rr_w;
-    T.cellref = reinterpret_cast<uint16_t *>(smem + Lo.cellref_w) + Lo.cellref_skip;
-    T.reftab = reinterpret_cast<double *>(smem + Lo.reftab_w) + Lo.reftab_skip;
+    // label-relative ranks index the staged slice: it starts at the band's first cell
+    T.cellref = reinterpret_cast<uint16_t *>(smem + Lo.cellref_w) + Lo.cellref_skip - K.tab_rank_lo;
+    if (K.stage_reftab) T.reftab = reinterpret_cast<double *>(smem + Lo.reftab_w) + Lo.reftab_skip;
   }
   WarpState ws;
   ws.cnt = smem + (tab_bytes >> 2) + warp * SPR_WARP_WORDS(CNT32);
@@ -219,7 +230,12 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
   ws.qcount = 0;
   unsigned long long best = 0ull, n_hits = 0ull, n_inl = 0ull, n_probed = 0ull, n_skipped = 0ull;
 
-  const SprBox lb = l >= 0 ? V.labelbox[l] : SprBox{0, -(1 << 30), 0, -(1 << 30)};
+  SprBox lb = l >= 0 ? V.labelbox[l] : SprBox{0, -(1 << 30), 0, -(1 << 30)};
+  if (SMEM_TAB) {  // marked cells inside the band only (plane row r holds across cell r - 1): query groups that cannot reach it are skipped
+    const int32_t band_lo = ((int32_t)K.row_begin - 1) << F, band_hi = ((int32_t)K.row_end - 1) << F;
+    if (d == 0) { lb.x0 = max(lb.x0, band_lo); lb.x1 = min(lb.x1, band_hi); }
+    else        { lb.y0 = max(lb.y0, band_lo); lb.y1 = min(lb.y1, band_hi); }
+  }
   const int g0 = l >= 0 ? V.label_gseg[l] : 0, g1 = l >= 0 ? V.label_gseg[l + 1] : 0;
   const int32_t *q_fx = d ? V.qrotq_yx : V.qrotq_xy;
 
@@ -265,11 +281,11 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
     if (SMEM_TAB && !staged) {
       if (lane == 0 && atomicExch(stage_flag, 1u) == 0u) {
         spr_mbar_expect_tx(bar, Lo.reftab_b + Lo.bits_b + Lo.r16_b + Lo.rr_b + Lo.cellref_b);
-        spr_bulk_g2s(smem + Lo.reftab_w, GT.reftab - Lo.reftab_skip, Lo.reftab_b, bar);
-        spr_bulk_g2s(smem + Lo.bits_w, GT.bits, Lo.bits_b, bar);
-        spr_bulk_g2s(smem + Lo.r16_w, GT.r16, Lo.r16_b, bar);
-        spr_bulk_g2s(smem + Lo.rr_w, GT.row_rank, Lo.rr_b, bar);
-        spr_bulk_g2s(smem + Lo.cellref_w, GT.cellref - Lo.cellref_skip, Lo.cellref_b, bar);
+        if (Lo.reftab_b) spr_bulk_g2s(smem + Lo.reftab_w, GT.reftab - Lo.reftab_skip, Lo.reftab_b, bar);
+        spr_bulk_g2s(smem + Lo.bits_w, GT.bits + (size_t)K.row_begin * W, Lo.bits_b, bar);
+        spr_bulk_g2s(smem + Lo.r16_w, GT.r16 + (size_t)K.row_begin * W, Lo.r16_b, bar);
+        spr_bulk_g2s(smem + Lo.rr_w, GT.row_rank + K.row_begin, Lo.rr_b, bar);
+        spr_bulk_g2s(smem + Lo.cellref_w, GT.cellref + K.tab_rank_lo - Lo.cellref_skip, Lo.cellref_b, bar);
       }
       for (uint32_t spin = 0; !spr_mbar_try_wait(bar, 0u); spin++)
         if (spin > 200000000u) __trap();  // a lost copy must not hang the GPU
@@ -278,7 +294,7 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
     spr_cnt_zero<CNT32>(ws.cnt, lane);
     const int32_t aq0 = spr_fx(across, G.S);
     const int32_t bq0 = spr_fx(__ldg(V.lat + along_off), G.S);
-    const int32_t aqb = spr_bias_across(aq0, F), bqb = spr_bias_along(bq0, F);
+    const int32_t aqb = spr_bias_across(aq0, F) - row_shift, bqb = spr_bias_along(bq0, F);
     // patch window of the warp's 1024 translations (unbiased fixed point)
     const int32_t big = 1 << 30;
     const bool live = valid != 0u;
@@ -435,18 +451,38 @@ static cudaError_t spr_launch_cfg(const SprView &V, const SprLaunch &K, int n_wg
   return cudaGetLastError();
 }
 
-// warps per CTA of the shared-memory-resident variant for this pass; 0: the tables are read in place
+// warps per CTA of the shared-memory-resident variant for this pass (its band, K.row_begin .. K.row_end);
+// 0: the tables are read in place
 int spr_score_smem_warps(const SprView &V, const SprLaunch &K, int tables_mode) {
   const bool cnt32 = V.nqp > 65535;
   const size_t warp_bytes = (size_t)(cnt32 ? SPR_WARP_WORDS(true) : SPR_WARP_WORDS(false)) * 4;
-  const uint32_t tab = spr_tab_layout(V.grid.plane_words[K.dir], (uint32_t)V.grid.R[K.dir], K.tab_cell_base, K.tab_cells,
-                                      K.tab_ref_base, K.tab_refs).total_w * 4u;
-  int smem_warps = 0;
-  if (tables_mode == SPR_TABLES_AUTO && K.label >= 0 && K.tab_refs < SPR_CELL_MULTI && (size_t)tab + 8 * warp_bytes <= SPR_SMEM_LIMIT) {
-    smem_warps = (int)((SPR_SMEM_LIMIT - tab) / warp_bytes);
-    if (smem_warps > 24) smem_warps = 24;
-  }
-  return smem_warps >= 8 ? smem_warps : 0;
+  if (tables_mode != SPR_TABLES_AUTO || K.label < 0 || K.tab_refs >= SPR_CELL_MULTI || K.row_end <= K.row_begin) return 0;
+  const uint32_t tab = spr_tab_layout((uint32_t)V.grid.W[K.dir], K.row_end - K.row_begin, K.tab_cell_base + K.tab_rank_lo, K.tab_cells,
+                                      K.tab_ref_base, K.stage_reftab ? K.tab_refs : 0u).total_w * 4u;
+  if ((size_t)tab + 8 * warp_bytes > SPR_SMEM_LIMIT) return 0;
+  const int smem_warps = (int)((SPR_SMEM_LIMIT - tab) / warp_bytes);
+  return smem_warps > 24 ? 24 : smem_warps;
+}
+
+// Row bands of plane (label, dir) for the exact passes: the whole plane when its tables leave room for at
+// least 16 warps' counters (24 on BASELINE config 2), otherwise bands of a multiple of 8 rows sized for 16
+// warps with the landmark table staged only if it is small.  The per-cell slot table is assumed spread evenly
+// over the rows with a factor 2 of slack; spr_score_smem_warps gives the exact verdict per band.
+void spr_score_plan(const SprView &V, uint32_t dir, uint32_t label_cells, uint32_t label_refs, uint32_t *band_rows, int *stage_reftab) {
+  const bool cnt32 = V.nqp > 65535;
+  const size_t warp_bytes = (size_t)(cnt32 ? SPR_WARP_WORDS(true) : SPR_WARP_WORDS(false)) * 4;
+  const size_t W = (size_t)V.grid.W[dir], R = (size_t)V.grid.R[dir];
+  const size_t reftab_bytes = 40 * (size_t)label_refs + 32;
+  const size_t whole = reftab_bytes + (R + 1) * W * 4 + R * W * 2 + R * 4 + 2 * (size_t)label_cells + 64;
+  if (whole + 16 * warp_bytes <= SPR_SMEM_LIMIT) { *band_rows = (uint32_t)R; *stage_reftab = 1; return; }
+  *stage_reftab = reftab_bytes <= 48 * 1024;
+  const size_t budget = SPR_SMEM_LIMIT - 16 * warp_bytes - (*stage_reftab ? reftab_bytes : 0) - W * 4 - 128;
+  const double per_row = (double)(W * 6 + 4) + 2.0 * 2.0 * (double)label_cells / (double)R;
+  size_t rows = (size_t)((double)budget / per_row);
+  rows &= ~(size_t)7;
+  if (rows < 8) { *band_rows = 0; return; }   // a single row band does not fit: read in place
+  const size_t bands = (R + rows - 1) / rows;
+  *band_rows = (uint32_t)((((R + bands - 1) / bands) + 7) & ~(size_t)7);
 }
 
 cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int tables_mode, int sm_count,
@@ -466,11 +502,11 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int t
   const size_t warp_bytes = (size_t)(cnt32 ? SPR_WARP_WORDS(true) : SPR_WARP_WORDS(false)) * 4;
   if (n_launches) (*n_launches)++;  // K.work_counter was zeroed by the caller (one memset for all passes)
 
-  // shared-memory-resident plane: one CTA per SM with as many warps as fit next to the tables
-  const uint32_t tab = spr_tab_layout(V.grid.plane_words[K.dir], (uint32_t)V.grid.R[K.dir], K.tab_cell_base, K.tab_cells,
-                                      K.tab_ref_base, K.tab_refs).total_w * 4u;
+  // shared-memory-resident band: one CTA per SM with as many warps as fit next to the tables
   const int smem_warps = spr_score_smem_warps(V, K, tables_mode);
   if (smem_warps >= 8) {
+    const uint32_t tab = spr_tab_layout((uint32_t)V.grid.W[K.dir], K.row_end - K.row_begin, K.tab_cell_base + K.tab_rank_lo, K.tab_cells,
+                                        K.tab_ref_base, K.stage_reftab ? K.tab_refs : 0u).total_w * 4u;
     const long long want = (n_items + smem_warps - 1) / smem_warps;
     const int grid = (int)(want < sm_count ? want : sm_count);
     const size_t smem = (size_t)tab + (size_t)smem_warps * warp_bytes;

@@ -21,8 +21,12 @@ struct SprLaunch {
   uint32_t n_chunks_total;          // size of the chunk list (indexes the global counters)
   int32_t  label;                   // label bucket probed by this pass; -1: no queries at all
   uint32_t dir;                     // bitmap direction of every chunk in [chunk_begin, chunk_end)
-  uint32_t tab_cells, tab_refs;     // marked cells / landmarks of (label, dir): sizes of the staged tables
-  uint32_t tab_cell_base, tab_ref_base; // their first cell / landmark (alignment of the bulk copies)
+  uint32_t row_begin, row_end;      // row band of the plane whose tables this pass stages in shared memory (multiples of 8;
+                                    //   the whole plane: 0 .. R); hits outside the band belong to another pass
+  uint32_t tab_rank_lo, tab_cells;  // label-relative rank of the band's first marked cell, marked cells in the band
+  uint32_t tab_refs;                // landmarks of the label
+  uint32_t tab_cell_base, tab_ref_base; // absolute rank of the label's first cell / first landmark row (alignment of the bulk copies)
+  int32_t  stage_reftab;            // 1: the label's landmark table is staged too; 0: read in place
   int32_t  first, last;             // first / last pass over these chunks: counters start at 0 / are reduced
   int32_t  shard_index, shard_count;
   void    *gcnt;                    // device: per-hypothesis inlier counters carried between passes
@@ -77,6 +81,8 @@ cudaError_t spr_launch_rotate(const SprView &V, int32_t *qrotq_xy, int32_t *qrot
 
 // one (label, direction) pass of the lattice search
 int spr_score_smem_warps(const SprView &V, const SprLaunch &K, int tables_mode);  // 0: this pass reads its tables in place
+// row bands of plane (label, dir) for the exact passes (band_rows == 0: read in place)
+void spr_score_plan(const SprView &V, uint32_t dir, uint32_t label_cells, uint32_t label_refs, uint32_t *band_rows, int *stage_reftab);
 cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int tables_mode, int sm_count,
                                      cudaStream_t st, int *n_launches);
 

@@ -24,6 +24,9 @@
 #ifndef SPB_THREADS
 #define SPB_THREADS 768
 #endif
+#ifndef SPB_GLOBAL_MINB
+#define SPB_GLOBAL_MINB 3   // resident 256-thread CTAs per SM of the variant that reads the planes in place
+#endif
 
 __device__ __forceinline__ uint32_t spb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void spb_mbar_init(uint64_t *bar, uint32_t count) {
@@ -72,7 +75,7 @@ __device__ __forceinline__ void spb_ripple(uint32_t (&P)[PLANES], uint32_t c, in
 // picks one of four bitmap variants by the half-cell the point falls in (spr_variant_mark_kernel),
 // planes read in place; the counters start from zero and replace the first bound.
 template <int PLANES, bool SMEM_TAB, bool REFINE>
-__global__ void __launch_bounds__(SMEM_TAB ? SPB_THREADS : 256, SMEM_TAB ? 1 : 3)
+__global__ void __launch_bounds__(SMEM_TAB ? SPB_THREADS : 256, SMEM_TAB ? 1 : SPB_GLOBAL_MINB)
 spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constant__ SprBoundLaunch B, const int n_dg_local,
                          const long long n_items) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -553,7 +556,7 @@ static cudaError_t spb_launch(const SprView &V, const SprBoundLaunch &B, int n_d
     const long long want = (n_items + SPB_THREADS / 32 - 1) / (SPB_THREADS / 32);
     spr_bound_lattice_kernel<PLANES, true, false><<<(int)(want < sm_count ? want : sm_count), SPB_THREADS, smem, st>>>(V, B, n_dg_local, n_items);
   } else {
-    const long long want = (n_items + 7) / 8, cap = (long long)sm_count * 3;
+    const long long want = (n_items + 7) / 8, cap = (long long)sm_count * SPB_GLOBAL_MINB;
     if (B.cand_items)
       spr_bound_lattice_kernel<PLANES, false, true><<<(int)(want < cap ? want : cap), 256, 0, st>>>(V, B, n_dg_local, n_items);
     else
