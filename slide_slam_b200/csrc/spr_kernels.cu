@@ -75,8 +75,9 @@ struct SprTabLayout {
 // band_rows rows of the plane (a multiple of 8, starting at a multiple of 8) + one all-zero row behind them;
 // cell_first / cells: absolute rank of the band's first marked cell and their number; refs == 0: the
 // landmark table is not staged (read in place).
+// zero_row: 0 for a whole plane (its own first / last rows are the zero rows).
 __host__ __device__ static inline SprTabLayout spr_tab_layout(uint32_t W, uint32_t band_rows, uint32_t cell_first, uint32_t cells,
-                                                              uint32_t ref_base, uint32_t refs) {
+                                                              uint32_t ref_base, uint32_t refs, uint32_t zero_row) {
   SprTabLayout o;
   o.reftab_skip = 5u * (ref_base & 1u);
   o.cellref_skip = cell_first & 7u;
@@ -87,7 +88,7 @@ __host__ __device__ static inline SprTabLayout spr_tab_layout(uint32_t W, uint32
   o.cellref_b = (((cell_first & 7u) + cells) * 2u + 15u) & ~15u;
   uint32_t w = 0;
   o.reftab_w = w;  w += o.reftab_b >> 2;
-  o.bits_w = w;    w += (o.bits_b >> 2) + ((W + 3u) & ~3u);   // + the zero row (kept 16-byte aligned)
+  o.bits_w = w;    w += (o.bits_b >> 2) + (zero_row ? ((W + 3u) & ~3u) : 0u);   // + the zero row (kept 16-byte aligned)
   o.r16_w = w;     w += o.r16_b >> 2;
   o.rr_w = w;      w += o.rr_b >> 2;
   o.cellref_w = w; w += o.cellref_b >> 2;
@@ -191,7 +192,8 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
   // row; rows outside the band clamp onto the zero row (unsigned min), so the probe code is the same as for
   // a whole plane.  Tables read in place cover the whole plane (rows 0 and R - 1 are its zero rows).
   const uint32_t band_rows = SMEM_TAB ? K.row_end - K.row_begin : (uint32_t)G.R[d];
-  const uint32_t Rm1 = SMEM_TAB ? band_rows : (uint32_t)G.R[d] - 1u;
+  const bool whole_plane = !SMEM_TAB || band_rows == (uint32_t)G.R[d];   // its rows 0 and R - 1 are the zero rows
+  const uint32_t Rm1 = whole_plane ? (uint32_t)G.R[d] - 1u : band_rows;
   const int32_t row_shift = SMEM_TAB ? (int32_t)(K.row_begin << F) : 0;
 
   // tables of this pass' plane (bits, ranks, per-cell landmark slots, the label's landmark
@@ -207,7 +209,7 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
     // phase may find no candidate item at all): that warp arms an mbarrier with the byte count
     // and issues the TMA bulk copies (cp.async.bulk global -> shared); every warp with work
     // waits on the barrier's phase before its first probe.
-    Lo = spr_tab_layout(W, band_rows, GT.cell_base + K.tab_rank_lo, K.tab_cells, V.ref_base[l], K.stage_reftab ? K.tab_refs : 0u);
+    Lo = spr_tab_layout(W, band_rows, GT.cell_base + K.tab_rank_lo, K.tab_cells, V.ref_base[l], K.stage_reftab ? K.tab_refs : 0u, whole_plane ? 0u : 1u);
     bar = reinterpret_cast<uint64_t *>(smem + Lo.total_w - 4);
     stage_flag = smem + Lo.total_w - 2;
     if (threadIdx.x == 0) {
@@ -215,7 +217,8 @@ spr_score_lattice_kernel(const SprView V, const SprLaunch K, const int n_wg_loca
       *stage_flag = 0u;
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (uint32_t i = threadIdx.x; i < ((W + 3u) & ~3u); i += blockDim.x) smem[Lo.bits_w + band_rows * W + i] = 0u;  // the zero row
+    if (!whole_plane)
+      for (uint32_t i = threadIdx.x; i < ((W + 3u) & ~3u); i += blockDim.x) smem[Lo.bits_w + band_rows * W + i] = 0u;  // the zero row
     __syncthreads();
     T.bits = smem + Lo.bits_w;
     T.r16 = reinterpret_cast<uint16_t *>(smem + Lo.r16_w);
@@ -458,7 +461,8 @@ int spr_score_smem_warps(const SprView &V, const SprLaunch &K, int tables_mode) 
   const size_t warp_bytes = (size_t)(cnt32 ? SPR_WARP_WORDS(true) : SPR_WARP_WORDS(false)) * 4;
   if (tables_mode != SPR_TABLES_AUTO || K.label < 0 || K.tab_refs >= SPR_CELL_MULTI || K.row_end <= K.row_begin) return 0;
   const uint32_t tab = spr_tab_layout((uint32_t)V.grid.W[K.dir], K.row_end - K.row_begin, K.tab_cell_base + K.tab_rank_lo, K.tab_cells,
-                                      K.tab_ref_base, K.stage_reftab ? K.tab_refs : 0u).total_w * 4u;
+                                      K.tab_ref_base, K.stage_reftab ? K.tab_refs : 0u,
+                                      K.row_end - K.row_begin == (uint32_t)V.grid.R[K.dir] ? 0u : 1u).total_w * 4u;
   if ((size_t)tab + 8 * warp_bytes > SPR_SMEM_LIMIT) return 0;
   const int smem_warps = (int)((SPR_SMEM_LIMIT - tab) / warp_bytes);
   return smem_warps > 24 ? 24 : smem_warps;
@@ -506,7 +510,8 @@ cudaError_t spr_launch_score_lattice(const SprView &V, const SprLaunch &K, int t
   const int smem_warps = spr_score_smem_warps(V, K, tables_mode);
   if (smem_warps >= 8) {
     const uint32_t tab = spr_tab_layout((uint32_t)V.grid.W[K.dir], K.row_end - K.row_begin, K.tab_cell_base + K.tab_rank_lo, K.tab_cells,
-                                        K.tab_ref_base, K.stage_reftab ? K.tab_refs : 0u).total_w * 4u;
+                                        K.tab_ref_base, K.stage_reftab ? K.tab_refs : 0u,
+                                        K.row_end - K.row_begin == (uint32_t)V.grid.R[K.dir] ? 0u : 1u).total_w * 4u;
     const long long want = (n_items + smem_warps - 1) / smem_warps;
     const int grid = (int)(want < sm_count ? want : sm_count);
     const size_t smem = (size_t)tab + (size_t)smem_warps * warp_bytes;
