@@ -179,8 +179,6 @@ struct slide_pr_handle {
   bool force_exhaustive = false;  // env SLIDE_PR_EXHAUSTIVE=1
   int refine_min = 32;            // candidate double groups from which the bounds are refined (env SLIDE_PR_REFINE_MIN; < 0: never)
   bool refine_forced = false;     // env SLIDE_PR_REFINE_MIN given: refine whenever there are that many candidates
-  bool window_mode = true;        // env SLIDE_PR_WINDOW=0 disables the windowed bound kernel (A/B, tests of the other paths)
-  double qrad = 0;                // largest |(x, y)| of the prepared query map (search frame)
   size_t bound_smem = 0;          // env SLIDE_PR_BOUND_SMEM (test hook): shared-memory budget of the bound planner, 0 = all
   bool ring_major = false;        // lattice of the prepared problem is chunked ring by ring (anytime budget may bind)
   cudaStream_t stream = nullptr;
@@ -330,7 +328,6 @@ int slide_pr_create(const slide_pr_params *p, slide_pr_handle **out) {
   // SLIDE_PR_EXHAUSTIVE=1 verifies every hypothesis exactly (no bound-and-verify pruning)
   if (const char *v = std::getenv("SLIDE_PR_EXHAUSTIVE")) h->force_exhaustive = std::atoi(v) != 0;
   if (const char *v = std::getenv("SLIDE_PR_REFINE_MIN")) { h->refine_min = std::atoi(v); h->refine_forced = true; }
-  if (const char *v = std::getenv("SLIDE_PR_WINDOW")) h->window_mode = std::atoi(v) != 0;
   if (const char *v = std::getenv("SLIDE_PR_BOUND_SMEM")) { const long b = std::atol(v); if (b > 0) h->bound_smem = (size_t)b; }
   *out = h;
   return SLIDE_PR_OK;
@@ -481,7 +478,6 @@ static int prepare_impl(slide_pr_handle *h, RefSide *slot, bool trusted, const d
     if (!std::isfinite(r)) { h->err = "non-finite query coordinate"; return SLIDE_PR_ERR_NONFINITE; }
     qrad = std::max(qrad, r);
   }
-  h->qrad = qrad;
   const double reach = qrad + std::max(std::fabs(half_x), std::fabs(half_y)) + h->p.match_xy_step_size;
   // reference index: a function of the reference rows, the cell size / thresholds and the reach
   const bool same_ref = h->rs->ref_index_valid && (int)(h->rs->cached_ref.size() / 7) == n_ref && reach <= h->rs->cached_reach &&
@@ -752,32 +748,6 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     h->bounds_valid = false;
     for (uint32_t d = 0; d < 2 && !reuse; d++) {
       if (h->L.dir_end[d] <= h->L.dir_begin[d]) continue;
-      // small query map against planes that do not fit in shared memory (streaming submap queries): the windowed
-      // kernel stages, per batch of neighbouring double groups, only the part of the planes their probes can reach
-      {
-        const SprGrid &G = h->V.grid;
-        const double qU = h->qrad * (1.0 + 1e-9) + 1e-9;   // |c qx - s qy| <= hypot(qx, qy), plus rounding
-        const double g0a = d ? G.g0y : G.g0x, g0b = d ? G.g0x : G.g0y;
-        const int32_t qr[4] = {(int32_t)std::floor((-qU - g0a) * G.S) - 1, (int32_t)std::floor((qU - g0a) * G.S) + 1,
-                               (int32_t)std::floor((-qU - g0b) * G.S) - 1, (int32_t)std::floor((qU - g0b) * G.S) + 1};
-        int per_w = 1;
-        if (h->window_mode && h->bound_smem == 0 && spr_bound_window_plan(h->V, d, (int)active.size(), qr, &per_w)) {
-          for (size_t i = 0; i < active.size(); i += (size_t)per_w) {
-            B.chunk_begin = h->L.dir_begin[d]; B.chunk_end = h->L.dir_end[d]; B.dir = d;
-            B.row_begin = B.row_end = 0u;
-            B.n_labels = (int32_t)std::min<size_t>((size_t)per_w, active.size() - i);
-            for (int k = 0; k < B.n_labels; k++) B.labels[k] = active[i + (size_t)k];
-            B.first = i == 0;
-            B.last = i + (size_t)per_w >= active.size();
-            if ((rc = next_counter()) != SLIDE_PR_OK) return rc;
-            B.work_counter = K.work_counter;
-            SPR_CUDA(h, spr_launch_bound_window(h->V, B, qr, n_planes, h->sm_count, st, &launches));
-            K.work_counter++;
-            passes_left--;
-          }
-          continue;
-        }
-      }
       int per = 1;
       uint32_t band_rows = 0;
       spr_bound_plan(h->V, d, (int)active.size(), h->bound_smem, &per, &band_rows);

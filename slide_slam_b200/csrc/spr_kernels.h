@@ -92,11 +92,6 @@ void spr_bound_plan(const SprView &V, uint32_t dir, int n_active, size_t smem_bu
 uint32_t spr_refine_band_rows(const SprView &V, uint32_t dir, size_t smem_budget);  // 0: refinement reads the variant planes in place
 cudaError_t spr_launch_bound_lattice(const SprView &V, const SprBoundLaunch &B, int n_planes, int sm_count, cudaStream_t st,
                                      int *n_launches);
-// windowed variant (small query map against a large reference map): q_range = {lo, hi of the rotated queries' fixed
-// across coordinate over all yaws, lo, hi of the along coordinate} for direction B.dir
-bool spr_bound_window_plan(const SprView &V, uint32_t dir, int n_active, const int32_t q_range[4], int *labels_per_launch);
-cudaError_t spr_launch_bound_window(const SprView &V, const SprBoundLaunch &B, const int32_t q_range[4], int n_planes, int sm_count,
-                                    cudaStream_t st, int *n_launches);
 // work items of direction `B.dir` whose largest bound reaches the running best -> items[0 .. *count)
 cudaError_t spr_launch_select_items(const SprView &V, const SprBoundLaunch &B, const unsigned long long *best_key,
                                     uint32_t *items, uint32_t *count, int sm_count, cudaStream_t st);

@@ -296,235 +296,6 @@ spr_bound_lattice_kernel(const __grid_constant__ SprView V, const __grid_constan
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Windowed variant: a SMALL query map against a LARGE reference map (streaming submap queries, BASELINE
-// config 5).  The planes do not fit in shared memory and a whole row band would be read for a handful of
-// query landmarks per work item -- but the cells a work item can touch are only those within the query
-// cloud's radius of its 32 x 64 translations.  A CTA therefore takes a BATCH of SPB_WIN_WARPS consecutive
-// double groups (neighbouring lattice tiles, one per warp), computes the window of plane rows / words any of
-// their probes can reach (exact fixed-point bounds: lane origins + the query cloud's coordinate range over
-// all yaws), stages that window of every label's plane in shared memory, and each warp then runs ALL yaw
-// candidates of its double group out of shared memory.  Batches whose window does not fit (ragged ring
-// edges) read the planes in place.  Same probes, same counters, same outputs as spr_bound_lattice_kernel.
-// ---------------------------------------------------------------------------------------------
-#define SPB_WIN_WARPS 8        // double groups per batch
-#ifndef SPB_WIN_SPLIT
-#define SPB_WIN_SPLIT 3        // warps per double group: each takes every SPB_WIN_SPLIT-th yaw candidate
-#endif
-struct SprWindowArgs {
-  int32_t q_lo_across, q_hi_across, q_lo_along, q_hi_along;  // range of the rotated queries' fixed coordinates (all yaws), direction of B.dir
-  uint32_t smem_words;                                       // capacity of the staged window, 32-bit words
-};
-
-template <int PLANES>
-__global__ void __launch_bounds__(SPB_WIN_WARPS * SPB_WIN_SPLIT * 32, 1)
-spr_bound_window_kernel(const __grid_constant__ SprView V, const __grid_constant__ SprBoundLaunch B, const __grid_constant__ SprWindowArgs A,
-                        const int n_dg_local, const int n_batches) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  __shared__ int32_t s_red[4][SPB_WIN_WARPS];
-  __shared__ int s_batch;
-  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) % SPB_WIN_WARPS, split = (threadIdx.x >> 5) / SPB_WIN_WARPS;
-  const SprGrid &G = V.grid;
-  const int32_t F = G.F;
-  const uint32_t d = B.dir;
-  const uint32_t W = (uint32_t)G.W[d], R = (uint32_t)G.R[d];
-  const uint32_t maxbit2 = (uint32_t)G.maxbit[d] + 32u;
-  const int32_t *q_fx = d ? V.qrotq_yx : V.qrotq_xy;
-  const uint32_t n_wg_total = B.n_chunks_total / SPR_WARP_CHUNKS;
-  const int32_t big = 1 << 30;
-
-  for (;;) {
-    __syncthreads();  // the previous batch's window is no longer read
-    if (threadIdx.x == 0) s_batch = (int)atomicAdd(B.work_counter, 1ull);
-    __syncthreads();
-    const int batch = s_batch;
-    if (batch >= n_batches) break;
-    // this warp's double group and this lane's two chunks
-    const int k_local = batch * SPB_WIN_WARPS + warp;
-    const bool have = k_local < n_dg_local;
-    const int dg = B.shard_index + (have ? k_local : 0) * B.shard_count;
-    const uint32_t cidx = B.chunk_begin + (uint32_t)dg * (2 * SPR_WARP_CHUNKS) + (uint32_t)lane;
-    uint4 c0 = make_uint4(0u, 0u, 0u, 0u);
-    uint32_t validB = 0u;
-    if (have) {
-      c0 = __ldcs(reinterpret_cast<const uint4 *>(V.chunks + cidx));
-      validB = __ldcs(reinterpret_cast<const uint4 *>(V.chunks + cidx + SPR_WARP_CHUNKS)).w;
-    }
-    const double across = __hiloint2double((int)c0.y, (int)c0.x);
-    const uint32_t along_off = c0.z, validA = c0.w;
-    const int32_t aq0 = spr_fx(across, G.S);
-    const int32_t bq0 = spr_fx(have ? __ldg(V.lat + along_off) : 0.0, G.S);
-    const int32_t aqb = spr_bias_across(aq0, F), bqb2 = spr_bias_along(bq0, F) + (32 << F);
-    const bool live = validA != 0u;
-    const int32_t ext = (validB ? 64 : 32) << F;
-    const int32_t lx0 = d ? bq0 : aq0, lx1 = d ? bq0 + ext : aq0;
-    const int32_t ly0 = d ? aq0 : bq0, ly1 = d ? aq0 : bq0 + ext;
-    const int32_t X0 = __reduce_min_sync(SPR_FULL, live ? lx0 : big), X1 = __reduce_max_sync(SPR_FULL, live ? lx1 : -big);
-    const int32_t Y0 = __reduce_min_sync(SPR_FULL, live ? ly0 : big), Y1 = __reduce_max_sync(SPR_FULL, live ? ly1 : -big);
-    // window of the batch: rows (across) and words (along) any probe of a live lane can reach
-    const int32_t a_lo = __reduce_min_sync(SPR_FULL, live ? aqb : big), a_hi = __reduce_max_sync(SPR_FULL, live ? aqb : -big);
-    const int32_t b_lo = __reduce_min_sync(SPR_FULL, live ? bqb2 : big), b_hi = __reduce_max_sync(SPR_FULL, live ? bqb2 : -big);
-    if (lane == 0 && split == 0) { s_red[0][warp] = a_lo; s_red[1][warp] = a_hi; s_red[2][warp] = b_lo; s_red[3][warp] = b_hi; }
-    __syncthreads();
-    int32_t wa_lo = big, wa_hi = -big, wb_lo = big, wb_hi = -big;
-#pragma unroll
-    for (int w = 0; w < SPB_WIN_WARPS; w++) {
-      wa_lo = min(wa_lo, s_red[0][w]); wa_hi = max(wa_hi, s_red[1][w]);
-      wb_lo = min(wb_lo, s_red[2][w]); wb_hi = max(wb_hi, s_red[3][w]);
-    }
-    const bool any_live = wa_lo <= wa_hi;
-    // plane row of a probe = (aqb + q_across) >> F; its three words = ((bqb2 + q_along) >> (F + 5)) - 1 .. + 1
-    const int32_t row_lo = any_live ? (wa_lo + A.q_lo_across) >> F : 0, row_hi = any_live ? (wa_hi + A.q_hi_across) >> F : 0;
-    const int32_t word_lo = any_live ? ((wb_lo + A.q_lo_along) >> (F + 5)) - 1 : 0, word_hi = any_live ? ((wb_hi + A.q_hi_along) >> (F + 5)) + 1 : 0;
-    const uint32_t Wr = (uint32_t)(row_hi - row_lo + 1), Ww = (uint32_t)(word_hi - word_lo + 1);
-    const uint32_t pitch = Ww | 1u;                               // odd pitch: neighbouring rows in different banks
-    const uint32_t label_words = (Wr + 1u) * pitch;               // + the zero row at index Wr
-    const bool windowed = any_live && (unsigned long long)label_words * (unsigned)B.n_labels <= A.smem_words && Wr < 65536u && Ww < 65536u;
-    if (windowed) {
-      for (int k = 0; k < B.n_labels; k++) {
-        const uint32_t *plane = V.bitmap + ((size_t)B.labels[k] * G.label_stride + (d ? G.plane_words[0] : 0u));
-        uint32_t *dst = smem + (size_t)k * label_words;
-        for (uint32_t i = threadIdx.x; i < label_words; i += blockDim.x) {
-          const uint32_t r = i / pitch, c = i - r * pitch;
-          const int32_t pr = row_lo + (int32_t)r, pc = word_lo + (int32_t)c;
-          uint32_t v = 0u;
-          if (r < Wr && c < Ww && pr >= 0 && pr < (int32_t)R && pc >= 0 && pc < (int32_t)W) v = __ldg(plane + (size_t)pr * W + (size_t)pc);
-          dst[i] = v;
-        }
-      }
-    }
-    __syncthreads();
-    if (!have || X0 > X1) continue;  // (the barriers above were passed by every warp)
-
-    for (int a = split; a < V.n_yaw; a += SPB_WIN_SPLIT) {
-      uint32_t PA[PLANES], PB[PLANES];
-      uint32_t *gpA = B.planes + (((size_t)a * n_wg_total + cidx / SPR_WARP_CHUNKS) * PLANES) * 32 + lane;
-      uint32_t *gpB = gpA + (size_t)PLANES * 32;
-      if (B.first) {
-#pragma unroll
-        for (int i = 0; i < PLANES; i++) PA[i] = PB[i] = 0u;
-      } else {
-#pragma unroll
-        for (int i = 0; i < PLANES; i++) { PA[i] = __ldcs(gpA + i * 32); PB[i] = __ldcs(gpB + i * 32); }
-      }
-      uint32_t p4A = 0u, p8A = 0u, p16A = 0u, p4B = 0u, p8B = 0u, p16B = 0u;
-      bool have4 = false, have8 = false, have16 = false;
-      for (int k = 0; k < B.n_labels; k++) {
-        const int l = B.labels[k];
-        const int g0 = V.label_gseg[l], g1 = V.label_gseg[l + 1];
-        if (g0 >= g1) continue;
-        const SprBox lb = V.labelbox[l];
-        if (lb.x0 >= lb.x1 || lb.y0 >= lb.y1) continue;
-        const uint32_t *gbits = V.bitmap + ((size_t)l * G.label_stride + (d ? G.plane_words[0] : 0u));
-        const uint32_t *wbits = smem + (size_t)k * label_words;
-        const int32_t tx_lo = lb.x0 - X1, tx_hi = lb.x1 - X0, ty_lo = lb.y0 - Y1, ty_hi = lb.y1 - Y0;
-        const int4 *gbp = reinterpret_cast<const int4 *>(V.gbox) + ((size_t)a * (size_t)V.n_groups + (size_t)g0);
-        const int4 *qgp = reinterpret_cast<const int4 *>(q_fx + 2 * (size_t)a * (size_t)V.nqp) + (size_t)g0 * (SPR_QGROUP / 2);
-        for (int gb = g0; gb < g1; gb += 32) {
-          bool vis = false;
-          if (gb + lane < g1) {
-            const int4 box = __ldg(gbp + (gb - g0) + lane);  // (x0, x1, y0, y1)
-            vis = box.y > tx_lo && box.x < tx_hi && box.w > ty_lo && box.z < ty_hi;
-          }
-          uint32_t vm = __ballot_sync(SPR_FULL, vis);
-          while (vm) {
-            const int kk = __ffs(vm) - 1;
-            vm &= vm - 1;
-            const int4 *q = qgp + (size_t)(gb - g0 + kk) * (SPR_QGROUP / 2);
-            int4 v[SPR_QGROUP / 2];
-#pragma unroll
-            for (int u = 0; u < SPR_QGROUP / 2; u++) v[u] = __ldg(q + u);
-#pragma unroll
-            for (int hq = 0; hq < 2; hq++) {  // four queries at a time
-              uint32_t HA[4], HB[4];
-#pragma unroll
-              for (int u = 0; u < 4; u++) {
-                const int4 vv = v[2 * hq + (u >> 1)];
-                const int32_t qa_ = (u & 1) ? vv.z : vv.x, qb_ = (u & 1) ? vv.w : vv.y;
-                uint32_t w0, w1, w2, bit;
-                if (windowed) {
-                  // window-relative row / word; anything outside (only the padding queries' sentinel coordinates) lands on
-                  // the zero row
-                  const uint32_t row = min((uint32_t)(((aqb + qa_) >> F) - row_lo), Wr);
-                  const int32_t bsum = bqb2 + qb_;
-                  bit = (uint32_t)(bsum >> F);
-                  const uint32_t word = min((uint32_t)((bsum >> (F + 5)) - word_lo), Ww - 2u);
-                  const uint32_t *p = wbits + row * pitch + max(word, 1u);
-                  w0 = p[-1]; w1 = p[0]; w2 = p[1];
-                } else {
-                  const uint32_t row = min((uint32_t)((aqb + qa_) >> F), R - 1u);
-                  bit = min((uint32_t)((bqb2 + qb_) >> F), maxbit2);
-                  const uint32_t *p = gbits + (size_t)row * W + (bit >> 5);
-                  w0 = __ldg(p - 1); w1 = __ldg(p); w2 = __ldg(p + 1);
-                }
-                HA[u] = __funnelshift_r(w0, w1, bit);
-                HB[u] = __funnelshift_r(w1, w2, bit);
-              }
-              uint32_t tA, tB, f4A, f4B;
-              spb_fa(PA[0], HA[0], HA[1], PA[0], tA);
-              spb_fa(PA[0], HA[2], HA[3], PA[0], tB);
-              spb_fa(PA[1], tA, tB, PA[1], f4A);
-              spb_fa(PB[0], HB[0], HB[1], PB[0], tA);
-              spb_fa(PB[0], HB[2], HB[3], PB[0], tB);
-              spb_fa(PB[1], tA, tB, PB[1], f4B);
-              if (!have4) { p4A = f4A; p4B = f4B; have4 = true; continue; }
-              uint32_t e8A, e8B;
-              spb_fa(PA[2], p4A, f4A, PA[2], e8A);
-              spb_fa(PB[2], p4B, f4B, PB[2], e8B);
-              have4 = false;
-              if (!have8) { p8A = e8A; p8B = e8B; have8 = true; continue; }
-              uint32_t s16A, s16B;
-              spb_fa(PA[3], p8A, e8A, PA[3], s16A);
-              spb_fa(PB[3], p8B, e8B, PB[3], s16B);
-              have8 = false;
-              if (!have16) { p16A = s16A; p16B = s16B; have16 = true; continue; }
-              uint32_t cA, cB;
-              spb_fa(PA[4], p16A, s16A, PA[4], cA);
-              spb_fa(PB[4], p16B, s16B, PB[4], cB);
-              have16 = false;
-              spb_ripple<PLANES>(PA, cA, 5);
-              spb_ripple<PLANES>(PB, cB, 5);
-            }
-          }
-        }
-      }
-      if (have4) { spb_ripple<PLANES>(PA, p4A, 2); spb_ripple<PLANES>(PB, p4B, 2); }
-      if (have8) { spb_ripple<PLANES>(PA, p8A, 3); spb_ripple<PLANES>(PB, p8B, 3); }
-      if (have16) { spb_ripple<PLANES>(PA, p16A, 4); spb_ripple<PLANES>(PB, p16B, 4); }
-#pragma unroll
-      for (int i = 0; i < PLANES; i++) {
-        PA[i] &= validA;
-        PB[i] &= validB;
-        __stcs(gpA + i * 32, PA[i]);
-        __stcs(gpB + i * 32, PB[i]);
-      }
-      if (B.last) {
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-          const uint32_t valid = half ? validB : validA;
-          uint32_t cand = valid, val = 0u;
-#pragma unroll
-          for (int i = PLANES - 1; i >= 0; i--) {
-            const uint32_t t = cand & (half ? PB[i] : PA[i]);
-            if (t) { cand = t; val |= 1u << i; }
-          }
-          const bool lv = valid != 0u;
-          const uint32_t packed = lv ? ((val << 5) | (uint32_t)(__ffs(cand) - 1)) : 0u;
-          const uint32_t wmax = __reduce_max_sync(SPR_FULL, packed);
-          const uint32_t who = __ballot_sync(SPR_FULL, packed == wmax && lv);
-          const uint32_t grp = cidx / SPR_WARP_CHUNKS + (uint32_t)half;
-          if (lane == 0) B.item_ub[(size_t)a * n_wg_total + grp] = wmax >> 5;
-          if (who && lane == __ffs(who) - 1)
-            atomicMax(B.seed_key + (size_t)a * SPR_SEED_SLOTS + grp % SPR_SEED_SLOTS,
-                      ((unsigned long long)(val + 1u) << SPR_KEY_IDX_BITS) |
-                          ((unsigned long long)(cidx + (uint32_t)half * SPR_WARP_CHUNKS) * 32ull + (unsigned long long)(packed & 31u)));
-        }
-      }
-      __syncwarp();
-    }
-  }
-}
-
 // Exact score of the best-bounded hypotheses -- SPR_SEED_SLOTS per yaw candidate, one per residue
 // class of the work-item columns -- (one CTA each, the warps stride over the query landmarks): seeds the running best of the verification phase.  Same
 // decision code as the hypothesis-list scorer.
@@ -790,55 +561,6 @@ static cudaError_t spb_launch(const SprView &V, const SprBoundLaunch &B, int n_d
       spr_bound_lattice_kernel<PLANES, false, true><<<(int)(want < cap ? want : cap), 256, 0, st>>>(V, B, n_dg_local, n_items);
     else
       spr_bound_lattice_kernel<PLANES, false, false><<<(int)(want < cap ? want : cap), 256, 0, st>>>(V, B, n_dg_local, n_items);
-  }
-  return cudaGetLastError();
-}
-
-// Is the windowed variant the one to use for direction `dir`?  Yes when the planes do not fit in shared memory
-// as a whole (otherwise spr_bound_lattice_kernel stages them) and the window a batch of SPB_WIN_WARPS
-// neighbouring double groups can reach -- the query cloud's extent plus the batch's own -- fits for at least
-// one label.  labels_per_launch: how many labels' windows fit together.
-bool spr_bound_window_plan(const SprView &V, uint32_t dir, int n_active, const int32_t q_range[4], int *labels_per_launch) {
-  const size_t W4 = (size_t)V.grid.W[dir] * 4, R = (size_t)V.grid.R[dir];
-  if ((R + 1) * W4 + 64 <= SPR_SMEM_LIMIT - 64) return false;   // whole planes fit: the staged-plane kernel is the better one
-  const int F = V.grid.F;
-  const double cells_across = (double)((long long)q_range[1] - (long long)q_range[0]) / (double)(1 << F) + 32.0 * SPB_WIN_WARPS + 4.0;
-  const double cells_along = (double)((long long)q_range[3] - (long long)q_range[2]) / (double)(1 << F) + 64.0 + 4.0;
-  const double label_words = (cells_across + 1.0) * (cells_along / 32.0 + 4.0);
-  const double cap = (double)((SPR_SMEM_LIMIT - 2048) / 4);
-  const int per = (int)(cap / label_words);
-  if (per < 1) return false;
-  *labels_per_launch = per > SPR_BOUND_MAX_LABELS ? SPR_BOUND_MAX_LABELS : (per > n_active ? n_active : per);
-  return true;
-}
-
-cudaError_t spr_launch_bound_window(const SprView &V, const SprBoundLaunch &B, const int32_t q_range[4], int n_planes, int sm_count,
-                                    cudaStream_t st, int *n_launches) {
-  if (B.chunk_end <= B.chunk_begin || V.n_yaw <= 0 || B.n_labels <= 0) return cudaSuccess;
-  const int n_wg = (int)((B.chunk_end - B.chunk_begin) / SPR_WARP_CHUNKS);
-  const int sc = B.shard_count > 1 ? B.shard_count : 1;
-  const int si = B.shard_count > 1 ? B.shard_index : 0;
-  const int n_dg_local = spr_shard_local_groups(n_wg, si, sc) / 2;
-  if (n_dg_local <= 0) return cudaSuccess;
-  SprBoundLaunch B2 = B;
-  B2.shard_index = si;
-  B2.shard_count = sc;
-  SprWindowArgs A;
-  A.q_lo_across = q_range[0]; A.q_hi_across = q_range[1]; A.q_lo_along = q_range[2]; A.q_hi_along = q_range[3];
-  const size_t smem = SPR_SMEM_LIMIT - 2048;
-  A.smem_words = (uint32_t)(smem / 4);
-  const int n_batches = (n_dg_local + SPB_WIN_WARPS - 1) / SPB_WIN_WARPS;
-  if (n_launches) (*n_launches)++;
-  const int grid = n_batches < sm_count ? n_batches : sm_count;
-  cudaError_t e;
-  if (n_planes == 12) {
-    e = cudaFuncSetAttribute(spr_bound_window_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    spr_bound_window_kernel<12><<<grid, SPB_WIN_WARPS * SPB_WIN_SPLIT * 32, smem, st>>>(V, B2, A, n_dg_local, n_batches);
-  } else {
-    e = cudaFuncSetAttribute(spr_bound_window_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    spr_bound_window_kernel<16><<<grid, SPB_WIN_WARPS * SPB_WIN_SPLIT * 32, smem, st>>>(V, B2, A, n_dg_local, n_batches);
   }
   return cudaGetLastError();
 }

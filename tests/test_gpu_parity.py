@@ -580,41 +580,3 @@ def test_streaming_reuse_of_reference_index_and_lattice():
     assert (info.best_num_inliers, info.match.best_hyp_index) == (want["best_num_inliers"], want["best_hyp_index"])
     pr.close()
 
-
-def test_windowed_bound_kernel_equals_the_plane_kernels():
-    """Small query map against a reference map whose occupancy planes do not fit in shared memory (the
-    streaming case): the windowed bound kernel stages only the reachable part of the planes per batch of
-    work items.  Its bounds must equal, hypothesis by hypothesis, those of the kernels that read whole
-    planes (SLIDE_PR_WINDOW=0), dominate the oracle's exact counts, and leave the winner unchanged."""
-    big, queries = synth.config_stream(n_map=13000, n_queries=2, n_sub=150, seed=91)
-    kw = dict(match_xy_step_size=0.5, yaw_step_deg=10.0, match_threshold=0.5, match_threshold_dimension=1.0,
-              ignore_dimension=0, min_num_inliers=10)
-    op = O.make_params(**kw)
-    for q in queries:
-        pr = make_pr(kw)
-        found, _, _, info, ri, qi = pr.findTransformation(big, q)
-        assert found and info.match.search_mode == 1
-        sref, sqry = big.copy(), q.copy()
-        sref[:, 1:3] -= np.array(info.centroid_ref[:]); sqry[:, 1:3] -= np.array(info.centroid_qry[:])
-        pr.prepare(sref, sqry, info.half_x, info.half_y)
-        res_x, _ = pr.search(exhaustive=True)
-        assert (res_x.best_num_inliers, res_x.best_hyp_index) == (info.best_num_inliers, info.match.best_hyp_index)
-        ny, nt = info.match.n_yaw, info.match.n_translations
-        t_win = info.match.best_hyp_index // ny
-        slices = [(max(t_win - 40, 0), t_win + 40), (0, 64), (nt - 64, nt), (nt // 3, nt // 3 + 3000)]
-        os.environ["SLIDE_PR_WINDOW"] = "0"
-        pr0 = make_pr(kw)
-        os.environ.pop("SLIDE_PR_WINDOW")
-        pr0.prepare(sref, sqry, info.half_x, info.half_y)
-        for tb, te in slices:
-            _, bw = pr.search(tb, te, want_counts=True, bounds_only=True)
-            _, b0 = pr0.search(tb, te, want_counts=True, bounds_only=True)
-            assert np.array_equal(bw, b0), f"slice [{tb}, {te})"
-        tb, te = slices[0]
-        want = O.match_maps(op, sref, sqry, info.half_x, info.half_y, tb * ny, te * ny, want_counts=True, n_threads=-1)
-        _, bw = pr.search(tb, te, want_counts=True, bounds_only=True)
-        _, exact = pr.search(tb, te, want_counts=True)
-        assert np.array_equal(exact, want["counts"]) and (bw >= exact).all()
-        r0, _ = pr0.search()
-        assert (r0.best_num_inliers, r0.best_hyp_index) == (info.best_num_inliers, info.match.best_hyp_index)
-        pr.close(); pr0.close()
