@@ -28,6 +28,7 @@
 #include "spr_delaunay.h"
 #include "spr_generate.h"
 #include "spr_host.h"
+#include "spr_join.h"
 #include "spr_kernels.h"
 
 namespace {
@@ -155,6 +156,13 @@ struct RefSide {
   bool ref_index_valid = false;
   bool ranks_pending = false;        // stage 2 of the index (rank tables) not built / uploaded yet
   const double *pending_ref7 = nullptr;
+  bool rows_valid = false;           // cached_ref holds the rows of the prepared reference map
+  bool ref7_uploaded = false;        // ... and d_ref7 their device copy
+  // pair-join scorer (spr_join.h): landmarks binned by label and coarse cell, both join directions
+  spr::JoinRef J;
+  bool join_valid = false;
+  slide_pr_params join_p{};
+  DevBuf dj_rec0, dj_rec1, dj_cs0, dj_cs1, dj_nbr, dj_labelbox;
   DevBuf d_labelbox, d_bitmap, d_rank16, d_rank16b, d_rowrank, d_rowrankb, d_cellref, d_cellrefb, d_cellbase, d_cellbaseb,
       d_reftab, d_refbase, d_cand, d_cand1, d_vbitmap, d_labof, d_ref7;
   // cache bookkeeping (unused by the anonymous slot)
@@ -166,7 +174,8 @@ struct RefSide {
   uint64_t last_use = 0;
   void release() {
     for (DevBuf *b : {&d_labelbox, &d_bitmap, &d_rank16, &d_rank16b, &d_rowrank, &d_rowrankb, &d_cellref, &d_cellrefb, &d_cellbase,
-                      &d_cellbaseb, &d_reftab, &d_refbase, &d_cand, &d_cand1, &d_vbitmap, &d_labof, &d_ref7})
+                      &d_cellbaseb, &d_reftab, &d_refbase, &d_cand, &d_cand1, &d_vbitmap, &d_labof, &d_ref7,
+                      &dj_rec0, &dj_rec1, &dj_cs0, &dj_cs1, &dj_nbr, &dj_labelbox})
       b->release();
   }
 };
@@ -181,6 +190,18 @@ struct slide_pr_handle {
   bool refine_forced = false;     // env SLIDE_PR_REFINE_MIN given: refine whenever there are that many candidates
   size_t bound_smem = 0;          // env SLIDE_PR_BOUND_SMEM (test hook): shared-memory budget of the bound planner, 0 = all
   bool ring_major = false;        // lattice of the prepared problem is chunked ring by ring (anytime budget may bind)
+  bool env_lattice = false;       // env SLIDE_PR_ENGINE=lattice: the bound-and-verify lattice kernels are the default search
+  double Tstar = 0, Sstar = 0;    // thresholds of the prepared problem (spr::sqrt_threshold / div3_threshold)
+  bool lattice_ready = false;     // index structures of the lattice kernels built for the prepared problem (built on demand)
+  bool join_ready = false;        // structures of the pair-join scorer built for the prepared problem
+  // pair-join scorer: query side, lattice blocks, device copies
+  spr::QuerySet JQ;
+  spr::uvec<int32_t> j_glabel;
+  spr::uvec<SprJoinBlock> j_blocks;
+  bool j_blocks_valid = false;
+  double j_drift = 0;
+  DevBuf dj_lat, dj_cs, dj_qxy, dj_qdims, dj_qlabel, dj_glabel, dj_qrot, dj_gbox, dj_blocks;
+  SprJoinView JV{};
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // uploads that overlap the bound phase of a search
   cudaStream_t side_stream = nullptr;  // verification passes of the second bitmap direction
@@ -329,6 +350,8 @@ int slide_pr_create(const slide_pr_params *p, slide_pr_handle **out) {
   if (const char *v = std::getenv("SLIDE_PR_EXHAUSTIVE")) h->force_exhaustive = std::atoi(v) != 0;
   if (const char *v = std::getenv("SLIDE_PR_REFINE_MIN")) { h->refine_min = std::atoi(v); h->refine_forced = true; }
   if (const char *v = std::getenv("SLIDE_PR_BOUND_SMEM")) { const long b = std::atol(v); if (b > 0) h->bound_smem = (size_t)b; }
+  // SLIDE_PR_ENGINE=lattice: searches default to the bound-and-verify lattice kernels instead of the pair-join scorer (A/B)
+  if (const char *v = std::getenv("SLIDE_PR_ENGINE")) h->env_lattice = std::strcmp(v, "lattice") == 0;
   *out = h;
   return SLIDE_PR_OK;
 }
@@ -339,7 +362,8 @@ void slide_pr_destroy(slide_pr_handle *h) {
   for (DevBuf *b : {&h->d_lat, &h->d_chunks, &h->d_cs, &h->d_qxy, &h->d_qdims, &h->d_labelseg, &h->d_qlabel, &h->d_gbox, &h->d_gcnt, &h->d_qrot,
                     &h->d_qrotq, &h->d_qrotq_yx, &h->d_work, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps,
                     &h->d_tri, &h->d_tri_out, &h->d_ubplanes, &h->d_itemub, &h->d_seed, &h->d_canditems, &h->d_candcount, &h->d_dgitems,
-                    &h->d_dgcount})
+                    &h->d_dgcount, &h->dj_lat, &h->dj_cs, &h->dj_qxy, &h->dj_qdims, &h->dj_qlabel, &h->dj_glabel, &h->dj_qrot,
+                    &h->dj_gbox, &h->dj_blocks})
     b->release();
   h->anon.release();
   for (auto &kv : h->cache) kv.second->release();
@@ -412,14 +436,28 @@ static int finish_ranks(slide_pr_handle *h, cudaStream_t st) {
   return SLIDE_PR_OK;
 }
 
+// Which search a prepared problem gets by default: the pair-join scorer, unless the parameters / environment
+// ask for the lattice kernels or the problem is outside the scorer's limits (u16 counters; the anytime
+// budget works ring by ring).
+static bool join_supported(const slide_pr_handle *h) { return !h->ring_major && h->n_qry <= 65535; }
+static bool join_is_default(const slide_pr_handle *h) {
+  return h->p.exhaustive_search == 0 && !h->force_exhaustive && !h->env_lattice && join_supported(h);
+}
+static int lattice_prepare(slide_pr_handle *h);
+static int join_prepare(slide_pr_handle *h);
+
 // slot: where the reference-map index lives (the anonymous slot or a cache entry).  trusted: ref7 IS the
 // slot's cached rows (a cache entry at its current version), so the byte comparison is skipped.
+// Copies the maps, uploads the raw rows and builds the structures of the default search; those of the
+// other engine are built on demand by the search that needs them.
 static int prepare_impl(slide_pr_handle *h, RefSide *slot, bool trusted, const double *ref7, int32_t n_ref, const double *qry7,
                         int32_t n_qry, double half_x, double half_y) {
   if (!h) return SLIDE_PR_ERR_INVALID;
   h->rs = slot;
   h->prepared = false;
   h->bounds_valid = false;
+  h->lattice_ready = false;
+  h->join_ready = false;
   if (n_ref < 0 || n_qry < 0 || (n_ref > 0 && !ref7) || (n_qry > 0 && !qry7)) { h->err = "bad map arguments"; return SLIDE_PR_ERR_INVALID; }
   if (n_qry >= (1 << 22)) { h->err = "more than 2^22 query landmarks"; return SLIDE_PR_ERR_UNSUPPORTED; }
   const double t0 = now_ms();
@@ -432,17 +470,152 @@ static int prepare_impl(slide_pr_handle *h, RefSide *slot, bool trusted, const d
   h->h2d_bytes = 0;
   h->yaw_half = h->p.inter_loop_closure ? h->p.match_yaw_half_range : h->p.match_yaw_half_range_intra;
   h->n_ref = n_ref; h->n_qry = n_qry;
-  const bool ring_major = budget_may_bind(h->p, half_x, half_y, h->yaw_half, n_qry);
-  h->ring_major = ring_major;
+  h->ring_major = budget_may_bind(h->p, half_x, half_y, h->yaw_half, n_qry);
   h->lat_tb = 0; h->lat_te = -1;
-  int rc;
   h->reuse_flags = 0;
+  h->prepare_ms = 0;
+  h->Tstar = spr::sqrt_threshold(h->p.match_threshold);
+  h->Sstar = spr::div3_threshold(h->p.match_threshold_dimension);
+  for (int j = 0; j < n_qry; j++)
+    if (!std::isfinite(qry7[7 * (size_t)j + 1]) || !std::isfinite(qry7[7 * (size_t)j + 2])) { h->err = "non-finite query coordinate"; return SLIDE_PR_ERR_NONFINITE; }
+  int rc;
+  // rows of the reference map: page-locked host copy + device copy, kept while the same bytes come again
+  const bool same_rows = slot->rows_valid && (int)(slot->cached_ref.size() / 7) == n_ref &&
+                         (trusted || n_ref == 0 || std::memcmp(slot->cached_ref.data(), ref7, (size_t)n_ref * 7 * sizeof(double)) == 0);
+  if (!same_rows) {
+    if (!trusted) slot->cached_ref.assign(ref7, ref7 + (size_t)n_ref * 7);
+    slot->rows_valid = true;
+    slot->ref_index_valid = false; slot->ranks_pending = false;
+    slot->join_valid = false;
+    slot->ref7_uploaded = false;
+  }
+  if (!slot->ref7_uploaded) {
+    if ((rc = upload(h, slot->d_ref7, slot->cached_ref, st))) return rc;
+    slot->ref7_uploaded = true;
+  }
+  h->qry_rows.assign(qry7, qry7 + (size_t)n_qry * 7);
+  if ((rc = upload(h, h->d_qry7, h->qry_rows, st))) return rc;
+  SPR_CUDA(h, h->d_work.ensure(4096 * sizeof(unsigned long long)));
+  SPR_CUDA(h, h->d_best.ensure(sizeof(unsigned long long)));
+  SPR_CUDA(h, h->d_stats.ensure(4 * sizeof(unsigned long long)));
+  SPR_CUDA(h, h->d_match.ensure(std::max<size_t>(n_qry, 1) * sizeof(int32_t)));
+  g_trace.mark("rows_upload");
+  rc = join_is_default(h) ? join_prepare(h) : lattice_prepare(h);
+  if (rc != SLIDE_PR_OK) return rc;
+  // no synchronisation here: every upload reads page-locked vectors owned by the handle (the
+  // caller's rows were copied), which stay untouched until the next prepare
+  SPR_CUDA(h, cudaEventRecord(h->ev_prep, st));  // a search on another stream waits for these uploads
+  if (g_pageable_uploads.load() > 0) SPR_CUDA(h, cudaStreamSynchronize(st));  // page-locking failed somewhere: do not rely on it
+  h->prepared = true;
+  h->prepare_ms = now_ms() - t0;
+  return SLIDE_PR_OK;
+}
+
+// Structures of the pair-join scorer for the prepared problem: reference landmarks by label and coarse cell
+// (kept per reference map), query groups, ring geometry and lattice blocks (kept while the search ranges repeat).
+static int join_prepare(slide_pr_handle *h) {
+  const double t0 = now_ms();
+  cudaStream_t st = h->stream;
+  RefSide *rs = h->rs;
+  int rc;
+  const bool same_ref = rs->join_valid && rs->join_p.match_xy_step_size == h->p.match_xy_step_size &&
+                        rs->join_p.match_threshold == h->p.match_threshold &&
+                        rs->join_p.match_threshold_dimension == h->p.match_threshold_dimension;
+  if (!same_ref) {
+    rs->join_valid = false;
+    if ((rc = spr::build_join_ref(h->p, rs->cached_ref.data(), h->n_ref, rs->J, h->err)) != SLIDE_PR_OK) return rc;
+    g_trace.mark("join_ref_build");
+    if ((rc = upload(h, rs->dj_rec0, rs->J.rec[0], st))) return rc;
+    if ((rc = upload(h, rs->dj_rec1, rs->J.rec[1], st))) return rc;
+    if ((rc = upload(h, rs->dj_cs0, rs->J.cell_start[0], st))) return rc;
+    if ((rc = upload(h, rs->dj_cs1, rs->J.cell_start[1], st))) return rc;
+    if ((rc = upload(h, rs->dj_nbr, rs->J.nbr, st))) return rc;
+    if ((rc = upload(h, rs->dj_labelbox, rs->J.labelbox, st))) return rc;
+    rs->join_valid = true;
+    rs->join_p = h->p;
+  } else {
+    h->reuse_flags |= 2;
+  }
+  // ring geometry and lattice samples (no chunks): a function of the scalar search parameters only
+  const bool same_lattice = h->lattice_valid && h->lat_hx == h->half_x && h->lat_hy == h->half_y && h->lat_yaw_half == h->yaw_half &&
+                            h->lat_p.match_xy_step_size == h->p.match_xy_step_size &&
+                            h->lat_p.match_yaw_angle_step_size == h->p.match_yaw_angle_step_size &&
+                            h->lat_p.disable_yaw_search == h->p.disable_yaw_search && !h->L.ring_major;
+  if (!same_lattice) {
+    h->lattice_valid = false; h->j_blocks_valid = false;
+    if ((rc = spr::build_lattice(h->p, h->half_x, h->half_y, h->yaw_half, 0, -1, false, h->L, h->err, true)) != SLIDE_PR_OK) return rc;
+    h->lat_hx = h->half_x; h->lat_hy = h->half_y; h->lat_yaw_half = h->yaw_half; h->lat_p = h->p;
+    h->lattice_valid = true;
+    h->lattice_on_device = false;
+  } else {
+    h->reuse_flags |= 1;
+  }
+  if (!h->j_blocks_valid) {
+    if ((rc = spr::build_join_blocks(h->L, h->p.match_xy_step_size, h->j_blocks, &h->j_drift, h->err)) != SLIDE_PR_OK) return rc;
+    if ((rc = upload(h, h->dj_lat, h->L.lat, st))) return rc;
+    if ((rc = upload(h, h->dj_cs, h->L.cs, st))) return rc;
+    if ((rc = upload(h, h->dj_blocks, h->j_blocks, st))) return rc;
+    h->j_blocks_valid = true;
+    g_trace.mark("join_blocks");
+  }
+  // query groups (label-major, Morton order inside a label)
+  if ((rc = spr::build_query_set(rs->J.labels, h->qry_rows.data(), h->n_qry, h->JQ, h->err)) != SLIDE_PR_OK) return rc;
+  const int n_groups = h->JQ.nqp / SPR_QGROUP;
+  h->j_glabel.assign((size_t)std::max(n_groups, 1), 0);
+  for (int g = 0; g < n_groups; g++) h->j_glabel[g] = h->JQ.qlabel[(size_t)g * SPR_QGROUP];  // a group's first entry is never padding
+  if ((rc = upload(h, h->dj_qxy, h->JQ.qxy, st))) return rc;
+  if ((rc = upload(h, h->dj_qdims, h->JQ.qdims, st))) return rc;
+  if ((rc = upload(h, h->dj_qlabel, h->JQ.qlabel, st))) return rc;
+  if ((rc = upload(h, h->dj_glabel, h->j_glabel, st))) return rc;
+  const size_t n_yaw = h->L.yaw.size();
+  SPR_CUDA(h, h->dj_qrot.ensure(std::max<size_t>(n_yaw * (size_t)h->JQ.nqp, 1) * 2 * sizeof(double)));
+  SPR_CUDA(h, h->dj_gbox.ensure(std::max<size_t>(n_yaw * (size_t)n_groups, 1) * sizeof(SprJoinBox)));
+  SprJoinView &V = h->JV;
+  V.lat = h->dj_lat.as<double>();
+  V.qrot = h->dj_qrot.as<double>();
+  V.gbox = h->dj_gbox.as<SprJoinBox>();
+  V.qdims = h->dj_qdims.as<double>();
+  V.glabel = h->dj_glabel.as<int32_t>();
+  V.qxy = h->dj_qxy.as<double>();
+  V.qlabel = h->dj_qlabel.as<int32_t>();
+  V.cs = h->dj_cs.as<double>();
+  V.nqp = h->JQ.nqp; V.n_groups = n_groups; V.n_yaw = (int32_t)n_yaw; V.n_labels = (int32_t)rs->J.labels.size();
+  V.rec[0] = rs->dj_rec0.as<SprJoinRef>(); V.rec[1] = rs->dj_rec1.as<SprJoinRef>();
+  V.cell_start[0] = rs->dj_cs0.as<uint32_t>(); V.cell_start[1] = rs->dj_cs1.as<uint32_t>();
+  V.nbr = rs->dj_nbr.as<SprJoinNbr>();
+  V.labelbox = rs->dj_labelbox.as<double>();
+  V.gx0 = rs->J.gx0; V.gy0 = rs->J.gy0; V.inv_w = rs->J.inv_w;
+  V.ncx = rs->J.ncx; V.ncy = rs->J.ncy;
+  V.Tstar = rs->J.Tstar; V.Sstar = rs->J.Sstar; V.thr_dim = h->p.match_threshold_dimension;
+  V.ignore_dim = h->p.ignore_dimension;
+  V.reach = rs->J.reach;
+  V.ireach = rs->J.reach + 2.0 * h->j_drift + 1e-9;
+  V.inv_step = 1.0 / h->p.match_xy_step_size;
+  V.blocks = h->dj_blocks.as<SprJoinBlock>();
+  V.n_blocks = (uint32_t)h->j_blocks.size();
+  h->join_ready = true;
+  h->prepare_ms += now_ms() - t0;
+  g_trace.mark("join_queries");
+  return SLIDE_PR_OK;
+}
+
+// Index structures of the lattice kernels (occupancy bitmaps, rank tables, chunked lattice, fixed-point query
+// groups) for the prepared problem, from the handle's copies of the maps.
+static int lattice_prepare(slide_pr_handle *h) {
+  const double t0 = now_ms();
+  cudaStream_t st = h->stream;
+  const double *ref7 = h->rs->cached_ref.data(), *qry7 = h->qry_rows.data();
+  const int32_t n_ref = h->n_ref, n_qry = h->n_qry;
+  const double half_x = h->half_x, half_y = h->half_y;
+  const bool ring_major = h->ring_major;
+  const bool trusted = true;   // prepare_impl has already compared / copied the rows
+  int rc;
   // lattice: a function of the scalar search parameters only
   const bool same_lattice = h->lattice_valid && h->lat_hx == half_x && h->lat_hy == half_y && h->lat_yaw_half == h->yaw_half &&
                             h->lat_p.match_xy_step_size == h->p.match_xy_step_size &&
                             h->lat_p.match_yaw_angle_step_size == h->p.match_yaw_angle_step_size &&
                             h->lat_p.disable_yaw_search == h->p.disable_yaw_search &&
-                            h->L.ring_major == ring_major;
+                            h->L.ring_major == ring_major && h->L.has_chunks;
   std::string lattice_err, query_err;
   bool lattice_started = false, query_started = false;
   // every exit path waits for the helper threads (they write into the handle)
@@ -452,6 +625,7 @@ static int prepare_impl(slide_pr_handle *h, RefSide *slot, bool trusted, const d
   } joiner{h, &lattice_started, &query_started};
   if (!same_lattice) {  // built on a helper thread while this one builds the bitmaps
     h->lattice_valid = false;
+    h->j_blocks_valid = false;   // the blocks of the pair-join scorer index the sample arrays that are rebuilt here
     h->worker_lattice.submit([h, half_x, half_y, ring_major, &lattice_err]() {
       cudaSetDevice(h->device);  // the page-locked buffers grown by this job belong to the handle's device (one process may drive several GPUs)
       return spr::build_lattice(h->p, half_x, half_y, h->yaw_half, 0, -1, ring_major, h->L, lattice_err);
@@ -502,7 +676,6 @@ static int prepare_impl(slide_pr_handle *h, RefSide *slot, bool trusted, const d
     start_query_job();  // the query set only needs the labels and the grid
     if ((rc = spr::build_ref_marks(h->p, ref7, n_ref, h->rs->R, h->err)) != SLIDE_PR_OK) return rc;
     g_trace.mark("ref_bitmaps_build");
-    if (!trusted) h->rs->cached_ref.assign(ref7, ref7 + (size_t)n_ref * 7);
     h->rs->cached_reach = h->rs->R.reach_limit; h->rs->cached_ref_p = h->p;
     h->rs->ref_index_valid = true;
     h->rs->ranks_pending = true;
@@ -518,7 +691,6 @@ static int prepare_impl(slide_pr_handle *h, RefSide *slot, bool trusted, const d
     if ((rc = upload(h, h->rs->d_reftab, h->rs->R.reftab, st))) return rc;
     if ((rc = upload(h, h->rs->d_refbase, h->rs->R.ref_base, st))) return rc;
     if ((rc = upload(h, h->rs->d_labof, h->rs->R.lab_of, st))) return rc;
-    if ((rc = upload(h, h->rs->d_ref7, h->rs->cached_ref, st))) return rc;
     g_trace.mark("ref_bitmaps_upload");
   } else {
     h->reuse_flags |= 2;
@@ -532,8 +704,6 @@ static int prepare_impl(slide_pr_handle *h, RefSide *slot, bool trusted, const d
   if ((rc = upload(h, h->d_qdims, h->Q.qdims, st))) return rc;
   if ((rc = upload(h, h->d_labelseg, h->Q.label_gseg, st))) return rc;
   if ((rc = upload(h, h->d_qlabel, h->Q.qlabel, st))) return rc;
-  h->qry_rows.assign(qry7, qry7 + (size_t)n_qry * 7);
-  if ((rc = upload(h, h->d_qry7, h->qry_rows, st))) return rc;
   if ((rc = join_lattice()) != SLIDE_PR_OK) return rc;
   const size_t nrot = (size_t)std::max<size_t>((size_t)h->L.yaw.size() * (size_t)h->Q.nqp, 1);
   const size_t ngb = (size_t)std::max<size_t>((size_t)h->L.yaw.size() * (size_t)(h->Q.nqp / SPR_QGROUP), 1);
@@ -541,10 +711,6 @@ static int prepare_impl(slide_pr_handle *h, RefSide *slot, bool trusted, const d
   SPR_CUDA(h, h->d_qrotq.ensure(nrot * 2 * sizeof(int32_t)));
   SPR_CUDA(h, h->d_qrotq_yx.ensure(nrot * 2 * sizeof(int32_t)));
   SPR_CUDA(h, h->d_gbox.ensure(ngb * sizeof(SprBox)));
-  SPR_CUDA(h, h->d_work.ensure(4096 * sizeof(unsigned long long)));
-  SPR_CUDA(h, h->d_best.ensure(sizeof(unsigned long long)));
-  SPR_CUDA(h, h->d_stats.ensure(4 * sizeof(unsigned long long)));
-  SPR_CUDA(h, h->d_match.ensure(std::max<size_t>(n_qry, 1) * sizeof(int32_t)));
 
   SprView &V = h->V;
   V.nqp = h->Q.nqp;
@@ -578,13 +744,20 @@ static int prepare_impl(slide_pr_handle *h, RefSide *slot, bool trusted, const d
   V.Sstar = h->rs->R.Sstar;
   V.thr_dim = h->p.match_threshold_dimension;
   V.ignore_dim = h->p.ignore_dimension;
-  // no synchronisation here: every upload reads page-locked vectors owned by the handle (the
-  // caller's rows were copied), which stay untouched until the next prepare
-  SPR_CUDA(h, cudaEventRecord(h->ev_prep, st));  // a search on another stream waits for these uploads
-  if (g_pageable_uploads.load() > 0) SPR_CUDA(h, cudaStreamSynchronize(st));  // page-locking failed somewhere: do not rely on it
-  h->prepared = true;
-  h->prepare_ms = now_ms() - t0;
+  h->lattice_ready = true;
+  h->prepare_ms += now_ms() - t0;
   g_trace.mark("query_upload");
+  return SLIDE_PR_OK;
+}
+
+// The lattice kernels' structures, built the first time a call needs them for the prepared problem.
+static int ensure_lattice(slide_pr_handle *h, cudaStream_t st) {
+  if (h->lattice_ready) return SLIDE_PR_OK;
+  const int rc = lattice_prepare(h);
+  if (rc != SLIDE_PR_OK) return rc;
+  SPR_CUDA(h, cudaEventRecord(h->ev_prep, h->stream));
+  if (st != h->stream) SPR_CUDA(h, cudaStreamWaitEvent(st, h->ev_prep, 0));
+  if (g_pageable_uploads.load() > 0) SPR_CUDA(h, cudaStreamSynchronize(h->stream));
   return SLIDE_PR_OK;
 }
 
@@ -643,6 +816,92 @@ static PlanePlan plan_plane(slide_pr_handle *h, const SprLaunch &K0, uint32_t d,
   return P;
 }
 
+// The pair-join scorer over the prepared problem: the exact inlier count of every hypothesis of the slice /
+// shard (spr_join.cu), arg-max on the device.  Two launches: rotate + score.
+static int join_search(slide_pr_handle *h, const slide_pr_search_opts &o, cudaStream_t st, slide_pr_match_result *out) {
+  int rc;
+  if (!h->join_ready) {
+    if ((rc = join_prepare(h)) != SLIDE_PR_OK) return rc;
+    SPR_CUDA(h, cudaEventRecord(h->ev_prep, h->stream));
+    if (st != h->stream) SPR_CUDA(h, cudaStreamWaitEvent(st, h->ev_prep, 0));
+  }
+  const int n_yaw = (int)h->L.yaw.size();
+  const int64_t n_trans = (int64_t)h->L.n_translations;
+  const int64_t tb = std::min<int64_t>(o.trans_begin < 0 ? 0 : o.trans_begin, n_trans);
+  const int64_t te = o.trans_end < 0 ? n_trans : std::max<int64_t>(std::min<int64_t>(o.trans_end, n_trans), tb);
+  int64_t n_counts = 0;
+  if (o.counts_out) {
+    if (o.trans_end < 0) { h->err = "counts_out needs trans_end >= 0"; return SLIDE_PR_ERR_INVALID; }
+    n_counts = (te - tb) * n_yaw;
+    if (n_counts > o.counts_cap) { h->err = "counts_cap too small"; return SLIDE_PR_ERR_INVALID; }
+    SPR_CUDA(h, h->d_counts.ensure(std::max<size_t>((size_t)n_counts, 1) * sizeof(int32_t)));
+    SPR_CUDA(h, cudaMemsetAsync(h->d_counts.p, 0xff, std::max<size_t>((size_t)n_counts, 1) * sizeof(int32_t), st));
+  }
+  SPR_CUDA(h, cudaMemsetAsync(h->d_best.p, 0, sizeof(unsigned long long), st));
+  // an inlier count reached elsewhere (another shard): see slide_pr_search
+  const unsigned long long incumbent_key = o.incumbent_inliers > 0 ? ((unsigned long long)(o.incumbent_inliers + 1) << SPR_KEY_IDX_BITS) : 0ull;
+  if (h->h_scalars.size() < 8) h->h_scalars.assign(8, 0ull);
+  if (incumbent_key) {
+    h->h_scalars[7] = incumbent_key;
+    SPR_CUDA(h, cudaMemcpyAsync(h->d_best.p, h->h_scalars.data() + 7, sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+  }
+  SPR_CUDA(h, cudaMemsetAsync(h->d_work.p, 0, sizeof(unsigned long long), st));
+  SprJoinLaunch K{};
+  K.work_counter = h->d_work.as<unsigned long long>();
+  K.best_key = h->d_best.as<unsigned long long>();
+  K.counts_out = o.counts_out ? h->d_counts.as<int32_t>() : nullptr;
+  K.ord_begin = (unsigned long long)tb; K.ord_end = (unsigned long long)te;
+  K.shard_index = o.shard_index; K.shard_count = o.shard_count;
+  int launches = 0;
+  SPR_CUDA(h, cudaEventRecord(h->ev0, st));
+  if (h->JV.nqp > 0 && n_yaw > 0) {
+    SPR_CUDA(h, spr_launch_join_rotate(h->JV, h->dj_qrot.as<double>(), h->dj_gbox.as<SprJoinBox>(), st));
+    launches++;
+  }
+  if (n_yaw > 0 && te > tb && !h->j_blocks.empty()) {
+    SPR_CUDA(h, spr_launch_join_score(h->JV, K, h->sm_count, st));
+    launches++;
+  }
+  SPR_CUDA(h, cudaEventRecord(h->ev1, st));
+  g_trace.mark("search_launch");
+  unsigned long long *hs = h->h_scalars.data();
+  hs[0] = 0ull;
+  SPR_CUDA(h, cudaMemcpyAsync(hs, h->d_best.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (o.counts_out && n_counts > 0)
+    SPR_CUDA(h, cudaMemcpyAsync(o.counts_out, h->d_counts.p, (size_t)n_counts * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  SPR_CUDA(h, cudaStreamSynchronize(st));
+  g_trace.mark("search_sync");
+  float ms = 0;
+  SPR_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  out->kernel_ms = ms;
+  out->gpu_launches = launches;
+  out->search_mode = 2;
+  out->rings_scored = h->L.rings;
+  out->h2d_bytes = h->h2d_bytes;
+  out->d2h_bytes = (int64_t)sizeof(unsigned long long) + n_counts * (int64_t)sizeof(int32_t);
+  // hypotheses scored by this shard: lattice samples of its blocks inside the slice x yaw candidates
+  {
+    const uint32_t sc = o.shard_count > 1 ? (uint32_t)o.shard_count : 1u, si = o.shard_count > 1 ? (uint32_t)o.shard_index : 0u;
+    uint64_t samples = 0;
+    for (size_t b = si; b < h->j_blocks.size(); b += sc) {
+      const SprJoinBlock &B = h->j_blocks[b];
+      if (tb == 0 && te == n_trans) { samples += (uint64_t)B.nx * B.ny; continue; }
+      for (uint32_t i = 0; i < B.nx; i++) {
+        const int64_t lo = std::max<int64_t>((int64_t)B.ord0 + (int64_t)i * B.row_stride, tb);
+        const int64_t hi = std::min<int64_t>((int64_t)B.ord0 + (int64_t)i * B.row_stride + B.ny, te);
+        if (hi > lo) samples += (uint64_t)(hi - lo);
+      }
+    }
+    out->hypotheses_scored = (int64_t)(samples * (uint64_t)n_yaw);
+  }
+  const unsigned long long key = hs[0];
+  if (key != 0ull && key != incumbent_key) {
+    out->best_num_inliers = spr_key_count(key);
+    out->best_hyp_index = spr_key_index(key);
+  }
+  return SLIDE_PR_OK;
+}
+
 int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_pr_match_result *out) {
   if (!h || !out) return SLIDE_PR_ERR_INVALID;
   if (!h->prepared) { h->err = "slide_pr_search before slide_pr_prepare"; return SLIDE_PR_ERR_INVALID; }
@@ -655,6 +914,18 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   fill_result_header(h, out);
   if (h->L.status == SLIDE_PR_SANITY_RETURN) return SLIDE_PR_OK;
   int rc;
+  // engine: the pair-join scorer (exhaustive = 4, or the default unless the handle says otherwise), or the
+  // lattice kernels (1: every hypothesis verified; 2: bounds only; 3: bound-and-verify)
+  {
+    const bool want_join = o.exhaustive == 4 || (o.exhaustive == 0 && join_is_default(h));
+    const bool can_join = join_supported(h) && !o.collect_stats && !o.reuse_bounds;
+    if (o.exhaustive == 4 && !can_join) { h->err = "the pair-join scorer does not serve this request (statistics, reused bounds, a binding compute budget or more than 65535 query landmarks)"; return SLIDE_PR_ERR_UNSUPPORTED; }
+    if (want_join && can_join) return join_search(h, o, st, out);
+    if (o.exhaustive == 3 || o.exhaustive == 4) o.exhaustive = 0;
+    if ((rc = ensure_lattice(h, st)) != SLIDE_PR_OK) return rc;
+    out->prepare_ms = (float)h->prepare_ms;
+    out->reuse = h->reuse_flags;
+  }
   const int64_t tb = o.trans_begin < 0 ? 0 : o.trans_begin, te = o.trans_end;
   if (tb != h->lat_tb || te != h->lat_te) {  // re-chunk the lattice for the requested slice
     if ((rc = spr::build_lattice(h->p, h->half_x, h->half_y, h->yaw_half, tb, te, h->ring_major, h->L, h->err)) != SLIDE_PR_OK) return rc;
@@ -727,7 +998,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
   // the result says so (search_mode = 0) and the caller skips the verification half.
   if (o.exhaustive == 2 && !can_bound && o.counts_out) { h->err = "upper bounds are not available for this problem"; return SLIDE_PR_ERR_UNSUPPORTED; }
   const bool bounds_only = o.exhaustive == 2 && can_bound;
-  const bool prune = bounds_only || (!o.exhaustive && !o.counts_out && !o.collect_stats && can_bound && !h->force_exhaustive && !h->p.exhaustive_search);
+  const bool prune = bounds_only || (!o.exhaustive && !o.counts_out && !o.collect_stats && can_bound && !h->force_exhaustive && h->p.exhaustive_search != 1);
   const int n_planes = spr_bound_planes(h->V.nqp);
   size_t cand_off[2] = {0, 0};
   if (prune) {
@@ -1026,7 +1297,7 @@ int slide_pr_extract(slide_pr_handle *h, int64_t hyp_index, int32_t *ref_idx_out
   io->R_t[6] = 0; io->R_t[7] = 0;  io->R_t[8] = 1;
   cudaStream_t st = h->stream;
   SPR_CUDA(h, spr_launch_extract(h->rs->d_ref7.as<double>(), h->n_ref, h->d_qry7.as<double>(), h->n_qry, c, s, tx, ty,
-                                 h->rs->R.Tstar, h->rs->R.Sstar, h->p.match_threshold_dimension, h->p.ignore_dimension,
+                                 h->Tstar, h->Sstar, h->p.match_threshold_dimension, h->p.ignore_dimension,
                                  h->d_match.as<int32_t>(), st));
   io->gpu_launches += 1;
   if ((int)h->h_match.size() < std::max(h->n_qry, 1)) h->h_match.resize(std::max(h->n_qry, 1));
@@ -1260,6 +1531,7 @@ int slide_pr_map_cache_put(slide_pr_handle *h, int64_t robot_id, uint64_t versio
   if (h->rs == &E) h->prepared = false;
   E.robot_id = robot_id; E.version = version; E.n_rows = n;
   E.ref_index_valid = false; E.ranks_pending = false;
+  E.join_valid = false; E.ref7_uploaded = false; E.rows_valid = true;
   E.shifted = h->p.inter_loop_closure != 0;
   E.cached_ref.assign(rows7, rows7 + (size_t)n * 7);
   double c[2] = {0, 0}, b[2] = {0, 0};
@@ -1514,6 +1786,7 @@ int slide_pr_generate_and_score(slide_pr_handle *h, const double *tris_model6, c
   slide_pr_generate_info local{}, *I = info ? info : &local;
   std::memset(I, 0, sizeof(*I));
   if (t_model == 0 || t_data == 0) return SLIDE_PR_OK;
+  { const int lrc = ensure_lattice(h, st); if (lrc != SLIDE_PR_OK) return lrc; }   // the list scorer probes the occupancy bitmaps
   if (h->rs->ranks_pending) { const int rrc = finish_ranks(h, st); if (rrc != SLIDE_PR_OK) return rrc; }
   GenDevice G;
   int rc = gen_match_on_device(h, tris_model6, labels_model3, t_model, tris_data6, labels_data3, t_data, threshold, &G);
@@ -1598,6 +1871,7 @@ int slide_pr_score_hypotheses(slide_pr_handle *h, const double *hyps4, int64_t n
   if (!h || !out || (n > 0 && !hyps4) || n < 0) return SLIDE_PR_ERR_INVALID;
   if (!h->prepared) { h->err = "slide_pr_score_hypotheses before slide_pr_prepare"; return SLIDE_PR_ERR_INVALID; }
   SPR_CUDA(h, cudaSetDevice(h->device));
+  { const int lrc = ensure_lattice(h, h->stream); if (lrc != SLIDE_PR_OK) return lrc; }   // the list scorer probes the occupancy bitmaps
   if (h->rs->ranks_pending) { const int rrc = finish_ranks(h, h->stream); if (rrc != SLIDE_PR_OK) return rrc; }
   cudaStream_t st = h->stream;
   fill_result_header(h, out);

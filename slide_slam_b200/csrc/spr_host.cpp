@@ -117,7 +117,8 @@ struct RectEmitter {
 }  // namespace
 
 int build_lattice(const slide_pr_params &p, double half_x, double half_y, double yaw_half,
-                  int64_t trans_begin, int64_t trans_end, bool ring_major, Lattice &L, std::string &err) {
+                  int64_t trans_begin, int64_t trans_end, bool ring_major, Lattice &L, std::string &err,
+                  bool rings_only) {
   // reset, keeping the vectors' capacity across calls
   L.status = 0; L.rings = 0; L.ox = L.oy = 0; L.n_translations = 0; L.ring_major = false;
   L.yaw.clear(); L.cs.clear(); L.lat.clear(); L.ring.clear();
@@ -216,7 +217,9 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
     RectEmitter E{L, k, R.x_off, R.y_off, xs, ys, trans_begin, trans_end, n_emitted};
     E.succ = ring_major ? nullptr : &succ;
     const int nx = (int)R.nx, ny = (int)R.ny;
-    if (!has_box) {
+    if (rings_only) {
+      // ring geometry and samples only
+    } else if (!has_box) {
       E.rect(0, nx, 0, ny, ord, (uint64_t)ny);
     } else {
       const uint64_t cnt_in = (uint64_t)(ny - n_in_y);
@@ -237,6 +240,12 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
   L.n_translations = ord;
   if (ord * (uint64_t)std::max<size_t>(L.yaw.size(), 1) >= (1ull << SPR_KEY_IDX_BITS)) {
     err = "more than 2^40 hypotheses"; return SLIDE_PR_ERR_UNSUPPORTED;
+  }
+  L.has_chunks = !rings_only;
+  if (rings_only) {
+    L.dg_bits.clear();
+    L.ring_major = ring_major;
+    return SLIDE_PR_OK;
   }
   // Group the chunks by direction (every warp = 32 consecutive chunks probes ONE bitmap plane),
   // padding each group to a whole number of warps with empty chunks.  ring_major keeps the
@@ -622,8 +631,12 @@ static inline uint32_t part1by1(uint32_t x) {
 }
 
 int build_query_set(const RefIndex &R, const double *qry7, int n_qry, QuerySet &Q, std::string &err) {
+  return build_query_set(R.labels, qry7, n_qry, Q, err);
+}
+
+int build_query_set(const std::vector<double> &labels, const double *qry7, int n_qry, QuerySet &Q, std::string &err) {
   Q.nq = Q.nqp = 0;  // the (page-locked) vectors keep their capacity across calls
-  const int n_labels = (int)R.labels.size();
+  const int n_labels = (int)labels.size();
   struct Item { int l; uint32_t morton; int j; };
   std::vector<Item> items;
   double minx = HUGE_VAL, maxx = -HUGE_VAL, miny = HUGE_VAL, maxy = -HUGE_VAL;
@@ -638,10 +651,10 @@ int build_query_set(const RefIndex &R, const double *qry7, int n_qry, QuerySet &
     const double *q = qry7 + 7 * (size_t)j;
     if (!(q[0] == q[0])) continue;
     const double lab = q[0] + 0.0;
-    auto it = std::lower_bound(R.labels.begin(), R.labels.end(), lab);
-    if (it == R.labels.end() || *it != lab) continue;  // no reference object can ever match it
+    auto it = std::lower_bound(labels.begin(), labels.end(), lab);
+    if (it == labels.end() || *it != lab) continue;  // no reference object can ever match it
     const uint32_t mx = (uint32_t)((q[1] - minx) * sx), my = (uint32_t)((q[2] - miny) * sy);
-    items.push_back({(int)(it - R.labels.begin()), part1by1(mx) | (part1by1(my) << 1), j});
+    items.push_back({(int)(it - labels.begin()), part1by1(mx) | (part1by1(my) << 1), j});
   }
   std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
     if (a.l != b.l) return a.l < b.l;
@@ -670,6 +683,177 @@ int build_query_set(const RefIndex &R, const double *qry7, int n_qry, QuerySet &
     Q.qxy[2 * s] = q[1]; Q.qxy[2 * s + 1] = q[2];
     Q.qdims[3 * s] = q[4]; Q.qdims[3 * s + 1] = q[5]; Q.qdims[3 * s + 2] = q[6];
   }
+  return SLIDE_PR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// pair-join scorer (spr_join.h)
+// ------------------------------------------------------------------------------------------
+int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, JoinRef &J, std::string &err) {
+  J.n_ref = n_ref;
+  J.labels.clear();
+  const double step = p.match_xy_step_size, thr = p.match_threshold;
+  if (!(step > 0) || !std::isfinite(step)) { err = "match_xy_step_size must be positive and finite"; return SLIDE_PR_ERR_INVALID; }
+  if (thr > 0 && std::isinf(thr)) { err = "infinite match_threshold is not supported"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  J.Tstar = sqrt_threshold(thr);
+  J.Sstar = div3_threshold(p.match_threshold_dimension);
+  const bool matchable = thr > 0 && std::isfinite(thr);
+  J.reach = matchable ? thr * (1.0 + 1e-9) + 1e-9 : 0.0;  // covers the fp64 rounding of the reference's test
+  double minx = HUGE_VAL, maxx = -HUGE_VAL, miny = HUGE_VAL, maxy = -HUGE_VAL;
+  for (int i = 0; i < n_ref; i++) {
+    const double *r = ref7 + 7 * (size_t)i;
+    if (!std::isfinite(r[1]) || !std::isfinite(r[2])) { err = "non-finite reference coordinate"; return SLIDE_PR_ERR_NONFINITE; }
+    minx = std::min(minx, r[1]); maxx = std::max(maxx, r[1]);
+    miny = std::min(miny, r[2]); maxy = std::max(maxy, r[2]);
+    if (r[0] == r[0]) J.labels.push_back(r[0] + 0.0);  // NaN labels never compare equal (PR.cpp:306)
+  }
+  std::sort(J.labels.begin(), J.labels.end());
+  J.labels.erase(std::unique(J.labels.begin(), J.labels.end()), J.labels.end());
+  const int n_labels = (int)J.labels.size();
+  if (n_ref == 0) { minx = maxx = miny = maxy = 0; }
+  // coarse grid: cells of 8 lattice steps (a block is about 10 steps wide), not smaller than the reach,
+  // and few enough that the per-label cell tables stay small
+  double w = std::max(8.0 * step, J.reach);
+  for (;;) {
+    const double cx = std::floor((maxx - minx) / w) + 1.0, cy = std::floor((maxy - miny) / w) + 1.0;
+    if (cx * cy * std::max(n_labels, 1) <= 16777216.0 && cx < 30000.0 && cy < 30000.0) break;
+    w *= 2.0;
+    if (!std::isfinite(w)) { err = "reference map extent is not finite"; return SLIDE_PR_ERR_NONFINITE; }
+  }
+  J.w = w; J.inv_w = 1.0 / w; J.gx0 = minx; J.gy0 = miny;
+  auto cell_of = [&](double v, double g0, int n) {  // the kernel evaluates the same expression (monotone in v)
+    const double f = std::floor((v - g0) * J.inv_w);
+    return (int)std::min(std::max(f, 0.0), (double)(n - 1));
+  };
+  J.ncx = (int)std::floor((maxx - minx) * J.inv_w) + 1;
+  J.ncy = (int)std::floor((maxy - miny) * J.inv_w) + 1;
+  const size_t n_cells = (size_t)J.ncx * (size_t)J.ncy;
+  // label bucket, cell and label bounding box of every landmark
+  std::vector<int32_t> lab((size_t)std::max(n_ref, 1), -1), cxs((size_t)std::max(n_ref, 1), 0), cys((size_t)std::max(n_ref, 1), 0);
+  J.labelbox.assign(4 * (size_t)std::max(n_labels, 1), 0.0);
+  for (int l = 0; l < n_labels; l++) {
+    J.labelbox[4 * (size_t)l] = HUGE_VAL; J.labelbox[4 * (size_t)l + 1] = -HUGE_VAL;
+    J.labelbox[4 * (size_t)l + 2] = HUGE_VAL; J.labelbox[4 * (size_t)l + 3] = -HUGE_VAL;
+  }
+  size_t n_kept = 0;
+  for (int i = 0; i < n_ref; i++) {
+    const double *r = ref7 + 7 * (size_t)i;
+    if (!(r[0] == r[0])) continue;
+    const int l = (int)(std::lower_bound(J.labels.begin(), J.labels.end(), r[0] + 0.0) - J.labels.begin());
+    lab[i] = l; cxs[i] = cell_of(r[1], J.gx0, J.ncx); cys[i] = cell_of(r[2], J.gy0, J.ncy);
+    double *lb = J.labelbox.data() + 4 * (size_t)l;
+    lb[0] = std::min(lb[0], r[1]); lb[1] = std::max(lb[1], r[1]);
+    lb[2] = std::min(lb[2], r[2]); lb[3] = std::max(lb[3], r[2]);
+    n_kept++;
+  }
+  // counting sort into both join orders (label, band, along cell); ascending reference index inside a cell
+  std::vector<uint32_t> pos0, pos1;  // record position of landmark i in each order
+  pos0.assign((size_t)std::max(n_ref, 1), 0u); pos1 = pos0;
+  for (int d = 0; d < 2; d++) {
+    uvec<uint32_t> &cs = J.cell_start[d];
+    cs.assign((size_t)std::max(n_labels, 1) * n_cells + 1, 0u);
+    auto key = [&](int i) -> size_t {
+      const size_t c = d == 0 ? (size_t)cxs[i] * (size_t)J.ncy + (size_t)cys[i] : (size_t)cys[i] * (size_t)J.ncx + (size_t)cxs[i];
+      return (size_t)lab[i] * n_cells + c;
+    };
+    for (int i = 0; i < n_ref; i++) if (lab[i] >= 0) cs[key(i) + 1]++;
+    for (size_t k = 1; k < cs.size(); k++) cs[k] += cs[k - 1];
+    std::vector<uint32_t> fill(cs.begin(), cs.end() - 1);
+    std::vector<uint32_t> &pos = d == 0 ? pos0 : pos1;
+    for (int i = 0; i < n_ref; i++) if (lab[i] >= 0) pos[i] = fill[key(i)]++;
+    J.rec[d].assign(std::max<size_t>(n_kept, 1), SprJoinRef{});
+  }
+  // same-label landmarks with a lower reference index that can match the same point: within 2 x reach
+  J.nbr.clear();
+  const double r2 = 2.0 * J.reach * (1.0 + 1e-9) + 1e-9;
+  const int span = (int)std::floor(r2 * J.inv_w) + 1;
+  const uvec<uint32_t> &cs0 = J.cell_start[0];
+  std::vector<int32_t> by_pos0(std::max<size_t>(n_kept, 1), -1);  // landmark at each record position of order 0
+  for (int i = 0; i < n_ref; i++) if (lab[i] >= 0) by_pos0[pos0[i]] = i;
+  for (int i = 0; i < n_ref; i++) {
+    if (lab[i] < 0) continue;
+    const double *r = ref7 + 7 * (size_t)i;
+    const uint32_t off = (uint32_t)J.nbr.size();
+    if (matchable) {
+      for (int cx = std::max(cxs[i] - span, 0); cx <= std::min(cxs[i] + span, J.ncx - 1); cx++) {
+        const int cy0 = std::max(cys[i] - span, 0), cy1 = std::min(cys[i] + span, J.ncy - 1);
+        const size_t base = (size_t)lab[i] * n_cells + (size_t)cx * (size_t)J.ncy;
+        for (uint32_t k = cs0[base + cy0]; k < cs0[base + cy1 + 1]; k++) {
+          const int o = by_pos0[k];
+          if (o >= i) continue;  // ascending inside a cell, but cells are visited in any order
+          const double *q = ref7 + 7 * (size_t)o;
+          if (std::fabs(q[1] - r[1]) <= r2 && std::fabs(q[2] - r[2]) <= r2) J.nbr.push_back(SprJoinNbr{q[1], q[2], q[4], q[5], q[6]});
+        }
+      }
+    }
+    const uint32_t cnt = (uint32_t)J.nbr.size() - off;
+    const SprJoinRef rec{r[1], r[2], r[4], r[5], r[6], off, cnt};
+    J.rec[0][pos0[i]] = rec;
+    J.rec[1][pos1[i]] = rec;
+  }
+  if (J.nbr.empty()) J.nbr.push_back(SprJoinNbr{});
+  return SLIDE_PR_OK;
+}
+
+int build_join_blocks(const Lattice &L, double step, uvec<SprJoinBlock> &blocks, double *drift, std::string &err) {
+  blocks.clear();
+  double dmax = 0.0;
+  const double *lat = L.lat.data();
+  // a rectangle ix in [ix0, ix1), iy in [iy0, iy1) of ring k; ordinal(ix, iy) = ord0 + (ix - ix0) * row_stride + (iy - iy0)
+  auto rect = [&](const Lattice::Ring &R, uint32_t k, int ix0, int ix1, int iy0, int iy1, uint64_t ord0, uint64_t row_stride) {
+    const int w = ix1 - ix0, h = iy1 - iy0;
+    if (w <= 0 || h <= 0) return;
+    // tiles of bw x bh samples: the short side in pieces of at most 32, the long side as far as the
+    // counters of a block reach (SPJ_MAX_SLOTS totals; micro-tile arrays with one spare row and word)
+    int bw, bh;
+    auto ok = [](int nx, int ny) {   // the kernel's limits: totals, and the micro-tile arrays with a spare row and word
+      return nx * ny <= SPJ_MAX_SLOTS && ((nx >> 1) + 2) * ((ny >> 1) + 1) + 1 <= SPJ_MAX_WORDS;
+    };
+    if (w <= h) {
+      const int pieces = (w + 31) / 32;
+      bw = (w + pieces - 1) / pieces;
+      bh = std::min(h, SPJ_MAX_SLOTS / bw);
+      while (bh > 1 && !ok(bw, bh)) bh--;
+    } else {
+      const int pieces = (h + 31) / 32;
+      bh = (h + pieces - 1) / pieces;
+      bw = std::min(w, SPJ_MAX_SLOTS / bh);
+      while (bw > 1 && !ok(bw, bh)) bw--;
+    }
+    for (int bx = ix0; bx < ix1; bx += bw)
+      for (int by = iy0; by < iy1; by += bh) {
+        SprJoinBlock B;
+        B.nx = (uint32_t)std::min(bw, ix1 - bx); B.ny = (uint32_t)std::min(bh, iy1 - by);
+        B.xi = R.x_off + (uint32_t)bx; B.yi = R.y_off + (uint32_t)by;
+        B.ord0 = (uint32_t)(ord0 + (uint64_t)(bx - ix0) * row_stride + (uint64_t)(by - iy0));
+        B.row_stride = (uint32_t)row_stride;
+        B.dir = B.ny >= B.nx ? 0u : 1u;
+        B.ring = k;
+        blocks.push_back(B);
+      }
+  };
+  for (size_t k = 0; k < L.ring.size(); k++) {
+    const Lattice::Ring &R = L.ring[k];
+    const double *xs = lat + R.x_off, *ys = lat + R.y_off;
+    for (uint32_t i = 0; i < R.nx; i++) dmax = std::max(dmax, std::fabs(xs[i] - (xs[0] + (double)i * step)));
+    for (uint32_t i = 0; i < R.ny; i++) dmax = std::max(dmax, std::fabs(ys[i] - (ys[0] + (double)i * step)));
+    const int nx = (int)R.nx, ny = (int)R.ny;
+    const int n_in_x = R.ixh >= R.ixl ? R.ixh - R.ixl + 1 : 0, n_in_y = R.iyh >= R.iyl ? R.iyh - R.iyl + 1 : 0;
+    const uint64_t ord = R.ord_base;
+    if (!(n_in_x > 0 && n_in_y > 0)) {
+      rect(R, (uint32_t)k, 0, nx, 0, ny, ord, (uint64_t)ny);
+    } else {  // the four rectangles around the already-searched box, in the reference's ordinal layout (build_lattice)
+      const uint64_t cnt_in = (uint64_t)(ny - n_in_y);
+      const uint64_t base_b = ord + (uint64_t)R.ixl * ny;
+      const uint64_t base_c = base_b + (uint64_t)n_in_x * cnt_in;
+      rect(R, (uint32_t)k, 0, R.ixl, 0, ny, ord, (uint64_t)ny);
+      rect(R, (uint32_t)k, R.ixl, R.ixh + 1, 0, R.iyl, base_b, cnt_in);
+      rect(R, (uint32_t)k, R.ixl, R.ixh + 1, R.iyh + 1, ny, base_b + (uint64_t)R.iyl, cnt_in);
+      rect(R, (uint32_t)k, R.ixh + 1, nx, 0, ny, base_c, (uint64_t)ny);
+    }
+    if (blocks.size() > (1u << 24)) { err = "more than 2^24 lattice blocks"; return SLIDE_PR_ERR_UNSUPPORTED; }
+  }
+  if (drift) *drift = dmax;
   return SLIDE_PR_OK;
 }
 

@@ -9,6 +9,7 @@
 
 #include "../../include/slide_pr.h"
 #include "spr_types.h"
+#include "spr_join_types.h"
 
 namespace spr {
 
@@ -57,13 +58,16 @@ struct Lattice {
   std::vector<uint8_t> sort_second;
   std::vector<uint32_t> dg_bits;  // [chunks / 64] valid bits (lattice translations) of every double group
   bool ring_major = false;
+  bool has_chunks = false;        // false after a rings_only build
   uint32_t dir_begin[2] = {0, 0}, dir_end[2] = {0, 0};  // !ring_major: all chunks of direction d
 };
 
 // PR.cpp:136-241.  yaw_half is match_yaw_half_range_ (inter) or the intra value.
 // trans_begin/trans_end (end < 0: none) restrict the valid bits to a range of ordinals.
+// rings_only: yaw table, ring geometry and lattice samples only, no chunks (all the pair-join scorer needs).
 int build_lattice(const slide_pr_params &p, double half_x, double half_y, double yaw_half,
-                  int64_t trans_begin, int64_t trans_end, bool ring_major, Lattice &L, std::string &err);
+                  int64_t trans_begin, int64_t trans_end, bool ring_major, Lattice &L, std::string &err,
+                  bool rings_only = false);
 
 // translation (x, y) of a canonical ordinal; false if out of range
 bool translation_of(const Lattice &L, uint64_t ordinal, double *x, double *y, int *ring);
@@ -113,6 +117,7 @@ struct QuerySet {
   uvec<int32_t> label_gseg;  // [n_labels + 1] group (SPR_QGROUP queries) boundaries
 };
 int build_query_set(const RefIndex &R, const double *qry7, int n_qry, QuerySet &Q, std::string &err);
+int build_query_set(const std::vector<double> &labels, const double *qry7, int n_qry, QuerySet &Q, std::string &err);
 
 // thresholds: sqrt(d2) < thr <=> d2 < Tstar ; (s / 3) < thr_dim <=> s < Sstar
 double sqrt_threshold(double thr);
@@ -126,5 +131,27 @@ void estimate_tf(const double *a2, const double *b2, int k, double *tf9);
 void svd_jacobi(const double *A, int n, double *U, double *S, double *V);
 void mat4_mul(const double *A, const double *B, double *C);
 bool mat4_rigid_inverse(const double *A, double *Ainv);
+
+
+// ------------------------------------------------------------------------------------------
+// pair-join scorer (spr_join.h): reference landmarks binned by label and coarse grid cell in both
+// join directions, lower-index neighbours of every landmark, and the lattice cut into blocks
+// ------------------------------------------------------------------------------------------
+struct JoinRef {
+  std::vector<double> labels;        // distinct finite reference labels, ascending
+  uvec<SprJoinRef> rec[2];
+  uvec<uint32_t> cell_start[2];      // [n_labels * n_cells + 1]
+  uvec<SprJoinNbr> nbr;
+  uvec<double> labelbox;             // [n_labels][4]
+  double gx0 = 0, gy0 = 0, w = 1, inv_w = 1;
+  int ncx = 1, ncy = 1;
+  double Tstar = 0, Sstar = 0;
+  double reach = 0;                  // a match implies |dx|, |dy| < reach
+  int n_ref = 0;
+};
+int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, JoinRef &J, std::string &err);
+// blocks of the lattice L (needs L.ring / L.lat); *drift: largest deviation of a sample from
+// first sample + index * step over all rings
+int build_join_blocks(const Lattice &L, double step, uvec<SprJoinBlock> &blocks, double *drift, std::string &err);
 
 }  // namespace spr

@@ -1,0 +1,30 @@
+// spr_join.h -- the pair-join scorer: exact inlier count of EVERY lattice hypothesis from the
+// (query landmark, reference landmark) pairs that can match at all.
+//
+// MatchMaps (place_recognition.cpp:98-387) counts, for every hypothesis (yaw, x, y), the query
+// landmarks that have a reference landmark of the same label within match_threshold_ (and with
+// matching dimensions).  Seen from a PAIR (q, r) under one yaw: the pair is an inlier exactly for the
+// lattice translations within match_threshold_ of  r - R(yaw) q  -- a handful of lattice points.  The
+// pair-join scorer enumerates those pairs through a coarse uniform grid over the reference map and
+// adds each pair's hits to per-hypothesis counters in shared memory: work proportional to the sum of
+// all inlier counts instead of (hypotheses x query landmarks).  The decision arithmetic is the
+// reference's (spr_core.h: fp64, every operation rounded separately), so every counter ends at the
+// reference's count; a query landmark with several matching reference landmarks is counted once, by
+// the match with the lowest reference index (the reference's "first match, then break",
+// PR.cpp:341-354).
+//
+//   block      : a rectangle of one ring's lattice (nx x ny samples) whose counters one CTA holds
+//   micro-tile : 2 x 2 neighbouring samples of a block packed as four u8 counters in one 32-bit
+//                word; four arrays of micro-tiles, shifted by (0|1, 0|1) samples, so that the 2 x 2
+//                neighbourhood a pair can hit always lies in ONE word of one array: one shared-memory
+//                atomic per pair.  The u8 counters are folded into u16 totals after every round of
+//                SPJ_THREADS query landmarks (a landmark adds at most 1 to a counter).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "spr_join_types.h"
+#include "spr_types.h"
+
+cudaError_t spr_launch_join_rotate(const SprJoinView &V, double *qrot, SprJoinBox *gbox, cudaStream_t st);
+cudaError_t spr_launch_join_score(const SprJoinView &V, const SprJoinLaunch &K, int sm_count, cudaStream_t st);

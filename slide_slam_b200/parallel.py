@@ -57,13 +57,17 @@ def allgather_winner(local_hyp_index: int, local_inliers: int, device=None, grou
 
 
 def sharded_search(pr, rank: int, world: int, device=None, group=None):
-    """One shard of a prepared search, in two phases: the bound phase of every shard (with its
+    """One shard of a prepared search.  Pair-join scorer (default engine): one pass.  Lattice kernels: two phases: the bound phase of every shard (with its
     exactly scored seed hypotheses), an all-reduce(max) of the seeds' inlier counts -- the one
     exchange branch-and-bound needs: the incumbent -- and the verification of the shard's
     hypotheses whose bound reaches that incumbent.  Shards that cannot hold the winner verify
     (almost) nothing.  A shard without anything >= the incumbent reports best_hyp_index = -1."""
     if world <= 1:
         return pr.search()[0]
+    if getattr(pr, "engine", "lattice") == "join":
+        # the pair-join scorer counts every hypothesis of the shard exactly in one pass (lattice blocks dealt
+        # round-robin): no bounds, no incumbent, only the final all-gather of the top-1 records
+        return pr.search(shard_index=rank, shard_count=world)[0]
     seed, _ = pr.search(shard_index=rank, shard_count=world, bounds_only=True)
     inc = torch.tensor([max(int(seed.best_num_inliers), 0)], dtype=torch.int64, device=device)
     dist.all_reduce(inc, op=dist.ReduceOp.MAX, group=group)

@@ -32,7 +32,9 @@ _ROSPARAMS = {
     "match_x_half_range_intra": ("match_x_half_range_intra", float),
     "match_y_half_range_intra": ("match_y_half_range_intra", float),
     "match_yaw_half_range_intra": ("match_yaw_half_range_intra", "deg"),
-    # not a rosparam of the reference: 1 = verify every hypothesis exactly instead of bound-and-verify
+    # not a rosparam of the reference: which kernels search the lattice.  0 (default) = the pair-join scorer (exact
+    # count of every hypothesis); 1 = the lattice kernels, every hypothesis verified; 2 = the lattice kernels,
+    # bound-and-verify.  Same winner, count and correspondences in every case.
     "exhaustive_search": ("exhaustive_search", int),
 }
 
@@ -73,7 +75,12 @@ class PlaceRecognition:
     """Drop-in for the reference class on the SlideMatch path.  `params` uses the rosparam names
     of place_recognition.cpp:24-75 (angles in degrees, like the yaml files)."""
 
-    def __init__(self, params: dict | None = None, device: int = -1, slidegraph: dict | None = None):
+    ENGINES = {"join": 0, "lattice_exhaustive": 1, "lattice": 2}
+
+    def __init__(self, params: dict | None = None, device: int = -1, slidegraph: dict | None = None, engine: str | None = None):
+        """engine: "join" (default: the pair-join scorer), "lattice" (bound-and-verify lattice kernels) or
+        "lattice_exhaustive"; sets the exhaustive_search parameter.  The environment variable
+        SLIDE_PR_ENGINE=lattice makes the lattice kernels the default of every handle (A/B runs)."""
         self._lib = capi.lib()
         self._p = capi.default_params()
         self._p.device = device
@@ -93,6 +100,11 @@ class PlaceRecognition:
                 raise KeyError(f"unknown place_recognition rosparam {k!r}")
             field, conv = _ROSPARAMS[k]
             setattr(self._p, field, self._lib.slide_pr_deg2rad(float(v)) if conv == "deg" else conv(v))
+        if engine is not None:
+            self._p.exhaustive_search = self.ENGINES[engine]
+        import os
+        lattice = self._p.exhaustive_search != 0 or os.environ.get("SLIDE_PR_ENGINE") == "lattice" or os.environ.get("SLIDE_PR_EXHAUSTIVE", "0") not in ("", "0")
+        self.engine = "lattice" if lattice else "join"   # what an unqualified search of this handle runs
         h = C.c_void_p()
         rc = self._lib.slide_pr_create(C.byref(self._p), C.byref(h))
         if rc != capi.OK:
@@ -174,14 +186,18 @@ class PlaceRecognition:
     def search(self, trans_begin: int = 0, trans_end: int = -1, shard_index: int = 0, shard_count: int = 1,
                want_counts: bool = False, stream: int | None = None, collect_stats: bool = False,
                exhaustive: bool = False, bounds_only: bool = False, incumbent_inliers: int = 0,
-               reuse_bounds: bool = False):
-        """exhaustive=False (default): bound-and-verify -- same winner, count and correspondences as
-        verifying every hypothesis exactly (exhaustive=True; implied by want_counts / collect_stats)."""
+               reuse_bounds: bool = False, engine: str | None = None):
+        """Default: the handle's engine (the pair-join scorer unless it was created otherwise).
+        exhaustive=True: the lattice kernels with every hypothesis verified; bounds_only=True: their bound phase
+        only (counts = upper bounds); engine="lattice": their bound-and-verify search; engine="join": the pair-join
+        scorer.  Same winner, count and correspondences in every mode."""
         o = capi.SearchOpts()
         o.trans_begin, o.trans_end, o.shard_index, o.shard_count = trans_begin, trans_end, shard_index, shard_count
         o.stream = stream
         o.collect_stats = int(collect_stats)
         o.exhaustive = 2 if bounds_only else int(exhaustive)  # 2: bound phase only (counts = upper bounds)
+        if engine is not None and not bounds_only and not exhaustive:
+            o.exhaustive = {"lattice": 3, "join": 4}[engine]
         o.incumbent_inliers = int(incumbent_inliers)
         o.reuse_bounds = int(reuse_bounds)
         counts = None

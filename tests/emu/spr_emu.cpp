@@ -13,6 +13,7 @@
 
 #include "../../slide_slam_b200/csrc/spr_core.h"
 #include "../../slide_slam_b200/csrc/spr_host.h"
+#include "../../slide_slam_b200/csrc/spr_join_core.h"
 
 extern "C" int spr_emu_match_maps(const slide_pr_params *p, const double *ref7, int n_ref,
                                   const double *qry7, int n_qry, double half_x, double half_y,
@@ -106,6 +107,109 @@ extern "C" int spr_emu_match_maps(const slide_pr_params *p, const double *ref7, 
   }
   if (best) { *best_count = spr_key_count(best); *best_index = spr_key_index(best); }
   *hyps_scored = scored; *filter_hits = hits;
+  return SLIDE_PR_OK;
+}
+
+// The pair-join scorer (spr_join.cu) run one thread at a time over the host-built structures: same blocks,
+// same visibility test, same rounds of SPJ_THREADS query landmarks between folds, same scan.
+extern "C" int spr_emu_join_match_maps(const slide_pr_params *p, const double *ref7, int n_ref,
+                                       const double *qry7, int n_qry, double half_x, double half_y,
+                                       long long trans_begin, long long trans_end, int *counts_out,
+                                       long long counts_cap, int *best_count, long long *best_index,
+                                       long long *hyps_scored, long long *filter_hits, char *errbuf, int errcap) {
+  std::string err;
+  spr::Lattice L;
+  const double yaw_half = p->inter_loop_closure ? p->match_yaw_half_range : p->match_yaw_half_range_intra;
+  int rc = spr::build_lattice(*p, half_x, half_y, yaw_half, 0, -1, false, L, err, true);
+  auto fail = [&](int code) { if (errbuf && errcap > 0) { strncpy(errbuf, err.c_str(), errcap - 1); errbuf[errcap - 1] = 0; } return code; };
+  if (rc != SLIDE_PR_OK) return fail(rc);
+  *best_count = -10000; *best_index = -1; *hyps_scored = 0; *filter_hits = 0;
+  if (L.status == SLIDE_PR_SANITY_RETURN) return SLIDE_PR_SANITY_RETURN;
+  spr::JoinRef J;
+  if ((rc = spr::build_join_ref(*p, ref7, n_ref, J, err)) != SLIDE_PR_OK) return fail(rc);
+  spr::uvec<SprJoinBlock> blocks;
+  double drift = 0;
+  if ((rc = spr::build_join_blocks(L, p->match_xy_step_size, blocks, &drift, err)) != SLIDE_PR_OK) return fail(rc);
+  spr::QuerySet Q;
+  if ((rc = spr::build_query_set(J.labels, qry7, n_qry, Q, err)) != SLIDE_PR_OK) return fail(rc);
+  const int n_yaw = (int)L.yaw.size(), nqp = Q.nqp, n_groups = nqp / SPR_QGROUP;
+  std::vector<int32_t> glabel((size_t)std::max(n_groups, 1), 0);
+  for (int g = 0; g < n_groups; g++) glabel[g] = Q.qlabel[(size_t)g * SPR_QGROUP];
+  std::vector<double> qrot(2 * (size_t)std::max(1, n_yaw * nqp));
+  std::vector<SprJoinBox> gbox((size_t)std::max(1, n_yaw * n_groups));
+  for (int a = 0; a < n_yaw; a++)
+    for (int g = 0; g < n_groups; g++) {   // spr_join_rotate_kernel
+      SprJoinBox box = {INFINITY, -INFINITY, INFINITY, -INFINITY};
+      for (int k = 0; k < SPR_QGROUP; k++) {
+        const int js = g * SPR_QGROUP + k;
+        double rx = NAN, ry = NAN;
+        if (Q.qlabel[js] >= 0) {
+          spr_rotate(L.cs[2 * a], L.cs[2 * a + 1], Q.qxy[2 * (size_t)js], Q.qxy[2 * (size_t)js + 1], &rx, &ry);
+          box.x0 = std::min(box.x0, std::nextafterf((float)rx, -INFINITY)); box.x1 = std::max(box.x1, std::nextafterf((float)rx, INFINITY));
+          box.y0 = std::min(box.y0, std::nextafterf((float)ry, -INFINITY)); box.y1 = std::max(box.y1, std::nextafterf((float)ry, INFINITY));
+        }
+        qrot[2 * ((size_t)a * nqp + js)] = rx; qrot[2 * ((size_t)a * nqp + js) + 1] = ry;
+      }
+      gbox[(size_t)a * n_groups + g] = box;
+    }
+  SprJoinView V{};
+  V.lat = L.lat.data(); V.qrot = qrot.data(); V.gbox = gbox.data(); V.qdims = Q.qdims.data(); V.glabel = glabel.data();
+  V.qxy = Q.qxy.data(); V.qlabel = Q.qlabel.data(); V.cs = L.cs.data();
+  V.nqp = nqp; V.n_groups = n_groups; V.n_yaw = n_yaw; V.n_labels = (int)J.labels.size();
+  for (int d = 0; d < 2; d++) { V.rec[d] = J.rec[d].data(); V.cell_start[d] = J.cell_start[d].data(); }
+  V.nbr = J.nbr.data(); V.labelbox = J.labelbox.data();
+  V.gx0 = J.gx0; V.gy0 = J.gy0; V.inv_w = J.inv_w; V.ncx = J.ncx; V.ncy = J.ncy;
+  V.Tstar = J.Tstar; V.Sstar = J.Sstar; V.thr_dim = p->match_threshold_dimension; V.ignore_dim = p->ignore_dimension;
+  V.reach = J.reach; V.ireach = J.reach + 2.0 * drift + 1e-9; V.inv_step = 1.0 / p->match_xy_step_size;
+  V.blocks = blocks.data(); V.n_blocks = (uint32_t)blocks.size();
+  const unsigned long long ob = trans_begin < 0 ? 0 : (unsigned long long)trans_begin;
+  const unsigned long long oe = trans_end < 0 ? L.n_translations : std::min<unsigned long long>((unsigned long long)trans_end, L.n_translations);
+  unsigned long long best = 0;
+  long long scored = 0;
+  std::vector<uint32_t> tile(4 * SPJ_MAX_WORDS);
+  std::vector<uint16_t> tot(SPJ_MAX_SLOTS);
+  for (int a = 0; a < n_yaw; a++)
+    for (const SprJoinBlock &blk : blocks) {
+      const SpjBlock B = spj_block(V, blk);
+      const int n_slots = B.nx * B.ny, n_words = ((B.nx >> 1) + 1) * B.nwy;
+      if (n_slots > SPJ_MAX_SLOTS || ((B.nx >> 1) + 2) * B.nwy + 1 > SPJ_MAX_WORDS) { err = "block exceeds the kernel's limits"; return fail(SLIDE_PR_ERR_INTERNAL); }
+      std::fill(tile.begin(), tile.end(), 0xdeadbeefu);   // only the words the kernel zeroes may be relied on
+      for (int w = 0; w < n_words; w++) tile[w] = tile[SPJ_MAX_WORDS + w] = tile[2 * SPJ_MAX_WORDS + w] = tile[3 * SPJ_MAX_WORDS + w] = 0u;
+      std::fill(tot.begin(), tot.begin() + n_slots, (uint16_t)0);
+      int in_round = 0;
+      auto fold = [&]() {
+        for (int w = 0; w < n_words; w++) spj_fold(tile.data(), w, B, tot.data());
+        for (int w = 0; w < n_words; w++) tile[w] = tile[SPJ_MAX_WORDS + w] = tile[2 * SPJ_MAX_WORDS + w] = tile[3 * SPJ_MAX_WORDS + w] = 0u;
+        in_round = 0;
+      };
+      for (int g = 0; g < n_groups; g++) {
+        if (!spj_visible(V, B, gbox[(size_t)a * n_groups + g], V.labelbox + 4 * (size_t)glabel[g])) continue;
+        for (int k = 0; k < SPR_QGROUP; k++) {
+          const int js = g * SPR_QGROUP + k;
+          const double rx = qrot[2 * ((size_t)a * nqp + js)], ry = qrot[2 * ((size_t)a * nqp + js) + 1];
+          if (rx == rx) spj_vote(V, B, glabel[g], rx, ry, Q.qdims.data() + 3 * (size_t)js, tile.data());
+        }
+        in_round += SPR_QGROUP;
+        if (in_round >= SPJ_THREADS) fold();
+      }
+      fold();
+      int s_lo, s_hi;
+      spj_slice(blk, ob, oe, &s_lo, &s_hi);
+      for (int s = s_lo; s < s_hi; s++) {
+        const int i = s / B.ny, j = s - i * B.ny;
+        const unsigned long long ord = (unsigned long long)blk.ord0 + (unsigned long long)i * blk.row_stride + (unsigned long long)j;
+        if (ord < ob || ord >= oe) { err = "slot outside the slice"; return fail(SLIDE_PR_ERR_INTERNAL); }
+        const unsigned long long key = spr_make_key(tot[s], ord * (unsigned long long)n_yaw + (unsigned long long)a);
+        if (key > best) best = key;
+        scored++;
+        if (counts_out) {
+          const long long slot = (long long)(ord - ob) * n_yaw + a;
+          if (slot >= 0 && slot < counts_cap) counts_out[slot] = (int)tot[s];
+        }
+      }
+    }
+  if (best) { *best_count = spr_key_count(best); *best_index = spr_key_index(best); }
+  *hyps_scored = scored;
   return SLIDE_PR_OK;
 }
 

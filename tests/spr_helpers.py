@@ -74,7 +74,7 @@ def emu_lib():
     if _emu is None:
         so = os.path.join(HERE, "emu", "libspr_emu.so")
         srcs = [os.path.join(HERE, "emu", "spr_emu.cpp"), os.path.join(ROOT, "slide_slam_b200", "csrc", "spr_host.cpp")]
-        deps = srcs + [os.path.join(ROOT, "slide_slam_b200", "csrc", f) for f in ("spr_core.h", "spr_types.h", "spr_host.h")]
+        deps = srcs + [os.path.join(ROOT, "slide_slam_b200", "csrc", f) for f in ("spr_core.h", "spr_types.h", "spr_host.h", "spr_join_core.h", "spr_join_types.h")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
             gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
             subprocess.run([gxx, "-O2", "-mpopcnt", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", so] + srcs, check=True)
@@ -82,6 +82,7 @@ def emu_lib():
         L.spr_emu_match_maps.argtypes = [C.POINTER(capi.Params), _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double,
                                          C.c_longlong, C.c_longlong, _ip, C.c_longlong, _ip, C.POINTER(C.c_longlong),
                                          C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_char_p, C.c_int]
+        L.spr_emu_join_match_maps.argtypes = L.spr_emu_match_maps.argtypes
         L.spr_emu_lattice.restype = C.c_longlong
         L.spr_emu_lattice.argtypes = [C.POINTER(capi.Params), C.c_double, C.c_double, _dp, _dp, C.c_longlong, _ip, _dp,
                                       C.c_int, _ip]
@@ -89,13 +90,15 @@ def emu_lib():
     return _emu
 
 
-def emu_match_maps(p: capi.Params, ref7, qry7, half_x, half_y, trans_begin=0, trans_end=-1, n_counts=0):
+def emu_match_maps(p: capi.Params, ref7, qry7, half_x, half_y, trans_begin=0, trans_end=-1, n_counts=0, engine="lattice"):
+    """engine: "lattice" = the chunked bitmap kernels' per-thread code, "join" = the pair-join scorer's."""
     ref7 = np.ascontiguousarray(ref7, np.float64).reshape(-1, 7)
     qry7 = np.ascontiguousarray(qry7, np.float64).reshape(-1, 7)
     counts = np.full(max(n_counts, 1), -1, np.int32)
     bc, bi, hs, fh = C.c_int(), C.c_longlong(), C.c_longlong(), C.c_longlong()
     eb = C.create_string_buffer(256)
-    rc = emu_lib().spr_emu_match_maps(C.byref(p), ref7.ctypes.data_as(_dp), len(ref7), qry7.ctypes.data_as(_dp), len(qry7),
+    fn = emu_lib().spr_emu_join_match_maps if engine == "join" else emu_lib().spr_emu_match_maps
+    rc = fn(C.byref(p), ref7.ctypes.data_as(_dp), len(ref7), qry7.ctypes.data_as(_dp), len(qry7),
                                       half_x, half_y, trans_begin, trans_end,
                                       counts.ctypes.data_as(_ip) if n_counts else None, n_counts, C.byref(bc), C.byref(bi),
                                       C.byref(hs), C.byref(fh), eb, 256)

@@ -16,6 +16,8 @@ exactly) must select the same winner as the default search, and the planted SE(2
 synthetic scene must be recovered where the score has a real peak (configs 4 and 5; config 3's
 maximum is a chance peak of the dense maps, see the test).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -24,6 +26,19 @@ from slide_slam_b200 import synth
 from slide_slam_b200.place_recognition import PlaceRecognition
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _lattice_engine():
+    """This module pins the lattice kernels (bound-and-verify, exhaustive verification, bounds): handles are
+    created with SLIDE_PR_ENGINE=lattice.  The default engine (pair-join scorer) is covered by tests/test_gpu_join.py."""
+    old = os.environ.get("SLIDE_PR_ENGINE")
+    os.environ["SLIDE_PR_ENGINE"] = "lattice"
+    yield
+    if old is None:
+        os.environ.pop("SLIDE_PR_ENGINE", None)
+    else:
+        os.environ["SLIDE_PR_ENGINE"] = old
 
 KW = dict(match_xy_step_size=0.5, yaw_step_deg=5.0, match_threshold=0.5, match_threshold_dimension=1.0,
           ignore_dimension=0, min_num_inliers=15)

@@ -17,6 +17,19 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # BASELINE.json north_star: transform parameters within 1e-5 relative
 
 
+@pytest.fixture(autouse=True, scope="module")
+def _lattice_engine():
+    """This module pins the lattice kernels (bound-and-verify, exhaustive verification, bounds): handles are
+    created with SLIDE_PR_ENGINE=lattice.  The default engine (pair-join scorer) is covered by tests/test_gpu_join.py."""
+    old = os.environ.get("SLIDE_PR_ENGINE")
+    os.environ["SLIDE_PR_ENGINE"] = "lattice"
+    yield
+    if old is None:
+        os.environ.pop("SLIDE_PR_ENGINE", None)
+    else:
+        os.environ["SLIDE_PR_ENGINE"] = old
+
+
 @pytest.fixture(scope="module")
 def gold():
     return H.golden_maps(), H.golden_cases(), H.golden_counts()

@@ -20,13 +20,14 @@ def _check_counts(op, ref, qry, hx, hy):
     n, status, tx, ty, yaw = H.emu_lattice(p, hx, hy, nt)
     assert status == 0 and n == nt
     assert np.array_equal(tx, lat[0]) and np.array_equal(ty, lat[1]) and np.array_equal(yaw, lat[3])  # bit-exact
-    e = H.emu_match_maps(p, ref, qry, hx, hy, n_counts=nt * ny)
-    assert e["rc"] == 0, e["err"]
     o = O.match_maps(op, ref, qry, hx, hy, want_counts=True)
-    assert e["hypotheses_scored"] == o["hypotheses_scored"] == nt * ny
-    bad = np.nonzero(e["counts"] != o["counts"])[0]
-    assert bad.size == 0, f"first mismatching hypotheses {bad[:5]}"
-    assert e["best_num_inliers"] == o["best_num_inliers"] and e["best_hyp_index"] == o["best_hyp_index"]
+    for engine in ("lattice", "join"):   # the chunked bitmap kernels' code and the pair-join scorer's
+        e = H.emu_match_maps(p, ref, qry, hx, hy, n_counts=nt * ny, engine=engine)
+        assert e["rc"] == 0, e["err"]
+        assert e["hypotheses_scored"] == o["hypotheses_scored"] == nt * ny
+        bad = np.nonzero(e["counts"] != o["counts"])[0]
+        assert bad.size == 0, f"{engine}: first mismatching hypotheses {bad[:5]}: {e['counts'][bad[:5]]} != {o['counts'][bad[:5]]}"
+        assert e["best_num_inliers"] == o["best_num_inliers"] and e["best_hyp_index"] == o["best_hyp_index"], engine
     return e
 
 
@@ -49,10 +50,11 @@ def test_golden_slices_of_large_cases():
         ny = len(O.enumerate_lattice(op, 6.0, 6.0)[3])  # yaw candidates do not depend on the range
         # translation-aligned sub-slice of the golden hypothesis slice
         tb, te = -(-int(lo) // ny), int(hi) // ny
-        e = H.emu_match_maps(H.to_capi_params(op), ref, qry, c["half_x"], c["half_y"], tb, te, n_counts=(te - tb) * ny)
-        assert e["rc"] == 0, e["err"]
         want = counts[name][tb * ny - int(lo): te * ny - int(lo)]
-        assert np.array_equal(e["counts"], want)
+        for engine in ("lattice", "join"):
+            e = H.emu_match_maps(H.to_capi_params(op), ref, qry, c["half_x"], c["half_y"], tb, te, n_counts=(te - tb) * ny, engine=engine)
+            assert e["rc"] == 0, e["err"]
+            assert np.array_equal(e["counts"], want), engine
 
 
 @pytest.mark.parametrize("seed", range(12))
@@ -93,10 +95,16 @@ def test_edge_cases():
     r4 = np.tile(np.array([[2, 1.0, 1.0, 0, 0.5, 0, 0]], float), (6, 1))
     q4 = np.tile(np.array([[2, 0.0, 0.0, 0, 0.5, 0, 0]], float), (5, 1))
     assert _check_counts(op, r4, q4, 6.0, 6.0)["best_num_inliers"] == 5
+    # more identical query landmarks than one round of the pair-join kernel holds: its u8 counters must not wrap
+    q5 = np.tile(np.array([[2, 0.0, 0.0, 0, 0.5, 0, 0]], float), (700, 1))
+    assert _check_counts(O.make_params(match_xy_step_size=0.5, yaw_step_deg=90.0), r4, q5, 3.0, 3.0)["best_num_inliers"] == 700
+    # threshold far above the step: 15 x 15 lattice samples per pair (general path of the pair-join kernel)
+    _check_counts(O.make_params(match_xy_step_size=0.1, yaw_step_deg=60.0, match_threshold=0.75), ref, qry, 4.0, 4.0)
     # sanity-check early return and zero rings
     assert _check_counts(op, ref, qry, 0.3, 0.3) is None
-    e = H.emu_match_maps(H.to_capi_params(op), ref, qry, 0.0, 0.0)
-    assert e["rc"] == 0 and e["hypotheses_scored"] == 0 and e["best_num_inliers"] == -10000
+    for engine in ("lattice", "join"):
+        e = H.emu_match_maps(H.to_capi_params(op), ref, qry, 0.0, 0.0, engine=engine)
+        assert e["rc"] == 0 and e["hypotheses_scored"] == 0 and e["best_num_inliers"] == -10000
     # rectangular half ranges (disable_yaw_search keeps x and y ranges apart, PR.cpp:777-782)
     op2 = O.make_params(match_xy_step_size=0.5, disable_yaw_search=1)
     _check_counts(op2, ref, qry, 12.0, 5.5)

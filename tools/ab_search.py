@@ -1,5 +1,5 @@
 """A/B timing of the lattice search across library builds (SLIDE_PR_LIB=<.so> selects one): binds only
-the entry points every build has.  usage: ab_search.py [config] [reps]"""
+the entry points every build has.  usage: ab_search.py [config] [reps] [modes: 4 pair-join, 3 bound-and-verify, 1 lattice exhaustive]"""
 import ctypes as C
 import os
 import sys
@@ -35,7 +35,9 @@ assert L.slide_pr_create(C.byref(p), C.byref(h)) == 0
 assert L.slide_pr_prepare(h, sref.ctypes.data_as(_dp), len(sref), sqry.ctypes.data_as(_dp), len(sqry), r["half_x"], r["half_y"]) == 0
 import torch  # L2 flush between searches, like bench.py
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-for mode in (0, 1):
+names = {4: "pair-join", 3: "bound-and-verify", 1: "lattice exhaustive"}
+modes = [int(m) for m in sys.argv[3].split(",")] if len(sys.argv) > 3 else [4, 3, 1]
+for mode in modes:
     ms = []
     for i in range(reps + 3):
         flush.fill_(1); torch.cuda.synchronize()
@@ -45,5 +47,5 @@ for mode in (0, 1):
         if i >= 3:
             ms.append(res.kernel_ms)
     if ms:
-        print(f"{os.path.basename(path)} cfg{cfg} {'exhaustive' if mode else 'default'}: kernel_ms min {min(ms):.3f} median {np.median(ms):.3f} "
+        print(f"{os.path.basename(path)} cfg{cfg} {names.get(mode, mode)}: kernel_ms min {min(ms):.3f} median {np.median(ms):.3f} "
               f"best={res.best_num_inliers} idx={res.best_hyp_index} hyp={res.hypotheses_scored} launches={res.gpu_launches}", flush=True)
