@@ -804,10 +804,10 @@ int build_join_blocks(const Lattice &L, double step, uvec<SprJoinBlock> &blocks,
     const int w = ix1 - ix0, h = iy1 - iy0;
     if (w <= 0 || h <= 0) return;
     // tiles of bw x bh samples: the short side in pieces of at most 32, the long side as far as the
-    // counters of a block reach (SPJ_MAX_SLOTS totals; micro-tile arrays with one spare row and word)
+    // counters of a block reach
     int bw, bh;
-    auto ok = [](int nx, int ny) {   // the kernel's limits: totals, and the micro-tile arrays with a spare row and word
-      return nx * ny <= SPJ_MAX_SLOTS && ((nx >> 1) + 2) * ((ny >> 1) + 1) + 1 <= SPJ_MAX_WORDS;
+    auto ok = [](int nx, int ny) {   // the kernel's limits: slot index of the arg-max, the two counter arrays
+      return nx * ny <= SPJ_MAX_SLOTS && 2 * nx * ((ny >> 1) + 1) <= SPJ_TILE_WORDS;
     };
     if (w <= h) {
       const int pieces = (w + 31) / 32;

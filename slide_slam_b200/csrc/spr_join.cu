@@ -49,20 +49,100 @@ cudaError_t spr_launch_join_rotate(const SprJoinView &V, double *qrot, SprJoinBo
 // ---------------------------------------------------------------------------------------------
 // the scorer
 // ---------------------------------------------------------------------------------------------
+// A query landmark as the lanes of its warp see it while its candidate pairs are processed.
+struct SpjQuery { double rx, ry, d1, d2, d3; int32_t label, pad; };
+
+// 32 query landmarks (a "quad" of four visible groups, one landmark per lane) against block B.  The
+// candidate reference landmarks of all 32 are gathered into one work list, which the lanes then process
+// side by side: filter (can the pair match under a translation of the block at all?), compaction, exact
+// tests and counter updates -- the lanes stay busy although the landmarks have different numbers of candidates.
+__device__ __forceinline__ void spj_quad(const SprJoinView &V, const SpjBlock &B, const double2 *__restrict__ qr, int g, int lane,
+                                         bool active, SpjQuery *sq, uint32_t *list, uint32_t *tile) {
+  int b0 = 0, b1 = -1, a0 = 0, a1 = -1;
+  const uint32_t *cstart = V.cell_start[B.dir];
+  if (active) {
+    const int js = g * SPR_QGROUP + (lane & 7);
+    const double2 q = __ldg(qr + js);
+    if (q.x == q.x) {   // not a padding entry
+      const double *qd = V.qdims + 3 * (size_t)js;
+      const int l = __ldg(V.glabel + g);
+      sq[lane].rx = q.x; sq[lane].ry = q.y;
+      sq[lane].d1 = __ldg(qd); sq[lane].d2 = __ldg(qd + 1); sq[lane].d3 = __ldg(qd + 2);
+      sq[lane].label = l;
+      spj_cells(V, B, q.x, q.y, &b0, &b1, &a0, &a1);
+      cstart += (size_t)l * (size_t)(V.ncx * V.ncy);
+    }
+  }
+  const int pitch = B.dir ? V.ncx : V.ncy;
+  const SprJoinRef *rec = V.rec[B.dir];
+  int band = b0;                 // next band to open
+  uint32_t r = 0u, r_end = 0u;   // records of the open band still to be listed
+  for (;;) {
+    // how many records this lane lists in this step: the rest of its open band and further bands, up to its share
+    uint32_t n = min(r_end - r, (uint32_t)SPJ_SHARE);
+    for (int bb = band; n < (uint32_t)SPJ_SHARE && bb <= b1; bb++)
+      n = min(n + (__ldg(cstart + bb * pitch + a1 + 1) - __ldg(cstart + bb * pitch + a0)), (uint32_t)SPJ_SHARE);
+    if (!__any_sync(SPJ_FULL, n != 0u)) break;
+    uint32_t incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(SPJ_FULL, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(SPJ_FULL, incl, 31);
+    uint32_t *out = list + (incl - n);
+    for (uint32_t k = 0; k < n;) {
+      if (r >= r_end) {   // open the next band (n > k guarantees there is one with records left)
+        r = __ldg(cstart + band * pitch + a0);
+        r_end = __ldg(cstart + band * pitch + a1 + 1);
+        band++;
+        continue;
+      }
+      out[k++] = (r++ << 5) | (uint32_t)lane;
+    }
+    __syncwarp();
+    // filter, compacting in place (a window's survivors land at or before the window)
+    uint32_t n_pairs = 0u;
+    for (uint32_t w0 = 0; w0 < total; w0 += 32) {
+      const uint32_t w = w0 + (uint32_t)lane;
+      uint32_t e = 0u;
+      bool ok = false;
+      if (w < total) {
+        e = list[w];
+        const double2 p = __ldg(reinterpret_cast<const double2 *>(rec + (e >> 5)));
+        const SpjQuery &q = sq[e & 31u];
+        ok = spj_near(B, q.rx, q.ry, p.x, p.y);
+      }
+      const uint32_t m = __ballot_sync(SPJ_FULL, ok);
+      __syncwarp();
+      if (ok) list[n_pairs + (uint32_t)__popc(m & ((1u << lane) - 1u))] = e;
+      n_pairs += (uint32_t)__popc(m);
+    }
+    __syncwarp();
+    for (uint32_t w = (uint32_t)lane; w < n_pairs; w += 32) {
+      const uint32_t e = list[w];
+      const SpjQuery &q = sq[e & 31u];
+      spj_pair(V, B, q.rx, q.ry, &q.d1, rec + (e >> 5), tile);
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(SPJ_THREADS, 4)
 spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_constant__ SprJoinLaunch K,
                       const uint32_t n_blocks_local, const unsigned long long n_items) {
-  __shared__ uint32_t s_tile[4 * SPJ_MAX_WORDS];
-  __shared__ uint32_t s_tot[SPJ_MAX_SLOTS / 2];    // u16 totals, two per word
+  __shared__ uint32_t s_tile[SPJ_TILE_WORDS];
+  __shared__ SpjQuery s_q[SPJ_WARPS][32];
+  __shared__ uint32_t s_list[SPJ_WARPS][SPJ_LIST];
   __shared__ uint16_t s_vis[SPJ_SEG_GROUPS];
-  __shared__ uint32_t s_nvis;
+  __shared__ uint32_t s_nvis, s_next;
   __shared__ unsigned long long s_item;
   __shared__ uint32_t s_red[SPJ_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (;;) {
     if (tid == 0) s_item = atomicAdd(K.work_counter, 1ull);
-    __syncthreads();   // also: the previous item's scan has finished with s_tot / s_red
+    __syncthreads();   // also: the previous item's scan has finished with s_tile / s_red
     const unsigned long long item = s_item;
     if (item >= n_items) break;
     const int a = (int)(item / n_blocks_local);
@@ -70,18 +150,14 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
     const SprJoinBlock blk = V.blocks[b];
     const SpjBlock B = spj_block(V, blk);
     const int n_slots = B.nx * B.ny;
-    const int n_words = ((B.nx >> 1) + 1) * B.nwy;
-    for (int w = tid; w < n_words; w += SPJ_THREADS) {
-      s_tile[w] = 0u; s_tile[SPJ_MAX_WORDS + w] = 0u; s_tile[2 * SPJ_MAX_WORDS + w] = 0u; s_tile[3 * SPJ_MAX_WORDS + w] = 0u;
-    }
-    for (int w = tid; w < (n_slots + 1) / 2; w += SPJ_THREADS) s_tot[w] = 0u;
+    for (int w = tid; w < 2 * B.stride; w += SPJ_THREADS) s_tile[w] = 0u;
 
     const SprJoinBox *gb = V.gbox + (size_t)a * (size_t)V.n_groups;
     const double2 *qr = reinterpret_cast<const double2 *>(V.qrot) + (size_t)a * (size_t)V.nqp;
 
     for (int seg0 = 0; seg0 < V.n_groups; seg0 += SPJ_SEG_GROUPS) {
-      if (tid == 0) s_nvis = 0u;
-      __syncthreads();   // s_tile / s_tot zeroed (first segment); s_vis free
+      if (tid == 0) { s_nvis = 0u; s_next = 0u; }
+      __syncthreads();   // counters zeroed (first segment); the previous segment's warps are done with s_vis
       // groups of the segment that some translation of the block brings over their label's landmarks
 #pragma unroll
       for (int k = 0; k < SPJ_SEG_GROUPS / SPJ_THREADS; k++) {
@@ -90,7 +166,7 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
         if (g < V.n_groups) {
           const float4 bx = __ldg(reinterpret_cast<const float4 *>(gb + g));
           const SprJoinBox box = {bx.x, bx.y, bx.z, bx.w};
-          vis = spj_visible(V, B, box, V.labelbox + 4 * (size_t)__ldg(V.glabel + g));
+          vis = spj_visible(B, box, V.labelbox + 4 * (size_t)__ldg(V.glabel + g));
         }
         const uint32_t m = __ballot_sync(SPJ_FULL, vis);
         uint32_t base = 0u;
@@ -99,44 +175,31 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
         if (vis) s_vis[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (uint16_t)(k * SPJ_THREADS + tid);
       }
       __syncthreads();
-      const int nvis = (int)s_nvis;
-      // rounds of SPJ_THREADS query landmarks: every landmark adds at most 1 to a counter, so the u8
-      // counters of the micro-tiles cannot wrap before they are folded into the totals
-      for (int gbase = 0; gbase < nvis; gbase += SPJ_THREADS / SPR_QGROUP) {
-        const int gi = gbase + (tid >> 3);
-        bool voted = false;
-        if (gi < nvis) {
-          const int g = seg0 + (int)s_vis[gi];
-          const int js = g * SPR_QGROUP + (tid & 7);
-          const double2 q = __ldg(qr + js);
-          if (q.x == q.x) {   // not a padding entry
-            const double *qd = V.qdims + 3 * (size_t)js;
-            const double qdl[3] = {__ldg(qd), __ldg(qd + 1), __ldg(qd + 2)};
-            voted = spj_vote(V, B, __ldg(V.glabel + g), q.x, q.y, qdl, s_tile);
-          }
-        }
-        if (!__syncthreads_or(voted)) continue;
-        // fold: the four samples of micro-tile (m, n) of array 0 collect their bytes from all four arrays
-        for (int w = tid; w < n_words; w += SPJ_THREADS) spj_fold(s_tile, w, B, reinterpret_cast<uint16_t *>(s_tot));
-        __syncthreads();
-        for (int w = tid; w < n_words; w += SPJ_THREADS) {
-          s_tile[w] = 0u; s_tile[SPJ_MAX_WORDS + w] = 0u; s_tile[2 * SPJ_MAX_WORDS + w] = 0u; s_tile[3 * SPJ_MAX_WORDS + w] = 0u;
-        }
-        __syncthreads();
+      const uint32_t nvis = s_nvis, n_quads = (nvis + 3u) / 4u;
+      // the warps take quads of visible groups (32 query landmarks) until none is left
+      for (;;) {
+        uint32_t quad = 0u;
+        if (lane == 0) quad = atomicAdd(&s_next, 1u);
+        quad = __shfl_sync(SPJ_FULL, quad, 0);
+        if (quad >= n_quads) break;
+        const uint32_t gi = quad * 4u + ((uint32_t)lane >> 3);
+        const bool active = gi < nvis;
+        spj_quad(V, B, qr, active ? seg0 + (int)s_vis[gi] : 0, lane, active, s_q[warp], s_list[warp], s_tile);
       }
+      __syncthreads();   // every warp is done with the segment's list (and, after the last segment, with its counter updates)
     }
-    if (V.n_groups <= 0) __syncthreads();   // the zeroed totals
+    if (V.n_groups <= 0) __syncthreads();   // the zeroed counters
 
     // ---- scan: slots of the block inside the requested slice of ordinals; max count, smallest ordinal
     int s_lo, s_hi;
     spj_slice(blk, K.ord_begin, K.ord_end, &s_lo, &s_hi);
-    const uint16_t *tot = reinterpret_cast<const uint16_t *>(s_tot);
+    const float inv_ny = 1.0f / (float)B.ny;
     uint32_t best = 0u;   // (count + 1) << 12 | (4095 - slot): max count, then smallest slot = smallest ordinal
     for (int s = s_lo + tid; s < s_hi; s += SPJ_THREADS) {
-      const uint32_t c = tot[s];
+      const int i = __float2int_rd(((float)s + 0.5f) * inv_ny), j = s - i * B.ny;   // exact: s < 4096
+      const uint32_t c = spj_total(s_tile, B, i, j);
       best = max(best, ((c + 1u) << 12) | (uint32_t)(SPJ_MAX_SLOTS - 1 - s));
       if (K.counts_out) {
-        const int i = s / B.ny, j = s - i * B.ny;
         const unsigned long long ord = (unsigned long long)blk.ord0 + (unsigned long long)i * blk.row_stride + (unsigned long long)j;
         K.counts_out[(ord - K.ord_begin) * (unsigned long long)V.n_yaw + (unsigned long long)a] = (int32_t)c;
       }
@@ -155,6 +218,7 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
         atomicMax(K.best_key, spr_make_key(c, ord * (unsigned long long)V.n_yaw + (unsigned long long)a));
       }
     }
+    (void)n_slots;
   }
 }
 

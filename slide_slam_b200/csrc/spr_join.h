@@ -13,12 +13,12 @@
 // the match with the lowest reference index (the reference's "first match, then break",
 // PR.cpp:341-354).
 //
-//   block      : a rectangle of one ring's lattice (nx x ny samples) whose counters one CTA holds
-//   micro-tile : 2 x 2 neighbouring samples of a block packed as four u8 counters in one 32-bit
-//                word; four arrays of micro-tiles, shifted by (0|1, 0|1) samples, so that the 2 x 2
-//                neighbourhood a pair can hit always lies in ONE word of one array: one shared-memory
-//                atomic per pair.  The u8 counters are folded into u16 totals after every round of
-//                SPJ_THREADS query landmarks (a landmark adds at most 1 to a counter).
+//   block      : a rectangle of one ring's lattice (nx x ny samples) whose counters one CTA holds in
+//                shared memory: two arrays of u16 counters, two per 32-bit word; word n of a row of array ay
+//                holds samples 2n - ay and 2n - ay + 1, so that the two neighbouring samples a pair can hit
+//                in a row always share ONE word of one array: one shared-memory atomic per pair and row.
+//   quad       : 32 query landmarks (four query groups) handled by one warp: the candidate reference
+//                landmarks of all 32 go through one work list so that the lanes stay busy.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -111,7 +111,7 @@ extern "C" int spr_emu_match_maps(const slide_pr_params *p, const double *ref7, 
 }
 
 // The pair-join scorer (spr_join.cu) run one thread at a time over the host-built structures: same blocks,
-// same visibility test, same rounds of SPJ_THREADS query landmarks between folds, same scan.
+// same visibility test, same per-pair code and counters, same scan.
 extern "C" int spr_emu_join_match_maps(const slide_pr_params *p, const double *ref7, int n_ref,
                                        const double *qry7, int n_qry, double half_x, double half_y,
                                        long long trans_begin, long long trans_end, int *counts_out,
@@ -166,45 +166,35 @@ extern "C" int spr_emu_join_match_maps(const slide_pr_params *p, const double *r
   const unsigned long long oe = trans_end < 0 ? L.n_translations : std::min<unsigned long long>((unsigned long long)trans_end, L.n_translations);
   unsigned long long best = 0;
   long long scored = 0;
-  std::vector<uint32_t> tile(4 * SPJ_MAX_WORDS);
-  std::vector<uint16_t> tot(SPJ_MAX_SLOTS);
+  std::vector<uint32_t> tile(SPJ_TILE_WORDS);
   for (int a = 0; a < n_yaw; a++)
     for (const SprJoinBlock &blk : blocks) {
       const SpjBlock B = spj_block(V, blk);
-      const int n_slots = B.nx * B.ny, n_words = ((B.nx >> 1) + 1) * B.nwy;
-      if (n_slots > SPJ_MAX_SLOTS || ((B.nx >> 1) + 2) * B.nwy + 1 > SPJ_MAX_WORDS) { err = "block exceeds the kernel's limits"; return fail(SLIDE_PR_ERR_INTERNAL); }
+      const int n_slots = B.nx * B.ny;
+      if (n_slots > SPJ_MAX_SLOTS || 2 * B.stride > SPJ_TILE_WORDS) { err = "block exceeds the kernel's limits"; return fail(SLIDE_PR_ERR_INTERNAL); }
       std::fill(tile.begin(), tile.end(), 0xdeadbeefu);   // only the words the kernel zeroes may be relied on
-      for (int w = 0; w < n_words; w++) tile[w] = tile[SPJ_MAX_WORDS + w] = tile[2 * SPJ_MAX_WORDS + w] = tile[3 * SPJ_MAX_WORDS + w] = 0u;
-      std::fill(tot.begin(), tot.begin() + n_slots, (uint16_t)0);
-      int in_round = 0;
-      auto fold = [&]() {
-        for (int w = 0; w < n_words; w++) spj_fold(tile.data(), w, B, tot.data());
-        for (int w = 0; w < n_words; w++) tile[w] = tile[SPJ_MAX_WORDS + w] = tile[2 * SPJ_MAX_WORDS + w] = tile[3 * SPJ_MAX_WORDS + w] = 0u;
-        in_round = 0;
-      };
+      std::fill(tile.begin(), tile.begin() + 2 * B.stride, 0u);
       for (int g = 0; g < n_groups; g++) {
-        if (!spj_visible(V, B, gbox[(size_t)a * n_groups + g], V.labelbox + 4 * (size_t)glabel[g])) continue;
+        if (!spj_visible(B, gbox[(size_t)a * n_groups + g], V.labelbox + 4 * (size_t)glabel[g])) continue;
         for (int k = 0; k < SPR_QGROUP; k++) {
           const int js = g * SPR_QGROUP + k;
           const double rx = qrot[2 * ((size_t)a * nqp + js)], ry = qrot[2 * ((size_t)a * nqp + js) + 1];
           if (rx == rx) spj_vote(V, B, glabel[g], rx, ry, Q.qdims.data() + 3 * (size_t)js, tile.data());
         }
-        in_round += SPR_QGROUP;
-        if (in_round >= SPJ_THREADS) fold();
       }
-      fold();
       int s_lo, s_hi;
       spj_slice(blk, ob, oe, &s_lo, &s_hi);
       for (int s = s_lo; s < s_hi; s++) {
         const int i = s / B.ny, j = s - i * B.ny;
         const unsigned long long ord = (unsigned long long)blk.ord0 + (unsigned long long)i * blk.row_stride + (unsigned long long)j;
         if (ord < ob || ord >= oe) { err = "slot outside the slice"; return fail(SLIDE_PR_ERR_INTERNAL); }
-        const unsigned long long key = spr_make_key(tot[s], ord * (unsigned long long)n_yaw + (unsigned long long)a);
+        const uint32_t cnt = spj_total(tile.data(), B, i, j);
+        const unsigned long long key = spr_make_key(cnt, ord * (unsigned long long)n_yaw + (unsigned long long)a);
         if (key > best) best = key;
         scored++;
         if (counts_out) {
           const long long slot = (long long)(ord - ob) * n_yaw + a;
-          if (slot >= 0 && slot < counts_cap) counts_out[slot] = (int)tot[s];
+          if (slot >= 0 && slot < counts_cap) counts_out[slot] = (int)cnt;
         }
       }
     }
