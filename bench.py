@@ -12,16 +12,16 @@ configs[1] -- two synthetic maps of 2,000 landmarks, 5 classes, 10 % outliers, l
 map pair per step (BASELINE config 4's "one pair-set per GPU"): weak scaling, no data-path
 collective.
 
-value  : hypotheses SCORED / s -- `slide_pr_search` with exhaustive = 1: the exact inlier count of
-         every hypothesis -- with both maps and their index structures resident in HBM; CUDA events
-         on the launching stream around each step, L2 flushed between steps.
-e2e    : the same metric through the public findTransformation call (exhaustive_search = 1) with
-         HOST buffers: index build, H2D copies, kernels, D2H of the result, refinement -- wall clock.
-search : the library's DEFAULT search of the same pair (bound-and-verify: an upper bound for every
-         hypothesis, exact verification where the bound reaches the running best; same winner,
-         count and correspondences): map pairs / s, device-timed and end to end.  Not the metric.
+value  : hypotheses SCORED / s -- the library's default search (`slide_pr_search`, pair-join scorer: the exact
+         inlier count of EVERY hypothesis, arg-max on the device) with both maps and their index structures
+         resident in HBM; CUDA events on the launching stream around each step, L2 flushed between steps.
+e2e    : the same metric through the public findTransformation call with HOST buffers: index build, H2D
+         copies, kernels, D2H of the result, refinement -- wall clock.
+lattice_kernels : the same pair through the library's other engine (occupancy-bitmap lattice kernels): every
+         hypothesis verified exactly, and bound-and-verify (an upper bound for every hypothesis, exact
+         verification where the bound reaches the running best).  Same winner; not the metric.
 roofline: the dominant kernel against the instruction-issue peak MEASURED in the same run by a
-         micro-kernel (the path is issue / ALU-pipe bound on shared-memory resident bitmaps);
+         micro-kernel (the path is issue bound on shared-memory / L1 resident structures);
          the HBM figure of SURVEY.md section 8d is kept beside it.
 extras : generator (triangle-hypothesis set (T) on the same pair), config3_shard (one 20 000 x 20 000
          pair, hypothesis space sharded over the ranks), config4 (28 pairs of 5 000 landmarks dealt
@@ -231,8 +231,8 @@ def run_ours(args, rank, world, local_rank):
     # weak scaling: every rank searches the SAME synthetic pair (fixed work per GPU), so that the
     # per-N values are comparable; the ranks do not share any data
     (ref, qry, truth), wname = workload(args.config, 0)
-    pr = PlaceRecognition(ROS, device=local_rank)                                  # library defaults (bound-and-verify)
-    prx = PlaceRecognition(dict(ROS, exhaustive_search=1), device=local_rank)      # every hypothesis verified exactly
+    pr = PlaceRecognition(ROS, device=local_rank)                        # library defaults: the pair-join scorer
+    prl = PlaceRecognition(ROS, device=local_rank, engine="lattice")     # the lattice kernels (bound-and-verify / exhaustive)
     lib = capi.lib()
 
     ref_h = torch.from_numpy(ref).pin_memory().numpy()
@@ -242,6 +242,7 @@ def run_ours(args, rank, world, local_rank):
     sref[:, 1:3] -= np.array(info.centroid_ref[:])
     sqry[:, 1:3] -= np.array(info.centroid_qry[:])
     pr.prepare(sref, sqry, info.half_x, info.half_y)   # inputs + index structures now resident in HBM
+    prl.prepare(sref, sqry, info.half_x, info.half_y)
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -252,18 +253,19 @@ def run_ours(args, rank, world, local_rank):
     rec_dev = torch.zeros(2 * n_rec, dtype=torch.int64, device=dev)
     rec_all = torch.zeros(2 * n_rec * max(world, 1), dtype=torch.int64, device=dev)
 
-    def timed_steps(exhaustive):
+    def timed_steps(handle, exhaustive, steps):
         step_ms, kern_ms, hyps, launches, last = [], [], 0, 0, None
-        for i in range(args.steps):
+        for i in range(steps):
             flush.fill_(1)                      # L2 flush between timed iterations (not timed)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            res, _ = pr.search(stream=stream.cuda_stream, exhaustive=exhaustive)
+            res, _ = handle.search(stream=stream.cuda_stream, exhaustive=exhaustive)
             e1.record(stream)
             e1.synchronize()
             step_ms.append(e0.elapsed_time(e1)); kern_ms.append(res.kernel_ms)
             hyps += res.hypotheses_scored; launches += res.gpu_launches
-            rec_host[2 * i], rec_host[2 * i + 1] = int(res.best_hyp_index), int(res.best_num_inliers)
+            if handle is pr:
+                rec_host[2 * i], rec_host[2 * i + 1] = int(res.best_hyp_index), int(res.best_num_inliers)
             last = res
         return step_ms, kern_ms, hyps, launches, last
 
@@ -271,8 +273,9 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
-        pr.search(stream=stream.cuda_stream, exhaustive=True)
         pr.search(stream=stream.cuda_stream)
+        prl.search(stream=stream.cuda_stream, exhaustive=True)
+        prl.search(stream=stream.cuda_stream)
     if world > 1:        # warm-up of the exchange too (NCCL sets its channels up lazily)
         for _ in range(2):
             rec_dev.copy_(rec_host, non_blocking=True)
@@ -282,7 +285,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
 
     # ---- the metric: every hypothesis scored exactly
-    step_ms, kern_ms, hyps, launches, res_x = timed_steps(True)
+    step_ms, kern_ms, hyps, launches, res_x = timed_steps(pr, False, args.steps)
     if world > 1:        # timed: the one exchange of the weak-scaling job
         torch.cuda.synchronize()
         dist.barrier()                      # untimed, like the L2 flushes: the ranks' untimed host work differs
@@ -297,8 +300,10 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    # ---- the default search (bound-and-verify) of the same pair
-    b_step_ms, b_kern_ms, b_hyps, b_launches, res_b = timed_steps(False)
+    # ---- the lattice kernels on the same pair: bound-and-verify, and every hypothesis verified exactly
+    n_l = max(min(args.steps, 5), 1)
+    b_step_ms, b_kern_ms, b_hyps, b_launches, res_b = timed_steps(prl, False, n_l)
+    lx_step_ms, lx_kern_ms, lx_hyps, lx_launches, res_lx = timed_steps(prl, True, n_l)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -313,6 +318,7 @@ def run_ours(args, rank, world, local_rank):
 
     total_ms, hyps_all, kernel_total_ms, launches_all = reduce_over_ranks(float(sum(step_ms)), hyps, float(sum(kern_ms)), launches)
     b_total_ms, b_hyps_all, b_kernel_total_ms, b_launches_all = reduce_over_ranks(float(sum(b_step_ms)), b_hyps, float(sum(b_kern_ms)), b_launches)
+    lx_total_ms, lx_hyps_all, lx_kernel_total_ms, lx_launches_all = reduce_over_ranks(float(sum(lx_step_ms)), lx_hyps, float(sum(lx_kern_ms)), lx_launches)
 
     peaks = None
     if rank == 0:   # issue-rate micro-benchmark, same run, same clocks
@@ -350,8 +356,8 @@ def run_ours(args, rank, world, local_rank):
             dt, n_h = float(a_[0]), float(b_[1])
         return dt, n_h, reused, last
 
-    x_s, x_hyps, x_reused, x_info = e2e_leg(prx)
-    d_s, d_hyps, d_reused, d_info = e2e_leg(pr)
+    x_s, x_hyps, x_reused, x_info = e2e_leg(pr)
+    d_s, d_hyps, d_reused, d_info = e2e_leg(prl)
 
     extras = run_extras(args, rank, world, local_rank, dev) if not args.no_extras else {}
 
@@ -360,32 +366,32 @@ def run_ours(args, rank, world, local_rank):
         value = hyps_all / (total_ms * 1e-3)
         hbm_peak, hbm_src = measured_peaks()
         counts = load_ncu_counts()
-        k_ms = float(np.mean(kern_ms))                          # rank 0's exhaustive step: 10 launches of spr_score_lattice_kernel
+        k_ms = float(np.mean(kern_ms))                          # rank 0's step: rotate + spr_join_score_kernel
         k_hyps = float(hyps) / n_steps
-        winst = counts.get("exhaustive_c2_winst_per_step")
-        roof = {"bound": "issue", "kernel": "spr_score_lattice_kernel (one launch per label and bitmap direction; 99.9 % of the step)",
+        winst = counts.get("join_c2_winst_per_step")
+        roof = {"bound": "issue", "kernel": "spr_join_score_kernel (one launch per search; > 99 % of the step)",
                 "unit": "Gwinst/s", "achieved": None, "peak": None, "frac": None,
-                "traffic": counts.get("exhaustive_c2_dram_bytes_per_launch"),
+                "traffic": counts.get("join_c2_dram_bytes_per_launch"),
                 "traffic_source": counts.get("source", "no ncu capture committed"),
                 "peak_source": "issue-rate micro-kernel (LOP3 + IMAD chains interleaved) in this run, slide_pr_measure_issue_peaks",
                 "note": "achieved = warp instructions of the step's launches (ncu smsp__inst_executed.sum, committed) / their CUDA-event "
-                        "duration in this run; the kernel works on shared-memory resident bitmaps and rank tables, so instruction issue "
-                        "(ALU pipe first) is the binding roof, not HBM (SURVEY.md section 8d)"}
+                        "duration in this run; the kernel joins L1 / shared-memory resident landmark bins and counts in shared memory, so "
+                        "instruction issue is the binding roof, not HBM (SURVEY.md section 8d)"}
         if winst and peaks:
             ach = winst / (k_ms * 1e-3)
             roof.update({"achieved": ach / 1e9, "peak": peaks["issue_winst_per_s"] / 1e9, "frac": ach / peaks["issue_winst_per_s"],
                          "winst_per_hypothesis": winst / k_hyps,
-                         "alu_pipe": {"share_of_instructions": counts.get("exhaustive_c2_alu_share"),
+                         "alu_pipe": {"share_of_instructions": counts.get("join_c2_alu_share"),
                                       "peak_Gwinst_per_s": peaks["alu_pipe_winst_per_s"] / 1e9,
-                                      "frac": (ach * counts["exhaustive_c2_alu_share"] / peaks["alu_pipe_winst_per_s"])
-                                      if counts.get("exhaustive_c2_alu_share") else None}})
+                                      "frac": (ach * counts["join_c2_alu_share"] / peaks["alu_pipe_winst_per_s"])
+                                      if counts.get("join_c2_alu_share") else None}})
         hbm_ach = ALG_BYTES_PER_HYP * k_hyps / (k_ms * 1e-3) / 1e9
         roof["hbm"] = {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "peak_source": hbm_src,
                        "note": "algorithmic 24 B/hypothesis (SURVEY 8d) x hypotheses of a step / kernel time: the looser roof"}
         if peaks:
             roof["measured_peaks"] = {k: v / 1e9 for k, v in peaks.items()}
             roof["measured_peaks"]["unit"] = "Gwinst/s"
-        b_winst = counts.get("search_c2_winst_per_step")
+        b_winst, lx_winst = counts.get("search_c2_winst_per_step"), counts.get("exhaustive_c2_winst_per_step")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / n_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -394,22 +400,29 @@ def run_ours(args, rank, world, local_rank):
                             "all result records at the end of the timed region" if world > 1 else "single GPU"),
             "best_num_inliers": int(res_x.best_num_inliers), "closure_found": bool(found),
             "kernel_ms_per_step": kernel_total_ms / n_steps, "gpu_launches": launches_all,
-            "search": {"note": "library default (bound-and-verify): bitmap-filter upper bound of every hypothesis, exact fp64 verification of "
-                               "those whose bound reaches the running best; winner, inlier count and correspondences identical",
-                       "pairs_per_s": world * n_steps / (b_total_ms * 1e-3), "ms_per_pair": b_total_ms / n_steps,
-                       "search_hyp_per_s": b_hyps_all / (b_total_ms * 1e-3), "kernel_ms_per_pair": b_kernel_total_ms / n_steps,
-                       "gpu_launches": b_launches_all,
-                       "same_winner": bool(res_b.best_hyp_index == res_x.best_hyp_index and res_b.best_num_inliers == res_x.best_num_inliers),
-                       "issue_frac": (b_winst / (float(np.mean(b_kern_ms)) * 1e-3) / peaks["issue_winst_per_s"]) if (b_winst and peaks) else None,
-                       "e2e_pairs_per_s": world * n_steps / d_s, "e2e_ms_per_pair": d_s / n_steps * 1e3,
-                       "e2e_h2d_bytes_per_pair": int(d_info.match.h2d_bytes), "e2e_d2h_bytes_per_pair": int(d_info.match.d2h_bytes),
-                       "e2e_host_prepare_ms": float(d_info.match.prepare_ms), "e2e_kernel_ms": float(d_info.match.kernel_ms)},
+            "pairs_per_s": world * n_steps / (total_ms * 1e-3),
+            "search_mode": int(res_x.search_mode),
+            "lattice_kernels": {
+                "note": "the library's other engine on the same pair (engine='lattice' / exhaustive_search = 2 | 1): occupancy-bitmap lattice "
+                        "kernels; bound_and_verify = upper bound of every hypothesis + exact verification of those reaching the running best; "
+                        "exhaustive = every hypothesis verified; same winner, count and correspondences as the pair-join scorer",
+                "same_winner": bool(res_b.best_hyp_index == res_x.best_hyp_index and res_b.best_num_inliers == res_x.best_num_inliers and
+                                    res_lx.best_hyp_index == res_x.best_hyp_index and res_lx.best_num_inliers == res_x.best_num_inliers),
+                "bound_and_verify": {"pairs_per_s": world * n_l / (b_total_ms * 1e-3), "ms_per_pair": b_total_ms / n_l,
+                                     "kernel_ms_per_pair": b_kernel_total_ms / n_l, "gpu_launches_per_pair": b_launches_all / (world * n_l),
+                                     "issue_frac": (b_winst / (float(np.mean(b_kern_ms)) * 1e-3) / peaks["issue_winst_per_s"]) if (b_winst and peaks) else None,
+                                     "e2e_pairs_per_s": world * n_steps / d_s, "e2e_ms_per_pair": d_s / n_steps * 1e3,
+                                     "e2e_h2d_bytes_per_pair": int(d_info.match.h2d_bytes), "e2e_host_prepare_ms": float(d_info.match.prepare_ms)},
+                "exhaustive": {"hypotheses_per_s": lx_hyps_all / (lx_total_ms * 1e-3), "ms_per_pair": lx_total_ms / n_l,
+                               "kernel_ms_per_pair": lx_kernel_total_ms / n_l, "gpu_launches_per_pair": lx_launches_all / (world * n_l),
+                               "issue_frac": (lx_winst / (float(np.mean(lx_kern_ms)) * 1e-3) / peaks["issue_winst_per_s"]) if (lx_winst and peaks) else None}},
             "clocks": clocks,
             "e2e": {"value": x_hyps / x_s, "unit": UNIT, "h2d_bytes_per_step": int(x_info.match.h2d_bytes),
                     "d2h_bytes_per_step": int(x_info.match.d2h_bytes), "ms_per_step": x_s / n_steps * 1e3,
                     "host_prepare_ms": float(x_info.match.prepare_ms), "kernel_ms": float(x_info.match.kernel_ms),
                     "index_reused_between_steps": bool(x_reused), "search_mode": int(x_info.match.search_mode),
-                    "note": "two distinct map pairs alternate, so every step rebuilds all index structures; exhaustive_search = 1",
+                    "pairs_per_s": world * n_steps / x_s,
+                    "note": "two distinct map pairs alternate, so every step rebuilds all index structures (landmark bins, query groups, lattice blocks)",
                     "api": "PlaceRecognition.findTransformation -> slide_pr_find_transformation (host buffers)"},
             "roofline": roof,
         }
@@ -419,7 +432,7 @@ def run_ours(args, rank, world, local_rank):
             out["cpu_baseline"] = cpu_reference_rate(ref, qry, args.cpu_seconds, threads)
             out["cpu_baseline_1thread"] = cpu_reference_rate(ref, qry, min(args.cpu_seconds, 8.0), 1)
         print(json.dumps(out), flush=True)
-    pr.close(); prx.close()
+    pr.close(); prl.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -488,8 +501,8 @@ def run_extras(args, rank, world, local_rank, dev):
     (mx, sm) = ranks_max_sum([min(t_ms[1:]), wins[-1][2], float(wins[-1][3])])
     if rank == 0:
         out["config3_shard"] = {
-            "note": "one 20000 x 20000 pair, hypothesis space sharded over the ranks: bound phase, all-reduce(max) of the incumbent, "
-                    "verification, all-gather of the 16-byte top-1 records (strong scaling); wall clock, max over ranks, best of 2 after a warm-up",
+            "note": "one 20000 x 20000 pair, hypothesis space (lattice blocks) sharded round-robin over the ranks, every hypothesis counted "
+                    "exactly, all-gather of the 16-byte top-1 records (strong scaling); wall clock, max over ranks, best of 2 after a warm-up",
             "n_gpus": world, "ms_per_pair": mx[0], "hypotheses": int(sm[2]), "hypotheses_per_s": sm[2] / (mx[0] * 1e-3),
             "slowest_rank_kernel_ms": mx[1], "mean_rank_kernel_ms": sm[1] / world,
             "best_num_inliers": int(wins[-1][0]), "best_hyp_index": int(wins[-1][1])}

@@ -521,9 +521,68 @@ static int join_prepare(slide_pr_handle *h) {
   const bool same_ref = rs->join_valid && rs->join_p.match_xy_step_size == h->p.match_xy_step_size &&
                         rs->join_p.match_threshold == h->p.match_threshold &&
                         rs->join_p.match_threshold_dimension == h->p.match_threshold_dimension;
+  // ring geometry and lattice samples (no chunks): a function of the scalar search parameters only
+  const bool same_lattice = h->lattice_valid && h->lat_hx == h->half_x && h->lat_hy == h->half_y && h->lat_yaw_half == h->yaw_half &&
+                            h->lat_p.match_xy_step_size == h->p.match_xy_step_size &&
+                            h->lat_p.match_yaw_angle_step_size == h->p.match_yaw_angle_step_size &&
+                            h->lat_p.disable_yaw_search == h->p.disable_yaw_search && !h->L.ring_major;
+  // the three host builds are independent: lattice + blocks and the reference-side bins on the helper threads,
+  // the query groups (which need the reference map's labels only) on this one
+  std::string lattice_err, ref_err;
+  bool lattice_started = false, ref_started = false;
+  struct Joiner {
+    slide_pr_handle *h; bool *l, *q;
+    ~Joiner() { if (*l) h->worker_lattice.wait(); if (*q) h->worker_query.wait(); }
+  } joiner{h, &lattice_started, &ref_started};
+  if (!same_lattice) {
+    h->lattice_valid = false; h->j_blocks_valid = false;
+  } else {
+    h->reuse_flags |= 1;
+  }
+  if (!h->j_blocks_valid) {
+    const bool build_rings = !same_lattice;
+    h->worker_lattice.submit([h, build_rings, &lattice_err]() {
+      cudaSetDevice(h->device);  // page-locked buffers grown by this job belong to the handle's device
+      int r = SLIDE_PR_OK;
+      if (build_rings) r = spr::build_lattice(h->p, h->half_x, h->half_y, h->yaw_half, 0, -1, false, h->L, lattice_err, true);
+      if (r == SLIDE_PR_OK && h->L.status == 0) r = spr::build_join_blocks(h->L, h->p.match_xy_step_size, h->j_blocks, &h->j_drift, lattice_err);
+      return r;
+    });
+    lattice_started = true;
+  }
+  // labels of the reference map: needed by the query groups before the bins are complete
+  std::vector<double> labels;
   if (!same_ref) {
     rs->join_valid = false;
-    if ((rc = spr::build_join_ref(h->p, rs->cached_ref.data(), h->n_ref, rs->J, h->err)) != SLIDE_PR_OK) return rc;
+    const double *ref7 = rs->cached_ref.data();
+    for (int i = 0; i < h->n_ref; i++) {
+      const double l = ref7[7 * (size_t)i];
+      if (l == l) labels.push_back(l + 0.0);
+    }
+    std::sort(labels.begin(), labels.end());
+    labels.erase(std::unique(labels.begin(), labels.end()), labels.end());
+    h->worker_query.submit([h, rs, &ref_err]() {
+      cudaSetDevice(h->device);
+      return spr::build_join_ref(h->p, rs->cached_ref.data(), h->n_ref, rs->J, ref_err);
+    });
+    ref_started = true;
+  } else {
+    h->reuse_flags |= 2;
+  }
+  // query groups (label-major, Morton order inside a label)
+  if ((rc = spr::build_query_set(same_ref ? rs->J.labels : labels, h->qry_rows.data(), h->n_qry, h->JQ, h->err)) != SLIDE_PR_OK) return rc;
+  const int n_groups = h->JQ.nqp / SPR_QGROUP;
+  h->j_glabel.assign((size_t)std::max(n_groups, 1), 0);
+  for (int g = 0; g < n_groups; g++) h->j_glabel[g] = h->JQ.qlabel[(size_t)g * SPR_QGROUP];  // a group's first entry is never padding
+  if ((rc = upload(h, h->dj_qxy, h->JQ.qxy, st))) return rc;
+  if ((rc = upload(h, h->dj_qdims, h->JQ.qdims, st))) return rc;
+  if ((rc = upload(h, h->dj_qlabel, h->JQ.qlabel, st))) return rc;
+  if ((rc = upload(h, h->dj_glabel, h->j_glabel, st))) return rc;
+  g_trace.mark("join_queries");
+  if (ref_started) {
+    rc = h->worker_query.wait();
+    ref_started = false;
+    if (rc != SLIDE_PR_OK) { h->err = ref_err; return rc; }
     g_trace.mark("join_ref_build");
     if ((rc = upload(h, rs->dj_rec0, rs->J.rec[0], st))) return rc;
     if ((rc = upload(h, rs->dj_rec1, rs->J.rec[1], st))) return rc;
@@ -533,40 +592,22 @@ static int join_prepare(slide_pr_handle *h) {
     if ((rc = upload(h, rs->dj_labelbox, rs->J.labelbox, st))) return rc;
     rs->join_valid = true;
     rs->join_p = h->p;
-  } else {
-    h->reuse_flags |= 2;
   }
-  // ring geometry and lattice samples (no chunks): a function of the scalar search parameters only
-  const bool same_lattice = h->lattice_valid && h->lat_hx == h->half_x && h->lat_hy == h->half_y && h->lat_yaw_half == h->yaw_half &&
-                            h->lat_p.match_xy_step_size == h->p.match_xy_step_size &&
-                            h->lat_p.match_yaw_angle_step_size == h->p.match_yaw_angle_step_size &&
-                            h->lat_p.disable_yaw_search == h->p.disable_yaw_search && !h->L.ring_major;
-  if (!same_lattice) {
-    h->lattice_valid = false; h->j_blocks_valid = false;
-    if ((rc = spr::build_lattice(h->p, h->half_x, h->half_y, h->yaw_half, 0, -1, false, h->L, h->err, true)) != SLIDE_PR_OK) return rc;
-    h->lat_hx = h->half_x; h->lat_hy = h->half_y; h->lat_yaw_half = h->yaw_half; h->lat_p = h->p;
-    h->lattice_valid = true;
-    h->lattice_on_device = false;
-  } else {
-    h->reuse_flags |= 1;
-  }
-  if (!h->j_blocks_valid) {
-    if ((rc = spr::build_join_blocks(h->L, h->p.match_xy_step_size, h->j_blocks, &h->j_drift, h->err)) != SLIDE_PR_OK) return rc;
+  if (lattice_started) {
+    rc = h->worker_lattice.wait();
+    lattice_started = false;
+    if (rc != SLIDE_PR_OK) { h->err = lattice_err; return rc; }
+    if (!same_lattice) {
+      h->lat_hx = h->half_x; h->lat_hy = h->half_y; h->lat_yaw_half = h->yaw_half; h->lat_p = h->p;
+      h->lattice_valid = true;
+      h->lattice_on_device = false;
+    }
     if ((rc = upload(h, h->dj_lat, h->L.lat, st))) return rc;
     if ((rc = upload(h, h->dj_cs, h->L.cs, st))) return rc;
     if ((rc = upload(h, h->dj_blocks, h->j_blocks, st))) return rc;
     h->j_blocks_valid = true;
     g_trace.mark("join_blocks");
   }
-  // query groups (label-major, Morton order inside a label)
-  if ((rc = spr::build_query_set(rs->J.labels, h->qry_rows.data(), h->n_qry, h->JQ, h->err)) != SLIDE_PR_OK) return rc;
-  const int n_groups = h->JQ.nqp / SPR_QGROUP;
-  h->j_glabel.assign((size_t)std::max(n_groups, 1), 0);
-  for (int g = 0; g < n_groups; g++) h->j_glabel[g] = h->JQ.qlabel[(size_t)g * SPR_QGROUP];  // a group's first entry is never padding
-  if ((rc = upload(h, h->dj_qxy, h->JQ.qxy, st))) return rc;
-  if ((rc = upload(h, h->dj_qdims, h->JQ.qdims, st))) return rc;
-  if ((rc = upload(h, h->dj_qlabel, h->JQ.qlabel, st))) return rc;
-  if ((rc = upload(h, h->dj_glabel, h->j_glabel, st))) return rc;
   const size_t n_yaw = h->L.yaw.size();
   SPR_CUDA(h, h->dj_qrot.ensure(std::max<size_t>(n_yaw * (size_t)h->JQ.nqp, 1) * 2 * sizeof(double)));
   SPR_CUDA(h, h->dj_gbox.ensure(std::max<size_t>(n_yaw * (size_t)n_groups, 1) * sizeof(SprJoinBox)));
@@ -595,7 +636,6 @@ static int join_prepare(slide_pr_handle *h) {
   V.n_blocks = (uint32_t)h->j_blocks.size();
   h->join_ready = true;
   h->prepare_ms += now_ms() - t0;
-  g_trace.mark("join_queries");
   return SLIDE_PR_OK;
 }
 

@@ -98,7 +98,9 @@ __device__ __forceinline__ void spj_quad(const SprJoinView &V, const SpjBlock &B
         band++;
         continue;
       }
-      out[k++] = (r++ << 5) | (uint32_t)lane;
+      const uint32_t m = min(r_end - r, n - k), e0 = (r << 5) | (uint32_t)lane;
+      for (uint32_t t = 0; t < m; t++) out[k + t] = e0 + (t << 5);
+      k += m; r += m;
     }
     __syncwarp();
     // filter, compacting in place (a window's survivors land at or before the window)
