@@ -133,10 +133,13 @@ __device__ __forceinline__ void spj_quad(const SprJoinView &V, const SpjBlock &B
 __global__ void __launch_bounds__(SPJ_THREADS, 4)
 spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_constant__ SprJoinLaunch K,
                       const uint32_t n_blocks_local, const unsigned long long n_items) {
-  __shared__ uint32_t s_tile[SPJ_TILE_WORDS];
-  __shared__ SpjQuery s_q[SPJ_WARPS][32];
-  __shared__ uint32_t s_list[SPJ_WARPS][SPJ_LIST];
-  __shared__ uint16_t s_vis[SPJ_SEG_GROUPS];
+  // dynamic shared memory (more than the 48 KB a static allocation may take): counters, staged query
+  // landmarks, per-warp work lists, visible groups
+  extern __shared__ __align__(16) unsigned char spj_smem[];
+  SpjQuery (*s_q)[32] = reinterpret_cast<SpjQuery (*)[32]>(spj_smem);
+  uint32_t *s_tile = reinterpret_cast<uint32_t *>(spj_smem + SPJ_WARPS * 32 * sizeof(SpjQuery));
+  uint32_t (*s_list)[SPJ_LIST] = reinterpret_cast<uint32_t (*)[SPJ_LIST]>(s_tile + SPJ_TILE_WORDS);
+  uint16_t *s_vis = reinterpret_cast<uint16_t *>(s_tile + SPJ_TILE_WORDS + SPJ_WARPS * SPJ_LIST);
   __shared__ uint32_t s_nvis, s_next;
   __shared__ unsigned long long s_item;
   __shared__ uint32_t s_red[SPJ_WARPS];
@@ -196,11 +199,11 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
     int s_lo, s_hi;
     spj_slice(blk, K.ord_begin, K.ord_end, &s_lo, &s_hi);
     const float inv_ny = 1.0f / (float)B.ny;
-    uint32_t best = 0u;   // (count + 1) << 12 | (4095 - slot): max count, then smallest slot = smallest ordinal
+    uint32_t best = 0u;   // (count + 1) << SPJ_SLOT_BITS | (SPJ_MAX_SLOTS - 1 - slot): max count, then smallest slot = smallest ordinal
     for (int s = s_lo + tid; s < s_hi; s += SPJ_THREADS) {
-      const int i = __float2int_rd(((float)s + 0.5f) * inv_ny), j = s - i * B.ny;   // exact: s < 4096
+      const int i = __float2int_rd(((float)s + 0.5f) * inv_ny), j = s - i * B.ny;   // exact: s < 2^13
       const uint32_t c = spj_total(s_tile, B, i, j);
-      best = max(best, ((c + 1u) << 12) | (uint32_t)(SPJ_MAX_SLOTS - 1 - s));
+      best = max(best, ((c + 1u) << SPJ_SLOT_BITS) | (uint32_t)(SPJ_MAX_SLOTS - 1 - s));
       if (K.counts_out) {
         const unsigned long long ord = (unsigned long long)blk.ord0 + (unsigned long long)i * blk.row_stride + (unsigned long long)j;
         K.counts_out[(ord - K.ord_begin) * (unsigned long long)V.n_yaw + (unsigned long long)a] = (int32_t)c;
@@ -214,7 +217,7 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
       for (int w = 1; w < SPJ_WARPS; w++) best = max(best, s_red[w]);
       if (best) {
         const int s = SPJ_MAX_SLOTS - 1 - (int)(best & (SPJ_MAX_SLOTS - 1));
-        const uint32_t c = (best >> 12) - 1u;
+        const uint32_t c = (best >> SPJ_SLOT_BITS) - 1u;
         const int i = s / B.ny, j = s - i * B.ny;
         const unsigned long long ord = (unsigned long long)blk.ord0 + (unsigned long long)i * blk.row_stride + (unsigned long long)j;
         atomicMax(K.best_key, spr_make_key(c, ord * (unsigned long long)V.n_yaw + (unsigned long long)a));
@@ -231,11 +234,14 @@ cudaError_t spr_launch_join_score(const SprJoinView &V, const SprJoinLaunch &K, 
   if (n_items == 0) return cudaSuccess;
   SprJoinLaunch L = K;
   L.shard_index = si; L.shard_count = sc;
+  const size_t smem = SPJ_WARPS * 32 * sizeof(SpjQuery) + (SPJ_TILE_WORDS + SPJ_WARPS * SPJ_LIST) * sizeof(uint32_t) + SPJ_SEG_GROUPS * sizeof(uint16_t);
+  cudaError_t e = cudaFuncSetAttribute(spr_join_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spr_join_score_kernel, SPJ_THREADS, 0);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spr_join_score_kernel, SPJ_THREADS, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   const unsigned long long cap = (unsigned long long)sm_count * (unsigned long long)per_sm;
-  spr_join_score_kernel<<<(unsigned)(n_items < cap ? n_items : cap), SPJ_THREADS, 0, st>>>(V, L, n_local, n_items);
+  spr_join_score_kernel<<<(unsigned)(n_items < cap ? n_items : cap), SPJ_THREADS, smem, st>>>(V, L, n_local, n_items);
   return cudaGetLastError();
 }

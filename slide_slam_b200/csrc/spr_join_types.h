@@ -4,11 +4,16 @@
 
 #define SPJ_WARPS 8
 #define SPJ_THREADS (SPJ_WARPS * 32)
-#define SPJ_MAX_SLOTS 4096             // lattice samples per block (12-bit slot index in the block's arg-max)
-#define SPJ_TILE_WORDS 4096            // shared-memory words of a block's counters: two arrays of nx * ((ny >> 1) + 1)
-#define SPJ_SEG_GROUPS (SPJ_THREADS * 4)   // query groups whose visibility is tested per pass
-#define SPJ_LIST 512                   // per-warp work list (candidate landmarks of 32 query landmarks), entries
-#define SPJ_SHARE (SPJ_LIST / 32)      // entries a lane may add per step
+#ifndef SPJ_SLOT_BITS
+#define SPJ_SLOT_BITS 12
+#endif
+#define SPJ_MAX_SLOTS (1 << SPJ_SLOT_BITS)   // lattice samples per block (slot index in the block's arg-max)
+#define SPJ_TILE_WORDS SPJ_MAX_SLOTS         // shared-memory words of a block's counters: two arrays of nx * ((ny >> 1) + 1)
+#define SPJ_SEG_GROUPS (SPJ_THREADS * 4)     // query groups whose visibility is tested per pass
+#ifndef SPJ_LIST
+#define SPJ_LIST 512                         // per-warp work list (candidate landmarks of 32 query landmarks), entries
+#endif
+#define SPJ_SHARE (SPJ_LIST / 32)            // entries a lane may add per step
 
 // one reference landmark in the join order of direction d (label-major, then coarse cell)
 struct SprJoinRef {

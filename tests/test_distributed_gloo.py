@@ -113,8 +113,13 @@ def _sharded_worker(rank, world, port, out_q):
         pr0 = _FakeShardedSearch([[(0, 8)], [(0, 2)]][rank], None, can_bound=False)
         res0 = parallel.sharded_search(pr0, rank, world)
         win0 = parallel.allgather_winner(res0.best_hyp_index, res0.best_num_inliers)
+        # default engine (pair-join scorer): one exact pass per shard, no incumbent exchange
+        prj = _FakeShardedSearch(hyps, seed)
+        prj.engine = "join"
+        resj = parallel.sharded_search(prj, rank, world)
+        winj = parallel.allgather_winner(resj.best_hyp_index, resj.best_num_inliers)
         out_q.put((rank, pr.calls, (res.best_num_inliers, res.best_hyp_index, res.gpu_launches), (win.inliers, win.hyp_index, win.rank),
-                   pr0.calls, (win0.inliers, win0.hyp_index, win0.rank)))
+                   pr0.calls, (win0.inliers, win0.hyp_index, win0.rank), prj.calls, (winj.inliers, winj.hyp_index, winj.rank)))
     finally:
         dist.destroy_process_group()
 
@@ -133,7 +138,8 @@ def test_two_phase_sharded_search_shares_the_incumbent():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, calls, local, win, calls0, win0 in results:
+    for rank, calls, local, win, calls0, win0, callsj, winj in results:
+        assert callsj == [(rank, world, False, 0, False)] and winj == (30, 77, 1)   # pair-join scorer: a single sharded search
         assert calls == [(rank, world, True, 0, False), (rank, world, False, 11, True)]  # incumbent = max(9, 11)
         assert win == (30, 77, 1)                     # ties to the smallest canonical index
         assert calls0 == [(rank, world, True, 0, False)]  # exhaustive fallback: no second call
