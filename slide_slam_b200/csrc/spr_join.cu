@@ -130,7 +130,7 @@ __device__ __forceinline__ void spj_quad(const SprJoinView &V, const SpjBlock &B
   }
 }
 
-__global__ void __launch_bounds__(SPJ_THREADS, 4)
+__global__ void __launch_bounds__(SPJ_THREADS, SPJ_MIN_CTAS)
 spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_constant__ SprJoinLaunch K,
                       const uint32_t n_blocks_local, const unsigned long long n_items) {
   // dynamic shared memory (more than the 48 KB a static allocation may take): counters, staged query

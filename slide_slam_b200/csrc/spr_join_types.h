@@ -14,6 +14,9 @@
 #define SPJ_LIST 512                         // per-warp work list (candidate landmarks of 32 query landmarks), entries
 #endif
 #define SPJ_SHARE (SPJ_LIST / 32)            // entries a lane may add per step
+#ifndef SPJ_MIN_CTAS
+#define SPJ_MIN_CTAS 4                        // resident CTAs per SM the kernel is compiled for (register budget)
+#endif
 
 // one reference landmark in the join order of direction d (label-major, then coarse cell)
 struct SprJoinRef {

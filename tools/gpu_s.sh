@@ -1,0 +1,9 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+rm -f gpurun_out/s_ab.log
+for lib in variants/libslide_pr_l256c4.so variants/libslide_pr_l256c5.so; do
+  SLIDE_PR_LIB=$lib timeout 200 python tools/ab_search.py 2 10 4 >> gpurun_out/s_ab.log 2>&1
+  SLIDE_PR_LIB=$lib timeout 300 python tools/ab_search.py 3 2 4 >> gpurun_out/s_ab.log 2>&1
+  for c in 4 5; do SLIDE_PR_LIB=$lib timeout 200 python tools/ncu_cfg_target.py $c 2>&1 | tail -1 >> gpurun_out/s_ab.log; done
+done
