@@ -155,7 +155,7 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
     const SprJoinBlock blk = V.blocks[b];
     const SpjBlock B = spj_block(V, blk);
     const int n_slots = B.nx * B.ny;
-    for (int w = tid; w < 2 * B.stride; w += SPJ_THREADS) s_tile[w] = 0u;
+    for (int w = tid; w < (2 * B.stride + 3) / 4; w += SPJ_THREADS) reinterpret_cast<uint4 *>(s_tile)[w] = make_uint4(0u, 0u, 0u, 0u);
 
     const SprJoinBox *gb = V.gbox + (size_t)a * (size_t)V.n_groups;
     const double2 *qr = reinterpret_cast<const double2 *>(V.qrot) + (size_t)a * (size_t)V.nqp;
@@ -164,8 +164,8 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
       if (tid == 0) { s_nvis = 0u; s_next = 0u; }
       __syncthreads();   // counters zeroed (first segment); the previous segment's warps are done with s_vis
       // groups of the segment that some translation of the block brings over their label's landmarks
-#pragma unroll
-      for (int k = 0; k < SPJ_SEG_GROUPS / SPJ_THREADS; k++) {
+      const int seg_passes = min(SPJ_SEG_GROUPS / SPJ_THREADS, (V.n_groups - seg0 + SPJ_THREADS - 1) / SPJ_THREADS);
+      for (int k = 0; k < seg_passes; k++) {
         const int g = seg0 + k * SPJ_THREADS + tid;
         bool vis = false;
         if (g < V.n_groups) {

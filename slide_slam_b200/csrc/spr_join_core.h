@@ -72,9 +72,18 @@ SPR_HD bool spj_near(const SpjBlock &B, double rx, double ry, double px, double 
 // two arrays of B.stride words, two u16 counters per word; word n of a row of array ay holds samples
 // 2n - ay and 2n - ay + 1, so the two samples a pair can hit in a row share ONE word of one array.
 SPR_HD void spj_pair(const SprJoinView &V, const SpjBlock &B, double rx, double ry, const double *qd, const SprJoinRef *rec, uint32_t *tile) {
-  if (!V.ignore_dim && !spr_dimension_match(SPJ_LD(&rec->d1), SPJ_LD(&rec->d2), SPJ_LD(&rec->d3), qd, V.thr_dim, V.Sstar)) return;   // PR.cpp:315-339
-  const double px = SPJ_LD(&rec->x), py = SPJ_LD(&rec->y);
-  const uint32_t nbr_off = SPJ_LD(&rec->nbr_off), nbr_cnt = SPJ_LD(&rec->nbr_cnt);
+#if defined(__CUDA_ARCH__)
+  // the 48-byte record in three 16-byte loads
+  const double2 r0 = __ldg(reinterpret_cast<const double2 *>(rec)), r1 = __ldg(reinterpret_cast<const double2 *>(rec) + 1);
+  const double2 r2 = __ldg(reinterpret_cast<const double2 *>(rec) + 2);
+  const double px = r0.x, py = r0.y, rd1 = r1.x, rd2 = r1.y, rd3 = r2.x;
+  const unsigned long long nb = (unsigned long long)__double_as_longlong(r2.y);
+  const uint32_t nbr_off = (uint32_t)nb, nbr_cnt = (uint32_t)(nb >> 32);
+#else
+  const double px = rec->x, py = rec->y, rd1 = rec->d1, rd2 = rec->d2, rd3 = rec->d3;
+  const uint32_t nbr_off = rec->nbr_off, nbr_cnt = rec->nbr_cnt;
+#endif
+  if (!V.ignore_dim && !spr_dimension_match(rd1, rd2, rd3, qd, V.thr_dim, V.Sstar)) return;   // PR.cpp:315-339
   // index ranges from the regular spacing (ireach covers the drift of the accumulated samples), then the
   // exact test on the samples themselves
   const double ux = SPR_DSUB(SPR_DSUB(px, rx), B.X0), uy = SPR_DSUB(SPR_DSUB(py, ry), B.Y0);
