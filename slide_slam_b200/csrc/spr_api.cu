@@ -554,13 +554,7 @@ static int join_prepare(slide_pr_handle *h) {
   std::vector<double> labels;
   if (!same_ref) {
     rs->join_valid = false;
-    const double *ref7 = rs->cached_ref.data();
-    for (int i = 0; i < h->n_ref; i++) {
-      const double l = ref7[7 * (size_t)i];
-      if (l == l) labels.push_back(l + 0.0);
-    }
-    std::sort(labels.begin(), labels.end());
-    labels.erase(std::unique(labels.begin(), labels.end()), labels.end());
+    spr::unique_labels(rs->cached_ref.data(), h->n_ref, labels);
     h->worker_query.submit([h, rs, &ref_err]() {
       cudaSetDevice(h->device);
       return spr::build_join_ref(h->p, rs->cached_ref.data(), h->n_ref, rs->J, ref_err);

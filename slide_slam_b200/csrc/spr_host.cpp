@@ -634,11 +634,30 @@ int build_query_set(const RefIndex &R, const double *qry7, int n_qry, QuerySet &
   return build_query_set(R.labels, qry7, n_qry, Q, err);
 }
 
+// distinct non-NaN labels of a map, ascending (-0.0 and 0.0 are one label: PR.cpp:306 compares with ==).
+// Maps have a handful of labels: a small sorted vector with binary search instead of sorting all rows.
+void unique_labels(const double *rows7, int n, std::vector<double> &labels) {
+  labels.clear();
+  double last = 0.0;
+  bool have_last = false;
+  for (int i = 0; i < n; i++) {
+    const double l = rows7[7 * (size_t)i];
+    if (!(l == l)) continue;  // NaN labels never compare equal
+    if (have_last && l == last) continue;
+    last = l; have_last = true;
+    auto it = std::lower_bound(labels.begin(), labels.end(), l + 0.0);
+    if (it == labels.end() || *it != l + 0.0) labels.insert(it, l + 0.0);
+  }
+}
+
 int build_query_set(const std::vector<double> &labels, const double *qry7, int n_qry, QuerySet &Q, std::string &err) {
   Q.nq = Q.nqp = 0;  // the (page-locked) vectors keep their capacity across calls
   const int n_labels = (int)labels.size();
-  struct Item { int l; uint32_t morton; int j; };
-  std::vector<Item> items;
+  // sort key: label bucket, Morton code, original index -- one 64-bit integer per kept query
+  // (20 bits of label bucket, 22 bits of index: slide_pr_prepare limits n_qry to 2^22)
+  std::vector<uint64_t> items;
+  items.reserve((size_t)n_qry);
+  if (n_labels >= (1 << 20)) { err = "more than 2^20 distinct labels"; return SLIDE_PR_ERR_UNSUPPORTED; }
   double minx = HUGE_VAL, maxx = -HUGE_VAL, miny = HUGE_VAL, maxy = -HUGE_VAL;
   for (int j = 0; j < n_qry; j++) {
     const double *q = qry7 + 7 * (size_t)j;
@@ -653,19 +672,32 @@ int build_query_set(const std::vector<double> &labels, const double *qry7, int n
     const double lab = q[0] + 0.0;
     auto it = std::lower_bound(labels.begin(), labels.end(), lab);
     if (it == labels.end() || *it != lab) continue;  // no reference object can ever match it
-    const uint32_t mx = (uint32_t)((q[1] - minx) * sx), my = (uint32_t)((q[2] - miny) * sy);
-    items.push_back({(int)(it - labels.begin()), part1by1(mx) | (part1by1(my) << 1), j});
+    // Morton code of the 11 high bits of each 16-bit coordinate (22 bits): groups stay spatially compact
+    const uint32_t mx = (uint32_t)((q[1] - minx) * sx) >> 5, my = (uint32_t)((q[2] - miny) * sy) >> 5;
+    const uint64_t morton = part1by1(mx) | (part1by1(my) << 1);
+    items.push_back(((uint64_t)(it - labels.begin()) << 44) | (morton << 22) | (uint64_t)j);
   }
-  std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
-    if (a.l != b.l) return a.l < b.l;
-    if (a.morton != b.morton) return a.morton < b.morton;
-    return a.j < b.j;
-  });
+  // stable LSD radix sort on the (label, Morton) bits: the items are generated in ascending index order
+  {
+    int key_bits = 22;
+    for (int nl = n_labels; nl > 1; nl >>= 1) key_bits++;
+    key_bits += 1;
+    std::vector<uint64_t> tmp(items.size());
+    uint32_t hist[2048];
+    for (int shift = 22; shift < 22 + key_bits; shift += 11) {
+      std::memset(hist, 0, sizeof(hist));
+      for (const uint64_t it : items) hist[(it >> shift) & 2047u]++;
+      uint32_t run = 0;
+      for (uint32_t &h : hist) { const uint32_t c = h; h = run; run += c; }
+      for (const uint64_t it : items) tmp[hist[(it >> shift) & 2047u]++] = it;
+      items.swap(tmp);
+    }
+  }
   Q.nq = (int)items.size();
   // every label segment is padded to a whole number of query groups; padding entries carry
   // qlabel = -1 and get the sentinel fixed-point coordinate (never inside the grid)
   std::vector<int> per_label(n_labels, 0);
-  for (const Item &it : items) per_label[it.l]++;
+  for (const uint64_t it : items) per_label[(size_t)(it >> 44)]++;
   Q.label_gseg.assign(n_labels + 1, 0);
   for (int l = 0; l < n_labels; l++) Q.label_gseg[l + 1] = Q.label_gseg[l] + (per_label[l] + SPR_QGROUP - 1) / SPR_QGROUP;
   Q.nqp = Q.label_gseg[n_labels] * SPR_QGROUP;
@@ -675,11 +707,12 @@ int build_query_set(const std::vector<double> &labels, const double *qry7, int n
   Q.qxy.assign(2 * n, 0.0);
   Q.qdims.assign(3 * n, 0.0);
   std::vector<int> fill(n_labels, 0);
-  for (const Item &it : items) {
-    const size_t s = (size_t)Q.label_gseg[it.l] * SPR_QGROUP + (size_t)fill[it.l]++;
-    const double *q = qry7 + 7 * (size_t)it.j;
-    Q.orig[s] = it.j;
-    Q.qlabel[s] = it.l;
+  for (const uint64_t it : items) {
+    const int l = (int)(it >> 44), j = (int)(it & ((1u << 22) - 1u));
+    const size_t s = (size_t)Q.label_gseg[l] * SPR_QGROUP + (size_t)fill[l]++;
+    const double *q = qry7 + 7 * (size_t)j;
+    Q.orig[s] = j;
+    Q.qlabel[s] = l;
     Q.qxy[2 * s] = q[1]; Q.qxy[2 * s + 1] = q[2];
     Q.qdims[3 * s] = q[4]; Q.qdims[3 * s + 1] = q[5]; Q.qdims[3 * s + 2] = q[6];
   }
@@ -705,10 +738,8 @@ int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, Join
     if (!std::isfinite(r[1]) || !std::isfinite(r[2])) { err = "non-finite reference coordinate"; return SLIDE_PR_ERR_NONFINITE; }
     minx = std::min(minx, r[1]); maxx = std::max(maxx, r[1]);
     miny = std::min(miny, r[2]); maxy = std::max(maxy, r[2]);
-    if (r[0] == r[0]) J.labels.push_back(r[0] + 0.0);  // NaN labels never compare equal (PR.cpp:306)
   }
-  std::sort(J.labels.begin(), J.labels.end());
-  J.labels.erase(std::unique(J.labels.begin(), J.labels.end()), J.labels.end());
+  unique_labels(ref7, n_ref, J.labels);  // NaN labels never compare equal (PR.cpp:306)
   const int n_labels = (int)J.labels.size();
   if (n_ref == 0) { minx = maxx = miny = maxy = 0; }
   // coarse grid: cells of 8 lattice steps (a block is about 10 steps wide), not smaller than the reach,

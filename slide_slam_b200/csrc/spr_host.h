@@ -118,6 +118,7 @@ struct QuerySet {
 };
 int build_query_set(const RefIndex &R, const double *qry7, int n_qry, QuerySet &Q, std::string &err);
 int build_query_set(const std::vector<double> &labels, const double *qry7, int n_qry, QuerySet &Q, std::string &err);
+void unique_labels(const double *rows7, int n, std::vector<double> &labels);
 
 // thresholds: sqrt(d2) < thr <=> d2 < Tstar ; (s / 3) < thr_dim <=> s < Sstar
 double sqrt_threshold(double thr);

@@ -52,12 +52,24 @@ cudaError_t spr_launch_join_rotate(const SprJoinView &V, double *qrot, SprJoinBo
 // A query landmark as the lanes of its warp see it while its candidate pairs are processed.
 struct SpjQuery { double rx, ry, d1, d2, d3; int32_t label, pad; };
 
-// 32 query landmarks (a "quad" of four visible groups, one landmark per lane) against block B.  The
-// candidate reference landmarks of all 32 are gathered into one work list, which the lanes then process
-// side by side: filter (can the pair match under a translation of the block at all?), compaction, exact
-// tests and counter updates -- the lanes stay busy although the landmarks have different numbers of candidates.
+// 32 query landmarks (a "quad" of four visible groups, one landmark per lane) against block B.  Every lane
+// looks up the record ranges of the coarse-cell bands its landmark can reach; a prefix sum over all ranges of
+// the warp turns them into ONE flat sequence of candidate (landmark, record) pairs, which the lanes then walk
+// side by side (a lane finds the range of its candidate by binary search in the prefix table): filter (can
+// the pair match under a translation of the block at all?), compaction of the survivors into the pair list,
+// exact tests and counter updates -- the lanes stay busy although the landmarks have different numbers of
+// candidates.
+__device__ __forceinline__ void spj_pairs(const SprJoinView &V, const SpjBlock &B, const SprJoinRef *rec, const SpjQuery *sq,
+                                          const uint32_t *list, uint32_t n_pairs, int lane, uint32_t *tile) {
+  for (uint32_t w = (uint32_t)lane; w < n_pairs; w += 32) {
+    const uint32_t e = list[w];
+    const SpjQuery &q = sq[e & 31u];
+    spj_pair(V, B, q.rx, q.ry, &q.d1, rec + (e >> 5), tile);
+  }
+}
+
 __device__ __forceinline__ void spj_quad(const SprJoinView &V, const SpjBlock &B, const double2 *__restrict__ qr, int g, int lane,
-                                         bool active, SpjQuery *sq, uint32_t *list, uint32_t *tile) {
+                                         bool active, SpjQuery *sq, uint32_t *list, uint32_t *pre, uint32_t *beg, uint32_t *tile) {
   int b0 = 0, b1 = -1, a0 = 0, a1 = -1;
   const uint32_t *cstart = V.cell_start[B.dir];
   if (active) {
@@ -75,59 +87,64 @@ __device__ __forceinline__ void spj_quad(const SprJoinView &V, const SpjBlock &B
   }
   const int pitch = B.dir ? V.ncx : V.ncy;
   const SprJoinRef *rec = V.rec[B.dir];
-  int band = b0;                 // next band to open
-  uint32_t r = 0u, r_end = 0u;   // records of the open band still to be listed
-  for (;;) {
-    // how many records this lane lists in this step: the rest of its open band and further bands, up to its share
-    uint32_t n = min(r_end - r, (uint32_t)SPJ_SHARE);
-    for (int bb = band; n < (uint32_t)SPJ_SHARE && bb <= b1; bb++)
-      n = min(n + (__ldg(cstart + bb * pitch + a1 + 1) - __ldg(cstart + bb * pitch + a0)), (uint32_t)SPJ_SHARE);
-    if (!__any_sync(SPJ_FULL, n != 0u)) break;
-    uint32_t incl = n;
+  uint32_t n_pairs = 0u;
+  for (int bb = b0; __any_sync(SPJ_FULL, bb <= b1); bb += SPJ_BANDS) {
+    // record ranges of the lane's next SPJ_BANDS bands, and their places in the warp's flat candidate sequence
+    uint32_t bg[SPJ_BANDS], cnt[SPJ_BANDS], t = 0u;
+#pragma unroll
+    for (int k = 0; k < SPJ_BANDS; k++) {
+      uint32_t s = 0u, e = 0u;
+      if (bb + k <= b1) {
+        s = __ldg(cstart + (bb + k) * pitch + a0);
+        e = __ldg(cstart + (bb + k) * pitch + a1 + 1);
+      }
+      bg[k] = s; cnt[k] = e - s; t += e - s;
+    }
+    uint32_t incl = t;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(SPJ_FULL, incl, d);
-      if (lane >= d) incl += t;
+      const uint32_t u = __shfl_up_sync(SPJ_FULL, incl, d);
+      if (lane >= d) incl += u;
     }
     const uint32_t total = __shfl_sync(SPJ_FULL, incl, 31);
-    uint32_t *out = list + (incl - n);
-    for (uint32_t k = 0; k < n;) {
-      if (r >= r_end) {   // open the next band (n > k guarantees there is one with records left)
-        r = __ldg(cstart + band * pitch + a0);
-        r_end = __ldg(cstart + band * pitch + a1 + 1);
-        band++;
-        continue;
-      }
-      const uint32_t m = min(r_end - r, n - k), e0 = (r << 5) | (uint32_t)lane;
-      for (uint32_t t = 0; t < m; t++) out[k + t] = e0 + (t << 5);
-      k += m; r += m;
+    uint32_t at = incl - t;
+#pragma unroll
+    for (int k = 0; k < SPJ_BANDS; k++) {
+      pre[lane * SPJ_BANDS + k] = at;
+      beg[lane * SPJ_BANDS + k] = bg[k];
+      at += cnt[k];
     }
+    if (lane == 31) pre[32 * SPJ_BANDS] = total;
     __syncwarp();
-    // filter, compacting in place (a window's survivors land at or before the window)
-    uint32_t n_pairs = 0u;
     for (uint32_t w0 = 0; w0 < total; w0 += 32) {
-      const uint32_t w = w0 + (uint32_t)lane;
+      const uint32_t w = w0 + (uint32_t)lane;   // consecutive lanes take consecutive candidates: neighbouring records, coalesced loads
       uint32_t e = 0u;
       bool ok = false;
       if (w < total) {
-        e = list[w];
+        uint32_t lo = 0u;   // the last range that starts at or before candidate w (empty ranges share their start with the next one)
+#pragma unroll
+        for (uint32_t step = 16 * SPJ_BANDS; step >= 1; step >>= 1)
+          if (pre[lo + step] <= w) lo += step;
+        e = ((beg[lo] + (w - pre[lo])) << 5) | (lo / SPJ_BANDS);
         const double2 p = __ldg(reinterpret_cast<const double2 *>(rec + (e >> 5)));
         const SpjQuery &q = sq[e & 31u];
         ok = spj_near(B, q.rx, q.ry, p.x, p.y);
       }
       const uint32_t m = __ballot_sync(SPJ_FULL, ok);
-      __syncwarp();
       if (ok) list[n_pairs + (uint32_t)__popc(m & ((1u << lane) - 1u))] = e;
       n_pairs += (uint32_t)__popc(m);
+      if (n_pairs + 32u > (uint32_t)SPJ_LIST) {   // the pair list is full: exact tests and counter updates now
+        __syncwarp();
+        spj_pairs(V, B, rec, sq, list, n_pairs, lane, tile);
+        __syncwarp();
+        n_pairs = 0u;
+      }
     }
-    __syncwarp();
-    for (uint32_t w = (uint32_t)lane; w < n_pairs; w += 32) {
-      const uint32_t e = list[w];
-      const SpjQuery &q = sq[e & 31u];
-      spj_pair(V, B, q.rx, q.ry, &q.d1, rec + (e >> 5), tile);
-    }
-    __syncwarp();
+    __syncwarp();   // the range tables are rewritten by the next pass
   }
+  __syncwarp();
+  spj_pairs(V, B, rec, sq, list, n_pairs, lane, tile);
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(SPJ_THREADS, SPJ_MIN_CTAS)
@@ -139,7 +156,8 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
   SpjQuery (*s_q)[32] = reinterpret_cast<SpjQuery (*)[32]>(spj_smem);
   uint32_t *s_tile = reinterpret_cast<uint32_t *>(spj_smem + SPJ_WARPS * 32 * sizeof(SpjQuery));
   uint32_t (*s_list)[SPJ_LIST] = reinterpret_cast<uint32_t (*)[SPJ_LIST]>(s_tile + SPJ_TILE_WORDS);
-  uint16_t *s_vis = reinterpret_cast<uint16_t *>(s_tile + SPJ_TILE_WORDS + SPJ_WARPS * SPJ_LIST);
+  uint32_t (*s_rng)[SPJ_RANGE_WORDS] = reinterpret_cast<uint32_t (*)[SPJ_RANGE_WORDS]>(s_tile + SPJ_TILE_WORDS + SPJ_WARPS * SPJ_LIST);
+  uint16_t *s_vis = reinterpret_cast<uint16_t *>(s_tile + SPJ_TILE_WORDS + SPJ_WARPS * (SPJ_LIST + SPJ_RANGE_WORDS));
   __shared__ uint32_t s_nvis, s_next;
   __shared__ unsigned long long s_item;
   __shared__ uint32_t s_red[SPJ_WARPS];
@@ -189,7 +207,8 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
         if (quad >= n_quads) break;
         const uint32_t gi = quad * 4u + ((uint32_t)lane >> 3);
         const bool active = gi < nvis;
-        spj_quad(V, B, qr, active ? seg0 + (int)s_vis[gi] : 0, lane, active, s_q[warp], s_list[warp], s_tile);
+        spj_quad(V, B, qr, active ? seg0 + (int)s_vis[gi] : 0, lane, active, s_q[warp], s_list[warp], s_rng[warp],
+                 s_rng[warp] + 32 * SPJ_BANDS + 1, s_tile);
       }
       __syncthreads();   // every warp is done with the segment's list (and, after the last segment, with its counter updates)
     }
@@ -234,13 +253,22 @@ cudaError_t spr_launch_join_score(const SprJoinView &V, const SprJoinLaunch &K, 
   if (n_items == 0) return cudaSuccess;
   SprJoinLaunch L = K;
   L.shard_index = si; L.shard_count = sc;
-  const size_t smem = SPJ_WARPS * 32 * sizeof(SpjQuery) + (SPJ_TILE_WORDS + SPJ_WARPS * SPJ_LIST) * sizeof(uint32_t) + SPJ_SEG_GROUPS * sizeof(uint16_t);
-  cudaError_t e = cudaFuncSetAttribute(spr_join_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = SPJ_WARPS * 32 * sizeof(SpjQuery) + (SPJ_TILE_WORDS + SPJ_WARPS * (SPJ_LIST + SPJ_RANGE_WORDS)) * sizeof(uint32_t) +
+                      SPJ_SEG_GROUPS * sizeof(uint16_t);
+  // the opt-in to more than 48 KB of dynamic shared memory and the residency query are per device: done once
+  static int per_sm_of_device[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spr_join_score_kernel, SPJ_THREADS, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) per_sm = 1;
+  int per_sm = dev >= 0 && dev < 64 ? per_sm_of_device[dev] : 0;
+  if (per_sm == 0) {
+    e = cudaFuncSetAttribute(spr_join_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spr_join_score_kernel, SPJ_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (dev >= 0 && dev < 64) per_sm_of_device[dev] = per_sm;
+  }
   const unsigned long long cap = (unsigned long long)sm_count * (unsigned long long)per_sm;
   spr_join_score_kernel<<<(unsigned)(n_items < cap ? n_items : cap), SPJ_THREADS, smem, st>>>(V, L, n_local, n_items);
   return cudaGetLastError();

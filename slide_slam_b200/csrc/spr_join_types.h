@@ -11,9 +11,10 @@
 #define SPJ_TILE_WORDS SPJ_MAX_SLOTS         // shared-memory words of a block's counters: two arrays of nx * ((ny >> 1) + 1)
 #define SPJ_SEG_GROUPS (SPJ_THREADS * 4)     // query groups whose visibility is tested per pass
 #ifndef SPJ_LIST
-#define SPJ_LIST 512                         // per-warp work list (candidate landmarks of 32 query landmarks), entries
+#define SPJ_LIST 256                         // per-warp list of (landmark, record) pairs that passed the filter, entries
 #endif
-#define SPJ_SHARE (SPJ_LIST / 32)            // entries a lane may add per step
+#define SPJ_BANDS 4                          // coarse-cell bands of a landmark whose record ranges one pass gathers
+#define SPJ_RANGE_WORDS (2 * 32 * SPJ_BANDS + 2)   // per warp: start of every range in the flat candidate sequence (+ end), first record
 #ifndef SPJ_MIN_CTAS
 #define SPJ_MIN_CTAS 4                        // resident CTAs per SM the kernel is compiled for (register budget)
 #endif
