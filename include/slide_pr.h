@@ -61,8 +61,10 @@ typedef struct slide_pr_params {
   int32_t min_num_map_objects_to_start; /* 1 */
   int32_t inter_loop_closure;         /* 1 (public member PR.h:43) */
   int32_t device;                     /* CUDA device ordinal; -1 = current device */
-  int32_t exhaustive_search;          /* not a rosparam.  0 (default): bound-and-verify search; 1: every hypothesis of the
-                                         lattice is verified exactly, as the reference does (same winner either way) */
+  int32_t exhaustive_search;          /* not a rosparam: which kernels search the lattice.  0 (default): the pair-join scorer
+                                         (exact inlier count of every hypothesis); 1: the lattice kernels, every hypothesis
+                                         verified; 2: the lattice kernels, bound-and-verify.  Same winner, inlier count and
+                                         correspondences in every case */
 } slide_pr_params;
 
 typedef struct slide_pr_handle slide_pr_handle;
@@ -88,7 +90,8 @@ typedef struct slide_pr_match_result {
   int64_t groups_probed;       /* (warp, query group) pairs probed / skipped by the bounding-box test */
   int64_t groups_skipped;      /*   (0 unless stats were enabled) */
   int32_t reuse;               /* bit 0: lattice reused from the previous prepare, bit 1: reference-map index reused */
-  int32_t search_mode;         /* 0: every hypothesis verified exactly (exhaustive); 1: bound-and-verify (same winner) */
+  int32_t search_mode;         /* 2: pair-join scorer (every hypothesis counted exactly); 0: lattice kernels, every hypothesis
+                                  verified; 1: lattice kernels, bound-and-verify (same winner in every mode) */
 } slide_pr_match_result;
 
 /* Options for the sharded / sliced search (multi-GPU and tests). */
@@ -102,17 +105,20 @@ typedef struct slide_pr_search_opts {
   int64_t counts_cap;    /* capacity of counts_out in entries */
   void   *stream;        /* cudaStream_t to run on; NULL = the handle's own stream */
   int32_t collect_stats; /* 1: count filter hits (slower; implies exhaustive) */
-  int32_t exhaustive;    /* 1: verify every hypothesis exactly.  0 (default): bound-and-verify -- a cheap upper
-                            bound (bitmap filter hits) for every hypothesis, exact verification only where the
-                            bound reaches the running best; the winner, its count and its correspondences are
-                            the same.  counts_out / collect_stats / compute_budget_sec > 0 imply exhaustive.
-                            2: bound phase only (first half of a sharded search, and a test hook): the result holds
-                            the best exactly scored seed hypothesis; counts_out, if given, receives the upper bounds. */
+  int32_t exhaustive;    /* engine of this search.  0 (default): the handle's default (the pair-join scorer unless
+                            slide_pr_params.exhaustive_search / SLIDE_PR_ENGINE=lattice say otherwise).
+                            4: the pair-join scorer -- the exact inlier count of every hypothesis of the slice / shard.
+                            Lattice kernels: 1: every hypothesis verified exactly; 3: bound-and-verify -- a cheap upper
+                            bound (bitmap filter hits) for every hypothesis, exact verification only where the bound
+                            reaches the running best; 2: bound phase only (first half of a sharded bound-and-verify
+                            search, and a test hook): the result holds the best exactly scored seed hypothesis;
+                            counts_out, if given, receives the upper bounds.  collect_stats, reuse_bounds, more than
+                            65535 query landmarks and a compute budget that can bind are served by the lattice kernels. */
   int32_t incumbent_inliers; /* > 0: an inlier count already reached elsewhere (another shard of the same pair, after an
                             all-reduce(max) of the shards' bound-phase results): hypotheses whose bound is below it are
                             not verified.  A shard that finds nothing >= the incumbent reports best_hyp_index = -1. */
-  int32_t reuse_bounds;  /* 1: the bounds of the preceding exhaustive = 2 call on the same prepared problem and shard are
-                            still on the device: skip the bound phase and go straight to the verification */
+  int32_t reuse_bounds;  /* lattice kernels: 1: the bounds of the preceding exhaustive = 2 call on the same prepared problem and
+                            shard are still on the device: skip the bound phase and go straight to the verification */
 } slide_pr_search_opts;
 
 typedef struct slide_pr_tf_result {
@@ -148,7 +154,8 @@ int slide_pr_match_maps(slide_pr_handle *h, const double *ref7, int32_t n_ref,
                         int32_t *ref_idx_out, int32_t *qry_idx_out, slide_pr_match_result *out);
 
 /* The same search split in its stages, for sharded multi-GPU use and for timing:
- *   prepare : host index build + H2D of both maps           (inputs become HBM-resident)
+ *   prepare : host index build + H2D of both maps           (inputs become HBM-resident; the structures of the
+ *             engine that is not the handle's default are built by the first search that asks for it)
  *   search  : the scoring kernels over this shard/slice     -> local best (count, canonical index)
  *   extract : correspondences + R_t of ONE hypothesis (the global winner after the all-gather) */
 int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, const double *qry7,
