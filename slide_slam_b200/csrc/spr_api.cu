@@ -229,6 +229,7 @@ struct slide_pr_handle {
   spr::Lattice L;
   RefSide anon;                        // slot of maps handed over by value (slide_pr_prepare & co.)
   std::map<int64_t, std::unique_ptr<RefSide>> cache;   // slots keyed by robot id (slide_pr_map_cache_put)
+  std::vector<std::unique_ptr<RefSide>> free_slots;   // dropped slots, kept with their page-locked and device buffers for reuse
   RefSide *rs = &anon;                 // the slot of the prepared problem
   uint64_t use_clock = 0;
   size_t cache_capacity = 64;          // least recently used slots beyond this many are dropped
@@ -368,6 +369,8 @@ void slide_pr_destroy(slide_pr_handle *h) {
   h->anon.release();
   for (auto &kv : h->cache) kv.second->release();
   h->cache.clear();
+  for (auto &f : h->free_slots) f->release();
+  h->free_slots.clear();
   spr_clipper_destroy(h->clipper);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1537,6 +1540,16 @@ int slide_pr_find_intra_loop_closure(slide_pr_handle *h, const double *meas7, in
 // over once per version: its centroid-shifted rows stay page-locked on the host and on the device, and
 // the reference-side index (occupancy bitmaps, rank tables) is built the first time the map is searched
 // AS A REFERENCE and reused by every later pair until the version changes.
+// A slot that leaves the cache keeps its buffers (page-locked host vectors, device allocations) in a small
+// pool: allocating them afresh for every batch of maps costs more than the searches themselves.
+static void retire_slot(slide_pr_handle *h, std::unique_ptr<RefSide> slot) {
+  slot->rows_valid = false; slot->ref_index_valid = false; slot->ranks_pending = false;
+  slot->join_valid = false; slot->ref7_uploaded = false;
+  slot->robot_id = -1; slot->version = 0; slot->n_rows = 0;
+  if (h->free_slots.size() < 16) h->free_slots.push_back(std::move(slot));
+  else slot->release();
+}
+
 int slide_pr_map_cache_put(slide_pr_handle *h, int64_t robot_id, uint64_t version, const double *rows7, int32_t n) {
   if (!h || n < 0 || (n > 0 && !rows7)) return SLIDE_PR_ERR_INVALID;
   SPR_CUDA(h, cudaSetDevice(h->device));
@@ -1556,10 +1569,13 @@ int slide_pr_map_cache_put(slide_pr_handle *h, int64_t robot_id, uint64_t versio
       for (auto k = h->cache.begin(); k != h->cache.end(); ++k)
         if (k->second->last_use < lru->second->last_use) lru = k;
       if (h->rs == lru->second.get()) { h->rs = &h->anon; h->prepared = false; }
-      lru->second->release();
+      retire_slot(h, std::move(lru->second));
       h->cache.erase(lru);
     }
-    it = h->cache.emplace(robot_id, std::unique_ptr<RefSide>(new RefSide())).first;
+    std::unique_ptr<RefSide> fresh;
+    if (!h->free_slots.empty()) { fresh = std::move(h->free_slots.back()); h->free_slots.pop_back(); }
+    else fresh.reset(new RefSide());
+    it = h->cache.emplace(robot_id, std::move(fresh)).first;
   }
   RefSide &E = *it->second;
   if (h->rs == &E) h->prepared = false;
@@ -1590,7 +1606,7 @@ int slide_pr_map_cache_drop(slide_pr_handle *h, int64_t robot_id) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   if (h->rs == it->second.get()) { h->rs = &h->anon; h->prepared = false; }
-  it->second->release();
+  retire_slot(h, std::move(it->second));
   h->cache.erase(it);
   return SLIDE_PR_OK;
 }
