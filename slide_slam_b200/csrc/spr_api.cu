@@ -162,7 +162,7 @@ struct RefSide {
   spr::JoinRef J;
   bool join_valid = false;
   slide_pr_params join_p{};
-  DevBuf dj_rec0, dj_rec1, dj_cs0, dj_cs1, dj_nbr, dj_labelbox;
+  DevBuf dj_rec0, dj_rec1, dj_xy0, dj_xy1, dj_cs0, dj_cs1, dj_nbr, dj_labelbox;
   DevBuf d_labelbox, d_bitmap, d_rank16, d_rank16b, d_rowrank, d_rowrankb, d_cellref, d_cellrefb, d_cellbase, d_cellbaseb,
       d_reftab, d_refbase, d_cand, d_cand1, d_vbitmap, d_labof, d_ref7;
   // cache bookkeeping (unused by the anonymous slot)
@@ -175,7 +175,7 @@ struct RefSide {
   void release() {
     for (DevBuf *b : {&d_labelbox, &d_bitmap, &d_rank16, &d_rank16b, &d_rowrank, &d_rowrankb, &d_cellref, &d_cellrefb, &d_cellbase,
                       &d_cellbaseb, &d_reftab, &d_refbase, &d_cand, &d_cand1, &d_vbitmap, &d_labof, &d_ref7,
-                      &dj_rec0, &dj_rec1, &dj_cs0, &dj_cs1, &dj_nbr, &dj_labelbox})
+                      &dj_rec0, &dj_rec1, &dj_xy0, &dj_xy1, &dj_cs0, &dj_cs1, &dj_nbr, &dj_labelbox})
       b->release();
   }
 };
@@ -583,6 +583,8 @@ static int join_prepare(slide_pr_handle *h) {
     g_trace.mark("join_ref_build");
     if ((rc = upload(h, rs->dj_rec0, rs->J.rec[0], st))) return rc;
     if ((rc = upload(h, rs->dj_rec1, rs->J.rec[1], st))) return rc;
+    if ((rc = upload(h, rs->dj_xy0, rs->J.xy[0], st))) return rc;
+    if ((rc = upload(h, rs->dj_xy1, rs->J.xy[1], st))) return rc;
     if ((rc = upload(h, rs->dj_cs0, rs->J.cell_start[0], st))) return rc;
     if ((rc = upload(h, rs->dj_cs1, rs->J.cell_start[1], st))) return rc;
     if ((rc = upload(h, rs->dj_nbr, rs->J.nbr, st))) return rc;
@@ -619,6 +621,7 @@ static int join_prepare(slide_pr_handle *h) {
   V.cs = h->dj_cs.as<double>();
   V.nqp = h->JQ.nqp; V.n_groups = n_groups; V.n_yaw = (int32_t)n_yaw; V.n_labels = (int32_t)rs->J.labels.size();
   V.rec[0] = rs->dj_rec0.as<SprJoinRef>(); V.rec[1] = rs->dj_rec1.as<SprJoinRef>();
+  V.xy[0] = rs->dj_xy0.as<double>(); V.xy[1] = rs->dj_xy1.as<double>();
   V.cell_start[0] = rs->dj_cs0.as<uint32_t>(); V.cell_start[1] = rs->dj_cs1.as<uint32_t>();
   V.nbr = rs->dj_nbr.as<SprJoinNbr>();
   V.labelbox = rs->dj_labelbox.as<double>();

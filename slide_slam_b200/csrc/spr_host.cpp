@@ -793,6 +793,7 @@ int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, Join
     std::vector<uint32_t> &pos = d == 0 ? pos0 : pos1;
     for (int i = 0; i < n_ref; i++) if (lab[i] >= 0) pos[i] = fill[key(i)]++;
     J.rec[d].assign(std::max<size_t>(n_kept, 1), SprJoinRef{});
+    J.xy[d].assign(2 * std::max<size_t>(n_kept, 1), 0.0);
   }
   // same-label landmarks with a lower reference index that can match the same point: within 2 x reach
   J.nbr.clear();
@@ -821,6 +822,8 @@ int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, Join
     const SprJoinRef rec{r[1], r[2], r[4], r[5], r[6], off, cnt};
     J.rec[0][pos0[i]] = rec;
     J.rec[1][pos1[i]] = rec;
+    J.xy[0][2 * (size_t)pos0[i]] = r[1]; J.xy[0][2 * (size_t)pos0[i] + 1] = r[2];
+    J.xy[1][2 * (size_t)pos1[i]] = r[1]; J.xy[1][2 * (size_t)pos1[i] + 1] = r[2];
   }
   if (J.nbr.empty()) J.nbr.push_back(SprJoinNbr{});
   return SLIDE_PR_OK;

@@ -141,6 +141,7 @@ bool mat4_rigid_inverse(const double *A, double *Ainv);
 struct JoinRef {
   std::vector<double> labels;        // distinct finite reference labels, ascending
   uvec<SprJoinRef> rec[2];
+  uvec<double> xy[2];                // [records][2]: the coordinates alone, for the candidate filter
   uvec<uint32_t> cell_start[2];      // [n_labels * n_cells + 1]
   uvec<SprJoinNbr> nbr;
   uvec<double> labelbox;             // [n_labels][4]

@@ -87,6 +87,7 @@ __device__ __forceinline__ void spj_quad(const SprJoinView &V, const SpjBlock &B
   }
   const int pitch = B.dir ? V.ncx : V.ncy;
   const SprJoinRef *rec = V.rec[B.dir];
+  const double2 *xy = reinterpret_cast<const double2 *>(V.xy[B.dir]);
   uint32_t n_pairs = 0u;
   for (int bb = b0; __any_sync(SPJ_FULL, bb <= b1); bb += SPJ_BANDS) {
     // record ranges of the lane's next SPJ_BANDS bands, and their places in the warp's flat candidate sequence
@@ -126,7 +127,7 @@ __device__ __forceinline__ void spj_quad(const SprJoinView &V, const SpjBlock &B
         for (uint32_t step = 16 * SPJ_BANDS; step >= 1; step >>= 1)
           if (pre[lo + step] <= w) lo += step;
         e = ((beg[lo] + (w - pre[lo])) << 5) | (lo / SPJ_BANDS);
-        const double2 p = __ldg(reinterpret_cast<const double2 *>(rec + (e >> 5)));
+        const double2 p = __ldg(xy + (e >> 5));
         const SpjQuery &q = sq[e & 31u];
         ok = spj_near(B, q.rx, q.ry, p.x, p.y);
       }

@@ -48,6 +48,7 @@ struct SprJoinView {
   const double *cs;            // [n_yaw][2]
   int32_t nqp, n_groups, n_yaw, n_labels;
   const SprJoinRef *rec[2];    // per direction
+  const double *xy[2];         // per direction: (x, y) of every record again, 16 bytes each: what the candidate filter reads
   const uint32_t *cell_start[2];  // per direction: [n_labels * n_cells + 1] first record of (label, cell)
   const SprJoinNbr *nbr;
   const double *labelbox;      // [n_labels][4] x0, x1, y0, y1 of the label's reference landmarks

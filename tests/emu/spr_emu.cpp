@@ -156,7 +156,7 @@ extern "C" int spr_emu_join_match_maps(const slide_pr_params *p, const double *r
   V.lat = L.lat.data(); V.qrot = qrot.data(); V.gbox = gbox.data(); V.qdims = Q.qdims.data(); V.glabel = glabel.data();
   V.qxy = Q.qxy.data(); V.qlabel = Q.qlabel.data(); V.cs = L.cs.data();
   V.nqp = nqp; V.n_groups = n_groups; V.n_yaw = n_yaw; V.n_labels = (int)J.labels.size();
-  for (int d = 0; d < 2; d++) { V.rec[d] = J.rec[d].data(); V.cell_start[d] = J.cell_start[d].data(); }
+  for (int d = 0; d < 2; d++) { V.rec[d] = J.rec[d].data(); V.xy[d] = J.xy[d].data(); V.cell_start[d] = J.cell_start[d].data(); }
   V.nbr = J.nbr.data(); V.labelbox = J.labelbox.data();
   V.gx0 = J.gx0; V.gy0 = J.gy0; V.inv_w = J.inv_w; V.ncx = J.ncx; V.ncy = J.ncy;
   V.Tstar = J.Tstar; V.Sstar = J.Sstar; V.thr_dim = p->match_threshold_dimension; V.ignore_dim = p->ignore_dimension;

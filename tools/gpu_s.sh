@@ -1,21 +1,10 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_cache.py -m gpu -x -q > gpurun_out/s_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/s_pytest.log
-cat > /tmp/c4.py <<'PY'
-import os, sys, time
-sys.path.insert(0, os.getcwd())
-import numpy as np
-import bench
-from slide_slam_b200 import synth
-from slide_slam_b200.place_recognition import PlaceRecognition
-pr = PlaceRecognition(bench.ROS)
-maps = synth.config_robots(8, 5000)
-pairs = [(i, j) for i in range(8) for j in range(i + 1, 8)]
-for rep in range(4):
-    t0 = time.perf_counter()
-    outs = pr.findTransformationBatch(maps, pairs)
-    dt = time.perf_counter() - t0
-    print("batch", rep, "s", dt, "pairs/s", 28 / dt, "kernel_ms_sum", sum(o.match.kernel_ms for o in outs), "prepare_ms_sum", sum(o.match.prepare_ms for o in outs), flush=True)
-PY
-timeout 300 python /tmp/c4.py > gpurun_out/s_c4.log 2>&1
+rm -f gpurun_out/s_ab.log
+timeout 600 python -m pytest tests/test_gpu_join.py -m gpu -x -q -k "not config3 and not config4 and not config5" > gpurun_out/s_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/s_pytest.log
+timeout 200 python tools/ab_search.py 2 10 4 >> gpurun_out/s_ab.log 2>&1
+timeout 300 python tools/ab_search.py 3 2 4 >> gpurun_out/s_ab.log 2>&1
+for c in 4 5; do timeout 200 python tools/ncu_cfg_target.py $c 2>&1 | tail -1 >> gpurun_out/s_ab.log; done
+M=smsp__inst_executed.sum,gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,sm__inst_executed.avg.per_cycle_elapsed,l1tex__t_sector_hit_rate.pct
+timeout 300 ncu --metrics $M --clock-control none -k regex:spr_join_score -c 1 --csv --log-file gpurun_out/s_join_c2.csv python tools/ncu_step_target.py join 2 > gpurun_out/s_ncu.log 2>&1
