@@ -122,11 +122,12 @@ __device__ __forceinline__ void spj_quad(const SprJoinView &V, const SpjBlock &B
       uint32_t e = 0u;
       bool ok = false;
       if (w < total) {
-        uint32_t lo = 0u;   // the last range that starts at or before candidate w (empty ranges share their start with the next one)
+        const uint32_t *rp = pre;   // -> the last range that starts at or before candidate w (empty ranges share their start with the next one)
 #pragma unroll
         for (uint32_t step = 16 * SPJ_BANDS; step >= 1; step >>= 1)
-          if (pre[lo + step] <= w) lo += step;
-        e = ((beg[lo] + (w - pre[lo])) << 5) | (lo / SPJ_BANDS);
+          if (rp[step] <= w) rp += step;
+        const uint32_t lo = (uint32_t)(rp - pre);
+        e = ((rp[32 * SPJ_BANDS + 1] + (w - rp[0])) << 5) | (lo / SPJ_BANDS);   // beg = pre + 32 * SPJ_BANDS + 1
         const double2 p = __ldg(xy + (e >> 5));
         const SpjQuery &q = sq[e & 31u];
         ok = spj_near(B, q.rx, q.ry, p.x, p.y);
@@ -173,7 +174,6 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
     const uint32_t b = (uint32_t)K.shard_index + (uint32_t)(item % n_blocks_local) * (uint32_t)K.shard_count;
     const SprJoinBlock blk = V.blocks[b];
     const SpjBlock B = spj_block(V, blk);
-    const int n_slots = B.nx * B.ny;
     for (int w = tid; w < (2 * B.stride + 3) / 4; w += SPJ_THREADS) reinterpret_cast<uint4 *>(s_tile)[w] = make_uint4(0u, 0u, 0u, 0u);
 
     const SprJoinBox *gb = V.gbox + (size_t)a * (size_t)V.n_groups;
@@ -243,7 +243,6 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
         atomicMax(K.best_key, spr_make_key(c, ord * (unsigned long long)V.n_yaw + (unsigned long long)a));
       }
     }
-    (void)n_slots;
   }
 }
 
