@@ -186,6 +186,16 @@ int slide_pr_find_intra_loop_closure(slide_pr_handle *h, const double *measureme
                                      const double *candidate_pose16, double *tf16,
                                      slide_pr_tf_result *out /* may be NULL */);
 
+/* Several candidate key poses for ONE set of measurements (the reference tries one candidate per attempt,
+ * sloamNode.cpp:355-486).  submaps7[k] (n_subs[k] rows) and candidate_poses16 + 16 k describe
+ * candidate k; out[k] and tf16_out + 16 k receive what slide_pr_find_intra_loop_closure returns for it
+ * (out[k].found tells whether tf16_out + 16 k was written).  The candidates' searches are enqueued back to back --
+ * the host prepares candidate k + 1 while the GPU scores candidate k -- and the host waits once for all of them. */
+int slide_pr_find_intra_loop_closure_batch(slide_pr_handle *h, const double *measurements7, int32_t n_meas,
+                                           const double *const *submaps7, const int32_t *n_subs, const double *query_pose16,
+                                           const double *candidate_poses16, int32_t n_cand, double *tf16_out,
+                                           slide_pr_tf_result *out /* n_cand */);
+
 /* PlaceRecognition::solveLSQ (PR.h:127-130, PR.cpp:632-695): Kabsch on k matched pairs.
  * tgt3 = map objects, src3 = detection objects (k x 3). */
 int slide_pr_solve_lsq(const double *tgt3, const double *src3, int32_t k, double *xyz_yaw4,

@@ -24,7 +24,7 @@ EXPORTS = [
     "slide_pr_abi_version", "slide_pr_deg2rad", "slide_pr_default_params", "slide_pr_create",
     "slide_pr_destroy", "slide_pr_set_params", "slide_pr_last_error", "slide_pr_match_maps",
     "slide_pr_prepare", "slide_pr_search", "slide_pr_lattice_info", "slide_pr_extract", "slide_pr_find_transformation",
-    "slide_pr_find_inter_loop_closure", "slide_pr_find_intra_loop_closure", "slide_pr_solve_lsq",
+    "slide_pr_find_inter_loop_closure", "slide_pr_find_intra_loop_closure", "slide_pr_find_intra_loop_closure_batch", "slide_pr_solve_lsq",
     "slide_pr_get_xyz_yaw_from_tf", "slide_pr_find_transformation_batch", "slide_pr_pack_record",
     "slide_pr_merge_records", "slide_pr_match_triangles", "slide_pr_score_hypotheses",
     "slide_pr_match_triangles_labeled", "slide_pr_estimate_tf", "slide_pr_triangle_hypotheses",
@@ -201,6 +201,8 @@ def lib():
                                                    C.POINTER(TfResult)]
     L.slide_pr_find_intra_loop_closure.argtypes = [C.c_void_p, _dp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp,
                                                    C.POINTER(TfResult)]
+    L.slide_pr_find_intra_loop_closure_batch.argtypes = [C.c_void_p, _dp, C.c_int32, C.POINTER(_dp), _ip, _dp, _dp, C.c_int32, _dp,
+                                                         C.POINTER(TfResult)]
     L.slide_pr_solve_lsq.argtypes = [_dp, _dp, C.c_int32, _dp, _dp]
     L.slide_pr_get_xyz_yaw_from_tf.argtypes = [_dp, _dp]
     L.slide_pr_find_transformation_batch.argtypes = [C.c_void_p, C.POINTER(_dp), _ip, C.c_int32, _ip, _ip,

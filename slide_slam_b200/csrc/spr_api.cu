@@ -240,6 +240,9 @@ struct slide_pr_handle {
   SprView V{};
   unsigned long long gen_cap = 0;      // capacity (entries) of the generator's match-key buffer, kept across calls
   SprClipper *clipper = nullptr;       // SlideGraph half: device-resident CLIPPER problem (created on first use)
+  DevBuf d_batch_keys, d_batch_match;  // batched intra search: one best key / one correspondence row per candidate
+  spr::uvec<unsigned long long> h_batch_keys;
+  spr::uvec<int32_t> h_batch_match;
   spr::uvec<int32_t> h_match;          // page-locked D2H targets
   spr::uvec<unsigned long long> h_scalars;
 };
@@ -282,6 +285,16 @@ static int upload_raw(slide_pr_handle *h, DevBuf &b, const void *src, size_t byt
   if (bytes) SPR_CUDA(h, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
   h->h2d_bytes += (int64_t)bytes;
   return SLIDE_PR_OK;
+}
+
+// A slot that leaves the cache keeps its buffers (page-locked host vectors, device allocations) in a small
+// pool: allocating them afresh for every batch of maps costs more than the searches themselves.
+static void retire_slot(slide_pr_handle *h, std::unique_ptr<RefSide> slot) {
+  slot->rows_valid = false; slot->ref_index_valid = false; slot->ranks_pending = false;
+  slot->join_valid = false; slot->ref7_uploaded = false;
+  slot->robot_id = -1; slot->version = 0; slot->n_rows = 0;
+  if (h->free_slots.size() < 16) h->free_slots.push_back(std::move(slot));
+  else slot->release();
 }
 
 extern "C" {
@@ -364,7 +377,7 @@ void slide_pr_destroy(slide_pr_handle *h) {
                     &h->d_qrotq, &h->d_qrotq_yx, &h->d_work, &h->d_qry7, &h->d_best, &h->d_counts, &h->d_match, &h->d_stats, &h->d_hyps,
                     &h->d_tri, &h->d_tri_out, &h->d_ubplanes, &h->d_itemub, &h->d_seed, &h->d_canditems, &h->d_candcount, &h->d_dgitems,
                     &h->d_dgcount, &h->dj_lat, &h->dj_cs, &h->dj_qxy, &h->dj_qdims, &h->dj_qlabel, &h->dj_glabel, &h->dj_qrot,
-                    &h->dj_gbox, &h->dj_blocks})
+                    &h->dj_gbox, &h->dj_blocks, &h->d_batch_keys, &h->d_batch_match})
     b->release();
   h->anon.release();
   for (auto &kv : h->cache) kv.second->release();
@@ -1502,6 +1515,32 @@ int slide_pr_find_inter_loop_closure(slide_pr_handle *h, const double *ref7, int
   return SLIDE_PR_OK;
 }
 
+// measurements (query's local frame) into the map frame, PR.cpp:421-439
+static void intra_move_measurements(const double *meas7, int32_t n_meas, const double *P, std::vector<double> &moved) {
+  moved.resize((size_t)n_meas * 7);
+  for (int i = 0; i < n_meas; i++) {
+    const double *m = meas7 + 7 * (size_t)i;
+    double v[4];
+    for (int r = 0; r < 4; r++) v[r] = ((P[r * 4] * m[1] + P[r * 4 + 1] * m[2]) + P[r * 4 + 2] * m[3]) + P[r * 4 + 3] * 1.0;
+    double *o = moved.data() + 7 * (size_t)i;
+    o[0] = m[0]; o[1] = v[0] / v[3]; o[2] = v[1] / v[3]; o[3] = v[2] / v[3];
+    o[4] = m[4]; o[5] = m[5]; o[6] = m[6];
+  }
+}
+
+// loop-closure transform from the lattice / LSQ result and the two poses, PR.cpp:455-494
+static void intra_compose_tf(const slide_pr_tf_result *out, const double *query_pose16, const double *candidate_pose16, double *tf16) {
+  const double yaw = out->xyz_yaw[3];
+  double lc[16] = {0};
+  lc[0] = std::cos(yaw); lc[1] = -std::sin(yaw); lc[4] = std::sin(yaw); lc[5] = std::cos(yaw);
+  lc[10] = 1; lc[15] = 1;
+  lc[3] = out->xyz_yaw[0]; lc[7] = out->xyz_yaw[1]; lc[11] = 0.0;
+  double cinv[16], drift[16];
+  spr::mat4_rigid_inverse(candidate_pose16, cinv);
+  spr::mat4_mul(cinv, query_pose16, drift);                            // PR.cpp:478
+  spr::mat4_mul(drift, lc, tf16);                                      // PR.cpp:483-494
+}
+
 int slide_pr_find_intra_loop_closure(slide_pr_handle *h, const double *meas7, int32_t n_meas, const double *submap7,
                                      int32_t n_sub, const double *query_pose16, const double *candidate_pose16,
                                      double *tf16, slide_pr_tf_result *out_opt) {
@@ -1510,30 +1549,151 @@ int slide_pr_find_intra_loop_closure(slide_pr_handle *h, const double *meas7, in
   std::memset(out, 0, sizeof(*out));
   if (n_meas == 0 || n_sub == 0) return SLIDE_PR_NOT_FOUND;            // PR.cpp:395-398
   if (n_meas < 4) return SLIDE_PR_NOT_FOUND;                           // PR.cpp:400-403
-  std::vector<double> moved((size_t)n_meas * 7);
-  const double *P = query_pose16;
-  for (int i = 0; i < n_meas; i++) {                                   // PR.cpp:421-439
-    const double *m = meas7 + 7 * (size_t)i;
-    double v[4];
-    for (int r = 0; r < 4; r++) v[r] = ((P[r * 4] * m[1] + P[r * 4 + 1] * m[2]) + P[r * 4 + 2] * m[3]) + P[r * 4 + 3] * 1.0;
-    double *o = moved.data() + 7 * (size_t)i;
-    o[0] = m[0]; o[1] = v[0] / v[3]; o[2] = v[1] / v[3]; o[3] = v[2] / v[3];
-    o[4] = m[4]; o[5] = m[5]; o[6] = m[6];
-  }
+  std::vector<double> moved;
+  intra_move_measurements(meas7, n_meas, query_pose16, moved);
   const int32_t saved = h->p.inter_loop_closure;
   h->p.inter_loop_closure = 0;  // the caller's intra instance has inter_loop_closure = false (sloamNode.cpp:23)
   const int rc = slide_pr_find_transformation(h, submap7, n_sub, moved.data(), n_meas, nullptr, nullptr, out);
   h->p.inter_loop_closure = saved;
   if (rc != SLIDE_PR_OK) return rc;
-  const double yaw = out->xyz_yaw[3];
-  double lc[16] = {0};                                                 // PR.cpp:455-470
-  lc[0] = std::cos(yaw); lc[1] = -std::sin(yaw); lc[4] = std::sin(yaw); lc[5] = std::cos(yaw);
-  lc[10] = 1; lc[15] = 1;
-  lc[3] = out->xyz_yaw[0]; lc[7] = out->xyz_yaw[1]; lc[11] = 0.0;
-  double cinv[16], drift[16];
-  spr::mat4_rigid_inverse(candidate_pose16, cinv);
-  spr::mat4_mul(cinv, query_pose16, drift);                            // PR.cpp:478
-  spr::mat4_mul(drift, lc, tf16);                                      // PR.cpp:483-494
+  intra_compose_tf(out, query_pose16, candidate_pose16, tf16);
+  return SLIDE_PR_OK;
+}
+
+// Several candidate key poses for ONE set of measurements (the reference tries one
+// candidate per attempt, sloamNode.cpp:355-486).  The candidates' searches are enqueued back to back on the
+// handle's stream -- the host prepares candidate k + 1 while the GPU scores candidate k -- and the host waits
+// once for all of them: one synchronisation for the searches, one for the correspondences.
+int slide_pr_find_intra_loop_closure_batch(slide_pr_handle *h, const double *meas7, int32_t n_meas, const double *const *submaps7,
+                                           const int32_t *n_subs, const double *query_pose16, const double *candidate_poses16,
+                                           int32_t n_cand, double *tf16_out, slide_pr_tf_result *out) {
+  if (!h || !out || !tf16_out || !query_pose16 || !candidate_poses16 || n_cand < 0 || (n_cand > 0 && (!submaps7 || !n_subs))) return SLIDE_PR_ERR_INVALID;
+  if (n_meas < 0 || (n_meas > 0 && !meas7)) { h->err = "bad measurement arguments"; return SLIDE_PR_ERR_INVALID; }
+  for (int k = 0; k < n_cand; k++) {
+    std::memset(&out[k], 0, sizeof(out[k]));
+    if (n_subs[k] < 0 || (n_subs[k] > 0 && !submaps7[k])) { h->err = "bad submap arguments"; return SLIDE_PR_ERR_INVALID; }
+  }
+  if (n_cand == 0 || n_meas < 4) return SLIDE_PR_OK;                   // PR.cpp:395-403: no closure for any candidate
+  const int32_t saved = h->p.inter_loop_closure;
+  struct Restore { slide_pr_handle *h; int32_t v; ~Restore() { h->p.inter_loop_closure = v; } } restore{h, saved};
+  h->p.inter_loop_closure = 0;  // the caller's intra instance has inter_loop_closure = false (sloamNode.cpp:23)
+  const double hx = h->p.match_x_half_range_intra, hy = h->p.match_y_half_range_intra;   // PR.cpp:808-810
+  const bool pipelined = h->p.exhaustive_search == 0 && !h->force_exhaustive && !h->env_lattice && n_meas <= 65535 && n_cand <= 4096 &&
+                         !budget_may_bind(h->p, hx, hy, h->p.match_yaw_half_range_intra, n_meas);
+  if (!pipelined) {   // the lattice kernels keep per-search state on the handle: one candidate at a time
+    h->p.inter_loop_closure = saved;
+    for (int k = 0; k < n_cand; k++) {
+      const int rc = slide_pr_find_intra_loop_closure(h, meas7, n_meas, submaps7[k], n_subs[k], query_pose16, candidate_poses16 + 16 * (size_t)k,
+                                                      tf16_out + 16 * (size_t)k, &out[k]);
+      if (rc < 0) return rc;
+    }
+    return SLIDE_PR_OK;
+  }
+  SPR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  std::vector<double> moved;
+  intra_move_measurements(meas7, n_meas, query_pose16, moved);
+  DevBuf &d_keys = h->d_batch_keys, &d_matches = h->d_batch_match;
+  SPR_CUDA(h, d_keys.ensure((size_t)n_cand * sizeof(unsigned long long)));
+  SPR_CUDA(h, d_matches.ensure((size_t)n_cand * (size_t)n_meas * sizeof(int32_t)));
+  SPR_CUDA(h, cudaMemsetAsync(d_keys.p, 0, (size_t)n_cand * sizeof(unsigned long long), st));
+  if (h->h_batch_keys.size() < (size_t)n_cand) h->h_batch_keys.resize((size_t)n_cand);
+  if (h->h_batch_match.size() < (size_t)n_cand * (size_t)n_meas) h->h_batch_match.resize((size_t)n_cand * (size_t)n_meas);
+  std::vector<std::unique_ptr<RefSide>> slots((size_t)n_cand);
+  auto give_back = [&]() {
+    cudaStreamSynchronize(st);
+    h->rs = &h->anon; h->prepared = false;
+    for (auto &sl : slots) if (sl) retire_slot(h, std::move(sl));
+  };
+  int rc = SLIDE_PR_OK;
+  bool work_zeroed = false;
+  int n_yaw = 0;
+  bool sanity = false;
+  for (int k = 0; k < n_cand && rc == SLIDE_PR_OK && !sanity; k++) {
+    if (n_subs[k] == 0) continue;                                      // PR.cpp:395-398
+    if (!h->free_slots.empty()) { slots[k] = std::move(h->free_slots.back()); h->free_slots.pop_back(); }
+    else slots[k].reset(new RefSide());
+    RefSide &E = *slots[k];
+    E.cached_ref.assign(submaps7[k], submaps7[k] + (size_t)n_subs[k] * 7);
+    E.rows_valid = true; E.ref_index_valid = false; E.ranks_pending = false; E.join_valid = false; E.ref7_uploaded = false;
+    E.n_rows = n_subs[k]; E.shifted = false;
+    if ((rc = prepare_impl(h, &E, true, E.cached_ref.data(), n_subs[k], moved.data(), n_meas, hx, hy)) != SLIDE_PR_OK) break;
+    if (h->L.status == SLIDE_PR_SANITY_RETURN) { sanity = true; break; }   // the lattice is the same for every candidate
+    if (!h->join_ready) { h->err = "internal: pair-join structures missing in the batched intra search"; rc = SLIDE_PR_ERR_INTERNAL; break; }
+    n_yaw = (int)h->L.yaw.size();
+    if (!work_zeroed) {   // after the first prepare: d_work exists
+      if (cudaMemsetAsync(h->d_work.p, 0, (size_t)n_cand * sizeof(unsigned long long), st) != cudaSuccess) { h->err = "cudaMemsetAsync"; rc = SLIDE_PR_ERR_CUDA; break; }
+      work_zeroed = true;
+    }
+    SprJoinLaunch K{};
+    K.work_counter = h->d_work.as<unsigned long long>() + k;
+    K.best_key = d_keys.as<unsigned long long>() + k;
+    K.ord_begin = 0ull; K.ord_end = (unsigned long long)h->L.n_translations;
+    cudaError_t e = cudaSuccess;
+    if (h->JV.nqp > 0 && n_yaw > 0) e = spr_launch_join_rotate(h->JV, h->dj_qrot.as<double>(), h->dj_gbox.as<SprJoinBox>(), st);
+    if (e == cudaSuccess && n_yaw > 0 && !h->j_blocks.empty()) e = spr_launch_join_score(h->JV, K, h->sm_count, st);
+    if (e != cudaSuccess) { h->err = std::string("batched intra search: ") + cudaGetErrorString(e); rc = SLIDE_PR_ERR_CUDA; break; }
+    fill_result_header(h, &out[k].match);
+    out[k].match.search_mode = 2;
+    out[k].match.gpu_launches = 2;
+    out[k].match.rings_scored = h->L.rings;
+    out[k].match.hypotheses_scored = (int64_t)h->L.n_translations * n_yaw;
+  }
+  if (rc != SLIDE_PR_OK) { give_back(); return rc; }
+  if (sanity) {   // MatchMaps' early return for every candidate: nothing found (PR.cpp:169-175, 819, 849)
+    for (int k = 0; k < n_cand; k++) { out[k].match.status = SLIDE_PR_SANITY_RETURN; out[k].half_x = hx; out[k].half_y = hy; }
+    give_back();
+    return SLIDE_PR_OK;
+  }
+  if (cudaMemcpyAsync(h->h_batch_keys.data(), d_keys.p, (size_t)n_cand * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess) { h->err = "batched intra search: copy of the results failed"; give_back(); return SLIDE_PR_ERR_CUDA; }
+  // correspondences of every candidate's winner: all extraction kernels, then one wait
+  for (int k = 0; k < n_cand; k++) {
+    if (!slots[k]) continue;
+    const unsigned long long key = h->h_batch_keys[k];
+    slide_pr_match_result &m = out[k].match;
+    if (key == 0ull || n_yaw <= 0) continue;
+    m.best_num_inliers = spr_key_count(key);
+    m.best_hyp_index = spr_key_index(key);
+    double tx, ty;
+    int ring;
+    if (!spr::translation_of(h->L, (uint64_t)(m.best_hyp_index / n_yaw), &tx, &ty, &ring)) { h->err = "hypothesis index out of range"; give_back(); return SLIDE_PR_ERR_INTERNAL; }
+    const int a = (int)(m.best_hyp_index % n_yaw);
+    const double c = h->L.cs[2 * a], s = h->L.cs[2 * a + 1];
+    m.R_t[0] = c; m.R_t[1] = -s; m.R_t[2] = tx;  // PR.cpp:246-251
+    m.R_t[3] = s; m.R_t[4] = c;  m.R_t[5] = ty;
+    m.R_t[6] = 0; m.R_t[7] = 0;  m.R_t[8] = 1;
+    const cudaError_t e = spr_launch_extract(slots[k]->d_ref7.as<double>(), n_subs[k], h->d_qry7.as<double>(), n_meas, c, s, tx, ty, h->Tstar, h->Sstar,
+                                             h->p.match_threshold_dimension, h->p.ignore_dimension, d_matches.as<int32_t>() + (size_t)k * n_meas, st);
+    if (e != cudaSuccess) { h->err = std::string("batched intra search: ") + cudaGetErrorString(e); give_back(); return SLIDE_PR_ERR_CUDA; }
+    m.gpu_launches += 1;
+  }
+  if (cudaMemcpyAsync(h->h_batch_match.data(), d_matches.p, (size_t)n_cand * (size_t)n_meas * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess) { h->err = "batched intra search: copy of the correspondences failed"; give_back(); return SLIDE_PR_ERR_CUDA; }
+  std::vector<int32_t> ri((size_t)std::max(n_meas, 1)), qi((size_t)std::max(n_meas, 1));
+  const double zero2[2] = {0, 0};
+  for (int k = 0; k < n_cand; k++) {
+    out[k].half_x = hx; out[k].half_y = hy; out[k].yaw_half = h->p.match_yaw_half_range_intra;
+    if (!slots[k]) continue;
+    slide_pr_match_result &m = out[k].match;
+    int n = 0;
+    if (m.best_hyp_index >= 0) {
+      const int32_t *mt = h->h_batch_match.data() + (size_t)k * n_meas;
+      for (int j = 0; j < n_meas; j++)
+        if (mt[j] >= 0) { ri[n] = mt[j]; qi[n] = j; n++; }
+      if (n != m.best_num_inliers) {   // brute-force recount of the winner must agree with the scorer
+        char buf[160];
+        std::snprintf(buf, sizeof(buf), "self-check failed: candidate %d, counted %d != brute-force %d for hypothesis %lld", k, m.best_num_inliers, n, (long long)m.best_hyp_index);
+        h->err = buf;
+        give_back();
+        return SLIDE_PR_ERR_INTERNAL;
+      }
+    }
+    m.n_matched = n;
+    if (finish_transformation(h->p, slots[k]->cached_ref.data(), moved.data(), zero2, zero2, ri.data(), qi.data(), &out[k]) == SLIDE_PR_OK)
+      intra_compose_tf(&out[k], query_pose16, candidate_poses16 + 16 * (size_t)k, tf16_out + 16 * (size_t)k);
+  }
+  give_back();
   return SLIDE_PR_OK;
 }
 
@@ -1543,16 +1703,6 @@ int slide_pr_find_intra_loop_closure(slide_pr_handle *h, const double *meas7, in
 // over once per version: its centroid-shifted rows stay page-locked on the host and on the device, and
 // the reference-side index (occupancy bitmaps, rank tables) is built the first time the map is searched
 // AS A REFERENCE and reused by every later pair until the version changes.
-// A slot that leaves the cache keeps its buffers (page-locked host vectors, device allocations) in a small
-// pool: allocating them afresh for every batch of maps costs more than the searches themselves.
-static void retire_slot(slide_pr_handle *h, std::unique_ptr<RefSide> slot) {
-  slot->rows_valid = false; slot->ref_index_valid = false; slot->ranks_pending = false;
-  slot->join_valid = false; slot->ref7_uploaded = false;
-  slot->robot_id = -1; slot->version = 0; slot->n_rows = 0;
-  if (h->free_slots.size() < 16) h->free_slots.push_back(std::move(slot));
-  else slot->release();
-}
-
 int slide_pr_map_cache_put(slide_pr_handle *h, int64_t robot_id, uint64_t version, const double *rows7, int32_t n) {
   if (!h || n < 0 || (n > 0 && !rows7)) return SLIDE_PR_ERR_INVALID;
   SPR_CUDA(h, cudaSetDevice(h->device));

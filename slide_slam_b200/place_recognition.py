@@ -375,6 +375,23 @@ class PlaceRecognition:
         self.last = out
         return rc == capi.OK, tf.reshape(4, 4)
 
+    def findIntraLoopClosureBatch(self, measurements, submaps, query_pose, candidate_poses):
+        """Several candidate key poses for one set of measurements (slide_pr_find_intra_loop_closure_batch): submaps =
+        list of n x 7 arrays, candidate_poses = list of 4x4 matrices.  Returns [(closure_found, tfFromQuery2Candidate,
+        TfResult), ...] -- per candidate what findIntraLoopClosure returns."""
+        meas = capi.as_rows7(measurements)
+        rows = [capi.as_rows7(m) for m in submaps]
+        k = len(rows)
+        ptrs = (C.POINTER(C.c_double) * max(k, 1))(*[capi.dptr(r) for r in rows])
+        sizes = np.array([len(r) for r in rows] or [0], np.int32)
+        qp = np.ascontiguousarray(query_pose, np.float64).reshape(16)
+        cps = np.ascontiguousarray(np.array(candidate_poses, np.float64).reshape(max(k, 1) if k else 0, 16) if k else np.zeros((1, 16)))
+        tfs = np.zeros((max(k, 1), 16))
+        out = (capi.TfResult * max(k, 1))()
+        self._check(self._lib.slide_pr_find_intra_loop_closure_batch(self._h, capi.dptr(meas), len(meas), ptrs, capi.iptr(sizes), capi.dptr(qp),
+                                                                     capi.dptr(cps), k, capi.dptr(tfs), out))
+        return [(bool(out[i].found), tfs[i].reshape(4, 4).copy(), out[i]) for i in range(k)]
+
     # -- PlaceRecognition::solveLSQ / getxyzYawfromTF (PR.cpp:632-711) --------------------------
     def solveLSQ(self, map_objects_matched, detection_objects_matched):
         tgt = np.ascontiguousarray(map_objects_matched, np.float64).reshape(-1, 3)

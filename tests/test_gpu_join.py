@@ -275,3 +275,46 @@ def test_config5_streaming_queries_against_50000_landmarks_full_size():
         assert bool(info.match.reuse & 2) == (k > 0)          # the reference map's join index is built once
     pr.close()
     _check_against_oracle_and_lattice(big, queries[0], 3, lattice_exhaustive=False)
+
+
+def test_intra_loop_closure_batch_equals_single_calls(gold):
+    """slide_pr_find_intra_loop_closure_batch (candidates enqueued back to back, one wait): per candidate exactly what
+    findIntraLoopClosure returns -- found flag, inlier count, winner, transform -- including a candidate without a
+    closure, an empty submap and a repeated candidate; and the lattice-engine fallback of the same entry."""
+    maps, cases, _ = gold
+    ci = cases["prtest_intra_lsq1"]
+
+    def pose(yaw, t):
+        m = np.eye(4); m[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]; m[:3, 3] = t
+        return m
+    qp = pose(0.3, [1.0, -2.0, 0.1])
+    meas_local = maps[ci["qry"]].copy()
+    inv = np.linalg.inv(qp)
+    meas_local[:, 1:4] = (meas_local[:, 1:4] - qp[:3, 3]) @ inv[:3, :3].T
+    sub = maps[ci["ref"]]
+    rng = np.random.default_rng(5)
+    far = sub.copy(); far[:, 1:3] += 500.0                      # nothing within reach: no closure
+    jitter = sub.copy(); jitter[:, 1:3] += rng.normal(0, 0.05, (len(sub), 2))
+    fewer = sub[: len(sub) // 2].copy()
+    submaps = [sub, far, np.zeros((0, 7)), jitter, fewer, sub]
+    cposes = [pose(-0.2, [0.5, 0.5, 0.0]), np.eye(4), np.eye(4), pose(0.1, [0.0, 1.0, 0.0]), pose(0.0, [2.0, 0.0, 0.0]), pose(-0.2, [0.5, 0.5, 0.0])]
+    for engine in (None, "lattice"):
+        pri = make_pr(ci["params"], engine=engine) if engine else make_pr(ci["params"])
+        single = []
+        for s_, c_ in zip(submaps, cposes):
+            f, tf = pri.findIntraLoopClosure(meas_local, s_, qp, c_)
+            single.append((f, tf, pri.last.best_num_inliers, pri.last.match.best_hyp_index))
+        batch = pri.findIntraLoopClosureBatch(meas_local, submaps, qp, cposes)
+        assert len(batch) == len(submaps)
+        assert [b[0] for b in batch] == [s[0] for s in single]
+        assert batch[0][0] and batch[5][0] and not batch[1][0] and not batch[2][0]
+        for (bf, btf, bo), (sf, stf, sn, si) in zip(batch, single):
+            assert bf == sf
+            if sf:
+                assert bo.best_num_inliers == sn and bo.match.best_hyp_index == si
+                assert btf.tolist() == stf.tolist()          # same code path downstream of the search: bit-identical
+        # the handle keeps working for ordinary calls afterwards
+        f, tf = pri.findIntraLoopClosure(meas_local, sub, qp, cposes[0])
+        assert f and tf.tolist() == single[0][1].tolist()
+        assert pri.findIntraLoopClosureBatch(meas_local, [], qp, []) == []
+        pri.close()

@@ -1,10 +1,29 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-rm -f gpurun_out/s_ab.log
-timeout 600 python -m pytest tests/test_gpu_join.py -m gpu -x -q -k "not config3 and not config4 and not config5" > gpurun_out/s_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/s_pytest.log
-timeout 200 python tools/ab_search.py 2 10 4 >> gpurun_out/s_ab.log 2>&1
-timeout 300 python tools/ab_search.py 3 2 4 >> gpurun_out/s_ab.log 2>&1
-for c in 4 5; do timeout 200 python tools/ncu_cfg_target.py $c 2>&1 | tail -1 >> gpurun_out/s_ab.log; done
-M=smsp__inst_executed.sum,gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,sm__inst_executed.avg.per_cycle_elapsed,l1tex__t_sector_hit_rate.pct
-timeout 300 ncu --metrics $M --clock-control none -k regex:spr_join_score -c 1 --csv --log-file gpurun_out/s_join_c2.csv python tools/ncu_step_target.py join 2 > gpurun_out/s_ncu.log 2>&1
+cat > /tmp/intra.py <<'PY'
+import os, sys, time
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import numpy as np
+import spr_helpers as H
+from slide_slam_b200.place_recognition import PlaceRecognition
+maps, cases = H.golden_maps(), H.golden_cases()
+ci = cases["prtest_intra_lsq1"]
+pr = PlaceRecognition(H.rosparams_from_golden(ci["params"])); pr.inter_loop_closure = False
+meas, sub = maps[ci["qry"]], maps[ci["ref"]]
+K = 16
+rng = np.random.default_rng(0)
+subs = []
+for k in range(K):
+    t = sub.copy(); t[:, 1:3] += rng.normal(0, 0.02, (len(sub), 2)); subs.append(t)
+poses = [np.eye(4)] * K
+for rep in range(3):
+    t0 = time.perf_counter()
+    for s in subs: pr.findIntraLoopClosure(meas, s, np.eye(4), np.eye(4))
+    t1 = time.perf_counter()
+    out = pr.findIntraLoopClosureBatch(meas, subs, np.eye(4), poses)
+    t2 = time.perf_counter()
+    print(f"{K} candidates: single calls {(t1-t0)*1e3:.2f} ms, batch {(t2-t1)*1e3:.2f} ms, found {sum(o[0] for o in out)}", flush=True)
+PY
+timeout 120 python /tmp/intra.py > gpurun_out/s_intra.log 2>&1
+SLIDE_PR_TRACE=1 timeout 120 python /tmp/intra.py 2>&1 | tail -30 > gpurun_out/s_intra_trace.log
