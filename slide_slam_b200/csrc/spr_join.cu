@@ -218,15 +218,33 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
     // ---- scan: slots of the block inside the requested slice of ordinals; max count, smallest ordinal
     int s_lo, s_hi;
     spj_slice(blk, K.ord_begin, K.ord_end, &s_lo, &s_hi);
-    const float inv_ny = 1.0f / (float)B.ny;
     uint32_t best = 0u;   // (count + 1) << SPJ_SLOT_BITS | (SPJ_MAX_SLOTS - 1 - slot): max count, then smallest slot = smallest ordinal
-    for (int s = s_lo + tid; s < s_hi; s += SPJ_THREADS) {
-      const int i = __float2int_rd(((float)s + 0.5f) * inv_ny), j = s - i * B.ny;   // exact: s < 2^13
-      const uint32_t c = spj_total(s_tile, B, i, j);
-      best = max(best, ((c + 1u) << SPJ_SLOT_BITS) | (uint32_t)(SPJ_MAX_SLOTS - 1 - s));
-      if (K.counts_out) {
-        const unsigned long long ord = (unsigned long long)blk.ord0 + (unsigned long long)i * blk.row_stride + (unsigned long long)j;
-        K.counts_out[(ord - K.ord_begin) * (unsigned long long)V.n_yaw + (unsigned long long)a] = (int32_t)c;
+    if (!K.counts_out && s_lo == 0 && s_hi == B.nx * B.ny) {
+      // the whole block (the usual case): two samples per step -- word n of array 0 holds samples (2n, 2n + 1) of its
+      // row, array 1 contributes the high half of its word n to sample 2n and the low half of word n + 1 to 2n + 1
+      const float inv_nwy = 1.0f / (float)B.nwy;
+      for (int w = tid; w < B.stride; w += SPJ_THREADS) {
+        const int i = __float2int_rd(((float)w + 0.5f) * inv_nwy), n = w - i * B.nwy, j = 2 * n;   // exact: w < 2^13
+        if (j >= B.ny) continue;   // the spare word of an even-length row
+        const uint32_t w0 = s_tile[w], w1 = s_tile[B.stride + w];
+        const int s = i * B.ny + j;
+        const uint32_t c0 = (w0 & 0xffffu) + (w1 >> 16);
+        best = max(best, ((c0 + 1u) << SPJ_SLOT_BITS) | (uint32_t)(SPJ_MAX_SLOTS - 1 - s));
+        if (j + 1 < B.ny) {
+          const uint32_t c1 = (w0 >> 16) + (s_tile[B.stride + w + 1] & 0xffffu);
+          best = max(best, ((c1 + 1u) << SPJ_SLOT_BITS) | (uint32_t)(SPJ_MAX_SLOTS - 2 - s));
+        }
+      }
+    } else {
+      const float inv_ny = 1.0f / (float)B.ny;
+      for (int s = s_lo + tid; s < s_hi; s += SPJ_THREADS) {
+        const int i = __float2int_rd(((float)s + 0.5f) * inv_ny), j = s - i * B.ny;   // exact: s < 2^13
+        const uint32_t c = spj_total(s_tile, B, i, j);
+        best = max(best, ((c + 1u) << SPJ_SLOT_BITS) | (uint32_t)(SPJ_MAX_SLOTS - 1 - s));
+        if (K.counts_out) {
+          const unsigned long long ord = (unsigned long long)blk.ord0 + (unsigned long long)i * blk.row_stride + (unsigned long long)j;
+          K.counts_out[(ord - K.ord_begin) * (unsigned long long)V.n_yaw + (unsigned long long)a] = (int32_t)c;
+        }
       }
     }
     best = __reduce_max_sync(SPJ_FULL, best);
