@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cfloat>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -642,8 +643,13 @@ static int join_prepare(slide_pr_handle *h) {
   V.ncx = rs->J.ncx; V.ncy = rs->J.ncy;
   V.Tstar = rs->J.Tstar; V.Sstar = rs->J.Sstar; V.thr_dim = h->p.match_threshold_dimension;
   V.ignore_dim = h->p.ignore_dimension;
-  V.reach = rs->J.reach;
-  V.ireach = rs->J.reach + 2.0 * h->j_drift + 1e-9;
+  // the enumeration margins also cover the rounding of the reference's test at the magnitude of the coordinates involved
+  // (negligible against the 1e-9 slack of J.reach unless the maps sit millions of metres from the origin)
+  double qmag = 0.0;
+  for (int j = 0; j < h->n_qry; j++) qmag = std::max(qmag, std::hypot(h->qry_rows[7 * (size_t)j + 1], h->qry_rows[7 * (size_t)j + 2]));
+  const double round_slack = 64.0 * DBL_EPSILON * (rs->J.max_abs + qmag + std::max(std::fabs(h->half_x), std::fabs(h->half_y)));
+  V.reach = rs->J.reach + round_slack;
+  V.ireach = V.reach + 2.0 * h->j_drift + 1e-9;
   V.inv_step = 1.0 / h->p.match_xy_step_size;
   V.blocks = h->dj_blocks.as<SprJoinBlock>();
   V.n_blocks = (uint32_t)h->j_blocks.size();

@@ -797,7 +797,10 @@ int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, Join
   }
   // same-label landmarks with a lower reference index that can match the same point: within 2 x reach
   J.nbr.clear();
-  const double r2 = 2.0 * J.reach * (1.0 + 1e-9) + 1e-9;
+  // (+ the rounding of the reference's test at the magnitude of the map's coordinates)
+  const double mag = std::max({std::fabs(minx), std::fabs(maxx), std::fabs(miny), std::fabs(maxy)});
+  const double r2 = 2.0 * J.reach * (1.0 + 1e-9) + 1e-9 + 64.0 * DBL_EPSILON * mag;
+  J.max_abs = mag;
   const int span = (int)std::floor(r2 * J.inv_w) + 1;
   const uvec<uint32_t> &cs0 = J.cell_start[0];
   std::vector<int32_t> by_pos0(std::max<size_t>(n_kept, 1), -1);  // landmark at each record position of order 0

@@ -148,7 +148,8 @@ struct JoinRef {
   double gx0 = 0, gy0 = 0, w = 1, inv_w = 1;
   int ncx = 1, ncy = 1;
   double Tstar = 0, Sstar = 0;
-  double reach = 0;                  // a match implies |dx|, |dy| < reach
+  double reach = 0;                  // a match implies |dx|, |dy| < reach (at ordinary coordinate magnitudes; see max_abs)
+  double max_abs = 0;                // largest |coordinate| of the map
   int n_ref = 0;
 };
 int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, JoinRef &J, std::string &err);

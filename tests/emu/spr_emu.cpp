@@ -160,7 +160,10 @@ extern "C" int spr_emu_join_match_maps(const slide_pr_params *p, const double *r
   V.nbr = J.nbr.data(); V.labelbox = J.labelbox.data();
   V.gx0 = J.gx0; V.gy0 = J.gy0; V.inv_w = J.inv_w; V.ncx = J.ncx; V.ncy = J.ncy;
   V.Tstar = J.Tstar; V.Sstar = J.Sstar; V.thr_dim = p->match_threshold_dimension; V.ignore_dim = p->ignore_dimension;
-  V.reach = J.reach; V.ireach = J.reach + 2.0 * drift + 1e-9; V.inv_step = 1.0 / p->match_xy_step_size;
+  double qmag = 0.0;
+  for (int j = 0; j < n_qry; j++) qmag = std::max(qmag, std::hypot(qry7[7 * (size_t)j + 1], qry7[7 * (size_t)j + 2]));
+  V.reach = J.reach + 64.0 * 2.220446049250313e-16 * (J.max_abs + qmag + std::max(std::fabs(half_x), std::fabs(half_y)));
+  V.ireach = V.reach + 2.0 * drift + 1e-9; V.inv_step = 1.0 / p->match_xy_step_size;
   V.blocks = blocks.data(); V.n_blocks = (uint32_t)blocks.size();
   const unsigned long long ob = trans_begin < 0 ? 0 : (unsigned long long)trans_begin;
   const unsigned long long oe = trans_end < 0 ? L.n_translations : std::min<unsigned long long>((unsigned long long)trans_end, L.n_translations);

@@ -98,6 +98,11 @@ def test_edge_cases():
     # more identical query landmarks than one round of the pair-join kernel holds: its u8 counters must not wrap
     q5 = np.tile(np.array([[2, 0.0, 0.0, 0, 0.5, 0, 0]], float), (700, 1))
     assert _check_counts(O.make_params(match_xy_step_size=0.5, yaw_step_deg=90.0), r4, q5, 3.0, 3.0)["best_num_inliers"] == 700
+    # maps far from the origin (intra mode searches in the map frame: no centroid shift): coordinates of 3e5 m, where
+    # one ulp is 6e-11 m -- the enumeration margins of the pair-join scorer scale with the coordinate magnitude
+    far_r, far_q = ref.copy(), qry.copy()
+    far_r[:, 1] += 3.0e5; far_r[:, 2] -= 2.0e5; far_q[:, 1] += 3.0e5; far_q[:, 2] -= 2.0e5
+    _check_counts(O.make_params(match_xy_step_size=0.5, yaw_step_deg=90.0, disable_yaw_search=1), far_r, far_q, 6.0, 6.0)
     # threshold far above the step: 15 x 15 lattice samples per pair (general path of the pair-join kernel)
     _check_counts(O.make_params(match_xy_step_size=0.1, yaw_step_deg=60.0, match_threshold=0.75), ref, qry, 4.0, 4.0)
     # sanity-check early return and zero rings
