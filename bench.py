@@ -286,6 +286,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- the metric: every hypothesis scored exactly
     step_ms, kern_ms, hyps, launches, res_x = timed_steps(pr, False, args.steps)
+    exchange_ms = 0.0
     if world > 1:        # timed: the one exchange of the weak-scaling job
         torch.cuda.synchronize()
         dist.barrier()                      # untimed, like the L2 flushes: the ranks' untimed host work differs
@@ -295,7 +296,8 @@ def run_ours(args, rank, world, local_rank):
         dist.all_gather_into_tensor(rec_all, rec_dev)
         e1.record(stream)
         e1.synchronize()
-        step_ms.append(e0.elapsed_time(e1))
+        exchange_ms = e0.elapsed_time(e1)
+        step_ms.append(exchange_ms)
         assert bool((rec_all.view(world, -1, 2)[:, :, 1] == int(res_x.best_num_inliers)).all())  # same pair on every rank
     torch.cuda.synchronize()
     if world > 1:
@@ -400,6 +402,7 @@ def run_ours(args, rank, world, local_rank):
                             "all result records at the end of the timed region" if world > 1 else "single GPU"),
             "best_num_inliers": int(res_x.best_num_inliers), "closure_found": bool(found),
             "kernel_ms_per_step": kernel_total_ms / n_steps, "gpu_launches": launches_all,
+            "exchange_ms": exchange_ms,   # rank 0: the one all-gather of all steps' records (inside the timed region, N > 1)
             "pairs_per_s": world * n_steps / (total_ms * 1e-3),
             "search_mode": int(res_x.search_mode),
             "lattice_kernels": {
