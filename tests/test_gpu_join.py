@@ -149,6 +149,44 @@ def test_random_maps_every_hypothesis(seed):
     pr.close()
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_dense_and_clustered_maps_every_hypothesis(seed):
+    """The kernel's own hard cases (same generator as tests/test_host_index.py runs through the CPU emulation): clusters of
+    near-duplicate reference landmarks (first-match attribution), several quads and full pair lists per block (the list is
+    flushed mid-pass), more than four cell bands per landmark (several passes), thresholds from a third of the step to four
+    steps, one label or many, rectangular ranges.  Every per-hypothesis count against the oracle."""
+    rng = np.random.default_rng(7000 + seed)
+    n_ref, n_qry = int(rng.integers(20, 160)), int(rng.integers(20, 120))
+    n_labels = int(rng.choice([1, 1, 2, 6]))
+    ref, qry = H.random_maps(rng, n_ref, n_qry, extent=float(rng.uniform(4, 12)), n_labels=n_labels,
+                             dup_frac=float(rng.choice([0.0, 0.3, 0.6])), grid=(0.125 if seed % 4 == 0 else None))
+    if seed % 3 == 0:
+        k = min(12, n_ref)
+        ref[:k, 1:3] = ref[0, 1:3] + rng.normal(0, 0.1, (k, 2))
+        ref[:k, 0] = ref[0, 0]
+    step = float(rng.choice([0.5, 0.25, 0.4]))
+    thr = float(step * rng.choice([0.34, 1.0, 1.0, 1.7, 4.0]))
+    kw = dict(match_xy_step_size=step, yaw_step_deg=float(rng.choice([45.0, 60.0, 36.0])), match_threshold=thr,
+              match_threshold_dimension=float(rng.choice([1.0, 0.4])), ignore_dimension=int(seed % 5 == 2),
+              disable_yaw_search=int(seed % 6 == 5))
+    hx = float(rng.uniform(3, 9))
+    hy = hx if seed % 2 else float(rng.uniform(3, 9))
+    op = O.make_params(**kw)
+    if O.enumerate_lattice(op, hx, hy) is None:
+        pytest.skip("range below one lattice step")
+    want = O.match_maps(op, ref, qry, hx, hy, want_counts=True)
+    pr = make_pr(kw)
+    pr.prepare(ref, qry, hx, hy)
+    nt, ny, _ = pr.lattice_info()
+    res, got = pr.search(0, nt, want_counts=True)
+    assert res.search_mode == JOIN
+    bad = np.nonzero(got != want["counts"])[0]
+    assert bad.size == 0, f"first mismatching hypotheses {bad[:5]}: {got[bad[:5]]} != {want['counts'][bad[:5]]}"
+    res2, _ = pr.search()          # the whole-block scan path (no per-hypothesis output)
+    assert (res2.best_num_inliers, res2.best_hyp_index) == (want["best_num_inliers"], want["best_hyp_index"])
+    pr.close()
+
+
 def test_edge_cases():
     kw = dict(match_xy_step_size=0.5, yaw_step_deg=45.0)
     rng = np.random.default_rng(1)

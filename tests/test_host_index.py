@@ -73,6 +73,40 @@ def test_random_maps_every_hypothesis(seed):
     _check_counts(op, ref, qry, hx, hy)
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_pair_join_scorer_dense_and_clustered_maps(seed):
+    """The pair-join scorer's own hard cases, every hypothesis against the oracle: clusters of near-duplicate reference
+    landmarks (first-match attribution through the lower-index neighbour lists), many query landmarks per block (several
+    quads, full pair lists), thresholds from a third of the step to four steps, one label or many, rectangular ranges."""
+    rng = np.random.default_rng(7000 + seed)
+    n_ref, n_qry = int(rng.integers(20, 160)), int(rng.integers(20, 120))
+    n_labels = int(rng.choice([1, 1, 2, 6]))
+    ref, qry = H.random_maps(rng, n_ref, n_qry, extent=float(rng.uniform(4, 12)), n_labels=n_labels,
+                             dup_frac=float(rng.choice([0.0, 0.3, 0.6])), grid=(0.125 if seed % 4 == 0 else None))
+    if seed % 3 == 0:   # a tight cluster: up to 12 reference landmarks within one threshold of each other
+        k = min(12, n_ref)
+        ref[:k, 1:3] = ref[0, 1:3] + rng.normal(0, 0.1, (k, 2))
+        ref[:k, 0] = ref[0, 0]
+    step = float(rng.choice([0.5, 0.25, 0.4]))
+    thr = float(step * rng.choice([0.34, 1.0, 1.0, 1.7, 4.0]))
+    op = O.make_params(match_xy_step_size=step, yaw_step_deg=float(rng.choice([45.0, 60.0, 36.0])), match_threshold=thr,
+                       match_threshold_dimension=float(rng.choice([1.0, 0.4])), ignore_dimension=int(seed % 5 == 2),
+                       disable_yaw_search=int(seed % 6 == 5))
+    hx = float(rng.uniform(3, 9))
+    hy = hx if seed % 2 else float(rng.uniform(3, 9))
+    p = H.to_capi_params(op)
+    lat = O.enumerate_lattice(op, hx, hy)
+    if lat is None:
+        pytest.skip("range below one lattice step")
+    n = len(lat[0]) * len(lat[3])
+    o = O.match_maps(op, ref, qry, hx, hy, want_counts=True)
+    e = H.emu_match_maps(p, ref, qry, hx, hy, n_counts=n, engine="join")
+    assert e["rc"] == 0, e["err"]
+    bad = np.nonzero(e["counts"] != o["counts"])[0]
+    assert bad.size == 0, f"first mismatching hypotheses {bad[:5]}: {e['counts'][bad[:5]]} != {o['counts'][bad[:5]]}"
+    assert (e["best_num_inliers"], e["best_hyp_index"]) == (o["best_num_inliers"], o["best_hyp_index"])
+
+
 def test_edge_cases():
     op = O.make_params(match_xy_step_size=0.5, yaw_step_deg=45.0)
     rng = np.random.default_rng(1)
