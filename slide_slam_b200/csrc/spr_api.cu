@@ -156,7 +156,6 @@ struct RefSide {
   slide_pr_params cached_ref_p{};    // parameters the index depends on
   bool ref_index_valid = false;
   bool ranks_pending = false;        // stage 2 of the index (rank tables) not built / uploaded yet
-  const double *pending_ref7 = nullptr;
   bool rows_valid = false;           // cached_ref holds the rows of the prepared reference map
   bool ref7_uploaded = false;        // ... and d_ref7 their device copy
   // pair-join scorer (spr_join.h): landmarks binned by label and coarse cell, both join directions
@@ -224,7 +223,7 @@ struct slide_pr_handle {
   spr::uvec<double> qry_rows;       // copy of the query rows (source of the asynchronous upload)
   double lat_hx = 0, lat_hy = 0, lat_yaw_half = 0;
   slide_pr_params lat_p{};
-  bool lattice_valid = false, lattice_on_device = false;
+  bool lattice_valid = false;
   int reuse_flags = 0;
   int64_t h2d_bytes = 0;
   spr::Lattice L;
@@ -613,7 +612,6 @@ static int join_prepare(slide_pr_handle *h) {
     if (!same_lattice) {
       h->lat_hx = h->half_x; h->lat_hy = h->half_y; h->lat_yaw_half = h->yaw_half; h->lat_p = h->p;
       h->lattice_valid = true;
-      h->lattice_on_device = false;
     }
     if ((rc = upload(h, h->dj_lat, h->L.lat, st))) return rc;
     if ((rc = upload(h, h->dj_cs, h->L.cs, st))) return rc;
