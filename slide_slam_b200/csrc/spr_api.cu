@@ -94,7 +94,6 @@ class Worker {
     { std::lock_guard<std::mutex> g(m_); job_ = std::move(job); busy_ = true; }
     cv_.notify_all();
   }
-  bool pending() const { return busy_; }
   int wait() {  // result of the last submitted job (0 if none)
     std::unique_lock<std::mutex> g(m_);
     cv_.wait(g, [this] { return !busy_; });
