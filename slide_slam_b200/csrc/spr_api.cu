@@ -806,6 +806,10 @@ static int lattice_prepare(slide_pr_handle *h) {
   return SLIDE_PR_OK;
 }
 
+// The hypothesis-list scorer runs on the default engine's structures: the landmark bins of the pair-join scorer, or the
+// occupancy bitmaps of the lattice kernels.  Returns through *join which kernel to launch.
+static int ensure_list_scorer(slide_pr_handle *h, cudaStream_t st, bool *join);
+
 // The lattice kernels' structures, built the first time a call needs them for the prepared problem.
 static int ensure_lattice(slide_pr_handle *h, cudaStream_t st) {
   if (h->lattice_ready) return SLIDE_PR_OK;
@@ -821,6 +825,21 @@ int slide_pr_prepare(slide_pr_handle *h, const double *ref7, int32_t n_ref, cons
                      double half_x, double half_y) {
   if (!h) return SLIDE_PR_ERR_INVALID;
   return prepare_impl(h, &h->anon, false, ref7, n_ref, qry7, n_qry, half_x, half_y);
+}
+
+static int ensure_list_scorer(slide_pr_handle *h, cudaStream_t st, bool *join) {
+  *join = join_is_default(h);
+  if (!*join) {
+    int rc = ensure_lattice(h, st);
+    if (rc == SLIDE_PR_OK && h->rs->ranks_pending) rc = finish_ranks(h, st);
+    return rc;
+  }
+  if (h->join_ready) return SLIDE_PR_OK;
+  const int rc = join_prepare(h);
+  if (rc != SLIDE_PR_OK) return rc;
+  SPR_CUDA(h, cudaEventRecord(h->ev_prep, h->stream));
+  if (st != h->stream) SPR_CUDA(h, cudaStreamWaitEvent(st, h->ev_prep, 0));
+  return SLIDE_PR_OK;
 }
 
 static void fill_result_header(slide_pr_handle *h, slide_pr_match_result *out) {
@@ -1992,8 +2011,8 @@ int slide_pr_generate_and_score(slide_pr_handle *h, const double *tris_model6, c
   slide_pr_generate_info local{}, *I = info ? info : &local;
   std::memset(I, 0, sizeof(*I));
   if (t_model == 0 || t_data == 0) return SLIDE_PR_OK;
-  { const int lrc = ensure_lattice(h, st); if (lrc != SLIDE_PR_OK) return lrc; }   // the list scorer probes the occupancy bitmaps
-  if (h->rs->ranks_pending) { const int rrc = finish_ranks(h, st); if (rrc != SLIDE_PR_OK) return rrc; }
+  bool list_join = false;
+  { const int lrc = ensure_list_scorer(h, st, &list_join); if (lrc != SLIDE_PR_OK) return lrc; }
   GenDevice G;
   int rc = gen_match_on_device(h, tris_model6, labels_model3, t_model, tris_data6, labels_data3, t_data, threshold, &G);
   if (rc != SLIDE_PR_OK) return rc;
@@ -2009,8 +2028,13 @@ int slide_pr_generate_and_score(slide_pr_handle *h, const double *tris_model6, c
   SPR_CUDA(h, spr_launch_gen_kabsch(G.tris_m, G.tris_d, G.perm_m, G.perm_d, G.model_idx, G.data_idx, n, h->d_hyps.as<double>(),
                                     nullptr, nullptr, st));
   SPR_CUDA(h, cudaEventRecord(e2, st));
-  SPR_CUDA(h, spr_launch_score_list(h->V, h->d_hyps.as<double>(), n, h->d_counts.as<int32_t>(), h->d_best.as<unsigned long long>(),
-                                    h->sm_count, st));
+  if (list_join) {
+    SPR_CUDA(h, spr_launch_join_score_list(h->JV, h->d_hyps.as<double>(), n, h->d_counts.as<int32_t>(), h->d_best.as<unsigned long long>(),
+                                           h->sm_count, st));
+  } else {
+    SPR_CUDA(h, spr_launch_score_list(h->V, h->d_hyps.as<double>(), n, h->d_counts.as<int32_t>(), h->d_best.as<unsigned long long>(),
+                                      h->sm_count, st));
+  }
   SPR_CUDA(h, cudaEventRecord(e3, st));
   if (h->h_scalars.size() < 8) h->h_scalars.assign(8, 0ull);
   SPR_CUDA(h, cudaMemcpyAsync(h->h_scalars.data(), h->d_best.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -2077,8 +2101,8 @@ int slide_pr_score_hypotheses(slide_pr_handle *h, const double *hyps4, int64_t n
   if (!h || !out || (n > 0 && !hyps4) || n < 0) return SLIDE_PR_ERR_INVALID;
   if (!h->prepared) { h->err = "slide_pr_score_hypotheses before slide_pr_prepare"; return SLIDE_PR_ERR_INVALID; }
   SPR_CUDA(h, cudaSetDevice(h->device));
-  { const int lrc = ensure_lattice(h, h->stream); if (lrc != SLIDE_PR_OK) return lrc; }   // the list scorer probes the occupancy bitmaps
-  if (h->rs->ranks_pending) { const int rrc = finish_ranks(h, h->stream); if (rrc != SLIDE_PR_OK) return rrc; }
+  bool list_join = false;
+  { const int lrc = ensure_list_scorer(h, h->stream, &list_join); if (lrc != SLIDE_PR_OK) return lrc; }
   cudaStream_t st = h->stream;
   fill_result_header(h, out);
   out->status = SLIDE_PR_OK;
@@ -2088,8 +2112,13 @@ int slide_pr_score_hypotheses(slide_pr_handle *h, const double *hyps4, int64_t n
   if (counts_out) SPR_CUDA(h, h->d_counts.ensure((size_t)n * sizeof(int32_t)));
   SPR_CUDA(h, cudaMemsetAsync(h->d_best.p, 0, sizeof(unsigned long long), st));
   SPR_CUDA(h, cudaEventRecord(h->ev0, st));
-  SPR_CUDA(h, spr_launch_score_list(h->V, h->d_hyps.as<double>(), n, counts_out ? h->d_counts.as<int32_t>() : nullptr,
-                                    h->d_best.as<unsigned long long>(), h->sm_count, st));
+  if (list_join) {
+    SPR_CUDA(h, spr_launch_join_score_list(h->JV, h->d_hyps.as<double>(), n, counts_out ? h->d_counts.as<int32_t>() : nullptr,
+                                           h->d_best.as<unsigned long long>(), h->sm_count, st));
+  } else {
+    SPR_CUDA(h, spr_launch_score_list(h->V, h->d_hyps.as<double>(), n, counts_out ? h->d_counts.as<int32_t>() : nullptr,
+                                      h->d_best.as<unsigned long long>(), h->sm_count, st));
+  }
   SPR_CUDA(h, cudaEventRecord(h->ev1, st));
   unsigned long long key = 0;
   SPR_CUDA(h, cudaMemcpyAsync(&key, h->d_best.p, sizeof(key), cudaMemcpyDeviceToHost, st));

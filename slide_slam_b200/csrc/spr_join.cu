@@ -264,6 +264,70 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// explicit hypothesis lists (c, s, x, y) -- e.g. the 2-D Kabsch fits of matched triangles -- scored with the
+// MatchMaps predicate (PR.cpp:272-357) through the landmark bins: warp per hypothesis, lanes stride over the
+// query landmarks; a landmark counts when ANY reference landmark of its label matches (the reference stops at
+// the first one it finds)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+spr_join_score_list_kernel(const SprJoinView V, const double *__restrict__ hyps4, long long n, int32_t *__restrict__ counts_out,
+                           unsigned long long *best_key) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const size_t n_cells = (size_t)V.ncx * (size_t)V.ncy;
+  unsigned long long best = 0ull;
+  for (long long h = warp0; h < n; h += n_warps) {
+    const double c = hyps4[4 * h], s = hyps4[4 * h + 1], tx = hyps4[4 * h + 2], ty = hyps4[4 * h + 3];
+    int cnt = 0;
+    for (int js = lane; js < V.nqp; js += 32) {
+      const int l = __ldg(V.qlabel + js);
+      if (l < 0) continue;  // padding
+      double rx, ry;
+      spr_rotate(c, s, __ldg(V.qxy + 2 * (size_t)js), __ldg(V.qxy + 2 * (size_t)js + 1), &rx, &ry);
+      const double xt = SPR_DADD(rx, tx), yt = SPR_DADD(ry, ty);
+      // coarse cells within reach of the transformed landmark (+ the rounding of the test at this magnitude)
+      const double reach = V.reach + 1e-12 * (fabs(xt) + fabs(yt));
+      double fx0 = floor(SPR_DMUL(SPR_DSUB(SPR_DSUB(xt, reach), V.gx0), V.inv_w)), fx1 = floor(SPR_DMUL(SPR_DSUB(SPR_DADD(xt, reach), V.gx0), V.inv_w));
+      double fy0 = floor(SPR_DMUL(SPR_DSUB(SPR_DSUB(yt, reach), V.gy0), V.inv_w)), fy1 = floor(SPR_DMUL(SPR_DSUB(SPR_DADD(yt, reach), V.gy0), V.inv_w));
+      fx0 = fmax(fx0, 0.0); fy0 = fmax(fy0, 0.0);
+      fx1 = fmin(fx1, (double)(V.ncx - 1)); fy1 = fmin(fy1, (double)(V.ncy - 1));
+      if (!(fx0 <= fx1) || !(fy0 <= fy1)) continue;
+      const uint32_t *cstart = V.cell_start[0] + (size_t)l * n_cells;
+      const double *qd = V.qdims + 3 * (size_t)js;
+      const double qdl[3] = {__ldg(qd), __ldg(qd + 1), __ldg(qd + 2)};
+      bool hit = false;
+      for (int cx = (int)fx0; cx <= (int)fx1 && !hit; cx++) {
+        const uint32_t r_end = __ldg(cstart + cx * V.ncy + (int)fy1 + 1);
+        for (uint32_t r = __ldg(cstart + cx * V.ncy + (int)fy0); r < r_end && !hit; r++) {
+          const SprJoinRef *rec = V.rec[0] + r;
+          hit = spr_distance_match(rx, ry, tx, ty, __ldg(&rec->x), __ldg(&rec->y), V.Tstar) &&
+                (V.ignore_dim || spr_dimension_match(__ldg(&rec->d1), __ldg(&rec->d2), __ldg(&rec->d3), qdl, V.thr_dim, V.Sstar));
+        }
+      }
+      cnt += hit ? 1 : 0;
+    }
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) cnt += __shfl_xor_sync(SPJ_FULL, cnt, dlt);
+    if (lane == 0) {
+      if (counts_out) counts_out[h] = cnt;
+      const unsigned long long key = spr_make_key((uint32_t)cnt, (unsigned long long)h);
+      best = key > best ? key : best;
+    }
+  }
+  if (lane == 0 && best != 0ull) atomicMax(best_key, best);
+}
+
+cudaError_t spr_launch_join_score_list(const SprJoinView &V, const double *hyps4, long long n, int32_t *counts_out,
+                                       unsigned long long *best_key, int sm_count, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const long long want = (n + 7) / 8;
+  const long long cap = (long long)sm_count * 8;
+  spr_join_score_list_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(V, hyps4, n, counts_out, best_key);
+  return cudaGetLastError();
+}
+
 cudaError_t spr_launch_join_score(const SprJoinView &V, const SprJoinLaunch &K, int sm_count, cudaStream_t st) {
   const int sc = K.shard_count > 1 ? K.shard_count : 1, si = K.shard_count > 1 ? K.shard_index : 0;
   const uint32_t n_local = V.n_blocks > (uint32_t)si ? (V.n_blocks - (uint32_t)si + (uint32_t)sc - 1) / (uint32_t)sc : 0u;

@@ -28,3 +28,6 @@
 
 cudaError_t spr_launch_join_rotate(const SprJoinView &V, double *qrot, SprJoinBox *gbox, cudaStream_t st);
 cudaError_t spr_launch_join_score(const SprJoinView &V, const SprJoinLaunch &K, int sm_count, cudaStream_t st);
+// explicit hypothesis list (n x 4: c, s, x, y) against the prepared maps: inlier count of each, best (max count, lowest index)
+cudaError_t spr_launch_join_score_list(const SprJoinView &V, const double *hyps4, long long n, int32_t *counts_out,
+                                       unsigned long long *best_key, int sm_count, cudaStream_t st);
