@@ -2,7 +2,8 @@
 //
 // Host control flow mirrors PlaceRecognition::findInterLoopClosure -> findTransformation ->
 // MatchMaps -> solveLSQ (place_recognition.cpp:498-538, 736-945, 98-387, 632-695); the scoring
-// itself only ever runs on the GPU (spr_kernels.cu).  There is no CPU fallback.
+// itself only ever runs on the GPU (spr_join.cu: the default pair-join scorer; spr_kernels*.cu: the
+// lattice kernels).  There is no CPU fallback.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -1062,7 +1063,7 @@ int slide_pr_search(slide_pr_handle *h, const slide_pr_search_opts *opts, slide_
     }
     return SLIDE_PR_OK;
   };
-  // bound-and-verify (default): upper bounds of all hypotheses first, then exact verification of
+  // bound-and-verify (the lattice kernels' default): upper bounds of all hypotheses first, then exact verification of
   // those whose bound reaches the running best.  Exhaustive verification of every hypothesis
   // when per-hypothesis counts / statistics are requested, with a compute budget (ring by ring),
   // or on request (opts.exhaustive).

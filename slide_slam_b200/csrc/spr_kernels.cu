@@ -1,9 +1,10 @@
-// spr_kernels.cu -- sm_100a kernels of the SlideMatch lattice search.
+// spr_kernels.cu -- sm_100a kernels of the SlideMatch lattice search, lattice engine (the library's
+// second engine; the default search is the pair-join scorer, spr_join.cu).
 //
 // Replaces the five nested loops of PlaceRecognition::MatchMaps (place_recognition.cpp:178-372):
 // the EXACT inlier count of hypotheses -- all of them in the exhaustive mode, the candidates that
-// survive the bound phase (spr_kernels_bound.cu) in the default bound-and-verify mode.
-// Work decomposition (DESIGN.md section 3):
+// survive the bound phase (spr_kernels_bound.cu) in the bound-and-verify mode.
+// Work decomposition (DESIGN.md section 4):
 //   * the search runs as one PASS per (label, bitmap direction): all CTAs work on the same
 //     occupancy plane at the same time, so the plane and its rank tables are staged once per CTA
 //     into SHARED MEMORY with TMA bulk copies when they fit (lazily, by the first warp that has
