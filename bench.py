@@ -156,7 +156,7 @@ def cpu_reference_setup(ref, qry):
     return O, op, sref, sqry, half
 
 
-def cpu_reference_rate(ref, qry, seconds: float, threads: int):
+def cpu_reference_rate(ref, qry, seconds: float, threads: int, gpu=None):
     """The reference's CPU algorithm (oracle) on the first M hypotheses of the workload in canonical
     order; M sized for ~`seconds` of wall time with `threads` threads (1 = the faithful single loop:
     the reference runs MatchMaps on one std::thread, sloamNode.cpp:109)."""
@@ -167,11 +167,19 @@ def cpu_reference_rate(ref, qry, seconds: float, threads: int):
     dt = max(time.perf_counter() - t0, 1e-3)
     m = int(max(m, min(m * seconds / dt, 5e7)))
     t0 = time.perf_counter()
-    r = O.match_maps(op, sref, sqry, half["half_x"], half["half_y"], 0, m, n_threads=threads)
+    r = O.match_maps(op, sref, sqry, half["half_x"], half["half_y"], 0, m, want_counts=gpu is not None, n_threads=threads)
     dt = time.perf_counter() - t0
     what = "single thread, the reference's own loop nest" if threads == 1 else f"{threads} OpenMP threads over hypotheses"
-    return {"value": r["hypotheses_scored"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"first {m} hypotheses (canonical order) of the same workload, oracle/slide_oracle.c, {what}, {dt:.1f} s"}
+    out = {"value": r["hypotheses_scored"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": f"first {m} hypotheses (canonical order) of the same workload, oracle/slide_oracle.c, {what}, {dt:.1f} s"}
+    if gpu is not None:   # the results on the CPU's slice must match the GPU's on the same slice
+        n_yaw = gpu.lattice_info()[1]
+        te = m // n_yaw                       # whole translations inside the sample
+        if te > 0:
+            _, got = gpu.search(0, te, want_counts=True)
+            out["slice_equals_gpu"] = bool(np.array_equal(got, r["counts"][: te * n_yaw]))
+            out["slice_hypotheses_compared"] = int(te * n_yaw)
+    return out
 
 
 def run_reference(args, rank, world):
@@ -432,7 +440,8 @@ def run_ours(args, rank, world, local_rank):
         out.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
-            out["cpu_baseline"] = cpu_reference_rate(ref, qry, args.cpu_seconds, threads)
+            pr.prepare(sref, sqry, info.half_x, info.half_y)   # the e2e legs re-prepared the handle
+            out["cpu_baseline"] = cpu_reference_rate(ref, qry, args.cpu_seconds, threads, gpu=pr)
             out["cpu_baseline_1thread"] = cpu_reference_rate(ref, qry, min(args.cpu_seconds, 8.0), 1)
         print(json.dumps(out), flush=True)
     pr.close(); prl.close()
