@@ -149,20 +149,24 @@ __device__ __forceinline__ void spj_quad(const SprJoinView &V, const SpjBlock &B
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(SPJ_THREADS, SPJ_MIN_CTAS)
+// WARPS x 32 threads per CTA, CTAS resident CTAs per SM: 8 x 4 for ordinary query maps; 4 x 7 when the query map is small
+// (few quads per work item: more items in flight per SM pay more than wide CTAs).
+template <int WARPS, int CTAS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS)
 spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_constant__ SprJoinLaunch K,
                       const uint32_t n_blocks_local, const unsigned long long n_items) {
   // dynamic shared memory (more than the 48 KB a static allocation may take): counters, staged query
   // landmarks, per-warp work lists, visible groups
   extern __shared__ __align__(16) unsigned char spj_smem[];
   SpjQuery (*s_q)[32] = reinterpret_cast<SpjQuery (*)[32]>(spj_smem);
-  uint32_t *s_tile = reinterpret_cast<uint32_t *>(spj_smem + SPJ_WARPS * 32 * sizeof(SpjQuery));
+  uint32_t *s_tile = reinterpret_cast<uint32_t *>(spj_smem + WARPS * 32 * sizeof(SpjQuery));
   uint32_t (*s_list)[SPJ_LIST] = reinterpret_cast<uint32_t (*)[SPJ_LIST]>(s_tile + SPJ_TILE_WORDS);
-  uint32_t (*s_rng)[SPJ_RANGE_WORDS] = reinterpret_cast<uint32_t (*)[SPJ_RANGE_WORDS]>(s_tile + SPJ_TILE_WORDS + SPJ_WARPS * SPJ_LIST);
-  uint16_t *s_vis = reinterpret_cast<uint16_t *>(s_tile + SPJ_TILE_WORDS + SPJ_WARPS * (SPJ_LIST + SPJ_RANGE_WORDS));
+  uint32_t (*s_rng)[SPJ_RANGE_WORDS] = reinterpret_cast<uint32_t (*)[SPJ_RANGE_WORDS]>(s_tile + SPJ_TILE_WORDS + WARPS * SPJ_LIST);
+  uint16_t *s_vis = reinterpret_cast<uint16_t *>(s_tile + SPJ_TILE_WORDS + WARPS * (SPJ_LIST + SPJ_RANGE_WORDS));
   __shared__ uint32_t s_nvis, s_next;
   __shared__ unsigned long long s_item;
-  __shared__ uint32_t s_red[SPJ_WARPS];
+  __shared__ uint32_t s_red[WARPS];
+  constexpr int THREADS = WARPS * 32, SEG_GROUPS = THREADS * 4;   // query groups whose visibility is tested per pass
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (;;) {
@@ -174,18 +178,18 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
     const uint32_t b = (uint32_t)K.shard_index + (uint32_t)(item % n_blocks_local) * (uint32_t)K.shard_count;
     const SprJoinBlock blk = V.blocks[b];
     const SpjBlock B = spj_block(V, blk);
-    for (int w = tid; w < (2 * B.stride + 3) / 4; w += SPJ_THREADS) reinterpret_cast<uint4 *>(s_tile)[w] = make_uint4(0u, 0u, 0u, 0u);
+    for (int w = tid; w < (2 * B.stride + 3) / 4; w += THREADS) reinterpret_cast<uint4 *>(s_tile)[w] = make_uint4(0u, 0u, 0u, 0u);
 
     const SprJoinBox *gb = V.gbox + (size_t)a * (size_t)V.n_groups;
     const double2 *qr = reinterpret_cast<const double2 *>(V.qrot) + (size_t)a * (size_t)V.nqp;
 
-    for (int seg0 = 0; seg0 < V.n_groups; seg0 += SPJ_SEG_GROUPS) {
+    for (int seg0 = 0; seg0 < V.n_groups; seg0 += SEG_GROUPS) {
       if (tid == 0) { s_nvis = 0u; s_next = 0u; }
       __syncthreads();   // counters zeroed (first segment); the previous segment's warps are done with s_vis
       // groups of the segment that some translation of the block brings over their label's landmarks
-      const int seg_passes = min(SPJ_SEG_GROUPS / SPJ_THREADS, (V.n_groups - seg0 + SPJ_THREADS - 1) / SPJ_THREADS);
+      const int seg_passes = min(SEG_GROUPS / THREADS, (V.n_groups - seg0 + THREADS - 1) / THREADS);
       for (int k = 0; k < seg_passes; k++) {
-        const int g = seg0 + k * SPJ_THREADS + tid;
+        const int g = seg0 + k * THREADS + tid;
         bool vis = false;
         if (g < V.n_groups) {
           const float4 bx = __ldg(reinterpret_cast<const float4 *>(gb + g));
@@ -196,7 +200,7 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
         uint32_t base = 0u;
         if (lane == 0 && m) base = atomicAdd(&s_nvis, (uint32_t)__popc(m));
         base = __shfl_sync(SPJ_FULL, base, 0);
-        if (vis) s_vis[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (uint16_t)(k * SPJ_THREADS + tid);
+        if (vis) s_vis[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (uint16_t)(k * THREADS + tid);
       }
       __syncthreads();
       const uint32_t nvis = s_nvis, n_quads = (nvis + 3u) / 4u;
@@ -223,7 +227,7 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
       // the whole block (the usual case): two samples per step -- word n of array 0 holds samples (2n, 2n + 1) of its
       // row, array 1 contributes the high half of its word n to sample 2n and the low half of word n + 1 to 2n + 1
       const float inv_nwy = 1.0f / (float)B.nwy;
-      for (int w = tid; w < B.stride; w += SPJ_THREADS) {
+      for (int w = tid; w < B.stride; w += THREADS) {
         const int i = __float2int_rd(((float)w + 0.5f) * inv_nwy), n = w - i * B.nwy, j = 2 * n;   // exact: w < 2^13
         if (j >= B.ny) continue;   // the spare word of an even-length row
         const uint32_t w0 = s_tile[w], w1 = s_tile[B.stride + w];
@@ -237,7 +241,7 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
       }
     } else {
       const float inv_ny = 1.0f / (float)B.ny;
-      for (int s = s_lo + tid; s < s_hi; s += SPJ_THREADS) {
+      for (int s = s_lo + tid; s < s_hi; s += THREADS) {
         const int i = __float2int_rd(((float)s + 0.5f) * inv_ny), j = s - i * B.ny;   // exact: s < 2^13
         const uint32_t c = spj_total(s_tile, B, i, j);
         best = max(best, ((c + 1u) << SPJ_SLOT_BITS) | (uint32_t)(SPJ_MAX_SLOTS - 1 - s));
@@ -252,7 +256,7 @@ spr_join_score_kernel(const __grid_constant__ SprJoinView V, const __grid_consta
     __syncthreads();
     if (tid == 0) {
 #pragma unroll
-      for (int w = 1; w < SPJ_WARPS; w++) best = max(best, s_red[w]);
+      for (int w = 1; w < WARPS; w++) best = max(best, s_red[w]);
       if (best) {
         const int s = SPJ_MAX_SLOTS - 1 - (int)(best & (SPJ_MAX_SLOTS - 1));
         const uint32_t c = (best >> SPJ_SLOT_BITS) - 1u;
@@ -328,15 +332,10 @@ cudaError_t spr_launch_join_score_list(const SprJoinView &V, const double *hyps4
   return cudaGetLastError();
 }
 
-cudaError_t spr_launch_join_score(const SprJoinView &V, const SprJoinLaunch &K, int sm_count, cudaStream_t st) {
-  const int sc = K.shard_count > 1 ? K.shard_count : 1, si = K.shard_count > 1 ? K.shard_index : 0;
-  const uint32_t n_local = V.n_blocks > (uint32_t)si ? (V.n_blocks - (uint32_t)si + (uint32_t)sc - 1) / (uint32_t)sc : 0u;
-  const unsigned long long n_items = (unsigned long long)n_local * (unsigned long long)(V.n_yaw > 0 ? V.n_yaw : 0);
-  if (n_items == 0) return cudaSuccess;
-  SprJoinLaunch L = K;
-  L.shard_index = si; L.shard_count = sc;
-  const size_t smem = SPJ_WARPS * 32 * sizeof(SpjQuery) + (SPJ_TILE_WORDS + SPJ_WARPS * (SPJ_LIST + SPJ_RANGE_WORDS)) * sizeof(uint32_t) +
-                      SPJ_SEG_GROUPS * sizeof(uint16_t);
+template <int WARPS, int CTAS>
+static cudaError_t spj_launch(const SprJoinView &V, const SprJoinLaunch &L, uint32_t n_local, unsigned long long n_items, int sm_count, cudaStream_t st) {
+  constexpr size_t smem = WARPS * 32 * sizeof(SpjQuery) + (SPJ_TILE_WORDS + WARPS * (SPJ_LIST + SPJ_RANGE_WORDS)) * sizeof(uint32_t) +
+                          WARPS * 32 * 4 * sizeof(uint16_t);
   // the opt-in to more than 48 KB of dynamic shared memory and the residency query are per device: done once
   static int per_sm_of_device[64] = {0};
   int dev = 0;
@@ -344,14 +343,26 @@ cudaError_t spr_launch_join_score(const SprJoinView &V, const SprJoinLaunch &K, 
   if (e != cudaSuccess) return e;
   int per_sm = dev >= 0 && dev < 64 ? per_sm_of_device[dev] : 0;
   if (per_sm == 0) {
-    e = cudaFuncSetAttribute(spr_join_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(spr_join_score_kernel<WARPS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spr_join_score_kernel, SPJ_THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spr_join_score_kernel<WARPS, CTAS>, WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     if (dev >= 0 && dev < 64) per_sm_of_device[dev] = per_sm;
   }
   const unsigned long long cap = (unsigned long long)sm_count * (unsigned long long)per_sm;
-  spr_join_score_kernel<<<(unsigned)(n_items < cap ? n_items : cap), SPJ_THREADS, smem, st>>>(V, L, n_local, n_items);
+  spr_join_score_kernel<WARPS, CTAS><<<(unsigned)(n_items < cap ? n_items : cap), WARPS * 32, smem, st>>>(V, L, n_local, n_items);
   return cudaGetLastError();
+}
+
+cudaError_t spr_launch_join_score(const SprJoinView &V, const SprJoinLaunch &K, int sm_count, cudaStream_t st) {
+  const int sc = K.shard_count > 1 ? K.shard_count : 1, si = K.shard_count > 1 ? K.shard_index : 0;
+  const uint32_t n_local = V.n_blocks > (uint32_t)si ? (V.n_blocks - (uint32_t)si + (uint32_t)sc - 1) / (uint32_t)sc : 0u;
+  const unsigned long long n_items = (unsigned long long)n_local * (unsigned long long)(V.n_yaw > 0 ? V.n_yaw : 0);
+  if (n_items == 0) return cudaSuccess;
+  SprJoinLaunch L = K;
+  L.shard_index = si; L.shard_count = sc;
+  // small query maps (at most 16 quads per work item): narrow CTAs, more of them
+  if (V.n_groups <= 64) return spj_launch<4, 7>(V, L, n_local, n_items, sm_count, st);
+  return spj_launch<SPJ_WARPS, SPJ_MIN_CTAS>(V, L, n_local, n_items, sm_count, st);
 }

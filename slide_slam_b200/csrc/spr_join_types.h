@@ -2,14 +2,15 @@
 #pragma once
 #include <stdint.h>
 
+#ifndef SPJ_WARPS
 #define SPJ_WARPS 8
+#endif
 #define SPJ_THREADS (SPJ_WARPS * 32)
 #ifndef SPJ_SLOT_BITS
 #define SPJ_SLOT_BITS 12
 #endif
 #define SPJ_MAX_SLOTS (1 << SPJ_SLOT_BITS)   // lattice samples per block (slot index in the block's arg-max)
 #define SPJ_TILE_WORDS SPJ_MAX_SLOTS         // shared-memory words of a block's counters: two arrays of nx * ((ny >> 1) + 1)
-#define SPJ_SEG_GROUPS (SPJ_THREADS * 4)     // query groups whose visibility is tested per pass
 #ifndef SPJ_LIST
 #define SPJ_LIST 256                         // per-warp list of (landmark, record) pairs that passed the filter, entries
 #endif
