@@ -542,14 +542,14 @@ static int join_prepare(slide_pr_handle *h) {
                             h->lat_p.match_xy_step_size == h->p.match_xy_step_size &&
                             h->lat_p.match_yaw_angle_step_size == h->p.match_yaw_angle_step_size &&
                             h->lat_p.disable_yaw_search == h->p.disable_yaw_search && !h->L.ring_major;
-  // the three host builds are independent: lattice + blocks and the reference-side bins on the helper threads,
-  // the query groups (which need the reference map's labels only) on this one
-  std::string lattice_err, ref_err;
-  bool lattice_started = false, ref_started = false;
+  // the three host builds are independent: lattice + blocks and the query groups on the helper threads (a sleeping
+  // thread takes a while to wake up), the reference-side bins -- the longest of the three -- on this one
+  std::string lattice_err, query_err;
+  bool lattice_started = false, query_started = false;
   struct Joiner {
     slide_pr_handle *h; bool *l, *q;
     ~Joiner() { if (*l) h->worker_lattice.wait(); if (*q) h->worker_query.wait(); }
-  } joiner{h, &lattice_started, &ref_started};
+  } joiner{h, &lattice_started, &query_started};
   if (!same_lattice) {
     h->lattice_valid = false; h->j_blocks_valid = false;
   } else {
@@ -566,33 +566,18 @@ static int join_prepare(slide_pr_handle *h) {
     });
     lattice_started = true;
   }
-  // labels of the reference map: needed by the query groups before the bins are complete
-  std::vector<double> labels;
+  // query groups (label-major, Morton order inside a label): they need the reference map's labels only, which the job
+  // collects itself while the bins (and with them rs->J.labels) are being rebuilt
+  h->worker_query.submit([h, rs, same_ref, &query_err]() {
+    cudaSetDevice(h->device);
+    std::vector<double> labels;
+    if (!same_ref) spr::unique_labels(rs->cached_ref.data(), h->n_ref, labels);
+    return spr::build_query_set(same_ref ? rs->J.labels : labels, h->qry_rows.data(), h->n_qry, h->JQ, query_err);
+  });
+  query_started = true;
   if (!same_ref) {
     rs->join_valid = false;
-    spr::unique_labels(rs->cached_ref.data(), h->n_ref, labels);
-    h->worker_query.submit([h, rs, &ref_err]() {
-      cudaSetDevice(h->device);
-      return spr::build_join_ref(h->p, rs->cached_ref.data(), h->n_ref, rs->J, ref_err);
-    });
-    ref_started = true;
-  } else {
-    h->reuse_flags |= 2;
-  }
-  // query groups (label-major, Morton order inside a label)
-  if ((rc = spr::build_query_set(same_ref ? rs->J.labels : labels, h->qry_rows.data(), h->n_qry, h->JQ, h->err)) != SLIDE_PR_OK) return rc;
-  const int n_groups = h->JQ.nqp / SPR_QGROUP;
-  h->j_glabel.assign((size_t)std::max(n_groups, 1), 0);
-  for (int g = 0; g < n_groups; g++) h->j_glabel[g] = h->JQ.qlabel[(size_t)g * SPR_QGROUP];  // a group's first entry is never padding
-  if ((rc = upload(h, h->dj_qxy, h->JQ.qxy, st))) return rc;
-  if ((rc = upload(h, h->dj_qdims, h->JQ.qdims, st))) return rc;
-  if ((rc = upload(h, h->dj_qlabel, h->JQ.qlabel, st))) return rc;
-  if ((rc = upload(h, h->dj_glabel, h->j_glabel, st))) return rc;
-  g_trace.mark("join_queries");
-  if (ref_started) {
-    rc = h->worker_query.wait();
-    ref_started = false;
-    if (rc != SLIDE_PR_OK) { h->err = ref_err; return rc; }
+    if ((rc = spr::build_join_ref(h->p, rs->cached_ref.data(), h->n_ref, rs->J, h->err)) != SLIDE_PR_OK) return rc;
     g_trace.mark("join_ref_build");
     if ((rc = upload(h, rs->dj_rec0, rs->J.rec[0], st))) return rc;
     if ((rc = upload(h, rs->dj_rec1, rs->J.rec[1], st))) return rc;
@@ -604,7 +589,20 @@ static int join_prepare(slide_pr_handle *h) {
     if ((rc = upload(h, rs->dj_labelbox, rs->J.labelbox, st))) return rc;
     rs->join_valid = true;
     rs->join_p = h->p;
+  } else {
+    h->reuse_flags |= 2;
   }
+  rc = h->worker_query.wait();
+  query_started = false;
+  if (rc != SLIDE_PR_OK) { h->err = query_err; return rc; }
+  const int n_groups = h->JQ.nqp / SPR_QGROUP;
+  h->j_glabel.assign((size_t)std::max(n_groups, 1), 0);
+  for (int g = 0; g < n_groups; g++) h->j_glabel[g] = h->JQ.qlabel[(size_t)g * SPR_QGROUP];  // a group's first entry is never padding
+  if ((rc = upload(h, h->dj_qxy, h->JQ.qxy, st))) return rc;
+  if ((rc = upload(h, h->dj_qdims, h->JQ.qdims, st))) return rc;
+  if ((rc = upload(h, h->dj_qlabel, h->JQ.qlabel, st))) return rc;
+  if ((rc = upload(h, h->dj_glabel, h->j_glabel, st))) return rc;
+  g_trace.mark("join_queries");
   if (lattice_started) {
     rc = h->worker_lattice.wait();
     lattice_started = false;

@@ -116,11 +116,34 @@ struct RectEmitter {
 
 }  // namespace
 
+// One axis of a ring's lattice: the samples start, start + step, ... <= end by repeated fp64 addition, exactly
+// as the reference's loops (PR.cpp:230-232), written to out[0 .. cap).  In the shadow of the addition chain:
+// the closed index range [*lo, *hi] of the samples inside [in_lo, in_hi] (left untouched when there is none) and
+// the largest deviation of a sample from start + i * step (folded into *drift).  Returns the count, cap + 1 when
+// cap does not suffice.
+static uint32_t accumulate_samples(double start, double end, double step, double *out, uint32_t cap, double in_lo, double in_hi,
+                                   int *lo, int *hi, double *drift) {
+  uint32_t n = 0;
+  int l = -1, h = -1;
+  double d0 = 0.0, d1 = 0.0;
+  for (double v = start; v <= end; v += step) {
+    if (n >= cap) return cap + 1;
+    out[n] = v;
+    if (v >= in_lo && v <= in_hi) { if (l < 0) l = (int)n; h = (int)n; }
+    const double dev = std::fabs(v - (start + (double)n * step));
+    if (n & 1u) d1 = std::max(d1, dev); else d0 = std::max(d0, dev);
+    n++;
+  }
+  if (l >= 0) { *lo = l; *hi = h; }
+  *drift = std::max(*drift, std::max(d0, d1));
+  return n;
+}
+
 int build_lattice(const slide_pr_params &p, double half_x, double half_y, double yaw_half,
                   int64_t trans_begin, int64_t trans_end, bool ring_major, Lattice &L, std::string &err,
                   bool rings_only) {
   // reset, keeping the vectors' capacity across calls
-  L.status = 0; L.rings = 0; L.ox = L.oy = 0; L.n_translations = 0; L.ring_major = false;
+  L.status = 0; L.rings = 0; L.ox = L.oy = 0; L.n_translations = 0; L.ring_major = false; L.drift = 0;
   L.yaw.clear(); L.cs.clear(); L.lat.clear(); L.ring.clear();
   // L.chunks keeps its size while chunks are emitted (n_emitted tracks the fill level); every exit
   // before the emission is complete leaves it empty
@@ -179,35 +202,26 @@ int build_lattice(const slide_pr_params &p, double half_x, double half_y, double
     L.lat.resize(lat0 + (size_t)est_x + (size_t)est_y);
     double *lp = L.lat.data() + lat0;
     R.x_off = (uint32_t)lat0;
-    uint32_t n = 0;
-    for (double x = x_neg_start; x <= x_pos_end; x += step) {                // PR.cpp:230
-      if (n >= (uint32_t)est_x) { err = "internal: lattice sample estimate too small"; return SLIDE_PR_ERR_INTERNAL; }
-      lp[n++] = x;
-    }
+    // samples, already-searched centre box as closed index ranges (PR.cpp:238-239) and drift, in one pass per axis
+    R.ixl = 0; R.ixh = -1; R.iyl = 0; R.iyh = -1;
+    uint32_t n = accumulate_samples(x_neg_start, x_pos_end, step, lp, (uint32_t)est_x, x_left_prev, x_right_prev, &R.ixl, &R.ixh, &L.drift);  // PR.cpp:230
+    if (n > (uint32_t)est_x) { err = "internal: lattice sample estimate too small"; return SLIDE_PR_ERR_INTERNAL; }
     R.nx = n;
     R.y_off = R.x_off + n;
     lp += n;
-    n = 0;
-    for (double y = y_neg_start; y <= y_pos_end; y += step) {                // PR.cpp:232
-      if (n >= (uint32_t)est_y) { err = "internal: lattice sample estimate too small"; return SLIDE_PR_ERR_INTERNAL; }
-      lp[n++] = y;
+    if (y_neg_start == x_neg_start && y_pos_end == x_pos_end && y_left_prev == x_left_prev && y_right_prev == x_right_prev &&
+        n <= (uint32_t)est_y) {
+      // square search range (the usual case, PR.cpp:777-782): the y loop adds the same numbers in the same order
+      std::memcpy(lp, lp - n, (size_t)n * sizeof(double));
+      R.iyl = R.ixl; R.iyh = R.ixh;
+    } else {
+      n = accumulate_samples(y_neg_start, y_pos_end, step, lp, (uint32_t)est_y, y_left_prev, y_right_prev, &R.iyl, &R.iyh, &L.drift);         // PR.cpp:232
+      if (n > (uint32_t)est_y) { err = "internal: lattice sample estimate too small"; return SLIDE_PR_ERR_INTERNAL; }
     }
     R.ny = n;
     L.lat.resize((size_t)R.y_off + n);
     // lat may have been reallocated: take pointers now
     const double *xs = L.lat.data() + R.x_off, *ys = L.lat.data() + R.y_off;
-    // already-searched centre box as closed index ranges, PR.cpp:238-239
-    R.ixl = 0; R.ixh = -1; R.iyl = 0; R.iyh = -1;
-    {
-      int lo = -1, hi = -1;
-      for (int i = 0; i < (int)R.nx; i++)
-        if (xs[i] >= x_left_prev && xs[i] <= x_right_prev) { if (lo < 0) lo = i; hi = i; }
-      if (lo >= 0) { R.ixl = lo; R.ixh = hi; }
-      lo = hi = -1;
-      for (int i = 0; i < (int)R.ny; i++)
-        if (ys[i] >= y_left_prev && ys[i] <= y_right_prev) { if (lo < 0) lo = i; hi = i; }
-      if (lo >= 0) { R.iyl = lo; R.iyh = hi; }
-    }
     const int n_in_x = R.ixh >= R.ixl ? R.ixh - R.ixl + 1 : 0;
     const int n_in_y = R.iyh >= R.iyl ? R.iyh - R.iyl + 1 : 0;
     const bool has_box = n_in_x > 0 && n_in_y > 0;
@@ -732,14 +746,42 @@ int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, Join
   J.Sstar = div3_threshold(p.match_threshold_dimension);
   const bool matchable = thr > 0 && std::isfinite(thr);
   J.reach = matchable ? thr * (1.0 + 1e-9) + 1e-9 : 0.0;  // covers the fp64 rounding of the reference's test
+  // pass 1: extent of the map and the label bucket of every landmark.  Maps carry a handful of classes: the
+  // distinct labels are collected in order of appearance (linear search) and ranked afterwards; maps with
+  // many labels take the sorted-vector path.
   double minx = HUGE_VAL, maxx = -HUGE_VAL, miny = HUGE_VAL, maxy = -HUGE_VAL;
+  std::vector<int32_t> lab((size_t)std::max(n_ref, 1), -1), cxs((size_t)std::max(n_ref, 1), 0), cys((size_t)std::max(n_ref, 1), 0);
+  constexpr int kSeenMax = 16;
+  double seen[kSeenMax];
+  int n_seen = 0;
+  bool few_labels = true;
   for (int i = 0; i < n_ref; i++) {
     const double *r = ref7 + 7 * (size_t)i;
     if (!std::isfinite(r[1]) || !std::isfinite(r[2])) { err = "non-finite reference coordinate"; return SLIDE_PR_ERR_NONFINITE; }
     minx = std::min(minx, r[1]); maxx = std::max(maxx, r[1]);
     miny = std::min(miny, r[2]); maxy = std::max(maxy, r[2]);
+    if (!few_labels || !(r[0] == r[0])) continue;  // NaN labels never compare equal (PR.cpp:306)
+    int k = 0;
+    while (k < n_seen && seen[k] != r[0]) k++;      // -0.0 == 0.0: one label
+    if (k == n_seen) {
+      if (n_seen == kSeenMax) { few_labels = false; continue; }
+      seen[n_seen++] = r[0] + 0.0;
+    }
+    lab[i] = k;
   }
-  unique_labels(ref7, n_ref, J.labels);  // NaN labels never compare equal (PR.cpp:306)
+  if (few_labels) {
+    int order[kSeenMax], rank[kSeenMax];
+    for (int k = 0; k < n_seen; k++) order[k] = k;
+    std::sort(order, order + n_seen, [&](int a, int b) { return seen[a] < seen[b]; });
+    for (int k = 0; k < n_seen; k++) { rank[order[k]] = k; J.labels.push_back(seen[order[k]]); }
+    for (int i = 0; i < n_ref; i++) if (lab[i] >= 0) lab[i] = rank[lab[i]];
+  } else {
+    unique_labels(ref7, n_ref, J.labels);
+    for (int i = 0; i < n_ref; i++) {
+      const double l = ref7[7 * (size_t)i];
+      lab[i] = l == l ? (int)(std::lower_bound(J.labels.begin(), J.labels.end(), l + 0.0) - J.labels.begin()) : -1;
+    }
+  }
   const int n_labels = (int)J.labels.size();
   if (n_ref == 0) { minx = maxx = miny = maxy = 0; }
   // coarse grid: cells of 8 lattice steps (a block is about 10 steps wide), not smaller than the reach,
@@ -759,8 +801,7 @@ int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, Join
   J.ncx = (int)std::floor((maxx - minx) * J.inv_w) + 1;
   J.ncy = (int)std::floor((maxy - miny) * J.inv_w) + 1;
   const size_t n_cells = (size_t)J.ncx * (size_t)J.ncy;
-  // label bucket, cell and label bounding box of every landmark
-  std::vector<int32_t> lab((size_t)std::max(n_ref, 1), -1), cxs((size_t)std::max(n_ref, 1), 0), cys((size_t)std::max(n_ref, 1), 0);
+  // pass 2: cell and label bounding box of every landmark
   J.labelbox.assign(4 * (size_t)std::max(n_labels, 1), 0.0);
   for (int l = 0; l < n_labels; l++) {
     J.labelbox[4 * (size_t)l] = HUGE_VAL; J.labelbox[4 * (size_t)l + 1] = -HUGE_VAL;
@@ -768,30 +809,31 @@ int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, Join
   }
   size_t n_kept = 0;
   for (int i = 0; i < n_ref; i++) {
+    if (lab[i] < 0) continue;
     const double *r = ref7 + 7 * (size_t)i;
-    if (!(r[0] == r[0])) continue;
-    const int l = (int)(std::lower_bound(J.labels.begin(), J.labels.end(), r[0] + 0.0) - J.labels.begin());
-    lab[i] = l; cxs[i] = cell_of(r[1], J.gx0, J.ncx); cys[i] = cell_of(r[2], J.gy0, J.ncy);
-    double *lb = J.labelbox.data() + 4 * (size_t)l;
+    cxs[i] = cell_of(r[1], J.gx0, J.ncx); cys[i] = cell_of(r[2], J.gy0, J.ncy);
+    double *lb = J.labelbox.data() + 4 * (size_t)lab[i];
     lb[0] = std::min(lb[0], r[1]); lb[1] = std::max(lb[1], r[1]);
     lb[2] = std::min(lb[2], r[2]); lb[3] = std::max(lb[3], r[2]);
     n_kept++;
   }
-  // counting sort into both join orders (label, band, along cell); ascending reference index inside a cell
+  // counting sort into both join orders (label, band, along cell); ascending reference index inside a cell.
+  // Counts go two slots up, so that after the prefix sum cs[key + 1] is the key's insertion cursor and, once
+  // every landmark is placed, cs[0 .. n_keys] is the table of first records (cs[n_keys + 1] repeats the total).
   std::vector<uint32_t> pos0, pos1;  // record position of landmark i in each order
   pos0.assign((size_t)std::max(n_ref, 1), 0u); pos1 = pos0;
   for (int d = 0; d < 2; d++) {
     uvec<uint32_t> &cs = J.cell_start[d];
-    cs.assign((size_t)std::max(n_labels, 1) * n_cells + 1, 0u);
-    auto key = [&](int i) -> size_t {
-      const size_t c = d == 0 ? (size_t)cxs[i] * (size_t)J.ncy + (size_t)cys[i] : (size_t)cys[i] * (size_t)J.ncx + (size_t)cxs[i];
-      return (size_t)lab[i] * n_cells + c;
-    };
-    for (int i = 0; i < n_ref; i++) if (lab[i] >= 0) cs[key(i) + 1]++;
-    for (size_t k = 1; k < cs.size(); k++) cs[k] += cs[k - 1];
-    std::vector<uint32_t> fill(cs.begin(), cs.end() - 1);
+    cs.assign((size_t)std::max(n_labels, 1) * n_cells + 2, 0u);
     std::vector<uint32_t> &pos = d == 0 ? pos0 : pos1;
-    for (int i = 0; i < n_ref; i++) if (lab[i] >= 0) pos[i] = fill[key(i)]++;
+    for (int i = 0; i < n_ref; i++) {   // pos holds the landmark's key until it is placed
+      if (lab[i] < 0) continue;
+      const size_t c = d == 0 ? (size_t)cxs[i] * (size_t)J.ncy + (size_t)cys[i] : (size_t)cys[i] * (size_t)J.ncx + (size_t)cxs[i];
+      pos[i] = (uint32_t)((size_t)lab[i] * n_cells + c);
+      cs[(size_t)pos[i] + 2]++;
+    }
+    for (size_t k = 1; k < cs.size(); k++) cs[k] += cs[k - 1];
+    for (int i = 0; i < n_ref; i++) if (lab[i] >= 0) pos[i] = cs[(size_t)pos[i] + 1]++;
     J.rec[d].assign(std::max<size_t>(n_kept, 1), SprJoinRef{});
     J.xy[d].assign(2 * std::max<size_t>(n_kept, 1), 0.0);
   }
@@ -805,8 +847,8 @@ int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, Join
   const uvec<uint32_t> &cs0 = J.cell_start[0];
   std::vector<int32_t> by_pos0(std::max<size_t>(n_kept, 1), -1);  // landmark at each record position of order 0
   for (int i = 0; i < n_ref; i++) if (lab[i] >= 0) by_pos0[pos0[i]] = i;
-  for (int i = 0; i < n_ref; i++) {
-    if (lab[i] < 0) continue;
+  for (size_t at = 0; at < n_kept; at++) {   // in record order: the cell table is read front to back
+    const int i = by_pos0[at];
     const double *r = ref7 + 7 * (size_t)i;
     const uint32_t off = (uint32_t)J.nbr.size();
     if (matchable) {
@@ -815,7 +857,7 @@ int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, Join
         const size_t base = (size_t)lab[i] * n_cells + (size_t)cx * (size_t)J.ncy;
         for (uint32_t k = cs0[base + cy0]; k < cs0[base + cy1 + 1]; k++) {
           const int o = by_pos0[k];
-          if (o >= i) continue;  // ascending inside a cell, but cells are visited in any order
+          if (o >= i) continue;  // only landmarks the reference meets earlier (PR.cpp:299: input order)
           const double *q = ref7 + 7 * (size_t)o;
           if (std::fabs(q[1] - r[1]) <= r2 && std::fabs(q[2] - r[2]) <= r2) J.nbr.push_back(SprJoinNbr{q[1], q[2], q[4], q[5], q[6]});
         }
@@ -823,9 +865,9 @@ int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, Join
     }
     const uint32_t cnt = (uint32_t)J.nbr.size() - off;
     const SprJoinRef rec{r[1], r[2], r[4], r[5], r[6], off, cnt};
-    J.rec[0][pos0[i]] = rec;
+    J.rec[0][at] = rec;
     J.rec[1][pos1[i]] = rec;
-    J.xy[0][2 * (size_t)pos0[i]] = r[1]; J.xy[0][2 * (size_t)pos0[i] + 1] = r[2];
+    J.xy[0][2 * at] = r[1]; J.xy[0][2 * at + 1] = r[2];
     J.xy[1][2 * (size_t)pos1[i]] = r[1]; J.xy[1][2 * (size_t)pos1[i] + 1] = r[2];
   }
   if (J.nbr.empty()) J.nbr.push_back(SprJoinNbr{});
@@ -834,8 +876,6 @@ int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, Join
 
 int build_join_blocks(const Lattice &L, double step, uvec<SprJoinBlock> &blocks, double *drift, std::string &err) {
   blocks.clear();
-  double dmax = 0.0;
-  const double *lat = L.lat.data();
   // a rectangle ix in [ix0, ix1), iy in [iy0, iy1) of ring k; ordinal(ix, iy) = ord0 + (ix - ix0) * row_stride + (iy - iy0)
   auto rect = [&](const Lattice::Ring &R, uint32_t k, int ix0, int ix1, int iy0, int iy1, uint64_t ord0, uint64_t row_stride) {
     const int w = ix1 - ix0, h = iy1 - iy0;
@@ -871,9 +911,6 @@ int build_join_blocks(const Lattice &L, double step, uvec<SprJoinBlock> &blocks,
   };
   for (size_t k = 0; k < L.ring.size(); k++) {
     const Lattice::Ring &R = L.ring[k];
-    const double *xs = lat + R.x_off, *ys = lat + R.y_off;
-    for (uint32_t i = 0; i < R.nx; i++) dmax = std::max(dmax, std::fabs(xs[i] - (xs[0] + (double)i * step)));
-    for (uint32_t i = 0; i < R.ny; i++) dmax = std::max(dmax, std::fabs(ys[i] - (ys[0] + (double)i * step)));
     const int nx = (int)R.nx, ny = (int)R.ny;
     const int n_in_x = R.ixh >= R.ixl ? R.ixh - R.ixl + 1 : 0, n_in_y = R.iyh >= R.iyl ? R.iyh - R.iyl + 1 : 0;
     const uint64_t ord = R.ord_base;
@@ -890,7 +927,7 @@ int build_join_blocks(const Lattice &L, double step, uvec<SprJoinBlock> &blocks,
     }
     if (blocks.size() > (1u << 24)) { err = "more than 2^24 lattice blocks"; return SLIDE_PR_ERR_UNSUPPORTED; }
   }
-  if (drift) *drift = dmax;
+  if (drift) *drift = L.drift;
   return SLIDE_PR_OK;
 }
 

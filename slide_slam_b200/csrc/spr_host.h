@@ -51,6 +51,7 @@ struct Lattice {
   };
   std::vector<Ring> ring;
   uint64_t n_translations = 0;
+  double drift = 0;               // largest deviation of a sample from (first sample of its axis) + index * step, over all rings
   uvec<SprChunk> chunks;   // grouped by direction (see dir_begin / Ring::dbegin), warp-padded
   uvec<SprChunk> scratch;  // regrouping buffer, kept for its capacity
   std::vector<int32_t> succ;      // scratch of build_lattice (kept for their capacity)
@@ -142,7 +143,7 @@ struct JoinRef {
   std::vector<double> labels;        // distinct finite reference labels, ascending
   uvec<SprJoinRef> rec[2];
   uvec<double> xy[2];                // [records][2]: the coordinates alone, for the candidate filter
-  uvec<uint32_t> cell_start[2];      // [n_labels * n_cells + 1]
+  uvec<uint32_t> cell_start[2];      // [n_labels * n_cells + 1] first record of (label, cell) (+ one spare entry)
   uvec<SprJoinNbr> nbr;
   uvec<double> labelbox;             // [n_labels][4]
   double gx0 = 0, gy0 = 0, w = 1, inv_w = 1;
@@ -153,7 +154,7 @@ struct JoinRef {
   int n_ref = 0;
 };
 int build_join_ref(const slide_pr_params &p, const double *ref7, int n_ref, JoinRef &J, std::string &err);
-// blocks of the lattice L (needs L.ring / L.lat); *drift: largest deviation of a sample from
+// blocks of the lattice L (needs L.ring / L.lat); *drift: L.drift, the largest deviation of a sample from
 // first sample + index * step over all rings
 int build_join_blocks(const Lattice &L, double step, uvec<SprJoinBlock> &blocks, double *drift, std::string &err);
 

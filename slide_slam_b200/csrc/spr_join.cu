@@ -117,25 +117,33 @@ __device__ __forceinline__ void spj_quad(const SprJoinView &V, const SpjBlock &B
     }
     if (lane == 31) pre[32 * SPJ_BANDS] = total;
     __syncwarp();
-    for (uint32_t w0 = 0; w0 < total; w0 += 32) {
-      const uint32_t w = w0 + (uint32_t)lane;   // consecutive lanes take consecutive candidates: neighbouring records, coalesced loads
-      uint32_t e = 0u;
-      bool ok = false;
-      if (w < total) {
-        const uint32_t *rp = pre;   // -> the last range that starts at or before candidate w (empty ranges share their start with the next one)
+    for (uint32_t w0 = 0; w0 < total; w0 += 64) {
+      // two candidates per lane and step (w and w + 32): their range searches and coordinate loads are independent of
+      // each other, which hides part of the latency of the dependent shared-memory and global loads; consecutive
+      // lanes still take consecutive candidates (neighbouring records, coalesced loads)
+      const uint32_t wa = w0 + (uint32_t)lane, wb = wa + 32u;
+      // -> the last range that starts at or before the candidate (empty ranges share their start with the next one);
+      // the search stays inside the table for any w, as pre[32 * SPJ_BANDS] = total
+      const uint32_t *ra = pre, *rb = pre;
 #pragma unroll
-        for (uint32_t step = 16 * SPJ_BANDS; step >= 1; step >>= 1)
-          if (rp[step] <= w) rp += step;
-        const uint32_t lo = (uint32_t)(rp - pre);
-        e = ((rp[32 * SPJ_BANDS + 1] + (w - rp[0])) << 5) | (lo / SPJ_BANDS);   // beg = pre + 32 * SPJ_BANDS + 1
-        const double2 p = __ldg(xy + (e >> 5));
-        const SpjQuery &q = sq[e & 31u];
-        ok = spj_near(B, q.rx, q.ry, p.x, p.y);
+      for (uint32_t step = 16 * SPJ_BANDS; step >= 1; step >>= 1) {
+        if (ra[step] <= wa) ra += step;
+        if (rb[step] <= wb) rb += step;
       }
-      const uint32_t m = __ballot_sync(SPJ_FULL, ok);
-      if (ok) list[n_pairs + (uint32_t)__popc(m & ((1u << lane) - 1u))] = e;
-      n_pairs += (uint32_t)__popc(m);
-      if (n_pairs + 32u > (uint32_t)SPJ_LIST) {   // the pair list is full: exact tests and counter updates now
+      uint32_t ea = 0u, eb = 0u;
+      bool oka = false, okb = false;
+      double2 pa = make_double2(0.0, 0.0), pb = pa;
+      // entry = (record << 5) | lane of the query landmark; beg = pre + 32 * SPJ_BANDS + 1
+      if (wa < total) { ea = ((ra[32 * SPJ_BANDS + 1] + (wa - ra[0])) << 5) | ((uint32_t)(ra - pre) / SPJ_BANDS); pa = __ldg(xy + (ea >> 5)); }
+      if (wb < total) { eb = ((rb[32 * SPJ_BANDS + 1] + (wb - rb[0])) << 5) | ((uint32_t)(rb - pre) / SPJ_BANDS); pb = __ldg(xy + (eb >> 5)); }
+      if (wa < total) { const SpjQuery &q = sq[ea & 31u]; oka = spj_near(B, q.rx, q.ry, pa.x, pa.y); }
+      if (wb < total) { const SpjQuery &q = sq[eb & 31u]; okb = spj_near(B, q.rx, q.ry, pb.x, pb.y); }
+      const uint32_t ma = __ballot_sync(SPJ_FULL, oka), mb = __ballot_sync(SPJ_FULL, okb);
+      const uint32_t below = (1u << lane) - 1u, na = (uint32_t)__popc(ma);
+      if (oka) list[n_pairs + (uint32_t)__popc(ma & below)] = ea;
+      if (okb) list[n_pairs + na + (uint32_t)__popc(mb & below)] = eb;
+      n_pairs += na + (uint32_t)__popc(mb);
+      if (n_pairs + 64u > (uint32_t)SPJ_LIST) {   // the pair list may not take another step: exact tests and counter updates now
         __syncwarp();
         spj_pairs(V, B, rec, sq, list, n_pairs, lane, tile);
         __syncwarp();

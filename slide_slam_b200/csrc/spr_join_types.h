@@ -12,7 +12,7 @@
 #define SPJ_MAX_SLOTS (1 << SPJ_SLOT_BITS)   // lattice samples per block (slot index in the block's arg-max)
 #define SPJ_TILE_WORDS SPJ_MAX_SLOTS         // shared-memory words of a block's counters: two arrays of nx * ((ny >> 1) + 1)
 #ifndef SPJ_LIST
-#define SPJ_LIST 256                         // per-warp list of (landmark, record) pairs that passed the filter, entries
+#define SPJ_LIST 256                         // per-warp list of (landmark, record) pairs that passed the filter, entries (>= 64)
 #endif
 #define SPJ_BANDS 4                          // coarse-cell bands of a landmark whose record ranges one pass gathers
 #define SPJ_RANGE_WORDS (2 * 32 * SPJ_BANDS + 2)   // per warp: start of every range in the flat candidate sequence (+ end), first record

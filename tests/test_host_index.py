@@ -125,6 +125,16 @@ def test_edge_cases():
     r3[1, 0] = -0.0
     q3[1, 0] = 0.0
     _check_counts(op, r3, q3, 6.0, 6.0)
+    # more distinct labels than the reference-side builder collects by linear search (16): its sorted-vector path,
+    # with NaN and -0.0 labels among them, in descending and in shuffled order of appearance
+    r6, q6 = H.random_maps(rng, 60, 50, extent=4.0)
+    r6[:, 0] = np.arange(60)[::-1] % 23 - 3.0
+    q6[:, 0] = rng.integers(-3, 20, 50)
+    r6[5, 0] = np.nan; r6[7, 0] = -0.0; q6[3, 0] = np.nan
+    assert _check_counts(op, r6, q6, 6.0, 6.0)["best_num_inliers"] > 0
+    r6[:, 0] = rng.permutation(60) % 16 * 0.5      # exactly 16 labels: still the linear-search path
+    q6[:, 0] = rng.integers(0, 16, 50) * 0.5
+    assert _check_counts(op, r6, q6, 6.0, 6.0)["best_num_inliers"] > 0
     # all landmarks identical (every reference object matches every query object)
     r4 = np.tile(np.array([[2, 1.0, 1.0, 0, 0.5, 0, 0]], float), (6, 1))
     q4 = np.tile(np.array([[2, 0.0, 0.0, 0, 0.5, 0, 0]], float), (5, 1))
