@@ -30,6 +30,7 @@ extras : generator (triangle-hypothesis set (T) on the same pair), config3_shard
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -263,6 +264,13 @@ def run_ours(args, rank, world, local_rank):
 
     def timed_steps(handle, exhaustive, steps):
         step_ms, kern_ms, hyps, launches, last = [], [], 0, 0, None
+        gc.collect(); gc.disable()              # no collector pause between a step's two events (as timeit does)
+        try:
+            return _timed_steps(handle, exhaustive, steps, step_ms, kern_ms, hyps, launches, last)
+        finally:
+            gc.enable()
+
+    def _timed_steps(handle, exhaustive, steps, step_ms, kern_ms, hyps, launches, last):
         for i in range(steps):
             flush.fill_(1)                      # L2 flush between timed iterations (not timed)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -351,6 +359,7 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        gc.collect(); gc.disable()
         t0 = time.perf_counter()
         n_h, reused, last = 0, 0, None
         for i in range(args.steps):
@@ -359,6 +368,7 @@ def run_ours(args, rank, world, local_rank):
             reused |= last.match.reuse
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        gc.enable()
         t = torch.tensor([dt, float(n_h)], dtype=torch.float64, device=dev)
         if world > 1:
             a_ = t.clone(); dist.all_reduce(a_, op=dist.ReduceOp.MAX)

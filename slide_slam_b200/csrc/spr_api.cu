@@ -482,6 +482,7 @@ static int prepare_impl(slide_pr_handle *h, RefSide *slot, bool trusted, const d
   // the previous prepare's uploads read the handle's page-locked vectors asynchronously: they must have
   // been consumed before those vectors are rebuilt (a search in between has already waited for them)
   SPR_CUDA(h, cudaEventSynchronize(h->ev_prep));
+  g_trace.mark("prev_uploads_wait");
   h->half_x = half_x; h->half_y = half_y;
   h->h2d_bytes = 0;
   h->yaw_half = h->p.inter_loop_closure ? h->p.match_yaw_half_range : h->p.match_yaw_half_range_intra;
@@ -589,11 +590,13 @@ static int join_prepare(slide_pr_handle *h) {
     if ((rc = upload(h, rs->dj_labelbox, rs->J.labelbox, st))) return rc;
     rs->join_valid = true;
     rs->join_p = h->p;
+    g_trace.mark("join_ref_upload");
   } else {
     h->reuse_flags |= 2;
   }
   rc = h->worker_query.wait();
   query_started = false;
+  g_trace.mark("join_queries_wait");
   if (rc != SLIDE_PR_OK) { h->err = query_err; return rc; }
   const int n_groups = h->JQ.nqp / SPR_QGROUP;
   h->j_glabel.assign((size_t)std::max(n_groups, 1), 0);
@@ -606,6 +609,7 @@ static int join_prepare(slide_pr_handle *h) {
   if (lattice_started) {
     rc = h->worker_lattice.wait();
     lattice_started = false;
+    g_trace.mark("join_blocks_wait");
     if (rc != SLIDE_PR_OK) { h->err = lattice_err; return rc; }
     if (!same_lattice) {
       h->lat_hx = h->half_x; h->lat_hy = h->half_y; h->lat_yaw_half = h->yaw_half; h->lat_p = h->p;

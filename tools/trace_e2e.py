@@ -8,7 +8,7 @@ ROS = {"search_xy_step_size": 0.5, "search_yaw_step_size_degrees": 5.0, "match_t
        "match_threshold_dimension": 1.0, "ignore_dimension": 0, "min_num_inliers": 15}
 pr = PlaceRecognition(ROS)
 pairs = [synth.make_pair(2000, seed=1002, classes="five", outlier_frac=0.1)[:2], synth.make_pair(2000, seed=1002 + 100000, classes="five", outlier_frac=0.1)[:2]]
-for i in range(8):
+for i in range(12):
     ref, qry = pairs[i & 1]
     t0 = time.perf_counter()
     out = pr.findTransformation(ref, qry)
