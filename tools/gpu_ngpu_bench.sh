@@ -1,5 +1,5 @@
 #!/bin/bash
-# N-GPU bench (NCCL).  usage: gpu_t.sh N [steps] [extra bench flags]
+# N-GPU bench (NCCL).  usage: gpu_ngpu_bench.sh N [steps] [extra bench flags]
 set -u
 N=${1:-2}; S=${2:-10}; shift; shift
 mkdir -p gpurun_out
